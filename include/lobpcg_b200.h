@@ -1,0 +1,120 @@
+/* include/lobpcg_b200.h — C ABI of liblobpcg_b200.so (plain pointers and sizes, no C++/torch types).
+ *
+ * Three layers, all `extern "C"`:
+ *
+ *  (1) reference entry points  <p>_lobpcg / <p>_ilobpcg, p in {s,d,c,z}  — declared in lobpcg.h, replace
+ *      reference src/core/lobpcg_impl.inc:60 and src/core/ilobpcg_impl.inc:54 (host state struct in, host
+ *      results out).
+ *  (2) built-in device operators returned as ordinary LinearOperator_<p>_t* (reference
+ *      include/lobpcg/linop.h:20-26); the solver recognises them by a tag in ctx->data and applies them to
+ *      whole blocks on the GPU (replaces the per-column loop of src/gram/gram_impl.inc:29-33).  Their
+ *      `matvec` member also works on host vectors, so reference-style callers can still apply them.
+ *      Any other operator is treated as a host callback and staged through host memory column by column.
+ *  (3) kernel-level entry points on DEVICE pointers (column-major, leading dimension in elements) — what
+ *      a maintainer of the reference would bind from src/gram, src/ortho, src/residual if only single
+ *      calls are to be offloaded; also what tests/ and bench.py drive.
+ *
+ * Scalars: s=float, d=double, c=float _Complex, z=double _Complex (interleaved re,im).  Complex and
+ * real data are passed as `void*` / `const void*`; real-valued side arrays (eigenvalues, norms,
+ * diagonals) are float for s,c and double for d,z.  All functions return 0 on success, non-zero after
+ * printing a message to stderr; nothing throws or aborts.
+ */
+#ifndef LOBPCG_B200_H
+#define LOBPCG_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lb2_ctx lb2_ctx;       /* one device + one stream + scratch */
+typedef struct lb2_solver lb2_solver; /* resumable solver instance (device resident) */
+
+/* ---- context ------------------------------------------------------------------------------------- */
+lb2_ctx *lb2_ctx_create(int device, void *cuda_stream /* cudaStream_t or NULL => own stream */);
+void lb2_ctx_destroy(lb2_ctx *ctx);
+int lb2_ctx_sync(lb2_ctx *ctx);
+int lb2_ctx_set_option(lb2_ctx *ctx, const char *key, int value);
+unsigned long long lb2_ctx_launches(lb2_ctx *ctx); /* kernels launched so far through this context */
+lb2_ctx *lb2_default_ctx(void);                    /* lazily created context on the current device */
+
+/* device memory for FFI callers that have no CUDA runtime of their own */
+void *lb2_malloc(size_t bytes);
+void lb2_free(void *dptr);
+void *lb2_malloc_host(size_t bytes); /* pinned */
+void lb2_free_host(void *hptr);
+int lb2_memcpy_h2d(lb2_ctx *ctx, void *dst, const void *src, size_t bytes);
+int lb2_memcpy_d2h(lb2_ctx *ctx, void *dst, const void *src, size_t bytes);
+int lb2_memset(lb2_ctx *ctx, void *dst, int byte, size_t bytes);
+
+/* ---- (2) built-in operators: host arrays in, device-resident operator out -------------------------- */
+/* Dirichlet stencil on a gx*gy*gz grid (x fastest): y_i = (cdiag + potential_i) x_i + coff * sum(nbrs).
+ * gy = gz = 1 gives 1-D, gz = 1 gives 2-D.  potential may be NULL. */
+void *lb2_op_stencil(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff,
+                     const void *potential_host);
+/* CSR with int64 row pointers and int32 column indices (host arrays are copied). */
+void *lb2_op_csr(char prefix, int64_t n, const int64_t *rowptr_host, const int32_t *col_host,
+                 const void *val_host);
+/* real diagonal (mass matrix B, Jacobi preconditioner T) */
+void *lb2_op_diag(char prefix, int64_t n, const void *diag_host);
+/* BdG-style pencil block A = [[K+shift, d],[conj d, K+shift]] with K the stencil above (config C4) */
+void *lb2_op_bdg(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff, double shift,
+                 double d_re, double d_im);
+void lb2_op_destroy(void *linop);
+/* Y = Op X on device block vectors (n x nc) */
+int lb2_op_apply(lb2_ctx *ctx, const void *linop, char prefix, int nc, const void *X, int64_t ldx, void *Y,
+                 int64_t ldy);
+
+/* ---- (1b) resumable solver on top of the same state struct --------------------------------------- */
+/* alg is a <prefix>_lobpcg_t*.  create+init = everything before the while loop of lobpcg_impl.inc:130;
+ * step(k) = at most k passes of that loop (stops early on convergence, returns passes done or <0);
+ * finish = download X, eigVals, resNorm, converged, iter into alg. */
+lb2_solver *lb2_solver_create(lb2_ctx *ctx, char prefix, void *alg, int indefinite);
+int lb2_solver_init(lb2_solver *s);
+int lb2_solver_step(lb2_solver *s, int max_steps);
+int lb2_solver_finish(lb2_solver *s);
+void lb2_solver_destroy(lb2_solver *s);
+/* X0 generated on the device from the portable counter-based generator instead of uploading alg->S */
+int lb2_solver_set_device_x0(lb2_solver *s, uint64_t seed);
+/* statistics: per-phase device milliseconds accumulated by step(); names via lb2_solver_stat_name */
+int lb2_solver_num_stats(void);
+const char *lb2_solver_stat_name(int i);
+double lb2_solver_stat(lb2_solver *s, int i);
+int lb2_solver_state(lb2_solver *s, uint64_t *iter, uint64_t *converged, int *use_ortho);
+
+/* ---- (3) kernels on device pointers -------------------------------------------------------------- */
+#define LB2_DECLARE_KERNELS(P)                                                                            \
+  /* G(ma x mb) = A^H B; upper!=0: Hermitian product (ma==mb), upper tiles computed, result mirrored */    \
+  int lb2_##P##_gram(lb2_ctx *ctx, int64_t n, int ma, int mb, const void *A, int64_t lda, const void *B,   \
+                     int64_t ldb, void *G, int ldg, int upper);                                            \
+  /* Out(n x nb) = alpha S(n x kd) C(kd x nb) + beta Out; alpha,beta point to one scalar each */           \
+  int lb2_##P##_tall_nn(lb2_ctx *ctx, int64_t n, int kd, int nb, const void *alpha, const void *S,         \
+                        int64_t lds, const void *C, int ldc, const void *beta, void *Out, int64_t ldo);    \
+  /* W = AX - BX diag(lambda) (W may be NULL), sumsq[j] = ||W[:,j]||^2 (may be NULL); lambda, sumsq real */ \
+  int lb2_##P##_residual(lb2_ctx *ctx, int64_t n, int nc, const void *AX, int64_t ldax, const void *BX,    \
+                         int64_t ldbx, const void *lambda, void *W, int64_t ldw, void *sumsq);             \
+  int lb2_##P##_col_sumsq(lb2_ctx *ctx, int64_t n, int nc, const void *X, int64_t ldx, void *sumsq);       \
+  /* X[i,j] = uniform[-.5,.5) from splitmix64(seed, j*n_global + row0 + i) */                              \
+  int lb2_##P##_fill_uniform(lb2_ctx *ctx, int64_t n, int nc, void *X, int64_t ldx, uint64_t seed,         \
+                             int64_t n_global, int64_t row0);                                              \
+  int lb2_##P##_spmm_stencil(lb2_ctx *ctx, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff,  \
+                             const void *potential, int nc, const void *X, int64_t ldx, void *Y,           \
+                             int64_t ldy);                                                                 \
+  int lb2_##P##_spmm_csr(lb2_ctx *ctx, int64_t n, const int64_t *rowptr, const int32_t *col,               \
+                         const void *val, int nc, const void *X, int64_t ldx, void *Y, int64_t ldy);       \
+  int lb2_##P##_spmm_diag(lb2_ctx *ctx, int64_t n, const void *diag, int nc, const void *X, int64_t ldx,   \
+                          void *Y, int64_t ldy);
+
+LB2_DECLARE_KERNELS(s)
+LB2_DECLARE_KERNELS(d)
+LB2_DECLARE_KERNELS(c)
+LB2_DECLARE_KERNELS(z)
+
+const char *lb2_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOBPCG_B200_H */

@@ -1,0 +1,475 @@
+"""ctypes binding of liblobpcg_b200.so — the host-side mirror of the reference's solver interface.
+
+Everything here goes through the C ABI declared in include/lobpcg_b200.h / include/lobpcg.h; there is no
+Python or CPU compute path.  Importing works without a GPU (symbols can be inspected), but any call that
+needs a device fails loudly.
+
+Reference interface being mirrored: ``<p>_lobpcg_t`` / ``lobpcg(alg)`` / ``ilobpcg(alg)``
+(reference lobpcg.h:10-92, 590-686) and ``LinearOperator_<p>_t`` (include/lobpcg/linop.h:7-26).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "_lib" / "liblobpcg_b200.so"
+
+PREFIX = {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
+          np.dtype(np.complex128): "z"}
+DTYPE = {v: k for k, v in PREFIX.items()}
+REAL = {"s": np.dtype(np.float32), "d": np.dtype(np.float64), "c": np.dtype(np.float32), "z": np.dtype(np.float64)}
+
+
+class LobpcgB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; no fallback of any kind exists."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise LobpcgB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m lobpcg_b200.build` (needs nvcc); "
+                "lobpcg_b200 has no CPU fallback")
+        _lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    vp, i64, i32, u64, dbl, ci = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_double, C.c_int
+    L.lb2_version.restype = C.c_char_p
+    L.lb2_ctx_create.restype = vp
+    L.lb2_ctx_create.argtypes = [ci, vp]
+    L.lb2_ctx_destroy.argtypes = [vp]
+    L.lb2_ctx_sync.argtypes = [vp]
+    L.lb2_ctx_set_option.argtypes = [vp, C.c_char_p, ci]
+    L.lb2_ctx_launches.restype = C.c_ulonglong
+    L.lb2_ctx_launches.argtypes = [vp]
+    L.lb2_default_ctx.restype = vp
+    L.lb2_malloc.restype = vp
+    L.lb2_malloc.argtypes = [C.c_size_t]
+    L.lb2_free.argtypes = [vp]
+    L.lb2_malloc_host.restype = vp
+    L.lb2_malloc_host.argtypes = [C.c_size_t]
+    L.lb2_free_host.argtypes = [vp]
+    L.lb2_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    L.lb2_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    L.lb2_memset.argtypes = [vp, vp, ci, C.c_size_t]
+    L.lb2_op_stencil.restype = vp
+    L.lb2_op_stencil.argtypes = [C.c_char, i64, i64, i64, dbl, dbl, vp]
+    L.lb2_op_csr.restype = vp
+    L.lb2_op_csr.argtypes = [C.c_char, i64, vp, vp, vp]
+    L.lb2_op_diag.restype = vp
+    L.lb2_op_diag.argtypes = [C.c_char, i64, vp]
+    L.lb2_op_bdg.restype = vp
+    L.lb2_op_bdg.argtypes = [C.c_char, i64, i64, i64, dbl, dbl, dbl, dbl, dbl]
+    L.lb2_op_destroy.argtypes = [vp]
+    L.lb2_op_apply.argtypes = [vp, vp, C.c_char, ci, vp, i64, vp, i64]
+    L.lb2_solver_create.restype = vp
+    L.lb2_solver_create.argtypes = [vp, C.c_char, vp, ci]
+    for f in ("init", "finish"):
+        getattr(L, f"lb2_solver_{f}").argtypes = [vp]
+    L.lb2_solver_step.argtypes = [vp, ci]
+    L.lb2_solver_destroy.argtypes = [vp]
+    L.lb2_solver_set_device_x0.argtypes = [vp, u64]
+    L.lb2_solver_stat_name.restype = C.c_char_p
+    L.lb2_solver_stat_name.argtypes = [ci]
+    L.lb2_solver_stat.restype = dbl
+    L.lb2_solver_stat.argtypes = [vp, ci]
+    L.lb2_solver_state.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(ci)]
+    L.lb2_comm_unique_id.argtypes = [vp, C.c_char_p]
+    L.lb2_ctx_attach_comm.argtypes = [vp, ci, ci, vp, C.c_char_p]
+    L.lb2_ctx_detach_comm.argtypes = [vp]
+    L.lb2_comm_allreduce.argtypes = [vp, vp, C.c_size_t, ci]
+    L.lb2_ipc_get_handle.argtypes = [vp, vp]
+    L.lb2_ipc_open_handle.restype = vp
+    L.lb2_ipc_open_handle.argtypes = [vp]
+    L.lb2_ipc_close_handle.argtypes = [vp]
+    for p in "sdcz":
+        getattr(L, f"lb2_{p}_state_alloc").restype = vp
+        getattr(L, f"lb2_{p}_state_alloc").argtypes = [u64, u64, u64, ci]
+        getattr(L, f"lb2_{p}_state_free").argtypes = [vp]
+        getattr(L, f"{p}_lobpcg").argtypes = [vp]
+        getattr(L, f"{p}_ilobpcg").argtypes = [vp]
+        getattr(L, f"lb2_{p}_gram").argtypes = [vp, i64, ci, ci, vp, i64, vp, i64, vp, ci, ci]
+        getattr(L, f"lb2_{p}_tall_nn").argtypes = [vp, i64, ci, ci, vp, vp, i64, vp, ci, vp, vp, i64]
+        getattr(L, f"lb2_{p}_residual").argtypes = [vp, i64, ci, vp, i64, vp, i64, vp, vp, i64, vp]
+        getattr(L, f"lb2_{p}_col_sumsq").argtypes = [vp, i64, ci, vp, i64, vp]
+        getattr(L, f"lb2_{p}_fill_uniform").argtypes = [vp, i64, ci, vp, i64, u64, i64, i64]
+        getattr(L, f"lb2_{p}_spmm_stencil").argtypes = [vp, i64, i64, i64, dbl, dbl, vp, ci, vp, i64, vp, i64]
+        getattr(L, f"lb2_{p}_spmm_csr").argtypes = [vp, i64, vp, vp, vp, ci, vp, i64, vp, i64]
+        getattr(L, f"lb2_{p}_spmm_diag").argtypes = [vp, i64, vp, ci, vp, i64, vp, i64]
+
+
+def _ck(rc, what):
+    if rc != 0:
+        raise LobpcgB200Error(f"{what} failed with code {rc}")
+
+
+# --------------------------------------------------------------------------------------------------- context
+class Context:
+    def __init__(self, device: int = -1, stream: int | None = None):
+        self.h = lib().lb2_ctx_create(device, stream)
+        if not self.h:
+            raise LobpcgB200Error("lb2_ctx_create failed (no CUDA device?)")
+
+    def sync(self):
+        _ck(lib().lb2_ctx_sync(self.h), "lb2_ctx_sync")
+
+    def set_option(self, key: str, value: int):
+        _ck(lib().lb2_ctx_set_option(self.h, key.encode(), int(value)), f"set_option({key})")
+
+    @property
+    def launches(self) -> int:
+        return int(lib().lb2_ctx_launches(self.h))
+
+    def close(self):
+        if self.h:
+            lib().lb2_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceArray:
+    """Column-major device block (n x nc, leading dimension ld >= n) owned through lb2_malloc."""
+
+    def __init__(self, shape, dtype, ld=None):
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = np.dtype(dtype)
+        n = self.shape[0]
+        nc = self.shape[1] if len(self.shape) > 1 else 1
+        self.ld = int(ld) if ld else max(n, 1)
+        self.nbytes = self.ld * max(nc, 1) * self.dtype.itemsize
+        self.ptr = lib().lb2_malloc(self.nbytes)
+        if not self.ptr:
+            raise LobpcgB200Error(f"device allocation of {self.nbytes} bytes failed")
+
+    @classmethod
+    def from_numpy(cls, ctx: Context, a: np.ndarray, ld=None):
+        a = np.asarray(a)
+        d = cls(a.shape, a.dtype, ld)
+        d.upload(ctx, a)
+        return d
+
+    def upload(self, ctx: Context, a: np.ndarray):
+        a = np.asarray(a, dtype=self.dtype)
+        n = self.shape[0]
+        nc = self.shape[1] if len(self.shape) > 1 else 1
+        buf = np.zeros((self.ld, nc), dtype=self.dtype, order="F")
+        buf[:n, :] = a.reshape((n, nc), order="F") if a.ndim == 1 else a
+        _ck(lib().lb2_memcpy_h2d(ctx.h, self.ptr, buf.ctypes.data, buf.nbytes), "h2d")
+
+    def numpy(self, ctx: Context) -> np.ndarray:
+        n = self.shape[0]
+        nc = self.shape[1] if len(self.shape) > 1 else 1
+        buf = np.empty((self.ld, nc), dtype=self.dtype, order="F")
+        _ck(lib().lb2_memcpy_d2h(ctx.h, buf.ctypes.data, self.ptr, buf.nbytes), "d2h")
+        out = np.asfortranarray(buf[:n, :])
+        return out[:, 0].copy() if len(self.shape) == 1 else out
+
+    def zero(self, ctx: Context):
+        _ck(lib().lb2_memset(ctx.h, self.ptr, 0, self.nbytes), "memset")
+
+    def free(self):
+        if self.ptr:
+            lib().lb2_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _scalar(dtype, v):
+    return np.array([v], dtype=dtype)
+
+
+# --------------------------------------------------------------------------------------------------- kernels
+def gram(ctx, A: DeviceArray, B: DeviceArray, upper=False) -> DeviceArray:
+    p = PREFIX[A.dtype]
+    n, ma = A.shape
+    mb = B.shape[1]
+    G = DeviceArray((ma, mb), A.dtype)
+    _ck(getattr(lib(), f"lb2_{p}_gram")(ctx.h, n, ma, mb, A.ptr, A.ld, B.ptr, B.ld, G.ptr, G.ld, int(upper)), "gram")
+    return G
+
+
+def tall_nn(ctx, S: DeviceArray, Cm: DeviceArray, Out: DeviceArray, alpha=1.0, beta=0.0):
+    p = PREFIX[S.dtype]
+    n, kd = S.shape
+    nb = Cm.shape[1]
+    a, b = _scalar(S.dtype, alpha), _scalar(S.dtype, beta)
+    _ck(getattr(lib(), f"lb2_{p}_tall_nn")(ctx.h, n, kd, nb, a.ctypes.data, S.ptr, S.ld, Cm.ptr, Cm.ld,
+                                           b.ctypes.data, Out.ptr, Out.ld), "tall_nn")
+    return Out
+
+
+def residual(ctx, AX: DeviceArray, BX: DeviceArray, lam: DeviceArray, write=True, norms=True):
+    p = PREFIX[AX.dtype]
+    n, nc = AX.shape
+    W = DeviceArray((n, nc), AX.dtype) if write else None
+    ss = DeviceArray((nc,), REAL[p]) if norms else None
+    _ck(getattr(lib(), f"lb2_{p}_residual")(ctx.h, n, nc, AX.ptr, AX.ld, BX.ptr, BX.ld, lam.ptr,
+                                            W.ptr if W else None, W.ld if W else 0, ss.ptr if ss else None), "residual")
+    return W, ss
+
+
+def col_sumsq(ctx, X: DeviceArray) -> DeviceArray:
+    p = PREFIX[X.dtype]
+    n, nc = X.shape
+    ss = DeviceArray((nc,), REAL[p])
+    _ck(getattr(lib(), f"lb2_{p}_col_sumsq")(ctx.h, n, nc, X.ptr, X.ld, ss.ptr), "col_sumsq")
+    return ss
+
+
+def fill_uniform(ctx, n, nc, dtype, seed, n_global=None, row0=0, ld=None) -> DeviceArray:
+    p = PREFIX[np.dtype(dtype)]
+    X = DeviceArray((n, nc), dtype, ld)
+    _ck(getattr(lib(), f"lb2_{p}_fill_uniform")(ctx.h, n, nc, X.ptr, X.ld, seed, n_global or n, row0), "fill_uniform")
+    return X
+
+
+# --------------------------------------------------------------------------------------------------- operators
+class LinOpStruct(C.Structure):
+    """LinearOperator_<p>_t (reference include/lobpcg/linop.h:20-26)."""
+    _fields_ = [("rows", C.c_uint64), ("cols", C.c_uint64), ("matvec", C.c_void_p), ("cleanup", C.c_void_p),
+                ("ctx", C.c_void_p)]
+
+
+class LinOpCtx(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_size", C.c_size_t)]
+
+
+class LinOp:
+    """Handle to a LinearOperator_<p>_t*.  Built-in operators live on the device."""
+
+    def __init__(self, handle, prefix, n, builtin=True, keep=()):
+        if not handle:
+            raise LobpcgB200Error("operator construction failed")
+        self.handle, self.prefix, self.n, self.builtin, self._keep = handle, prefix, n, builtin, keep
+
+    def apply(self, ctx: Context, X: DeviceArray, Y: DeviceArray | None = None) -> DeviceArray:
+        nc = X.shape[1] if len(X.shape) > 1 else 1
+        if Y is None:
+            Y = DeviceArray(X.shape, X.dtype, X.ld)
+        _ck(lib().lb2_op_apply(ctx.h, self.handle, self.prefix.encode(), nc, X.ptr, X.ld, Y.ptr, Y.ld), "op_apply")
+        return Y
+
+    def close(self):
+        if self.handle and self.builtin:
+            lib().lb2_op_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def stencil_op(grid, dtype, cdiag=None, coff=-1.0, potential=None) -> LinOp:
+    p = PREFIX[np.dtype(dtype)]
+    g = tuple(int(v) for v in grid) + (1,) * (3 - len(grid))
+    cdiag = 2.0 * len(grid) if cdiag is None else cdiag
+    pot = None if potential is None else np.ascontiguousarray(potential, dtype=REAL[p])
+    h = lib().lb2_op_stencil(p.encode(), g[0], g[1], g[2], cdiag, coff, pot.ctypes.data if pot is not None else None)
+    return LinOp(h, p, g[0] * g[1] * g[2])
+
+
+def csr_op(rowptr, col, val) -> LinOp:
+    val = np.ascontiguousarray(val)
+    p = PREFIX[val.dtype]
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    n = len(rowptr) - 1
+    h = lib().lb2_op_csr(p.encode(), n, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data)
+    return LinOp(h, p, n)
+
+
+def diag_op(d, dtype) -> LinOp:
+    p = PREFIX[np.dtype(dtype)]
+    d = np.ascontiguousarray(d, dtype=REAL[p])
+    return LinOp(lib().lb2_op_diag(p.encode(), len(d), d.ctypes.data), p, len(d))
+
+
+def bdg_op(grid, dtype, shift, d, cdiag=None, coff=-1.0) -> LinOp:
+    p = PREFIX[np.dtype(dtype)]
+    g = tuple(int(v) for v in grid) + (1,) * (3 - len(grid))
+    cdiag = 2.0 * len(grid) if cdiag is None else cdiag
+    d = complex(d)
+    return LinOp(lib().lb2_op_bdg(p.encode(), g[0], g[1], g[2], cdiag, coff, shift, d.real, d.imag), p,
+                 2 * g[0] * g[1] * g[2])
+
+
+def host_op(n, dtype, fn) -> LinOp:
+    """Foreign operator: a host callback y = fn(x) on single vectors, exactly the reference's
+    matvec_func_<p>_t (linop.h:15-17).  The solver stages columns through host memory for these."""
+    dtype = np.dtype(dtype)
+    p = PREFIX[dtype]
+    MV = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
+
+    def _mv(op, x, y):
+        xv = np.ctypeslib.as_array(C.cast(x, C.POINTER(C.c_byte)), shape=(n * dtype.itemsize,)).view(dtype)
+        yv = np.ctypeslib.as_array(C.cast(y, C.POINTER(C.c_byte)), shape=(n * dtype.itemsize,)).view(dtype)
+        yv[:] = fn(xv)
+
+    cb = MV(_mv)
+    ctx = LinOpCtx(None, 0)
+    st = LinOpStruct(n, n, C.cast(cb, C.c_void_p), None, C.cast(C.pointer(ctx), C.c_void_p))
+    return LinOp(C.addressof(st), p, n, builtin=False, keep=(cb, ctx, st))
+
+
+# --------------------------------------------------------------------------------------------------- solver
+def _state_struct(prefix):
+    rt = C.c_float if prefix in "sc" else C.c_double
+    vp = C.c_void_p
+
+    class State(C.Structure):
+        _fields_ = [("S", vp), ("Cx", vp), ("Cp", vp), ("AX", vp), ("AS", vp), ("BS", vp), ("eigVals", vp),
+                    ("resNorm", vp), ("signature", vp), ("wrk1", vp), ("wrk2", vp), ("wrk3", vp), ("wrk4", vp),
+                    ("rr_D", vp), ("rr_eigvals", vp), ("rr_tau", vp), ("rr_VR", vp), ("rr_sig", vp),
+                    ("rr_indices", vp), ("rr_ggev", vp), ("implicit_product_update", C.c_int8),
+                    ("verbosity", C.c_int8), ("iter", C.c_uint64), ("nev", C.c_uint64), ("converged", C.c_uint64),
+                    ("size", C.c_uint64), ("sizeSub", C.c_uint64), ("maxIter", C.c_uint64), ("tol", rt),
+                    ("A", vp), ("B", vp), ("T", vp)]
+
+    return State
+
+
+class SolverState:
+    """Owns a ``<p>_lobpcg_t`` allocated by lb2_<p>_state_alloc (host buffers)."""
+
+    def __init__(self, dtype, n, nev, k, indefinite=False):
+        self.dtype = np.dtype(dtype)
+        self.prefix = PREFIX[self.dtype]
+        self.n, self.nev, self.k, self.indefinite = int(n), int(nev), int(k), bool(indefinite)
+        self.ptr = getattr(lib(), f"lb2_{self.prefix}_state_alloc")(self.n, self.nev, self.k, int(indefinite))
+        if not self.ptr:
+            raise LobpcgB200Error("state allocation failed")
+        self.st = _state_struct(self.prefix).from_address(self.ptr)
+
+    def X(self) -> np.ndarray:
+        """View of alg->S[0 : n*k) as an (n,k) Fortran array."""
+        buf = (C.c_byte * (self.n * self.k * self.dtype.itemsize)).from_address(self.st.S)
+        return np.frombuffer(buf, dtype=self.dtype).reshape((self.n, self.k), order="F")
+
+    def eigvals(self):
+        buf = (C.c_byte * (self.k * REAL[self.prefix].itemsize)).from_address(self.st.eigVals)
+        return np.frombuffer(buf, dtype=REAL[self.prefix]).copy()
+
+    def resnorm(self):
+        buf = (C.c_byte * (self.k * REAL[self.prefix].itemsize)).from_address(self.st.resNorm)
+        return np.frombuffer(buf, dtype=REAL[self.prefix]).copy()
+
+    def signature(self):
+        if not self.st.signature:
+            return None
+        buf = (C.c_byte * (3 * self.k)).from_address(self.st.signature)
+        return np.frombuffer(buf, dtype=np.int8).copy()
+
+    def free(self):
+        if self.ptr:
+            getattr(lib(), f"lb2_{self.prefix}_state_free")(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _setup(A, X0, n, k, nev, dtype, tol, max_iter, B, T, indefinite, verbosity):
+    st = SolverState(dtype, n, nev, k, indefinite)
+    st.st.A = A.handle
+    st.st.B = B.handle if B is not None else None
+    st.st.T = T.handle if T is not None else None
+    st.st.maxIter = int(max_iter)
+    st.st.tol = float(tol)
+    st.st.verbosity = int(verbosity)
+    if X0 is not None:
+        st.X()[:, :] = X0
+    return st
+
+
+def lobpcg(A: LinOp, X0: np.ndarray, nev: int, tol: float, max_iter: int, B: LinOp | None = None,
+           T: LinOp | None = None, indefinite: bool = False, verbosity: int = 0):
+    """Drop-in call path: fill a ``<p>_lobpcg_t`` with HOST buffers and call ``<p>_lobpcg`` / ``<p>_ilobpcg``."""
+    X0 = np.asarray(X0)
+    n, k = X0.shape
+    st = _setup(A, X0, n, k, nev, X0.dtype, tol, max_iter, B, T, indefinite, verbosity)
+    fn = getattr(lib(), f"{st.prefix}_{'i' if indefinite else ''}lobpcg")
+    fn(st.ptr)
+    out = dict(eig=st.eigvals(), res=st.resnorm(), X=np.array(st.X(), order="F", copy=True),
+               iter=int(st.st.iter), converged=int(st.st.converged), sig=st.signature())
+    st.free()
+    return out
+
+
+class Solver:
+    """Resumable device-resident solver (lb2_solver_*): init / step(k) / finish on one state struct."""
+
+    def __init__(self, ctx: Context, A: LinOp, n: int, k: int, nev: int, dtype, tol: float, max_iter: int,
+                 B: LinOp | None = None, T: LinOp | None = None, X0: np.ndarray | None = None,
+                 device_seed: int | None = None, indefinite: bool = False, verbosity: int = 0):
+        self.ctx = ctx
+        self.ops = (A, B, T)
+        self.state_ = _setup(A, X0, n, k, nev, dtype, tol, max_iter, B, T, indefinite, verbosity)
+        self.h = lib().lb2_solver_create(ctx.h, self.state_.prefix.encode(), self.state_.ptr, int(indefinite))
+        if not self.h:
+            raise LobpcgB200Error("lb2_solver_create failed")
+        if device_seed is not None:
+            lib().lb2_solver_set_device_x0(self.h, int(device_seed))
+
+    def init(self):
+        _ck(lib().lb2_solver_init(self.h), "lb2_solver_init")
+
+    def step(self, max_steps: int) -> int:
+        rc = lib().lb2_solver_step(self.h, int(max_steps))
+        if rc < 0:
+            raise LobpcgB200Error(f"lb2_solver_step failed with code {rc}")
+        return rc
+
+    def finish(self):
+        _ck(lib().lb2_solver_finish(self.h), "lb2_solver_finish")
+        s = self.state_
+        return dict(eig=s.eigvals(), res=s.resnorm(), X=s.X(), iter=int(s.st.iter), converged=int(s.st.converged),
+                    sig=s.signature())
+
+    def progress(self):
+        it, cv, uo = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        lib().lb2_solver_state(self.h, C.byref(it), C.byref(cv), C.byref(uo))
+        return dict(iter=it.value, converged=cv.value, use_ortho=uo.value)
+
+    def stats(self) -> dict:
+        L = lib()
+        return {L.lb2_solver_stat_name(i).decode(): L.lb2_solver_stat(self.h, i) for i in range(L.lb2_solver_num_stats())}
+
+    def close(self):
+        if self.h:
+            lib().lb2_solver_destroy(self.h)
+            self.h = None
+        if self.state_:
+            self.state_.free()
+            self.state_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,421 @@
+// lobpcg_b200/csrc/capi.cu — the C ABI declared in include/lobpcg_b200.h and include/lobpcg.h.
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "common.cuh"
+#include "context.h"
+#include "kernels.h"
+#include "solver.h"
+#include "../../include/lobpcg_b200.h"
+
+using namespace lb2;
+
+namespace lb2 {
+void* ctx_scratch(lb2_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return ctx->ws;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
+  if (ctx->ws) cudaFree(ctx->ws);
+  ctx->ws = nullptr;
+  ctx->ws_bytes = 0;
+  const size_t want = bytes + (bytes >> 1) + (1 << 20);
+  cudaError_t e = cudaMalloc(&ctx->ws, want);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "lobpcg_b200: cannot allocate %zu bytes of scratch (%s)\n", want, cudaGetErrorString(e));
+    return nullptr;
+  }
+  ctx->ws_bytes = want;
+  return ctx->ws;
+}
+}  // namespace lb2
+
+extern "C" {
+
+const char* lb2_version(void) { return "lobpcg_b200 0.1 (sm_100a)"; }
+
+lb2_ctx* lb2_ctx_create(int device, void* cuda_stream) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "lobpcg_b200: no CUDA device available — this library has no CPU fallback\n");
+    return nullptr;
+  }
+  if (device < 0) cudaGetDevice(&device);
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  lb2_ctx* c = new lb2_ctx();
+  c->device = device;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (cuda_stream) {
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete c;
+      return nullptr;
+    }
+    c->own_stream = true;
+  }
+  return c;
+}
+
+void lb2_ctx_destroy(lb2_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->cublas) cublasDestroy(c->cublas);
+  if (c->cusolver) cusolverDnDestroy(c->cusolver);
+  if (c->ws) cudaFree(c->ws);
+  if (c->solver_ws) cudaFree(c->solver_ws);
+  if (c->solver_hws) free(c->solver_hws);
+  if (c->dev_info) cudaFree(c->dev_info);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int lb2_ctx_sync(lb2_ctx* c) {
+  LB2_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
+  if (!c || !key) return -1;
+  if (!strcmp(key, "gram_tile")) c->gram_tile = value;
+  else if (!strcmp(key, "nn_tile")) c->nn_tile = value;
+  else if (!strcmp(key, "force_simt")) c->force_simt = value;
+  else if (!strcmp(key, "spmm_cols")) c->spmm_cols = value;
+  else return -1;
+  return 0;
+}
+
+unsigned long long lb2_ctx_launches(lb2_ctx* c) { return c ? c->launches : 0ULL; }
+
+static std::mutex g_mu;
+static std::map<int, lb2_ctx*> g_default;
+lb2_ctx* lb2_default_ctx(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    fprintf(stderr, "lobpcg_b200: no CUDA device available — this library has no CPU fallback\n");
+    return nullptr;
+  }
+  auto it = g_default.find(dev);
+  if (it != g_default.end()) return it->second;
+  lb2_ctx* c = lb2_ctx_create(dev, nullptr);
+  g_default[dev] = c;
+  return c;
+}
+
+void* lb2_malloc(size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "lobpcg_b200: cudaMalloc(%zu) failed: %s\n", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+void lb2_free(void* p) { if (p) cudaFree(p); }
+void* lb2_malloc_host(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void lb2_free_host(void* p) { if (p) cudaFreeHost(p); }
+int lb2_memcpy_h2d(lb2_ctx* c, void* dst, const void* src, size_t bytes) {
+  LB2_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  LB2_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int lb2_memcpy_d2h(lb2_ctx* c, void* dst, const void* src, size_t bytes) {
+  LB2_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  LB2_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int lb2_memset(lb2_ctx* c, void* dst, int byte, size_t bytes) {
+  LB2_CUDA_OK(cudaMemsetAsync(dst, byte, bytes, c->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// built-in operators
+// ---------------------------------------------------------------------------------------------------
+static size_t scalar_size(char p) { return p == 's' ? 4 : (p == 'd' || p == 'c') ? 8 : 16; }
+static size_t real_size(char p) { return (p == 's' || p == 'c') ? 4 : 8; }
+
+// host-pointer matvec so that reference-style callers (linop_apply on host vectors) keep working
+static void builtin_host_matvec(const LinOpRaw* op, void* x, void* y) {
+  const BuiltinOp* b = builtin_of(op);
+  if (!b) return;
+  lb2_ctx* c = lb2_default_ctx();
+  if (!c) return;
+  const size_t bytes = scalar_size(b->prefix) * (size_t)b->n;
+  void *dx = lb2_malloc(bytes), *dy = lb2_malloc(bytes);
+  if (!dx || !dy) { lb2_free(dx); lb2_free(dy); return; }
+  lb2_memcpy_h2d(c, dx, x, bytes);
+  lb2_op_apply(c, op, b->prefix, 1, dx, b->n, dy, b->n);
+  lb2_memcpy_d2h(c, y, dy, bytes);
+  lb2_free(dx);
+  lb2_free(dy);
+}
+
+static void builtin_cleanup(LinOpCtxRaw* ctx) {
+  if (!ctx) return;
+  BuiltinOp* b = (BuiltinOp*)ctx->data;
+  if (b && b->magic == kOpMagic) {
+    if (b->potential) cudaFree(b->potential);
+    if (b->rowptr) cudaFree(b->rowptr);
+    if (b->col) cudaFree(b->col);
+    if (b->val) cudaFree(b->val);
+    if (b->diag) cudaFree(b->diag);
+    b->magic = 0;
+    free(b);
+  }
+  free(ctx);
+}
+
+static LinOpRaw* wrap_builtin(BuiltinOp* b) {
+  LinOpCtxRaw* lc = (LinOpCtxRaw*)calloc(1, sizeof(LinOpCtxRaw));
+  LinOpRaw* op = (LinOpRaw*)calloc(1, sizeof(LinOpRaw));
+  lc->data = b;
+  lc->data_size = sizeof(BuiltinOp);
+  op->rows = op->cols = (uint64_t)b->n_global;
+  op->matvec = builtin_host_matvec;
+  op->cleanup = builtin_cleanup;
+  op->ctx = lc;
+  b->self = op;
+  return op;
+}
+
+static BuiltinOp* new_builtin(int kind, char prefix, int64_t n) {
+  BuiltinOp* b = (BuiltinOp*)calloc(1, sizeof(BuiltinOp));
+  b->magic = kOpMagic;
+  b->kind = kind;
+  b->prefix = prefix;
+  cudaGetDevice(&b->device);
+  b->n = b->n_global = n;
+  return b;
+}
+
+static void* upload(const void* host, size_t bytes) {
+  if (!host || !bytes) return nullptr;
+  void* d = lb2_malloc(bytes);
+  if (!d) return nullptr;
+  if (cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(d);
+    return nullptr;
+  }
+  return d;
+}
+
+static bool valid_prefix(char p) { return p == 's' || p == 'd' || p == 'c' || p == 'z'; }
+
+void* lb2_op_stencil(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff,
+                     const void* potential_host) {
+  if (!valid_prefix(prefix) || gx < 1 || gy < 1 || gz < 1) return nullptr;
+  if (!lb2_default_ctx()) return nullptr;
+  BuiltinOp* b = new_builtin(OP_STENCIL, prefix, gx * gy * gz);
+  b->gx = gx; b->gy = gy; b->gz = gz; b->cdiag = cdiag; b->coff = coff;
+  if (potential_host) {
+    b->potential = upload(potential_host, real_size(prefix) * (size_t)b->n);
+    if (!b->potential) { free(b); return nullptr; }
+  }
+  return wrap_builtin(b);
+}
+
+void* lb2_op_bdg(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff, double shift,
+                 double d_re, double d_im) {
+  if (!valid_prefix(prefix) || gx < 1 || gy < 1 || gz < 1) return nullptr;
+  if (!lb2_default_ctx()) return nullptr;
+  BuiltinOp* b = new_builtin(OP_BDG, prefix, 2 * gx * gy * gz);
+  b->gx = gx; b->gy = gy; b->gz = gz; b->cdiag = cdiag; b->coff = coff; b->shift = shift;
+  b->dre = d_re; b->dim = d_im;
+  return wrap_builtin(b);
+}
+
+void* lb2_op_csr(char prefix, int64_t n, const int64_t* rowptr_host, const int32_t* col_host, const void* val_host) {
+  if (!valid_prefix(prefix) || n < 1 || !rowptr_host || !col_host || !val_host) return nullptr;
+  if (!lb2_default_ctx()) return nullptr;
+  BuiltinOp* b = new_builtin(OP_CSR, prefix, n);
+  b->nnz = rowptr_host[n];
+  b->rowptr = (int64_t*)upload(rowptr_host, sizeof(int64_t) * (size_t)(n + 1));
+  b->col = (int32_t*)upload(col_host, sizeof(int32_t) * (size_t)b->nnz);
+  b->val = upload(val_host, scalar_size(prefix) * (size_t)b->nnz);
+  if (!b->rowptr || !b->col || !b->val) {
+    LinOpCtxRaw* lc = (LinOpCtxRaw*)calloc(1, sizeof(LinOpCtxRaw));
+    lc->data = b;
+    builtin_cleanup(lc);
+    return nullptr;
+  }
+  return wrap_builtin(b);
+}
+
+void* lb2_op_diag(char prefix, int64_t n, const void* diag_host) {
+  if (!valid_prefix(prefix) || n < 1 || !diag_host) return nullptr;
+  if (!lb2_default_ctx()) return nullptr;
+  BuiltinOp* b = new_builtin(OP_DIAG, prefix, n);
+  b->diag = upload(diag_host, real_size(prefix) * (size_t)n);
+  if (!b->diag) { free(b); return nullptr; }
+  return wrap_builtin(b);
+}
+
+void lb2_op_destroy(void* linop) {
+  LinOpRaw* op = (LinOpRaw*)linop;
+  if (!op) return;
+  if (op->cleanup && op->ctx) op->cleanup(op->ctx);
+  free(op);
+}
+
+int lb2_op_apply(lb2_ctx* ctx, const void* linop, char prefix, int nc, const void* X, int64_t ldx, void* Y, int64_t ldy) {
+  const BuiltinOp* b = builtin_of((const LinOpRaw*)linop);
+  if (!b) {
+    fprintf(stderr, "lobpcg_b200: lb2_op_apply needs a built-in device operator\n");
+    return -1;
+  }
+  switch (prefix) {
+    case 's': return apply_builtin<float>(ctx, b, nc, (const float*)X, ldx, (float*)Y, ldy);
+    case 'd': return apply_builtin<double>(ctx, b, nc, (const double*)X, ldx, (double*)Y, ldy);
+    case 'c': return apply_builtin<c32>(ctx, b, nc, (const c32*)X, ldx, (c32*)Y, ldy);
+    case 'z': return apply_builtin<c64>(ctx, b, nc, (const c64*)X, ldx, (c64*)Y, ldy);
+  }
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// solver handle + reference entry points
+// ---------------------------------------------------------------------------------------------------
+struct lb2_solver {
+  SolverBase* impl;
+};
+
+lb2_solver* lb2_solver_create(lb2_ctx* ctx, char prefix, void* alg, int indefinite) {
+  if (!ctx || !alg || !valid_prefix(prefix)) return nullptr;
+  SolverBase* s = make_solver(ctx, prefix, alg, indefinite);
+  if (!s) return nullptr;
+  lb2_solver* h = new lb2_solver();
+  h->impl = s;
+  return h;
+}
+int lb2_solver_init(lb2_solver* s) { return s ? s->impl->init() : -1; }
+int lb2_solver_step(lb2_solver* s, int max_steps) { return s ? s->impl->step(max_steps) : -1; }
+int lb2_solver_finish(lb2_solver* s) { return s ? s->impl->finish() : -1; }
+void lb2_solver_destroy(lb2_solver* s) {
+  if (!s) return;
+  delete s->impl;
+  delete s;
+}
+int lb2_solver_set_device_x0(lb2_solver* s, uint64_t seed) {
+  if (!s) return -1;
+  s->impl->use_device_x0 = true;
+  s->impl->device_seed = seed;
+  return 0;
+}
+int lb2_solver_num_stats(void) { return PH_COUNT; }
+const char* lb2_solver_stat_name(int i) {
+  static const char* names[PH_COUNT] = {"spmm_ms", "gram_ms", "tall_nn_ms", "residual_ms", "small_dense_ms", "comm_ms", "other_ms"};
+  return (i >= 0 && i < PH_COUNT) ? names[i] : "";
+}
+double lb2_solver_stat(lb2_solver* s, int i) { return (s && i >= 0 && i < PH_COUNT) ? s->impl->phase_ms[i] : 0.0; }
+int lb2_solver_state(lb2_solver* s, uint64_t* iter, uint64_t* converged, int* use_ortho) {
+  if (!s) return -1;
+  s->impl->state(iter, converged, use_ortho);
+  return 0;
+}
+
+static void run_solver(char prefix, void* alg, int indefinite) {
+  lb2_ctx* ctx = lb2_default_ctx();
+  if (!ctx) return;
+  lb2_solver* s = lb2_solver_create(ctx, prefix, alg, indefinite);
+  if (!s) return;
+  if (lb2_solver_init(s) == 0) {
+    int rc = lb2_solver_step(s, INT_MAX);
+    if (rc >= 0) lb2_solver_finish(s);
+  }
+  lb2_solver_destroy(s);
+}
+
+#define LB2_ENTRY(P, T)                                                                               \
+  void P##_lobpcg(void* alg) { run_solver(#P[0], alg, 0); }                                            \
+  void P##_ilobpcg(void* alg) { run_solver(#P[0], alg, 1); }                                           \
+  void* lb2_##P##_state_alloc(uint64_t n, uint64_t nev, uint64_t sizeSub, int indefinite) {            \
+    State<T>* a = (State<T>*)calloc(1, sizeof(State<T>));                                              \
+    if (!a) return nullptr;                                                                            \
+    a->size = n; a->nev = nev; a->sizeSub = sizeSub;                                                   \
+    a->S = (T*)calloc((size_t)3 * n * sizeSub, sizeof(T)); /* lazily backed; only X is touched */      \
+    a->eigVals = (real_t<T>*)calloc(sizeSub, sizeof(real_t<T>));                                       \
+    a->resNorm = (real_t<T>*)calloc(sizeSub, sizeof(real_t<T>));                                       \
+    if (indefinite) a->signature = (int8_t*)calloc(3 * sizeSub, 1);                                    \
+    if (!a->S || !a->eigVals || !a->resNorm) {                                                         \
+      fprintf(stderr, "lobpcg_b200: state allocation failed\n");                                       \
+      free(a->S); free(a->eigVals); free(a->resNorm); free(a->signature); free(a);                     \
+      return nullptr;                                                                                  \
+    }                                                                                                  \
+    return a;                                                                                          \
+  }                                                                                                    \
+  void lb2_##P##_state_free(void* alg) {                                                               \
+    State<T>* a = (State<T>*)alg;                                                                      \
+    if (!a) return;                                                                                    \
+    free(a->S); free(a->eigVals); free(a->resNorm); free(a->signature);                                \
+    free(a);                                                                                           \
+  }                                                                                                    \
+  int lb2_##P##_gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const void* A, int64_t lda, const void* B, \
+                     int64_t ldb, void* G, int ldg, int upper) {                                       \
+    return gram<T>(ctx, n, ma, mb, (const T*)A, lda, (const T*)B, ldb, (T*)G, ldg, upper);             \
+  }                                                                                                    \
+  int lb2_##P##_tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, const void* alpha, const void* S,     \
+                        int64_t lds, const void* C, int ldc, const void* beta, void* Out, int64_t ldo) { \
+    return tall_nn<T>(ctx, n, kd, nb, *(const T*)alpha, (const T*)S, lds, (const T*)C, ldc, *(const T*)beta, \
+                      (T*)Out, ldo);                                                                   \
+  }                                                                                                    \
+  int lb2_##P##_residual(lb2_ctx* ctx, int64_t n, int nc, const void* AX, int64_t ldax, const void* BX, \
+                         int64_t ldbx, const void* lambda, void* W, int64_t ldw, void* sumsq) {        \
+    return residual<T>(ctx, n, nc, (const T*)AX, ldax, (const T*)BX, ldbx, (const real_t<T>*)lambda,   \
+                       (T*)W, ldw, (real_t<T>*)sumsq);                                                 \
+  }                                                                                                    \
+  int lb2_##P##_col_sumsq(lb2_ctx* ctx, int64_t n, int nc, const void* X, int64_t ldx, void* sumsq) {  \
+    return col_sumsq<T>(ctx, n, nc, (const T*)X, ldx, (real_t<T>*)sumsq);                              \
+  }                                                                                                    \
+  int lb2_##P##_fill_uniform(lb2_ctx* ctx, int64_t n, int nc, void* X, int64_t ldx, uint64_t seed,     \
+                             int64_t n_global, int64_t row0) {                                         \
+    return fill_uniform<T>(ctx, n, nc, (T*)X, ldx, seed, n_global, row0);                              \
+  }                                                                                                    \
+  int lb2_##P##_spmm_stencil(lb2_ctx* ctx, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff, \
+                             const void* potential, int nc, const void* X, int64_t ldx, void* Y,       \
+                             int64_t ldy) {                                                            \
+    StencilDesc d;                                                                                     \
+    memset(&d, 0, sizeof(d));                                                                          \
+    d.gx = (int)gx; d.gy = (int)gy; d.gz = (int)gz; d.cdiag = cdiag; d.coff = coff;                    \
+    d.potential = potential;                                                                           \
+    return spmm_stencil<T>(ctx, d, nc, (const T*)X, ldx, (T*)Y, ldy);                                  \
+  }                                                                                                    \
+  int lb2_##P##_spmm_csr(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col,           \
+                         const void* val, int nc, const void* X, int64_t ldx, void* Y, int64_t ldy) {  \
+    return spmm_csr<T>(ctx, n, rowptr, col, (const T*)val, nc, (const T*)X, ldx, (T*)Y, ldy);          \
+  }                                                                                                    \
+  int lb2_##P##_spmm_diag(lb2_ctx* ctx, int64_t n, const void* diag, int nc, const void* X, int64_t ldx, \
+                          void* Y, int64_t ldy) {                                                      \
+    return spmm_diag<T>(ctx, n, (const real_t<T>*)diag, nc, (const T*)X, ldx, (T*)Y, ldy);             \
+  }
+
+LB2_ENTRY(s, float)
+LB2_ENTRY(d, double)
+LB2_ENTRY(c, c32)
+LB2_ENTRY(z, c64)
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU hooks (comm.cu provides the NCCL-backed implementation when a communicator is attached)
+// ---------------------------------------------------------------------------------------------------
+namespace lb2 {
+int comm_allreduce_impl(void* comm, void* buf, size_t count, bool is_double, cudaStream_t st);
+int comm_rank_impl(void* comm);
+int comm_size_impl(void* comm);
+int allreduce_sum(lb2_ctx* ctx, void* buf, size_t count, bool is_double) {
+  if (!ctx->comm) return 0;
+  ctx->launches++;
+  return comm_allreduce_impl(ctx->comm, buf, count, is_double, ctx->stream);
+}
+int comm_rank(lb2_ctx* ctx) { return ctx->comm ? comm_rank_impl(ctx->comm) : 0; }
+int comm_size(lb2_ctx* ctx) { return ctx->comm ? comm_size_impl(ctx->comm) : 1; }
+}  // namespace lb2

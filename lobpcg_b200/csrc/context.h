@@ -1,0 +1,42 @@
+// lobpcg_b200/csrc/context.h — per-device execution context behind the opaque `lb2_ctx` of the C ABI
+// (include/lobpcg_b200.h).  One stream, one growable scratch buffer for split-reduction partials,
+// cuBLAS/cuSOLVER handles for the small (<= 3k x 3k) dense factorizations only.
+#pragma once
+#include <cuda_runtime.h>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#include <stdint.h>
+#include <stddef.h>
+
+struct lb2_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  // scratch for deterministic split-n partial sums (Gram) and per-CTA norm partials
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // small-dense library handles (created lazily)
+  cublasHandle_t cublas = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+  void* solver_ws = nullptr;   // cuSOLVER device workspace
+  size_t solver_ws_bytes = 0;
+  void* solver_hws = nullptr;  // cuSOLVER host workspace (X* API)
+  size_t solver_hws_bytes = 0;
+  int* dev_info = nullptr;
+  // tuning knobs (lb2_ctx_set_option)
+  int gram_tile = 0;     // 0 = heuristic, 64 or 128
+  int nn_tile = 0;       // 0 = heuristic
+  int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
+  int spmm_cols = 0;     // CSR SpMM columns per thread (0 = heuristic)
+  // launch counter (bench.py "gpu_launches")
+  unsigned long long launches = 0;
+  // multi-GPU (row-partitioned) state; comm == nullptr => single GPU
+  void* comm = nullptr;  // lb2::Comm*
+};
+
+namespace lb2 {
+// returns a scratch pointer of at least `bytes` (grows, stream-ordered-safe because every user is
+// enqueued on ctx->stream and growth synchronizes first).
+void* ctx_scratch(lb2_ctx* ctx, size_t bytes);
+}  // namespace lb2

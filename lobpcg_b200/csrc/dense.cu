@@ -1,0 +1,543 @@
+// lobpcg_b200/csrc/dense.cu — the two tall-skinny contraction families of the LOBPCG hot path.
+//
+//   K2/K3  Gram      G (ma x mb)  = A^H B          A: n x ma, B: n x mb, column-major, n >> ma,mb
+//          replaces syrk/herk + gemm_tn/hn at  src/gram/gram_impl.inc:54-63,92-101,
+//          src/rayleigh/rayleigh_ritz_modified_impl.inc:75-77,193-195 (reference).
+//   K4-K6  tall NN   Out (n x nb) = alpha * S C + beta * Out     S: n x kd, C: kd x nb
+//          replaces gemm_nn at src/core/lobpcg_impl.inc:36,207 (projection), src/ortho/svqb_impl.inc:101
+//          (U <- U T), src/ortho/ortho_drop_impl.inc:79 (U -= V C).
+//
+// f64 runs on the FP64 tensor pipe (DMMA.8x8x4 via mma.sync.m8n8k4 — tcgen05 has no f64 kind), operands
+// staged global->shared with cp.async (LDGSTS) in a multi-stage ring, fragments read conflict-free from
+// padded tiles (row stride == 4 mod 16 doubles).  The Gram contraction is a reduction over n: each CTA
+// owns one output tile and one contiguous n-range ("split"), partial tiles go to scratch and a second
+// kernel sums them in a fixed order (deterministic, no atomics) and mirrors the Hermitian half.
+// f32 / c32 / c64 currently use the generic register-blocked SIMT kernels at the bottom.
+#include "common.cuh"
+#include "context.h"
+#include "kernels.h"
+
+namespace lb2 {
+
+// =====================================================================================================
+// cp.async tile loader: NCOLS columns x RUN contiguous doubles -> smem[c*LDS + e], zero-filled outside
+// [run0,run_end) x [col0,col_end).
+// =====================================================================================================
+template <int NCOLS, int RUN, int LDS, int NT, bool VEC>
+__device__ __forceinline__ void load_tile_f64(double* sm, const double* __restrict__ base, int64_t ld,
+                                              int64_t run0, int64_t run_end, int col0, int col_end,
+                                              int tid) {
+  if constexpr (VEC) {
+    constexpr int CPC = RUN / 2;
+    constexpr int TOTAL = NCOLS * CPC;
+#pragma unroll
+    for (int id0 = 0; id0 < TOTAL; id0 += NT) {
+      const int id = id0 + tid;
+      if (TOTAL % NT != 0 && id >= TOTAL) break;
+      const int c = id / CPC, ch = id % CPC;
+      const int64_t e = run0 + 2 * ch;
+      int bytes = 0;
+      const double* src = base;
+      if (col0 + c < col_end && e < run_end) {
+        bytes = (run_end - e >= 2) ? 16 : 8;
+        src = base + (int64_t)(col0 + c) * ld + e;
+      }
+      cp_async_zfill<16>(sm + c * LDS + 2 * ch, src, bytes);
+    }
+  } else {
+    constexpr int TOTAL = NCOLS * RUN;
+#pragma unroll
+    for (int id0 = 0; id0 < TOTAL; id0 += NT) {
+      const int id = id0 + tid;
+      if (TOTAL % NT != 0 && id >= TOTAL) break;
+      const int c = id / RUN, el = id % RUN;
+      const int64_t e = run0 + el;
+      int bytes = 0;
+      const double* src = base;
+      if (col0 + c < col_end && e < run_end) {
+        bytes = 8;
+        src = base + (int64_t)(col0 + c) * ld + e;
+      }
+      cp_async_zfill<8>(sm + c * LDS + el, src, bytes);
+    }
+  }
+}
+
+// upper-triangular tile enumeration: t -> (i <= j)
+__device__ __forceinline__ void upper_tile(int t, int& i, int& j) {
+  j = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+  while ((j + 1) * (j + 2) / 2 <= t) ++j;
+  while (j * (j + 1) / 2 > t) --j;
+  i = t - j * (j + 1) / 2;
+}
+
+// =====================================================================================================
+// K2/K3 f64: DMMA Gram.  grid = (ntiles, nsplit).
+// =====================================================================================================
+template <int TM, int TN, int WM, int WN, int BK, int STAGES, bool VEC>
+__global__ void __launch_bounds__(WM* WN * 32)
+    gram_dmma_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                     int ma, int mb, int64_t n, int64_t rows_per_split, int upper, int ntm,
+                     double* __restrict__ out, int64_t split_stride, int ldo) {
+  constexpr int NT = WM * WN * 32;
+  constexpr int LDS = BK + 4;
+  constexpr int MB = TM / WM / 8;
+  constexpr int NB = TN / WN / 8;
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + (size_t)STAGES * TM * LDS;
+
+  int ti, tj;
+  if (upper) upper_tile(blockIdx.x, ti, tj);
+  else { ti = blockIdx.x % ntm; tj = blockIdx.x / ntm; }
+  const int m0 = ti * TM, c0 = tj * TN;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r_end = min(n, r_begin + rows_per_split);
+  const int nchunks = (r_end > r_begin) ? (int)((r_end - r_begin + BK - 1) / BK) : 0;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WM, wn = warp / WM;
+  const int g = lane >> 2, t = lane & 3;
+
+  double acc[MB][NB][2];
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto issue = [&](int chunk) {
+    if (chunk < nchunks) {
+      const int s = chunk % STAGES;
+      const int64_t r = r_begin + (int64_t)chunk * BK;
+      load_tile_f64<TM, BK, LDS, NT, VEC>(As + (size_t)s * TM * LDS, A, lda, r, r_end, m0, ma, tid);
+      load_tile_f64<TN, BK, LDS, NT, VEC>(Bs + (size_t)s * TN * LDS, B, ldb, r, r_end, c0, mb, tid);
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) issue(s);
+
+  for (int chunk = 0; chunk < nchunks; chunk++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(chunk + STAGES - 1);
+    const double* as = As + (size_t)(chunk % STAGES) * TM * LDS + (wm * MB * 8 + g) * LDS + t;
+    const double* bs = Bs + (size_t)(chunk % STAGES) * TN * LDS + (wn * NB * 8 + g) * LDS + t;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ks++) {
+      double a[MB], b[NB];
+#pragma unroll
+      for (int i = 0; i < MB; i++) a[i] = as[i * 8 * LDS + ks * 4];
+#pragma unroll
+      for (int j = 0; j < NB; j++) b[j] = bs[j * 8 * LDS + ks * 4];
+#pragma unroll
+      for (int i = 0; i < MB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) dmma884(acc[i][j], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  double* o = out + (int64_t)blockIdx.y * split_stride;
+#pragma unroll
+  for (int i = 0; i < MB; i++) {
+    const int row = m0 + wm * MB * 8 + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const int col = c0 + wn * NB * 8 + j * 8 + 2 * t;
+      if (row < ma) {
+        if (col < mb) o[row + (int64_t)col * ldo] = acc[i][j][0];
+        if (col + 1 < mb) o[row + (int64_t)(col + 1) * ldo] = acc[i][j][1];
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// Generic SIMT Gram (all scalar types): 64x64 tile, BK=16, 256 threads x (4x4) outputs.
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+    gram_simt_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb, int ma,
+                     int mb, int64_t n, int64_t rows_per_split, int upper, int ntm, T* __restrict__ out,
+                     int64_t split_stride, int ldo) {
+  constexpr int TS = 64, BK = 16;
+  __shared__ T As[BK][TS + 1];
+  __shared__ T Bs[BK][TS + 1];
+  int ti, tj;
+  if (upper) upper_tile(blockIdx.x, ti, tj);
+  else { ti = blockIdx.x % ntm; tj = blockIdx.x / ntm; }
+  const int m0 = ti * TS, c0 = tj * TS;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r_end = min(n, r_begin + rows_per_split);
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = zero<T>();
+  const int lc = tid / 4, lk = (tid % 4) * 4;
+  for (int64_t r = r_begin; r < r_end; r += BK) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int64_t rr = r + lk + q;
+      T va = zero<T>(), vb = zero<T>();
+      if (rr < r_end) {
+        if (m0 + lc < ma) va = A[(int64_t)(m0 + lc) * lda + rr];
+        if (c0 + lc < mb) vb = B[(int64_t)(c0 + lc) * ldb + rr];
+      }
+      As[lk + q][lc] = va;
+      Bs[lk + q][lc] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) fmac_(acc[i][j], a[i], b[j]);
+    }
+    __syncthreads();
+  }
+  T* o = out + (int64_t)blockIdx.y * split_stride;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int row = m0 + ty * 4 + i, col = c0 + tx * 4 + j;
+      if (row < ma && col < mb) o[row + (int64_t)col * ldo] = acc[i][j];
+    }
+}
+
+// Sum the split partials in fixed order; optionally mirror the upper triangle (conjugated) into the
+// lower one so consumers may read either half.
+template <typename T>
+__global__ void gram_reduce_kernel(const T* __restrict__ part, int64_t split_stride, int nsplit, int ma,
+                                   int mb, int mirror, T* __restrict__ G, int ldg) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)ma * mb) return;
+  const int r = (int)(idx % ma), c = (int)(idx / ma);
+  const bool flip = mirror && r > c;
+  const int64_t src = flip ? ((int64_t)c + (int64_t)r * ma) : ((int64_t)r + (int64_t)c * ma);
+  T s = zero<T>();
+  for (int k = 0; k < nsplit; k++) s = add_(s, part[(int64_t)k * split_stride + src]);
+  G[r + (int64_t)c * ldg] = flip ? conj_(s) : s;
+}
+
+// =====================================================================================================
+// K4-K6 f64: DMMA tall NN.  grid.x = row_tiles * col_tiles (col tile fastest => CTAs sharing an S row
+// block are co-resident and hit L2).
+// =====================================================================================================
+template <int TM, int TN, int WM, int WN, int BK, int STAGES, bool VECA, bool VECB>
+__global__ void __launch_bounds__(WM* WN * 32)
+    tall_nn_dmma_kernel(const double* __restrict__ S, int64_t lds, const double* __restrict__ C, int ldc,
+                        double* __restrict__ Out, int64_t ldo, int64_t n, int kd, int nb, int nct,
+                        double alpha, double beta) {
+  constexpr int NT = WM * WN * 32;
+  constexpr int LDA = TM + 4;
+  constexpr int LDB = BK + 4;
+  constexpr int MB = TM / WM / 8;
+  constexpr int NB = TN / WN / 8;
+  extern __shared__ __align__(16) double smem[];
+  double* Ss = smem;                                   // [STAGES][BK][LDA]
+  double* Cs = smem + (size_t)STAGES * BK * LDA;       // [STAGES][TN][LDB]
+
+  const int ct = blockIdx.x % nct;
+  const int64_t rt = blockIdx.x / nct;
+  const int64_t r0 = rt * TM;
+  const int c0 = ct * TN;
+  const int nchunks = (kd + BK - 1) / BK;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WM, wn = warp / WM;
+  const int g = lane >> 2, t = lane & 3;
+
+  double acc[MB][NB][2];
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto issue = [&](int chunk) {
+    if (chunk < nchunks) {
+      const int s = chunk % STAGES;
+      const int k0 = chunk * BK;
+      load_tile_f64<BK, TM, LDA, NT, VECA>(Ss + (size_t)s * BK * LDA, S, lds, r0, n, k0, kd, tid);
+      load_tile_f64<TN, BK, LDB, NT, VECB>(Cs + (size_t)s * TN * LDB, C, ldc, k0, kd, c0, nb, tid);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) issue(s);
+
+  for (int chunk = 0; chunk < nchunks; chunk++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(chunk + STAGES - 1);
+    const double* as = Ss + (size_t)(chunk % STAGES) * BK * LDA + t * LDA + wm * MB * 8 + g;
+    const double* bs = Cs + (size_t)(chunk % STAGES) * TN * LDB + (wn * NB * 8 + g) * LDB + t;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ks++) {
+      double a[MB], b[NB];
+#pragma unroll
+      for (int i = 0; i < MB; i++) a[i] = as[ks * 4 * LDA + i * 8];
+#pragma unroll
+      for (int j = 0; j < NB; j++) b[j] = bs[j * 8 * LDB + ks * 4];
+#pragma unroll
+      for (int i = 0; i < MB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) dmma884(acc[i][j], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int i = 0; i < MB; i++) {
+    const int64_t row = r0 + wm * MB * 8 + i * 8 + g;
+    if (row >= n) continue;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const int col = c0 + wn * NB * 8 + j * 8 + 2 * t;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        if (col + q < nb) {
+          double* p = Out + row + (int64_t)(col + q) * ldo;
+          double v = alpha * acc[i][j][q];
+          if (beta != 0.0) v += beta * (*p);
+          *p = v;
+        }
+      }
+    }
+  }
+}
+
+// Generic SIMT tall NN (all scalar types): 64 rows x 64 cols tile, BK = 16.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    tall_nn_simt_kernel(const T* __restrict__ S, int64_t lds, const T* __restrict__ C, int ldc,
+                        T* __restrict__ Out, int64_t ldo, int64_t n, int kd, int nb, int nct, T alpha,
+                        T beta, int beta_zero) {
+  constexpr int TS = 64, BK = 16;
+  __shared__ T Ss[BK][TS + 1];
+  __shared__ T Cs[BK][TS + 1];
+  const int ct = blockIdx.x % nct;
+  const int64_t rt = blockIdx.x / nct;
+  const int64_t r0 = rt * TS;
+  const int c0 = ct * TS;
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;  // tx -> rows (contiguous), ty -> cols
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = zero<T>();
+  for (int k0 = 0; k0 < kd; k0 += BK) {
+    // S tile: BK columns x 64 rows, rows contiguous
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int id = tid + q * 256;
+      const int kk = id / TS, rr = id % TS;
+      T v = zero<T>();
+      if (k0 + kk < kd && r0 + rr < n) v = S[(int64_t)(k0 + kk) * lds + r0 + rr];
+      Ss[kk][rr] = v;
+    }
+    // C tile: 64 columns x BK (k contiguous)
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int id = tid + q * 256;
+      const int cc = id / BK, kk = id % BK;
+      T v = zero<T>();
+      if (k0 + kk < kd && c0 + cc < nb) v = C[(int64_t)(c0 + cc) * ldc + k0 + kk];
+      Cs[kk][cc] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = Ss[k][tx + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Cs[k][ty * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) fma_(acc[i][j], a[i], b[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int64_t row = r0 + tx + 16 * i;
+      const int col = c0 + ty * 4 + j;
+      if (row < n && col < nb) {
+        T* p = Out + row + (int64_t)col * ldo;
+        T v = mul_(alpha, acc[i][j]);
+        if (!beta_zero) v = add_(v, mul_(beta, *p));
+        *p = v;
+      }
+    }
+}
+
+// =====================================================================================================
+// Host launchers
+// =====================================================================================================
+template <int TM, int TN, int WM, int WN, int BK, int STAGES>
+static int launch_gram_dmma(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda,
+                            const double* B, int64_t ldb, double* G, int ldg, int upper) {
+  const int ntm = (ma + TM - 1) / TM, ntn = (mb + TN - 1) / TN;
+  const int ntiles = upper ? ntm * (ntm + 1) / 2 : ntm * ntn;
+  // one resident CTA per SM; fill the machine with splits of the n range
+  int nsplit = ctx->sm_count / ntiles;
+  if (nsplit < 1) nsplit = 1;
+  const int64_t min_rows = 8 * BK;
+  if ((int64_t)nsplit * min_rows > n) nsplit = (int)((n + min_rows - 1) / min_rows);
+  if (nsplit < 1) nsplit = 1;
+  int64_t rps = (n + nsplit - 1) / nsplit;
+  rps = (rps + BK - 1) / BK * BK;
+  nsplit = (int)((n + rps - 1) / rps);
+  const bool direct = (nsplit == 1 && !upper && ldg == ma);
+  const int64_t split_stride = (int64_t)ma * mb;
+  double* part = direct ? G : (double*)ctx_scratch(ctx, sizeof(double) * split_stride * nsplit);
+  if (!part) return -1;
+  const bool vec = (lda % 2 == 0) && (ldb % 2 == 0) && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
+  constexpr size_t smem = sizeof(double) * (size_t)STAGES * (TM + TN) * (BK + 4);
+  dim3 grid(ntiles, nsplit), block(WM * WN * 32);
+  if (vec) {
+    auto k = gram_dmma_kernel<TM, TN, WM, WN, BK, STAGES, true>;
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, block, smem, ctx->stream>>>(A, lda, B, ldb, ma, mb, n, rps, upper, ntm, part, split_stride, ma);
+  } else {
+    auto k = gram_dmma_kernel<TM, TN, WM, WN, BK, STAGES, false>;
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, block, smem, ctx->stream>>>(A, lda, B, ldb, ma, mb, n, rps, upper, ntm, part, split_stride, ma);
+  }
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  if (!direct) {
+    const int64_t tot = (int64_t)ma * mb;
+    gram_reduce_kernel<double><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
+        part, split_stride, nsplit, ma, mb, upper, G, ldg);
+    ctx->launches++;
+    LB2_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+template <typename T>
+static int launch_gram_simt(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const T* B,
+                            int64_t ldb, T* G, int ldg, int upper) {
+  constexpr int TS = 64, BK = 16;
+  const int ntm = (ma + TS - 1) / TS, ntn = (mb + TS - 1) / TS;
+  const int ntiles = upper ? ntm * (ntm + 1) / 2 : ntm * ntn;
+  int nsplit = (ctx->sm_count * 4) / ntiles;
+  if (nsplit < 1) nsplit = 1;
+  const int64_t min_rows = 16 * BK;
+  if ((int64_t)nsplit * min_rows > n) nsplit = (int)((n + min_rows - 1) / min_rows);
+  if (nsplit < 1) nsplit = 1;
+  int64_t rps = (n + nsplit - 1) / nsplit;
+  rps = (rps + BK - 1) / BK * BK;
+  nsplit = (int)((n + rps - 1) / rps);
+  const int64_t split_stride = (int64_t)ma * mb;
+  T* part = (T*)ctx_scratch(ctx, sizeof(T) * split_stride * nsplit);
+  if (!part) return -1;
+  dim3 grid(ntiles, nsplit);
+  gram_simt_kernel<T><<<grid, 256, 0, ctx->stream>>>(A, lda, B, ldb, ma, mb, n, rps, upper, ntm, part,
+                                                     split_stride, ma);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  const int64_t tot = (int64_t)ma * mb;
+  gram_reduce_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(part, split_stride, nsplit,
+                                                                               ma, mb, upper, G, ldg);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// G = A^H B.  upper != 0: A and B span the same columns of a Hermitian product (G = G^H): only tiles on
+// or above the diagonal are computed and the result is mirrored, so all of G is valid on return.
+template <typename T>
+int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const T* B, int64_t ldb, T* G,
+         int ldg, int upper) {
+  if (ma <= 0 || mb <= 0) return 0;
+  if (upper && ma != mb) return -2;
+  if (n <= 0) {
+    LB2_CUDA_OK(cudaMemset2DAsync(G, sizeof(T) * ldg, 0, sizeof(T) * ma, mb, ctx->stream));
+    return 0;
+  }
+  if constexpr (std::is_same<T, double>::value) {
+    if (!ctx->force_simt) {
+      int tile = ctx->gram_tile;
+      if (tile == 0) tile = (ma > 192 || mb > 192) ? 128 : 64;
+      if (tile == 128) return launch_gram_dmma<128, 128, 2, 4, 16, 4>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+      return launch_gram_dmma<64, 64, 2, 2, 16, 4>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+    }
+  }
+  return launch_gram_simt<T>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+}
+
+template <int TM, int TN, int WM, int WN, int BK, int STAGES>
+static int launch_nn_dmma(lb2_ctx* ctx, int64_t n, int kd, int nb, double alpha, const double* S,
+                          int64_t lds, const double* C, int ldc, double beta, double* Out, int64_t ldo) {
+  const int nct = (nb + TN - 1) / TN;
+  const int64_t nrt = (n + TM - 1) / TM;
+  const bool veca = (lds % 2 == 0) && ((uintptr_t)S % 16 == 0);
+  const bool vecb = (ldc % 2 == 0) && ((uintptr_t)C % 16 == 0);
+  constexpr size_t smem = sizeof(double) * (size_t)STAGES * (BK * (TM + 4) + TN * (BK + 4));
+  const unsigned grid = (unsigned)(nrt * nct);
+  dim3 block(WM * WN * 32);
+#define LB2_NN_LAUNCH(VA, VB)                                                                         \
+  {                                                                                                   \
+    auto k = tall_nn_dmma_kernel<TM, TN, WM, WN, BK, STAGES, VA, VB>;                                 \
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k<<<grid, block, smem, ctx->stream>>>(S, lds, C, ldc, Out, ldo, n, kd, nb, nct, alpha, beta);     \
+  }
+  if (veca && vecb) LB2_NN_LAUNCH(true, true)
+  else if (veca) LB2_NN_LAUNCH(true, false)
+  else if (vecb) LB2_NN_LAUNCH(false, true)
+  else LB2_NN_LAUNCH(false, false)
+#undef LB2_NN_LAUNCH
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Out = alpha * S C + beta * Out.  Out must not alias S (the drivers ping-pong slabs instead).
+template <typename T>
+int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_t lds, const T* C, int ldc,
+            T beta, T* Out, int64_t ldo) {
+  if (n <= 0 || nb <= 0) return 0;
+  if constexpr (std::is_same<T, double>::value) {
+    if (!ctx->force_simt && kd > 0) {
+      int tile = ctx->nn_tile;
+      if (tile == 0) tile = (nb > 96) ? 128 : 64;
+      if (tile == 128) return launch_nn_dmma<128, 128, 2, 4, 16, 4>(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
+      return launch_nn_dmma<128, 64, 4, 2, 16, 4>(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
+    }
+  }
+  const int nct = (nb + 63) / 64;
+  const int64_t nrt = (n + 63) / 64;
+  const bool bz = (real_(beta) == real_t<T>(0)) && (abs2_(beta) == real_t<T>(0));
+  tall_nn_simt_kernel<T><<<(unsigned)(nrt * nct), 256, 0, ctx->stream>>>(S, lds, C, ldc, Out, ldo, n, kd, nb,
+                                                                       nct, alpha, beta, bz ? 1 : 0);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+#define LB2_INST(T)                                                                                   \
+  template int gram<T>(lb2_ctx*, int64_t, int, int, const T*, int64_t, const T*, int64_t, T*, int, int); \
+  template int tall_nn<T>(lb2_ctx*, int64_t, int, int, T, const T*, int64_t, const T*, int, T, T*, int64_t);
+LB2_INST(float)
+LB2_INST(double)
+LB2_INST(c32)
+LB2_INST(c64)
+#undef LB2_INST
+
+}  // namespace lb2

@@ -1,0 +1,63 @@
+// lobpcg_b200/csrc/kernels.h — internal C++ (templated) interface of the device kernels.  The C ABI in
+// include/lobpcg_b200.h instantiates these for s/d/c/z.  All pointers are DEVICE pointers, all matrices
+// column-major, all work is enqueued on ctx->stream.  Return 0 on success.
+#pragma once
+#include <stdint.h>
+#include <type_traits>
+#include "common.cuh"
+#include "context.h"
+
+namespace lb2 {
+
+// ---- dense.cu ---------------------------------------------------------------------------------------
+template <typename T>
+int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const T* B, int64_t ldb, T* G,
+         int ldg, int upper);
+template <typename T>
+int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_t lds, const T* C, int ldc,
+            T beta, T* Out, int64_t ldo);
+
+// ---- elementwise.cu ---------------------------------------------------------------------------------
+// W[:,j] = AX[:,j] - lambda[j] * BX[:,j]  (W may be null: norms only); sumsq[j] = ||W[:,j]||^2 (may be null)
+template <typename T>
+int residual(lb2_ctx* ctx, int64_t n, int nc, const T* AX, int64_t ldax, const T* BX, int64_t ldbx,
+             const real_t<T>* lambda, T* W, int64_t ldw, real_t<T>* sumsq);
+// sumsq[j] = ||X[:,j]||_2^2, j < nc
+template <typename T>
+int col_sumsq(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, real_t<T>* sumsq);
+// out[0] = sum_j sumsq[j]  (Frobenius^2) on device
+template <typename R>
+int sum_reals(lb2_ctx* ctx, int nc, const R* v, R* out);
+template <typename T>
+int fill_uniform(lb2_ctx* ctx, int64_t n, int nc, T* X, int64_t ldx, uint64_t seed, int64_t n_global,
+                 int64_t row0);  // X[i,j] <- uniform(seed, counter = j*n_global + row0 + i)
+// X[:,j] *= s[j] (s on device) or X *= s0 (s == null)
+template <typename T>
+int scale_cols(lb2_ctx* ctx, int64_t n, int nc, T* X, int64_t ldx, const real_t<T>* s, real_t<T> s0);
+// x *= 1/sqrt(sumsq[0]) when sumsq[0] > 0 (power iteration step, estimate_norm)
+template <typename T>
+int normalize_by(lb2_ctx* ctx, int64_t n, T* x, const real_t<T>* sumsq);
+template <typename T>
+int copy_block(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy);
+
+// ---- spmm.cu ----------------------------------------------------------------------------------------
+struct StencilDesc {
+  int gx, gy, gz;          // local grid (gz = local planes of the z-slab)
+  double cdiag, coff;      // y = (cdiag + v + shift) x + coff * sum(neighbours)
+  double shift;            // extra diagonal shift (BdG: K + shift)
+  const void* potential;   // real_t<T>[n_local] or null
+  const void* halo_lo;     // T plane (gx*gy) below z=0 per column, or null (Dirichlet)
+  const void* halo_hi;     // T plane above z=gz-1 per column, or null
+  int64_t halo_ld;         // column stride of the halo planes
+  int bdg;                 // 1: operator acts on [u;v] (n = 2*gx*gy*gz), coupling d / conj(d)
+  double dre, dim;
+};
+template <typename T>
+int spmm_stencil(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy);
+template <typename T>
+int spmm_csr(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val, int nc,
+             const T* X, int64_t ldx, T* Y, int64_t ldy);
+template <typename T>
+int spmm_diag(lb2_ctx* ctx, int64_t n, const real_t<T>* d, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy);
+
+}  // namespace lb2

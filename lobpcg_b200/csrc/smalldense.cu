@@ -1,0 +1,385 @@
+// lobpcg_b200/csrc/smalldense.cu — the small (<= 3k x 3k) projected problem, kept on the device.
+//
+// D1-D8 of SURVEY.md §2b: diagonal scaling, Cholesky + condition estimate + D R^-1, congruence transform,
+// symmetric/Hermitian eigensolve, QR of Z_{1,perp}^T, SVQB transform, orthogonality error.  These are
+// O(k^3) on <= 900 x 900 matrices (< 1 % of the reference's time); the factorizations call
+// cuSOLVER/cuBLAS as plain library routines, everything around them is small hand-written kernels so that
+// no matrix leaves the device (the host only reads back `info`, a condition number or a column count).
+//
+// Reference call sites: src/rayleigh/rayleigh_ritz_impl.inc:49-96, rayleigh_ritz_modified_impl.inc:70-269,
+// src/ortho/svqb_impl.inc:64-98, src/ortho/ortho_err_upper_impl.inc:2-13.
+#include "common.cuh"
+#include "context.h"
+#include "smalldense.h"
+
+namespace lb2 {
+
+template <typename T> struct CudaType;
+template <> struct CudaType<float>  { static constexpr cudaDataType v = CUDA_R_32F; static constexpr cudaDataType r = CUDA_R_32F; };
+template <> struct CudaType<double> { static constexpr cudaDataType v = CUDA_R_64F; static constexpr cudaDataType r = CUDA_R_64F; };
+template <> struct CudaType<c32>    { static constexpr cudaDataType v = CUDA_C_32F; static constexpr cudaDataType r = CUDA_R_32F; };
+template <> struct CudaType<c64>    { static constexpr cudaDataType v = CUDA_C_64F; static constexpr cudaDataType r = CUDA_R_64F; };
+
+#define LB2_SOLVER_OK(expr)                                                                          \
+  do {                                                                                               \
+    cusolverStatus_t _s = (expr);                                                                    \
+    if (_s != CUSOLVER_STATUS_SUCCESS) {                                                             \
+      fprintf(stderr, "lobpcg_b200: cuSOLVER status %d at %s:%d (%s)\n", (int)_s, __FILE__, __LINE__, #expr); \
+      return -1;                                                                                     \
+    }                                                                                                \
+  } while (0)
+#define LB2_BLAS_OK(expr)                                                                            \
+  do {                                                                                               \
+    cublasStatus_t _s = (expr);                                                                      \
+    if (_s != CUBLAS_STATUS_SUCCESS) {                                                               \
+      fprintf(stderr, "lobpcg_b200: cuBLAS status %d at %s:%d (%s)\n", (int)_s, __FILE__, __LINE__, #expr); \
+      return -1;                                                                                     \
+    }                                                                                                \
+  } while (0)
+
+static cusolverDnParams_t g_params = nullptr;
+
+int sd_init(lb2_ctx* ctx) {
+  if (!ctx->cublas) {
+    LB2_BLAS_OK(cublasCreate(&ctx->cublas));
+    LB2_BLAS_OK(cublasSetStream(ctx->cublas, ctx->stream));
+    LB2_BLAS_OK(cublasSetPointerMode(ctx->cublas, CUBLAS_POINTER_MODE_HOST));
+  }
+  if (!ctx->cusolver) {
+    LB2_SOLVER_OK(cusolverDnCreate(&ctx->cusolver));
+    LB2_SOLVER_OK(cusolverDnSetStream(ctx->cusolver, ctx->stream));
+  }
+  if (!g_params) LB2_SOLVER_OK(cusolverDnCreateParams(&g_params));
+  if (!ctx->dev_info) LB2_CUDA_OK(cudaMalloc(&ctx->dev_info, sizeof(int) * 4));
+  return 0;
+}
+
+static int ensure_ws(lb2_ctx* ctx, size_t dev_bytes, size_t host_bytes) {
+  if (dev_bytes > ctx->solver_ws_bytes) {
+    LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->solver_ws) cudaFree(ctx->solver_ws);
+    ctx->solver_ws = nullptr;
+    const size_t want = dev_bytes + (dev_bytes >> 2) + 1024;
+    LB2_CUDA_OK(cudaMalloc(&ctx->solver_ws, want));
+    ctx->solver_ws_bytes = want;
+  }
+  if (host_bytes > ctx->solver_hws_bytes) {
+    LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    free(ctx->solver_hws);
+    ctx->solver_hws = malloc(host_bytes + 1024);
+    if (!ctx->solver_hws) return -1;
+    ctx->solver_hws_bytes = host_bytes + 1024;
+  }
+  return 0;
+}
+
+static int read_info(lb2_ctx* ctx, int* h_info) {
+  LB2_CUDA_OK(cudaMemcpyAsync(h_info, ctx->dev_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+template <typename T>
+int sd_potrf_upper(lb2_ctx* ctx, int m, T* A, int lda, int* h_info) {
+  if (sd_init(ctx)) return -1;
+  size_t wd = 0, wh = 0;
+  LB2_SOLVER_OK(cusolverDnXpotrf_bufferSize(ctx->cusolver, g_params, CUBLAS_FILL_MODE_UPPER, m, CudaType<T>::v, A,
+                                            lda, CudaType<T>::v, &wd, &wh));
+  if (ensure_ws(ctx, wd, wh)) return -1;
+  LB2_SOLVER_OK(cusolverDnXpotrf(ctx->cusolver, g_params, CUBLAS_FILL_MODE_UPPER, m, CudaType<T>::v, A, lda,
+                                 CudaType<T>::v, ctx->solver_ws, wd, ctx->solver_hws, wh, ctx->dev_info));
+  ctx->launches++;
+  return read_info(ctx, h_info);
+}
+
+template <typename T>
+int sd_syevd_upper(lb2_ctx* ctx, int m, T* A, int lda, real_t<T>* w, int* h_info) {
+  if (sd_init(ctx)) return -1;
+  size_t wd = 0, wh = 0;
+  LB2_SOLVER_OK(cusolverDnXsyevd_bufferSize(ctx->cusolver, g_params, CUSOLVER_EIG_MODE_VECTOR,
+                                            CUBLAS_FILL_MODE_UPPER, m, CudaType<T>::v, A, lda, CudaType<T>::r, w,
+                                            CudaType<T>::v, &wd, &wh));
+  if (ensure_ws(ctx, wd, wh)) return -1;
+  LB2_SOLVER_OK(cusolverDnXsyevd(ctx->cusolver, g_params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, m,
+                                 CudaType<T>::v, A, lda, CudaType<T>::r, w, CudaType<T>::v, ctx->solver_ws, wd,
+                                 ctx->solver_hws, wh, ctx->dev_info));
+  ctx->launches++;
+  return read_info(ctx, h_info);
+}
+
+// orgqr / ungqr have no 64-bit generic API: typed overloads
+static cusolverStatus_t orgqr_bs(cusolverDnHandle_t h, int m, int n, int k, const float* A, int lda, const float* tau, int* lw) { return cusolverDnSorgqr_bufferSize(h, m, n, k, A, lda, tau, lw); }
+static cusolverStatus_t orgqr_bs(cusolverDnHandle_t h, int m, int n, int k, const double* A, int lda, const double* tau, int* lw) { return cusolverDnDorgqr_bufferSize(h, m, n, k, A, lda, tau, lw); }
+static cusolverStatus_t orgqr_bs(cusolverDnHandle_t h, int m, int n, int k, const c32* A, int lda, const c32* tau, int* lw) { return cusolverDnCungqr_bufferSize(h, m, n, k, (const cuComplex*)A, lda, (const cuComplex*)tau, lw); }
+static cusolverStatus_t orgqr_bs(cusolverDnHandle_t h, int m, int n, int k, const c64* A, int lda, const c64* tau, int* lw) { return cusolverDnZungqr_bufferSize(h, m, n, k, (const cuDoubleComplex*)A, lda, (const cuDoubleComplex*)tau, lw); }
+static cusolverStatus_t orgqr_run(cusolverDnHandle_t h, int m, int n, int k, float* A, int lda, const float* tau, float* w, int lw, int* info) { return cusolverDnSorgqr(h, m, n, k, A, lda, tau, w, lw, info); }
+static cusolverStatus_t orgqr_run(cusolverDnHandle_t h, int m, int n, int k, double* A, int lda, const double* tau, double* w, int lw, int* info) { return cusolverDnDorgqr(h, m, n, k, A, lda, tau, w, lw, info); }
+static cusolverStatus_t orgqr_run(cusolverDnHandle_t h, int m, int n, int k, c32* A, int lda, const c32* tau, c32* w, int lw, int* info) { return cusolverDnCungqr(h, m, n, k, (cuComplex*)A, lda, (const cuComplex*)tau, (cuComplex*)w, lw, info); }
+static cusolverStatus_t orgqr_run(cusolverDnHandle_t h, int m, int n, int k, c64* A, int lda, const c64* tau, c64* w, int lw, int* info) { return cusolverDnZungqr(h, m, n, k, (cuDoubleComplex*)A, lda, (const cuDoubleComplex*)tau, (cuDoubleComplex*)w, lw, info); }
+
+// A (rows x cols, rows >= cols) <- Q of its thin QR.  tau: cols scalars of scratch.
+template <typename T>
+int sd_qr_q(lb2_ctx* ctx, int rows, int cols, T* A, int lda, T* tau) {
+  if (sd_init(ctx)) return -1;
+  size_t wd = 0, wh = 0;
+  LB2_SOLVER_OK(cusolverDnXgeqrf_bufferSize(ctx->cusolver, g_params, rows, cols, CudaType<T>::v, A, lda,
+                                            CudaType<T>::v, tau, CudaType<T>::v, &wd, &wh));
+  int lw = 0;
+  LB2_SOLVER_OK(orgqr_bs(ctx->cusolver, rows, cols, cols, A, lda, tau, &lw));
+  const size_t need = wd > sizeof(T) * (size_t)lw ? wd : sizeof(T) * (size_t)lw;
+  if (ensure_ws(ctx, need, wh)) return -1;
+  LB2_SOLVER_OK(cusolverDnXgeqrf(ctx->cusolver, g_params, rows, cols, CudaType<T>::v, A, lda, CudaType<T>::v, tau,
+                                 CudaType<T>::v, ctx->solver_ws, wd, ctx->solver_hws, wh, ctx->dev_info));
+  LB2_SOLVER_OK(orgqr_run(ctx->cusolver, rows, cols, cols, A, lda, tau, (T*)ctx->solver_ws, lw, ctx->dev_info));
+  ctx->launches += 2;
+  return 0;
+}
+
+// ---- cuBLAS typed shims ---------------------------------------------------------------------------
+static cublasStatus_t gemm_(cublasHandle_t h, cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k, const float* al, const float* A, int lda, const float* B, int ldb, const float* be, float* C, int ldc) { return cublasSgemm(h, ta, tb, m, n, k, al, A, lda, B, ldb, be, C, ldc); }
+static cublasStatus_t gemm_(cublasHandle_t h, cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k, const double* al, const double* A, int lda, const double* B, int ldb, const double* be, double* C, int ldc) { return cublasDgemm(h, ta, tb, m, n, k, al, A, lda, B, ldb, be, C, ldc); }
+static cublasStatus_t gemm_(cublasHandle_t h, cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k, const c32* al, const c32* A, int lda, const c32* B, int ldb, const c32* be, c32* C, int ldc) { return cublasCgemm(h, ta, tb, m, n, k, (const cuComplex*)al, (const cuComplex*)A, lda, (const cuComplex*)B, ldb, (const cuComplex*)be, (cuComplex*)C, ldc); }
+static cublasStatus_t gemm_(cublasHandle_t h, cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k, const c64* al, const c64* A, int lda, const c64* B, int ldb, const c64* be, c64* C, int ldc) { return cublasZgemm(h, ta, tb, m, n, k, (const cuDoubleComplex*)al, (const cuDoubleComplex*)A, lda, (const cuDoubleComplex*)B, ldb, (const cuDoubleComplex*)be, (cuDoubleComplex*)C, ldc); }
+static cublasStatus_t trsm_(cublasHandle_t h, cublasSideMode_t s, cublasFillMode_t u, cublasOperation_t t, cublasDiagType_t d, int m, int n, const float* al, const float* A, int lda, float* B, int ldb) { return cublasStrsm(h, s, u, t, d, m, n, al, A, lda, B, ldb); }
+static cublasStatus_t trsm_(cublasHandle_t h, cublasSideMode_t s, cublasFillMode_t u, cublasOperation_t t, cublasDiagType_t d, int m, int n, const double* al, const double* A, int lda, double* B, int ldb) { return cublasDtrsm(h, s, u, t, d, m, n, al, A, lda, B, ldb); }
+static cublasStatus_t trsm_(cublasHandle_t h, cublasSideMode_t s, cublasFillMode_t u, cublasOperation_t t, cublasDiagType_t d, int m, int n, const c32* al, const c32* A, int lda, c32* B, int ldb) { return cublasCtrsm(h, s, u, t, d, m, n, (const cuComplex*)al, (const cuComplex*)A, lda, (cuComplex*)B, ldb); }
+static cublasStatus_t trsm_(cublasHandle_t h, cublasSideMode_t s, cublasFillMode_t u, cublasOperation_t t, cublasDiagType_t d, int m, int n, const c64* al, const c64* A, int lda, c64* B, int ldb) { return cublasZtrsm(h, s, u, t, d, m, n, (const cuDoubleComplex*)al, (const cuDoubleComplex*)A, lda, (cuDoubleComplex*)B, ldb); }
+
+// C = op(A) op(B), opa: 'N' or 'H' (conjugate transpose; plain transpose for real types); small matrices.
+template <typename T>
+int sd_gemm(lb2_ctx* ctx, char opa, int m, int n, int k, const T* A, int lda, const T* B, int ldb, T* C, int ldc) {
+  if (sd_init(ctx)) return -1;
+  if (m <= 0 || n <= 0) return 0;
+  const T one = make<T>(1), zer = zero<T>();
+  const cublasOperation_t ta = (opa == 'N') ? CUBLAS_OP_N : (Sc<T>::cplx ? CUBLAS_OP_C : CUBLAS_OP_T);
+  LB2_BLAS_OK(gemm_(ctx->cublas, ta, CUBLAS_OP_N, m, n, k, &one, A, lda, B, ldb, &zer, C, ldc));
+  ctx->launches++;
+  return 0;
+}
+
+// X <- X R^-1 (R upper triangular, non-unit): the reference's trsm_run (blas_wrapper.h:364-386)
+template <typename T>
+int sd_trsm_run(lb2_ctx* ctx, int rows, int m, const T* R, int ldr, T* X, int ldx) {
+  if (sd_init(ctx)) return -1;
+  const T one = make<T>(1);
+  LB2_BLAS_OK(trsm_(ctx->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, rows,
+                    m, &one, R, ldr, X, ldx));
+  ctx->launches++;
+  return 0;
+}
+
+// ---- hand-written small kernels ---------------------------------------------------------------------
+// D[i] = 1/sqrt(|G_ii|) (1 if zero); G <- D G D.  rayleigh_ritz_impl.inc:49-60, svqb_impl.inc:65-73.
+template <typename T>
+__global__ void dscale_kernel(int m, T* __restrict__ G, int ldg, real_t<T>* __restrict__ D, int phase) {
+  using R = real_t<T>;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (phase == 0) {
+    if (idx < m) {
+      const R gii = sqrt(abs2_(G[idx + (int64_t)idx * ldg]));
+      D[idx] = (gii > R(0)) ? R(1) / sqrt(gii) : R(1);
+    }
+  } else {
+    if (idx < m * m) {
+      const int i = idx % m, j = idx / m;
+      T* p = G + i + (int64_t)j * ldg;
+      *p = rscale_(*p, D[i] * D[j]);
+    }
+  }
+}
+template <typename T>
+int sd_dscale(lb2_ctx* ctx, int m, T* G, int ldg, real_t<T>* D) {
+  dscale_kernel<T><<<(m + 127) / 128, 128, 0, ctx->stream>>>(m, G, ldg, D, 0);
+  dscale_kernel<T><<<(m * m + 255) / 256, 256, 0, ctx->stream>>>(m, G, ldg, D, 1);
+  ctx->launches += 2;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// M (m x m) <- diag(D)
+template <typename T>
+__global__ void set_diag_kernel(int m, T* __restrict__ M, int ldm, const real_t<T>* __restrict__ D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < m * m) {
+    const int i = idx % m, j = idx / m;
+    M[i + (int64_t)j * ldm] = (i == j) ? make<T>(D[i]) : zero<T>();
+  }
+}
+template <typename T>
+int sd_set_diag(lb2_ctx* ctx, int m, T* M, int ldm, const real_t<T>* D) {
+  set_diag_kernel<T><<<(m * m + 255) / 256, 256, 0, ctx->stream>>>(m, M, ldm, D);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// rcond_1(R) = 1 / (||R||_1 ||R^-1||_1) with R^-1 = diag(1/D) * DinvR (exact, where LAPACK trcon estimates;
+// rayleigh_ritz_modified_impl.inc:169-178).  One block; out[0] = rcond.
+template <typename T>
+__global__ void rcond_kernel(int m, const T* __restrict__ Rm, int ldr, const T* __restrict__ DinvR, int ldd,
+                             const real_t<T>* __restrict__ D, real_t<T>* __restrict__ out) {
+  using R = real_t<T>;
+  __shared__ R s1[256], s2[256];
+  R n1 = 0, n2 = 0;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    R c1 = 0, c2 = 0;
+    for (int i = 0; i <= j; i++) {
+      c1 += sqrt(abs2_(Rm[i + (int64_t)j * ldr]));
+      c2 += sqrt(abs2_(DinvR[i + (int64_t)j * ldd])) / D[i];
+    }
+    n1 = fmax(n1, c1);
+    n2 = fmax(n2, c2);
+  }
+  s1[threadIdx.x] = n1;
+  s2[threadIdx.x] = n2;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s1[threadIdx.x] = fmax(s1[threadIdx.x], s1[threadIdx.x + o]);
+      s2[threadIdx.x] = fmax(s2[threadIdx.x], s2[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const R p = s1[0] * s2[0];
+    out[0] = (p > R(0) && isfinite((double)p)) ? R(1) / p : R(0);
+  }
+}
+template <typename T>
+int sd_rcond(lb2_ctx* ctx, int m, const T* Rm, int ldr, const T* DinvR, int ldd, const real_t<T>* D,
+             real_t<T>* out_dev) {
+  rcond_kernel<T><<<1, 256, 0, ctx->stream>>>(m, Rm, ldr, DinvR, ldd, D, out_dev);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Out (rows x cols, ld ldo) <- plain transpose of In[r0:r0+cols, c0:c0+rows] :  Out[j,i] = In[r0+i, c0+j]
+// (Z_{1,perp}^T extraction, rayleigh_ritz_modified_impl.inc:100-104 — no conjugation, as the reference)
+template <typename T>
+__global__ void transpose_kernel(int rows, int cols, const T* __restrict__ In, int ldi, T* __restrict__ Out, int ldo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < rows * cols) {
+    const int j = idx % rows, i = idx / rows;
+    Out[j + (int64_t)i * ldo] = In[i + (int64_t)j * ldi];
+  }
+}
+template <typename T>
+int sd_transpose(lb2_ctx* ctx, int rows, int cols, const T* In, int ldi, T* Out, int ldo) {
+  if (rows <= 0 || cols <= 0) return 0;
+  transpose_kernel<T><<<(rows * cols + 255) / 256, 256, 0, ctx->stream>>>(rows, cols, In, ldi, Out, ldo);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// SVQB transform (svqb_impl.inc:82-98): thresh = tau*max|lam|; for retained j (all j unless drop and
+// |lam_j| < thresh): Tm[:,c] = D .* V[:,j] / sqrt(max(|lam_j|, thresh)).  count[0] = retained columns.
+template <typename T>
+__global__ void svqb_transform_kernel(int m, const T* __restrict__ V, int ldv, const real_t<T>* __restrict__ lam,
+                                      const real_t<T>* __restrict__ D, real_t<T> tau, int drop,
+                                      T* __restrict__ Tm, int ldt, int* __restrict__ count) {
+  using R = real_t<T>;
+  __shared__ R smax[256];
+  __shared__ int spos[1024 + 1];
+  R mx = 0;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) mx = fmax(mx, fabs(lam[j]));
+  smax[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + o]);
+    __syncthreads();
+  }
+  const R thresh = tau * smax[0];
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int j = 0; j < m; j++) {
+      const bool keep = !(drop && fabs(lam[j]) < thresh);
+      spos[j] = keep ? c : -1;
+      c += keep ? 1 : 0;
+    }
+    count[0] = c;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+    const int i = idx % m, j = idx / m;
+    const int c = spos[j];
+    if (c >= 0) {
+      const R df = R(1) / sqrt(fmax(fabs(lam[j]), thresh));
+      Tm[i + (int64_t)c * ldt] = rscale_(V[i + (int64_t)j * ldv], D[i] * df);
+    }
+  }
+}
+template <typename T>
+int sd_svqb_transform(lb2_ctx* ctx, int m, const T* V, int ldv, const real_t<T>* lam, const real_t<T>* D,
+                      real_t<T> tau, int drop, T* Tm, int ldt, int* count_dev) {
+  if (m > 1024) {
+    fprintf(stderr, "lobpcg_b200: svqb block wider than 1024 columns is not supported\n");
+    return -1;
+  }
+  svqb_transform_kernel<T><<<1, 256, 0, ctx->stream>>>(m, V, ldv, lam, D, tau, drop, Tm, ldt, count_dev);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ||G - I||_F from the upper triangle (ortho_err_upper_impl.inc:2-13) and ||G||_F of a full matrix.
+template <typename T>
+__global__ void ortho_err_kernel(int rows, int cols, const T* __restrict__ G, int ldg, int mode,
+                                 real_t<T>* __restrict__ out) {
+  using R = real_t<T>;
+  __shared__ R red[256];
+  R s = 0;
+  for (int idx = threadIdx.x; idx < rows * cols; idx += blockDim.x) {
+    const int i = idx % rows, j = idx / rows;
+    const R a = sqrt(abs2_(G[i + (int64_t)j * ldg]));
+    if (mode == 0) {  // upper-triangle identity error
+      if (i == j) s += (a - R(1)) * (a - R(1));
+      else if (i < j) s += R(2) * a * a;
+    } else {
+      s += a * a;
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sqrt(red[0]);
+}
+template <typename T>
+int sd_ortho_err_upper(lb2_ctx* ctx, int m, const T* G, int ldg, real_t<T>* out_dev) {
+  ortho_err_kernel<T><<<1, 256, 0, ctx->stream>>>(m, m, G, ldg, 0, out_dev);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+int sd_frob(lb2_ctx* ctx, int rows, int cols, const T* G, int ldg, real_t<T>* out_dev) {
+  ortho_err_kernel<T><<<1, 256, 0, ctx->stream>>>(rows, cols, G, ldg, 1, out_dev);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+#define LB2_INST(T)                                                                                         \
+  template int sd_potrf_upper<T>(lb2_ctx*, int, T*, int, int*);                                             \
+  template int sd_syevd_upper<T>(lb2_ctx*, int, T*, int, real_t<T>*, int*);                                 \
+  template int sd_qr_q<T>(lb2_ctx*, int, int, T*, int, T*);                                                 \
+  template int sd_gemm<T>(lb2_ctx*, char, int, int, int, const T*, int, const T*, int, T*, int);            \
+  template int sd_trsm_run<T>(lb2_ctx*, int, int, const T*, int, T*, int);                                  \
+  template int sd_dscale<T>(lb2_ctx*, int, T*, int, real_t<T>*);                                            \
+  template int sd_set_diag<T>(lb2_ctx*, int, T*, int, const real_t<T>*);                                    \
+  template int sd_rcond<T>(lb2_ctx*, int, const T*, int, const T*, int, const real_t<T>*, real_t<T>*);      \
+  template int sd_transpose<T>(lb2_ctx*, int, int, const T*, int, T*, int);                                 \
+  template int sd_svqb_transform<T>(lb2_ctx*, int, const T*, int, const real_t<T>*, const real_t<T>*, real_t<T>, int, T*, int, int*); \
+  template int sd_ortho_err_upper<T>(lb2_ctx*, int, const T*, int, real_t<T>*);                             \
+  template int sd_frob<T>(lb2_ctx*, int, int, const T*, int, real_t<T>*);
+LB2_INST(float)
+LB2_INST(double)
+LB2_INST(c32)
+LB2_INST(c64)
+#undef LB2_INST
+
+}  // namespace lb2

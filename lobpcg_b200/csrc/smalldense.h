@@ -1,0 +1,20 @@
+// lobpcg_b200/csrc/smalldense.h — device-resident small dense helpers (see smalldense.cu).
+#pragma once
+#include "common.cuh"
+#include "context.h"
+
+namespace lb2 {
+int sd_init(lb2_ctx* ctx);
+template <typename T> int sd_potrf_upper(lb2_ctx* ctx, int m, T* A, int lda, int* h_info);
+template <typename T> int sd_syevd_upper(lb2_ctx* ctx, int m, T* A, int lda, real_t<T>* w, int* h_info);
+template <typename T> int sd_qr_q(lb2_ctx* ctx, int rows, int cols, T* A, int lda, T* tau);
+template <typename T> int sd_gemm(lb2_ctx* ctx, char opa, int m, int n, int k, const T* A, int lda, const T* B, int ldb, T* C, int ldc);
+template <typename T> int sd_trsm_run(lb2_ctx* ctx, int rows, int m, const T* R, int ldr, T* X, int ldx);
+template <typename T> int sd_dscale(lb2_ctx* ctx, int m, T* G, int ldg, real_t<T>* D);
+template <typename T> int sd_set_diag(lb2_ctx* ctx, int m, T* M, int ldm, const real_t<T>* D);
+template <typename T> int sd_rcond(lb2_ctx* ctx, int m, const T* Rm, int ldr, const T* DinvR, int ldd, const real_t<T>* D, real_t<T>* out_dev);
+template <typename T> int sd_transpose(lb2_ctx* ctx, int rows, int cols, const T* In, int ldi, T* Out, int ldo);
+template <typename T> int sd_svqb_transform(lb2_ctx* ctx, int m, const T* V, int ldv, const real_t<T>* lam, const real_t<T>* D, real_t<T> tau, int drop, T* Tm, int ldt, int* count_dev);
+template <typename T> int sd_ortho_err_upper(lb2_ctx* ctx, int m, const T* G, int ldg, real_t<T>* out_dev);
+template <typename T> int sd_frob(lb2_ctx* ctx, int rows, int cols, const T* G, int ldg, real_t<T>* out_dev);
+}  // namespace lb2

@@ -1,0 +1,725 @@
+// lobpcg_b200/csrc/solver.cu — device-resident definite LOBPCG driver (see solver.h for the memory plan).
+//
+// Reference being mirrored (same state machine, same constants):
+//   driver            src/core/lobpcg_impl.inc:60-248
+//   initial RR        src/rayleigh/rayleigh_ritz_impl.inc:37-100
+//   modified RR       src/rayleigh/rayleigh_ritz_modified_impl.inc:42-273   (tol_skip = 5e-3, sticky useOrtho)
+//   ortho_drop/svqb   src/ortho/ortho_drop_impl.inc:43-125, src/ortho/svqb_impl.inc:48-106 (3 x 3 sweeps)
+//   residual / norms  src/residual/residual_impl.inc:32-99   (2-norm even when B != NULL)
+//   estimate_norm     src/residual/estimate_norm_impl.inc:38-57  (10 power steps)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <inttypes.h>
+
+#include "common.cuh"
+#include "context.h"
+#include "kernels.h"
+#include "smalldense.h"
+#include "solver.h"
+
+namespace lb2 {
+
+// -------------------------------------------------------------------------------------------------------
+template <typename T>
+int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy) {
+  if (b->prefix != Sc<T>::prefix) {
+    fprintf(stderr, "lobpcg_b200: operator built for type '%c' applied to type '%c'\n", b->prefix, Sc<T>::prefix);
+    return -1;
+  }
+  switch (b->kind) {
+    case OP_STENCIL:
+    case OP_BDG: {
+      StencilDesc d;
+      d.gx = (int)b->gx; d.gy = (int)b->gy; d.gz = (int)b->gz;
+      d.cdiag = b->cdiag; d.coff = b->coff; d.shift = b->shift;
+      d.potential = b->potential;
+      d.halo_lo = b->halo_lo; d.halo_hi = b->halo_hi; d.halo_ld = b->halo_ld;
+      d.bdg = (b->kind == OP_BDG) ? 1 : 0;
+      d.dre = b->dre; d.dim = b->dim;
+      return spmm_stencil<T>(ctx, d, nc, X, ldx, Y, ldy);
+    }
+    case OP_CSR:
+      return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy);
+    case OP_DIAG:
+      return spmm_diag<T>(ctx, b->n, (const real_t<T>*)b->diag, nc, X, ldx, Y, ldy);
+  }
+  return -1;
+}
+template int apply_builtin<float>(lb2_ctx*, const BuiltinOp*, int, const float*, int64_t, float*, int64_t);
+template int apply_builtin<double>(lb2_ctx*, const BuiltinOp*, int, const double*, int64_t, double*, int64_t);
+template int apply_builtin<c32>(lb2_ctx*, const BuiltinOp*, int, const c32*, int64_t, c32*, int64_t);
+template int apply_builtin<c64>(lb2_ctx*, const BuiltinOp*, int, const c64*, int64_t, c64*, int64_t);
+
+// -------------------------------------------------------------------------------------------------------
+struct Timers {
+  struct Rec { int ph; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  size_t used = 0;
+  cudaStream_t st = nullptr;
+  void begin(int ph) {
+    if (used == recs.size()) {
+      Rec r; r.ph = ph;
+      cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+      recs.push_back(r);
+    }
+    recs[used].ph = ph;
+    cudaEventRecord(recs[used].a, st);
+  }
+  void end() { cudaEventRecord(recs[used].b, st); used++; }
+  void collect(double* ms) {  // call after a stream synchronize
+    for (size_t i = 0; i < used; i++) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, recs[i].a, recs[i].b) == cudaSuccess) ms[recs[i].ph] += t;
+    }
+    used = 0;
+  }
+  ~Timers() { for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
+};
+
+#define LB2_TRY(expr)                                                                    \
+  do {                                                                                   \
+    int _rc = (expr);                                                                    \
+    if (_rc != 0) {                                                                      \
+      fprintf(stderr, "lobpcg_b200: %s failed (%d) at %s:%d\n", #expr, _rc, __FILE__, __LINE__); \
+      return _rc;                                                                        \
+    }                                                                                    \
+  } while (0)
+
+template <typename T> struct EpsTol;  // EPS_TOL of src/core/lobpcg_{s,d,c,z}.c
+template <> struct EpsTol<float>  { static constexpr double v = 1e-5; };
+template <> struct EpsTol<double> { static constexpr double v = 1e-12; };
+template <> struct EpsTol<c32>    { static constexpr double v = 1e-5; };
+template <> struct EpsTol<c64>    { static constexpr double v = 1e-12; };
+
+template <typename T>
+class Solver : public SolverBase {
+  using R = real_t<T>;
+  static constexpr bool kDouble = sizeof(R) == 8;
+  static constexpr int kCplx = Sc<T>::cplx ? 2 : 1;
+
+ public:
+  Solver(lb2_ctx* c, State<T>* a, bool indefinite) : ctx(c), alg(a), indef(indefinite) { tm.st = c->stream; }
+  ~Solver() override { release(); }
+
+  int init() override;
+  int step(int max_steps) override;
+  int finish() override;
+  void state(uint64_t* it, uint64_t* cv, int* uo) override {
+    if (it) *it = iter;
+    if (cv) *cv = conv;
+    if (uo) *uo = useOrtho;
+  }
+
+ private:
+  lb2_ctx* ctx;
+  State<T>* alg;
+  bool indef;
+  Timers tm;
+  int64_t n = 0, ng = 0, row0 = 0;
+  int k = 0, nev = 0;
+  T* slab[2] = {nullptr, nullptr};
+  int cur = 0;
+  T *AS = nullptr, *wA = nullptr, *wB = nullptr;
+  T *G = nullptr, *GA = nullptr, *DinvR = nullptr, *Z = nullptr, *Tmp = nullptr, *Cx = nullptr, *Cp = nullptr,
+    *Q = nullptr, *Tau = nullptr;
+  R *D = nullptr, *Lam = nullptr, *Eig = nullptr, *Sums = nullptr, *Scal = nullptr;
+  int* Count = nullptr;
+  R* hbuf = nullptr;  // pinned
+  T *hX = nullptr, *hY = nullptr;  // host staging for host-callback operators
+  int np = 0, nw = 0;
+  int useOrtho = 0;
+  uint64_t iter = 0, conv = 0;
+  R ANorm = 0, BNorm = 1;
+  std::vector<R> hEig, hRes;
+  const LinOpRaw *opA = nullptr, *opB = nullptr, *opT = nullptr;
+  bool inited = false, done = false;
+
+  T* Xp() { return slab[cur]; }
+  T* col(T* base, int64_t c) { return base + c * n; }
+
+  void release();
+  int alloc();
+  int sync() { LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); tm.collect(phase_ms); return 0; }
+  int d2h(void* dst, const void* src, size_t bytes) {
+    LB2_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+  }
+
+  int apply(const LinOpRaw* op, int nc, const T* X, T* Y);
+  int gram_ar(int ma, int mb, const T* A, const T* B, T* Gout, int upper);
+  int nn(int kd, int nb, T alpha, const T* S, const T* C, int ldc, T beta, T* Out);
+  int sumsq_total(int nc, const T* X, R* out_dev);  // out_dev[0] = ||X||_F^2 (all ranks)
+  int estimate_norm(const LinOpRaw* op, uint64_t seed, R* out);
+  int gram_self_B(int m, T* S, T* Gout);             // S^H B S (mirrored)
+  int chol_transform(int m, int* bad);               // G -> D, R (in G), DinvR ; bad=1 if potrf failed or rcond small
+  int rr_initial();
+  int rr_modified(int m, int from_col);
+  int cp_from_z(int m, const T* Zm, T* VQ);           // VQ (m x k) = Z_perp Q
+  int svqb(T* U, int nu, R tau, bool drop, int* nret);
+  int ortho_drop(T* U, int nu, T* V, int nv, int* nret);
+  int residual_pass(bool initial);
+  int step_impl(int max_steps, int* passes_out);
+  void print_state(bool header);
+};
+
+template <typename T>
+void Solver<T>::release() {
+  T** big[] = {&slab[0], &slab[1], &AS, &wA, &wB, &G, &GA, &DinvR, &Z, &Tmp, &Cx, &Cp, &Q, &Tau};
+  for (auto p : big) { if (*p) cudaFree(*p); *p = nullptr; }
+  R** rs[] = {&D, &Lam, &Eig, &Sums, &Scal};
+  for (auto p : rs) { if (*p) cudaFree(*p); *p = nullptr; }
+  if (Count) cudaFree(Count); Count = nullptr;
+  if (hbuf) cudaFreeHost(hbuf); hbuf = nullptr;
+  if (hX) cudaFreeHost(hX); hX = nullptr;
+  if (hY) cudaFreeHost(hY); hY = nullptr;
+}
+
+template <typename T>
+int Solver<T>::alloc() {
+  const size_t nk = (size_t)n * k;
+  const size_t m3 = 3 * (size_t)k;
+  LB2_CUDA_OK(cudaMalloc(&slab[0], sizeof(T) * 3 * nk));
+  LB2_CUDA_OK(cudaMalloc(&slab[1], sizeof(T) * 3 * nk));
+  LB2_CUDA_OK(cudaMalloc(&AS, sizeof(T) * 3 * nk));
+  LB2_CUDA_OK(cudaMalloc(&wA, sizeof(T) * std::max<size_t>(nk, 2 * (size_t)n)));
+  LB2_CUDA_OK(cudaMalloc(&wB, sizeof(T) * std::max<size_t>(nk, 2 * (size_t)n)));
+  T** sm[] = {&G, &GA, &DinvR, &Z, &Tmp};
+  for (auto p : sm) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * m3));
+  LB2_CUDA_OK(cudaMalloc(&Cx, sizeof(T) * m3 * k));
+  LB2_CUDA_OK(cudaMalloc(&Cp, sizeof(T) * m3 * k));
+  LB2_CUDA_OK(cudaMalloc(&Q, sizeof(T) * m3 * k));
+  LB2_CUDA_OK(cudaMalloc(&Tau, sizeof(T) * m3));
+  LB2_CUDA_OK(cudaMalloc(&D, sizeof(R) * m3));
+  LB2_CUDA_OK(cudaMalloc(&Lam, sizeof(R) * m3));
+  LB2_CUDA_OK(cudaMalloc(&Eig, sizeof(R) * m3));
+  LB2_CUDA_OK(cudaMalloc(&Sums, sizeof(R) * (m3 + 16)));
+  LB2_CUDA_OK(cudaMalloc(&Scal, sizeof(R) * 16));
+  LB2_CUDA_OK(cudaMalloc(&Count, sizeof(int) * 4));
+  LB2_CUDA_OK(cudaMallocHost(&hbuf, sizeof(R) * (m3 + 32)));
+  hEig.assign(k, R(0));
+  hRes.assign(k, R(0));
+  return 0;
+}
+
+// Y = Op X.  Built-in operators run as block kernels; anything else is a host callback (reference
+// linop.h:15-17) and is staged through pinned host memory column by column — functional, not fast.
+template <typename T>
+int Solver<T>::apply(const LinOpRaw* op, int nc, const T* X, T* Y) {
+  if (nc <= 0) return 0;
+  const BuiltinOp* b = builtin_of(op);
+  if (b) {
+    tm.begin(PH_SPMM);
+    int rc = apply_builtin<T>(ctx, b, nc, X, n, Y, n);
+    tm.end();
+    return rc;
+  }
+  if (!hX) {
+    LB2_CUDA_OK(cudaMallocHost(&hX, sizeof(T) * (size_t)n * std::max(k, 2)));
+    LB2_CUDA_OK(cudaMallocHost(&hY, sizeof(T) * (size_t)n * std::max(k, 2)));
+  }
+  const int chunk = std::max(k, 2);
+  for (int c0 = 0; c0 < nc; c0 += chunk) {
+    const int w = std::min(chunk, nc - c0);
+    LB2_CUDA_OK(cudaMemcpyAsync(hX, X + (int64_t)c0 * n, sizeof(T) * (size_t)n * w, cudaMemcpyDeviceToHost, ctx->stream));
+    LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (int j = 0; j < w; j++) op->matvec(op, hX + (size_t)j * n, hY + (size_t)j * n);
+    LB2_CUDA_OK(cudaMemcpyAsync(Y + (int64_t)c0 * n, hY, sizeof(T) * (size_t)n * w, cudaMemcpyHostToDevice, ctx->stream));
+    LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+template <typename T>
+int Solver<T>::gram_ar(int ma, int mb, const T* A, const T* B, T* Gout, int upper) {
+  tm.begin(PH_GRAM);
+  int rc = gram<T>(ctx, n, ma, mb, A, n, B, n, Gout, ma, upper);
+  tm.end();
+  if (rc) return rc;
+  if (ctx->comm) {
+    tm.begin(PH_COMM);
+    rc = allreduce_sum(ctx, Gout, (size_t)ma * mb * kCplx, kDouble);
+    tm.end();
+  }
+  return rc;
+}
+
+template <typename T>
+int Solver<T>::nn(int kd, int nb, T alpha, const T* S, const T* C, int ldc, T beta, T* Out) {
+  tm.begin(PH_TALLNN);
+  int rc = tall_nn<T>(ctx, n, kd, nb, alpha, S, n, C, ldc, beta, Out, n);
+  tm.end();
+  return rc;
+}
+
+template <typename T>
+int Solver<T>::sumsq_total(int nc, const T* X, R* out_dev) {
+  // nc <= 3k everywhere in this solver (Sums holds 3k + 16 entries)
+  tm.begin(PH_RESID);
+  int rc = col_sumsq<T>(ctx, n, nc, X, n, Sums);
+  if (!rc) rc = sum_reals<R>(ctx, nc, Sums, out_dev);
+  tm.end();
+  if (!rc && ctx->comm) rc = allreduce_sum(ctx, out_dev, 1, kDouble);
+  return rc;
+}
+
+template <typename T>
+int Solver<T>::estimate_norm(const LinOpRaw* op, uint64_t seed, R* out) {
+  T* x = wA;
+  T* y = wB;
+  LB2_TRY(fill_uniform<T>(ctx, n, 1, x, n, seed, ng, row0));
+  LB2_TRY(sumsq_total(1, x, Scal));
+  LB2_TRY(normalize_by<T>(ctx, n, x, Scal));
+  for (int it = 0; it < 10; it++) {
+    LB2_TRY(apply(op, 1, x, y));
+    LB2_TRY(sumsq_total(1, y, Scal));
+    LB2_TRY(normalize_by<T>(ctx, n, y, Scal));
+    std::swap(x, y);
+  }
+  LB2_TRY(d2h(hbuf, Scal, sizeof(R)));
+  LB2_TRY(sync());
+  *out = std::sqrt(hbuf[0]);
+  return 0;
+}
+
+// G = S^H B S, all of it valid (mirrored when B == NULL, full product otherwise; gram_impl.inc:49-67)
+template <typename T>
+int Solver<T>::gram_self_B(int m, T* S, T* Gout) {
+  if (!opB) return gram_ar(m, m, S, S, Gout, 1);
+  for (int c0 = 0; c0 < m; c0 += k) {
+    const int w = std::min(k, m - c0);
+    LB2_TRY(apply(opB, w, col(S, c0), wA));
+    LB2_TRY(gram_ar(m, w, S, wA, Gout + (size_t)c0 * m, 0));
+  }
+  return 0;
+}
+
+// D-scaling, upper Cholesky, condition check, DinvR = D R^-1  (rayleigh_ritz_modified_impl.inc:148-186)
+template <typename T>
+int Solver<T>::chol_transform(int m, int* bad) {
+  tm.begin(PH_SMALL);
+  int info = 0;
+  LB2_TRY(sd_dscale<T>(ctx, m, G, m, D));
+  LB2_TRY(sd_potrf_upper<T>(ctx, m, G, m, &info));
+  if (info != 0) { tm.end(); *bad = 1; return 0; }
+  LB2_TRY(sd_set_diag<T>(ctx, m, DinvR, m, D));
+  LB2_TRY(sd_trsm_run<T>(ctx, m, m, G, m, DinvR, m));
+  LB2_TRY(sd_rcond<T>(ctx, m, G, m, DinvR, m, D, Scal));
+  LB2_TRY(d2h(hbuf, Scal, sizeof(R)));
+  tm.end();
+  LB2_TRY(sync());
+  *bad = (hbuf[0] < (R)5.0e-3) ? 2 : 0;
+  return 0;
+}
+
+// Initial Rayleigh-Ritz on X (rayleigh_ritz_impl.inc:37-100) + X <- X Cx (lobpcg_impl.inc:99-104)
+template <typename T>
+int Solver<T>::rr_initial() {
+  T* X = Xp();
+  LB2_TRY(gram_self_B(k, X, G));
+  int bad = 0;
+  LB2_TRY(chol_transform(k, &bad));
+  if (bad == 1) {
+    fprintf(stderr, "rayleigh_ritz: Cholesky failed\n");
+    return 1;
+  }
+  LB2_TRY(apply(opA, k, X, AS));
+  LB2_TRY(gram_ar(k, k, X, AS, GA, 1));
+  tm.begin(PH_SMALL);
+  LB2_TRY(sd_gemm<T>(ctx, 'N', k, k, k, GA, k, DinvR, k, Tmp, k));
+  LB2_TRY(sd_gemm<T>(ctx, 'H', k, k, k, DinvR, k, Tmp, k, Z, k));
+  int info = 0;
+  LB2_TRY(sd_syevd_upper<T>(ctx, k, Z, k, Lam, &info));
+  if (info != 0) {
+    tm.end();
+    fprintf(stderr, "rayleigh_ritz: eigensolve failed\n");
+    return 1;
+  }
+  LB2_TRY(sd_gemm<T>(ctx, 'N', k, k, k, DinvR, k, Z, k, Cx, k));
+  LB2_CUDA_OK(cudaMemcpyAsync(Eig, Lam, sizeof(R) * k, cudaMemcpyDeviceToDevice, ctx->stream));
+  tm.end();
+  T* Xn = slab[1 - cur];
+  LB2_TRY(nn(k, k, make<T>(1), X, Cx, k, zero<T>(), Xn));
+  cur = 1 - cur;
+  return 0;
+}
+
+// VQ (m x k) = Z[:, k:m] * orth(Z[0:k, k:m]^T)   (rayleigh_ritz_modified_impl.inc:98-130 / 230-264)
+template <typename T>
+int Solver<T>::cp_from_z(int m, const T* Zm, T* VQ) {
+  const int nrem = m - k;
+  LB2_TRY(sd_transpose<T>(ctx, nrem, k, Zm + (size_t)k * m, m, Q, nrem));
+  LB2_TRY(sd_qr_q<T>(ctx, nrem, k, Q, nrem, Tau));
+  LB2_TRY(sd_gemm<T>(ctx, 'N', m, k, nrem, Zm + (size_t)k * m, m, Q, nrem, VQ, m));
+  return 0;
+}
+
+// Modified Rayleigh-Ritz on S = slab[cur][:, 0:m].  On return useOrtho in {0,1,2}; for 0/1: Cx, Cp (m x k,
+// ld m) and Eig[0:k] are set.  AS[:, from_col:m] is (re)computed here.
+template <typename T>
+int Solver<T>::rr_modified(int m, int from_col) {
+  T* S = Xp();
+  const int nrem = m - k;
+  if (useOrtho == 0) {
+    LB2_TRY(gram_self_B(m, S, G));
+    int bad = 0;
+    LB2_TRY(chol_transform(m, &bad));
+    if (bad) {
+      if (bad == 1) fprintf(stderr, "rayleigh_ritz_modified: Cholesky failed\n");
+      useOrtho = 2;
+      return 0;
+    }
+  } else {
+    useOrtho = 1;
+  }
+  LB2_TRY(apply(opA, m - from_col, col(S, from_col), col(AS, from_col)));
+  LB2_TRY(gram_ar(m, m, S, AS, GA, 1));
+  tm.begin(PH_SMALL);
+  T* Zm = Z;
+  if (useOrtho == 0) {
+    LB2_TRY(sd_gemm<T>(ctx, 'N', m, m, m, GA, m, DinvR, m, Tmp, m));
+    LB2_TRY(sd_gemm<T>(ctx, 'H', m, m, m, DinvR, m, Tmp, m, Z, m));
+  } else {
+    Zm = GA;
+  }
+  int info = 0;
+  LB2_TRY(sd_syevd_upper<T>(ctx, m, Zm, m, Lam, &info));
+  if (info != 0) {
+    tm.end();
+    fprintf(stderr, "rayleigh_ritz_modified: eigensolve failed (info=%d)\n", info);
+    return 1;
+  }
+  LB2_CUDA_OK(cudaMemcpyAsync(Eig, Lam, sizeof(R) * k, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (useOrtho == 0) {
+    LB2_TRY(sd_gemm<T>(ctx, 'N', m, k, m, DinvR, m, Zm, m, Cx, m));
+  } else {
+    LB2_CUDA_OK(cudaMemcpyAsync(Cx, Zm, sizeof(T) * (size_t)m * k, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if (nrem < k) {
+    // reference guard (:90-94, :222-226): no room for a k-column P basis
+    LB2_CUDA_OK(cudaMemsetAsync(Cp, 0, sizeof(T) * (size_t)m * k, ctx->stream));
+  } else if (useOrtho == 0) {
+    LB2_TRY(cp_from_z(m, Zm, Tmp));
+    LB2_TRY(sd_gemm<T>(ctx, 'N', m, k, m, DinvR, m, Tmp, m, Cp, m));
+  } else {
+    LB2_TRY(cp_from_z(m, Zm, Cp));
+  }
+  tm.end();
+  return 0;
+}
+
+// SVQB (svqb_impl.inc:48-106): U (n x nu) <- U T, returns retained columns.
+template <typename T>
+int Solver<T>::svqb(T* U, int nu, R tau, bool drop, int* nret) {
+  *nret = nu;
+  if (nu == 0) return 0;
+  if (opB) {
+    LB2_TRY(apply(opB, nu, U, wA));
+    LB2_TRY(gram_ar(nu, nu, U, wA, G, 1));
+  } else {
+    LB2_TRY(gram_ar(nu, nu, U, U, G, 1));
+  }
+  tm.begin(PH_SMALL);
+  LB2_TRY(sd_dscale<T>(ctx, nu, G, nu, D));
+  int info = 0;
+  LB2_TRY(sd_syevd_upper<T>(ctx, nu, G, nu, Lam, &info));
+  if (info != 0) {
+    tm.end();
+    fprintf(stderr, "svqb: eig failed with info=%d\n", info);
+    return 0;  // reference returns cols unchanged
+  }
+  LB2_TRY(sd_svqb_transform<T>(ctx, nu, G, nu, Lam, D, tau, drop ? 1 : 0, Tmp, nu, Count));
+  LB2_CUDA_OK(cudaMemcpyAsync(hbuf, Count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  tm.end();
+  LB2_TRY(sync());
+  const int keep = *(int*)hbuf;
+  LB2_TRY(nn(nu, keep, make<T>(1), U, Tmp, nu, zero<T>(), wB));
+  tm.begin(PH_OTHER);
+  LB2_TRY(copy_block<T>(ctx, n, keep, wB, n, U, n));
+  tm.end();
+  *nret = keep;
+  return 0;
+}
+
+// ortho_drop (ortho_drop_impl.inc:43-125): B-orthogonalise U against V, B-orthonormalise U.
+template <typename T>
+int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret) {
+  *nret = nu0;
+  if (nu0 == 0 || nv == 0) return 0;
+  if (ng < (int64_t)nu0 + nv) {
+    fprintf(stderr, "ortho_drop: overdetermined shape m=%lu < n_u+n_v=%lu+%lu\n", (unsigned long)ng,
+            (unsigned long)nu0, (unsigned long)nv);
+    return 0;
+  }
+  const R eps = (R)EpsTol<T>::v;
+  int nu = nu0;
+  // ||B V||_F
+  R BV_norm = 0;
+  {
+    double acc = 0;
+    if (!opB) {
+      LB2_TRY(sumsq_total(nv, V, Scal));
+      LB2_TRY(d2h(hbuf, Scal, sizeof(R)));
+      LB2_TRY(sync());
+      acc = hbuf[0];
+    } else {
+      for (int c0 = 0; c0 < nv; c0 += k) {
+        const int w = std::min(k, nv - c0);
+        LB2_TRY(apply(opB, w, col(V, c0), wA));
+        LB2_TRY(sumsq_total(w, wA, Scal));
+        LB2_TRY(d2h(hbuf, Scal, sizeof(R)));
+        LB2_TRY(sync());
+        acc += hbuf[0];
+      }
+    }
+    BV_norm = (R)std::sqrt(acc);
+    if (BV_norm < eps) BV_norm = 1;
+  }
+  for (int outer = 0; outer < 3; outer++) {
+    // C = V^H B U ; U -= V C
+    const T* BU = U;
+    if (opB) { LB2_TRY(apply(opB, nu, U, wA)); BU = wA; }
+    LB2_TRY(gram_ar(nv, nu, V, BU, Tmp, 0));
+    LB2_TRY(nn(nv, nu, make<T>(-1), V, Tmp, nv, make<T>(1), U));
+    for (int inner = 0; inner < 3; inner++) {
+      int keep = nu;
+      LB2_TRY(svqb(U, nu, eps, true, &keep));
+      if (keep != nu) {
+        fprintf(stderr, "ortho_drop: svqb dropped columns (%lu -> %lu)\n", (unsigned long)nu, (unsigned long)keep);
+        nu = keep;
+      }
+      if (nu == 0) break;
+      // ||U^H B U - I||_F / (||B U|| ||U||)
+      LB2_TRY(sumsq_total(nu, U, Scal + 1));
+      if (opB) {
+        LB2_TRY(apply(opB, nu, U, wA));
+        LB2_TRY(gram_ar(nu, nu, U, wA, G, 1));
+        LB2_TRY(sumsq_total(nu, wA, Scal + 2));
+      } else {
+        LB2_TRY(gram_ar(nu, nu, U, U, G, 1));
+      }
+      LB2_TRY(sd_ortho_err_upper<T>(ctx, nu, G, nu, Scal));
+      LB2_TRY(d2h(hbuf, Scal, 3 * sizeof(R)));
+      LB2_TRY(sync());
+      R U_norm = std::sqrt(hbuf[1]);
+      if (U_norm < eps) U_norm = 1;
+      const R BU_norm = opB ? std::sqrt(hbuf[2]) : U_norm;
+      const R rerr = hbuf[0] / (BU_norm * U_norm);
+      if (rerr < eps) break;
+    }
+    if (nu == 0) break;
+    // ||V^H B U||_F / (||B V|| ||U||)
+    const T* BU2 = U;
+    if (opB) { LB2_TRY(apply(opB, nu, U, wA)); BU2 = wA; }
+    LB2_TRY(gram_ar(nv, nu, V, BU2, Tmp, 0));
+    LB2_TRY(sd_frob<T>(ctx, nv, nu, Tmp, nv, Scal));
+    LB2_TRY(sumsq_total(nu, U, Scal + 1));
+    LB2_TRY(d2h(hbuf, Scal, 2 * sizeof(R)));
+    LB2_TRY(sync());
+    R U_norm = std::sqrt(hbuf[1]);
+    if (U_norm < eps) U_norm = 1;
+    const R rerr = hbuf[0] / (BV_norm * U_norm);
+    if (rerr < eps) break;
+  }
+  *nret = nu;
+  return 0;
+}
+
+template <typename T>
+void Solver<T>::print_state(bool header) {
+  if (alg->verbosity <= 0) return;
+  if (header)
+    printf("Iteration %" PRIu64 "\t Converged Eigenpairs: %" PRIu64 "/%" PRIu64 "\n", iter, conv, (uint64_t)nev);
+  for (int i = 0; i < nev; i++)
+    printf("Eigenvalue %" PRIu64 ": %.9e\t Residual Norm: %.5e\n", (uint64_t)i, (double)hEig[i], (double)hRes[i]);
+  printf("\n");
+}
+
+// After X (slab[cur][:,0:k]) and Eig are final for this pass: AX, residual norms of the first nev columns,
+// convergence count (contiguous prefix, lobpcg_impl.inc:224-228).  Leaves B X in wA when B != NULL.
+template <typename T>
+int Solver<T>::residual_pass(bool initial) {
+  T* X = Xp();
+  LB2_TRY(apply(opA, k, X, AS));
+  const T* BX = X;
+  if (opB) { LB2_TRY(apply(opB, k, X, wA)); BX = wA; }
+  tm.begin(PH_RESID);
+  LB2_TRY(residual<T>(ctx, n, nev, AS, n, BX, n, Eig, nullptr, 0, Sums));
+  tm.end();
+  if (ctx->comm) LB2_TRY(allreduce_sum(ctx, Sums, nev, kDouble));
+  LB2_TRY(d2h(hbuf, Sums, sizeof(R) * nev));
+  LB2_TRY(d2h(hbuf + nev, Eig, sizeof(R) * k));
+  LB2_TRY(sync());
+  for (int i = 0; i < k; i++) hEig[i] = hbuf[nev + i];
+  const R bn = BNorm > 0 ? BNorm : R(1);
+  for (int i = 0; i < nev; i++) hRes[i] = std::sqrt(hbuf[i]) / (ANorm + std::fabs(hEig[i]) * bn);
+  if (initial) {
+    conv = 0;
+  } else {
+    conv = 0;
+    for (int i = 0; i < nev; i++) {
+      if (hRes[i] > alg->tol) break;
+      conv++;
+    }
+  }
+  return 0;
+}
+
+template <typename T>
+int Solver<T>::init() {
+  ng = (int64_t)alg->size;
+  n = ng;
+  row0 = 0;
+  k = (int)alg->sizeSub;
+  nev = (int)alg->nev;
+  opA = alg->A; opB = alg->B; opT = alg->T_;
+  // parameter validation, same messages as lobpcg_impl.inc:66-75
+  if (!opA) { fprintf(stderr, "lobpcg: A operator must not be NULL\n"); return 1; }
+  if (alg->nev > alg->sizeSub) {
+    fprintf(stderr, "lobpcg: nev (%lu) > sizeSub (%lu)\n", (unsigned long)alg->nev, (unsigned long)alg->sizeSub);
+    return 1;
+  }
+  if (3 * alg->sizeSub > alg->size) {
+    fprintf(stderr, "lobpcg: 3*sizeSub (%lu) > size (%lu)\n", (unsigned long)(3 * alg->sizeSub), (unsigned long)alg->size);
+    return 1;
+  }
+  const BuiltinOp* ba = builtin_of(opA);
+  if (ba && ba->n != ba->n_global) { n = ba->n; }  // row-partitioned operator: local rows
+  if (ctx->comm && ba) { /* row offset = sum of lower ranks' rows; equal slabs */ row0 = (int64_t)comm_rank(ctx) * n; }
+  LB2_CUDA_OK(cudaSetDevice(ctx->device));
+  if (sd_init(ctx)) return 1;
+  LB2_TRY(alloc());
+
+  // X0: device generator, or upload of alg->S[0 : n*k) (rows row0.. of every column when partitioned)
+  cur = 0;
+  T* X = Xp();
+  if (use_device_x0) {
+    LB2_TRY(fill_uniform<T>(ctx, n, k, X, n, device_seed, ng, row0));
+  } else {
+    LB2_CUDA_OK(cudaMemcpy2DAsync(X, sizeof(T) * n, alg->S + row0, sizeof(T) * ng, sizeof(T) * n, k,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+  }
+  LB2_TRY(estimate_norm(opA, 0xA5EEDULL, &ANorm));
+  if (opB) LB2_TRY(estimate_norm(opB, 0xB5EEDULL, &BNorm));
+  else BNorm = 1;
+  if (alg->verbosity > 0) printf("F-Norm: %.5e %.5e\n", (double)ANorm, (double)BNorm);
+
+  LB2_TRY(sumsq_total(k, X, Scal));
+  LB2_TRY(d2h(hbuf, Scal, sizeof(R)));
+  LB2_TRY(sync());
+  if (std::sqrt(hbuf[0]) < (R)EpsTol<T>::v) LB2_TRY(fill_uniform<T>(ctx, n, k, X, n, 0xC0FFEEULL, ng, row0));
+
+  if (int rc = rr_initial()) return rc;
+  LB2_TRY(residual_pass(true));
+  // W for all k columns (iter 0 uses sizeW = sizeSub, lobpcg_impl.inc:134), preconditioned
+  np = 0;
+  nw = k;
+  {
+    T* X2 = Xp();
+    const T* BX = opB ? wA : X2;
+    T* Wdst = col(X2, k);
+    tm.begin(PH_RESID);
+    LB2_TRY(residual<T>(ctx, n, k, AS, n, BX, n, Eig, opT ? wB : Wdst, n, nullptr));
+    tm.end();
+    if (opT) LB2_TRY(apply(opT, k, wB, Wdst));
+  }
+  print_state(false);
+  useOrtho = 0;
+  conv = 0;
+  iter = 0;
+  done = false;
+  inited = true;
+  return 0;
+}
+
+template <typename T>
+int Solver<T>::step(int max_steps) {
+  if (!inited) return -1;
+  int passes = 0;
+  const int rc = step_impl(max_steps, &passes);
+  if (rc != 0) return rc > 0 ? -rc : rc;
+  return passes;
+}
+
+template <typename T>
+int Solver<T>::step_impl(int max_steps, int* passes_out) {
+  int& passes = *passes_out;
+  while (!done && passes < max_steps && iter < alg->maxIter) {
+    T* S = Xp();
+    T* V = S;
+    T* W = col(S, k + np);
+    // orthogonalise W against [X, P_act]
+    if (useOrtho) {
+      int keep = nw;
+      LB2_TRY(ortho_drop(W, nw, V, k + np, &keep));
+      nw = keep;
+    }
+    int m = k + np + nw;
+    if (int rc = rr_modified(m, k)) return rc;
+    if (useOrtho == 2) {
+      useOrtho = 1;
+      int keep = nw;
+      LB2_TRY(ortho_drop(W, nw, V, k + np, &keep));
+      nw = keep;
+      m = k + np + nw;
+      if (int rc = rr_modified(m, k)) return rc;
+    }
+    // X_new = S Cx into the other slab
+    T* Sn = slab[1 - cur];
+    LB2_TRY(nn(m, k, make<T>(1), S, Cx, m, zero<T>(), Sn));
+    cur = 1 - cur;
+    LB2_TRY(residual_pass(false));
+    if (alg->verbosity > 0) print_state(true);
+    passes++;
+    if (conv == (uint64_t)nev) {
+      done = true;
+      break;
+    }
+    // P_act and W_act only for the unconverged columns, written at their compacted positions
+    const int nconv = (int)conv;
+    const int nact = k - nconv;
+    T* Sold = slab[1 - cur];
+    LB2_TRY(nn(m, nact, make<T>(1), Sold, Cp + (size_t)nconv * m, m, zero<T>(), col(Sn, k)));
+    {
+      const T* BX = opB ? wA : Sn;
+      T* Wdst = col(Sn, k + nact);
+      tm.begin(PH_RESID);
+      LB2_TRY(residual<T>(ctx, n, nact, col(AS, nconv), n, BX + (int64_t)nconv * n, n, Eig + nconv,
+                          opT ? wB : Wdst, n, nullptr));
+      tm.end();
+      if (opT) LB2_TRY(apply(opT, nact, wB, Wdst));
+    }
+    np = nact;
+    nw = nact;
+    iter++;
+  }
+  LB2_TRY(sync());
+  return 0;
+}
+
+template <typename T>
+int Solver<T>::finish() {
+  if (!inited) return 1;
+  T* X = Xp();
+  LB2_CUDA_OK(cudaMemcpy2DAsync(alg->S + row0, sizeof(T) * ng, X, sizeof(T) * n, sizeof(T) * n, k,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  LB2_TRY(sync());
+  for (int i = 0; i < k; i++) alg->eigVals[i] = hEig[i];
+  for (int i = 0; i < nev; i++) alg->resNorm[i] = hRes[i];
+  alg->converged = conv;
+  alg->iter = iter;
+  return 0;
+}
+
+SolverBase* make_solver(lb2_ctx* ctx, char prefix, void* alg, int indefinite) {
+  switch (prefix) {
+    case 's': return new Solver<float>(ctx, (State<float>*)alg, indefinite != 0);
+    case 'd': return new Solver<double>(ctx, (State<double>*)alg, indefinite != 0);
+    case 'c': return new Solver<c32>(ctx, (State<c32>*)alg, indefinite != 0);
+    case 'z': return new Solver<c64>(ctx, (State<c64>*)alg, indefinite != 0);
+  }
+  return nullptr;
+}
+
+}  // namespace lb2
