@@ -82,6 +82,10 @@ int lb2_solver_set_device_x0(lb2_solver *s, uint64_t seed);
 int lb2_solver_num_stats(void);
 const char *lb2_solver_stat_name(int i);
 double lb2_solver_stat(lb2_solver *s, int i);
+/* algorithmic work of the phase: flops for gram / tall_nn, bytes for spmm / residual */
+double lb2_solver_stat_work(lb2_solver *s, int i);
+unsigned long long lb2_solver_stat_calls(lb2_solver *s, int i);
+void lb2_solver_reset_stats(lb2_solver *s);
 int lb2_solver_state(lb2_solver *s, uint64_t *iter, uint64_t *converged, int *use_ortho);
 
 /* ---- (3) kernels on device pointers -------------------------------------------------------------- */
@@ -111,6 +115,15 @@ LB2_DECLARE_KERNELS(s)
 LB2_DECLARE_KERNELS(d)
 LB2_DECLARE_KERNELS(c)
 LB2_DECLARE_KERNELS(z)
+
+/* ---- multi-GPU (one process per GPU; rows of all block vectors are partitioned) -------------------- */
+int lb2_comm_unique_id(void *out128, const char *nccl_lib_path);   /* rank 0; broadcast by the launcher */
+int lb2_ctx_attach_comm(lb2_ctx *ctx, int rank, int size, const void *unique_id128, const char *nccl_lib_path);
+int lb2_ctx_detach_comm(lb2_ctx *ctx);
+int lb2_comm_allreduce(lb2_ctx *ctx, void *dev_buf, size_t count, int is_double);
+int lb2_ipc_get_handle(void *dev_ptr, void *out64);
+void *lb2_ipc_open_handle(const void *in64);
+int lb2_ipc_close_handle(void *mapped_ptr);
 
 const char *lb2_version(void);
 

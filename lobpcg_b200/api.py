@@ -84,6 +84,11 @@ def _declare(L):
     L.lb2_solver_stat_name.argtypes = [ci]
     L.lb2_solver_stat.restype = dbl
     L.lb2_solver_stat.argtypes = [vp, ci]
+    L.lb2_solver_stat_work.restype = dbl
+    L.lb2_solver_stat_work.argtypes = [vp, ci]
+    L.lb2_solver_stat_calls.restype = C.c_ulonglong
+    L.lb2_solver_stat_calls.argtypes = [vp, ci]
+    L.lb2_solver_reset_stats.argtypes = [vp]
     L.lb2_solver_state.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(ci)]
     L.lb2_comm_unique_id.argtypes = [vp, C.c_char_p]
     L.lb2_ctx_attach_comm.argtypes = [vp, ci, ci, vp, C.c_char_p]
@@ -457,8 +462,17 @@ class Solver:
         return dict(iter=it.value, converged=cv.value, use_ortho=uo.value)
 
     def stats(self) -> dict:
+        """{phase: dict(ms, work, calls)}; work = algorithmic flops (gram, tall_nn) or bytes (spmm, residual)."""
         L = lib()
-        return {L.lb2_solver_stat_name(i).decode(): L.lb2_solver_stat(self.h, i) for i in range(L.lb2_solver_num_stats())}
+        out = {}
+        for i in range(L.lb2_solver_num_stats()):
+            name = L.lb2_solver_stat_name(i).decode().replace("_ms", "")
+            out[name] = dict(ms=L.lb2_solver_stat(self.h, i), work=L.lb2_solver_stat_work(self.h, i),
+                             calls=int(L.lb2_solver_stat_calls(self.h, i)))
+        return out
+
+    def reset_stats(self):
+        lib().lb2_solver_reset_stats(self.h)
 
     def close(self):
         if self.h:

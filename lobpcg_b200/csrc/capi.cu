@@ -316,6 +316,12 @@ const char* lb2_solver_stat_name(int i) {
   return (i >= 0 && i < PH_COUNT) ? names[i] : "";
 }
 double lb2_solver_stat(lb2_solver* s, int i) { return (s && i >= 0 && i < PH_COUNT) ? s->impl->phase_ms[i] : 0.0; }
+double lb2_solver_stat_work(lb2_solver* s, int i) { return (s && i >= 0 && i < PH_COUNT) ? s->impl->phase_work[i] : 0.0; }
+unsigned long long lb2_solver_stat_calls(lb2_solver* s, int i) { return (s && i >= 0 && i < PH_COUNT) ? s->impl->phase_calls[i] : 0ULL; }
+void lb2_solver_reset_stats(lb2_solver* s) {
+  if (!s) return;
+  for (int i = 0; i < PH_COUNT; i++) { s->impl->phase_ms[i] = 0; s->impl->phase_work[i] = 0; s->impl->phase_calls[i] = 0; }
+}
 int lb2_solver_state(lb2_solver* s, uint64_t* iter, uint64_t* converged, int* use_ortho) {
   if (!s) return -1;
   s->impl->state(iter, converged, use_ortho);

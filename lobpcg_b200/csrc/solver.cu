@@ -151,6 +151,14 @@ class Solver : public SolverBase {
   int gram_ar(int ma, int mb, const T* A, const T* B, T* Gout, int upper);
   int nn(int kd, int nb, T alpha, const T* S, const T* C, int ldc, T beta, T* Out);
   int sumsq_total(int nc, const T* X, R* out_dev);  // out_dev[0] = ||X||_F^2 (all ranks)
+  int resid(int nc, const T* AXp, const T* BXp, const R* lam, T* Wp, R* ss) {
+    tm.begin(PH_RESID);
+    int rc = residual<T>(ctx, n, nc, AXp, n, BXp, n, lam, Wp, n, ss);
+    tm.end();
+    phase_work[PH_RESID] += (Wp ? 3.0 : 2.0) * (double)n * nc * sizeof(T);
+    phase_calls[PH_RESID]++;
+    return rc;
+  }
   int estimate_norm(const LinOpRaw* op, uint64_t seed, R* out);
   int gram_self_B(int m, T* S, T* Gout);             // S^H B S (mirrored)
   int chol_transform(int m, int* bad);               // G -> D, R (in G), DinvR ; bad=1 if potrf failed or rcond small
@@ -213,6 +221,11 @@ int Solver<T>::apply(const LinOpRaw* op, int nc, const T* X, T* Y) {
     tm.begin(PH_SPMM);
     int rc = apply_builtin<T>(ctx, b, nc, X, n, Y, n);
     tm.end();
+    double bytes = 2.0 * (double)n * nc * sizeof(T);
+    if (b->kind == OP_CSR) bytes += (double)b->nnz * (sizeof(T) + 4) + 8.0 * (double)(b->n + 1);
+    if (b->kind == OP_DIAG) bytes += (double)n * sizeof(R);
+    phase_work[PH_SPMM] += bytes;
+    phase_calls[PH_SPMM]++;
     return rc;
   }
   if (!hX) {
@@ -236,6 +249,8 @@ int Solver<T>::gram_ar(int ma, int mb, const T* A, const T* B, T* Gout, int uppe
   tm.begin(PH_GRAM);
   int rc = gram<T>(ctx, n, ma, mb, A, n, B, n, Gout, ma, upper);
   tm.end();
+  phase_work[PH_GRAM] += (Sc<T>::cplx ? 4.0 : 1.0) * (double)n * ma * (upper ? (double)(ma + 1) : 2.0 * mb);
+  phase_calls[PH_GRAM]++;
   if (rc) return rc;
   if (ctx->comm) {
     tm.begin(PH_COMM);
@@ -250,6 +265,8 @@ int Solver<T>::nn(int kd, int nb, T alpha, const T* S, const T* C, int ldc, T be
   tm.begin(PH_TALLNN);
   int rc = tall_nn<T>(ctx, n, kd, nb, alpha, S, n, C, ldc, beta, Out, n);
   tm.end();
+  phase_work[PH_TALLNN] += (Sc<T>::cplx ? 8.0 : 2.0) * (double)n * kd * nb;
+  phase_calls[PH_TALLNN]++;
   return rc;
 }
 
@@ -260,6 +277,8 @@ int Solver<T>::sumsq_total(int nc, const T* X, R* out_dev) {
   int rc = col_sumsq<T>(ctx, n, nc, X, n, Sums);
   if (!rc) rc = sum_reals<R>(ctx, nc, Sums, out_dev);
   tm.end();
+  phase_work[PH_RESID] += (double)n * nc * sizeof(T);
+  phase_calls[PH_RESID]++;
   if (!rc && ctx->comm) rc = allreduce_sum(ctx, out_dev, 1, kDouble);
   return rc;
 }
@@ -544,9 +563,7 @@ int Solver<T>::residual_pass(bool initial) {
   LB2_TRY(apply(opA, k, X, AS));
   const T* BX = X;
   if (opB) { LB2_TRY(apply(opB, k, X, wA)); BX = wA; }
-  tm.begin(PH_RESID);
-  LB2_TRY(residual<T>(ctx, n, nev, AS, n, BX, n, Eig, nullptr, 0, Sums));
-  tm.end();
+  LB2_TRY(resid(nev, AS, BX, Eig, nullptr, Sums));
   if (ctx->comm) LB2_TRY(allreduce_sum(ctx, Sums, nev, kDouble));
   LB2_TRY(d2h(hbuf, Sums, sizeof(R) * nev));
   LB2_TRY(d2h(hbuf + nev, Eig, sizeof(R) * k));
@@ -619,9 +636,7 @@ int Solver<T>::init() {
     T* X2 = Xp();
     const T* BX = opB ? wA : X2;
     T* Wdst = col(X2, k);
-    tm.begin(PH_RESID);
-    LB2_TRY(residual<T>(ctx, n, k, AS, n, BX, n, Eig, opT ? wB : Wdst, n, nullptr));
-    tm.end();
+    LB2_TRY(resid(k, AS, BX, Eig, opT ? wB : Wdst, nullptr));
     if (opT) LB2_TRY(apply(opT, k, wB, Wdst));
   }
   print_state(false);
@@ -684,10 +699,7 @@ int Solver<T>::step_impl(int max_steps, int* passes_out) {
     {
       const T* BX = opB ? wA : Sn;
       T* Wdst = col(Sn, k + nact);
-      tm.begin(PH_RESID);
-      LB2_TRY(residual<T>(ctx, n, nact, col(AS, nconv), n, BX + (int64_t)nconv * n, n, Eig + nconv,
-                          opT ? wB : Wdst, n, nullptr));
-      tm.end();
+      LB2_TRY(resid(nact, col(AS, nconv), BX + (int64_t)nconv * n, Eig + nconv, opT ? wB : Wdst, nullptr));
       if (opT) LB2_TRY(apply(opT, nact, wB, Wdst));
     }
     np = nact;

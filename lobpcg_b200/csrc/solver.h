@@ -99,6 +99,8 @@ struct SolverBase {
   virtual int finish() = 0;
   virtual void state(uint64_t* iter, uint64_t* conv, int* use_ortho) = 0;
   double phase_ms[PH_COUNT] = {0};
+  double phase_work[PH_COUNT] = {0};   // algorithmic flops (gram, tall_nn) or bytes (spmm, residual)
+  uint64_t phase_calls[PH_COUNT] = {0};
   uint64_t device_seed = 0;
   bool use_device_x0 = false;
 };

@@ -1,0 +1,104 @@
+"""Drop-in boundary checks that need no GPU: the shared library loads, exports every symbol the headers
+declare, and the state / operator structs have the reference's layout."""
+import ctypes as C
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from lobpcg_b200 import api
+
+ROOT = Path(__file__).resolve().parent.parent
+INC = ROOT / "include"
+REFROOT = Path("/root/reference")
+
+PROBE = r"""
+#include <stdio.h>
+#include <stddef.h>
+%s
+#define F(TY, f) printf(#TY "." #f " %%zu\n", offsetof(TY, f));
+#define STATE(TY) printf(#TY " %%zu\n", sizeof(TY)); F(TY,S) F(TY,Cx) F(TY,Cp) F(TY,AX) F(TY,AS) F(TY,BS) \
+  F(TY,eigVals) F(TY,resNorm) F(TY,signature) F(TY,wrk1) F(TY,wrk2) F(TY,wrk3) F(TY,wrk4) F(TY,rr_D) \
+  F(TY,rr_eigvals) F(TY,rr_tau) F(TY,rr_VR) F(TY,rr_sig) F(TY,rr_indices) F(TY,rr_ggev) \
+  F(TY,implicit_product_update) F(TY,verbosity) F(TY,iter) F(TY,nev) F(TY,converged) F(TY,size) F(TY,sizeSub) \
+  F(TY,maxIter) F(TY,tol) F(TY,A) F(TY,B) F(TY,T)
+#define OP(TY) printf(#TY " %%zu\n", sizeof(TY)); F(TY,rows) F(TY,cols) F(TY,matvec) F(TY,cleanup) F(TY,ctx)
+int main(void) {
+  STATE(s_lobpcg_t) STATE(d_lobpcg_t) STATE(c_lobpcg_t) STATE(z_lobpcg_t)
+  OP(LinearOperator_s_t) OP(LinearOperator_d_t) OP(LinearOperator_c_t) OP(LinearOperator_z_t)
+  printf("linop_ctx_t %%zu\n", sizeof(linop_ctx_t));
+  return 0;
+}
+"""
+
+
+def _layout(includes, flags, tmp_path, name):
+    src = tmp_path / f"{name}.c"
+    src.write_text(PROBE % includes)
+    exe = tmp_path / name
+    subprocess.run(["gcc", "-std=c11", "-w", *flags, str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    return dict(line.rsplit(" ", 1) for line in out.strip().splitlines())
+
+
+def test_library_loads_and_exports_declared_symbols():
+    L = api.lib()
+    assert b"sm_100a" in L.lb2_version()
+    hdr = (INC / "lobpcg_b200.h").read_text()
+    names = set(re.findall(r"\b(lb2_[a-z0-9_]+)\s*\(", hdr))
+    names = {n for n in names if "##" not in n}
+    kern = set(re.findall(r"lb2_##P##_([a-z0-9_]+)\(", hdr))
+    assert {"gram", "tall_nn", "residual", "col_sumsq", "fill_uniform", "spmm_stencil", "spmm_csr", "spmm_diag"} <= kern
+    for p in "sdcz":
+        names |= {f"lb2_{p}_{k}" for k in kern}
+        names |= {f"{p}_lobpcg", f"{p}_ilobpcg", f"lb2_{p}_state_alloc", f"lb2_{p}_state_free"}
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, f"declared in include/ but not exported: {missing}"
+    assert len(names) >= 80
+
+
+def test_state_struct_matches_ctypes_mirror(tmp_path):
+    ours = _layout('#include "lobpcg.h"', [f"-I{INC}"], tmp_path, "ours")
+    for p in "sdcz":
+        S = api._state_struct(p)
+        assert int(ours[f"{p}_lobpcg_t"]) == C.sizeof(S)
+        for f, _ in S._fields_:
+            assert int(ours[f"{p}_lobpcg_t.{f}"]) == getattr(S, f).offset, (p, f)
+    assert int(ours["LinearOperator_d_t"]) == C.sizeof(api.LinOpStruct)
+    assert int(ours["linop_ctx_t"]) == C.sizeof(api.LinOpCtx)
+
+
+@pytest.mark.skipif(not REFROOT.exists(), reason="reference tree only exists in the build container")
+def test_state_struct_matches_reference_header(tmp_path):
+    ours = _layout('#include "lobpcg.h"', [f"-I{INC}"], tmp_path, "ours")
+    ref = _layout('#include "lobpcg/linop.h"\n#include "lobpcg.h"',
+                  [f"-I{REFROOT}", f"-I{REFROOT}/include", f"-I{REFROOT}/include/lobpcg"], tmp_path, "ref")
+    assert ours == ref
+
+
+def test_c11_generic_front_end_compiles_and_links(tmp_path):
+    """A reference-style C11 caller (lobpcg(alg) through _Generic, linop_create, <p>_lobpcg_alloc) builds
+    against include/lobpcg.h and links to the shared library; it is only run on a GPU box (test_gpu_solver)."""
+    src = ROOT / "tests" / "c_caller" / "caller.c"
+    exe = tmp_path / "caller"
+    libdir = api.LIB_PATH.parent
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", f"-I{INC}", str(src), "-o", str(exe), f"-L{libdir}",
+                    "-llobpcg_b200", f"-Wl,-rpath,{libdir}", "-lm"], check=True)
+    assert exe.exists()
+
+
+def test_no_cpu_fallback_without_library(monkeypatch, tmp_path):
+    monkeypatch.setattr(api, "_lib", None)
+    monkeypatch.setattr(api, "LIB_PATH", tmp_path / "missing.so")
+    with pytest.raises(api.LobpcgB200Error):
+        api.lib()
+
+
+def test_product_never_imports_oracle():
+    for py in (ROOT / "lobpcg_b200").rglob("*.py"):
+        txt = py.read_text()
+        assert "oracle" not in re.sub(r'""".*?"""', "", txt, flags=re.S).replace("# oracle", ""), py
+    for cu in (ROOT / "lobpcg_b200" / "csrc").iterdir():
+        assert "oracle/" not in cu.read_text(), cu

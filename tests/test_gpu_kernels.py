@@ -1,0 +1,252 @@
+"""GPU parity tests of the individual kernels, through the C ABI (lobpcg_b200.api -> liblobpcg_b200.so),
+against the CPU oracle (oracle/numpy_oracle.py) and the reference's golden vectors.
+
+Tolerances: the kernels are floating point; sums are re-associated (split-n partial tiles, DMMA fragment
+order), so parity is `rtol` relative to the magnitude of the result: 1e-12 (d,z), 2e-5 (s,c).  Generators
+and integer index work (fill_uniform) are bit-exact."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from lobpcg_b200 import api
+from lobpcg_b200 import problems as pr
+from oracle import numpy_oracle as no
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+KA = json.loads((GOLD / "known_answers.json").read_text())
+REF = np.load(GOLD / "reference_runs.npz")
+DTYPES = [np.float64, np.float32, np.complex128, np.complex64]
+
+
+def rtol(dt):
+    return 1e-12 if np.dtype(dt) in (np.dtype(np.float64), np.dtype(np.complex128)) else 2e-5
+
+
+def rand(rng, shape, dt):
+    a = rng.standard_normal(shape)
+    if np.dtype(dt).kind == "c":
+        a = a + 1j * rng.standard_normal(shape)
+    return np.asfortranarray(a.astype(dt))
+
+
+def close(got, ref, tol):
+    scale = max(float(np.abs(ref).max()), 1e-30) if ref.size else 1.0
+    err = float(np.abs(got - ref).max()) / scale if ref.size else 0.0
+    assert err < tol, f"rel err {err:.3e} >= {tol:.1e}"
+
+
+# ------------------------------------------------------------------------------------------------ Gram
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(1, 1, 1), (37, 3, 5), (4099, 20, 20), (30001, 64, 33), (20000, 150, 129),
+                                   (8193, 260, 7)])
+def test_gram_matches_oracle(ctx, dt, shape):
+    n, ma, mb = shape
+    rng = np.random.default_rng(n + ma)
+    A, B = rand(rng, (n, ma), dt), rand(rng, (n, mb), dt)
+    dA, dB = api.DeviceArray.from_numpy(ctx, A), api.DeviceArray.from_numpy(ctx, B)
+    close(api.gram(ctx, dA, dB).numpy(ctx), no.gram_cross(A, B), rtol(dt))
+    G = api.gram(ctx, dA, dA, upper=True).numpy(ctx)
+    full = A.conj().T @ A
+    close(np.triu(G), no.gram_self(A), rtol(dt))       # reference semantics: upper triangle (syrk/herk)
+    close(G, full, rtol(dt))                            # ours additionally mirrors => full Hermitian matrix
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_gram_padded_leading_dimension_and_odd_alignment(ctx, dt):
+    """ld > n, odd ld and an odd column offset force the non-vectorised cp.async path."""
+    rng = np.random.default_rng(5)
+    n, ma = 5001, 70
+    A = rand(rng, (n, ma), dt)
+    dA = api.DeviceArray.from_numpy(ctx, A, ld=n + 6)
+    close(api.gram(ctx, dA, dA, upper=True).numpy(ctx), A.conj().T @ A, rtol(dt))
+    dB = api.DeviceArray.from_numpy(ctx, A, ld=n + 1)
+    close(api.gram(ctx, dB, dA).numpy(ctx), A.conj().T @ A, rtol(dt))
+
+
+def test_gram_known_answers_from_reference_tests(ctx):
+    k = KA["gram_self_d_general"]                      # reference tests/test_gram.c:156-174
+    U = np.asfortranarray(np.array(k["U"], dtype=np.float64))
+    G = api.gram(ctx, api.DeviceArray.from_numpy(ctx, U), api.DeviceArray.from_numpy(ctx, U), upper=True).numpy(ctx)
+    assert abs(G[0, 0] - 2.0) < 1e-12 and abs(G[0, 1] - 1.0) < 1e-12 and abs(G[1, 1] - 2.0) < 1e-12
+    k = KA["gram_self_z_with_B"]                       # tests/test_gram.c:203-227: G = U^H B U
+    U = np.asfortranarray(np.array(k["U_re"], dtype=np.complex128) + 1j * np.array(k["U_im"]))
+    B = api.diag_op(np.array(k["Bdiag"]), np.complex128)
+    dU = api.DeviceArray.from_numpy(ctx, U)
+    G = api.gram(ctx, dU, B.apply(ctx, dU)).numpy(ctx)
+    assert abs(G[0, 0] - 4.0) < 1e-12 and abs(G[0, 1]) < 1e-12 and abs(G[1, 1] - 6.0) < 1e-12
+
+
+def test_gram_is_deterministic(ctx):
+    rng = np.random.default_rng(1)
+    A = rand(rng, (50000, 96), np.float64)
+    dA = api.DeviceArray.from_numpy(ctx, A)
+    G1 = api.gram(ctx, dA, dA, upper=True).numpy(ctx)
+    G2 = api.gram(ctx, dA, dA, upper=True).numpy(ctx)
+    assert np.array_equal(G1, G2)
+
+
+def test_gram_simt_and_dmma_paths_agree(ctx):
+    rng = np.random.default_rng(2)
+    A, B = rand(rng, (12345, 130), np.float64), rand(rng, (12345, 90), np.float64)
+    dA, dB = api.DeviceArray.from_numpy(ctx, A), api.DeviceArray.from_numpy(ctx, B)
+    G1 = api.gram(ctx, dA, dB).numpy(ctx)
+    for tile in (64, 128):
+        ctx.set_option("gram_tile", tile)
+        close(api.gram(ctx, dA, dB).numpy(ctx), G1, 1e-13)
+    ctx.set_option("gram_tile", 0)
+    ctx.set_option("force_simt", 1)
+    G2 = api.gram(ctx, dA, dB).numpy(ctx)
+    ctx.set_option("force_simt", 0)
+    close(G2, G1, 1e-13)
+
+
+# ------------------------------------------------------------------------------------------------ tall NN
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(1, 1, 1), (130, 5, 3), (4097, 60, 40), (30001, 33, 129), (9000, 300, 70)])
+@pytest.mark.parametrize("ab", [(1.0, 0.0), (-1.0, 1.0)])
+def test_tall_nn_matches_oracle(ctx, dt, shape, ab):
+    n, kd, nb = shape
+    rng = np.random.default_rng(n + kd + nb)
+    S, Cm, O0 = rand(rng, (n, kd), dt), rand(rng, (kd, nb), dt), rand(rng, (n, nb), dt)
+    dO = api.DeviceArray.from_numpy(ctx, O0)
+    api.tall_nn(ctx, api.DeviceArray.from_numpy(ctx, S), api.DeviceArray.from_numpy(ctx, Cm), dO, alpha=ab[0], beta=ab[1])
+    close(dO.numpy(ctx), ab[0] * (S @ Cm) + ab[1] * O0, rtol(dt) * 10)
+
+
+def test_tall_nn_beta_zero_ignores_nan_output(ctx):
+    rng = np.random.default_rng(3)
+    S, Cm = rand(rng, (3000, 40), np.float64), rand(rng, (40, 24), np.float64)
+    dO = api.DeviceArray.from_numpy(ctx, np.full((3000, 24), np.nan))
+    api.tall_nn(ctx, api.DeviceArray.from_numpy(ctx, S), api.DeviceArray.from_numpy(ctx, Cm), dO, 1.0, 0.0)
+    close(dO.numpy(ctx), S @ Cm, 1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ residual
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(1, 1), (777, 3), (100003, 17)])
+def test_residual_and_norms_match_oracle(ctx, dt, shape):
+    n, nc = shape
+    rng = np.random.default_rng(n)
+    AX, BX = rand(rng, (n, nc), dt), rand(rng, (n, nc), dt)
+    lam = rng.standard_normal(nc).astype(api.REAL[api.PREFIX[np.dtype(dt)]])
+    W, ss = api.residual(ctx, api.DeviceArray.from_numpy(ctx, AX), api.DeviceArray.from_numpy(ctx, BX),
+                         api.DeviceArray.from_numpy(ctx, lam))
+    Wr = no.get_residual(BX, AX, lam)      # oracle: W = AX - X diag(lam) with X := BX
+    close(W.numpy(ctx), Wr, rtol(dt))
+    close(ss.numpy(ctx), np.linalg.norm(Wr, axis=0) ** 2, rtol(dt) * 10)
+    _, ss2 = api.residual(ctx, api.DeviceArray.from_numpy(ctx, AX), api.DeviceArray.from_numpy(ctx, BX),
+                          api.DeviceArray.from_numpy(ctx, lam), write=False)
+    assert np.array_equal(ss.numpy(ctx), ss2.numpy(ctx))
+    close(api.col_sumsq(ctx, api.DeviceArray.from_numpy(ctx, AX)).numpy(ctx), np.linalg.norm(AX, axis=0) ** 2, rtol(dt) * 10)
+
+
+def test_residual_known_answer_from_reference_tests(ctx):
+    k = KA["residual_noneigvec_real"]                  # tests/test_residual.c:277-300: R = [-1, 0, 3]
+    x = np.array(k["x"])[:, None]
+    ax = np.array(k["Adiag"])[:, None] * x
+    W, ss = api.residual(ctx, api.DeviceArray.from_numpy(ctx, ax), api.DeviceArray.from_numpy(ctx, x),
+                         api.DeviceArray.from_numpy(ctx, np.array([k["lambda"]])))
+    assert np.allclose(W.numpy(ctx)[:, 0], k["R"], atol=1e-15)
+    assert abs(np.sqrt(ss.numpy(ctx)[0]) / (3.0 + 2.0) - np.sqrt(10.0) / 5.0) < 1e-15   # test_residual.c:450-529
+
+
+# ------------------------------------------------------------------------------------------------ generator
+@pytest.mark.parametrize("dt", DTYPES)
+def test_fill_uniform_is_bit_exact_with_host_generator(ctx, dt):
+    n, k = 1237, 5
+    X = api.fill_uniform(ctx, n, k, dt, seed=7).numpy(ctx)
+    assert np.array_equal(X, pr.initial_block(n, k, 7, dt))
+    # row-partitioned fill reproduces the same global block (multi-GPU invariance)
+    lo = api.fill_uniform(ctx, 600, k, dt, seed=7, n_global=n, row0=0).numpy(ctx)
+    hi = api.fill_uniform(ctx, n - 600, k, dt, seed=7, n_global=n, row0=600).numpy(ctx)
+    assert np.array_equal(np.vstack([lo, hi]), X)
+
+
+# ------------------------------------------------------------------------------------------------ SpMM
+GRIDS = [(1,), (5,), (300,), (33, 7), (100, 100), (7, 5, 3), (32, 8, 16), (45, 37, 29), (64, 64, 64)]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("grid", GRIDS)
+def test_stencil_and_csr_match_oracle(ctx, dt, grid):
+    n = int(np.prod(grid))
+    rng = np.random.default_rng(n)
+    for nc in (1, 6):
+        X = rand(rng, (n, nc), dt)
+        ref = no.op_stencil(grid)(X)
+        dX = api.DeviceArray.from_numpy(ctx, X)
+        close(api.stencil_op(grid, dt).apply(ctx, dX).numpy(ctx), ref, rtol(dt))
+        rp, c, v = pr.laplacian_csr(grid)
+        close(api.csr_op(rp, c, v.astype(dt)).apply(ctx, dX).numpy(ctx), ref, rtol(dt))
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+def test_stencil_with_potential_and_diag_operator(ctx, dt):
+    grid = (21, 17, 13)
+    n = int(np.prod(grid))
+    rng = np.random.default_rng(9)
+    X = rand(rng, (n, 5), dt)
+    pot = pr.harmonic_potential(grid, 0.3)
+    dX = api.DeviceArray.from_numpy(ctx, X)
+    close(api.stencil_op(grid, dt, potential=pot).apply(ctx, dX).numpy(ctx), no.op_stencil(grid, potential=pot)(X), 1e-13)
+    d = pr.mass_diagonal(n)
+    close(api.diag_op(d, dt).apply(ctx, dX).numpy(ctx), d[:, None] * X, 1e-15)
+
+
+def test_csr_general_sparsity_and_wide_blocks(ctx):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(4)
+    n = 5000
+    M = sp.random(n, n, density=0.002, random_state=3, format="csr") + sp.eye(n, format="csr") * 3.0
+    M = M.tocsr(); M.sort_indices()
+    X = rand(rng, (n, 45), np.float64)
+    op = api.csr_op(M.indptr, M.indices, M.data)
+    dX = api.DeviceArray.from_numpy(ctx, X)
+    for cols in (0, 4, 8, 16, 32):
+        ctx.set_option("spmm_cols", cols)
+        close(op.apply(ctx, dX).numpy(ctx), M @ X, 1e-13)
+    ctx.set_option("spmm_cols", 0)
+
+
+def test_bdg_operator_matches_dense_blocks(ctx):
+    grid = (6, 5, 4)
+    m = int(np.prod(grid))
+    K = no.op_stencil(grid)
+    shift, d = 0.5, 0.5 * np.exp(0.7j)
+    rng = np.random.default_rng(6)
+    X = rand(rng, (2 * m, 3), np.complex128)
+    u, v = X[:m], X[m:]
+    ref = np.vstack([K(u) + shift * u + d * v, np.conj(d) * u + K(v) + shift * v])
+    got = api.bdg_op(grid, np.complex128, shift, d).apply(ctx, api.DeviceArray.from_numpy(ctx, X)).numpy(ctx)
+    close(got, ref, 1e-13)
+
+
+def test_stencil_linearity_at_full_size(ctx):
+    """Size-independent property at the BASELINE size (160^3): A(aX + bY) = a AX + b AY and symmetry
+    <X, A Y> = <A X, Y>, checked through Gram kernels so that nothing leaves the device but 2x2 matrices."""
+    g = (160, 160, 160)
+    n = g[0] ** 3
+    A = api.stencil_op(g, np.float64)
+    X = api.fill_uniform(ctx, n, 2, np.float64, seed=1)
+    AX = A.apply(ctx, X)
+    G1 = api.gram(ctx, X, AX).numpy(ctx)          # X^T A X must be symmetric
+    assert abs(G1[0, 1] - G1[1, 0]) < 1e-10 * abs(G1).max()
+    Cm = api.DeviceArray.from_numpy(ctx, np.array([[2.0], [-3.0]]))
+    Z = api.DeviceArray((n, 1), np.float64)
+    api.tall_nn(ctx, X, Cm, Z)                    # Z = 2 x0 - 3 x1
+    AZ = A.apply(ctx, Z)
+    AZ2 = api.DeviceArray((n, 1), np.float64)
+    api.tall_nn(ctx, AX, Cm, AZ2)
+    diff = api.DeviceArray((n, 1), np.float64)
+    one = api.DeviceArray.from_numpy(ctx, np.array([1.0]))
+    W, ss = api.residual(ctx, AZ, AZ2, one)       # AZ - 1*AZ2
+    assert np.sqrt(ss.numpy(ctx)[0]) < 1e-12 * np.sqrt(api.col_sumsq(ctx, AZ).numpy(ctx)[0])
+    # analytic check: constant-one vector -> interior rows give 0, faces give boundary counts
+    ones = api.DeviceArray.from_numpy(ctx, np.ones((n, 1)))
+    s = api.col_sumsq(ctx, A.apply(ctx, ones)).numpy(ctx)[0]
+    gi = g[0]
+    expected = 6 * (gi - 2) ** 2 * 1 + 12 * (gi - 2) * 4 + 8 * 9
+    assert abs(s - expected) < 1e-9 * expected
