@@ -72,6 +72,7 @@ int lb2_op_apply(lb2_ctx *ctx, const void *linop, char prefix, int nc, const voi
  * step(k) = at most k passes of that loop (stops early on convergence, returns passes done or <0);
  * finish = download X, eigVals, resNorm, converged, iter into alg. */
 lb2_solver *lb2_solver_create(lb2_ctx *ctx, char prefix, void *alg, int indefinite);
+int lb2_solver_prepare(lb2_solver *s); /* validate + allocate only (called by init if not done before) */
 int lb2_solver_init(lb2_solver *s);
 int lb2_solver_step(lb2_solver *s, int max_steps);
 int lb2_solver_finish(lb2_solver *s);
@@ -106,6 +107,11 @@ int lb2_solver_state(lb2_solver *s, uint64_t *iter, uint64_t *converged, int *us
   int lb2_##P##_spmm_stencil(lb2_ctx *ctx, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff,  \
                              const void *potential, int nc, const void *X, int64_t ldx, void *Y,           \
                              int64_t ldy);                                                                 \
+  /* same with z-halo planes (column stride halo_ld) below z=0 / above z=gz-1; NULL = Dirichlet */        \
+  int lb2_##P##_spmm_stencil_halo(lb2_ctx *ctx, int64_t gx, int64_t gy, int64_t gz, double cdiag,          \
+                                  double coff, const void *potential, const void *halo_lo,                 \
+                                  const void *halo_hi, int64_t halo_ld, int nc, const void *X, int64_t ldx, \
+                                  void *Y, int64_t ldy);                                                   \
   int lb2_##P##_spmm_csr(lb2_ctx *ctx, int64_t n, const int64_t *rowptr, const int32_t *col,               \
                          const void *val, int nc, const void *X, int64_t ldx, void *Y, int64_t ldy);       \
   int lb2_##P##_spmm_diag(lb2_ctx *ctx, int64_t n, const void *diag, int nc, const void *X, int64_t ldx,   \
@@ -117,6 +123,13 @@ LB2_DECLARE_KERNELS(c)
 LB2_DECLARE_KERNELS(z)
 
 /* ---- multi-GPU (one process per GPU; rows of all block vectors are partitioned) -------------------- */
+/* rank-local z-slab [z0, z0+gz_local) of a gx*gy*gz_global stencil; alg->size stays the GLOBAL row count */
+void *lb2_op_stencil_slab(char prefix, int64_t gx, int64_t gy, int64_t gz_local, int64_t gz_global, int64_t z0,
+                          double cdiag, double coff, const void *potential_local_host);
+/* the solver keeps every tall block in one device arena; neighbours map it through CUDA IPC and the stencil
+ * kernel reads their boundary planes directly over NVLink */
+int lb2_solver_arena(lb2_solver *s, void **ptr, size_t *bytes);
+int lb2_solver_set_peers(lb2_solver *s, const void *lo_arena, const void *hi_arena);
 int lb2_comm_unique_id(void *out128, const char *nccl_lib_path);   /* rank 0; broadcast by the launcher */
 int lb2_ctx_attach_comm(lb2_ctx *ctx, int rank, int size, const void *unique_id128, const char *nccl_lib_path);
 int lb2_ctx_detach_comm(lb2_ctx *ctx);

@@ -78,6 +78,11 @@ def _declare(L):
     for f in ("init", "finish"):
         getattr(L, f"lb2_solver_{f}").argtypes = [vp]
     L.lb2_solver_step.argtypes = [vp, ci]
+    L.lb2_solver_prepare.argtypes = [vp]
+    L.lb2_solver_arena.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.lb2_solver_set_peers.argtypes = [vp, vp, vp]
+    L.lb2_op_stencil_slab.restype = vp
+    L.lb2_op_stencil_slab.argtypes = [C.c_char, i64, i64, i64, i64, i64, dbl, dbl, vp]
     L.lb2_solver_destroy.argtypes = [vp]
     L.lb2_solver_set_device_x0.argtypes = [vp, u64]
     L.lb2_solver_stat_name.restype = C.c_char_p
@@ -110,6 +115,7 @@ def _declare(L):
         getattr(L, f"lb2_{p}_col_sumsq").argtypes = [vp, i64, ci, vp, i64, vp]
         getattr(L, f"lb2_{p}_fill_uniform").argtypes = [vp, i64, ci, vp, i64, u64, i64, i64]
         getattr(L, f"lb2_{p}_spmm_stencil").argtypes = [vp, i64, i64, i64, dbl, dbl, vp, ci, vp, i64, vp, i64]
+        getattr(L, f"lb2_{p}_spmm_stencil_halo").argtypes = [vp, i64, i64, i64, dbl, dbl, vp, vp, vp, i64, ci, vp, i64, vp, i64]
         getattr(L, f"lb2_{p}_spmm_csr").argtypes = [vp, i64, vp, vp, vp, ci, vp, i64, vp, i64]
         getattr(L, f"lb2_{p}_spmm_diag").argtypes = [vp, i64, vp, ci, vp, i64, vp, i64]
 
@@ -185,13 +191,23 @@ class DeviceArray:
         out = np.asfortranarray(buf[:n, :])
         return out[:, 0].copy() if len(self.shape) == 1 else out
 
+    def rows(self, row0: int, nrows: int) -> "DeviceArray":
+        """Non-owning view of rows [row0, row0+nrows) of every column (same leading dimension)."""
+        v = object.__new__(DeviceArray)
+        v.shape = (int(nrows),) + tuple(self.shape[1:])
+        v.dtype, v.ld = self.dtype, self.ld
+        v.ptr = self.ptr + int(row0) * self.dtype.itemsize
+        v.nbytes = 0
+        v._owner = self
+        return v
+
     def zero(self, ctx: Context):
         _ck(lib().lb2_memset(ctx.h, self.ptr, 0, self.nbytes), "memset")
 
     def free(self):
-        if self.ptr:
+        if self.ptr and not hasattr(self, "_owner"):
             lib().lb2_free(self.ptr)
-            self.ptr = None
+        self.ptr = None
 
     def __del__(self):
         try:
@@ -294,6 +310,27 @@ def stencil_op(grid, dtype, cdiag=None, coff=-1.0, potential=None) -> LinOp:
     pot = None if potential is None else np.ascontiguousarray(potential, dtype=REAL[p])
     h = lib().lb2_op_stencil(p.encode(), g[0], g[1], g[2], cdiag, coff, pot.ctypes.data if pot is not None else None)
     return LinOp(h, p, g[0] * g[1] * g[2])
+
+
+def stencil_slab_op(grid, z0, gz_local, dtype, cdiag=None, coff=-1.0, potential_local=None) -> LinOp:
+    """Rank-local z-slab [z0, z0+gz_local) of a 3-D stencil (row-partitioned multi-GPU runs)."""
+    p = PREFIX[np.dtype(dtype)]
+    gx, gy, gz = (int(v) for v in grid)
+    cdiag = 6.0 if cdiag is None else cdiag
+    pot = None if potential_local is None else np.ascontiguousarray(potential_local, dtype=REAL[p])
+    h = lib().lb2_op_stencil_slab(p.encode(), gx, gy, gz_local, gz, z0, cdiag, coff,
+                                  pot.ctypes.data if pot is not None else None)
+    return LinOp(h, p, gx * gy * gz_local)
+
+
+def stencil_halo_apply(ctx, grid_local, X: DeviceArray, halo_lo, halo_hi, halo_ld, cdiag=6.0, coff=-1.0) -> DeviceArray:
+    """Kernel-level stencil on one z-slab with explicit halo-plane device pointers (ints or None)."""
+    p = PREFIX[X.dtype]
+    gx, gy, gz = grid_local
+    Y = DeviceArray(X.shape, X.dtype)
+    _ck(getattr(lib(), f"lb2_{p}_spmm_stencil_halo")(ctx.h, gx, gy, gz, cdiag, coff, None, halo_lo, halo_hi, halo_ld,
+                                                     X.shape[1], X.ptr, X.ld, Y.ptr, Y.ld), "spmm_stencil_halo")
+    return Y
 
 
 def csr_op(rowptr, col, val) -> LinOp:
@@ -440,6 +477,17 @@ class Solver:
             raise LobpcgB200Error("lb2_solver_create failed")
         if device_seed is not None:
             lib().lb2_solver_set_device_x0(self.h, int(device_seed))
+
+    def prepare(self):
+        _ck(lib().lb2_solver_prepare(self.h), "lb2_solver_prepare")
+
+    def arena(self):
+        ptr, nbytes = C.c_void_p(0), C.c_size_t(0)
+        _ck(lib().lb2_solver_arena(self.h, C.byref(ptr), C.byref(nbytes)), "lb2_solver_arena")
+        return ptr.value, nbytes.value
+
+    def set_peers(self, lo, hi):
+        _ck(lib().lb2_solver_set_peers(self.h, lo, hi), "lb2_solver_set_peers")
 
     def init(self):
         _ck(lib().lb2_solver_init(self.h), "lb2_solver_init")

@@ -223,6 +223,18 @@ void* lb2_op_stencil(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdi
   return wrap_builtin(b);
 }
 
+// rank-local z-slab [z0, z0+gz_local) of a gx*gy*gz_global stencil (row-partitioned multi-GPU runs)
+void* lb2_op_stencil_slab(char prefix, int64_t gx, int64_t gy, int64_t gz_local, int64_t gz_global, int64_t z0,
+                          double cdiag, double coff, const void* potential_local_host) {
+  LinOpRaw* op = (LinOpRaw*)lb2_op_stencil(prefix, gx, gy, gz_local, cdiag, coff, potential_local_host);
+  if (!op) return nullptr;
+  BuiltinOp* b = (BuiltinOp*)op->ctx->data;
+  b->n_global = gx * gy * gz_global;
+  b->row0 = gx * gy * z0;
+  op->rows = op->cols = (uint64_t)b->n_global;
+  return op;
+}
+
 void* lb2_op_bdg(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff, double shift,
                  double d_re, double d_im) {
   if (!valid_prefix(prefix) || gx < 1 || gy < 1 || gz < 1) return nullptr;
@@ -297,6 +309,17 @@ lb2_solver* lb2_solver_create(lb2_ctx* ctx, char prefix, void* alg, int indefini
   return h;
 }
 int lb2_solver_init(lb2_solver* s) { return s ? s->impl->init() : -1; }
+int lb2_solver_prepare(lb2_solver* s) { return s ? s->impl->prepare() : -1; }
+int lb2_solver_arena(lb2_solver* s, void** ptr, size_t* bytes) {
+  if (!s) return -1;
+  s->impl->arena_info(ptr, bytes);
+  return 0;
+}
+int lb2_solver_set_peers(lb2_solver* s, const void* lo_arena, const void* hi_arena) {
+  if (!s) return -1;
+  s->impl->set_peers(lo_arena, hi_arena);
+  return 0;
+}
 int lb2_solver_step(lb2_solver* s, int max_steps) { return s ? s->impl->step(max_steps) : -1; }
 int lb2_solver_finish(lb2_solver* s) { return s ? s->impl->finish() : -1; }
 void lb2_solver_destroy(lb2_solver* s) {
@@ -392,6 +415,15 @@ static void run_solver(char prefix, void* alg, int indefinite) {
     memset(&d, 0, sizeof(d));                                                                          \
     d.gx = (int)gx; d.gy = (int)gy; d.gz = (int)gz; d.cdiag = cdiag; d.coff = coff;                    \
     d.potential = potential;                                                                           \
+    return spmm_stencil<T>(ctx, d, nc, (const T*)X, ldx, (T*)Y, ldy);                                  \
+  }                                                                                                    \
+  int lb2_##P##_spmm_stencil_halo(lb2_ctx* ctx, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff, \
+                                  const void* potential, const void* halo_lo, const void* halo_hi,     \
+                                  int64_t halo_ld, int nc, const void* X, int64_t ldx, void* Y, int64_t ldy) { \
+    StencilDesc d;                                                                                     \
+    memset(&d, 0, sizeof(d));                                                                          \
+    d.gx = (int)gx; d.gy = (int)gy; d.gz = (int)gz; d.cdiag = cdiag; d.coff = coff;                    \
+    d.potential = potential; d.halo_lo = halo_lo; d.halo_hi = halo_hi; d.halo_ld = halo_ld;            \
     return spmm_stencil<T>(ctx, d, nc, (const T*)X, ldx, (T*)Y, ldy);                                  \
   }                                                                                                    \
   int lb2_##P##_spmm_csr(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col,           \

@@ -106,6 +106,9 @@ class Solver : public SolverBase {
   int init() override;
   int step(int max_steps) override;
   int finish() override;
+  void arena_info(void** p, size_t* bytes) override { *p = arena; *bytes = arena_bytes; }
+  void set_peers(const void* lo, const void* hi) override { peer_lo = (const char*)lo; peer_hi = (const char*)hi; }
+  int prepare() override;
   void state(uint64_t* it, uint64_t* cv, int* uo) override {
     if (it) *it = iter;
     if (cv) *cv = conv;
@@ -119,6 +122,9 @@ class Solver : public SolverBase {
   Timers tm;
   int64_t n = 0, ng = 0, row0 = 0;
   int k = 0, nev = 0;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  const char *peer_lo = nullptr, *peer_hi = nullptr;  // neighbours' arena bases (CUDA-IPC mappings), or null
   T* slab[2] = {nullptr, nullptr};
   int cur = 0;
   T *AS = nullptr, *wA = nullptr, *wB = nullptr;
@@ -134,7 +140,7 @@ class Solver : public SolverBase {
   R ANorm = 0, BNorm = 1;
   std::vector<R> hEig, hRes;
   const LinOpRaw *opA = nullptr, *opB = nullptr, *opT = nullptr;
-  bool inited = false, done = false;
+  bool inited = false, done = false, prepared = false;
 
   T* Xp() { return slab[cur]; }
   T* col(T* base, int64_t c) { return base + c * n; }
@@ -174,7 +180,10 @@ class Solver : public SolverBase {
 
 template <typename T>
 void Solver<T>::release() {
-  T** big[] = {&slab[0], &slab[1], &AS, &wA, &wB, &G, &GA, &DinvR, &Z, &Tmp, &Cx, &Cp, &Q, &Tau};
+  if (arena) cudaFree(arena);
+  arena = nullptr;
+  slab[0] = slab[1] = AS = wA = wB = nullptr;
+  T** big[] = {&G, &GA, &DinvR, &Z, &Tmp, &Cx, &Cp, &Q, &Tau};
   for (auto p : big) { if (*p) cudaFree(*p); *p = nullptr; }
   R** rs[] = {&D, &Lam, &Eig, &Sums, &Scal};
   for (auto p : rs) { if (*p) cudaFree(*p); *p = nullptr; }
@@ -188,11 +197,18 @@ template <typename T>
 int Solver<T>::alloc() {
   const size_t nk = (size_t)n * k;
   const size_t m3 = 3 * (size_t)k;
-  LB2_CUDA_OK(cudaMalloc(&slab[0], sizeof(T) * 3 * nk));
-  LB2_CUDA_OK(cudaMalloc(&slab[1], sizeof(T) * 3 * nk));
-  LB2_CUDA_OK(cudaMalloc(&AS, sizeof(T) * 3 * nk));
-  LB2_CUDA_OK(cudaMalloc(&wA, sizeof(T) * std::max<size_t>(nk, 2 * (size_t)n)));
-  LB2_CUDA_OK(cudaMalloc(&wB, sizeof(T) * std::max<size_t>(nk, 2 * (size_t)n)));
+  // one arena for every tall block: a single allocation => a single CUDA-IPC handle, and identical offsets on
+  // every rank of a row-partitioned run (peer halo address = peer arena base + my offset)
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t slab_b = al(sizeof(T) * 3 * nk), wrk_b = al(sizeof(T) * std::max<size_t>(nk, 2 * (size_t)n));
+  arena_bytes = 3 * slab_b + 2 * wrk_b;
+  LB2_CUDA_OK(cudaMalloc(&arena, arena_bytes));
+  char* base = (char*)arena;
+  slab[0] = (T*)base; base += slab_b;
+  slab[1] = (T*)base; base += slab_b;
+  AS = (T*)base; base += slab_b;
+  wA = (T*)base; base += wrk_b;
+  wB = (T*)base;
   T** sm[] = {&G, &GA, &DinvR, &Z, &Tmp};
   for (auto p : sm) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * m3));
   LB2_CUDA_OK(cudaMalloc(&Cx, sizeof(T) * m3 * k));
@@ -218,6 +234,27 @@ int Solver<T>::apply(const LinOpRaw* op, int nc, const T* X, T* Y) {
   if (nc <= 0) return 0;
   const BuiltinOp* b = builtin_of(op);
   if (b) {
+    BuiltinOp local;
+    if (ctx->comm && b->n != b->n_global && (b->kind == OP_STENCIL)) {
+      // z-slab partition: every rank's X must be complete before neighbours read its boundary planes; a
+      // one-element all-reduce on the solver stream is the barrier (all later overwrites of X are separated
+      // from this read by the Gram / norm all-reduces of the pass).
+      tm.begin(PH_COMM);
+      int rcb = allreduce_sum(ctx, Scal + 12, 1, kDouble);
+      tm.end();
+      if (rcb) return rcb;
+      local = *b;
+      const size_t off = (size_t)((const char*)X - (const char*)arena);
+      if (off >= arena_bytes) {
+        fprintf(stderr, "lobpcg_b200: partitioned operator applied to a buffer outside the solver arena\n");
+        return -1;
+      }
+      const int64_t plane = b->gx * b->gy;
+      local.halo_lo = peer_lo ? (const void*)((const T*)(peer_lo + off) + (b->gz - 1) * plane) : nullptr;
+      local.halo_hi = peer_hi ? (const void*)(peer_hi + off) : nullptr;
+      local.halo_ld = n;
+      b = &local;
+    }
     tm.begin(PH_SPMM);
     int rc = apply_builtin<T>(ctx, b, nc, X, n, Y, n);
     tm.end();
@@ -584,7 +621,8 @@ int Solver<T>::residual_pass(bool initial) {
 }
 
 template <typename T>
-int Solver<T>::init() {
+int Solver<T>::prepare() {
+  if (prepared) return 0;
   ng = (int64_t)alg->size;
   n = ng;
   row0 = 0;
@@ -602,11 +640,25 @@ int Solver<T>::init() {
     return 1;
   }
   const BuiltinOp* ba = builtin_of(opA);
-  if (ba && ba->n != ba->n_global) { n = ba->n; }  // row-partitioned operator: local rows
-  if (ctx->comm && ba) { /* row offset = sum of lower ranks' rows; equal slabs */ row0 = (int64_t)comm_rank(ctx) * n; }
+  if (ba && ba->n != ba->n_global) {  // row-partitioned operator: local rows, equal slabs on every rank
+    n = ba->n;
+    row0 = ba->row0;
+    if (!ctx->comm) {
+      fprintf(stderr, "lobpcg: row-partitioned operator needs a communicator (lb2_ctx_attach_comm)\n");
+      return 1;
+    }
+  }
   LB2_CUDA_OK(cudaSetDevice(ctx->device));
   if (sd_init(ctx)) return 1;
   LB2_TRY(alloc());
+  LB2_CUDA_OK(cudaMemsetAsync(Scal, 0, sizeof(R) * 16, ctx->stream));
+  prepared = true;
+  return 0;
+}
+
+template <typename T>
+int Solver<T>::init() {
+  if (int rc = prepare()) return rc;
 
   // X0: device generator, or upload of alg->S[0 : n*k) (rows row0.. of every column when partitioned)
   cur = 0;

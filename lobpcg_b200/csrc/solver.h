@@ -61,6 +61,7 @@ struct BuiltinOp {
   int device;
   int64_t n;        // local rows
   int64_t n_global; // == n on a single GPU
+  int64_t row0;     // first global row of this rank's slab
   // stencil / bdg
   int64_t gx, gy, gz;
   double cdiag, coff, shift, dre, dim;
@@ -94,7 +95,10 @@ enum Phase { PH_SPMM = 0, PH_GRAM, PH_TALLNN, PH_RESID, PH_SMALL, PH_COMM, PH_OT
 
 struct SolverBase {
   virtual ~SolverBase() {}
+  virtual int prepare() = 0;  // validate + allocate (row-partitioned runs exchange arena handles between prepare and init)
   virtual int init() = 0;
+  virtual void arena_info(void** p, size_t* bytes) = 0;
+  virtual void set_peers(const void* lo, const void* hi) = 0;
   virtual int step(int max_steps) = 0;
   virtual int finish() = 0;
   virtual void state(uint64_t* iter, uint64_t* conv, int* use_ortho) = 0;

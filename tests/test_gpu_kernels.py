@@ -250,3 +250,27 @@ def test_stencil_linearity_at_full_size(ctx):
     gi = g[0]
     expected = 6 * (gi - 2) ** 2 * 1 + 12 * (gi - 2) * 4 + 8 * 9
     assert abs(s - expected) < 1e-9 * expected
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32])
+def test_stencil_z_slabs_with_halo_planes_reproduce_the_global_operator(ctx, dt):
+    """Row-partitioned form used on several GPUs, emulated on one: each z-slab is applied by its own launch and
+    reads the neighbouring slab's boundary plane through the halo pointers (on an NVSwitch box those are CUDA-IPC
+    mappings of the neighbour rank's memory)."""
+    g, world, nc = (20, 12, 16), 4, 5
+    n = int(np.prod(g))
+    plane = g[0] * g[1]
+    rng = np.random.default_rng(12)
+    X = rand(rng, (n, nc), dt)
+    ref = no.op_stencil(g)(X)
+    dX = api.DeviceArray.from_numpy(ctx, X)
+    item = np.dtype(dt).itemsize
+    out = []
+    for r in range(world):
+        gzl = g[2] // world
+        row0, nl = r * gzl * plane, gzl * plane
+        lo = dX.ptr + (row0 - plane) * item if r > 0 else None
+        hi = dX.ptr + (row0 + nl) * item if r + 1 < world else None
+        Y = api.stencil_halo_apply(ctx, (g[0], g[1], gzl), dX.rows(row0, nl), lo, hi, n)
+        out.append(Y.numpy(ctx))
+    close(np.vstack(out), ref, rtol(dt))
