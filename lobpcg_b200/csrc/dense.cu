@@ -15,6 +15,7 @@
 // f32 / c32 / c64 currently use the generic register-blocked SIMT kernels at the bottom.
 #include "common.cuh"
 #include "context.h"
+#include <cmath>
 #include "kernels.h"
 
 namespace lb2 {
@@ -74,8 +75,8 @@ __device__ __forceinline__ void upper_tile(int t, int& i, int& j) {
 // =====================================================================================================
 // K2/K3 f64: DMMA Gram.  grid = (ntiles, nsplit).
 // =====================================================================================================
-template <int TM, int TN, int WM, int WN, int BK, int STAGES, bool VEC>
-__global__ void __launch_bounds__(WM* WN * 32)
+template <int TM, int TN, int WM, int WN, int BK, int STAGES, int OCC, bool VEC>
+__global__ void __launch_bounds__(WM* WN * 32, OCC)
     gram_dmma_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
                      int ma, int mb, int64_t n, int64_t rows_per_split, int upper, int ntm,
                      double* __restrict__ out, int64_t split_stride, int ldo) {
@@ -388,13 +389,13 @@ __global__ void __launch_bounds__(256)
 // =====================================================================================================
 // Host launchers
 // =====================================================================================================
-template <int TM, int TN, int WM, int WN, int BK, int STAGES>
+template <int TM, int TN, int WM, int WN, int BK, int STAGES, int OCC>
 static int launch_gram_dmma(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda,
                             const double* B, int64_t ldb, double* G, int ldg, int upper) {
   const int ntm = (ma + TM - 1) / TM, ntn = (mb + TN - 1) / TN;
   const int ntiles = upper ? ntm * (ntm + 1) / 2 : ntm * ntn;
-  // one resident CTA per SM; fill the machine with splits of the n range
-  int nsplit = ctx->sm_count / ntiles;
+  // OCC resident CTAs per SM; fill the machine with splits of the n range (one wave, deterministic order)
+  int nsplit = (ctx->sm_count * OCC) / ntiles;
   if (nsplit < 1) nsplit = 1;
   const int64_t min_rows = 8 * BK;
   if ((int64_t)nsplit * min_rows > n) nsplit = (int)((n + min_rows - 1) / min_rows);
@@ -410,11 +411,11 @@ static int launch_gram_dmma(lb2_ctx* ctx, int64_t n, int ma, int mb, const doubl
   constexpr size_t smem = sizeof(double) * (size_t)STAGES * (TM + TN) * (BK + 4);
   dim3 grid(ntiles, nsplit), block(WM * WN * 32);
   if (vec) {
-    auto k = gram_dmma_kernel<TM, TN, WM, WN, BK, STAGES, true>;
+    auto k = gram_dmma_kernel<TM, TN, WM, WN, BK, STAGES, OCC, true>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, block, smem, ctx->stream>>>(A, lda, B, ldb, ma, mb, n, rps, upper, ntm, part, split_stride, ma);
   } else {
-    auto k = gram_dmma_kernel<TM, TN, WM, WN, BK, STAGES, false>;
+    auto k = gram_dmma_kernel<TM, TN, WM, WN, BK, STAGES, OCC, false>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, block, smem, ctx->stream>>>(A, lda, B, ldb, ma, mb, n, rps, upper, ntm, part, split_stride, ma);
   }
@@ -474,9 +475,28 @@ int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const
   if constexpr (std::is_same<T, double>::value) {
     if (!ctx->force_simt) {
       int tile = ctx->gram_tile;
-      if (tile == 0) tile = (ma > 192 || mb > 192) ? 128 : 64;
-      if (tile == 128) return launch_gram_dmma<128, 128, 2, 4, 16, 4>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
-      return launch_gram_dmma<64, 64, 2, 2, 16, 4>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+      if (tile == 0) {
+        // cost model: padded tile area (upper: tiles on/above the diagonal) x wave quantisation / relative speed
+        const int cand[3] = {128, 96, 64};
+        const int occ[3] = {1, 2, 3};
+        const double speed[3] = {1.0, 0.97, 0.85};
+        double best = 1e300;
+        for (int i = 0; i < 3; i++) {
+          const int t = cand[i];
+          const int ntm = (ma + t - 1) / t, ntn = (mb + t - 1) / t;
+          const int ntiles = upper ? ntm * (ntm + 1) / 2 : ntm * ntn;
+          const int slots = ctx->sm_count * occ[i];
+          int nsplit = slots / ntiles;
+          if (nsplit < 1) nsplit = 1;
+          const double waves = (double)(ntiles * nsplit + slots - 1) / slots;   // >= 1 when ntiles > slots
+          const double fill = (double)ntiles * nsplit / (std::ceil(waves) * slots);
+          const double cost = (double)ntiles * t * t / (speed[i] * fill);
+          if (cost < best) { best = cost; tile = t; }
+        }
+      }
+      if (tile == 128) return launch_gram_dmma<128, 128, 2, 4, 16, 4, 1>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+      if (tile == 96) return launch_gram_dmma<96, 96, 2, 4, 16, 3, 2>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+      return launch_gram_dmma<64, 64, 2, 2, 16, 3, 3>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
     }
   }
   return launch_gram_simt<T>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
@@ -515,10 +535,23 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
   if (n <= 0 || nb <= 0) return 0;
   if constexpr (std::is_same<T, double>::value) {
     if (!ctx->force_simt && kd > 0) {
-      int tile = ctx->nn_tile;
-      if (tile == 0) tile = (nb > 96) ? 128 : 64;
-      if (tile == 128) return launch_nn_dmma<128, 128, 2, 4, 16, 4>(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
-      return launch_nn_dmma<128, 64, 4, 2, 16, 4>(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
+      // 128-wide column tiles plus one narrower remainder tile (32/64/96) so that padding stays below 32 columns
+      const int forced = ctx->nn_tile;
+      const int nfull = (forced == 0 || forced == 128) ? nb / 128 : 0;
+      int rc = 0;
+      if (nfull > 0)
+        rc = launch_nn_dmma<128, 128, 2, 4, 16, 4>(ctx, n, kd, nfull * 128, alpha, S, lds, C, ldc, beta, Out, ldo);
+      const int rem = nb - nfull * 128;
+      if (rc == 0 && rem > 0) {
+        const double* Cr = C + (int64_t)nfull * 128 * ldc;
+        double* Or = Out + (int64_t)nfull * 128 * ldo;
+        const int w = forced ? forced : (rem + 31) / 32 * 32;
+        if (w <= 32) rc = launch_nn_dmma<128, 32, 8, 1, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
+        else if (w <= 64) rc = launch_nn_dmma<128, 64, 4, 2, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
+        else if (w <= 96) rc = launch_nn_dmma<128, 96, 4, 2, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
+        else rc = launch_nn_dmma<128, 128, 2, 4, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
+      }
+      return rc;
     }
   }
   const int nct = (nb + 63) / 64;

@@ -16,134 +16,209 @@
 namespace lb2 {
 
 // =====================================================================================================
-// Stencil: CTA = TX x TY points of the xy-plane, marches a z-chunk keeping (z-1, z, z+1) in registers;
-// the current plane goes through a double-buffered shared tile for the x/y neighbours.  Each thread
-// carries NCOL columns of the block vector => NCOL independent load streams in flight.
+// Stencil: CTA = TX x TY points of the xy-plane marching a z-chunk.  Whole (TX+2)x(TY+2) plane tiles
+// (with their x/y halo ring, zero-filled outside the grid = Dirichlet) are staged global->shared by
+// cp.async (LDGSTS, 16-byte chunks on the aligned interior) into a ring of D+2 planes, D planes ahead
+// of the compute, so no thread ever waits on a global load it has just issued.  Per output the thread
+// reads its 4 in-plane neighbours and the centre of the next plane from shared memory; z-1 / z / z+1
+// centres rotate through registers.  One __syncthreads per plane.  Planes z=-1 and z=gz come from the
+// halo pointers (peer memory on a row-partitioned run) or are zero.
 // =====================================================================================================
-template <typename T, int TX, int TY, int NCOL>
-__global__ void __launch_bounds__(TX* TY)
-    stencil_kernel(StencilDesc d, int nc, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y,
-                   int64_t ldy, int ntx, int nty, int zchunk) {
+template <typename T, int N> struct alignas(N * sizeof(T)) Pack { T v[N]; };
+
+template <typename T, int TXT, int TY, int EPT, int D, bool VECP, bool HAS_POT, bool BDG>
+__global__ void __launch_bounds__(TXT* TY)
+    stencil_kernel(StencilDesc d, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy, int ntx,
+                   int nty, int zchunk) {
   using R = real_t<T>;
-  __shared__ T tile[2][NCOL][TY + 2][TX + 2];
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  using PK = Pack<T, EPT>;
+  constexpr int TX = TXT * EPT;                // tile width in points; each thread owns EPT consecutive x
+  constexpr int NT = TXT * TY;
+  constexpr int VEC = 16 / sizeof(T);          // elements per 16-byte cp.async chunk
+  constexpr int PADL = (VEC > EPT) ? VEC : EPT;  // interior starts 16-byte (and pack) aligned
+  constexpr int RS = TX + 2 * PADL;            // row stride (elements)
+  constexpr int ROWS = TY + 2;
+  constexpr int NS = D + 2;                    // ring slots
+  constexpr int PLANE_ELEMS = ROWS * RS;
+  // copy slots of one plane tile: VECP: 16-byte interior chunks + 2 single halo elements per row; else elementwise
+  constexpr int NCH = VECP ? ROWS * (TX / VEC) : ROWS * (TX + 2);
+  constexpr int NHL = VECP ? 2 * ROWS : 0;
+  constexpr int NSLOT = (NCH + NHL + NT - 1) / NT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* ring = reinterpret_cast<T*>(smem_raw);    // [NS][ROWS][RS]
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TXT, ty = tid / TXT;
   const int bx = blockIdx.x % ntx, by = (blockIdx.x / ntx) % nty, bz = blockIdx.x / (ntx * nty);
-  const int x = bx * TX + tx, y = by * TY + ty;
+  const int x0 = bx * TX, y0 = by * TY;
+  const int x = x0 + tx * EPT, y = y0 + ty;
   const int z0 = bz * zchunk, z1 = min(d.gz, z0 + zchunk);
-  const int c0 = blockIdx.y * NCOL;
-  const bool inside = (x < d.gx) && (y < d.gy);
+  const int col = blockIdx.y;
   const int64_t plane = (int64_t)d.gx * d.gy;
-  const int64_t m = plane * d.gz;                 // points per field (BdG: n = 2m)
-  const int half = d.bdg ? blockIdx.z : 0;        // BdG: 0 = u block, 1 = v block
+  const int64_t m = plane * d.gz;              // points per field (BdG: n = 2m)
+  const int half = BDG ? blockIdx.z : 0;       // BdG: 0 = u block, 1 = v block
   const int64_t hoff = (int64_t)half * m;
-  const int64_t pxy = (int64_t)y * d.gx + x;
   const R cd = (R)(d.cdiag + d.shift), co = (R)d.coff;
-  const R* pot = (const R*)d.potential;
-  const T* hlo = (const T*)d.halo_lo;
-  const T* hhi = (const T*)d.halo_hi;
+  const T* xcol = X + (int64_t)col * ldx + hoff;
+  const T* hlo = d.halo_lo ? (const T*)d.halo_lo + (int64_t)col * d.halo_ld + hoff : nullptr;
+  const T* hhi = d.halo_hi ? (const T*)d.halo_hi + (int64_t)col * d.halo_ld + hoff : nullptr;
+  const int nplanes = (z1 - z0) + 2;           // planes z0-1 .. z1
 
-  const T* xc[NCOL];
-  T* yc[NCOL];
-  bool cv[NCOL];
+  // z-invariant copy descriptors of this thread: offset inside a plane (or -1 = zero fill) and inside a tile
+  int goff[NSLOT], soff[NSLOT];
 #pragma unroll
-  for (int c = 0; c < NCOL; c++) {
-    cv[c] = (c0 + c < nc);
-    const int cc = cv[c] ? c0 + c : c0;
-    xc[c] = X + (int64_t)cc * ldx + hoff;
-    yc[c] = Y + (int64_t)cc * ldy + hoff;
-  }
-
-  auto ld_plane = [&](int c, int z) -> T {
-    // value at (x,y,z) of column c; z may be -1 or gz (halo / Dirichlet zero)
-    if (!inside || !cv[c]) return zero<T>();
-    if (z < 0) return hlo ? hlo[(int64_t)(c0 + c) * d.halo_ld + hoff + pxy] : zero<T>();
-    if (z >= d.gz) return hhi ? hhi[(int64_t)(c0 + c) * d.halo_ld + hoff + pxy] : zero<T>();
-    return xc[c][(int64_t)z * plane + pxy];
-  };
-  auto ld_xy = [&](int c, int xx, int yy, int z) -> T {
-    if (xx < 0 || xx >= d.gx || yy < 0 || yy >= d.gy || !cv[c]) return zero<T>();
-    return xc[c][(int64_t)z * plane + (int64_t)yy * d.gx + xx];
-  };
-
-  T prev[NCOL], cur[NCOL], next[NCOL];
-#pragma unroll
-  for (int c = 0; c < NCOL; c++) {
-    prev[c] = ld_plane(c, z0 - 1);
-    cur[c] = ld_plane(c, z0);
-    next[c] = ld_plane(c, z0 + 1);
-  }
-
-  for (int z = z0; z < z1; z++) {
-    const int buf = (z - z0) & 1;
-    T nn[NCOL];
-#pragma unroll
-    for (int c = 0; c < NCOL; c++) {
-      nn[c] = (z + 2 <= z1) ? ld_plane(c, z + 2) : zero<T>();  // prefetch z+2 (z1 may be gz => halo)
-      tile[buf][c][ty + 1][tx + 1] = cur[c];
-      if (tx == 0) tile[buf][c][ty + 1][0] = ld_xy(c, x - 1, y, z);
-      if (tx == TX - 1) tile[buf][c][ty + 1][TX + 1] = ld_xy(c, x + 1, y, z);
-      if (ty == 0) tile[buf][c][0][tx + 1] = ld_xy(c, x, y - 1, z);
-      if (ty == TY - 1) tile[buf][c][TY + 1][tx + 1] = ld_xy(c, x, y + 1, z);
+  for (int s = 0; s < NSLOT; s++) {
+    const int id = tid + s * NT;
+    goff[s] = -1;
+    soff[s] = -1;
+    if (id < NCH) {
+      int r, xx, sx;
+      if (VECP) { r = id / (TX / VEC); const int c = id % (TX / VEC); xx = x0 + c * VEC; sx = PADL + c * VEC; }
+      else { r = id / (TX + 2); const int c = id % (TX + 2); xx = x0 - 1 + c; sx = PADL - 1 + c; }
+      const int yy = y0 - 1 + r;
+      soff[s] = r * RS + sx;
+      if (yy >= 0 && yy < d.gy && xx >= 0 && xx < d.gx) goff[s] = yy * d.gx + xx;
+    } else if (id < NCH + NHL) {
+      const int h = id - NCH;
+      const int r = h >> 1, right = h & 1;
+      const int yy = y0 - 1 + r, xx = right ? x0 + TX : x0 - 1;
+      soff[s] = r * RS + (right ? PADL + TX : PADL - 1);
+      if (yy >= 0 && yy < d.gy && xx >= 0 && xx < d.gx) goff[s] = yy * d.gx + xx;
     }
-    __syncthreads();
-    if (inside) {
-      const int64_t idx = (int64_t)z * plane + pxy;
-      const R dg = cd + (pot ? pot[idx] : R(0));
+  }
+
+  auto issue = [&](int q) {
+    if (q < nplanes) {
+      const int z = z0 - 1 + q;
+      const T* src = (z < 0) ? hlo : (z >= d.gz) ? hhi : xcol + (int64_t)z * plane;
+      T* dst = ring + (q % NS) * PLANE_ELEMS;
 #pragma unroll
-      for (int c = 0; c < NCOL; c++) {
-        if (!cv[c]) continue;
-        T nb = add_(add_(tile[buf][c][ty + 1][tx], tile[buf][c][ty + 1][tx + 2]),
-                    add_(tile[buf][c][ty][tx + 1], tile[buf][c][ty + 2][tx + 1]));
-        nb = add_(nb, add_(prev[c], next[c]));
-        T r = add_(rscale_(cur[c], dg), rscale_(nb, co));
-        if (d.bdg) {
-          // coupling block: u rows get d * v, v rows get conj(d) * u
-          const T other = X[(int64_t)(c0 + c) * ldx + (half ? 0 : m) + idx];
-          if constexpr (Sc<T>::cplx) {
-            T dd;
-            dd.re = (R)d.dre;
-            dd.im = half ? (R)(-d.dim) : (R)d.dim;
-            fma_(r, dd, other);
-          } else {
-            r = add_(r, rscale_(other, (R)d.dre));
-          }
-        }
-        yc[c][idx] = r;
+      for (int s = 0; s < NSLOT; s++) {
+        if (soff[s] < 0) continue;
+        const bool ok = (src != nullptr) && goff[s] >= 0;
+        const void* g = ok ? (const void*)(src + goff[s]) : (const void*)X;
+        if (VECP && tid + s * NT < NCH) cp_async_zfill<16>(dst + soff[s], g, ok ? 16 : 0);
+        else cp_async_zfill<(int)sizeof(T)>(dst + soff[s], g, ok ? (int)sizeof(T) : 0);
       }
     }
+    cp_async_commit();
+  };
+
 #pragma unroll
-    for (int c = 0; c < NCOL; c++) {
-      prev[c] = cur[c];
-      cur[c] = next[c];
-      next[c] = nn[c];
+  for (int q = 0; q <= D; q++) issue(q);
+
+  const int ctr = (ty + 1) * RS + PADL + tx * EPT;   // my first centre inside a plane tile (pack aligned)
+  const bool rowin = (y < d.gy);
+  const bool full = rowin && (x + EPT <= d.gx);
+  const bool any = rowin && (x < d.gx);
+  PK prev, cur;
+#pragma unroll
+  for (int e = 0; e < EPT; e++) prev.v[e] = cur.v[e] = zero<T>();
+  const int64_t idx0 = (int64_t)(z0 - 1) * plane + (int64_t)y * d.gx + x;
+  T* yp = Y + (int64_t)col * ldy + hoff + idx0;                       // advanced by `plane` per step
+  const R* pp = HAS_POT ? (const R*)d.potential + idx0 : nullptr;
+  const T* op = BDG ? X + (int64_t)col * ldx + (half ? 0 : m) + idx0 : nullptr;
+  int slot = 0;
+  for (int q = 0; q < nplanes - 1; q++) {
+    cp_async_wait<D - 1>();
+    __syncthreads();
+    issue(q + D + 1);
+    const T* pl = ring + slot * PLANE_ELEMS;
+    slot = (slot + 1 == NS) ? 0 : slot + 1;
+    const T* pn = ring + slot * PLANE_ELEMS;
+    if (q == 0) cur = *reinterpret_cast<const PK*>(pl + ctr);   // priming step: plane z0-1 only feeds `prev`
+    const PK next = *reinterpret_cast<const PK*>(pn + ctr);
+    if (q > 0 && any) {
+      const PK up = *reinterpret_cast<const PK*>(pl + ctr - RS);
+      const PK dn = *reinterpret_cast<const PK*>(pl + ctr + RS);
+      const T left = pl[ctr - 1], right = pl[ctr + EPT];
+      PK out;
+#pragma unroll
+      for (int e = 0; e < EPT; e++) {
+        const T xl = (e == 0) ? left : cur.v[e - 1];
+        const T xr = (e == EPT - 1) ? right : cur.v[e + 1];
+        T nb = add_(add_(xl, xr), add_(up.v[e], dn.v[e]));
+        nb = add_(nb, add_(prev.v[e], next.v[e]));
+        R dg = cd;
+        if (HAS_POT) { if (full || x + e < d.gx) dg += pp[e]; }
+        T r = add_(rscale_(cur.v[e], dg), rscale_(nb, co));
+        if (BDG) {
+          if (full || x + e < d.gx) {
+            const T other = op[e];             // coupling: u rows get d v, v rows get conj(d) u
+            if constexpr (Sc<T>::cplx) {
+              T dd;
+              dd.re = (R)d.dre;
+              dd.im = half ? (R)(-d.dim) : (R)d.dim;
+              fma_(r, dd, other);
+            } else {
+              r = add_(r, rscale_(other, (R)d.dre));
+            }
+          }
+        }
+        out.v[e] = r;
+      }
+      if (VECP && full) {
+        *reinterpret_cast<PK*>(yp) = out;
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPT; e++)
+          if (x + e < d.gx) yp[e] = out.v[e];
+      }
     }
+    prev = cur;
+    cur = next;
+    yp += plane;
+    if (HAS_POT) pp += plane;
+    if (BDG) op += plane;
   }
+  cp_async_wait<0>();
+}
+
+template <typename T, int TXT, int TY, int EPT, int D>
+static int launch_stencil(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int PADL = (VEC > EPT) ? VEC : EPT;
+  constexpr int TX = TXT * EPT;
+  constexpr size_t smem = sizeof(T) * (size_t)(D + 2) * (TY + 2) * (TX + 2 * PADL);
+  const int halves = d.bdg ? 2 : 1;
+  const int ntx = (d.gx + TX - 1) / TX, nty = (d.gy + TY - 1) / TY;
+  // z chunks: long marches amortise the 2 extra planes per chunk; split only to fill the machine
+  int zchunk = d.gz;
+  const int64_t base_ctas = (int64_t)ntx * nty * nc * halves;
+  while (zchunk > 32 && base_ctas * ((d.gz + zchunk - 1) / zchunk) < 16LL * ctx->sm_count) zchunk = (zchunk + 1) / 2;
+  const int nz = (d.gz + zchunk - 1) / zchunk;
+  const int64_t plane = (int64_t)d.gx * d.gy;
+  if (plane >= (1LL << 31)) return -2;
+  constexpr int AL = (VEC > EPT) ? VEC : EPT;
+  auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+  const bool vec_ok = (d.gx % AL == 0) && (ldx % AL == 0) && (ldy % AL == 0) && (plane % AL == 0) && al16(X) && al16(Y) &&
+                      (!d.halo_lo || (al16(d.halo_lo) && d.halo_ld % AL == 0)) &&
+                      (!d.halo_hi || (al16(d.halo_hi) && d.halo_ld % AL == 0)) && (!d.bdg || (plane * d.gz) % AL == 0);
+  dim3 grid(ntx * nty * nz, nc, halves);
+#define LB2_ST(VP, HP, BD)                                                                                   \
+  {                                                                                                          \
+    auto kern = stencil_kernel<T, TXT, TY, EPT, D, VP, HP, BD>;                                              \
+    if (smem > 48 * 1024)                                                                                    \
+      LB2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    kern<<<grid, TXT * TY, smem, ctx->stream>>>(d, X, ldx, Y, ldy, ntx, nty, zchunk);                        \
+  }
+  const bool hp = d.potential != nullptr;
+  if (d.bdg) { if (vec_ok) LB2_ST(true, false, true) else LB2_ST(false, false, true) }
+  else if (hp) { if (vec_ok) LB2_ST(true, true, false) else LB2_ST(false, true, false) }
+  else { if (vec_ok) LB2_ST(true, false, false) else LB2_ST(false, false, false) }
+#undef LB2_ST
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 template <typename T>
 int spmm_stencil(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy) {
   if (nc <= 0) return 0;
-  constexpr int NCOL = (sizeof(T) >= 16) ? 2 : 4;
-  const int halves = d.bdg ? 2 : 1;
-  if (d.gy == 1 && d.gz == 1) {
-    constexpr int TX = 128, TY = 1;
-    const int ntx = (d.gx + TX - 1) / TX;
-    dim3 grid(ntx, (nc + NCOL - 1) / NCOL, halves);
-    stencil_kernel<T, TX, TY, NCOL><<<grid, TX * TY, 0, ctx->stream>>>(d, nc, X, ldx, Y, ldy, ntx, 1, 1);
-  } else {
-    constexpr int TX = 32, TY = 8;
-    const int ntx = (d.gx + TX - 1) / TX, nty = (d.gy + TY - 1) / TY;
-    // z chunks: enough CTAs to fill the machine, but long enough marches to amortise the 3-plane prologue
-    int zchunk = d.gz;
-    const int64_t base_ctas = (int64_t)ntx * nty * ((nc + NCOL - 1) / NCOL) * halves;
-    while (zchunk > 16 && base_ctas * ((d.gz + zchunk - 1) / zchunk) < 8LL * ctx->sm_count) zchunk = (zchunk + 1) / 2;
-    const int nz = (d.gz + zchunk - 1) / zchunk;
-    dim3 grid(ntx * nty * nz, (nc + NCOL - 1) / NCOL, halves);
-    stencil_kernel<T, TX, TY, NCOL><<<grid, TX * TY, 0, ctx->stream>>>(d, nc, X, ldx, Y, ldy, ntx, nty, zchunk);
-  }
-  ctx->launches++;
-  LB2_CUDA_OK(cudaGetLastError());
-  return 0;
+  if (nc > 65535) return -2;
+  constexpr int EPT = Sc<T>::cplx ? 1 : 2;   // consecutive x points per thread (16-byte packs for double)
+  if (d.gy == 1 && d.gz == 1) return launch_stencil<T, 128, 1, EPT, 2>(ctx, d, nc, X, ldx, Y, ldy);
+  return launch_stencil<T, 32, 8, EPT, 4>(ctx, d, nc, X, ldx, Y, ldy);
 }
 
 // =====================================================================================================

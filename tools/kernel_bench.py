@@ -1,0 +1,56 @@
+"""Isolated kernel timing (CUDA events on the launching stream, L2-exceeding inputs):
+   python tools/kernel_bench.py stencil G NC | csr G NC | gram N M [upper] | nn N KD NB | resid N NC"""
+import sys, json
+sys.path.insert(0, ".")
+import numpy as np
+import torch
+from lobpcg_b200 import api, problems as pr
+
+mode = sys.argv[1]
+stream = torch.cuda.Stream()
+ctx = api.Context(0, stream.cuda_stream)
+for kv in [a for a in sys.argv if "=" in a]:
+    k, v = kv.split("="); ctx.set_option(k, int(v))
+args = [a for a in sys.argv[2:] if "=" not in a]
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm): fn()
+    ctx.sync()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); fn(); e1.record(stream); ctx.sync()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+if mode in ("stencil", "csr"):
+    g, nc = int(args[0]), int(args[1]); n = g ** 3
+    X = api.fill_uniform(ctx, n, nc, np.float64, 1); Y = api.DeviceArray((n, nc), np.float64)
+    if mode == "csr":
+        rp, c, v = pr.laplacian_csr((g, g, g)); op = api.csr_op(rp, c, v); extra = len(v) * 12 + 8 * (n + 1)
+    else:
+        op = api.stencil_op((g, g, g), np.float64); extra = 0
+    med, mn = timeit(lambda: op.apply(ctx, X, Y))
+    b = 2.0 * n * nc * 8 + extra
+    print(json.dumps(dict(kernel=mode, g=g, nc=nc, ms=med, ms_min=mn, gbs=b / med / 1e6, frac_hbm=b / med / 1e6 / 6536.7)))
+elif mode == "gram":
+    n, m = int(args[0]), int(args[1]); upper = len(args) > 2 and args[2] == "upper"
+    A = api.fill_uniform(ctx, n, m, np.float64, 1); B = A if upper else api.fill_uniform(ctx, n, m, np.float64, 2)
+    L = api.lib(); G = api.DeviceArray((m, m), np.float64)
+    med, mn = timeit(lambda: L.lb2_d_gram(ctx.h, n, m, m, A.ptr, A.ld, B.ptr, B.ld, G.ptr, m, int(upper)))
+    fl = n * m * (m + 1.0) if upper else 2.0 * n * m * m
+    print(json.dumps(dict(kernel="gram", n=n, m=m, upper=upper, ms=med, ms_min=mn, tflops=fl / med / 1e9, frac=fl / med / 1e9 / 35.76)))
+elif mode == "nn":
+    n, kd, nb = int(args[0]), int(args[1]), int(args[2])
+    S = api.fill_uniform(ctx, n, kd, np.float64, 1); Cm = api.fill_uniform(ctx, kd, nb, np.float64, 2); O = api.DeviceArray((n, nb), np.float64)
+    med, mn = timeit(lambda: api.tall_nn(ctx, S, Cm, O))
+    fl = 2.0 * n * kd * nb
+    print(json.dumps(dict(kernel="tall_nn", n=n, kd=kd, nb=nb, ms=med, ms_min=mn, tflops=fl / med / 1e9, frac=fl / med / 1e9 / 35.76)))
+elif mode == "resid":
+    n, nc = int(args[0]), int(args[1])
+    AX = api.fill_uniform(ctx, n, nc, np.float64, 1); BX = api.fill_uniform(ctx, n, nc, np.float64, 2)
+    lam = api.DeviceArray.from_numpy(ctx, np.ones(nc)); W = api.DeviceArray((n, nc), np.float64); ss = api.DeviceArray((nc,), np.float64)
+    L = api.lib()
+    med, mn = timeit(lambda: L.lb2_d_residual(ctx.h, n, nc, AX.ptr, n, BX.ptr, n, lam.ptr, W.ptr, n, ss.ptr))
+    b = 3.0 * n * nc * 8
+    print(json.dumps(dict(kernel="residual", n=n, nc=nc, ms=med, gbs=b / med / 1e6, frac_hbm=b / med / 1e6 / 6536.7)))
