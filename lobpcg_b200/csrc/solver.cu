@@ -623,6 +623,10 @@ int Solver<T>::residual_pass(bool initial) {
 template <typename T>
 int Solver<T>::prepare() {
   if (prepared) return 0;
+  if (indef) {
+    fprintf(stderr, "ilobpcg: the indefinite solver is not available in this build of lobpcg_b200\n");
+    return 1;
+  }
   ng = (int64_t)alg->size;
   n = ng;
   row0 = 0;
