@@ -363,6 +363,88 @@ int sd_frob(lb2_ctx* ctx, int rows, int cols, const T* G, int ldg, real_t<T>* ou
   return 0;
 }
 
+
+// general small triangular solve with the upper factor R: side 'L': op(R) X = B, side 'R': X op(R) = B; op 'N' or 'H'
+template <typename T>
+int sd_trsm_upper(lb2_ctx* ctx, char side, char op, int rows, int cols, const T* R, int ldr, T* X, int ldx) {
+  if (sd_init(ctx)) return -1;
+  const T one = make<T>(1);
+  const cublasOperation_t t = (op == 'N') ? CUBLAS_OP_N : (Sc<T>::cplx ? CUBLAS_OP_C : CUBLAS_OP_T);
+  LB2_BLAS_OK(trsm_(ctx->cublas, side == 'L' ? CUBLAS_SIDE_LEFT : CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, t,
+                    CUBLAS_DIAG_NON_UNIT, rows, cols, &one, R, ldr, X, ldx));
+  ctx->launches++;
+  return 0;
+}
+
+// C = alpha * op(A) B + beta * C on small matrices
+template <typename T>
+int sd_gemm_ab(lb2_ctx* ctx, char opa, int m, int n, int k, T alpha, const T* A, int lda, const T* B, int ldb, T beta,
+               T* C, int ldc) {
+  if (sd_init(ctx)) return -1;
+  if (m <= 0 || n <= 0) return 0;
+  const cublasOperation_t ta = (opa == 'N') ? CUBLAS_OP_N : (Sc<T>::cplx ? CUBLAS_OP_C : CUBLAS_OP_T);
+  LB2_BLAS_OK(gemm_(ctx->cublas, ta, CUBLAS_OP_N, m, n, k, &alpha, A, lda, B, ldb, &beta, C, ldc));
+  ctx->launches++;
+  return 0;
+}
+
+// Indefinite RR back end (replaces GGEV + B-normalisation + signature sort of the reference,
+// src/rayleigh/indefinite_rr_impl.inc:73-145): input mu (ascending) and V with V^H G_B V = diag(mu) (columns of
+// R^-1 W); output columns scaled to |v^H G_B v| = 1, theta = 1/mu, signature = sign(mu), ordered positive
+// signature first with theta ascending, then negative signature with theta descending (bubble_sort_sig_impl.inc).
+template <typename T>
+__global__ void indef_finalize_kernel(int m, const real_t<T>* __restrict__ mu, const T* __restrict__ V, int ldv,
+                                      T* __restrict__ VR, int ldo, real_t<T>* __restrict__ theta,
+                                      int8_t* __restrict__ sig) {
+  using R = real_t<T>;
+  __shared__ int npos_s;
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int j = 0; j < m; j++) c += (mu[j] >= R(0)) ? 1 : 0;
+    npos_s = c;
+  }
+  __syncthreads();
+  const int npos = npos_s, nneg = m - npos;
+  // mu ascending: indices [0,nneg) negative (theta descending as listed), [nneg,m) positive (theta ascending when reversed)
+  for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+    const int i = idx % m, jo = idx / m;                 // output column jo
+    const int js = (jo < npos) ? (m - 1 - jo) : (jo - npos);
+    const R a = fabs(mu[js]);
+    const R sc = (a > R(1e-30)) ? R(1) / sqrt(a) : R(1);
+    VR[i + (int64_t)jo * ldo] = rscale_(V[i + (int64_t)js * ldv], sc);
+    if (i == 0) {
+      theta[jo] = (a > R(1e-30)) ? R(1) / mu[js] : ((mu[js] >= R(0)) ? R(1e30) : R(-1e30));
+      sig[jo] = (mu[js] >= R(0)) ? 1 : -1;
+    }
+  }
+  (void)nneg;
+}
+template <typename T>
+int sd_indef_finalize(lb2_ctx* ctx, int m, const real_t<T>* mu, const T* V, int ldv, T* VR, int ldo,
+                      real_t<T>* theta, int8_t* sig) {
+  indef_finalize_kernel<T><<<1, 256, 0, ctx->stream>>>(m, mu, V, ldv, VR, ldo, theta, sig);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Cp = [0; Cx[nx:m, :]]  (indefinite_rr_modified_impl.inc:229-235)
+template <typename T>
+__global__ void cp_lower_kernel(int m, int nx, const T* __restrict__ Cx, T* __restrict__ Cp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < m * nx) {
+    const int i = idx % m;
+    Cp[idx] = (i < nx) ? zero<T>() : Cx[idx];
+  }
+}
+template <typename T>
+int sd_cp_lower(lb2_ctx* ctx, int m, int nx, const T* Cx, T* Cp) {
+  cp_lower_kernel<T><<<(m * nx + 255) / 256, 256, 0, ctx->stream>>>(m, nx, Cx, Cp);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 #define LB2_INST(T)                                                                                         \
   template int sd_potrf_upper<T>(lb2_ctx*, int, T*, int, int*);                                             \
   template int sd_syevd_upper<T>(lb2_ctx*, int, T*, int, real_t<T>*, int*);                                 \
@@ -375,7 +457,11 @@ int sd_frob(lb2_ctx* ctx, int rows, int cols, const T* G, int ldg, real_t<T>* ou
   template int sd_transpose<T>(lb2_ctx*, int, int, const T*, int, T*, int);                                 \
   template int sd_svqb_transform<T>(lb2_ctx*, int, const T*, int, const real_t<T>*, const real_t<T>*, real_t<T>, int, T*, int, int*); \
   template int sd_ortho_err_upper<T>(lb2_ctx*, int, const T*, int, real_t<T>*);                             \
-  template int sd_frob<T>(lb2_ctx*, int, int, const T*, int, real_t<T>*);
+  template int sd_frob<T>(lb2_ctx*, int, int, const T*, int, real_t<T>*);                                  \
+  template int sd_trsm_upper<T>(lb2_ctx*, char, char, int, int, const T*, int, T*, int);                  \
+  template int sd_gemm_ab<T>(lb2_ctx*, char, int, int, int, T, const T*, int, const T*, int, T, T*, int); \
+  template int sd_indef_finalize<T>(lb2_ctx*, int, const real_t<T>*, const T*, int, T*, int, real_t<T>*, int8_t*); \
+  template int sd_cp_lower<T>(lb2_ctx*, int, int, const T*, T*);
 LB2_INST(float)
 LB2_INST(double)
 LB2_INST(c32)

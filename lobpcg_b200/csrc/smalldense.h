@@ -17,4 +17,8 @@ template <typename T> int sd_transpose(lb2_ctx* ctx, int rows, int cols, const T
 template <typename T> int sd_svqb_transform(lb2_ctx* ctx, int m, const T* V, int ldv, const real_t<T>* lam, const real_t<T>* D, real_t<T> tau, int drop, T* Tm, int ldt, int* count_dev);
 template <typename T> int sd_ortho_err_upper(lb2_ctx* ctx, int m, const T* G, int ldg, real_t<T>* out_dev);
 template <typename T> int sd_frob(lb2_ctx* ctx, int rows, int cols, const T* G, int ldg, real_t<T>* out_dev);
+template <typename T> int sd_trsm_upper(lb2_ctx* ctx, char side, char op, int rows, int cols, const T* R, int ldr, T* X, int ldx);
+template <typename T> int sd_gemm_ab(lb2_ctx* ctx, char opa, int m, int n, int k, T alpha, const T* A, int lda, const T* B, int ldb, T beta, T* C, int ldc);
+template <typename T> int sd_indef_finalize(lb2_ctx* ctx, int m, const real_t<T>* mu, const T* V, int ldv, T* VR, int ldo, real_t<T>* theta, int8_t* sig);
+template <typename T> int sd_cp_lower(lb2_ctx* ctx, int m, int nx, const T* Cx, T* Cp);
 }  // namespace lb2

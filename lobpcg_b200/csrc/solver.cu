@@ -132,9 +132,12 @@ class Solver : public SolverBase {
     *Q = nullptr, *Tau = nullptr;
   R *D = nullptr, *Lam = nullptr, *Eig = nullptr, *Sums = nullptr, *Scal = nullptr;
   int* Count = nullptr;
+  R* Theta = nullptr;      // indefinite RR: all m Ritz values, signature-sorted
+  int8_t* dSig = nullptr;  // indefinite RR: signatures (+1/-1), sorted
   R* hbuf = nullptr;  // pinned
   T *hX = nullptr, *hY = nullptr;  // host staging for host-callback operators
   int np = 0, nw = 0;
+  int sig_len = 0;
   int useOrtho = 0;
   uint64_t iter = 0, conv = 0;
   R ANorm = 0, BNorm = 1;
@@ -172,7 +175,9 @@ class Solver : public SolverBase {
   int rr_modified(int m, int from_col);
   int cp_from_z(int m, const T* Zm, T* VQ);           // VQ (m x k) = Z_perp Q
   int svqb(T* U, int nu, R tau, bool drop, int* nret);
-  int ortho_drop(T* U, int nu, T* V, int nv, int* nret);
+  int ortho_drop(T* U, int nu, T* V, int nv, int* nret, bool indefinite = false);
+  int rr_indef(int m, int from_col, bool initial);
+  int ortho_indef_mat(int m, int nu, int nv, T* U, const T* V, const T* mat);
   int residual_pass(bool initial);
   int step_impl(int max_steps, int* passes_out);
   void print_state(bool header);
@@ -188,6 +193,8 @@ void Solver<T>::release() {
   R** rs[] = {&D, &Lam, &Eig, &Sums, &Scal};
   for (auto p : rs) { if (*p) cudaFree(*p); *p = nullptr; }
   if (Count) cudaFree(Count); Count = nullptr;
+  if (Theta) cudaFree(Theta); Theta = nullptr;
+  if (dSig) cudaFree(dSig); dSig = nullptr;
   if (hbuf) cudaFreeHost(hbuf); hbuf = nullptr;
   if (hX) cudaFreeHost(hX); hX = nullptr;
   if (hY) cudaFreeHost(hY); hY = nullptr;
@@ -221,6 +228,8 @@ int Solver<T>::alloc() {
   LB2_CUDA_OK(cudaMalloc(&Sums, sizeof(R) * (m3 + 16)));
   LB2_CUDA_OK(cudaMalloc(&Scal, sizeof(R) * 16));
   LB2_CUDA_OK(cudaMalloc(&Count, sizeof(int) * 4));
+  LB2_CUDA_OK(cudaMalloc(&Theta, sizeof(R) * m3));
+  LB2_CUDA_OK(cudaMalloc(&dSig, m3));
   LB2_CUDA_OK(cudaMallocHost(&hbuf, sizeof(R) * (m3 + 32)));
   hEig.assign(k, R(0));
   hRes.assign(k, R(0));
@@ -500,7 +509,7 @@ int Solver<T>::svqb(T* U, int nu, R tau, bool drop, int* nret) {
 
 // ortho_drop (ortho_drop_impl.inc:43-125): B-orthogonalise U against V, B-orthonormalise U.
 template <typename T>
-int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret) {
+int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret, bool indefinite) {
   *nret = nu0;
   if (nu0 == 0 || nv == 0) return 0;
   if (ng < (int64_t)nu0 + nv) {
@@ -510,6 +519,8 @@ int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret) {
   }
   const R eps = (R)EpsTol<T>::v;
   int nu = nu0;
+  // indefinite metric (ortho_indefinite_impl.inc:98-105): signature matrix sig = V^H B V, kept in GA
+  if (indefinite) LB2_TRY(gram_self_B(nv, V, GA));
   // ||B V||_F
   R BV_norm = 0;
   {
@@ -537,7 +548,12 @@ int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret) {
     const T* BU = U;
     if (opB) { LB2_TRY(apply(opB, nu, U, wA)); BU = wA; }
     LB2_TRY(gram_ar(nv, nu, V, BU, Tmp, 0));
-    LB2_TRY(nn(nv, nu, make<T>(-1), V, Tmp, nv, make<T>(1), U));
+    if (indefinite) {  // U -= V (sig (V^H B U))   (ortho_indefinite_impl.inc:121-133)
+      LB2_TRY(sd_gemm<T>(ctx, 'N', nv, nu, nv, GA, nv, Tmp, nv, Z, nv));
+      LB2_TRY(nn(nv, nu, make<T>(-1), V, Z, nv, make<T>(1), U));
+    } else {
+      LB2_TRY(nn(nv, nu, make<T>(-1), V, Tmp, nv, make<T>(1), U));
+    }
     for (int inner = 0; inner < 3; inner++) {
       int keep = nu;
       LB2_TRY(svqb(U, nu, eps, true, &keep));
@@ -561,7 +577,8 @@ int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret) {
       R U_norm = std::sqrt(hbuf[1]);
       if (U_norm < eps) U_norm = 1;
       const R BU_norm = opB ? std::sqrt(hbuf[2]) : U_norm;
-      const R rerr = hbuf[0] / (BU_norm * U_norm);
+      // ortho_indefinite uses ||U||^2 as denominator (ortho_indefinite_impl.inc:141-152)
+      const R rerr = indefinite ? hbuf[0] / (U_norm * U_norm) : hbuf[0] / (BU_norm * U_norm);
       if (rerr < eps) break;
     }
     if (nu == 0) break;
@@ -579,6 +596,120 @@ int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret) {
     if (rerr < eps) break;
   }
   *nret = nu;
+  return 0;
+}
+
+// Coefficient-space orthogonalisation of U (m x nu) against V (m x nv) in the metric `mat` (m x m):
+// ortho_indefinite_mat + svqb_mat of the reference (src/ortho/ortho_indefinite_mat_impl.inc:52-123,
+// src/ortho/svqb_mat_impl.inc:49-100), everything on the device.  Scratch lives in DinvR / Q / GA.
+template <typename T>
+int Solver<T>::ortho_indef_mat(int m, int nu, int nv, T* U, const T* V, const T* mat) {
+  if (nu == 0 || nv == 0) return 0;
+  if (m < nu + nv) {
+    fprintf(stderr, "ortho_indefinite_mat: overdetermined m=%lu < n_u+n_v=%lu+%lu\n", (unsigned long)m,
+            (unsigned long)nu, (unsigned long)nv);
+    return 0;
+  }
+  const R eps = (R)EpsTol<T>::v;
+  const size_t blk = (size_t)3 * k * k;
+  T* t1 = DinvR;            // m x max(nu,nv)
+  T* t2 = DinvR + blk;      // m x nu
+  T* c1 = DinvR + 2 * blk;  // nv x nu  /  nu x nu
+  T* c2 = Q;                // nu x nu transform
+  LB2_TRY(sd_gemm<T>(ctx, 'N', m, nv, m, mat, m, V, m, t1, m));
+  LB2_TRY(sd_frob<T>(ctx, m, nv, t1, m, Scal));
+  LB2_TRY(d2h(hbuf, Scal, sizeof(R)));
+  LB2_TRY(sync());
+  R MV_norm = hbuf[0];
+  if (MV_norm < eps) MV_norm = 1;
+  for (int outer = 0; outer < 3; outer++) {
+    // U -= V V^H mat V V^H mat U, right to left (:85-101)
+    LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, m, mat, m, U, m, t1, m));
+    LB2_TRY(sd_gemm<T>(ctx, 'H', nv, nu, m, V, m, t1, m, c1, nv));
+    LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, nv, V, m, c1, nv, t2, m));
+    LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, m, mat, m, t2, m, t1, m));
+    LB2_TRY(sd_gemm<T>(ctx, 'H', nv, nu, m, V, m, t1, m, c1, nv));
+    LB2_TRY(sd_gemm_ab<T>(ctx, 'N', m, nu, nv, make<T>(-1), V, m, c1, nv, make<T>(1), U, m));
+    for (int inner = 0; inner < 3; inner++) {
+      // svqb_mat, drop = 'n'
+      LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, m, mat, m, U, m, t1, m));
+      LB2_TRY(sd_gemm<T>(ctx, 'H', nu, nu, m, U, m, t1, m, c1, nu));
+      LB2_TRY(sd_dscale<T>(ctx, nu, c1, nu, D));
+      int info = 0;
+      LB2_TRY(sd_syevd_upper<T>(ctx, nu, c1, nu, Lam, &info));
+      if (info != 0) {
+        fprintf(stderr, "svqb_mat: eig failed with info=%d\n", info);
+        return 0;
+      }
+      LB2_TRY(sd_svqb_transform<T>(ctx, nu, c1, nu, Lam, D, eps, 0, c2, nu, Count));
+      LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, nu, U, m, c2, nu, t2, m));
+      LB2_CUDA_OK(cudaMemcpyAsync(U, t2, sizeof(T) * (size_t)m * nu, cudaMemcpyDeviceToDevice, ctx->stream));
+      // ||U^H mat U - I_sig||_F / ||U||^2
+      LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, m, mat, m, U, m, t1, m));
+      LB2_TRY(sd_gemm<T>(ctx, 'H', nu, nu, m, U, m, t1, m, c1, nu));
+      LB2_TRY(sd_ortho_err_upper<T>(ctx, nu, c1, nu, Scal));
+      LB2_TRY(sd_frob<T>(ctx, m, nu, U, m, Scal + 1));
+      LB2_TRY(d2h(hbuf, Scal, 2 * sizeof(R)));
+      LB2_TRY(sync());
+      R Un = hbuf[1];
+      if (Un < eps) Un = 1;
+      if (hbuf[0] / (Un * Un) < eps) break;
+    }
+    LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, m, mat, m, U, m, t1, m));
+    LB2_TRY(sd_gemm<T>(ctx, 'H', nv, nu, m, V, m, t1, m, c1, nv));
+    LB2_TRY(sd_frob<T>(ctx, nv, nu, c1, nv, Scal));
+    LB2_TRY(sd_frob<T>(ctx, m, nu, U, m, Scal + 1));
+    LB2_TRY(d2h(hbuf, Scal, 2 * sizeof(R)));
+    LB2_TRY(sync());
+    R Un = hbuf[1];
+    if (Un < eps) Un = 1;
+    if (hbuf[0] / (MV_norm * Un) < eps) break;
+  }
+  return 0;
+}
+
+// Indefinite Rayleigh-Ritz on S = slab[cur][:, 0:m] (reference src/rayleigh/indefinite_rr_impl.inc:51-149 and
+// indefinite_rr_modified_impl.inc:58-255).  The reference hands (G_A, G_B) to LAPACK GGEV, B-normalises the
+// eigenvectors twice and checks their B-orthogonality (quality flag); cuSOLVER has no GGEV, and for the pencils
+// this solver targets G_A = S^H A S is Hermitian positive definite, so the same eigenpairs are obtained from a
+// Hermitian problem: G_A = R^H R, K = R^-H G_B R^-1 = W diag(mu) W^H, v = R^-1 w, theta = 1/mu, v^H G_B v = mu.
+// The eigenvectors are G_B-orthogonal by construction (the reference's quality_flag == 1 path).
+template <typename T>
+int Solver<T>::rr_indef(int m, int from_col, bool initial) {
+  T* S = Xp();
+  LB2_TRY(apply(opA, m - from_col, col(S, from_col), col(AS, from_col)));
+  LB2_TRY(gram_ar(m, m, S, AS, GA, 1));
+  LB2_TRY(gram_self_B(m, S, G));
+  tm.begin(PH_SMALL);
+  LB2_CUDA_OK(cudaMemcpyAsync(Tmp, G, sizeof(T) * (size_t)m * m, cudaMemcpyDeviceToDevice, ctx->stream));
+  int info = 0;
+  LB2_TRY(sd_potrf_upper<T>(ctx, m, GA, m, &info));
+  if (info != 0) {
+    tm.end();
+    fprintf(stderr, "indefinite_rayleigh_ritz: S^H A S is not positive definite (info=%d); the device path needs a "
+                    "positive definite A-Gram (GGEV fallback not available)\n", info);
+    return 1;
+  }
+  LB2_TRY(sd_trsm_upper<T>(ctx, 'R', 'N', m, m, GA, m, Tmp, m));
+  LB2_TRY(sd_trsm_upper<T>(ctx, 'L', 'H', m, m, GA, m, Tmp, m));
+  LB2_TRY(sd_syevd_upper<T>(ctx, m, Tmp, m, Lam, &info));
+  if (info != 0) {
+    tm.end();
+    fprintf(stderr, "indefinite_rayleigh_ritz: eigensolve failed (info=%d)\n", info);
+    return 1;
+  }
+  LB2_TRY(sd_trsm_upper<T>(ctx, 'L', 'N', m, m, GA, m, Tmp, m));
+  LB2_TRY(sd_indef_finalize<T>(ctx, m, Lam, Tmp, m, Z, m, Theta, dSig));
+  LB2_CUDA_OK(cudaMemcpyAsync(Eig, Theta, sizeof(R) * k, cudaMemcpyDeviceToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaMemcpyAsync(Cx, Z, sizeof(T) * (size_t)m * k, cudaMemcpyDeviceToDevice, ctx->stream));
+  sig_len = m;
+  if (!initial) {
+    LB2_TRY(sd_cp_lower<T>(ctx, m, k, Cx, Cp));
+    tm.end();
+    LB2_TRY(ortho_indef_mat(m, k, k, Cp, Cx, G));
+  } else {
+    tm.end();
+  }
   return 0;
 }
 
@@ -623,8 +754,8 @@ int Solver<T>::residual_pass(bool initial) {
 template <typename T>
 int Solver<T>::prepare() {
   if (prepared) return 0;
-  if (indef) {
-    fprintf(stderr, "ilobpcg: the indefinite solver is not available in this build of lobpcg_b200\n");
+  if (indef && !alg->B) {
+    fprintf(stderr, "ilobpcg: B operator must not be NULL\n");
     return 1;
   }
   ng = (int64_t)alg->size;
@@ -683,7 +814,17 @@ int Solver<T>::init() {
   LB2_TRY(sync());
   if (std::sqrt(hbuf[0]) < (R)EpsTol<T>::v) LB2_TRY(fill_uniform<T>(ctx, n, k, X, n, 0xC0FFEEULL, ng, row0));
 
-  if (int rc = rr_initial()) return rc;
+  if (indef) {
+    // ilobpcg_impl.inc:100-113: B-orthonormalise X (svqb, no dropping), indefinite RR, X <- X Cx
+    int keep = k;
+    LB2_TRY(svqb(X, k, (R)EpsTol<T>::v, false, &keep));
+    if (int rc = rr_indef(k, 0, true)) return rc;
+    T* Xn = slab[1 - cur];
+    LB2_TRY(nn(k, k, make<T>(1), Xp(), Cx, k, zero<T>(), Xn));
+    cur = 1 - cur;
+  } else {
+    if (int rc = rr_initial()) return rc;
+  }
   LB2_TRY(residual_pass(true));
   // W for all k columns (iter 0 uses sizeW = sizeSub, lobpcg_impl.inc:134), preconditioned
   np = 0;
@@ -721,14 +862,18 @@ int Solver<T>::step_impl(int max_steps, int* passes_out) {
     T* V = S;
     T* W = col(S, k + np);
     // orthogonalise W against [X, P_act]
-    if (useOrtho) {
+    if (useOrtho || indef) {
       int keep = nw;
-      LB2_TRY(ortho_drop(W, nw, V, k + np, &keep));
+      LB2_TRY(ortho_drop(W, nw, V, k + np, &keep, indef));
       nw = keep;
     }
     int m = k + np + nw;
-    if (int rc = rr_modified(m, k)) return rc;
-    if (useOrtho == 2) {
+    if (indef) {
+      if (int rc = rr_indef(m, k, false)) return rc;
+    } else if (int rc = rr_modified(m, k)) {
+      return rc;
+    }
+    if (!indef && useOrtho == 2) {
       useOrtho = 1;
       int keep = nw;
       LB2_TRY(ortho_drop(W, nw, V, k + np, &keep));
@@ -775,6 +920,10 @@ int Solver<T>::finish() {
   LB2_TRY(sync());
   for (int i = 0; i < k; i++) alg->eigVals[i] = hEig[i];
   for (int i = 0; i < nev; i++) alg->resNorm[i] = hRes[i];
+  if (indef && alg->signature && sig_len > 0) {
+    LB2_CUDA_OK(cudaMemcpyAsync(alg->signature, dSig, (size_t)sig_len, cudaMemcpyDeviceToHost, ctx->stream));
+    LB2_TRY(sync());
+  }
   alg->converged = conv;
   alg->iter = iter;
   return 0;

@@ -15,6 +15,7 @@ import sys
 from pathlib import Path
 
 import numpy as np
+import scipy.sparse as sp  # noqa: F401  (import before oracle/_ref is dlopen'ed: importing scipy afterwards crashes)
 
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
@@ -166,6 +167,45 @@ def solver_runs(out):
     run("z3d", rb.op_stencil((10, 10, 10), np.complex128), pr.initial_block(n, 8, 9, np.complex128), 4, 1e-8, 3000)
 
 
+def indefinite_cases():
+    """Inputs of the ilobpcg parity cases (shared with tests/test_gpu_solver.py through this module)."""
+    cases = {}
+    # BdG-style Hermitian pencil, config C4 at 6^3 (SURVEY §8d): A=[[K+c,d],[conj d,K+c]], B=diag(I,-I)
+    g = (6, 6, 6); m = 216
+    X0 = pr.initial_block(2 * m, 8, 13, np.complex128); X0[m:] *= 0.1      # B-positive start
+    cases["ilob_bdg_z"] = dict(kind="bdg", grid=g, dtype=np.complex128, shift=0.5, d=0.5 * np.exp(0.7j),
+                               bdiag=np.concatenate([np.ones(m), -np.ones(m)]), X0=X0, nev=4, tol=1e-9, it=3000)
+    X0 = pr.initial_block(2 * m, 8, 14, np.float64); X0[m:] *= 0.1
+    cases["ilob_bdg_d"] = dict(kind="bdg", grid=g, dtype=np.float64, shift=0.5, d=0.3,
+                               bdiag=np.concatenate([np.ones(m), -np.ones(m)]), X0=X0, nev=4, tol=1e-9, it=3000)
+    # block Laplacian / block swap (reference tests/test_ilobpcg.c:160-223): A=blkdiag(K,K), B=[[0,I],[I,0]], start [u;u]
+    mm = 50
+    rp, cc, vv = pr.laplacian_csr((mm,))
+    K = sp.csr_matrix((vv, cc, rp), shape=(mm, mm))
+    Ab = sp.block_diag([K, K]).tocsr(); Ab.sort_indices()
+    Bb = sp.bmat([[None, sp.eye(mm)], [sp.eye(mm), None]]).tocsr(); Bb.sort_indices()
+    u = pr.initial_block(mm, 6, 3)
+    cases["ilob_swap_d"] = dict(kind="csr", A=(Ab.indptr, Ab.indices, Ab.data.astype(np.float64)),
+                                B=(Bb.indptr, Bb.indices, Bb.data.astype(np.float64)),
+                                X0=np.asfortranarray(np.vstack([u, u])), nev=3, tol=1e-8, it=3000)
+    return cases
+
+
+def indefinite_runs(out):
+    for tag, c in indefinite_cases().items():
+        if c["kind"] == "bdg":
+            A = rb.op_bdg(c["grid"], c["dtype"], c["shift"], c["d"])
+            B = rb.op_diag(c["bdiag"], c["dtype"])
+        else:
+            A, B = rb.op_csr(*c["A"]), rb.op_csr(*c["B"])
+        r = rb.solve(A, c["X0"], c["nev"], c["tol"], c["it"], B=B, indefinite=True)
+        out[f"run_{tag}_eig"] = r["eig"]
+        out[f"run_{tag}_res"] = r["res"]
+        out[f"run_{tag}_sig"] = r["sig"]
+        out[f"run_{tag}_meta"] = np.array([r["iter"], r["converged"], c["nev"], c["X0"].shape[1]])
+        print(tag, "iter", r["iter"], "conv", r["converged"], r["eig"][:c["nev"]], r["sig"][:c["nev"]])
+
+
 if __name__ == "__main__":
     if not rb.available():
         raise SystemExit("build oracle/_ref first: make -C oracle")
@@ -173,5 +213,8 @@ if __name__ == "__main__":
     out = {}
     single_calls(out)
     solver_runs(out)
+    indefinite_runs(out)
     np.savez_compressed(OUT / "reference_runs.npz", **out)
-    print("wrote", OUT / "reference_runs.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB")
+    print("wrote", OUT / "reference_runs.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB", flush=True)
+    import os
+    os._exit(0)  # skip interpreter teardown (operator handles would be freed after the library is gone)

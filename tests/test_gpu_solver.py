@@ -206,6 +206,46 @@ def test_c2_size_csr_passes_keep_invariants(ctx):
     assert np.allclose(rn, r["res"][:nev], rtol=0.25)   # ||A|| is a 10-step power estimate
 
 
+def _indefinite_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_cases", GOLD / "make_golden.py")
+    # make_golden imports oracle.ref_bindings at module level; that import is cheap and does not load _ref
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.indefinite_cases()
+
+
+@pytest.mark.parametrize("tag", ["ilob_bdg_z", "ilob_bdg_d", "ilob_swap_d"])
+def test_ilobpcg_matches_reference(tag):
+    """<p>_ilobpcg (reference src/core/ilobpcg_impl.inc:54) against the unmodified reference's run and, for the
+    BdG pencil, the analytic positive-signature spectrum sqrt((e+c)^2 - |d|^2)."""
+    c = _indefinite_cases()[tag]
+    if c["kind"] == "bdg":
+        A = api.bdg_op(c["grid"], c["dtype"], c["shift"], c["d"])
+        B = api.diag_op(c["bdiag"], c["dtype"])
+    else:
+        A, B = api.csr_op(*c["A"]), api.csr_op(*c["B"])
+    r = api.lobpcg(A, c["X0"], c["nev"], c["tol"], c["it"], B=B, indefinite=True)
+    nev = c["nev"]
+    _, conv_ref, _, _ = REF[f"run_{tag}_meta"]
+    assert r["converged"] == conv_ref == nev
+    assert relerr(r["eig"][:nev], REF[f"run_{tag}_eig"][:nev]) < 1e-10
+    assert np.all(r["res"][:nev] <= c["tol"])
+    assert np.all(r["sig"][:nev] == 1) and np.all(REF[f"run_{tag}_sig"][:nev] == 1)
+    if c["kind"] == "bdg":
+        assert relerr(r["eig"][:nev], pr.bdg_eigs(c["grid"], nev, c["shift"], abs(c["d"]))) < 1e-10
+        X = r["X"]
+        G = X.conj().T @ (c["bdiag"][:, None] * X)
+        assert np.linalg.norm(G[:nev, :nev] - np.eye(nev)) < 1e-8      # B-orthonormal, positive signature
+
+
+def test_ilobpcg_requires_B(capfd):
+    A = api.stencil_op((20,), np.float64)
+    r = api.lobpcg(A, pr.initial_block(20, 4, 1), 2, 1e-8, 10, indefinite=True)
+    assert r["iter"] == 0 and np.all(r["eig"] == 0)
+    assert "B operator must not be NULL" in capfd.readouterr().err
+
+
 def test_c11_caller_runs(tmp_path):
     """The reference-style C11 program of tests/c_caller (host callback + built-in operator + _Generic)."""
     exe = tmp_path / "caller"
