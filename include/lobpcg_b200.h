@@ -88,6 +88,8 @@ double lb2_solver_stat_work(lb2_solver *s, int i);
 unsigned long long lb2_solver_stat_calls(lb2_solver *s, int i);
 void lb2_solver_reset_stats(lb2_solver *s);
 int lb2_solver_state(lb2_solver *s, uint64_t *iter, uint64_t *converged, int *use_ortho);
+/* Ritz values (first neig) and residual norms (first nres) of the last pass, as doubles, without downloading X */
+int lb2_solver_results(lb2_solver *s, double *eig, int neig, double *res, int nres);
 
 /* ---- (3) kernels on device pointers -------------------------------------------------------------- */
 #define LB2_DECLARE_KERNELS(P)                                                                            \

@@ -94,6 +94,7 @@ def _declare(L):
     L.lb2_solver_stat_calls.restype = C.c_ulonglong
     L.lb2_solver_stat_calls.argtypes = [vp, ci]
     L.lb2_solver_reset_stats.argtypes = [vp]
+    L.lb2_solver_results.argtypes = [vp, C.POINTER(dbl), ci, C.POINTER(dbl), ci]
     L.lb2_solver_state.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(ci)]
     L.lb2_comm_unique_id.argtypes = [vp, C.c_char_p]
     L.lb2_ctx_attach_comm.argtypes = [vp, ci, ci, vp, C.c_char_p]
@@ -508,6 +509,13 @@ class Solver:
         it, cv, uo = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
         lib().lb2_solver_state(self.h, C.byref(it), C.byref(cv), C.byref(uo))
         return dict(iter=it.value, converged=cv.value, use_ortho=uo.value)
+
+    def results(self):
+        """(eig[0:k], res[0:nev]) of the last pass without downloading the eigenvectors."""
+        k, nev = self.state_.k, self.state_.nev
+        e, r = (C.c_double * k)(), (C.c_double * nev)()
+        _ck(lib().lb2_solver_results(self.h, e, k, r, nev), "lb2_solver_results")
+        return np.array(e), np.array(r)
 
     def stats(self) -> dict:
         """{phase: dict(ms, work, calls)}; work = algorithmic flops (gram, tall_nn) or bytes (spmm, residual)."""

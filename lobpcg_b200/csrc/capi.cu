@@ -345,6 +345,9 @@ void lb2_solver_reset_stats(lb2_solver* s) {
   if (!s) return;
   for (int i = 0; i < PH_COUNT; i++) { s->impl->phase_ms[i] = 0; s->impl->phase_work[i] = 0; s->impl->phase_calls[i] = 0; }
 }
+int lb2_solver_results(lb2_solver* s, double* eig, int neig, double* res, int nres) {
+  return s ? s->impl->results(eig, neig, res, nres) : -1;
+}
 int lb2_solver_state(lb2_solver* s, uint64_t* iter, uint64_t* converged, int* use_ortho) {
   if (!s) return -1;
   s->impl->state(iter, converged, use_ortho);

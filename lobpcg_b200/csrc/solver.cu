@@ -109,6 +109,11 @@ class Solver : public SolverBase {
   void arena_info(void** p, size_t* bytes) override { *p = arena; *bytes = arena_bytes; }
   void set_peers(const void* lo, const void* hi) override { peer_lo = (const char*)lo; peer_hi = (const char*)hi; }
   int prepare() override;
+  int results(double* eig, int neig, double* res, int nres) override {
+    for (int i = 0; i < neig && i < k; i++) eig[i] = (double)hEig[i];
+    for (int i = 0; i < nres && i < nev; i++) res[i] = (double)hRes[i];
+    return 0;
+  }
   void state(uint64_t* it, uint64_t* cv, int* uo) override {
     if (it) *it = iter;
     if (cv) *cv = conv;

@@ -102,6 +102,7 @@ struct SolverBase {
   virtual int step(int max_steps) = 0;
   virtual int finish() = 0;
   virtual void state(uint64_t* iter, uint64_t* conv, int* use_ortho) = 0;
+  virtual int results(double* eig, int neig, double* res, int nres) = 0;  // host copies of the last pass
   double phase_ms[PH_COUNT] = {0};
   double phase_work[PH_COUNT] = {0};   // algorithmic flops (gram, tall_nn) or bytes (spmm, residual)
   uint64_t phase_calls[PH_COUNT] = {0};
