@@ -156,6 +156,194 @@ __global__ void __launch_bounds__(WM* WN * 32, OCC)
 }
 
 // =====================================================================================================
+// c64 (double complex) on the FP64 tensor pipe: a complex MAC is four real DMMAs on the (re, im) parts of the
+// fragments.  Tiles hold interleaved complex elements (16 bytes, one cp.async each, always aligned); fragments are
+// read with 128-bit shared loads, conflict-free with a row stride == 4 (mod 8) complex elements ([col][k] tiles)
+// or == 2 (mod 8) ([k][row] tiles).
+// =====================================================================================================
+template <int NCOLS, int RUN, int LDS, int NT>
+__device__ __forceinline__ void load_tile_c64(c64* sm, const c64* __restrict__ base, int64_t ld, int64_t run0,
+                                              int64_t run_end, int col0, int col_end, int tid) {
+  constexpr int TOTAL = NCOLS * RUN;
+#pragma unroll
+  for (int id0 = 0; id0 < TOTAL; id0 += NT) {
+    const int id = id0 + tid;
+    if (TOTAL % NT != 0 && id >= TOTAL) break;
+    const int c = id / RUN, el = id % RUN;
+    const int64_t e = run0 + el;
+    const bool ok = (col0 + c < col_end) && (e < run_end);
+    const c64* src = ok ? base + (int64_t)(col0 + c) * ld + e : base;
+    cp_async_zfill<16>(sm + c * LDS + el, src, ok ? 16 : 0);
+  }
+}
+
+// G = A^H B (c64).  grid = (ntiles, nsplit), same split-n / deterministic reduction scheme as the real kernel.
+template <int TM, int TN, int WM, int WN, int BK, int STAGES, int OCC>
+__global__ void __launch_bounds__(WM* WN * 32, OCC)
+    gram_zmma_kernel(const c64* __restrict__ A, int64_t lda, const c64* __restrict__ B, int64_t ldb, int ma, int mb,
+                     int64_t n, int64_t rows_per_split, int upper, int ntm, c64* __restrict__ out,
+                     int64_t split_stride, int ldo) {
+  constexpr int NT = WM * WN * 32;
+  constexpr int LDS = BK + 4;
+  constexpr int MB = TM / WM / 8;
+  constexpr int NB = TN / WN / 8;
+  extern __shared__ __align__(16) unsigned char smem_raw_z[];
+  c64* As = reinterpret_cast<c64*>(smem_raw_z);
+  c64* Bs = As + (size_t)STAGES * TM * LDS;
+  int ti, tj;
+  if (upper) upper_tile(blockIdx.x, ti, tj);
+  else { ti = blockIdx.x % ntm; tj = blockIdx.x / ntm; }
+  const int m0 = ti * TM, c0 = tj * TN;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r_end = min(n, r_begin + rows_per_split);
+  const int nchunks = (r_end > r_begin) ? (int)((r_end - r_begin + BK - 1) / BK) : 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WM, wn = warp / WM;
+  const int g = lane >> 2, t = lane & 3;
+  double are[MB][NB][2], aim[MB][NB][2];
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) are[i][j][0] = are[i][j][1] = aim[i][j][0] = aim[i][j][1] = 0.0;
+  auto issue = [&](int chunk) {
+    if (chunk < nchunks) {
+      const int s = chunk % STAGES;
+      const int64_t r = r_begin + (int64_t)chunk * BK;
+      load_tile_c64<TM, BK, LDS, NT>(As + (size_t)s * TM * LDS, A, lda, r, r_end, m0, ma, tid);
+      load_tile_c64<TN, BK, LDS, NT>(Bs + (size_t)s * TN * LDS, B, ldb, r, r_end, c0, mb, tid);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) issue(s);
+  for (int chunk = 0; chunk < nchunks; chunk++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(chunk + STAGES - 1);
+    const c64* as = As + (size_t)(chunk % STAGES) * TM * LDS + (wm * MB * 8 + g) * LDS + t;
+    const c64* bs = Bs + (size_t)(chunk % STAGES) * TN * LDS + (wn * NB * 8 + g) * LDS + t;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ks++) {
+      c64 a[MB], b[NB];
+#pragma unroll
+      for (int i = 0; i < MB; i++) a[i] = as[i * 8 * LDS + ks * 4];
+#pragma unroll
+      for (int j = 0; j < NB; j++) b[j] = bs[j * 8 * LDS + ks * 4];
+#pragma unroll
+      for (int i = 0; i < MB; i++) {
+        const double nim = -a[i].im;
+#pragma unroll
+        for (int j = 0; j < NB; j++) {   // conj(a) * b
+          dmma884(are[i][j], a[i].re, b[j].re);
+          dmma884(are[i][j], a[i].im, b[j].im);
+          dmma884(aim[i][j], a[i].re, b[j].im);
+          dmma884(aim[i][j], nim, b[j].re);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  c64* o = out + (int64_t)blockIdx.y * split_stride;
+#pragma unroll
+  for (int i = 0; i < MB; i++) {
+    const int row = m0 + wm * MB * 8 + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const int col = c0 + wn * NB * 8 + j * 8 + 2 * t;
+      if (row < ma) {
+        if (col < mb) o[row + (int64_t)col * ldo] = c64{are[i][j][0], aim[i][j][0]};
+        if (col + 1 < mb) o[row + (int64_t)(col + 1) * ldo] = c64{are[i][j][1], aim[i][j][1]};
+      }
+    }
+  }
+}
+
+// Out = alpha S C + beta Out (c64)
+template <int TM, int TN, int WM, int WN, int BK, int STAGES, int OCC>
+__global__ void __launch_bounds__(WM* WN * 32, OCC)
+    tall_nn_zmma_kernel(const c64* __restrict__ S, int64_t lds, const c64* __restrict__ C, int ldc,
+                        c64* __restrict__ Out, int64_t ldo, int64_t n, int kd, int nb, int nct, c64 alpha, c64 beta,
+                        int beta_zero) {
+  constexpr int NT = WM * WN * 32;
+  constexpr int LDA = TM + 2;
+  constexpr int LDB = BK + 4;
+  constexpr int MB = TM / WM / 8;
+  constexpr int NB = TN / WN / 8;
+  extern __shared__ __align__(16) unsigned char smem_raw_z[];
+  c64* Ss = reinterpret_cast<c64*>(smem_raw_z);       // [STAGES][BK][LDA]
+  c64* Cs = Ss + (size_t)STAGES * BK * LDA;            // [STAGES][TN][LDB]
+  const int ct = blockIdx.x % nct;
+  const int64_t rt = blockIdx.x / nct;
+  const int64_t r0 = rt * TM;
+  const int c0 = ct * TN;
+  const int nchunks = (kd + BK - 1) / BK;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WM, wn = warp / WM;
+  const int g = lane >> 2, t = lane & 3;
+  double are[MB][NB][2], aim[MB][NB][2];
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) are[i][j][0] = are[i][j][1] = aim[i][j][0] = aim[i][j][1] = 0.0;
+  auto issue = [&](int chunk) {
+    if (chunk < nchunks) {
+      const int s = chunk % STAGES;
+      const int k0 = chunk * BK;
+      load_tile_c64<BK, TM, LDA, NT>(Ss + (size_t)s * BK * LDA, S, lds, r0, n, k0, kd, tid);
+      load_tile_c64<TN, BK, LDB, NT>(Cs + (size_t)s * TN * LDB, C, ldc, k0, kd, c0, nb, tid);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) issue(s);
+  for (int chunk = 0; chunk < nchunks; chunk++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(chunk + STAGES - 1);
+    const c64* as = Ss + (size_t)(chunk % STAGES) * BK * LDA + t * LDA + wm * MB * 8 + g;
+    const c64* bs = Cs + (size_t)(chunk % STAGES) * TN * LDB + (wn * NB * 8 + g) * LDB + t;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ks++) {
+      c64 a[MB], b[NB];
+#pragma unroll
+      for (int i = 0; i < MB; i++) a[i] = as[ks * 4 * LDA + i * 8];
+#pragma unroll
+      for (int j = 0; j < NB; j++) b[j] = bs[j * 8 * LDB + ks * 4];
+#pragma unroll
+      for (int i = 0; i < MB; i++) {
+        const double nim = -a[i].im;
+#pragma unroll
+        for (int j = 0; j < NB; j++) {   // a * b
+          dmma884(are[i][j], a[i].re, b[j].re);
+          dmma884(are[i][j], nim, b[j].im);
+          dmma884(aim[i][j], a[i].re, b[j].im);
+          dmma884(aim[i][j], a[i].im, b[j].re);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < MB; i++) {
+    const int64_t row = r0 + wm * MB * 8 + i * 8 + g;
+    if (row >= n) continue;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const int col = c0 + wn * NB * 8 + j * 8 + 2 * t;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        if (col + q < nb) {
+          c64* p = Out + row + (int64_t)(col + q) * ldo;
+          c64 v = mul_(alpha, c64{are[i][j][q], aim[i][j][q]});
+          if (!beta_zero) v = add_(v, mul_(beta, *p));
+          *p = v;
+        }
+      }
+    }
+  }
+}
+
+// =====================================================================================================
 // Generic SIMT Gram (all scalar types): 64x64 tile, BK=16, 256 threads x (4x4) outputs.
 // =====================================================================================================
 template <typename T>
@@ -461,6 +649,54 @@ static int launch_gram_simt(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A,
   return 0;
 }
 
+
+static int launch_gram_zmma(lb2_ctx* ctx, int64_t n, int ma, int mb, const c64* A, int64_t lda, const c64* B,
+                            int64_t ldb, c64* G, int ldg, int upper) {
+  constexpr int TM = 64, TN = 64, WM = 2, WN = 2, BK = 8, STAGES = 4, OCC = 2;
+  const int ntm = (ma + TM - 1) / TM, ntn = (mb + TN - 1) / TN;
+  const int ntiles = upper ? ntm * (ntm + 1) / 2 : ntm * ntn;
+  int nsplit = (ctx->sm_count * OCC) / ntiles;
+  if (nsplit < 1) nsplit = 1;
+  const int64_t min_rows = 16 * BK;
+  if ((int64_t)nsplit * min_rows > n) nsplit = (int)((n + min_rows - 1) / min_rows);
+  if (nsplit < 1) nsplit = 1;
+  int64_t rps = (n + nsplit - 1) / nsplit;
+  rps = (rps + BK - 1) / BK * BK;
+  nsplit = (int)((n + rps - 1) / rps);
+  const int64_t split_stride = (int64_t)ma * mb;
+  c64* part = (c64*)ctx_scratch(ctx, sizeof(c64) * split_stride * nsplit);
+  if (!part) return -1;
+  constexpr size_t smem = sizeof(c64) * (size_t)STAGES * (TM + TN) * (BK + 4);
+  auto k = gram_zmma_kernel<TM, TN, WM, WN, BK, STAGES, OCC>;
+  LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<dim3(ntiles, nsplit), WM * WN * 32, smem, ctx->stream>>>(A, lda, B, ldb, ma, mb, n, rps, upper, ntm, part,
+                                                              split_stride, ma);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  const int64_t tot = (int64_t)ma * mb;
+  gram_reduce_kernel<c64><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(part, split_stride, nsplit, ma, mb,
+                                                                                 upper, G, ldg);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_nn_zmma(lb2_ctx* ctx, int64_t n, int kd, int nb, c64 alpha, const c64* S, int64_t lds, const c64* C,
+                          int ldc, c64 beta, c64* Out, int64_t ldo) {
+  constexpr int TM = 64, TN = 64, WM = 2, WN = 2, BK = 8, STAGES = 4, OCC = 2;
+  const int nct = (nb + TN - 1) / TN;
+  const int64_t nrt = (n + TM - 1) / TM;
+  constexpr size_t smem = sizeof(c64) * (size_t)STAGES * (BK * (TM + 2) + TN * (BK + 4));
+  auto k = tall_nn_zmma_kernel<TM, TN, WM, WN, BK, STAGES, OCC>;
+  LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool bz = (beta.re == 0.0 && beta.im == 0.0);
+  k<<<(unsigned)(nrt * nct), WM * WN * 32, smem, ctx->stream>>>(S, lds, C, ldc, Out, ldo, n, kd, nb, nct, alpha, beta,
+                                                               bz ? 1 : 0);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // G = A^H B.  upper != 0: A and B span the same columns of a Hermitian product (G = G^H): only tiles on
 // or above the diagonal are computed and the result is mirrored, so all of G is valid on return.
 template <typename T>
@@ -498,6 +734,9 @@ int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const
       if (tile == 96) return launch_gram_dmma<96, 96, 2, 4, 16, 3, 2>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
       return launch_gram_dmma<64, 64, 2, 2, 16, 3, 3>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
     }
+  }
+  if constexpr (std::is_same<T, c64>::value) {
+    if (!ctx->force_simt) return launch_gram_zmma(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
   }
   return launch_gram_simt<T>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
 }
@@ -553,6 +792,9 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
       }
       return rc;
     }
+  }
+  if constexpr (std::is_same<T, c64>::value) {
+    if (!ctx->force_simt && kd > 0) return launch_nn_zmma(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
   }
   const int nct = (nb + 63) / 64;
   const int64_t nrt = (n + 63) / 64;
