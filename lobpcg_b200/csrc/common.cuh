@@ -144,4 +144,19 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
+// TF32 tensor-core tile (legacy mma.sync path; SASS HMMA.1688.F32.TF32): D(16x8) += A(16x8,row) * B(8x8,col).
+// lane = 4*g + t: a0=A[g][t] a1=A[g+8][t] a2=A[g][t+4] a3=A[g+8][t+4]; b0=B[t][g] b1=B[t+4][g];
+// c0=C[g][2t] c1=C[g][2t+1] c2=C[g+8][2t] c3=C[g+8][2t+1].
+__device__ __forceinline__ void mma_tf32_1688(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// split an fp32 value into tf32 hi + tf32 lo (x ~= hi + lo to ~2^-22 relative): 3xTF32 keeps fp32-level accuracy
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(lo) : "f"(r));
+}
+
 }  // namespace lb2

@@ -344,6 +344,224 @@ __global__ void __launch_bounds__(WM* WN * 32, OCC)
 }
 
 // =====================================================================================================
+// f32 on the tensor cores: 3xTF32 (hi*hi + hi*lo + lo*hi, fp32 accumulate) through mma.sync.m16n8k8.tf32 — the
+// algorithm's own tolerances (EPS_TOL = 1e-5 for s/c, src/core/lobpcg_s.c:10) need fp32-accurate Grams, plain TF32
+// (10-bit mantissa) is not enough (SURVEY §7 hard part 2).  Same cp.async ring / split-n structure as the f64
+// kernels; tiles are [col][BK+4] floats with BK = 32 (row stride == 4 mod 32 => conflict-free fragment loads).
+// =====================================================================================================
+template <int NCOLS, int RUN, int LDS, int NT, bool VEC>
+__device__ __forceinline__ void load_tile_f32(float* sm, const float* __restrict__ base, int64_t ld, int64_t run0,
+                                              int64_t run_end, int col0, int col_end, int tid) {
+  if constexpr (VEC) {
+    constexpr int CPC = RUN / 4;
+    constexpr int TOTAL = NCOLS * CPC;
+#pragma unroll
+    for (int id0 = 0; id0 < TOTAL; id0 += NT) {
+      const int id = id0 + tid;
+      if (TOTAL % NT != 0 && id >= TOTAL) break;
+      const int c = id / CPC, ch = id % CPC;
+      const int64_t e = run0 + 4 * ch;
+      int bytes = 0;
+      const float* src = base;
+      if (col0 + c < col_end && e < run_end) {
+        const int64_t left = run_end - e;
+        bytes = left >= 4 ? 16 : (int)left * 4;
+        src = base + (int64_t)(col0 + c) * ld + e;
+      }
+      cp_async_zfill<16>(sm + c * LDS + 4 * ch, src, bytes);
+    }
+  } else {
+    constexpr int TOTAL = NCOLS * RUN;
+#pragma unroll
+    for (int id0 = 0; id0 < TOTAL; id0 += NT) {
+      const int id = id0 + tid;
+      if (TOTAL % NT != 0 && id >= TOTAL) break;
+      const int c = id / RUN, el = id % RUN;
+      const int64_t e = run0 + el;
+      const bool ok = (col0 + c < col_end) && (e < run_end);
+      cp_async_zfill<4>(sm + c * LDS + el, ok ? base + (int64_t)(col0 + c) * ld + e : base, ok ? 4 : 0);
+    }
+  }
+}
+
+template <int TM, int TN, int WM, int WN, int BK, int STAGES, bool VEC>
+__global__ void __launch_bounds__(WM* WN * 32)
+    gram_tf32_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int ma,
+                     int mb, int64_t n, int64_t rows_per_split, int upper, int ntm, float* __restrict__ out,
+                     int64_t split_stride, int ldo) {
+  constexpr int NT = WM * WN * 32;
+  constexpr int LDS = BK + 4;
+  constexpr int MB = TM / WM / 16;   // 16-row MMA blocks per warp
+  constexpr int NB = TN / WN / 8;    // 8-col MMA blocks per warp
+  extern __shared__ __align__(16) unsigned char smem_raw_f[];
+  float* As = reinterpret_cast<float*>(smem_raw_f);
+  float* Bs = As + (size_t)STAGES * TM * LDS;
+  int ti, tj;
+  if (upper) upper_tile(blockIdx.x, ti, tj);
+  else { ti = blockIdx.x % ntm; tj = blockIdx.x / ntm; }
+  const int m0 = ti * TM, c0 = tj * TN;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r_end = min(n, r_begin + rows_per_split);
+  const int nchunks = (r_end > r_begin) ? (int)((r_end - r_begin + BK - 1) / BK) : 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WM, wn = warp / WM;
+  const int g = lane >> 2, t = lane & 3;
+  float acc[MB][NB][4];
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
+  auto issue = [&](int chunk) {
+    if (chunk < nchunks) {
+      const int s = chunk % STAGES;
+      const int64_t r = r_begin + (int64_t)chunk * BK;
+      load_tile_f32<TM, BK, LDS, NT, VEC>(As + (size_t)s * TM * LDS, A, lda, r, r_end, m0, ma, tid);
+      load_tile_f32<TN, BK, LDS, NT, VEC>(Bs + (size_t)s * TN * LDS, B, ldb, r, r_end, c0, mb, tid);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) issue(s);
+  for (int chunk = 0; chunk < nchunks; chunk++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(chunk + STAGES - 1);
+    const float* as = As + (size_t)(chunk % STAGES) * TM * LDS + (wm * MB * 16 + g) * LDS + t;
+    const float* bs = Bs + (size_t)(chunk % STAGES) * TN * LDS + (wn * NB * 8 + g) * LDS + t;
+#pragma unroll
+    for (int ks = 0; ks < BK / 8; ks++) {
+      uint32_t ah[MB][4], al[MB][4], bh[NB][2], bl[NB][2];
+#pragma unroll
+      for (int i = 0; i < MB; i++) {
+        const float* p = as + i * 16 * LDS + ks * 8;
+        split_tf32(p[0], ah[i][0], al[i][0]);
+        split_tf32(p[8 * LDS], ah[i][1], al[i][1]);
+        split_tf32(p[4], ah[i][2], al[i][2]);
+        split_tf32(p[8 * LDS + 4], ah[i][3], al[i][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+        const float* p = bs + j * 8 * LDS + ks * 8;
+        split_tf32(p[0], bh[j][0], bl[j][0]);
+        split_tf32(p[4], bh[j][1], bl[j][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < MB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+          mma_tf32_1688(acc[i][j], al[i], bh[j]);
+          mma_tf32_1688(acc[i][j], ah[i], bl[j]);
+          mma_tf32_1688(acc[i][j], ah[i], bh[j]);
+        }
+    }
+  }
+  cp_async_wait<0>();
+  float* o = out + (int64_t)blockIdx.y * split_stride;
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int row = m0 + wm * MB * 16 + i * 16 + g + ((q & 2) ? 8 : 0);
+        const int col = c0 + wn * NB * 8 + j * 8 + 2 * t + (q & 1);
+        if (row < ma && col < mb) o[row + (int64_t)col * ldo] = acc[i][j][q];
+      }
+}
+
+template <int TM, int TN, int WM, int WN, int BK, int STAGES, bool VECA, bool VECB>
+__global__ void __launch_bounds__(WM* WN * 32)
+    tall_nn_tf32_kernel(const float* __restrict__ S, int64_t lds, const float* __restrict__ C, int ldc,
+                        float* __restrict__ Out, int64_t ldo, int64_t n, int kd, int nb, int nct, float alpha,
+                        float beta) {
+  constexpr int NT = WM * WN * 32;
+  constexpr int LDA = TM + 8;        // [k][row] tile, row stride == 8 mod 32
+  constexpr int LDB = BK + 4;        // [col][k] tile
+  constexpr int MB = TM / WM / 16;
+  constexpr int NB = TN / WN / 8;
+  extern __shared__ __align__(16) unsigned char smem_raw_f[];
+  float* Ss = reinterpret_cast<float*>(smem_raw_f);   // [STAGES][BK][LDA]
+  float* Cs = Ss + (size_t)STAGES * BK * LDA;          // [STAGES][TN][LDB]
+  const int ct = blockIdx.x % nct;
+  const int64_t rt = blockIdx.x / nct;
+  const int64_t r0 = rt * TM;
+  const int c0 = ct * TN;
+  const int nchunks = (kd + BK - 1) / BK;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WM, wn = warp / WM;
+  const int g = lane >> 2, t = lane & 3;
+  float acc[MB][NB][4];
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
+  auto issue = [&](int chunk) {
+    if (chunk < nchunks) {
+      const int s = chunk % STAGES;
+      const int k0 = chunk * BK;
+      load_tile_f32<BK, TM, LDA, NT, VECA>(Ss + (size_t)s * BK * LDA, S, lds, r0, n, k0, kd, tid);
+      load_tile_f32<TN, BK, LDB, NT, VECB>(Cs + (size_t)s * TN * LDB, C, ldc, k0, kd, c0, nb, tid);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) issue(s);
+  for (int chunk = 0; chunk < nchunks; chunk++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(chunk + STAGES - 1);
+    const float* as = Ss + (size_t)(chunk % STAGES) * BK * LDA + t * LDA + wm * MB * 16 + g;
+    const float* bs = Cs + (size_t)(chunk % STAGES) * TN * LDB + (wn * NB * 8 + g) * LDB + t;
+#pragma unroll
+    for (int ks = 0; ks < BK / 8; ks++) {
+      uint32_t ah[MB][4], al[MB][4], bh[NB][2], bl[NB][2];
+#pragma unroll
+      for (int i = 0; i < MB; i++) {
+        const float* p = as + ks * 8 * LDA + i * 16;
+        split_tf32(p[0], ah[i][0], al[i][0]);
+        split_tf32(p[8], ah[i][1], al[i][1]);
+        split_tf32(p[4 * LDA], ah[i][2], al[i][2]);
+        split_tf32(p[4 * LDA + 8], ah[i][3], al[i][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+        const float* p = bs + j * 8 * LDB + ks * 8;
+        split_tf32(p[0], bh[j][0], bl[j][0]);
+        split_tf32(p[4], bh[j][1], bl[j][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < MB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+          mma_tf32_1688(acc[i][j], al[i], bh[j]);
+          mma_tf32_1688(acc[i][j], ah[i], bl[j]);
+          mma_tf32_1688(acc[i][j], ah[i], bh[j]);
+        }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int64_t row = r0 + wm * MB * 16 + i * 16 + g + ((q & 2) ? 8 : 0);
+        const int col = c0 + wn * NB * 8 + j * 8 + 2 * t + (q & 1);
+        if (row < n && col < nb) {
+          float* p = Out + row + (int64_t)col * ldo;
+          float v = alpha * acc[i][j][q];
+          if (beta != 0.f) v += beta * (*p);
+          *p = v;
+        }
+      }
+}
+
+// =====================================================================================================
 // Generic SIMT Gram (all scalar types): 64x64 tile, BK=16, 256 threads x (4x4) outputs.
 // =====================================================================================================
 template <typename T>
@@ -650,6 +868,70 @@ static int launch_gram_simt(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A,
 }
 
 
+static int launch_gram_tf32(lb2_ctx* ctx, int64_t n, int ma, int mb, const float* A, int64_t lda, const float* B,
+                            int64_t ldb, float* G, int ldg, int upper) {
+  constexpr int TM = 128, TN = 128, WM = 2, WN = 4, BK = 32, STAGES = 3;
+  const int ntm = (ma + TM - 1) / TM, ntn = (mb + TN - 1) / TN;
+  const int ntiles = upper ? ntm * (ntm + 1) / 2 : ntm * ntn;
+  int nsplit = ctx->sm_count / ntiles;
+  if (nsplit < 1) nsplit = 1;
+  const int64_t min_rows = 8 * BK;
+  if ((int64_t)nsplit * min_rows > n) nsplit = (int)((n + min_rows - 1) / min_rows);
+  if (nsplit < 1) nsplit = 1;
+  int64_t rps = (n + nsplit - 1) / nsplit;
+  rps = (rps + BK - 1) / BK * BK;
+  nsplit = (int)((n + rps - 1) / rps);
+  const int64_t split_stride = (int64_t)ma * mb;
+  float* part = (float*)ctx_scratch(ctx, sizeof(float) * split_stride * nsplit);
+  if (!part) return -1;
+  const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
+  constexpr size_t smem = sizeof(float) * (size_t)STAGES * (TM + TN) * (BK + 4);
+  dim3 grid(ntiles, nsplit), block(WM * WN * 32);
+  if (vec) {
+    auto k = gram_tf32_kernel<TM, TN, WM, WN, BK, STAGES, true>;
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, block, smem, ctx->stream>>>(A, lda, B, ldb, ma, mb, n, rps, upper, ntm, part, split_stride, ma);
+  } else {
+    auto k = gram_tf32_kernel<TM, TN, WM, WN, BK, STAGES, false>;
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, block, smem, ctx->stream>>>(A, lda, B, ldb, ma, mb, n, rps, upper, ntm, part, split_stride, ma);
+  }
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  const int64_t tot = (int64_t)ma * mb;
+  gram_reduce_kernel<float><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(part, split_stride, nsplit, ma,
+                                                                                   mb, upper, G, ldg);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_nn_tf32(lb2_ctx* ctx, int64_t n, int kd, int nb, float alpha, const float* S, int64_t lds,
+                          const float* C, int ldc, float beta, float* Out, int64_t ldo) {
+  constexpr int TM = 128, TN = 128, WM = 2, WN = 4, BK = 32, STAGES = 3;
+  const int nct = (nb + TN - 1) / TN;
+  const int64_t nrt = (n + TM - 1) / TM;
+  const bool veca = (lds % 4 == 0) && ((uintptr_t)S % 16 == 0);
+  const bool vecb = (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0);
+  constexpr size_t smem = sizeof(float) * (size_t)STAGES * (BK * (TM + 8) + TN * (BK + 4));
+  const unsigned grid = (unsigned)(nrt * nct);
+  dim3 block(WM * WN * 32);
+#define LB2_NNF_LAUNCH(VA, VB)                                                                        \
+  {                                                                                                   \
+    auto k = tall_nn_tf32_kernel<TM, TN, WM, WN, BK, STAGES, VA, VB>;                                 \
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k<<<grid, block, smem, ctx->stream>>>(S, lds, C, ldc, Out, ldo, n, kd, nb, nct, alpha, beta);     \
+  }
+  if (veca && vecb) LB2_NNF_LAUNCH(true, true)
+  else if (veca) LB2_NNF_LAUNCH(true, false)
+  else if (vecb) LB2_NNF_LAUNCH(false, true)
+  else LB2_NNF_LAUNCH(false, false)
+#undef LB2_NNF_LAUNCH
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 static int launch_gram_zmma(lb2_ctx* ctx, int64_t n, int ma, int mb, const c64* A, int64_t lda, const c64* B,
                             int64_t ldb, c64* G, int ldg, int upper) {
   constexpr int TM = 64, TN = 64, WM = 2, WN = 2, BK = 8, STAGES = 4, OCC = 2;
@@ -738,6 +1020,9 @@ int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const
   if constexpr (std::is_same<T, c64>::value) {
     if (!ctx->force_simt) return launch_gram_zmma(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
   }
+  if constexpr (std::is_same<T, float>::value) {
+    if (!ctx->force_simt) return launch_gram_tf32(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+  }
   return launch_gram_simt<T>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
 }
 
@@ -795,6 +1080,9 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
   }
   if constexpr (std::is_same<T, c64>::value) {
     if (!ctx->force_simt && kd > 0) return launch_nn_zmma(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
+  }
+  if constexpr (std::is_same<T, float>::value) {
+    if (!ctx->force_simt && kd > 0) return launch_nn_tf32(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
   }
   const int nct = (nb + 63) / 64;
   const int64_t nrt = (n + 63) / 64;
