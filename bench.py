@@ -247,7 +247,7 @@ def run_ours(args):
     e2e = None
     if world == 1 and not args.no_e2e:
         X_dev = s.finish()["X"]            # any non-zero host block will do as X0; reuse the current iterate
-        passes = max(args.steps, 4)
+        passes = max(args.steps, 12)   # set-up (X0 upload, ||A||, initial RR, download) amortises over the passes
         st2 = api._setup(A, None, n, k, nev, np.float64, 1e-8, passes, None, None, False, 0)
         st2.X()[:, :] = X_dev
         s.close()

@@ -82,6 +82,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   if (!c || !key) return -1;
   if (!strcmp(key, "gram_tile")) c->gram_tile = value;
   else if (!strcmp(key, "nn_tile")) c->nn_tile = value;
+  else if (!strcmp(key, "nn_bk")) c->nn_bk = value;
   else if (!strcmp(key, "force_simt")) c->force_simt = value;
   else if (!strcmp(key, "spmm_cols")) c->spmm_cols = value;
   else return -1;

@@ -27,6 +27,7 @@ struct lb2_ctx {
   // tuning knobs (lb2_ctx_set_option)
   int gram_tile = 0;     // 0 = heuristic, 64 or 128
   int nn_tile = 0;       // 0 = heuristic
+  int nn_bk = 0;         // K chunk of the 128x128 tall_nn tile: 0/16 or 32 (tuning)
   int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
   int spmm_cols = 0;     // CSR SpMM columns per thread (0 = heuristic)
   // launch counter (bench.py "gpu_launches")

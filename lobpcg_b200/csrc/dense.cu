@@ -64,6 +64,57 @@ __device__ __forceinline__ void load_tile_f64(double* sm, const double* __restri
   }
 }
 
+// Per-thread view of the same copy: the (column, chunk) slots of a thread are the same for every K chunk, so the
+// source pointer of slot 0 is kept in a register pair and advanced by a uniform step; slot s is slot 0 plus
+// s * slot_stride in global memory and a compile-time offset in shared memory.  This removes the per-copy index
+// arithmetic (~25 integer instructions per LDGSTS in the first version, which kept the two warps of a scheduler
+// away from the DMMA pipe: ncu showed 80 % pipe utilisation with `wait` as the second stall reason).
+template <int NCOLS, int RUN, int LDS, int NT, bool VEC>
+struct TileLoaderF64 {
+  static constexpr int EPC = VEC ? 2 : 1;             // elements per copy
+  static constexpr int CPC = RUN / EPC;               // copies per column
+  static constexpr int TOTAL = NCOLS * CPC;
+  static constexpr int NSLOT = TOTAL / NT;
+  static constexpr int CSTEP = NT / CPC;              // columns between consecutive slots of a thread
+  static_assert(TOTAL % NT == 0 && NT % CPC == 0, "tile / thread-count mismatch");
+  const double* p;        // slot-0 source for the current chunk
+  int64_t slot_stride;    // CSTEP * ld
+  int soff;               // slot-0 offset inside a stage
+  int roff;               // offset of this thread's copy inside the run
+  unsigned colmask;       // bit s: column of slot s exists
+  __device__ __forceinline__ void init(const double* base, int64_t ld, int64_t run0, int col0, int col_end, int tid) {
+    const int c = tid / CPC, ch = tid % CPC;
+    roff = ch * EPC;
+    soff = c * LDS + roff;
+    slot_stride = (int64_t)CSTEP * ld;
+    colmask = 0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++)
+      if (col0 + c + s * CSTEP < col_end) colmask |= 1u << s;
+    // clamp the pointer of non-existing columns to a valid address (never dereferenced: src-size 0)
+    p = base + (int64_t)(col0 + c) * ld + run0 + roff;
+  }
+  // copy one chunk into `stage`; `valid` = number of run elements that exist from the start of this chunk
+  __device__ __forceinline__ void issue(double* stage, const double* safe, int64_t valid) const {
+    if (valid >= RUN) {
+#pragma unroll
+      for (int s = 0; s < NSLOT; s++) {
+        const bool ok = (colmask >> s) & 1u;
+        cp_async_zfill<EPC * 8>(stage + soff + s * CSTEP * LDS, ok ? p + s * slot_stride : safe, ok ? EPC * 8 : 0);
+      }
+    } else {
+      const int64_t left = valid - roff;
+      const int bytes = left >= EPC ? EPC * 8 : (left > 0 ? (int)left * 8 : 0);
+#pragma unroll
+      for (int s = 0; s < NSLOT; s++) {
+        const bool ok = ((colmask >> s) & 1u) && bytes > 0;
+        cp_async_zfill<EPC * 8>(stage + soff + s * CSTEP * LDS, ok ? p + s * slot_stride : safe, ok ? bytes : 0);
+      }
+    }
+  }
+  __device__ __forceinline__ void advance(int64_t step) { p += step; }
+};
+
 // upper-triangular tile enumeration: t -> (i <= j)
 __device__ __forceinline__ void upper_tile(int t, int& i, int& j) {
   j = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
@@ -106,25 +157,35 @@ __global__ void __launch_bounds__(WM* WN * 32, OCC)
 #pragma unroll
     for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  auto issue = [&](int chunk) {
-    if (chunk < nchunks) {
-      const int s = chunk % STAGES;
-      const int64_t r = r_begin + (int64_t)chunk * BK;
-      load_tile_f64<TM, BK, LDS, NT, VEC>(As + (size_t)s * TM * LDS, A, lda, r, r_end, m0, ma, tid);
-      load_tile_f64<TN, BK, LDS, NT, VEC>(Bs + (size_t)s * TN * LDS, B, ldb, r, r_end, c0, mb, tid);
+  TileLoaderF64<TM, BK, LDS, NT, VEC> la;
+  TileLoaderF64<TN, BK, LDS, NT, VEC> lb;
+  la.init(A, lda, r_begin, m0, ma, tid);
+  lb.init(B, ldb, r_begin, c0, mb, tid);
+  int issued = 0, wstage = 0;
+  auto issue = [&]() {
+    if (issued < nchunks) {
+      const int64_t valid = (r_end - r_begin) - (int64_t)issued * BK;
+      la.issue(As + wstage * (TM * LDS), A, valid);
+      lb.issue(Bs + wstage * (TN * LDS), B, valid);
+      la.advance(BK);
+      lb.advance(BK);
     }
+    issued++;
+    wstage = (wstage + 1 == STAGES) ? 0 : wstage + 1;
     cp_async_commit();
   };
 
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; s++) issue(s);
+  for (int s = 0; s < STAGES - 1; s++) issue();
 
+  int rstage = 0;
   for (int chunk = 0; chunk < nchunks; chunk++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    issue(chunk + STAGES - 1);
-    const double* as = As + (size_t)(chunk % STAGES) * TM * LDS + (wm * MB * 8 + g) * LDS + t;
-    const double* bs = Bs + (size_t)(chunk % STAGES) * TN * LDS + (wn * NB * 8 + g) * LDS + t;
+    issue();
+    const double* as = As + rstage * (TM * LDS) + (wm * MB * 8 + g) * LDS + t;
+    const double* bs = Bs + rstage * (TN * LDS) + (wn * NB * 8 + g) * LDS + t;
+    rstage = (rstage + 1 == STAGES) ? 0 : rstage + 1;
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ks++) {
       double a[MB], b[NB];
@@ -671,24 +732,45 @@ __global__ void __launch_bounds__(WM* WN * 32)
 #pragma unroll
     for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  auto issue = [&](int chunk) {
-    if (chunk < nchunks) {
-      const int s = chunk % STAGES;
-      const int k0 = chunk * BK;
-      load_tile_f64<BK, TM, LDA, NT, VECA>(Ss + (size_t)s * BK * LDA, S, lds, r0, n, k0, kd, tid);
-      load_tile_f64<TN, BK, LDB, NT, VECB>(Cs + (size_t)s * TN * LDB, C, ldc, k0, kd, c0, nb, tid);
+  // S tile: BK columns (k) x TM contiguous rows; rows beyond n are fixed per thread, k beyond kd only in the tail
+  TileLoaderF64<BK, TM, LDA, NT, VECA> la;
+  TileLoaderF64<TN, BK, LDB, NT, VECB> lb;
+  la.init(S, lds, r0, 0, BK, tid);
+  lb.init(C, ldc, 0, c0, nb, tid);
+  const int64_t rows_valid = n - r0;
+  int issued = 0, wstage = 0;
+  auto issue = [&]() {
+    if (issued < nchunks) {
+      const int kleft = kd - issued * BK;
+      if (kleft >= BK) {
+        la.issue(Ss + wstage * (BK * LDA), S, rows_valid);
+      } else {   // tail chunk: only the first kleft k-columns exist
+        TileLoaderF64<BK, TM, LDA, NT, VECA> lt = la;
+        lt.colmask = 0;
+#pragma unroll
+        for (int s = 0; s < lt.NSLOT; s++)
+          if (tid / lt.CPC + s * lt.CSTEP < kleft) lt.colmask |= 1u << s;
+        lt.issue(Ss + wstage * (BK * LDA), S, rows_valid);
+      }
+      lb.issue(Cs + wstage * (TN * LDB), C, (int64_t)kleft);
+      la.advance((int64_t)BK * lds);
+      lb.advance(BK);
     }
+    issued++;
+    wstage = (wstage + 1 == STAGES) ? 0 : wstage + 1;
     cp_async_commit();
   };
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; s++) issue(s);
+  for (int s = 0; s < STAGES - 1; s++) issue();
 
+  int rstage = 0;
   for (int chunk = 0; chunk < nchunks; chunk++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    issue(chunk + STAGES - 1);
-    const double* as = Ss + (size_t)(chunk % STAGES) * BK * LDA + t * LDA + wm * MB * 8 + g;
-    const double* bs = Cs + (size_t)(chunk % STAGES) * TN * LDB + (wn * NB * 8 + g) * LDB + t;
+    issue();
+    const double* as = Ss + rstage * (BK * LDA) + t * LDA + wm * MB * 8 + g;
+    const double* bs = Cs + rstage * (TN * LDB) + (wn * NB * 8 + g) * LDB + t;
+    rstage = (rstage + 1 == STAGES) ? 0 : rstage + 1;
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ks++) {
       double a[MB], b[NB];
@@ -1063,8 +1145,12 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
       const int forced = ctx->nn_tile;
       const int nfull = (forced == 0 || forced == 128) ? nb / 128 : 0;
       int rc = 0;
-      if (nfull > 0)
-        rc = launch_nn_dmma<128, 128, 2, 4, 16, 4>(ctx, n, kd, nfull * 128, alpha, S, lds, C, ldc, beta, Out, ldo);
+      if (nfull > 0) {
+        if (ctx->nn_bk != 16)
+          rc = launch_nn_dmma<128, 128, 2, 4, 32, 3>(ctx, n, kd, nfull * 128, alpha, S, lds, C, ldc, beta, Out, ldo);
+        else
+          rc = launch_nn_dmma<128, 128, 2, 4, 16, 4>(ctx, n, kd, nfull * 128, alpha, S, lds, C, ldc, beta, Out, ldo);
+      }
       const int rem = nb - nfull * 128;
       if (rc == 0 && rem > 0) {
         const double* Cr = C + (int64_t)nfull * 128 * ldc;
