@@ -4,6 +4,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "context.h"
@@ -30,6 +31,64 @@ void* ctx_scratch(lb2_ctx* ctx, size_t bytes) {
   return ctx->ws;
 }
 }  // namespace lb2
+
+// Structure detection for CSR input: if the matrix is exactly a Dirichlet 3/5/7-point stencil in natural ordering
+// (offsets {0,+-1,+-gx,+-gx*gy}, neighbour present iff inside the grid, one constant off-diagonal value, arbitrary
+// real diagonal) it is applied by the matrix-free stencil kernel with the diagonal as `potential`: per column that
+// reads 8 n bytes of diagonal (L2-resident across columns) instead of gathering 7 X values per row through L2.
+// Anything else (or LB2_CSR_NO_STENCIL_DETECT=1) takes the general CSR kernel.
+template <typename T>
+static bool detect_stencil(int64_t n, const int64_t* rp, const int32_t* col, const T* val, int64_t& gx, int64_t& gy,
+                           int64_t& gz, double& coff, std::vector<real_t<T>>& diag) {
+  if (getenv("LB2_CSR_NO_STENCIL_DETECT")) return false;
+  if (n < 2) return false;
+  int64_t a = 0, b = 0;   // second and third positive offsets
+  for (int64_t p = rp[0]; p < rp[1]; p++) {   // row 0 of a stencil: neighbours +1, +gx, +gx*gy
+    const int64_t o = col[p];
+    if (o == 0 || o == 1) continue;
+    if (!a) a = o; else if (!b) b = o; else return false;
+  }
+  gx = a ? a : n;
+  if (n % gx) return false;
+  gy = b ? b / gx : (a ? n / gx : 1);
+  if (b && (b % gx)) return false;
+  if (gy < 1 || (n / gx) % gy) return false;
+  gz = n / (gx * gy);
+  if (gx < 2 || gx * gy * gz != n) return false;
+  diag.assign((size_t)n, real_t<T>(0));
+  bool have_c = false;
+  double c = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t x = i % gx, y = (i / gx) % gy, z = i / (gx * gy);
+    const int64_t exp_off[6] = {-gx * gy, -gx, -1, 1, gx, gx * gy};
+    const bool exp_ok[6] = {z > 0, y > 0, x > 0, x + 1 < gx, y + 1 < gy, z + 1 < gz};
+    int64_t p = rp[i];
+    bool saw_diag = false;
+    for (int e = 0; e < 6; e++) {
+      // entries are ascending in column: the diagonal sits between offset -1 and +1
+      if (e == 3) {
+        if (p < rp[i + 1] && col[p] == i) {
+          if (Sc<T>::cplx && ((const real_t<T>*)&val[p])[1] != 0) return false;
+          diag[(size_t)i] = real_(val[p]);
+          saw_diag = true;
+          p++;
+        }
+      }
+      if (!exp_ok[e]) continue;
+      if (p >= rp[i + 1] || col[p] != i + exp_off[e]) return false;
+      if (Sc<T>::cplx && ((const real_t<T>*)&val[p])[1] != 0) return false;
+      const double v = (double)real_(val[p]);
+      if (!have_c) { c = v; have_c = true; }
+      else if (v != c) return false;
+      p++;
+    }
+    if (p != rp[i + 1]) return false;
+    (void)saw_diag;
+  }
+  if (!have_c) return false;
+  coff = c;
+  return true;
+}
 
 extern "C" {
 
@@ -249,6 +308,37 @@ void* lb2_op_bdg(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, 
 void* lb2_op_csr(char prefix, int64_t n, const int64_t* rowptr_host, const int32_t* col_host, const void* val_host) {
   if (!valid_prefix(prefix) || n < 1 || !rowptr_host || !col_host || !val_host) return nullptr;
   if (!lb2_default_ctx()) return nullptr;
+  {
+    int64_t gx = 0, gy = 0, gz = 0;
+    double coff = 0;
+    bool st = false, const_diag = false;
+    double diag0 = 0;
+    void* pot = nullptr;
+    auto finish = [&](auto& dg) {
+      if (!st) return;
+      const_diag = true;
+      diag0 = (double)dg[0];
+      for (size_t i = 1; i < dg.size() && const_diag; i++) const_diag = (dg[i] == dg[0]);
+      pot = upload(dg.data(), sizeof(dg[0]) * dg.size());
+    };
+    if (prefix == 'd') { std::vector<double> dg; st = detect_stencil<double>(n, rowptr_host, col_host, (const double*)val_host, gx, gy, gz, coff, dg); finish(dg); }
+    else if (prefix == 's') { std::vector<float> dg; st = detect_stencil<float>(n, rowptr_host, col_host, (const float*)val_host, gx, gy, gz, coff, dg); finish(dg); }
+    else if (prefix == 'z') { std::vector<double> dg; st = detect_stencil<c64>(n, rowptr_host, col_host, (const c64*)val_host, gx, gy, gz, coff, dg); finish(dg); }
+    else { std::vector<float> dg; st = detect_stencil<c32>(n, rowptr_host, col_host, (const c32*)val_host, gx, gy, gz, coff, dg); finish(dg); }
+    if (st && pot) {
+      BuiltinOp* b = new_builtin(OP_STENCIL, prefix, n);
+      b->gx = gx; b->gy = gy; b->gz = gz; b->cdiag = 0.0; b->coff = coff;
+      b->potential = pot;
+      if (const_diag) {   // constant diagonal: no per-point array at all
+        cudaFree(pot);
+        b->potential = nullptr;
+        b->cdiag = diag0;
+      }
+      b->nnz = rowptr_host[n];   // kept for the CSR traffic accounting of the solver statistics
+      b->from_csr = 1;
+      return wrap_builtin(b);
+    }
+  }
   BuiltinOp* b = new_builtin(OP_CSR, prefix, n);
   b->nnz = rowptr_host[n];
   b->rowptr = (int64_t*)upload(rowptr_host, sizeof(int64_t) * (size_t)(n + 1));

@@ -273,7 +273,7 @@ int Solver<T>::apply(const LinOpRaw* op, int nc, const T* X, T* Y) {
     int rc = apply_builtin<T>(ctx, b, nc, X, n, Y, n);
     tm.end();
     double bytes = 2.0 * (double)n * nc * sizeof(T);
-    if (b->kind == OP_CSR) bytes += (double)b->nnz * (sizeof(T) + 4) + 8.0 * (double)(b->n + 1);
+    if (b->kind == OP_CSR || b->from_csr) bytes += (double)b->nnz * (sizeof(T) + 4) + 8.0 * (double)(b->n + 1);
     if (b->kind == OP_DIAG) bytes += (double)n * sizeof(R);
     phase_work[PH_SPMM] += bytes;
     phase_calls[PH_SPMM]++;

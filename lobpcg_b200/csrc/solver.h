@@ -74,6 +74,7 @@ struct BuiltinOp {
   int32_t* col;
   void* val;
   int64_t nnz;
+  int from_csr;     // stencil operator recognised from CSR input (capi.cu: detect_stencil)
   // diag
   void* diag;
   // back pointer for host matvec shim

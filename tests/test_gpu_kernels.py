@@ -5,6 +5,7 @@ Tolerances: the kernels are floating point; sums are re-associated (split-n part
 order), so parity is `rtol` relative to the magnitude of the result: 1e-12 (d,z), 2e-5 (s,c).  Generators
 and integer index work (fill_uniform) are bit-exact."""
 import json
+import os
 from pathlib import Path
 
 import numpy as np
@@ -180,7 +181,14 @@ def test_stencil_and_csr_match_oracle(ctx, dt, grid):
         dX = api.DeviceArray.from_numpy(ctx, X)
         close(api.stencil_op(grid, dt).apply(ctx, dX).numpy(ctx), ref, rtol(dt))
         rp, c, v = pr.laplacian_csr(grid)
+        # CSR input that is a Dirichlet stencil is recognised and routed to the stencil kernel (capi.cu:
+        # detect_stencil); LB2_CSR_NO_STENCIL_DETECT forces the general CSR kernel — both must match the oracle
         close(api.csr_op(rp, c, v.astype(dt)).apply(ctx, dX).numpy(ctx), ref, rtol(dt))
+        os.environ["LB2_CSR_NO_STENCIL_DETECT"] = "1"
+        try:
+            close(api.csr_op(rp, c, v.astype(dt)).apply(ctx, dX).numpy(ctx), ref, rtol(dt))
+        finally:
+            del os.environ["LB2_CSR_NO_STENCIL_DETECT"]
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.complex128])
@@ -274,3 +282,26 @@ def test_stencil_z_slabs_with_halo_planes_reproduce_the_global_operator(ctx, dt)
         Y = api.stencil_halo_apply(ctx, (g[0], g[1], gzl), dX.rows(row0, nl), lo, hi, n)
         out.append(Y.numpy(ctx))
     close(np.vstack(out), ref, rtol(dt))
+
+
+def test_csr_stencil_detection_handles_variable_diagonal_and_rejects_near_misses(ctx):
+    """detect_stencil (capi.cu): a CSR matrix that IS a Dirichlet stencil with an arbitrary diagonal takes the
+    stencil kernel; one changed off-diagonal value or a missing entry must fall back to the general kernel — the
+    result is checked against the oracle either way."""
+    import scipy.sparse as sp
+    g = (12, 9, 7)
+    n = int(np.prod(g))
+    rng = np.random.default_rng(21)
+    X = rand(rng, (n, 5), np.float64)
+    dX = api.DeviceArray.from_numpy(ctx, X)
+    pot = rng.standard_normal(n)
+    rp, c, v = pr.laplacian_csr(g, potential=pot)
+    M = sp.csr_matrix((v, c, rp), shape=(n, n))
+    close(api.csr_op(rp, c, v).apply(ctx, dX).numpy(ctx), M @ X, 1e-13)
+    v2 = v.copy(); v2[5] = -1.5                      # one off-diagonal differs
+    M2 = sp.csr_matrix((v2, c, rp), shape=(n, n))
+    close(api.csr_op(rp, c, v2).apply(ctx, dX).numpy(ctx), M2 @ X, 1e-13)
+    M3 = M.tolil(); M3[40, 41] = 0.0; M3 = M3.tocsr(); M3.eliminate_zeros(); M3.sort_indices()   # missing neighbour
+    close(api.csr_op(M3.indptr, M3.indices, M3.data).apply(ctx, dX).numpy(ctx), M3 @ X, 1e-13)
+    M4 = (M + sp.eye(n, k=3, format="csr") * 0.25).tocsr(); M4.sort_indices()                    # extra band
+    close(api.csr_op(M4.indptr, M4.indices, M4.data).apply(ctx, dX).numpy(ctx), M4 @ X, 1e-13)

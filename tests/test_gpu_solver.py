@@ -46,9 +46,12 @@ def test_c1_laplacian_2d_matches_reference_and_analytic():
     assert np.linalg.norm(X[:, :nev].T @ AX - np.diag(r["eig"][:nev])) < 1e-8
 
 
-def test_c1_as_csr_operator():
+@pytest.mark.parametrize("detect", [True, False])
+def test_c1_as_csr_operator(detect, monkeypatch):
     g, n, nev, k = (100, 100), 10000, 10, 20
     rp, c, v = pr.laplacian_csr(g)
+    if not detect:
+        monkeypatch.setenv("LB2_CSR_NO_STENCIL_DETECT", "1")   # general CSR kernel instead of the recognised stencil
     r = api.lobpcg(api.csr_op(rp, c, v), pr.initial_block(n, k, 7), nev, 1e-8, 5000)
     check_against_reference("c1", r, 1e-8)
 
