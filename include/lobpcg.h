@@ -139,6 +139,93 @@ LB2_DECLARE_STATE(z, c64, f64)
   _Generic((*alg), s_lobpcg_t *: s_lobpcg_free, d_lobpcg_t *: d_lobpcg_free,                \
            c_lobpcg_t *: c_lobpcg_free, z_lobpcg_t *: z_lobpcg_free)(alg)
 
+
+/* ---- L2-L4 helpers of the reference (reference lobpcg.h:98-555), same names and signatures, on HOST buffers ----
+ * Exported so that unit-level callers of the reference link unchanged; each call stages its operands through the
+ * device (the solver itself never does).  Workspace arguments are accepted and ignored. */
+#define LB2_DECLARE_HELPERS(P, CT, RT)                                                                         \
+  void P##_apply_block_op(const LinearOperator_##P##_t *Op, CT *restrict X, CT *restrict Y, const uint64_t n,  \
+                          const uint64_t k);                                                                   \
+  void P##_gram_self(CT *restrict U, const uint64_t n, const uint64_t k, const LinearOperator_##P##_t *B,      \
+                     CT *restrict G, const uint64_t ldg, CT *restrict wrk);                                    \
+  void P##_gram_cross(CT *restrict V, const uint64_t nv, CT *restrict U, const uint64_t nu, const uint64_t n,  \
+                      const LinearOperator_##P##_t *B, CT *restrict G, const uint64_t ldg, CT *restrict wrk);  \
+  void P##_gram_self_mat(CT *restrict U, const uint64_t n, const uint64_t k, const CT *mat, CT *restrict G,    \
+                         const uint64_t ldg, CT *restrict wrk);                                                \
+  void P##_gram_cross_mat(CT *restrict V, const uint64_t nv, CT *restrict U, const uint64_t nu,                \
+                          const uint64_t n, const CT *mat, CT *restrict G, const uint64_t ldg,                 \
+                          CT *restrict wrk);                                                                   \
+  void P##_get_residual(const uint64_t size, const uint64_t sizeSub, CT *restrict X, CT *restrict AX,          \
+                        CT *restrict R, RT *restrict eigVal, CT *restrict wrk, LinearOperator_##P##_t *A,      \
+                        LinearOperator_##P##_t *B);                                                            \
+  void P##_get_residual_norm(const uint64_t size, const uint64_t nev, CT *restrict W, RT *restrict eigVals,    \
+                             RT *restrict resNorm, CT *restrict wrk1, CT *restrict wrk2, CT *restrict wrk3,    \
+                             const RT ANorm, const RT BNorm, LinearOperator_##P##_t *B);                       \
+  uint64_t P##_svqb(const uint64_t m, const uint64_t n, const RT tau, const char drop, CT *restrict U,         \
+                    CT *restrict wrk1, CT *restrict wrk2, CT *restrict wrk3, LinearOperator_##P##_t *B);       \
+  uint64_t P##_svqb_mat(const uint64_t m, const uint64_t n, const RT tau, const char drop, CT *restrict U,     \
+                        CT *restrict mat, CT *restrict wrk1, CT *restrict wrk2, CT *restrict wrk3);            \
+  uint64_t P##_ortho_drop(const uint64_t m, const uint64_t n_u, const uint64_t n_v, const RT eps_ortho,        \
+                          const RT eps_drop, CT *restrict U, CT *restrict V, CT *restrict wrk1,                \
+                          CT *restrict wrk2, CT *restrict wrk3, LinearOperator_##P##_t *B);                    \
+  uint64_t P##_ortho_indefinite(const uint64_t m, const uint64_t n_u, const uint64_t n_v, const RT eps_ortho,  \
+                                const RT eps_drop, CT *restrict U, CT *restrict V, CT *restrict sig,           \
+                                CT *restrict wrk1, CT *restrict wrk2, CT *restrict wrk3,                       \
+                                LinearOperator_##P##_t *B);                                                    \
+  uint64_t P##_ortho_indefinite_mat(const uint64_t m, const uint64_t n_u, const uint64_t n_v,                  \
+                                    const RT eps_ortho, const RT eps_drop, CT *restrict U, CT *restrict V,     \
+                                    CT *restrict mat, CT *restrict wrk1, CT *restrict wrk2, CT *restrict wrk3); \
+  void P##_rayleigh_ritz(const uint64_t size, const uint64_t sizeSub, CT *restrict S, CT *restrict Cx,         \
+                         RT *restrict eigVal, CT *restrict wrk1, CT *restrict wrk2, CT *restrict wrk3,         \
+                         RT *restrict rr_D, LinearOperator_##P##_t *A, LinearOperator_##P##_t *B);             \
+  void P##_rayleigh_ritz_modified(const uint64_t size, const uint64_t nx, const uint64_t mult,                 \
+                                  const uint64_t nconv, const uint64_t ndrop, uint8_t *useOrtho,               \
+                                  CT *restrict S, const CT *restrict AX, CT *restrict wrk1, CT *restrict wrk2, \
+                                  CT *restrict wrk3, CT *restrict Cx, CT *restrict Cp, RT *restrict eigVal,    \
+                                  RT *restrict rr_eigvals, CT *restrict rr_tau, RT *restrict rr_D,             \
+                                  LinearOperator_##P##_t *A, LinearOperator_##P##_t *B);                       \
+  void P##_indefinite_rayleigh_ritz(const uint64_t size, const uint64_t sizeSub, CT *restrict S,               \
+                                    CT *restrict Cx, RT *restrict eigVal, int8_t *restrict signature,          \
+                                    CT *restrict wrk1, CT *restrict wrk2, CT *restrict wrk3, CT *restrict wrk4, \
+                                    uint64_t *restrict rr_indices, CT *restrict rr_ggev,                       \
+                                    LinearOperator_##P##_t *A, LinearOperator_##P##_t *B);                     \
+  void P##_indefinite_rayleigh_ritz_modified(                                                                  \
+      const uint64_t size, const uint64_t nx, const uint64_t mult, const uint64_t nconv, const uint64_t ndrop, \
+      CT *restrict S, const CT *restrict AX, CT *restrict wrk1, CT *restrict wrk2, CT *restrict wrk3,          \
+      CT *restrict wrk4, CT *Cx, CT *restrict Cp, CT *Cx_ortho, RT *restrict eigVal, int8_t *restrict signature, \
+      int *restrict quality_flag, RT *restrict rr_eigvals, int8_t *restrict rr_sig,                            \
+      uint64_t *restrict rr_indices, CT *restrict rr_VR, CT *restrict rr_ggev, LinearOperator_##P##_t *A,      \
+      LinearOperator_##P##_t *B);                                                                              \
+  void P##_fill_random(uint64_t n, CT *x);                                                                     \
+  RT P##_estimate_norm(uint64_t size, LinearOperator_##P##_t *A, CT *wrk1, CT *wrk2);
+
+LB2_DECLARE_HELPERS(s, f32, f32)
+LB2_DECLARE_HELPERS(d, f64, f64)
+LB2_DECLARE_HELPERS(c, c32, f32)
+LB2_DECLARE_HELPERS(z, c64, f64)
+
+#define LB2_G4(x, name) _Generic((x), f32 *: s_##name, f64 *: d_##name, c32 *: c_##name, c64 *: z_##name)
+#define get_residual(size, sizeSub, X, AX, R, eigVal, wrk, A, B) LB2_G4(X, get_residual)(size, sizeSub, X, AX, R, eigVal, wrk, A, B)
+#define get_residual_norm(size, nev, W, eigVals, resNorm, w1, w2, w3, ANorm, BNorm, B) \
+  LB2_G4(W, get_residual_norm)(size, nev, W, eigVals, resNorm, w1, w2, w3, ANorm, BNorm, B)
+#define svqb(m, n, tau, drop, U, w1, w2, w3, B) LB2_G4(U, svqb)(m, n, tau, drop, U, w1, w2, w3, B)
+#define svqb_mat(m, n, tau, drop, U, mat, w1, w2, w3) LB2_G4(U, svqb_mat)(m, n, tau, drop, U, mat, w1, w2, w3)
+#define ortho_drop(m, n_u, n_v, eo, ed, U, V, w1, w2, w3, B) LB2_G4(U, ortho_drop)(m, n_u, n_v, eo, ed, U, V, w1, w2, w3, B)
+#define ortho_indefinite(m, n_u, n_v, eo, ed, U, V, sig, w1, w2, w3, B) \
+  LB2_G4(U, ortho_indefinite)(m, n_u, n_v, eo, ed, U, V, sig, w1, w2, w3, B)
+#define ortho_indefinite_mat(m, n_u, n_v, eo, ed, U, V, mat, w1, w2, w3) \
+  LB2_G4(U, ortho_indefinite_mat)(m, n_u, n_v, eo, ed, U, V, mat, w1, w2, w3)
+#define rayleigh_ritz(size, sizeSub, S, Cx, eigVal, w1, w2, w3, rr_D, A, B) \
+  LB2_G4(S, rayleigh_ritz)(size, sizeSub, S, Cx, eigVal, w1, w2, w3, rr_D, A, B)
+#define rayleigh_ritz_modified(size, nx, mult, nconv, ndrop, useOrtho, S, AX, w1, w2, w3, Cx, Cp, eigVal, re, rt, rd, A, B) \
+  LB2_G4(S, rayleigh_ritz_modified)(size, nx, mult, nconv, ndrop, useOrtho, S, AX, w1, w2, w3, Cx, Cp, eigVal, re, rt, rd, A, B)
+#define apply_block_op(Op, X, Y, n, k) LB2_G4(X, apply_block_op)(Op, X, Y, n, k)
+#define gram_self(U, n, k, B, G, ldg, wrk) LB2_G4(U, gram_self)(U, n, k, B, G, ldg, wrk)
+#define gram_cross(V, nv, U, nu, n, B, G, ldg, wrk) LB2_G4(U, gram_cross)(V, nv, U, nu, n, B, G, ldg, wrk)
+#define gram_self_mat(U, n, k, mat, G, ldg, wrk) LB2_G4(U, gram_self_mat)(U, n, k, mat, G, ldg, wrk)
+#define gram_cross_mat(V, nv, U, nu, n, mat, G, ldg, wrk) LB2_G4(U, gram_cross_mat)(V, nv, U, nu, n, mat, G, ldg, wrk)
+#define fill_random(n, x) LB2_G4(x, fill_random)(n, x)
+
 #include "lobpcg_b200.h"
 
 #endif /* LOBPCG_B200_COMPAT_LOBPCG_H */

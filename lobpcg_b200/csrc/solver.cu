@@ -18,6 +18,7 @@
 #include "kernels.h"
 #include "smalldense.h"
 #include "solver.h"
+#include "../../include/lobpcg_b200.h"
 
 namespace lb2 {
 
@@ -109,6 +110,31 @@ class Solver : public SolverBase {
   void arena_info(void** p, size_t* bytes) override { *p = arena; *bytes = arena_bytes; }
   void set_peers(const void* lo, const void* hi) override { peer_lo = (const char*)lo; peer_hi = (const char*)hi; }
   int prepare() override;
+  // minimal set-up for the helper API: n rows, blocks of at most kmax columns, no validation of 3k <= n
+  int helper_setup(int64_t rows, int kmax, const LinOpRaw* A, const LinOpRaw* B) {
+    ng = n = rows; row0 = 0; k = kmax > 0 ? kmax : 1; nev = k;
+    opA = A; opB = B; opT = nullptr;
+    LB2_CUDA_OK(cudaSetDevice(ctx->device));
+    if (sd_init(ctx)) return 1;
+    LB2_TRY(alloc());
+    LB2_CUDA_OK(cudaMemsetAsync(Scal, 0, sizeof(R) * 16, ctx->stream));
+    prepared = true;
+    return 0;
+  }
+  int up(T* dev, const T* host, int64_t rows, int cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    LB2_CUDA_OK(cudaMemcpyAsync(dev, host, sizeof(T) * (size_t)rows * cols, cudaMemcpyHostToDevice, ctx->stream));
+    LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  int down(T* host, const T* dev, int64_t rows, int cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    LB2_CUDA_OK(cudaMemcpyAsync(host, dev, sizeof(T) * (size_t)rows * cols, cudaMemcpyDeviceToHost, ctx->stream));
+    LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  double eps_override = -1;   // helper API: caller-supplied eps_ortho / eps_drop (the drivers always pass EPS_TOL)
+  R eps_tol() const { return eps_override >= 0 ? (R)eps_override : (R)EpsTol<T>::v; }
   int results(double* eig, int neig, double* res, int nres) override {
     for (int i = 0; i < neig && i < k; i++) eig[i] = (double)hEig[i];
     for (int i = 0; i < nres && i < nev; i++) res[i] = (double)hRes[i];
@@ -120,7 +146,7 @@ class Solver : public SolverBase {
     if (uo) *uo = useOrtho;
   }
 
- private:
+ public:  // (the host-buffer helper API at the end of this file drives the same building blocks)
   lb2_ctx* ctx;
   State<T>* alg;
   bool indef;
@@ -183,6 +209,7 @@ class Solver : public SolverBase {
   int ortho_drop(T* U, int nu, T* V, int nv, int* nret, bool indefinite = false);
   int rr_indef(int m, int from_col, bool initial);
   int ortho_indef_mat(int m, int nu, int nv, T* U, const T* V, const T* mat);
+  int svqb_mat_dev(int m, int nu, T* U, const T* mat, R tau);
   int residual_pass(bool initial);
   int step_impl(int max_steps, int* passes_out);
   void print_state(bool header);
@@ -522,7 +549,7 @@ int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret, bool indefinit
             (unsigned long)nu0, (unsigned long)nv);
     return 0;
   }
-  const R eps = (R)EpsTol<T>::v;
+  const R eps = eps_tol();
   int nu = nu0;
   // indefinite metric (ortho_indefinite_impl.inc:98-105): signature matrix sig = V^H B V, kept in GA
   if (indefinite) LB2_TRY(gram_self_B(nv, V, GA));
@@ -604,6 +631,35 @@ int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret, bool indefinit
   return 0;
 }
 
+// svqb_mat (src/ortho/svqb_mat_impl.inc:49-100), drop = 'n': U (m x nu) <- U T with T from the eigendecomposition of
+// the D-scaled Gram U^H mat U.  Scratch: DinvR blocks t1/t2/c1 and Q.
+template <typename T>
+int Solver<T>::svqb_mat_dev(int m, int nu, T* U, const T* mat, R tau) {
+  if (nu == 0) return 0;
+  const size_t blk = (size_t)3 * k * k;
+  T* t1 = DinvR;
+  T* t2 = DinvR + blk;
+  T* c1 = DinvR + 2 * blk;
+  T* c2 = Q;
+  if (mat) {
+    LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, m, mat, m, U, m, t1, m));
+    LB2_TRY(sd_gemm<T>(ctx, 'H', nu, nu, m, U, m, t1, m, c1, nu));
+  } else {
+    LB2_TRY(sd_gemm<T>(ctx, 'H', nu, nu, m, U, m, U, m, c1, nu));
+  }
+  LB2_TRY(sd_dscale<T>(ctx, nu, c1, nu, D));
+  int info = 0;
+  LB2_TRY(sd_syevd_upper<T>(ctx, nu, c1, nu, Lam, &info));
+  if (info != 0) {
+    fprintf(stderr, "svqb_mat: eig failed with info=%d\n", info);
+    return 0;
+  }
+  LB2_TRY(sd_svqb_transform<T>(ctx, nu, c1, nu, Lam, D, tau, 0, c2, nu, Count));
+  LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, nu, U, m, c2, nu, t2, m));
+  LB2_CUDA_OK(cudaMemcpyAsync(U, t2, sizeof(T) * (size_t)m * nu, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
 // Coefficient-space orthogonalisation of U (m x nu) against V (m x nv) in the metric `mat` (m x m):
 // ortho_indefinite_mat + svqb_mat of the reference (src/ortho/ortho_indefinite_mat_impl.inc:52-123,
 // src/ortho/svqb_mat_impl.inc:49-100), everything on the device.  Scratch lives in DinvR / Q / GA.
@@ -615,7 +671,7 @@ int Solver<T>::ortho_indef_mat(int m, int nu, int nv, T* U, const T* V, const T*
             (unsigned long)nu, (unsigned long)nv);
     return 0;
   }
-  const R eps = (R)EpsTol<T>::v;
+  const R eps = eps_tol();
   const size_t blk = (size_t)3 * k * k;
   T* t1 = DinvR;            // m x max(nu,nv)
   T* t2 = DinvR + blk;      // m x nu
@@ -636,19 +692,7 @@ int Solver<T>::ortho_indef_mat(int m, int nu, int nv, T* U, const T* V, const T*
     LB2_TRY(sd_gemm<T>(ctx, 'H', nv, nu, m, V, m, t1, m, c1, nv));
     LB2_TRY(sd_gemm_ab<T>(ctx, 'N', m, nu, nv, make<T>(-1), V, m, c1, nv, make<T>(1), U, m));
     for (int inner = 0; inner < 3; inner++) {
-      // svqb_mat, drop = 'n'
-      LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, m, mat, m, U, m, t1, m));
-      LB2_TRY(sd_gemm<T>(ctx, 'H', nu, nu, m, U, m, t1, m, c1, nu));
-      LB2_TRY(sd_dscale<T>(ctx, nu, c1, nu, D));
-      int info = 0;
-      LB2_TRY(sd_syevd_upper<T>(ctx, nu, c1, nu, Lam, &info));
-      if (info != 0) {
-        fprintf(stderr, "svqb_mat: eig failed with info=%d\n", info);
-        return 0;
-      }
-      LB2_TRY(sd_svqb_transform<T>(ctx, nu, c1, nu, Lam, D, eps, 0, c2, nu, Count));
-      LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, nu, U, m, c2, nu, t2, m));
-      LB2_CUDA_OK(cudaMemcpyAsync(U, t2, sizeof(T) * (size_t)m * nu, cudaMemcpyDeviceToDevice, ctx->stream));
+      LB2_TRY(svqb_mat_dev(m, nu, U, mat, eps));
       // ||U^H mat U - I_sig||_F / ||U||^2
       LB2_TRY(sd_gemm<T>(ctx, 'N', m, nu, m, mat, m, U, m, t1, m));
       LB2_TRY(sd_gemm<T>(ctx, 'H', nu, nu, m, U, m, t1, m, c1, nu));
@@ -944,4 +988,357 @@ SolverBase* make_solver(lb2_ctx* ctx, char prefix, void* alg, int indefinite) {
   return nullptr;
 }
 
+// =======================================================================================================
+// Host-buffer helper API: the reference's L2-L4 helpers (reference lobpcg.h:98-555) with their original
+// signatures, so that unit-level callers link unchanged.  Every call uploads its operands, runs the same device
+// building blocks the solver uses, and downloads the result; the host workspace arguments (wrk*, rr_*) are
+// accepted and ignored.  These are convenience entry points — the solver itself never leaves the device.
+// =======================================================================================================
+template <typename T>
+struct HelperEnv {
+  State<T> st;
+  Solver<T>* s = nullptr;
+  bool ok = false;
+  HelperEnv(int64_t rows, int kmax, const LinOpRaw* A, const LinOpRaw* B) {
+    memset(&st, 0, sizeof(st));
+    lb2_ctx* ctx = lb2_default_ctx();
+    if (!ctx) return;
+    st.size = (uint64_t)rows;
+    st.sizeSub = st.nev = (uint64_t)(kmax > 0 ? kmax : 1);
+    s = new Solver<T>(ctx, &st, false);
+    ok = (s->helper_setup(rows, kmax, A, B) == 0);
+  }
+  ~HelperEnv() { delete s; }
+};
+
+template <typename T>
+static void h_apply_block_op(const LinOpRaw* op, T* X, T* Y, uint64_t n, uint64_t kc) {
+  const BuiltinOp* b = builtin_of(op);
+  if (!b) {  // foreign host operator: exactly the reference's loop (src/gram/gram_impl.inc:29-33)
+    for (uint64_t j = 0; j < kc; j++) op->matvec(op, X + j * n, Y + j * n);
+    return;
+  }
+  HelperEnv<T> e((int64_t)n, (int)std::max<uint64_t>(kc, 1), op, nullptr);
+  if (!e.ok) return;
+  Solver<T>& s = *e.s;
+  for (uint64_t c0 = 0; c0 < kc; c0 += 3 * (uint64_t)s.k) {
+    const int w = (int)std::min<uint64_t>(3 * (uint64_t)s.k, kc - c0);
+    if (s.up(s.slab[0], X + c0 * n, n, w) || s.apply(op, w, s.slab[0], s.slab[1]) || s.down(Y + c0 * n, s.slab[1], n, w)) return;
+  }
+}
+
+template <typename T>
+static void h_gram(T* V, uint64_t nv, T* U, uint64_t nu, uint64_t n, const LinOpRaw* B, T* G, bool self) {
+  // gram_self: G = U^H B U (B == NULL: upper triangle only, as syrk/herk); gram_cross: G = V^H B U (full)
+  const int kmax = (int)std::max<uint64_t>(std::max(nu, nv), 1);
+  HelperEnv<T> e((int64_t)n, kmax, nullptr, B);
+  if (!e.ok) return;
+  Solver<T>& s = *e.s;
+  T* dU = s.slab[0];
+  T* dV = self ? dU : s.slab[1];
+  if (s.up(dU, U, n, (int)nu)) return;
+  if (!self && s.up(dV, V, n, (int)nv)) return;
+  const T* BU = dU;
+  if (B) { if (s.apply(B, (int)nu, dU, s.wA)) return; BU = s.wA; }
+  const int rows = self ? (int)nu : (int)nv;
+  if (s.gram_ar(rows, (int)nu, dV, BU, s.G, (self && !B) ? 1 : 0)) return;
+  std::vector<T> h((size_t)rows * nu);
+  if (s.down(h.data(), s.G, rows, (int)nu)) return;
+  for (uint64_t j = 0; j < nu; j++)
+    for (int i = 0; i < rows; i++)
+      if (!(self && !B) || (uint64_t)i <= j) G[i + j * rows] = h[i + j * rows];
+}
+
+template <typename T>
+static void h_get_residual(uint64_t n, uint64_t kc, T* X, T* AX, T* W, real_t<T>* eig, const LinOpRaw* A, const LinOpRaw* B) {
+  HelperEnv<T> e((int64_t)n, (int)std::max<uint64_t>(kc, 1), A, B);
+  if (!e.ok) return;
+  Solver<T>& s = *e.s;
+  T* dX = s.slab[0];
+  if (s.up(dX, X, n, (int)kc)) return;
+  if (AX) { if (s.up(s.AS, AX, n, (int)kc)) return; }
+  else if (s.apply(A, (int)kc, dX, s.AS)) return;
+  const T* BX = dX;
+  if (B) { if (s.apply(B, (int)kc, dX, s.wA)) return; BX = s.wA; }
+  cudaMemcpyAsync(s.Eig, eig, sizeof(real_t<T>) * kc, cudaMemcpyHostToDevice, s.ctx->stream);
+  if (s.resid((int)kc, s.AS, BX, s.Eig, s.slab[1], nullptr)) return;
+  s.down(W, s.slab[1], n, (int)kc);
+}
+
+template <typename T>
+static void h_get_residual_norm(uint64_t n, uint64_t nev, T* W, real_t<T>* eig, real_t<T>* out, real_t<T> an, real_t<T> bn) {
+  using R = real_t<T>;
+  HelperEnv<T> e((int64_t)n, (int)std::max<uint64_t>(nev, 1), nullptr, nullptr);
+  if (!e.ok) return;
+  Solver<T>& s = *e.s;
+  if (s.up(s.slab[0], W, n, (int)nev)) return;
+  if (col_sumsq<T>(s.ctx, n, (int)nev, s.slab[0], n, s.Sums)) return;
+  std::vector<R> ss(nev);
+  cudaMemcpyAsync(ss.data(), s.Sums, sizeof(R) * nev, cudaMemcpyDeviceToHost, s.ctx->stream);
+  cudaStreamSynchronize(s.ctx->stream);
+  const R b = bn > 0 ? bn : R(1);
+  for (uint64_t i = 0; i < nev; i++) out[i] = std::sqrt(ss[i]) / (an + std::fabs(eig[i]) * b);
+}
+
+template <typename T>
+static uint64_t h_svqb(uint64_t m, uint64_t nc, real_t<T> tau, char drop, T* U, const LinOpRaw* B) {
+  if (nc == 0) return 0;
+  HelperEnv<T> e((int64_t)m, (int)nc, nullptr, B);
+  if (!e.ok) return nc;
+  Solver<T>& s = *e.s;
+  int keep = (int)nc;
+  if (s.up(s.slab[0], U, m, (int)nc) || s.svqb(s.slab[0], (int)nc, tau, drop == 'y', &keep) || s.down(U, s.slab[0], m, keep)) return nc;
+  return (uint64_t)keep;
+}
+
+template <typename T>
+static uint64_t h_ortho(uint64_t m, uint64_t nu, uint64_t nv, real_t<T> eps_ortho, T* U, T* V, const LinOpRaw* B, bool indefinite) {
+  if (nu == 0 || nv == 0) return nu;
+  HelperEnv<T> e((int64_t)m, (int)std::max(nu, nv), nullptr, B);
+  if (!e.ok) return nu;
+  Solver<T>& s = *e.s;
+  s.eps_override = (double)eps_ortho;
+  T* dV = s.slab[0];
+  T* dU = s.slab[0] + (int64_t)nv * s.n;
+  int keep = (int)nu;
+  if (s.up(dV, V, m, (int)nv) || s.up(dU, U, m, (int)nu) || s.ortho_drop(dU, (int)nu, dV, (int)nv, &keep, indefinite) ||
+      s.down(U, dU, m, keep))
+    return nu;
+  return (uint64_t)keep;
+}
+
+template <typename T>
+static void h_rr(uint64_t n, uint64_t kc, T* S, T* Cx, real_t<T>* eig, const LinOpRaw* A, const LinOpRaw* B) {
+  HelperEnv<T> e((int64_t)n, (int)kc, A, B);
+  if (!e.ok) return;
+  Solver<T>& s = *e.s;
+  if (s.up(s.Xp(), S, n, (int)kc) || s.rr_initial()) return;
+  s.down(Cx, s.Cx, kc, (int)kc);
+  cudaMemcpyAsync(eig, s.Eig, sizeof(real_t<T>) * kc, cudaMemcpyDeviceToHost, s.ctx->stream);
+  cudaStreamSynchronize(s.ctx->stream);
+}
+
+template <typename T>
+static void h_rr_mod(uint64_t n, uint64_t nx, uint64_t mult, uint64_t nconv, uint64_t nretain, uint8_t* useOrtho, T* S,
+                     const T* AX, T* Cx, T* Cp, real_t<T>* eig, const LinOpRaw* A, const LinOpRaw* B) {
+  const int m = (int)((mult - 1) * nx + nretain - (mult == 3 ? nconv : 0));
+  HelperEnv<T> e((int64_t)n, (int)nx, A, B);
+  if (!e.ok) return;
+  Solver<T>& s = *e.s;
+  if (s.up(s.Xp(), S, n, m)) return;
+  if (AX) { if (s.up(s.AS, AX, n, (int)nx)) return; }
+  else if (s.apply(A, (int)nx, s.Xp(), s.AS)) return;
+  s.useOrtho = *useOrtho;
+  if (s.rr_modified(m, (int)nx)) return;
+  *useOrtho = (uint8_t)s.useOrtho;
+  if (s.useOrtho == 2) return;
+  s.down(Cx, s.Cx, m, (int)nx);
+  s.down(Cp, s.Cp, m, (int)nx);
+  cudaMemcpyAsync(eig, s.Eig, sizeof(real_t<T>) * nx, cudaMemcpyDeviceToHost, s.ctx->stream);
+  cudaStreamSynchronize(s.ctx->stream);
+}
+
+template <typename T>
+static void h_irr(uint64_t n, uint64_t nx, int m, bool initial, T* S, const T* AX, T* Cx, T* Cp, T* Cx_ortho,
+                  real_t<T>* eig, int8_t* sig, int* quality, const LinOpRaw* A, const LinOpRaw* B) {
+  HelperEnv<T> e((int64_t)n, (int)nx, A, B);
+  if (!e.ok) return;
+  Solver<T>& s = *e.s;
+  if (s.up(s.Xp(), S, n, m)) return;
+  int from = 0;
+  if (!initial) {
+    from = (int)nx;
+    if (AX) { if (s.up(s.AS, AX, n, (int)nx)) return; }
+    else if (s.apply(A, (int)nx, s.Xp(), s.AS)) return;
+  }
+  if (s.rr_indef(m, from, initial)) return;
+  const int ncx = initial ? m : (int)nx;
+  if (initial) {
+    s.down(Cx, s.Z, m, m);   // all eigenvectors, signature-sorted
+    cudaMemcpyAsync(eig, s.Theta, sizeof(real_t<T>) * m, cudaMemcpyDeviceToHost, s.ctx->stream);
+  } else {
+    s.down(Cx, s.Cx, m, ncx);
+    s.down(Cp, s.Cp, m, ncx);
+    if (Cx_ortho) s.down(Cx_ortho, s.Cx, m, ncx);
+    cudaMemcpyAsync(eig, s.Eig, sizeof(real_t<T>) * nx, cudaMemcpyDeviceToHost, s.ctx->stream);
+    if (quality) *quality = 1;
+  }
+  cudaMemcpyAsync(sig, s.dSig, (size_t)m, cudaMemcpyDeviceToHost, s.ctx->stream);
+  cudaStreamSynchronize(s.ctx->stream);
+}
+
+// coefficient-space helpers: everything is small (m x m metric), rows = 3k >= m keeps the scratch large enough
+template <typename T>
+struct MatEnv {
+  HelperEnv<T> e;
+  T *dU = nullptr, *dV = nullptr, *dM = nullptr;
+  MatEnv(uint64_t m, uint64_t nu, uint64_t nv) : e((int64_t)(3 * std::max<uint64_t>({nu, nv, (m + 2) / 3, 1})),
+                                                     (int)std::max<uint64_t>({nu, nv, (m + 2) / 3, 1}), nullptr, nullptr) {
+    if (!e.ok) return;
+    Solver<T>& s = *e.s;
+    dM = s.G;  dU = s.Cp;  dV = s.Cx;   // G: 3k x 3k >= m x m; Cx, Cp: 3k x k >= m x n
+  }
+};
+
+template <typename T>
+static uint64_t h_svqb_mat(uint64_t m, uint64_t nc, real_t<T> tau, T* U, T* mat) {
+  if (nc == 0) return 0;
+  MatEnv<T> me(m, nc, 0);
+  if (!me.e.ok) return nc;
+  Solver<T>& s = *me.e.s;
+  if (s.up(me.dU, U, m, (int)nc) || (mat && s.up(me.dM, mat, m, (int)m))) return nc;
+  if (s.svqb_mat_dev((int)m, (int)nc, me.dU, mat ? me.dM : nullptr, tau)) return nc;
+  s.down(U, me.dU, m, (int)nc);
+  return nc;
+}
+
+template <typename T>
+static uint64_t h_ortho_indef_mat(uint64_t m, uint64_t nu, uint64_t nv, real_t<T> eps, T* U, T* V, T* mat) {
+  if (nu == 0 || nv == 0) return nu;
+  MatEnv<T> me(m, nu, nv);
+  if (!me.e.ok) return 0;
+  Solver<T>& s = *me.e.s;
+  s.eps_override = (double)eps;
+  if (s.up(me.dU, U, m, (int)nu) || s.up(me.dV, V, m, (int)nv) || s.up(me.dM, mat, m, (int)m)) return 0;
+  if (s.ortho_indef_mat((int)m, (int)nu, (int)nv, me.dU, me.dV, me.dM)) return 0;
+  s.down(U, me.dU, m, (int)nu);
+  return 0;   // the reference returns 0 ("no column dropping implemented")
+}
+
+template <typename T>
+static void h_gram_mat(T* V, uint64_t nv, T* U, uint64_t nu, uint64_t n, const T* mat, T* G, bool self) {
+  MatEnv<T> me(n, nu, nv);
+  if (!me.e.ok) return;
+  Solver<T>& s = *me.e.s;
+  T* dV = self ? me.dU : me.dV;
+  if (s.up(me.dU, U, n, (int)nu) || (!self && s.up(dV, V, n, (int)nv))) return;
+  const T* MU = me.dU;
+  if (mat) {
+    if (s.up(me.dM, mat, n, (int)n)) return;
+    if (sd_gemm<T>(s.ctx, 'N', (int)n, (int)nu, (int)n, me.dM, (int)n, me.dU, (int)n, s.Tmp, (int)n)) return;
+    MU = s.Tmp;
+  }
+  const int rows = self ? (int)nu : (int)nv;
+  if (sd_gemm<T>(s.ctx, 'H', rows, (int)nu, (int)n, dV, (int)n, MU, (int)n, s.Z, rows)) return;
+  std::vector<T> h((size_t)rows * nu);
+  if (s.down(h.data(), s.Z, rows, (int)nu)) return;
+  for (uint64_t j = 0; j < nu; j++)
+    for (int i = 0; i < rows; i++)
+      if (!(self && !mat) || (uint64_t)i <= j) G[i + j * rows] = h[i + j * rows];
+}
+
+template <typename T>
+static void h_fill_random(uint64_t n, T* x) {
+  static uint64_t calls = 0;
+  HelperEnv<T> e((int64_t)n, 1, nullptr, nullptr);
+  if (!e.ok) return;
+  Solver<T>& s = *e.s;
+  if (fill_uniform<T>(s.ctx, (int64_t)n, 1, s.slab[0], (int64_t)n, 0x5EEDULL + 7919ULL * calls++, (int64_t)n, 0)) return;
+  s.down(x, s.slab[0], n, 1);
+}
+
+template <typename T>
+static real_t<T> h_estimate_norm(uint64_t n, const LinOpRaw* A) {
+  HelperEnv<T> e((int64_t)n, 1, A, nullptr);
+  real_t<T> out = 0;
+  if (!e.ok) return out;
+  e.s->estimate_norm(A, 0xA5EEDULL, &out);
+  return out;
+}
+
 }  // namespace lb2
+
+using namespace lb2;
+extern "C" {
+#define LB2_HELPERS(P, T, RT)                                                                                         \
+  void P##_apply_block_op(const void* Op, T* X, T* Y, uint64_t n, uint64_t k) {                                        \
+    h_apply_block_op<T>((const LinOpRaw*)Op, X, Y, n, k);                                                              \
+  }                                                                                                                    \
+  void P##_gram_self(T* U, uint64_t n, uint64_t k, const void* B, T* G, uint64_t ldg, T* wrk) {                        \
+    (void)ldg; (void)wrk;                                                                                              \
+    h_gram<T>(nullptr, 0, U, k, n, (const LinOpRaw*)B, G, true);                                                       \
+  }                                                                                                                    \
+  void P##_gram_cross(T* V, uint64_t nv, T* U, uint64_t nu, uint64_t n, const void* B, T* G, uint64_t ldg, T* wrk) {   \
+    (void)ldg; (void)wrk;                                                                                              \
+    h_gram<T>(V, nv, U, nu, n, (const LinOpRaw*)B, G, false);                                                          \
+  }                                                                                                                    \
+  void P##_gram_self_mat(T* U, uint64_t n, uint64_t k, const T* mat, T* G, uint64_t ldg, T* wrk) {                     \
+    (void)ldg; (void)wrk;                                                                                              \
+    h_gram_mat<T>(nullptr, 0, U, k, n, mat, G, true);                                                                  \
+  }                                                                                                                    \
+  void P##_gram_cross_mat(T* V, uint64_t nv, T* U, uint64_t nu, uint64_t n, const T* mat, T* G, uint64_t ldg, T* wrk) { \
+    (void)ldg; (void)wrk;                                                                                              \
+    h_gram_mat<T>(V, nv, U, nu, n, mat, G, false);                                                                     \
+  }                                                                                                                    \
+  void P##_get_residual(uint64_t size, uint64_t sizeSub, T* X, T* AX, T* R, RT* eigVal, T* wrk, void* A, void* B) {    \
+    (void)wrk;                                                                                                         \
+    h_get_residual<T>(size, sizeSub, X, AX, R, eigVal, (const LinOpRaw*)A, (const LinOpRaw*)B);                        \
+  }                                                                                                                    \
+  void P##_get_residual_norm(uint64_t size, uint64_t nev, T* W, RT* eigVals, RT* resNorm, T* w1, T* w2, T* w3,         \
+                             RT ANorm, RT BNorm, void* B) {                                                            \
+    (void)w1; (void)w2; (void)w3; (void)B;                                                                             \
+    h_get_residual_norm<T>(size, nev, W, eigVals, resNorm, ANorm, BNorm);                                              \
+  }                                                                                                                    \
+  uint64_t P##_svqb(uint64_t m, uint64_t n, RT tau, char drop, T* U, T* w1, T* w2, T* w3, void* B) {                   \
+    (void)w1; (void)w2; (void)w3;                                                                                      \
+    return h_svqb<T>(m, n, tau, drop, U, (const LinOpRaw*)B);                                                          \
+  }                                                                                                                    \
+  uint64_t P##_svqb_mat(uint64_t m, uint64_t n, RT tau, char drop, T* U, T* mat, T* w1, T* w2, T* w3) {                \
+    (void)drop; (void)w1; (void)w2; (void)w3;                                                                          \
+    return h_svqb_mat<T>(m, n, tau, U, mat);                                                                           \
+  }                                                                                                                    \
+  uint64_t P##_ortho_drop(uint64_t m, uint64_t n_u, uint64_t n_v, RT eps_ortho, RT eps_drop, T* U, T* V, T* w1, T* w2, \
+                          T* w3, void* B) {                                                                            \
+    (void)eps_drop; (void)w1; (void)w2; (void)w3;                                                                      \
+    return h_ortho<T>(m, n_u, n_v, eps_ortho, U, V, (const LinOpRaw*)B, false);                                        \
+  }                                                                                                                    \
+  uint64_t P##_ortho_indefinite(uint64_t m, uint64_t n_u, uint64_t n_v, RT eps_ortho, RT eps_drop, T* U, T* V, T* sig, \
+                                T* w1, T* w2, T* w3, void* B) {                                                        \
+    (void)eps_drop; (void)sig; (void)w1; (void)w2; (void)w3; /* sig is recomputed as V^H B V */                        \
+    return h_ortho<T>(m, n_u, n_v, eps_ortho, U, V, (const LinOpRaw*)B, true);                                         \
+  }                                                                                                                    \
+  uint64_t P##_ortho_indefinite_mat(uint64_t m, uint64_t n_u, uint64_t n_v, RT eps_ortho, RT eps_drop, T* U, T* V,     \
+                                    T* mat, T* w1, T* w2, T* w3) {                                                     \
+    (void)eps_drop; (void)w1; (void)w2; (void)w3;                                                                      \
+    return h_ortho_indef_mat<T>(m, n_u, n_v, eps_ortho, U, V, mat);                                                    \
+  }                                                                                                                    \
+  void P##_rayleigh_ritz(uint64_t size, uint64_t sizeSub, T* S, T* Cx, RT* eigVal, T* w1, T* w2, T* w3, RT* rr_D,      \
+                         void* A, void* B) {                                                                           \
+    (void)w1; (void)w2; (void)w3; (void)rr_D;                                                                          \
+    h_rr<T>(size, sizeSub, S, Cx, eigVal, (const LinOpRaw*)A, (const LinOpRaw*)B);                                     \
+  }                                                                                                                    \
+  void P##_rayleigh_ritz_modified(uint64_t size, uint64_t nx, uint64_t mult, uint64_t nconv, uint64_t nretain,         \
+                                  uint8_t* useOrtho, T* S, const T* AX, T* w1, T* w2, T* w3, T* Cx, T* Cp, RT* eigVal, \
+                                  RT* rr_eigvals, T* rr_tau, RT* rr_D, void* A, void* B) {                             \
+    (void)w1; (void)w2; (void)w3; (void)rr_eigvals; (void)rr_tau; (void)rr_D;                                          \
+    h_rr_mod<T>(size, nx, mult, nconv, nretain, useOrtho, S, AX, Cx, Cp, eigVal, (const LinOpRaw*)A,                   \
+                (const LinOpRaw*)B);                                                                                   \
+  }                                                                                                                    \
+  void P##_indefinite_rayleigh_ritz(uint64_t size, uint64_t sizeSub, T* S, T* Cx, RT* eigVal, int8_t* signature,       \
+                                    T* w1, T* w2, T* w3, T* w4, uint64_t* rr_indices, T* rr_ggev, void* A, void* B) {  \
+    (void)w1; (void)w2; (void)w3; (void)w4; (void)rr_indices; (void)rr_ggev;                                           \
+    h_irr<T>(size, sizeSub, (int)sizeSub, true, S, nullptr, Cx, nullptr, nullptr, eigVal, signature, nullptr,          \
+             (const LinOpRaw*)A, (const LinOpRaw*)B);                                                                  \
+  }                                                                                                                    \
+  void P##_indefinite_rayleigh_ritz_modified(uint64_t size, uint64_t nx, uint64_t mult, uint64_t nconv,                \
+                                             uint64_t nretain, T* S, const T* AX, T* w1, T* w2, T* w3, T* w4, T* Cx,   \
+                                             T* Cp, T* Cx_ortho, RT* eigVal, int8_t* signature, int* quality_flag,     \
+                                             RT* rr_eigvals, int8_t* rr_sig, uint64_t* rr_indices, T* rr_VR,           \
+                                             T* rr_ggev, void* A, void* B) {                                           \
+    (void)w1; (void)w2; (void)w3; (void)w4; (void)rr_eigvals; (void)rr_sig; (void)rr_indices; (void)rr_VR;             \
+    (void)rr_ggev;                                                                                                     \
+    const int m = (int)((mult - 1) * nx + nretain - (mult == 3 ? nconv : 0));                                          \
+    h_irr<T>(size, nx, m, false, S, AX, Cx, Cp, Cx_ortho, eigVal, signature, quality_flag, (const LinOpRaw*)A,         \
+             (const LinOpRaw*)B);                                                                                      \
+  }                                                                                                                    \
+  void P##_fill_random(uint64_t n, T* x) { h_fill_random<T>(n, x); }                                                   \
+  RT P##_estimate_norm(uint64_t size, void* A, T* w1, T* w2) {                                                         \
+    (void)w1; (void)w2;                                                                                                \
+    return h_estimate_norm<T>(size, (const LinOpRaw*)A);                                                               \
+  }
+
+LB2_HELPERS(s, float, float)
+LB2_HELPERS(d, double, double)
+LB2_HELPERS(c, c32, float)
+LB2_HELPERS(z, c64, double)
+}  // extern "C"

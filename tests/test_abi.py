@@ -59,6 +59,37 @@ def test_library_loads_and_exports_declared_symbols():
     assert len(names) >= 80
 
 
+REFERENCE_HELPERS = ["get_residual", "get_residual_norm", "rayleigh_ritz", "rayleigh_ritz_modified", "svqb", "svqb_mat",
+                     "ortho_drop", "ortho_indefinite", "ortho_indefinite_mat", "indefinite_rayleigh_ritz",
+                     "indefinite_rayleigh_ritz_modified", "apply_block_op", "gram_self", "gram_cross", "gram_self_mat",
+                     "gram_cross_mat", "fill_random", "estimate_norm"]
+
+
+def test_all_80_reference_symbols_are_exported_and_declared():
+    """2 solver entry points + 18 helpers, for each of s/d/c/z (reference lobpcg.h:63-92, 98-555)."""
+    L = api.lib()
+    hdr = (INC / "lobpcg.h").read_text()
+    want = [f"{p}_{h}" for p in "sdcz" for h in ["lobpcg", "ilobpcg"] + REFERENCE_HELPERS]
+    assert len(want) == 80
+    assert not [n for n in want if not hasattr(L, n)]
+    for h in REFERENCE_HELPERS:
+        assert f"P##_{h}(" in hdr, f"{h} is not declared in include/lobpcg.h"
+
+
+@pytest.mark.skipif(not REFROOT.exists(), reason="reference tree only exists in the build container")
+def test_reference_test_programs_link_against_the_product_library():
+    """The reference's own tests, compiled unchanged against the reference's headers, resolve every symbol from
+    liblobpcg_b200.so (they are RUN on the GPU box by tests/test_gpu_reftests.py)."""
+    subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), "reftests"], check=True)
+    out = ROOT / "oracle" / "_ref" / "reftests"
+    for t in ["test_gram", "test_residual", "test_svqb", "test_ortho_drop", "test_rayleigh_ritz", "test_indefinite_rr",
+              "test_lobpcg", "test_ilobpcg"]:
+        exe = out / t
+        assert exe.exists()
+        needed = subprocess.run(["ldd", str(exe)], capture_output=True, text=True).stdout
+        assert "liblobpcg_b200.so" in needed and "libref_lobpcg" not in needed
+
+
 def test_state_struct_matches_ctypes_mirror(tmp_path):
     ours = _layout('#include "lobpcg.h"', [f"-I{INC}"], tmp_path, "ours")
     for p in "sdcz":

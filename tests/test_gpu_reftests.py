@@ -1,0 +1,58 @@
+"""The reference's OWN test programs, linked to the product library.
+
+oracle/Makefile (target `reftests`) compiles the unmodified sources of the reference's unit and integration tests
+(reference tests/test_*.c) against the reference's own headers, and links them to
+lobpcg_b200/_lib/liblobpcg_b200.so instead of the reference's objects.  Every helper and solver entry point they call
+(`d_gram_self`, `z_svqb`, `d_ortho_drop`, `d_rayleigh_ritz_modified`, `z_indefinite_rayleigh_ritz`, `d_lobpcg`,
+`z_ilobpcg`, ... — the 80 symbols of SURVEY §8b) therefore runs on the GPU, on the HOST buffers and HOST matvec
+callbacks those programs pass, and is judged by the reference's own assertions and known-answer vectors.
+
+The binaries are built in the development container (the reference tree does not exist on the GPU box) and travel
+with the snapshot under oracle/_ref/reftests/.
+
+Cases the UNMODIFIED reference itself fails in this container (reproduced with oracle/_ref) are listed in
+STALE and tolerated, nothing else is.
+"""
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+BIN = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "reftests"
+
+# name -> minimum number of passing cases (the reference's own count with its own library)
+PROGRAMS = {
+    "test_gram": 11, "test_residual": 9, "test_estimate_norm": 2, "test_svqb": 5, "test_svqb_drop": 8,
+    "test_svqb_mat": 5, "test_ortho_drop": 8, "test_ortho_indefinite": 13, "test_ortho_indefinite_mat": 2,
+    "test_rayleigh_ritz": 7, "test_indefinite_rr": 17, "test_lobpcg": 7, "test_ilobpcg": 5,
+}
+# stale/flaky cases of the reference's suite (they fail against the reference's own library too):
+#  * test_residual 10/11 expect a B-norm, the implementation uses the 2-norm (residual_impl.inc:83-98)
+#  * d_rr_modified_mult3 asserts the sign of a 1e-16 Ritz value of a rank-deficient fixture (test_rayleigh_ritz.c:653)
+STALE = {"test_residual": 2, "test_rayleigh_ritz": 1}
+
+
+def _run(name):
+    exe = BIN / name
+    if not exe.exists():
+        pytest.fail(f"{exe} is missing: run `make -C oracle reftests` in the development container")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    return r.returncode, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("name", sorted(PROGRAMS))
+def test_reference_test_program_passes_on_the_gpu_library(name):
+    rc, out = _run(name)
+    tail = out[-3000:]
+    assert rc in (0, 1), f"{name} crashed (rc={rc}):\n{tail}"
+    m = re.search(r"(\d+) passed, (\d+) failed", out)
+    m2 = re.search(r"(\d+)/(\d+) tests passed", out)   # older programs (test_residual.c:640-669, test_estimate_norm.c)
+    assert m or m2, f"{name}: no summary line\n{tail}"
+    passed = int(m.group(1)) if m else int(m2.group(1))
+    failed = int(m.group(2)) if m else int(m2.group(2)) - passed
+    assert failed <= STALE.get(name, 0), f"{name}: {failed} failing case(s)\n{tail}"
+    assert passed >= PROGRAMS[name], f"{name}: only {passed} cases passed\n{tail}"
+    if name not in STALE:
+        assert rc == 0, tail
