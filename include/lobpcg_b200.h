@@ -140,6 +140,11 @@ int lb2_ipc_get_handle(void *dev_ptr, void *out64);
 void *lb2_ipc_open_handle(const void *in64);
 int lb2_ipc_close_handle(void *mapped_ptr);
 
+/* host-only self-check of the work-list Gram schedule for a shape (no device needed): 0 = every 8x8 block of every
+ * tile owned once, rows partitioned exactly, contiguous items per CTA.  stats[4] (may be NULL): items, busiest CTA /
+ * mean CTA cost, issued / needed DMMA blocks, tiles. */
+int lb2_gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int bk, double *stats);
+
 const char *lb2_version(void);
 
 #ifdef __cplusplus

@@ -92,6 +92,10 @@ static bool detect_stencil(int64_t n, const int64_t* rp, const int32_t* col, con
 
 extern "C" {
 
+int lb2_gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int bk, double* stats) {
+  return lb2::gram_wl_plan_check(ma, mb, upper, n, ncta, bk, stats);
+}
+
 const char* lb2_version(void) { return "lobpcg_b200 0.1 (sm_100a)"; }
 
 lb2_ctx* lb2_ctx_create(int device, void* cuda_stream) {
@@ -124,6 +128,7 @@ void lb2_ctx_destroy(lb2_ctx* c) {
   cudaStreamSynchronize(c->stream);
   if (c->cublas) cublasDestroy(c->cublas);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
+  lb2::gram_wl_cache_free(c);
   if (c->ws) cudaFree(c->ws);
   if (c->solver_ws) cudaFree(c->solver_ws);
   if (c->solver_hws) free(c->solver_hws);
@@ -143,6 +148,10 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "nn_tile")) c->nn_tile = value;
   else if (!strcmp(key, "nn_bk")) c->nn_bk = value;
   else if (!strcmp(key, "force_simt")) c->force_simt = value;
+  else if (!strcmp(key, "gram_wl")) c->gram_wl = value;
+  else if (!strcmp(key, "gram_bk")) c->gram_bk = value;
+  else if (!strcmp(key, "gram_load_pct")) c->gram_load_pct = value;
+  else if (!strcmp(key, "gram_strip_max")) c->gram_strip_max = value;
   else if (!strcmp(key, "spmm_cols")) c->spmm_cols = value;
   else return -1;
   return 0;

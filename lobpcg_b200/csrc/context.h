@@ -28,6 +28,11 @@ struct lb2_ctx {
   int gram_tile = 0;     // 0 = heuristic, 64 or 128
   int nn_tile = 0;       // 0 = heuristic
   int nn_bk = 0;         // K chunk of the 128x128 tall_nn tile: 0/16 or 32 (tuning)
+  int gram_wl = -1;      // f64 Gram through the work-list kernel (gram_wl.cu): -1 = auto, 0 = never, 1 = always
+  int gram_bk = 0;       // K chunk of the work-list Gram: 0/16 or 32 (tuning)
+  int gram_strip_max = 0; // work-list Gram: ragged last tile columns narrower than this go to the lock-step kernel (0 = always, -1 = never)
+  int gram_load_pct = 0; // work-list Gram: staging-traffic cost of a tile with 256 columns in % of its DMMA time (0 = default)
+  void* gram_wl_cache = nullptr;   // lb2::WlCache* (schedules per Gram shape)
   int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
   int spmm_cols = 0;     // CSR SpMM columns per thread (0 = heuristic)
   // launch counter (bench.py "gpu_launches")
@@ -40,4 +45,5 @@ namespace lb2 {
 // returns a scratch pointer of at least `bytes` (grows, stream-ordered-safe because every user is
 // enqueued on ctx->stream and growth synchronizes first).
 void* ctx_scratch(lb2_ctx* ctx, size_t bytes);
+void gram_wl_cache_free(lb2_ctx* ctx);   // gram_wl.cu
 }  // namespace lb2

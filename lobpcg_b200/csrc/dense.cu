@@ -17,6 +17,7 @@
 #include "context.h"
 #include <cmath>
 #include "kernels.h"
+#include "tile_loader.cuh"
 
 namespace lb2 {
 
@@ -63,57 +64,6 @@ __device__ __forceinline__ void load_tile_f64(double* sm, const double* __restri
     }
   }
 }
-
-// Per-thread view of the same copy: the (column, chunk) slots of a thread are the same for every K chunk, so the
-// source pointer of slot 0 is kept in a register pair and advanced by a uniform step; slot s is slot 0 plus
-// s * slot_stride in global memory and a compile-time offset in shared memory.  This removes the per-copy index
-// arithmetic (~25 integer instructions per LDGSTS in the first version, which kept the two warps of a scheduler
-// away from the DMMA pipe: ncu showed 80 % pipe utilisation with `wait` as the second stall reason).
-template <int NCOLS, int RUN, int LDS, int NT, bool VEC>
-struct TileLoaderF64 {
-  static constexpr int EPC = VEC ? 2 : 1;             // elements per copy
-  static constexpr int CPC = RUN / EPC;               // copies per column
-  static constexpr int TOTAL = NCOLS * CPC;
-  static constexpr int NSLOT = TOTAL / NT;
-  static constexpr int CSTEP = NT / CPC;              // columns between consecutive slots of a thread
-  static_assert(TOTAL % NT == 0 && NT % CPC == 0, "tile / thread-count mismatch");
-  const double* p;        // slot-0 source for the current chunk
-  int64_t slot_stride;    // CSTEP * ld
-  int soff;               // slot-0 offset inside a stage
-  int roff;               // offset of this thread's copy inside the run
-  unsigned colmask;       // bit s: column of slot s exists
-  __device__ __forceinline__ void init(const double* base, int64_t ld, int64_t run0, int col0, int col_end, int tid) {
-    const int c = tid / CPC, ch = tid % CPC;
-    roff = ch * EPC;
-    soff = c * LDS + roff;
-    slot_stride = (int64_t)CSTEP * ld;
-    colmask = 0;
-#pragma unroll
-    for (int s = 0; s < NSLOT; s++)
-      if (col0 + c + s * CSTEP < col_end) colmask |= 1u << s;
-    // clamp the pointer of non-existing columns to a valid address (never dereferenced: src-size 0)
-    p = base + (int64_t)(col0 + c) * ld + run0 + roff;
-  }
-  // copy one chunk into `stage`; `valid` = number of run elements that exist from the start of this chunk
-  __device__ __forceinline__ void issue(double* stage, const double* safe, int64_t valid) const {
-    if (valid >= RUN) {
-#pragma unroll
-      for (int s = 0; s < NSLOT; s++) {
-        const bool ok = (colmask >> s) & 1u;
-        cp_async_zfill<EPC * 8>(stage + soff + s * CSTEP * LDS, ok ? p + s * slot_stride : safe, ok ? EPC * 8 : 0);
-      }
-    } else {
-      const int64_t left = valid - roff;
-      const int bytes = left >= EPC ? EPC * 8 : (left > 0 ? (int)left * 8 : 0);
-#pragma unroll
-      for (int s = 0; s < NSLOT; s++) {
-        const bool ok = ((colmask >> s) & 1u) && bytes > 0;
-        cp_async_zfill<EPC * 8>(stage + soff + s * CSTEP * LDS, ok ? p + s * slot_stride : safe, ok ? bytes : 0);
-      }
-    }
-  }
-  __device__ __forceinline__ void advance(int64_t step) { p += step; }
-};
 
 // upper-triangular tile enumeration: t -> (i <= j)
 __device__ __forceinline__ void upper_tile(int t, int& i, int& j) {
@@ -1061,6 +1011,35 @@ static int launch_nn_zmma(lb2_ctx* ctx, int64_t n, int kd, int nb, c64 alpha, co
   return 0;
 }
 
+// f64 Gram on the tile x equal-split grid (gram_dmma_kernel): every CTA of an n-range runs in the same wave, so the
+// operands come from HBM once and from L2 for every further tile.
+int gram_tiles_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B,
+                   int64_t ldb, double* G, int ldg, int upper) {
+  int tile = ctx->gram_tile;
+  if (tile == 0) {
+    // cost model: padded tile area (upper: tiles on/above the diagonal) x wave quantisation / relative speed
+    const int cand[3] = {128, 96, 64};
+    const int occ[3] = {1, 2, 3};
+    const double speed[3] = {1.0, 0.97, 0.85};
+    double best = 1e300;
+    for (int i = 0; i < 3; i++) {
+      const int t = cand[i];
+      const int ntm = (ma + t - 1) / t, ntn = (mb + t - 1) / t;
+      const int ntiles = upper ? ntm * (ntm + 1) / 2 : ntm * ntn;
+      const int slots = ctx->sm_count * occ[i];
+      int nsplit = slots / ntiles;
+      if (nsplit < 1) nsplit = 1;
+      const double waves = (double)(ntiles * nsplit + slots - 1) / slots;   // >= 1 when ntiles > slots
+      const double fill = (double)ntiles * nsplit / (std::ceil(waves) * slots);
+      const double cost = (double)ntiles * t * t / (speed[i] * fill);
+      if (cost < best) { best = cost; tile = t; }
+    }
+  }
+  if (tile == 128) return launch_gram_dmma<128, 128, 2, 4, 16, 4, 1>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+  if (tile == 96) return launch_gram_dmma<96, 96, 2, 4, 16, 3, 2>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+  return launch_gram_dmma<64, 64, 2, 2, 16, 3, 3>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+}
+
 // G = A^H B.  upper != 0: A and B span the same columns of a Hermitian product (G = G^H): only tiles on
 // or above the diagonal are computed and the result is mirrored, so all of G is valid on return.
 template <typename T>
@@ -1074,29 +1053,10 @@ int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const
   }
   if constexpr (std::is_same<T, double>::value) {
     if (!ctx->force_simt) {
-      int tile = ctx->gram_tile;
-      if (tile == 0) {
-        // cost model: padded tile area (upper: tiles on/above the diagonal) x wave quantisation / relative speed
-        const int cand[3] = {128, 96, 64};
-        const int occ[3] = {1, 2, 3};
-        const double speed[3] = {1.0, 0.97, 0.85};
-        double best = 1e300;
-        for (int i = 0; i < 3; i++) {
-          const int t = cand[i];
-          const int ntm = (ma + t - 1) / t, ntn = (mb + t - 1) / t;
-          const int ntiles = upper ? ntm * (ntm + 1) / 2 : ntm * ntn;
-          const int slots = ctx->sm_count * occ[i];
-          int nsplit = slots / ntiles;
-          if (nsplit < 1) nsplit = 1;
-          const double waves = (double)(ntiles * nsplit + slots - 1) / slots;   // >= 1 when ntiles > slots
-          const double fill = (double)ntiles * nsplit / (std::ceil(waves) * slots);
-          const double cost = (double)ntiles * t * t / (speed[i] * fill);
-          if (cost < best) { best = cost; tile = t; }
-        }
-      }
-      if (tile == 128) return launch_gram_dmma<128, 128, 2, 4, 16, 4, 1>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
-      if (tile == 96) return launch_gram_dmma<96, 96, 2, 4, 16, 3, 2>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
-      return launch_gram_dmma<64, 64, 2, 2, 16, 3, 3>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+      // work-list kernel (gram_wl.cu) for Hermitian products; forced for every shape with gram_wl = 1
+      if (ctx->gram_wl == 1 || (ctx->gram_wl < 0 && ctx->gram_tile == 0 && upper && n >= 4096))
+        return gram_wl_f64(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+      return gram_tiles_f64(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
     }
   }
   if constexpr (std::is_same<T, c64>::value) {

@@ -1,0 +1,588 @@
+// lobpcg_b200/csrc/gram_wl.cu — K2/K3 f64 Gram, work-list ("stream-K") version.
+//
+//   G (ma x mb) = A^H B,  A: n x ma, B: n x mb, column-major, n >> ma, mb          (reference: syrk/herk and
+//   gemm_tn at src/gram/gram_impl.inc:54-63,92-101, src/rayleigh/rayleigh_ritz_modified_impl.inc:75-77,193-195)
+//
+// The first Gram kernel (dense.cu: gram_dmma_kernel) runs its main loop at ~85 % of the DMMA issue rate, but on the
+// solver's shapes a third of the DMMAs it issues are wasted: (i) diagonal tiles of a Hermitian product compute the
+// full 128x128 square, (ii) the last tile row/column is padded to the tile size (m = 900 -> 1024), (iii) the grid is
+// tiles x equal n-splits, which rarely fills 148 SMs.  This version removes all three:
+//   * the unit of MMA work is the 8x8 output block; every warp owns an (8 x 4)-block window of its CTA's tile and a
+//     32-bit mask of the blocks it really computes.  Diagonal tiles use a hand-balanced cover of the upper triangle
+//     (136 of 256 blocks, at most 18 per warp instead of 32); ragged edge tiles use a warp grid chosen for their
+//     block extents.  A window may be "transposed" (the B panel feeds the MMA's row operand), which gives 4 x 8
+//     windows with the same accumulator registers — both operand fragments have the same shared-memory layout.
+//   * work = (tile, row range) items; tiles are laid end to end, weighted by their cost, and the 148 CTAs cut that
+//     line into equal pieces (a CTA may finish one tile and start the next).  Every item writes its partial tile to
+//     its own scratch slot; gram_wl_reduce_kernel sums the slots of a tile in item order — deterministic, no atomics.
+// The schedule (items, warp layouts) is built on the host once per shape and cached on the context.
+#include <algorithm>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "context.h"
+#include "kernels.h"
+#include "tile_loader.cuh"
+
+namespace lb2 {
+
+namespace {
+
+constexpr int WL_T = 128;       // tile edge (columns of A / B staged per CTA)
+constexpr int WL_NT = 256;      // threads per CTA (8 warps)
+constexpr int WL_BLK = WL_T / 8;
+
+struct WlWarp {                 // per-warp window of a tile layout
+  uint32_t mask;                // bit i*4+j: compute block (a-operand block a0+i, b-operand block b0+j)
+  uint8_t a0, b0;               // first 8-column block of the MMA row operand / column operand inside its panel
+  uint8_t transposed;           // 1: row operand comes from the B panel (G columns), column operand from the A panel
+  uint8_t shape;                // compile-time window shape id of `mask` (wl_stage_dispatch)
+};
+struct WlItem {
+  int64_t r_begin, r_end;       // rows of this piece
+  int32_t a_col0, a_cols;       // A panel: columns [a_col0, a_col0 + a_cols)
+  int32_t b_col0, b_cols;
+  int32_t layout;               // index of the first of 8 WlWarp entries
+  int32_t pad;
+};
+
+// Window shapes.  Per-DMMA predicates cost more than the DMMAs they skip (ptxas wraps every predicated mma.sync in
+// WARPSYNC), so the block mask of a warp is a COMPILE-TIME constant: 32 rectangles (na x nb blocks, na <= 8, nb <= 4)
+// and the two staircase patterns of the balanced diagonal cover; the kernel switches on a warp-uniform shape id once
+// per K chunk.  The host planner only emits masks from this list.
+__host__ __device__ constexpr uint32_t wl_rect_mask(int na, int nb) {
+  uint32_t m = 0;
+  for (int i = 0; i < na; i++)
+    for (int j = 0; j < nb; j++) m |= 1u << (i * 4 + j);
+  return m;
+}
+// staircase A (diag16 warps 0 and 6, transposed window): i = G column block 0..5, j = G row block 0..3, j <= i
+__host__ __device__ constexpr uint32_t wl_tri_a_mask() {
+  uint32_t m = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 4; j++)
+      if (j <= i) m |= 1u << (i * 4 + j);
+  return m;
+}
+// staircase B (diag16 warps 1 and 7): i = G row block 0..7, j -> G column block 4 + j; upper part minus the
+// (rows 0..3) x (columns 4..5) corner that belongs to staircase A
+__host__ __device__ constexpr uint32_t wl_tri_b_mask() {
+  uint32_t m = 0;
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 4; j++)
+      if (i <= 4 + j && !(i <= 3 && j <= 1)) m |= 1u << (i * 4 + j);
+  return m;
+}
+constexpr int WL_SHAPE_TRI_A = 32, WL_SHAPE_TRI_B = 33, WL_SHAPE_NONE = 34;
+
+template <uint32_t MASK, int BK, int LDS>
+__device__ __forceinline__ void wl_stage(double (&acc)[8][4][2], const double* __restrict__ as,
+                                         const double* __restrict__ bs) {
+#pragma unroll
+  for (int ks = 0; ks < BK / 4; ks++) {
+    double a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if ((MASK >> (4 * i)) & 0xFu) a[i] = as[i * 8 * LDS + ks * 4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (MASK & (0x11111111u << j)) b[j] = bs[j * 8 * LDS + ks * 4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if ((MASK >> (i * 4 + j)) & 1u) dmma884(acc[i][j], a[i], b[j]);
+  }
+}
+
+template <int BK, int LDS>
+__device__ __forceinline__ void wl_stage_dispatch(int shape, double (&acc)[8][4][2], const double* __restrict__ as,
+                                                  const double* __restrict__ bs) {
+#define WL_CASE(NA, NB) \
+  case ((NA - 1) * 4 + (NB - 1)): wl_stage<wl_rect_mask(NA, NB), BK, LDS>(acc, as, bs); break;
+#define WL_ROW(NA) WL_CASE(NA, 1) WL_CASE(NA, 2) WL_CASE(NA, 3) WL_CASE(NA, 4)
+  switch (shape) {
+    WL_ROW(8) WL_ROW(7) WL_ROW(6) WL_ROW(5) WL_ROW(4) WL_ROW(3) WL_ROW(2) WL_ROW(1)
+    case WL_SHAPE_TRI_A: wl_stage<wl_tri_a_mask(), BK, LDS>(acc, as, bs); break;
+    case WL_SHAPE_TRI_B: wl_stage<wl_tri_b_mask(), BK, LDS>(acc, as, bs); break;
+    default: break;
+  }
+#undef WL_ROW
+#undef WL_CASE
+}
+
+template <int BK, int STAGES, bool VEC>
+__global__ void __launch_bounds__(WL_NT, 1)
+    gram_wl_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                   const WlItem* __restrict__ items, const int* __restrict__ cta_first,
+                   const WlWarp* __restrict__ layouts, double* __restrict__ part) {
+  constexpr int LDS = BK + 4;
+  extern __shared__ __align__(16) double smem_wl[];
+  double* As = smem_wl;
+  double* Bs = smem_wl + (size_t)STAGES * WL_T * LDS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int it_end = cta_first[blockIdx.x + 1];
+  for (int it = cta_first[blockIdx.x]; it < it_end; ++it) {
+    const WlItem item = items[it];
+    const WlWarp cfg = layouts[item.layout + warp];
+    const uint32_t mask = cfg.mask;
+    const int shape = cfg.shape;
+    const int64_t rows = item.r_end - item.r_begin;
+    const int nchunks = (int)((rows + BK - 1) / BK);
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    TileLoaderF64<WL_T, BK, LDS, WL_NT, VEC> la, lb;
+    la.init(A, lda, item.r_begin, item.a_col0, item.a_col0 + item.a_cols, tid);
+    lb.init(B, ldb, item.r_begin, item.b_col0, item.b_col0 + item.b_cols, tid);
+    int issued = 0, wstage = 0;
+    auto issue = [&]() {
+      if (issued < nchunks) {
+        const int64_t valid = rows - (int64_t)issued * BK;
+        la.issue(As + wstage * (WL_T * LDS), A, valid);
+        lb.issue(Bs + wstage * (WL_T * LDS), B, valid);
+        la.advance(BK);
+        lb.advance(BK);
+      }
+      issued++;
+      wstage = (wstage + 1 == STAGES) ? 0 : wstage + 1;
+      cp_async_commit();
+    };
+    __syncthreads();   // every warp is done reading the stages of the previous item
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) issue();
+
+    const int aoff = (cfg.a0 * 8 + g) * LDS + t;
+    const int boff = (cfg.b0 * 8 + g) * LDS + t;
+    const double* abase = (cfg.transposed ? Bs : As) + aoff;
+    const double* bbase = (cfg.transposed ? As : Bs) + boff;
+    int rstage = 0;
+    for (int chunk = 0; chunk < nchunks; chunk++) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      issue();
+      const double* as = abase + rstage * (WL_T * LDS);
+      const double* bs = bbase + rstage * (WL_T * LDS);
+      rstage = (rstage + 1 == STAGES) ? 0 : rstage + 1;
+      wl_stage_dispatch<BK, LDS>(shape, acc, as, bs);
+    }
+    cp_async_wait<0>();
+
+    // partial tile: dense 128 x 128, column-major (row = G row inside the tile = A-panel column)
+    double* o = part + (int64_t)it * (WL_T * WL_T);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (!((mask >> (i * 4 + j)) & 1u)) continue;
+        const int ra = (cfg.a0 + i) * 8 + g;          // index along the MMA row operand
+        const int cb = (cfg.b0 + j) * 8 + 2 * t;      // index along the MMA column operand
+        if (!cfg.transposed) {
+          o[ra + cb * WL_T] = acc[i][j][0];
+          o[ra + (cb + 1) * WL_T] = acc[i][j][1];
+        } else {
+          o[cb + ra * WL_T] = acc[i][j][0];
+          o[cb + 1 + ra * WL_T] = acc[i][j][1];
+        }
+      }
+  }
+}
+
+// G[r, c] = sum over the item slots of its tile, in item order; upper: the lower triangle is the mirrored upper one.
+__global__ void gram_wl_reduce_kernel(const double* __restrict__ part, const int* __restrict__ tile_first, int ntm,
+                                      int ma, int mb, int upper, double* __restrict__ G, int ldg) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)ma * mb) return;
+  const int r = (int)(idx % ma), c = (int)(idx / ma);
+  const bool flip = upper && r > c;
+  const int sr = flip ? c : r, sc = flip ? r : c;
+  const int ti = sr / WL_T, tj = sc / WL_T;
+  const int tile = upper ? ti + tj * (tj + 1) / 2 : ti + tj * ntm;
+  const int s0 = tile_first[tile], s1 = tile_first[tile + 1];
+  const int64_t off = (sr - ti * WL_T) + (int64_t)(sc - tj * WL_T) * WL_T;
+  double s = 0.0;
+  for (int k = s0; k < s1; k++) s += part[(int64_t)k * (WL_T * WL_T) + off];
+  G[r + (int64_t)c * ldg] = s;
+}
+
+// ------------------------------------------------------------------------------------------------- schedule
+struct WlSchedule {
+  int nitems = 0, ncta = 0, ntm = 0, ntn = 0;
+  void* dev = nullptr;           // one allocation: items | cta_first | layouts | tile_first
+  const WlItem* items = nullptr;
+  const int* cta_first = nullptr;
+  const WlWarp* layouts = nullptr;
+  const int* tile_first = nullptr;
+};
+using WlKey = std::tuple<int, int, int, int64_t, int, int, int>;   // ma, mb, upper, n, ncta, BK, load_pct
+constexpr int WL_LOAD_PCT = 40;   // default staging cost of a 256-column tile relative to its DMMA time, in %
+struct WlCache {
+  std::map<WlKey, WlSchedule> map;
+};
+
+inline int popc(uint32_t v) { return __builtin_popcount(v); }
+
+// shape id of a mask (the kernel only has code for these); -1 = not representable
+int shape_of(uint32_t mask) {
+  if (mask == 0) return WL_SHAPE_NONE;
+  for (int na = 1; na <= 8; na++)
+    for (int nb = 1; nb <= 4; nb++)
+      if (mask == wl_rect_mask(na, nb)) return (na - 1) * 4 + (nb - 1);
+  if (mask == wl_tri_a_mask()) return WL_SHAPE_TRI_A;
+  if (mask == wl_tri_b_mask()) return WL_SHAPE_TRI_B;
+  return -1;
+}
+
+// warp grid for a rectangular tile of ra x cb 8-blocks: every warp gets an (na x nb) rectangle of blocks.  Ragged
+// diagonal tiles (the last one of a Hermitian product) also come here and compute their few sub-diagonal blocks.
+int rect_layout(int ra, int cb, WlWarp (&w)[8], int& cost) {
+  int best = 1 << 30, bWA = 2, bTr = 0;
+  for (int WA = 1; WA <= 8; WA *= 2) {
+    const int WB = 8 / WA;
+    const int a = (ra + WA - 1) / WA, b = (cb + WB - 1) / WB;
+    for (int tr = 0; tr < 2; tr++) {
+      const bool ok = tr ? (a <= 4 && b <= 8) : (a <= 8 && b <= 4);
+      if (!ok) continue;
+      if (a * b < best) { best = a * b; bWA = WA; bTr = tr; }
+    }
+  }
+  const int WA = bWA, WB = 8 / WA;
+  const int a = (ra + WA - 1) / WA, b = (cb + WB - 1) / WB;
+  cost = 0;
+  for (int q = 0; q < 8; q++) {
+    const int wa = q % WA, wb = q / WA;
+    WlWarp c{};
+    c.transposed = (uint8_t)bTr;
+    const int r0 = wa * a, c0 = wb * b;      // first G-row block / G-column block of this warp
+    const int nr = std::max(0, std::min(a, ra - r0)), nc = std::max(0, std::min(b, cb - c0));
+    if (nr > 0 && nc > 0) {
+      c.a0 = (uint8_t)(bTr ? c0 : r0);
+      c.b0 = (uint8_t)(bTr ? r0 : c0);
+      c.mask = bTr ? wl_rect_mask(nc, nr) : wl_rect_mask(nr, nc);
+    }
+    const int sh = shape_of(c.mask);
+    if (sh < 0) return -4;
+    c.shape = (uint8_t)sh;
+    w[q] = c;
+    cost = std::max(cost, popc(c.mask));
+  }
+  return 0;
+}
+
+// balanced cover of the upper triangle of a full 16 x 16-block diagonal tile: 136 blocks, at most 18 per warp
+int diag16_layout(WlWarp (&w)[8], int& cost) {
+  auto owner = [](int r, int c) {
+    if (r <= 3) return c <= 5 ? 0 : c <= 7 ? 1 : c <= 11 ? 2 : 4;
+    if (r <= 7) return c <= 7 ? 1 : c <= 11 ? 3 : 5;
+    if (r <= 11) return c <= 13 ? 6 : 7;
+    return 7;
+  };
+  //                    a0  b0  transposed      (transposed: a0 = first G-column block, b0 = first G-row block)
+  const int cfg[8][3] = {{0, 0, 1}, {0, 4, 0}, {0, 8, 0}, {4, 8, 0}, {0, 12, 0}, {4, 12, 0}, {8, 8, 1}, {8, 12, 0}};
+  cost = 0;
+  for (int q = 0; q < 8; q++) {
+    WlWarp c{};
+    c.a0 = (uint8_t)cfg[q][0];
+    c.b0 = (uint8_t)cfg[q][1];
+    c.transposed = (uint8_t)cfg[q][2];
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 4; j++) {
+        const int row = c.transposed ? c.b0 + j : c.a0 + i, col = c.transposed ? c.a0 + i : c.b0 + j;
+        if (row < 16 && col < 16 && row <= col && owner(row, col) == q) c.mask |= 1u << (i * 4 + j);
+      }
+    const int sh = shape_of(c.mask);
+    if (sh < 0) return -4;
+    c.shape = (uint8_t)sh;
+    w[q] = c;
+    cost = std::max(cost, popc(c.mask));
+  }
+  return 0;
+}
+
+struct WlPlan {   // host-side schedule
+  int ntm = 0, ntn = 0, ntiles = 0;
+  std::vector<WlItem> items;
+  std::vector<int> item_cta, item_tile, cta_first, tile_first;
+  std::vector<WlWarp> layouts;
+  std::vector<double> tile_cost;
+};
+
+int plan_schedule(int ma, int mb, int upper, int64_t n, int ncta, int BK, int load_pct, WlPlan& P) {
+  const int ntm = (ma + WL_T - 1) / WL_T, ntn = (mb + WL_T - 1) / WL_T;
+  struct Tile { int ti, tj, a_cols, b_cols, layout; double cost; };
+  std::vector<Tile> tiles;
+  std::vector<WlWarp>& layouts = P.layouts;
+  std::map<std::tuple<int, int, int>, std::pair<int, int>> lcache;   // (kind, ra, cb) -> (layout index, max blocks)
+  for (int tj = 0; tj < ntn; tj++)
+    for (int ti = 0; ti < (upper ? tj + 1 : ntm); ti++) {
+      Tile tl{};
+      tl.ti = ti; tl.tj = tj;
+      tl.a_cols = std::min(WL_T, ma - ti * WL_T);
+      tl.b_cols = std::min(WL_T, mb - tj * WL_T);
+      const int ra = (tl.a_cols + 7) / 8, cb = (tl.b_cols + 7) / 8;
+      const int kind = (upper && ti == tj) ? 1 : 0;
+      auto key = std::make_tuple(kind, ra, cb);
+      auto f = lcache.find(key);
+      if (f == lcache.end()) {
+        WlWarp w[8];
+        int cost = 0;
+        const int lrc = (kind == 1 && ra == WL_BLK && cb == WL_BLK) ? diag16_layout(w, cost) : rect_layout(ra, cb, w, cost);
+        if (lrc) return lrc;
+        const int idx = (int)layouts.size();
+        layouts.insert(layouts.end(), w, w + 8);
+        f = lcache.emplace(key, std::make_pair(idx, cost)).first;
+      }
+      tl.layout = f->second.first;
+      // cost relative to a full tile: DMMA blocks of the busiest warp, bounded below by the staging traffic
+      const double mma = f->second.second / 32.0;
+      const double load = 0.01 * load_pct * (tl.a_cols + tl.b_cols) / (2.0 * WL_T);
+      tl.cost = std::max(mma, load);
+      tiles.push_back(tl);
+      P.tile_cost.push_back(tl.cost);
+    }
+  const int ntiles = (int)tiles.size();
+  double total = 0;
+  for (auto& tl : tiles) total += tl.cost * (double)n;
+  const double L = total / ncta;
+  const int64_t min_rows = 16 * (int64_t)BK;
+  std::vector<WlItem>& items = P.items;
+  P.cta_first.assign(ncta + 1, 0);
+  P.tile_first.assign(ntiles + 1, 0);
+  double U = 0;
+  for (int tix = 0; tix < ntiles; tix++) {
+    const Tile& tl = tiles[tix];
+    P.tile_first[tix] = (int)items.size();
+    const double span = tl.cost * (double)n;
+    int b_lo = (int)std::floor(U / L), b_hi = (int)std::floor((U + span) / L);
+    b_lo = std::min(std::max(b_lo, 0), ncta - 1);
+    b_hi = std::min(std::max(b_hi, 0), ncta - 1);
+    auto boundary = [&](int b) -> int64_t {   // first row of tile `tix` that belongs to CTA b (or later)
+      if (b <= b_lo) return 0;
+      if (b > b_hi) return n;
+      const double u = (double)b * L - U;
+      int64_t r = (int64_t)std::llround(u / tl.cost / BK) * BK;
+      if (r < min_rows) r = 0;
+      if (n - r < min_rows) r = n;
+      return std::min<int64_t>(std::max<int64_t>(r, 0), n);
+    };
+    for (int b = b_lo; b <= b_hi; b++) {
+      const int64_t r0 = boundary(b), r1 = boundary(b + 1);
+      if (r1 <= r0) continue;
+      WlItem itx{};
+      itx.r_begin = r0; itx.r_end = r1;
+      itx.a_col0 = tl.ti * WL_T; itx.a_cols = tl.a_cols;
+      itx.b_col0 = tl.tj * WL_T; itx.b_cols = tl.b_cols;
+      itx.layout = tl.layout;
+      items.push_back(itx);
+      P.item_cta.push_back(b);
+      P.item_tile.push_back(tix);
+    }
+    U += span;
+  }
+  P.tile_first[ntiles] = (int)items.size();
+  const int nitems = (int)items.size();
+  // items are ordered by (tile, CTA) = by position on the line, so each CTA owns a contiguous run
+  int it = 0;
+  for (int b = 0; b < ncta; b++) {
+    while (it < nitems && P.item_cta[it] < b) it++;
+    P.cta_first[b] = it;
+  }
+  P.cta_first[ncta] = nitems;
+  for (int i = 1; i < nitems; i++)
+    if (P.item_cta[i] < P.item_cta[i - 1]) return -3;   // cannot happen
+  P.ntm = ntm; P.ntn = ntn; P.ntiles = ntiles;
+  return 0;
+}
+
+int build_schedule(lb2_ctx* ctx, int ma, int mb, int upper, int64_t n, int ncta, int BK, int load_pct, WlSchedule& S) {
+  WlPlan P;
+  const int rc = plan_schedule(ma, mb, upper, n, ncta, BK, load_pct, P);
+  if (rc) return rc;
+  const int nitems = (int)P.items.size(), ntiles = P.ntiles;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t o_items = 0, o_cta = al(sizeof(WlItem) * nitems), o_lay = o_cta + al(sizeof(int) * (ncta + 1)),
+               o_tile = o_lay + al(sizeof(WlWarp) * P.layouts.size()), tot = o_tile + al(sizeof(int) * (ntiles + 1));
+  std::vector<char> host(tot, 0);
+  memcpy(host.data() + o_items, P.items.data(), sizeof(WlItem) * nitems);
+  memcpy(host.data() + o_cta, P.cta_first.data(), sizeof(int) * (ncta + 1));
+  memcpy(host.data() + o_lay, P.layouts.data(), sizeof(WlWarp) * P.layouts.size());
+  memcpy(host.data() + o_tile, P.tile_first.data(), sizeof(int) * (ntiles + 1));
+  LB2_CUDA_OK(cudaMalloc(&S.dev, tot));
+  LB2_CUDA_OK(cudaMemcpyAsync(S.dev, host.data(), tot, cudaMemcpyHostToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  const char* d = (const char*)S.dev;
+  S.items = (const WlItem*)(d + o_items);
+  S.cta_first = (const int*)(d + o_cta);
+  S.layouts = (const WlWarp*)(d + o_lay);
+  S.tile_first = (const int*)(d + o_tile);
+  S.nitems = nitems; S.ncta = ncta; S.ntm = P.ntm; S.ntn = P.ntn;
+  return 0;
+}
+
+template <int BK, int STAGES>
+int launch_wl(lb2_ctx* ctx, const WlSchedule& S, int64_t n, int ma, int mb, const double* A, int64_t lda,
+              const double* B, int64_t ldb, double* G, int ldg, int upper) {
+  double* part = (double*)ctx_scratch(ctx, sizeof(double) * (size_t)S.nitems * WL_T * WL_T);
+  if (!part) return -1;
+  const bool vec = (lda % 2 == 0) && (ldb % 2 == 0) && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
+  constexpr size_t smem = sizeof(double) * (size_t)STAGES * 2 * WL_T * (BK + 4);
+  if (vec) {
+    auto k = gram_wl_kernel<BK, STAGES, true>;
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, S.items, S.cta_first, S.layouts, part);
+  } else {
+    auto k = gram_wl_kernel<BK, STAGES, false>;
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, S.items, S.cta_first, S.layouts, part);
+  }
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  const int64_t tot = (int64_t)ma * mb;
+  gram_wl_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(part, S.tile_first, S.ntm, ma, mb,
+                                                                               upper, G, ldg);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// Host-only self-check of a schedule (no CUDA calls; tests/test_abi.py runs it on CPU for many shapes): every needed
+// 8x8 block of every tile is owned by exactly one warp, the items of a tile partition [0, n) exactly, every CTA owns a
+// contiguous run of items.  stats: [0] items, [1] busiest CTA cost / mean CTA cost, [2] issued DMMA blocks x rows over
+// needed blocks x rows (1 = no wasted MMA), [3] tiles.
+int gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int BK, double* stats) {
+  WlPlan P;
+  int rc = plan_schedule(ma, mb, upper, n, ncta, BK, WL_LOAD_PCT, P);
+  if (rc) return rc;
+  if (upper && ma != mb) return -2;
+  std::vector<double> cta_cost(ncta, 0.0);
+  double issued = 0, needed = 0;
+  for (int tix = 0; tix < P.ntiles; tix++) {
+    const int i0 = P.tile_first[tix], i1 = P.tile_first[tix + 1];
+    if (i1 <= i0) return 10;
+    int64_t r = 0;
+    for (int i = i0; i < i1; i++) {
+      if (P.items[i].r_begin != r || P.items[i].r_end <= r || P.item_tile[i] != tix) return 11;
+      if (i > i0 && P.items[i].r_begin % BK) return 12;
+      r = P.items[i].r_end;
+      cta_cost[P.item_cta[i]] += P.tile_cost[tix] * (double)(P.items[i].r_end - P.items[i].r_begin);
+    }
+    if (r != n) return 13;
+    const WlItem& it0 = P.items[i0];
+    const int ra = (it0.a_cols + 7) / 8, cb = (it0.b_cols + 7) / 8;
+    const bool diag = upper && it0.a_col0 == it0.b_col0 && ra == WL_BLK && cb == WL_BLK;   // ragged diagonal tiles compute the full square
+    int owner[16][16];
+    for (auto& row : owner) for (int& v : row) v = 0;
+    int busiest = 0;
+    for (int w = 0; w < 8; w++) {
+      const WlWarp& c = P.layouts[it0.layout + w];
+      if (shape_of(c.mask) != c.shape) return 17;
+      busiest = std::max(busiest, popc(c.mask));
+      for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 4; j++)
+          if ((c.mask >> (i * 4 + j)) & 1u) {
+            const int row = c.transposed ? c.b0 + j : c.a0 + i, col = c.transposed ? c.a0 + i : c.b0 + j;
+            if (row >= 16 || col >= 16) return 14;
+            owner[row][col]++;
+          }
+    }
+    int need = 0;
+    for (int row = 0; row < 16; row++)
+      for (int col = 0; col < 16; col++) {
+        const bool want = row < ra && col < cb && (!diag || row <= col);
+        if (owner[row][col] != (want ? 1 : 0)) return 15;
+        need += want;
+      }
+    issued += 8.0 * busiest * (double)n;
+    needed += (double)need * (double)n;
+  }
+  for (int b = 0; b < ncta; b++)
+    for (int i = P.cta_first[b]; i < P.cta_first[b + 1]; i++)
+      if (P.item_cta[i] != b) return 16;
+  double mx = 0, sum = 0;
+  for (double c : cta_cost) { mx = std::max(mx, c); sum += c; }
+  if (stats) {
+    stats[0] = (double)P.items.size();
+    stats[1] = mx / (sum / ncta);
+    stats[2] = issued / needed;
+    stats[3] = (double)P.ntiles;
+  }
+  return 0;
+}
+
+void gram_wl_cache_free(lb2_ctx* ctx) {
+  WlCache* c = (WlCache*)ctx->gram_wl_cache;
+  if (!c) return;
+  for (auto& kv : c->map)
+    if (kv.second.dev) cudaFree(kv.second.dev);
+  delete c;
+  ctx->gram_wl_cache = nullptr;
+}
+
+static int run_wl(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B,
+                  int64_t ldb, double* G, int ldg, int upper) {
+  if (!ctx->gram_wl_cache) ctx->gram_wl_cache = new WlCache();
+  WlCache* cache = (WlCache*)ctx->gram_wl_cache;
+  const int BK = (ctx->gram_bk == 16) ? 16 : 32;
+  // one CTA per SM; small problems use fewer CTAs so that a piece is never shorter than ~1024 rows of a full tile
+  const int64_t tiles_full = (int64_t)((ma + WL_T - 1) / WL_T) * ((mb + WL_T - 1) / WL_T);
+  const int ncta = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, tiles_full * n / 4096));
+  const int load_pct = ctx->gram_load_pct > 0 ? ctx->gram_load_pct : WL_LOAD_PCT;
+  const WlKey key(ma, mb, upper ? 1 : 0, n, ncta, BK, load_pct);
+  auto f = cache->map.find(key);
+  if (f == cache->map.end()) {
+    WlSchedule S;
+    const int rc = build_schedule(ctx, ma, mb, upper ? 1 : 0, n, ncta, BK, load_pct, S);
+    if (rc) return rc;
+    f = cache->map.emplace(key, S).first;
+  }
+  if (BK == 32) return launch_wl<32, 3>(ctx, f->second, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+  return launch_wl<16, 4>(ctx, f->second, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+}
+
+// G[c, i] = G[i, c] for the strip columns c = c0 .. c0 + r - 1 and every row i < c: lower mirror of a strip that was
+// computed as a rectangular product (its r x r diagonal block is made exactly symmetric, like the mirrored tiles)
+__global__ void mirror_strip_kernel(double* __restrict__ G, int ldg, int c0, int r) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = c0 + r;
+  if (idx >= m * r) return;
+  const int i = idx % m, c = c0 + idx / m;
+  if (i < c) G[c + (int64_t)i * ldg] = G[i + (int64_t)c * ldg];
+}
+
+// f64 Gram through the work-list kernel.  Same contract as gram<double>() in dense.cu.
+//
+// The work-list schedule has no two CTAs on the same rows at the same time, so every operand byte comes from HBM in
+// BK x 8-byte pieces; measured on B200 that pattern tops out near 2 TB/s, which a full 128 x 128 tile just stays under
+// (it needs 32 KB per 2 us and SM) but a narrow ragged tile does not (same panel traffic, a few DMMAs).  A Hermitian
+// product whose last tile column is narrow (m mod 128 < gram_strip_max, default: always) is therefore split: the leading
+// multiple of 128 goes through the work list, the strip G[:, c0:m] through the lock-step kernel of dense.cu (its CTAs
+// share the panel through L2), and the strip is mirrored.
+int gram_wl_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B, int64_t ldb,
+                double* G, int ldg, int upper) {
+  const int strip_max = ctx->gram_strip_max > 0 ? ctx->gram_strip_max : (ctx->gram_strip_max < 0 ? 0 : WL_T);
+  const int r = ma % WL_T, c0 = ma - r;
+  if (upper && c0 > 0 && r > 0 && r < strip_max) {
+    int rc = run_wl(ctx, n, c0, c0, A, lda, B, ldb, G, ldg, 1);
+    if (rc) return rc;
+    rc = gram_tiles_f64(ctx, n, ma, r, A, lda, B + (int64_t)c0 * ldb, ldb, G + (int64_t)c0 * ldg, ldg, 0);
+    if (rc) return rc;
+    mirror_strip_kernel<<<(ma * r + 255) / 256, 256, 0, ctx->stream>>>(G, ldg, c0, r);
+    ctx->launches++;
+    LB2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  return run_wl(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+}
+
+}  // namespace lb2

@@ -17,6 +17,14 @@ template <typename T>
 int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_t lds, const T* C, int ldc,
             T beta, T* Out, int64_t ldo);
 
+// gram_wl.cu: f64 Gram, work-list kernel (masked diagonal / ragged tiles, tiles laid end to end over the CTAs)
+int gram_wl_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B, int64_t ldb,
+                double* G, int ldg, int upper);
+// dense.cu: f64 Gram on the tile x equal-split grid (first kernel; still used for rectangular products and strips)
+int gram_tiles_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B,
+                   int64_t ldb, double* G, int ldg, int upper);
+int gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int BK, double* stats);
+
 // ---- elementwise.cu ---------------------------------------------------------------------------------
 // W[:,j] = AX[:,j] - lambda[j] * BX[:,j]  (W may be null: norms only); sumsq[j] = ||W[:,j]||^2 (may be null)
 template <typename T>

@@ -55,6 +55,51 @@ def test_gram_matches_oracle(ctx, dt, shape):
     close(G, full, rtol(dt))                            # ours additionally mirrors => full Hermitian matrix
 
 
+@pytest.mark.parametrize("shape", [(9000, 900), (20000, 300), (12345, 517), (8192, 128), (50000, 129), (6000, 1030),
+                                   (4500, 256), (7001, 384)])
+@pytest.mark.parametrize("opts", [{}, {"gram_bk": 16}, {"gram_strip_max": -1}, {"gram_wl": 0}])
+def test_gram_hermitian_worklist_kernel(ctx, shape, opts):
+    """f64 Hermitian products S^H S and S^H (H S) (H = real diagonal, so the product is symmetric) through the
+    work-list kernel: masked diagonal tiles, ragged last tile column (strip path and in-list path), odd n."""
+    n, m = shape
+    rng = np.random.default_rng(n + m)
+    S = rand(rng, (n, m), np.float64)
+    HS = np.asfortranarray(rng.uniform(0.5, 1.5, n)[:, None] * S)
+    dS, dHS = api.DeviceArray.from_numpy(ctx, S), api.DeviceArray.from_numpy(ctx, HS)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    try:
+        G1 = api.gram(ctx, dS, dS, upper=True).numpy(ctx)
+        G2 = api.gram(ctx, dS, dHS, upper=True).numpy(ctx)
+    finally:
+        for k in opts:
+            ctx.set_option(k, -1 if k == "gram_wl" else 0)
+    close(G1, S.T @ S, 1e-12)
+    close(G2, S.T @ HS, 1e-12)
+    assert np.array_equal(G1, G1.T) and np.array_equal(G2, G2.T)     # mirrored exactly
+
+
+def test_gram_worklist_rectangular_when_forced(ctx):
+    rng = np.random.default_rng(3)
+    A, B = rand(rng, (10000, 600), np.float64), rand(rng, (10000, 300), np.float64)
+    dA, dB = api.DeviceArray.from_numpy(ctx, A), api.DeviceArray.from_numpy(ctx, B)
+    ctx.set_option("gram_wl", 1)
+    try:
+        G = api.gram(ctx, dA, dB).numpy(ctx)
+    finally:
+        ctx.set_option("gram_wl", -1)
+    close(G, A.T @ B, 1e-12)
+
+
+def test_gram_worklist_is_deterministic(ctx):
+    rng = np.random.default_rng(4)
+    S = rand(rng, (30000, 420), np.float64)
+    dS = api.DeviceArray.from_numpy(ctx, S)
+    G1 = api.gram(ctx, dS, dS, upper=True).numpy(ctx)
+    G2 = api.gram(ctx, dS, dS, upper=True).numpy(ctx)
+    assert np.array_equal(G1, G2)
+
+
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_gram_padded_leading_dimension_and_odd_alignment(ctx, dt):
     """ld > n, odd ld and an odd column offset force the non-vectorised cp.async path."""

@@ -12,7 +12,9 @@ PFX = api.PREFIX[np.dtype(DT)]
 CMUL = 4.0 if np.dtype(DT).kind == "c" else 1.0
 stream = torch.cuda.Stream()
 ctx = api.Context(0, stream.cuda_stream)
-for kv in [a for a in sys.argv if "=" in a and not a.startswith("dtype=")]:
+MB = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("mb=")), None)
+PAD = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("pad=")), 0)
+for kv in [a for a in sys.argv if "=" in a and not a.startswith(("dtype=", "mb=", "pad="))]:
     k, v = kv.split("="); ctx.set_option(k, int(v))
 args = [a for a in sys.argv[2:] if "=" not in a]
 
@@ -38,15 +40,16 @@ if mode in ("stencil", "csr"):
     print(json.dumps(dict(kernel=mode, g=g, nc=nc, ms=med, ms_min=mn, gbs=b / med / 1e6, frac_hbm=b / med / 1e6 / 6536.7)))
 elif mode == "gram":
     n, m = int(args[0]), int(args[1]); upper = len(args) > 2 and args[2] == "upper"
-    A = api.fill_uniform(ctx, n, m, DT, 1); B = A if upper else api.fill_uniform(ctx, n, m, DT, 2)
-    L = api.lib(); G = api.DeviceArray((m, m), DT)
+    mb = MB or m
+    A = api.fill_uniform(ctx, n, m, DT, 1, ld=n + PAD); B = A if upper else api.fill_uniform(ctx, n, mb, DT, 2, ld=n + PAD)
+    L = api.lib(); G = api.DeviceArray((m, mb), DT)
     fn = getattr(L, f"lb2_{PFX}_gram")
-    med, mn = timeit(lambda: fn(ctx.h, n, m, m, A.ptr, A.ld, B.ptr, B.ld, G.ptr, m, int(upper)))
-    fl = CMUL * (n * m * (m + 1.0) if upper else 2.0 * n * m * m)
-    print(json.dumps(dict(kernel="gram", dtype=str(np.dtype(DT)), n=n, m=m, upper=upper, ms=med, ms_min=mn, tflops=fl / med / 1e9, frac=fl / med / 1e9 / 35.76)))
+    med, mn = timeit(lambda: fn(ctx.h, n, m, mb, A.ptr, A.ld, B.ptr, B.ld, G.ptr, m, int(upper)))
+    fl = CMUL * (n * m * (m + 1.0) if upper else 2.0 * n * m * mb)
+    print(json.dumps(dict(kernel="gram", dtype=str(np.dtype(DT)), n=n, m=m, mb=mb, upper=upper, ms=med, ms_min=mn, pad=PAD, tflops=fl / med / 1e9, frac=fl / med / 1e9 / 35.76, gbs=8.0 * n * (m + (0 if upper else mb)) / med / 1e6)))
 elif mode == "nn":
     n, kd, nb = int(args[0]), int(args[1]), int(args[2])
-    S = api.fill_uniform(ctx, n, kd, DT, 1); Cm = api.fill_uniform(ctx, kd, nb, DT, 2); O = api.DeviceArray((n, nb), DT)
+    S = api.fill_uniform(ctx, n, kd, DT, 1, ld=n + PAD); Cm = api.fill_uniform(ctx, kd, nb, DT, 2); O = api.DeviceArray((n, nb), DT, ld=n + PAD)
     med, mn = timeit(lambda: api.tall_nn(ctx, S, Cm, O))
     fl = CMUL * 2.0 * n * kd * nb
     print(json.dumps(dict(kernel="tall_nn", dtype=str(np.dtype(DT)), n=n, kd=kd, nb=nb, ms=med, ms_min=mn, tflops=fl / med / 1e9, frac=fl / med / 1e9 / 35.76)))
