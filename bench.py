@@ -236,7 +236,7 @@ def run_ours(args):
         "comm": {"ms_per_step": st["comm"]["ms"] / done},
     }
     roofline = {
-        "kernel": "gram_dmma_kernel (K2/K3: S^H S and S^H A S, FP64 tensor pipe DMMA.8x8x4)",
+        "kernel": "gram_wl_kernel + gram_dmma_kernel strip (K2/K3: S^H S and S^H A S, FP64 tensor pipe DMMA.8x8x4)",
         "bound": "tensor", "achieved": gram_tf, "peak": fp64, "unit": "TFLOP/s", "frac": gram_tf / fp64,
         "traffic": None, "peak_source": how64, "per_gpu": True,
         "algorithmic_flops_per_launch": st["gram"]["work"] / max(st["gram"]["calls"], 1) / world,

@@ -47,7 +47,7 @@ struct WlItem {
   int32_t a_col0, a_cols;       // A panel: columns [a_col0, a_col0 + a_cols)
   int32_t b_col0, b_cols;
   int32_t layout;               // index of the first of 8 WlWarp entries
-  int32_t pad;
+  int32_t same_panel;           // 1: A and B panels are the same columns of the same matrix -> staged once
 };
 
 // Window shapes.  Per-DMMA predicates cost more than the DMMAs they skip (ptxas wraps every predicated mma.sync in
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(WL_NT, 1)
 #pragma unroll
       for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    const bool same = item.same_panel != 0;   // diagonal tile of S^H S: one panel feeds both operands
     TileLoaderF64<WL_T, BK, LDS, WL_NT, VEC> la, lb;
     la.init(A, lda, item.r_begin, item.a_col0, item.a_col0 + item.a_cols, tid);
     lb.init(B, ldb, item.r_begin, item.b_col0, item.b_col0 + item.b_cols, tid);
@@ -149,9 +150,11 @@ __global__ void __launch_bounds__(WL_NT, 1)
       if (issued < nchunks) {
         const int64_t valid = rows - (int64_t)issued * BK;
         la.issue(As + wstage * (WL_T * LDS), A, valid);
-        lb.issue(Bs + wstage * (WL_T * LDS), B, valid);
         la.advance(BK);
-        lb.advance(BK);
+        if (!same) {
+          lb.issue(Bs + wstage * (WL_T * LDS), B, valid);
+          lb.advance(BK);
+        }
       }
       issued++;
       wstage = (wstage + 1 == STAGES) ? 0 : wstage + 1;
@@ -163,8 +166,9 @@ __global__ void __launch_bounds__(WL_NT, 1)
 
     const int aoff = (cfg.a0 * 8 + g) * LDS + t;
     const int boff = (cfg.b0 * 8 + g) * LDS + t;
-    const double* abase = (cfg.transposed ? Bs : As) + aoff;
-    const double* bbase = (cfg.transposed ? As : Bs) + boff;
+    const double* Bp = same ? As : Bs;
+    const double* abase = (cfg.transposed ? Bp : As) + aoff;
+    const double* bbase = (cfg.transposed ? As : Bp) + boff;
     int rstage = 0;
     for (int chunk = 0; chunk < nchunks; chunk++) {
       cp_async_wait<STAGES - 2>();
@@ -223,8 +227,8 @@ struct WlSchedule {
   const WlWarp* layouts = nullptr;
   const int* tile_first = nullptr;
 };
-using WlKey = std::tuple<int, int, int, int64_t, int, int, int>;   // ma, mb, upper, n, ncta, BK, load_pct
-constexpr int WL_LOAD_PCT = 40;   // default staging cost of a 256-column tile relative to its DMMA time, in %
+using WlKey = std::tuple<int, int, int, int64_t, int, int, int>;   // ma, mb, upper + 2 * same_ab, n, ncta, BK, load_pct
+constexpr int WL_LOAD_PCT = 70;   // default staging cost of a 256-column tile relative to its DMMA time, in %
 struct WlCache {
   std::map<WlKey, WlSchedule> map;
 };
@@ -316,9 +320,9 @@ struct WlPlan {   // host-side schedule
   std::vector<double> tile_cost;
 };
 
-int plan_schedule(int ma, int mb, int upper, int64_t n, int ncta, int BK, int load_pct, WlPlan& P) {
+int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, int BK, int load_pct, WlPlan& P) {
   const int ntm = (ma + WL_T - 1) / WL_T, ntn = (mb + WL_T - 1) / WL_T;
-  struct Tile { int ti, tj, a_cols, b_cols, layout; double cost; };
+  struct Tile { int ti, tj, a_cols, b_cols, layout, same; double cost; };
   std::vector<Tile> tiles;
   std::vector<WlWarp>& layouts = P.layouts;
   std::map<std::tuple<int, int, int>, std::pair<int, int>> lcache;   // (kind, ra, cb) -> (layout index, max blocks)
@@ -344,7 +348,8 @@ int plan_schedule(int ma, int mb, int upper, int64_t n, int ncta, int BK, int lo
       tl.layout = f->second.first;
       // cost relative to a full tile: DMMA blocks of the busiest warp, bounded below by the staging traffic
       const double mma = f->second.second / 32.0;
-      const double load = 0.01 * load_pct * (tl.a_cols + tl.b_cols) / (2.0 * WL_T);
+      tl.same = (same_ab && upper && ti == tj) ? 1 : 0;
+      const double load = 0.01 * load_pct * (tl.a_cols + (tl.same ? 0 : tl.b_cols)) / (2.0 * WL_T);
       tl.cost = std::max(mma, load);
       tiles.push_back(tl);
       P.tile_cost.push_back(tl.cost);
@@ -382,6 +387,7 @@ int plan_schedule(int ma, int mb, int upper, int64_t n, int ncta, int BK, int lo
       itx.a_col0 = tl.ti * WL_T; itx.a_cols = tl.a_cols;
       itx.b_col0 = tl.tj * WL_T; itx.b_cols = tl.b_cols;
       itx.layout = tl.layout;
+      itx.same_panel = tl.same;
       items.push_back(itx);
       P.item_cta.push_back(b);
       P.item_tile.push_back(tix);
@@ -403,9 +409,10 @@ int plan_schedule(int ma, int mb, int upper, int64_t n, int ncta, int BK, int lo
   return 0;
 }
 
-int build_schedule(lb2_ctx* ctx, int ma, int mb, int upper, int64_t n, int ncta, int BK, int load_pct, WlSchedule& S) {
+int build_schedule(lb2_ctx* ctx, int ma, int mb, int upper, int same_ab, int64_t n, int ncta, int BK, int load_pct,
+                   WlSchedule& S) {
   WlPlan P;
-  const int rc = plan_schedule(ma, mb, upper, n, ncta, BK, load_pct, P);
+  const int rc = plan_schedule(ma, mb, upper, same_ab, n, ncta, BK, load_pct, P);
   if (rc) return rc;
   const int nitems = (int)P.items.size(), ntiles = P.ntiles;
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -462,7 +469,7 @@ int launch_wl(lb2_ctx* ctx, const WlSchedule& S, int64_t n, int ma, int mb, cons
 // needed blocks x rows (1 = no wasted MMA), [3] tiles.
 int gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int BK, double* stats) {
   WlPlan P;
-  int rc = plan_schedule(ma, mb, upper, n, ncta, BK, WL_LOAD_PCT, P);
+  int rc = plan_schedule(ma, mb, upper, upper, n, ncta, BK, WL_LOAD_PCT, P);
   if (rc) return rc;
   if (upper && ma != mb) return -2;
   std::vector<double> cta_cost(ncta, 0.0);
@@ -538,11 +545,12 @@ static int run_wl(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int6
   const int64_t tiles_full = (int64_t)((ma + WL_T - 1) / WL_T) * ((mb + WL_T - 1) / WL_T);
   const int ncta = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, tiles_full * n / 4096));
   const int load_pct = ctx->gram_load_pct > 0 ? ctx->gram_load_pct : WL_LOAD_PCT;
-  const WlKey key(ma, mb, upper ? 1 : 0, n, ncta, BK, load_pct);
+  const int same_ab = (upper && A == B && lda == ldb) ? 1 : 0;
+  const WlKey key(ma, mb, (upper ? 1 : 0) + 2 * same_ab, n, ncta, BK, load_pct);
   auto f = cache->map.find(key);
   if (f == cache->map.end()) {
     WlSchedule S;
-    const int rc = build_schedule(ctx, ma, mb, upper ? 1 : 0, n, ncta, BK, load_pct, S);
+    const int rc = build_schedule(ctx, ma, mb, upper ? 1 : 0, same_ab, n, ncta, BK, load_pct, S);
     if (rc) return rc;
     f = cache->map.emplace(key, S).first;
   }

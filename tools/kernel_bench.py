@@ -41,7 +41,8 @@ if mode in ("stencil", "csr"):
 elif mode == "gram":
     n, m = int(args[0]), int(args[1]); upper = len(args) > 2 and args[2] == "upper"
     mb = MB or m
-    A = api.fill_uniform(ctx, n, m, DT, 1, ld=n + PAD); B = A if upper else api.fill_uniform(ctx, n, mb, DT, 2, ld=n + PAD)
+    distinct = "distinct" in args      # Hermitian product of two different blocks (S^H AS): upper, but two panels per tile
+    A = api.fill_uniform(ctx, n, m, DT, 1, ld=n + PAD); B = A if (upper and not distinct) else api.fill_uniform(ctx, n, mb, DT, 2, ld=n + PAD)
     L = api.lib(); G = api.DeviceArray((m, mb), DT)
     fn = getattr(L, f"lb2_{PFX}_gram")
     med, mn = timeit(lambda: fn(ctx.h, n, m, mb, A.ptr, A.ld, B.ptr, B.ld, G.ptr, m, int(upper)))
