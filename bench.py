@@ -235,10 +235,17 @@ def run_ours(args):
         "small_dense": {"ms_per_step": st["small_dense"]["ms"] / done},
         "comm": {"ms_per_step": st["comm"]["ms"] / done},
     }
+    traffic = None
+    tf = ROOT / "profiles" / "ncu_traffic_r01.json"
+    if tf.exists() and g == 160 and nev == 150 and world == 1:   # the ncu capture is of this shape on one GPU
+        t = json.loads(tf.read_text())["gram_wl_kernel"]
+        traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])
     roofline = {
         "kernel": "gram_wl_kernel + gram_dmma_kernel strip (K2/K3: S^H S and S^H A S, FP64 tensor pipe DMMA.8x8x4)",
         "bound": "tensor", "achieved": gram_tf, "peak": fp64, "unit": "TFLOP/s", "frac": gram_tf / fp64,
-        "traffic": None, "peak_source": how64, "per_gpu": True,
+        "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/ncu_traffic_r01.json); "
+                                             "algorithmic operand bytes per launch = n*m*8 = %.3g" % (n_local * 3.0 * k * 8),
+        "peak_source": how64, "per_gpu": True,
         "algorithmic_flops_per_launch": st["gram"]["work"] / max(st["gram"]["calls"], 1) / world,
         "share_of_step": st["gram"]["ms"] / (ms if ms > 0 else 1.0),
     }
