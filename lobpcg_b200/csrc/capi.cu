@@ -129,6 +129,7 @@ void lb2_ctx_destroy(lb2_ctx* c) {
   if (c->cublas) cublasDestroy(c->cublas);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
   lb2::gram_wl_cache_free(c);
+  lb2::hostcopy_free(c);
   if (c->ws) cudaFree(c->ws);
   if (c->solver_ws) cudaFree(c->solver_ws);
   if (c->solver_hws) free(c->solver_hws);
@@ -191,16 +192,9 @@ void* lb2_malloc_host(size_t bytes) {
   return p;
 }
 void lb2_free_host(void* p) { if (p) cudaFreeHost(p); }
-int lb2_memcpy_h2d(lb2_ctx* c, void* dst, const void* src, size_t bytes) {
-  LB2_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
-  LB2_CUDA_OK(cudaStreamSynchronize(c->stream));
-  return 0;
-}
-int lb2_memcpy_d2h(lb2_ctx* c, void* dst, const void* src, size_t bytes) {
-  LB2_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
-  LB2_CUDA_OK(cudaStreamSynchronize(c->stream));
-  return 0;
-}
+// pageable host memory <-> device; large blocks are pipelined through a pinned ring by several host threads (hostcopy.cu)
+int lb2_memcpy_h2d(lb2_ctx* c, void* dst, const void* src, size_t bytes) { return lb2::host_copy(c, dst, src, bytes, true); }
+int lb2_memcpy_d2h(lb2_ctx* c, void* dst, const void* src, size_t bytes) { return lb2::host_copy(c, dst, src, bytes, false); }
 int lb2_memset(lb2_ctx* c, void* dst, int byte, size_t bytes) {
   LB2_CUDA_OK(cudaMemsetAsync(dst, byte, bytes, c->stream));
   return 0;

@@ -32,6 +32,7 @@ struct lb2_ctx {
   int gram_bk = 0;       // K chunk of the work-list Gram: 0/16 or 32 (tuning)
   int gram_strip_max = 0; // work-list Gram: ragged last tile columns narrower than this go to the lock-step kernel (0 = always, -1 = never)
   int gram_load_pct = 0; // work-list Gram: staging-traffic cost of a tile with 256 columns in % of its DMMA time (0 = default)
+  void* hostcopy = nullptr;        // lb2::HostCopyState* (pinned ring for pageable host <-> device block transfers)
   void* gram_wl_cache = nullptr;   // lb2::WlCache* (schedules per Gram shape)
   int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
   int spmm_cols = 0;     // CSR SpMM columns per thread (0 = heuristic)
@@ -46,4 +47,7 @@ namespace lb2 {
 // enqueued on ctx->stream and growth synchronizes first).
 void* ctx_scratch(lb2_ctx* ctx, size_t bytes);
 void gram_wl_cache_free(lb2_ctx* ctx);   // gram_wl.cu
+// hostcopy.cu: pipelined copy between PAGEABLE host memory and the device (host-synchronous, ordered after ctx->stream)
+int host_copy(lb2_ctx* ctx, void* dst, const void* src, size_t bytes, bool to_device);
+void hostcopy_free(lb2_ctx* ctx);
 }  // namespace lb2

@@ -849,6 +849,8 @@ int Solver<T>::init() {
   T* X = Xp();
   if (use_device_x0) {
     LB2_TRY(fill_uniform<T>(ctx, n, k, X, n, device_seed, ng, row0));
+  } else if (n == ng) {   // whole columns: one contiguous block, pipelined through pinned chunks (hostcopy.cu)
+    LB2_TRY(host_copy(ctx, X, alg->S, sizeof(T) * (size_t)n * k, true));
   } else {
     LB2_CUDA_OK(cudaMemcpy2DAsync(X, sizeof(T) * n, alg->S + row0, sizeof(T) * ng, sizeof(T) * n, k,
                                   cudaMemcpyHostToDevice, ctx->stream));
@@ -964,8 +966,12 @@ template <typename T>
 int Solver<T>::finish() {
   if (!inited) return 1;
   T* X = Xp();
-  LB2_CUDA_OK(cudaMemcpy2DAsync(alg->S + row0, sizeof(T) * ng, X, sizeof(T) * n, sizeof(T) * n, k,
-                                cudaMemcpyDeviceToHost, ctx->stream));
+  if (n == ng) {
+    LB2_TRY(host_copy(ctx, alg->S, X, sizeof(T) * (size_t)n * k, false));
+  } else {
+    LB2_CUDA_OK(cudaMemcpy2DAsync(alg->S + row0, sizeof(T) * ng, X, sizeof(T) * n, sizeof(T) * n, k,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  }
   LB2_TRY(sync());
   for (int i = 0; i < k; i++) alg->eigVals[i] = hEig[i];
   for (int i = 0; i < nev; i++) alg->resNorm[i] = hRes[i];

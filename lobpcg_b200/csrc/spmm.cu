@@ -231,40 +231,46 @@ int spmm_stencil(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* X, int64_t
 // not by the (col,val) stream — a shared-memory staged variant of the matrix stream measured no faster.  Getting
 // past this needs a 3-D blocked row order (next round).
 // =====================================================================================================
-template <typename T, int NCOL>
-__global__ void __launch_bounds__(128)
+template <typename T, int NCOL, int RPT>
+__global__ void __launch_bounds__(256)
     csr_kernel(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                const T* __restrict__ val, int nc, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y,
                int64_t ldy) {
-  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // a CTA owns 256 * RPT consecutive rows (thread t: rows base + t + 256 i).  RPT > 1 was measured (r01: 1/2/4/8 rows per
+  // thread x 4/8/16/32 columns, 128^3 7-point matrix): no effect, the kernel stays at ~49 % of HBM with 8 or 16 columns
+  // per thread — it is bound by L2 sector reads (5 gathered lines per output), not by L1 reuse inside the CTA.
   const int c0 = blockIdx.y * NCOL;
-  if (row >= n) return;
   const int ncol = min(NCOL, nc - c0);
-  T acc[NCOL];
-#pragma unroll
-  for (int c = 0; c < NCOL; c++) acc[c] = zero<T>();
-  const int64_t p0 = rowptr[row], p1 = rowptr[row + 1];
   const T* xb = X + (int64_t)c0 * ldx;
-  if (ncol == NCOL) {
-    for (int64_t p = p0; p < p1; p++) {
-      const int64_t cj = col[p];
-      const T v = val[p];
+#pragma unroll 1
+  for (int i = 0; i < RPT; i++) {
+    const int64_t row = ((int64_t)blockIdx.x * RPT + i) * 256 + threadIdx.x;
+    if (row >= n) return;
+    T acc[NCOL];
 #pragma unroll
-      for (int c = 0; c < NCOL; c++) fma_(acc[c], v, xb[cj + (int64_t)c * ldx]);
-    }
-  } else {
-    for (int64_t p = p0; p < p1; p++) {
-      const int64_t cj = col[p];
-      const T v = val[p];
+    for (int c = 0; c < NCOL; c++) acc[c] = zero<T>();
+    const int64_t p0 = rowptr[row], p1 = rowptr[row + 1];
+    if (ncol == NCOL) {
+      for (int64_t p = p0; p < p1; p++) {
+        const int64_t cj = col[p];
+        const T v = val[p];
 #pragma unroll
-      for (int c = 0; c < NCOL; c++)
-        if (c < ncol) fma_(acc[c], v, xb[cj + (int64_t)c * ldx]);
+        for (int c = 0; c < NCOL; c++) fma_(acc[c], v, xb[cj + (int64_t)c * ldx]);
+      }
+    } else {
+      for (int64_t p = p0; p < p1; p++) {
+        const int64_t cj = col[p];
+        const T v = val[p];
+#pragma unroll
+        for (int c = 0; c < NCOL; c++)
+          if (c < ncol) fma_(acc[c], v, xb[cj + (int64_t)c * ldx]);
+      }
     }
+    T* yb = Y + (int64_t)c0 * ldy + row;
+#pragma unroll
+    for (int c = 0; c < NCOL; c++)
+      if (c < ncol) yb[(int64_t)c * ldy] = acc[c];
   }
-  T* yb = Y + (int64_t)c0 * ldy + row;
-#pragma unroll
-  for (int c = 0; c < NCOL; c++)
-    if (c < ncol) yb[(int64_t)c * ldy] = acc[c];
 }
 
 template <typename T>
@@ -272,14 +278,16 @@ int spmm_csr(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col,
              const T* X, int64_t ldx, T* Y, int64_t ldy) {
   if (n <= 0 || nc <= 0) return 0;
   int ncol = ctx->spmm_cols ? ctx->spmm_cols : 16;
-  const unsigned gx = (unsigned)((n + 127) / 128);
-#define LB2_CSR(NC)                                                                                   \
-  csr_kernel<T, NC><<<dim3(gx, (nc + NC - 1) / NC), 128, 0, ctx->stream>>>(n, rowptr, col, val, nc, X, ldx, Y, ldy)
+#define LB2_CSR2(NC, RP)                                                                                        \
+  csr_kernel<T, NC, RP><<<dim3((unsigned)((n + 256 * RP - 1) / (256 * RP)), (nc + NC - 1) / NC), 256, 0, ctx->stream>>>( \
+      n, rowptr, col, val, nc, X, ldx, Y, ldy)
+#define LB2_CSR(NC) LB2_CSR2(NC, 1)
   if (nc <= 4 || ncol <= 4) LB2_CSR(4);
   else if (nc <= 8 || ncol <= 8) LB2_CSR(8);
   else if (ncol <= 16 || sizeof(T) >= 16) LB2_CSR(16);
   else LB2_CSR(32);
 #undef LB2_CSR
+#undef LB2_CSR2
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
   return 0;
