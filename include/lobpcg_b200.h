@@ -62,6 +62,11 @@ void *lb2_op_diag(char prefix, int64_t n, const void *diag_host);
 /* BdG-style pencil block A = [[K+shift, d],[conj d, K+shift]] with K the stencil above (config C4) */
 void *lb2_op_bdg(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff, double shift,
                  double d_re, double d_im);
+/* Built-in preconditioner for alg->T (the reference only plans built-ins, README.md:15): T = p(A), `degree`
+ * steps of the Chebyshev iteration for A y = x on the spectrum window [lo, hi], i.e. `degree` block applies of A per
+ * block apply of T.  hi <= 0: Gershgorin bound of the built-in inner operator; lo <= 0: hi / 50.  The inner operator
+ * must outlive the result. */
+void *lb2_op_chebyshev(char prefix, const void *inner_linop, int degree, double lo, double hi);
 void lb2_op_destroy(void *linop);
 /* Y = Op X on device block vectors (n x nc) */
 int lb2_op_apply(lb2_ctx *ctx, const void *linop, char prefix, int nc, const void *X, int64_t ldx, void *Y,

@@ -72,6 +72,8 @@ def _declare(L):
     L.lb2_op_diag.argtypes = [C.c_char, i64, vp]
     L.lb2_op_bdg.restype = vp
     L.lb2_op_bdg.argtypes = [C.c_char, i64, i64, i64, dbl, dbl, dbl, dbl, dbl]
+    L.lb2_op_chebyshev.restype = vp
+    L.lb2_op_chebyshev.argtypes = [C.c_char, vp, ci, dbl, dbl]
     L.lb2_op_destroy.argtypes = [vp]
     L.lb2_op_apply.argtypes = [vp, vp, C.c_char, ci, vp, i64, vp, i64]
     L.lb2_solver_create.restype = vp
@@ -358,6 +360,12 @@ def bdg_op(grid, dtype, shift, d, cdiag=None, coff=-1.0) -> LinOp:
     d = complex(d)
     return LinOp(lib().lb2_op_bdg(p.encode(), g[0], g[1], g[2], cdiag, coff, shift, d.real, d.imag), p,
                  2 * g[0] * g[1] * g[2])
+
+
+def chebyshev_op(A: LinOp, degree: int, lo: float = 0.0, hi: float = 0.0) -> LinOp:
+    """Built-in preconditioner T = p(A) (lb2_op_chebyshev): `degree` Chebyshev steps for A y = x on [lo, hi]."""
+    h = lib().lb2_op_chebyshev(A.prefix.encode(), A.handle, int(degree), float(lo), float(hi))
+    return LinOp(h, A.prefix, A.n, keep=(A,))
 
 
 def host_op(n, dtype, fn) -> LinOp:

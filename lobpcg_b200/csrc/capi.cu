@@ -1,5 +1,7 @@
 // lobpcg_b200/csrc/capi.cu — the C ABI declared in include/lobpcg_b200.h and include/lobpcg.h.
 #include <climits>
+#include <cmath>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -279,10 +281,39 @@ void* lb2_op_stencil(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdi
   if (!lb2_default_ctx()) return nullptr;
   BuiltinOp* b = new_builtin(OP_STENCIL, prefix, gx * gy * gz);
   b->gx = gx; b->gy = gy; b->gz = gz; b->cdiag = cdiag; b->coff = coff;
+  double vmax = 0;
   if (potential_host) {
     b->potential = upload(potential_host, real_size(prefix) * (size_t)b->n);
     if (!b->potential) { free(b); return nullptr; }
+    for (int64_t i = 0; i < b->n; i++)
+      vmax = std::max(vmax, real_size(prefix) == 4 ? (double)((const float*)potential_host)[i] : ((const double*)potential_host)[i]);
   }
+  // Gershgorin bound of the spectrum: diagonal + |coff| * number of neighbours
+  b->spec_hi = cdiag + vmax + std::fabs(coff) * 2.0 * ((gx > 1) + (gy > 1) + (gz > 1));
+  return wrap_builtin(b);
+}
+
+// Built-in preconditioner T = p(A): `degree` steps of the Chebyshev iteration for A y = x on the spectrum
+// window [lo, hi] — a polynomial approximation of A^-1 that damps every component above `lo` by 1 / T_degree(sigma).
+// hi <= 0: Gershgorin bound of the inner built-in operator; lo <= 0: hi / 50.  The result is an ordinary
+// LinearOperator_<p>_t* for alg->T (the inner operator must outlive it).
+void* lb2_op_chebyshev(char prefix, const void* inner_linop, int degree, double lo, double hi) {
+  const LinOpRaw* in = (const LinOpRaw*)inner_linop;
+  if (!valid_prefix(prefix) || !in || degree < 0) return nullptr;
+  const BuiltinOp* bi = builtin_of(in);
+  if (hi <= 0) hi = bi ? bi->spec_hi : 0;
+  if (!(hi > 0)) {
+    fprintf(stderr, "lobpcg_b200: lb2_op_chebyshev needs an upper spectrum bound (hi) for this operator\n");
+    return nullptr;
+  }
+  if (lo <= 0) lo = hi / 50.0;
+  if (!(lo < hi)) return nullptr;
+  BuiltinOp* b = new_builtin(OP_CHEB, prefix, bi ? bi->n : (int64_t)in->rows);
+  if (bi) { b->n_global = bi->n_global; b->row0 = bi->row0; }
+  b->inner = in;
+  b->cheb_degree = degree;
+  b->cheb_lo = lo;
+  b->cheb_hi = hi;
   return wrap_builtin(b);
 }
 
@@ -305,7 +336,25 @@ void* lb2_op_bdg(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, 
   BuiltinOp* b = new_builtin(OP_BDG, prefix, 2 * gx * gy * gz);
   b->gx = gx; b->gy = gy; b->gz = gz; b->cdiag = cdiag; b->coff = coff; b->shift = shift;
   b->dre = d_re; b->dim = d_im;
+  b->spec_hi = cdiag + shift + std::fabs(coff) * 2.0 * ((gx > 1) + (gy > 1) + (gz > 1)) + std::hypot(d_re, d_im);
   return wrap_builtin(b);
+}
+
+static double csr_gershgorin(char prefix, int64_t n, const int64_t* rp, const void* val) {
+  double hi = 0;
+  for (int64_t i = 0; i < n; i++) {
+    double s = 0;
+    for (int64_t p = rp[i]; p < rp[i + 1]; p++) {
+      switch (prefix) {
+        case 's': s += std::fabs((double)((const float*)val)[p]); break;
+        case 'd': s += std::fabs(((const double*)val)[p]); break;
+        case 'c': s += std::hypot((double)((const float*)val)[2 * p], (double)((const float*)val)[2 * p + 1]); break;
+        default: s += std::hypot(((const double*)val)[2 * p], ((const double*)val)[2 * p + 1]); break;
+      }
+    }
+    hi = std::max(hi, s);
+  }
+  return hi;
 }
 
 void* lb2_op_csr(char prefix, int64_t n, const int64_t* rowptr_host, const int32_t* col_host, const void* val_host) {
@@ -339,6 +388,7 @@ void* lb2_op_csr(char prefix, int64_t n, const int64_t* rowptr_host, const int32
       }
       b->nnz = rowptr_host[n];   // kept for the CSR traffic accounting of the solver statistics
       b->from_csr = 1;
+      b->spec_hi = csr_gershgorin(prefix, n, rowptr_host, val_host);
       return wrap_builtin(b);
     }
   }
@@ -353,6 +403,7 @@ void* lb2_op_csr(char prefix, int64_t n, const int64_t* rowptr_host, const int32
     builtin_cleanup(lc);
     return nullptr;
   }
+  b->spec_hi = csr_gershgorin(prefix, n, rowptr_host, val_host);
   return wrap_builtin(b);
 }
 

@@ -8,6 +8,7 @@
 //
 // Reductions are two-stage and deterministic: grid (row chunks, columns) writes one partial per CTA,
 // a finishing kernel sums the chunks of each column in order.
+#include <algorithm>
 #include "common.cuh"
 #include "context.h"
 #include "kernels.h"
@@ -229,6 +230,70 @@ int copy_block(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, T* Y, i
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Chebyshev polynomial preconditioner (built-in T operator): the two vector updates of the
+// three-term recurrence, fused so that one step touches each block once.
+//   init:    d = x / theta, y = d
+//   update:  r_out = r_in - Ad;  d_out = c1 d_in + c2 r_out;  y += d_out   (r_in is x on the first step; d ping-pongs so that
+//            a neighbour rank may still be reading d_in's halo plane while this rank already runs the update)
+// HBM-bound: 3 (init) / 7 (update) block streams of n x nc scalars.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+    cheb_init_kernel(int64_t n, const T* __restrict__ X, int64_t ldx, T* __restrict__ D, T* __restrict__ Y, int64_t ldy,
+                     int64_t ldw, real_t<T> inv_theta) {
+  const int j = blockIdx.y;
+  const T* x = X + (int64_t)j * ldx;
+  T* d = D + (int64_t)j * ldw;
+  T* y = Y + (int64_t)j * ldy;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const T v = rscale_(x[i], inv_theta);
+    d[i] = v;
+    y[i] = v;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+    cheb_update_kernel(int64_t n, const T* __restrict__ AD, const T* __restrict__ Rin, int64_t ldrin,
+                       T* __restrict__ Rout, const T* __restrict__ Din, T* __restrict__ Dout, int64_t ldw,
+                       T* __restrict__ Y, int64_t ldy, real_t<T> c1, real_t<T> c2, int write_r) {
+  const int j = blockIdx.y;
+  const T* ad = AD + (int64_t)j * ldw;
+  const T* rin = Rin + (int64_t)j * ldrin;
+  T* rout = Rout + (int64_t)j * ldw;
+  const T* din = Din + (int64_t)j * ldw;
+  T* dout = Dout + (int64_t)j * ldw;
+  T* y = Y + (int64_t)j * ldy;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const T r = sub_(rin[i], ad[i]);
+    const T dn = add_(rscale_(din[i], c1), rscale_(r, c2));
+    if (write_r) rout[i] = r;
+    dout[i] = dn;
+    y[i] = add_(y[i], dn);
+  }
+}
+template <typename T>
+int cheb_init(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, T* D, T* Y, int64_t ldy, int64_t ldw,
+              real_t<T> inv_theta) {
+  if (n <= 0 || nc <= 0) return 0;
+  int gx = (int)std::min<int64_t>((n + 256 * 4 - 1) / (256 * 4), 1 << 20);
+  cheb_init_kernel<T><<<dim3(std::max(gx, 1), nc), 256, 0, ctx->stream>>>(n, X, ldx, D, Y, ldy, ldw, inv_theta);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+int cheb_update(lb2_ctx* ctx, int64_t n, int nc, const T* AD, const T* Rin, int64_t ldrin, T* Rout, const T* Din, T* Dout,
+                int64_t ldw, T* Y, int64_t ldy, real_t<T> c1, real_t<T> c2, bool write_r) {
+  if (n <= 0 || nc <= 0) return 0;
+  int gx = (int)std::min<int64_t>((n + 256 * 4 - 1) / (256 * 4), 1 << 20);
+  cheb_update_kernel<T><<<dim3(std::max(gx, 1), nc), 256, 0, ctx->stream>>>(n, AD, Rin, ldrin, Rout, Din, Dout, ldw, Y, ldy,
+                                                                           c1, c2, write_r ? 1 : 0);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 #define LB2_INST(T)                                                                                     \
   template int residual<T>(lb2_ctx*, int64_t, int, const T*, int64_t, const T*, int64_t, const real_t<T>*, \
                            T*, int64_t, real_t<T>*);                                                    \
@@ -236,7 +301,10 @@ int copy_block(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, T* Y, i
   template int fill_uniform<T>(lb2_ctx*, int64_t, int, T*, int64_t, uint64_t, int64_t, int64_t);                \
   template int scale_cols<T>(lb2_ctx*, int64_t, int, T*, int64_t, const real_t<T>*, real_t<T>);         \
   template int normalize_by<T>(lb2_ctx*, int64_t, T*, const real_t<T>*);                                \
-  template int copy_block<T>(lb2_ctx*, int64_t, int, const T*, int64_t, T*, int64_t);
+  template int copy_block<T>(lb2_ctx*, int64_t, int, const T*, int64_t, T*, int64_t);                   \
+  template int cheb_init<T>(lb2_ctx*, int64_t, int, const T*, int64_t, T*, T*, int64_t, int64_t, real_t<T>); \
+  template int cheb_update<T>(lb2_ctx*, int64_t, int, const T*, const T*, int64_t, T*, const T*, T*, int64_t, T*, int64_t, \
+                              real_t<T>, real_t<T>, bool);
 LB2_INST(float)
 LB2_INST(double)
 LB2_INST(c32)

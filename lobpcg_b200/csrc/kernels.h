@@ -48,6 +48,15 @@ int normalize_by(lb2_ctx* ctx, int64_t n, T* x, const real_t<T>* sumsq);
 template <typename T>
 int copy_block(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy);
 
+// Chebyshev preconditioner steps: d = x/theta, y = d;  r_out = r_in - AD, d = c1 d + c2 r_out, y += d.
+// Din, Dout, AD, Rout share the leading dimension ldw.
+template <typename T>
+int cheb_init(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, T* D, T* Y, int64_t ldy, int64_t ldw,
+              real_t<T> inv_theta);
+template <typename T>
+int cheb_update(lb2_ctx* ctx, int64_t n, int nc, const T* AD, const T* Rin, int64_t ldrin, T* Rout, const T* Din, T* Dout,
+                int64_t ldw, T* Y, int64_t ldy, real_t<T> c1, real_t<T> c2, bool write_r);
+
 // ---- spmm.cu ----------------------------------------------------------------------------------------
 struct StencilDesc {
   int gx, gy, gz;          // local grid (gz = local planes of the z-slab)

@@ -23,6 +23,28 @@
 namespace lb2 {
 
 // -------------------------------------------------------------------------------------------------------
+template <typename T, typename ApplyA>
+int cheb_apply(lb2_ctx* ctx, const BuiltinOp* b, int64_t n, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy, T* Rw,
+               T* D0, T* D1, T* ADw, int64_t ldw, ApplyA&& applyA) {
+  using R = real_t<T>;
+  const double theta = 0.5 * (b->cheb_hi + b->cheb_lo), delta = 0.5 * (b->cheb_hi - b->cheb_lo);
+  const double sigma = theta / delta;
+  double rho_old = 1.0 / sigma;
+  T* Dcur = D0;
+  T* Dnext = D1;
+  if (int rc = cheb_init<T>(ctx, n, nc, X, ldx, Dcur, Y, ldy, ldw, (R)(1.0 / theta))) return rc;
+  for (int j = 1; j <= b->cheb_degree; j++) {
+    if (int rc = applyA(nc, Dcur, ADw)) return rc;
+    const double rho = 1.0 / (2.0 * sigma - rho_old);
+    if (int rc = cheb_update<T>(ctx, n, nc, ADw, j == 1 ? X : Rw, j == 1 ? ldx : ldw, Rw, Dcur, Dnext, ldw, Y, ldy,
+                                (R)(rho * rho_old), (R)(2.0 * rho / delta), j < b->cheb_degree))
+      return rc;
+    std::swap(Dcur, Dnext);
+    rho_old = rho;
+  }
+  return 0;
+}
+
 template <typename T>
 int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy) {
   if (b->prefix != Sc<T>::prefix) {
@@ -45,6 +67,21 @@ int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t 
       return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy);
     case OP_DIAG:
       return spmm_diag<T>(ctx, b->n, (const real_t<T>*)b->diag, nc, X, ldx, Y, ldy);
+    case OP_CHEB: {   // stand-alone apply (outside a solver): temporary workspace
+      const BuiltinOp* in = builtin_of(b->inner);
+      if (!in) {
+        fprintf(stderr, "lobpcg_b200: chebyshev preconditioner needs a built-in inner operator outside the solver\n");
+        return -1;
+      }
+      T* w = nullptr;
+      const size_t blk = (size_t)b->n * nc;
+      LB2_CUDA_OK(cudaMalloc(&w, sizeof(T) * 4 * blk));
+      int rc = cheb_apply<T>(ctx, b, b->n, nc, X, ldx, Y, ldy, w, w + blk, w + 2 * blk, w + 3 * blk, b->n,
+                             [&](int c, const T* D, T* AD) { return apply_builtin<T>(ctx, in, c, D, b->n, AD, b->n); });
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(w);
+      return rc;
+    }
   }
   return -1;
 }
@@ -274,6 +311,17 @@ template <typename T>
 int Solver<T>::apply(const LinOpRaw* op, int nc, const T* X, T* Y) {
   if (nc <= 0) return 0;
   const BuiltinOp* b = builtin_of(op);
+  if (b && b->kind == OP_CHEB) {
+    // T = p(A): workspace = the slab that is not current plus AS[:, k:2k] (both dead whenever T is applied: the old
+    // [X P W] has just been projected and [AP AW] is recomputed by the next Rayleigh-Ritz; step_impl / init), which also
+    // keeps every vector the inner operator reads inside the arena (row-partitioned runs read halo planes from the
+    // neighbour's arena at the same offset)
+    if (nc > k) { fprintf(stderr, "lobpcg_b200: preconditioner applied to more than sizeSub columns\n"); return -1; }
+    T* w = slab[1 - cur];
+    if (X == w || Y == w) { fprintf(stderr, "lobpcg_b200: preconditioner workspace aliases its operands\n"); return -1; }
+    return cheb_apply<T>(ctx, b, n, nc, X, n, Y, n, w, col(w, k), col(w, 2 * k), col(AS, k), n,
+                         [&](int c, const T* D, T* AD) { return apply(b->inner, c, D, AD); });
+  }
   if (b) {
     BuiltinOp local;
     if (ctx->comm && b->n != b->n_global && (b->kind == OP_STENCIL)) {

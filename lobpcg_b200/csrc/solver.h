@@ -52,7 +52,7 @@ struct State {  // == <p>_lobpcg_t (reference lobpcg.h:13-55)
 
 // ---- built-in operators (tag lives at the head of ctx->data) -------------------------------------------
 constexpr uint64_t kOpMagic = 0x4C42324F50455221ULL;  // "LB2OPER!"
-enum OpKind { OP_STENCIL = 0, OP_CSR = 1, OP_DIAG = 2, OP_BDG = 3 };
+enum OpKind { OP_STENCIL = 0, OP_CSR = 1, OP_DIAG = 2, OP_BDG = 3, OP_CHEB = 4 };
 
 struct BuiltinOp {
   uint64_t magic;
@@ -77,6 +77,12 @@ struct BuiltinOp {
   int from_csr;     // stencil operator recognised from CSR input (capi.cu: detect_stencil)
   // diag
   void* diag;
+  // upper bound of the spectrum (Gershgorin), computed on the host at construction; 0 = unknown
+  double spec_hi;
+  // chebyshev preconditioner T = p(A): `degree` applications of `inner` per block apply, spectrum window [lo, hi]
+  const LinOpRaw* inner;
+  int cheb_degree;
+  double cheb_lo, cheb_hi;
   // back pointer for host matvec shim
   LinOpRaw* self;
 };
@@ -90,6 +96,13 @@ inline const BuiltinOp* builtin_of(const LinOpRaw* op) {
 // Y = Op X for a built-in operator (device block vectors)
 template <typename T>
 int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy);
+
+// Y = p(A) X for an OP_CHEB operator: cheb_degree steps of the Chebyshev iteration for A y = x on [lo, hi] from y = 0
+// (y_1 = x / theta; r_j = r_{j-1} - A d_{j-1}; d_j = rho_j rho_{j-1} d_{j-1} + (2 rho_j / delta) r_j; y += d_j).
+// R, D0, D1, AD: workspace blocks (n x nc, leading dimension ldw); applyA(nc, D, AD) computes AD = A D.
+template <typename T, typename ApplyA>
+int cheb_apply(lb2_ctx* ctx, const BuiltinOp* b, int64_t n, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy, T* Rw,
+               T* D0, T* D1, T* ADw, int64_t ldw, ApplyA&& applyA);
 
 // ---- phase statistics ----------------------------------------------------------------------------------
 enum Phase { PH_SPMM = 0, PH_GRAM, PH_TALLNN, PH_RESID, PH_SMALL, PH_COMM, PH_OTHER, PH_COUNT };

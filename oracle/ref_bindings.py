@@ -104,6 +104,14 @@ def op_bdg(grid, dtype, shift, d, cdiag=None, coff=-1.0):
     return RefOp(p, f(g[0], g[1], g[2], cdiag, coff, shift, d.real, d.imag), 2 * g[0] * g[1] * g[2])
 
 
+def op_cheb(A: RefOp, degree, lo, hi):
+    """T = p(A) for the reference solver: Chebyshev steps through A's own matvec (oracle/ref_harness.c)."""
+    f = getattr(lib(), f"ref_{A.prefix}_op_cheb")
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double]
+    f.restype = C.c_void_p
+    return RefOp(A.prefix, f(A.handle, int(degree), float(lo), float(hi)), A.n, (A,))
+
+
 def solve(A, X0, nev, tol, max_iter, B=None, T=None, indefinite=False, verbosity=0):
     """Run <p>_lobpcg / <p>_ilobpcg of the reference.  Returns dict(eig,res,X,iter,converged,sig)."""
     X = np.array(X0, order="F", copy=True)

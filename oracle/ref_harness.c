@@ -7,6 +7,7 @@
  * caller can bind:
  *
  *   ref_<p>_op_stencil / _op_csr / _op_diag / _op_bdg   build LinearOperator_<p>_t (linop.h:20-26)
+ *   ref_<p>_op_cheb                                     polynomial preconditioner over another operator (for alg->T)
  *   ref_<p>_op_apply                                    apply_block_op (src/gram/gram_impl.inc:29-33)
  *   ref_<p>_solve                                       <p>_lobpcg / <p>_ilobpcg (src/core/*_impl.inc)
  *
@@ -133,9 +134,40 @@ typedef struct {
     c.cdiag = cdiag; c.coff = coff; c.shift = shift; c.dre = dre; c.dim = dim;                   \
     return P##_mk((uint64_t)c.n, P##_mv_bdg, c);                                                 \
   }                                                                                              \
+  /* T = p(A): `degree` Chebyshev steps for A y = x on [lo, hi] through the inner operator's own matvec — the   \
+   * reference-side twin of lb2_op_chebyshev, used as alg->T of the UNMODIFIED reference solver in parity runs */  \
+  static void P##_mv_cheb(const OPT *op, CT *restrict x, CT *restrict y) {                       \
+    const href_ctx_t *c = (const href_ctx_t *)op->ctx->data;                                     \
+    const OPT *A = (const OPT *)c->val;                                                          \
+    const int64_t n = c->n;                                                                      \
+    CT *r = (CT *)c->scratch, *d = r + n, *ad = d + n;                                           \
+    const double theta = 0.5 * (c->dim + c->dre), delta = 0.5 * (c->dim - c->dre);               \
+    const double sigma = theta / delta;                                                          \
+    double rho_old = 1.0 / sigma;                                                                \
+    for (int64_t i = 0; i < n; i++) { r[i] = x[i]; d[i] = x[i] * (RT)(1.0 / theta); y[i] = d[i]; } \
+    for (int64_t j = 0; j < c->gx; j++) {                                                        \
+      A->matvec(A, d, ad);                                                                       \
+      const double rho = 1.0 / (2.0 * sigma - rho_old);                                          \
+      const RT c1 = (RT)(rho * rho_old), c2 = (RT)(2.0 * rho / delta);                           \
+      for (int64_t i = 0; i < n; i++) {                                                          \
+        r[i] -= ad[i];                                                                           \
+        d[i] = c1 * d[i] + c2 * r[i];                                                            \
+        y[i] += d[i];                                                                            \
+      }                                                                                          \
+      rho_old = rho;                                                                             \
+    }                                                                                            \
+  }                                                                                              \
+  void *ref_##P##_op_cheb(void *inner, int64_t degree, double lo, double hi) {                   \
+    href_ctx_t c = {0};                                                                          \
+    c.kind = 4; c.n = (int64_t)((OPT *)inner)->rows; c.gx = degree; c.dre = lo; c.dim = hi;      \
+    c.val = inner;                                                                               \
+    c.scratch = calloc((size_t)(3 * c.n), sizeof(CT));                                           \
+    return P##_mk((uint64_t)c.n, P##_mv_cheb, c);                                                \
+  }                                                                                              \
   void ref_##P##_op_free(void *opv) {                                                            \
     OPT *op = (OPT *)opv;                                                                        \
     if (!op) return;                                                                             \
+    free(((href_ctx_t *)op->ctx->data)->scratch);                                                \
     free(op->ctx->data);                                                                         \
     free(op->ctx);                                                                               \
     free(op);                                                                                    \

@@ -167,6 +167,37 @@ def solver_runs(out):
     run("z3d", rb.op_stencil((10, 10, 10), np.complex128), pr.initial_block(n, 8, 9, np.complex128), 4, 1e-8, 3000)
 
 
+def preconditioned_cases():
+    """Runs with the polynomial preconditioner T = p(A) (lb2_op_chebyshev / ref_<p>_op_cheb): (A builder args, T args)."""
+    g = (16, 16, 16)
+    pot = pr.harmonic_potential(g, 0.3)
+    return {
+        "cheb3d": dict(grid=g, pot=None, nev=6, k=12, degree=8, lo=0.3, hi=12.0, mass=False, csr=False),
+        "cheb_gen3d": dict(grid=(12, 12, 12), pot=None, nev=4, k=8, degree=5, lo=0.5, hi=12.0, mass=True, csr=False),
+        "cheb_pot_csr": dict(grid=g, pot=pot, nev=6, k=12, degree=6, lo=0.4, hi=12.0 + float(pot.max()), mass=False, csr=True),
+    }
+
+
+def preconditioned_runs(out):
+    for tag, c in preconditioned_cases().items():
+        g = c["grid"]; n = g[0] * g[1] * g[2]
+        if c["csr"]:
+            rp, cc, v = pr.laplacian_csr(g, potential=c["pot"])
+            A = rb.op_csr(rp, cc, v)
+        else:
+            A = rb.op_stencil(g, np.float64, potential=c["pot"])
+        B = rb.op_diag(pr.mass_diagonal(n), np.float64) if c["mass"] else None
+        T = rb.op_cheb(A, c["degree"], c["lo"], c["hi"])
+        X0 = pr.initial_block(n, c["k"], 7)
+        r = rb.solve(A, X0, c["nev"], 1e-8, 3000, B=B, T=T)
+        r0 = rb.solve(A, X0, c["nev"], 1e-8, 3000, B=B)
+        out[f"run_{tag}_eig"] = r["eig"]
+        out[f"run_{tag}_res"] = r["res"]
+        out[f"run_{tag}_meta"] = np.array([r["iter"], r["converged"], c["nev"], c["k"]])
+        out[f"run_{tag}_iter_without_T"] = np.array([r0["iter"]])
+        print(tag, "iter", r["iter"], "(without T:", r0["iter"], ") conv", r["converged"], r["eig"][:c["nev"]])
+
+
 def indefinite_cases():
     """Inputs of the ilobpcg parity cases (shared with tests/test_gpu_solver.py through this module)."""
     cases = {}
@@ -214,6 +245,12 @@ if __name__ == "__main__":
     single_calls(out)
     solver_runs(out)
     indefinite_runs(out)
+    preconditioned_runs(out)
+    old = OUT / "reference_runs.npz"
+    if old.exists():   # fixtures are deterministic (fixed time() in the harness): regenerating must not change them
+        prev = np.load(old)
+        changed = [k for k in prev.files if k in out and not np.array_equal(prev[k], out[k])]
+        print("keys changed by regeneration:", changed)
     np.savez_compressed(OUT / "reference_runs.npz", **out)
     print("wrote", OUT / "reference_runs.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB", flush=True)
     import os

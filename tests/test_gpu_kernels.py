@@ -366,3 +366,20 @@ def test_pipelined_host_copy_round_trip_is_exact(ctx):
         ss = api.col_sumsq(ctx, api.DeviceArray.from_numpy(ctx, np.ones((1000, 1))))     # small path still works
         assert abs(ss.numpy(ctx)[0] - 1000.0) < 1e-9
         d.free()
+
+
+# ------------------------------------------------------------------------------------------------ preconditioner
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("degree", [0, 1, 2, 7])
+def test_chebyshev_operator_matches_oracle(ctx, dt, degree):
+    """T = p(A) applied as a block operator (lb2_op_apply on an lb2_op_chebyshev handle) vs the numpy restatement."""
+    g = (9, 8, 7)
+    n = 9 * 8 * 7
+    rng = np.random.default_rng(degree)
+    X = rand(rng, (n, 5), dt)
+    A = api.stencil_op(g, dt)
+    T = api.chebyshev_op(A, degree, 0.25, 12.0)
+    Y = T.apply(ctx, api.DeviceArray.from_numpy(ctx, X)).numpy(ctx)
+    ref = no.op_chebyshev(no.op_stencil(g, dt), degree, 0.25, 12.0)(X.astype(np.complex128 if np.dtype(dt).kind == "c"
+                                                                            else np.float64))
+    close(Y, ref, 1e-12 if rtol(dt) < 1e-6 else 1e-4)

@@ -94,6 +94,47 @@ def test_float_generalized_pencil():
     assert relerr(r["eig"][:4], REF["run_gen3d_eig"][:4]) < 1e-4     # float agrees with the double reference run
 
 
+def _precond_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_cases", GOLD / "make_golden.py")
+    src = (GOLD / "make_golden.py").read_text()
+    ns = {"pr": pr, "np": np}
+    start = src.index("def preconditioned_cases():")
+    exec(src[start:src.index("def preconditioned_runs(out):")], ns)
+    return ns["preconditioned_cases"]()
+
+
+@pytest.mark.parametrize("tag", ["cheb3d", "cheb_gen3d", "cheb_pot_csr"])
+def test_builtin_chebyshev_preconditioner_matches_reference_run(tag):
+    """alg->T = lb2_op_chebyshev(A, ...) against the UNMODIFIED reference driven with the same polynomial as a host
+    callback T (oracle/ref_harness.c: ref_<p>_op_cheb): same converged count, eigenvalues to 1e-10, and the
+    preconditioner does its job (far fewer passes than the reference needs without T)."""
+    c = _precond_cases()[tag]
+    g = c["grid"]
+    n = g[0] * g[1] * g[2]
+    if c["csr"]:
+        A = api.csr_op(*pr.laplacian_csr(g, potential=c["pot"]))
+    else:
+        A = api.stencil_op(g, np.float64, potential=c["pot"])
+    B = api.diag_op(pr.mass_diagonal(n), np.float64) if c["mass"] else None
+    T = api.chebyshev_op(A, c["degree"], c["lo"], c["hi"])
+    r = api.lobpcg(A, pr.initial_block(n, c["k"], 7), c["nev"], 1e-8, 3000, B=B, T=T)
+    check_against_reference(tag, r, 1e-8)
+    it_ref = int(REF[f"run_{tag}_meta"][0])
+    it_plain = int(REF[f"run_{tag}_iter_without_T"][0])
+    assert r["iter"] <= it_ref + max(3, it_ref // 4)
+    assert r["iter"] * 3 < it_plain
+
+
+def test_chebyshev_default_window_uses_gershgorin_bound():
+    g = (14, 14, 14)
+    A = api.stencil_op(g, np.float64)
+    T = api.chebyshev_op(A, 6)                      # hi = 6 + 6*1 = 12 (Gershgorin), lo = hi / 50
+    r = api.lobpcg(A, pr.initial_block(14 ** 3, 8, 3), 4, 1e-8, 3000, T=T)
+    assert r["converged"] == 4
+    assert relerr(r["eig"][:4], pr.laplacian_eigs(g, 4)) < 1e-10
+
+
 def test_soft_locking_diag30():
     k = KA["lobpcg_softlock_diag30"]                    # reference tests/test_lobpcg.c:455-500
     r = api.lobpcg(api.diag_op(np.arange(1.0, 31.0), np.float64), pr.initial_block(30, 6, 5), 3, k["tol"], 500)

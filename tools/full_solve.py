@@ -1,13 +1,16 @@
 """Time-to-solution of a BASELINE config on 1..N GPUs (torchrun for N>1):
-   python tools/full_solve.py G NEV [tol] [maxiter]      -> JSON line with iterations, seconds, eigenvalue errors"""
+   python tools/full_solve.py G NEV [tol] [maxiter] [cheb=DEGREE,LO]   -> JSON line with iterations, seconds, eigenvalue errors
+cheb=DEGREE,LO uses the built-in polynomial preconditioner T = lb2_op_chebyshev(A, DEGREE, LO, Gershgorin bound)."""
 import os, sys, time, json
 sys.path.insert(0, ".")
 import numpy as np
 import torch
 from lobpcg_b200 import api, dist, problems as pr
 
-g = int(sys.argv[1]); nev = int(sys.argv[2]); tol = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-8
-maxit = int(sys.argv[4]) if len(sys.argv) > 4 else 5000
+cheb = next((a.split("=")[1] for a in sys.argv if a.startswith("cheb=")), None)
+argv = [a for a in sys.argv if not a.startswith("cheb=")]
+g = int(argv[1]); nev = int(argv[2]); tol = float(argv[3]) if len(argv) > 3 else 1e-8
+maxit = int(argv[4]) if len(argv) > 4 else 5000
 k = 2 * nev; n = g ** 3
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr)
@@ -19,7 +22,11 @@ if world > 1:
 else:
     part = None
     A = api.stencil_op((g, g, g), np.float64)
-s = api.Solver(ctx, A, n, k, nev, np.float64, tol, maxit, device_seed=7)
+T = None
+if cheb:
+    deg, lo = cheb.split(",")
+    T = api.chebyshev_op(A, int(deg), float(lo), 0.0)
+s = api.Solver(ctx, A, n, k, nev, np.float64, tol, maxit, T=T, device_seed=7)
 if part is not None:
     dist.attach(s, part)
 t0 = time.time(); s.init(); ctx.sync(); t_init = time.time() - t0
@@ -43,7 +50,7 @@ lib = api.lib()
 eigs, resn = s.results()
 stats = s.stats()
 if rank == 0:
-    out = dict(grid=g, nev=nev, k=k, n_gpus=world, tol=tol, init_s=t_init, solve_s=t_solve, passes=p["iter"] + 1,
+    out = dict(grid=g, nev=nev, k=k, n_gpus=world, tol=tol, preconditioner=("chebyshev degree,lo=" + cheb) if cheb else None, init_s=t_init, solve_s=t_solve, passes=p["iter"] + 1,
                converged=p["converged"], use_ortho=p["use_ortho"], s_per_pass=t_solve / (p["iter"] + 1),
                phases_ms_per_pass={kk: round(v["ms"] / (p["iter"] + 1), 2) for kk, v in stats.items()})
     an = pr.laplacian_eigs((g, g, g), nev)
