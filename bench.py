@@ -272,6 +272,37 @@ def run_ours(args):
     else:
         s.close()
 
+    # ---- time to solution of the same config (BASELINE metric "time-to-solution"): full solve to tol 1e-8 with the
+    # built-in polynomial preconditioner behind alg->T; the unpreconditioned solve needs 810 passes
+    # (profiles/full_solve_c5_1gpu_r01.json) and does not fit a bench run
+    tts = None
+    if not args.no_tts:
+        from lobpcg_b200 import problems as pr
+        if world > 1:
+            A2 = dist.partitioned_stencil(ctx, part, np.float64, k)
+        else:
+            A2 = api.stencil_op((g, g, g), np.float64)
+        T2 = api.chebyshev_op(A2, args.cheb_degree, args.cheb_lo, 0.0)
+        s2 = api.Solver(ctx, A2, n, k, nev, np.float64, 1e-8, 2000, T=T2, device_seed=7)
+        if part is not None:
+            dist.attach(s2, part)
+        barrier()
+        t0 = time.perf_counter()
+        s2.init()
+        while s2.step(10) == 10:
+            pass
+        barrier()
+        t_tts = time.perf_counter() - t0
+        p2 = s2.progress()
+        eigs2, res2 = s2.results()
+        an = pr.laplacian_eigs((g, g, g), nev)
+        tts = {"seconds": t_tts, "passes": int(p2["iter"]) + 1, "converged": int(p2["converged"]), "nev": nev, "tol": 1e-8,
+               "preconditioner": f"lb2_op_chebyshev(A, degree={args.cheb_degree}, lo={args.cheb_lo}, hi=Gershgorin)",
+               "max_rel_eig_err_vs_analytic": float(np.max(np.abs(eigs2[:nev] - an) / an)),
+               "max_resnorm": float(res2[:nev].max()),
+               "unpreconditioned_reference_point": "810 passes, 334 s on 1 GPU (profiles/full_solve_c5_1gpu_r01.json)"}
+        s2.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_reference_rate(g, nev, k, 2)
@@ -286,7 +317,7 @@ def run_ours(args):
             "config": {"workload": workload_desc(g, nev, k), "parallelism": f"rows in {world} z-slab(s)",
                        "l2": "inputs larger than L2 (each n x 3k slab is %.1f GB per GPU)" % (n_local * 3 * k * 8 / 1e9),
                        "solver_state": prog},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "time_to_solution": tts, "gpu_launches": int(launches),
             "clocks": clocks, "kernels": kernels, "hbm_peak_gbs": hbm, "hbm_peak_source": how_hbm,
         }
         print(json.dumps(line))
@@ -304,6 +335,9 @@ def main():
     ap.add_argument("--nev", type=int, default=150)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tts", action="store_true", help="skip the preconditioned full solve (time_to_solution)")
+    ap.add_argument("--cheb-degree", type=int, default=30)
+    ap.add_argument("--cheb-lo", type=float, default=0.04)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -14,7 +14,15 @@ import numpy as np
 
 from lobpcg_b200 import api, problems as pr
 
-which = sys.argv[1:] or ["C1", "C2", "C2csr", "C3d", "C3s", "C4"]
+CHEB = next((a.split("=")[1] for a in sys.argv[1:] if a.startswith("cheb=")), None)   # cheb=DEGREE,LO: built-in T = p(A)
+which = [a for a in sys.argv[1:] if not a.startswith("cheb=")] or ["C1", "C2", "C2csr", "C3d", "C3s", "C4"]
+
+
+def precond(A):
+    if not CHEB:
+        return None
+    deg, lo = CHEB.split(",")
+    return api.chebyshev_op(A, int(deg), float(lo), 0.0)
 ctx = api.Context(0)
 
 
@@ -31,7 +39,7 @@ def solve(name, A, n, nev, dtype, tol, B=None, T=None, indefinite=False, X0=None
     p = s.progress()
     eigs, resn = s.results()
     passes = p["iter"] + 1
-    out = dict(config=name, n=n, nev=nev, k=k, dtype=str(np.dtype(dtype)), tol=tol, init_s=round(t_init, 3),
+    out = dict(config=name + (f" + chebyshev T ({CHEB})" if CHEB and T is not None else ""), n=n, nev=nev, k=k, dtype=str(np.dtype(dtype)), tol=tol, init_s=round(t_init, 3),
                solve_s=round(t_solve, 3), passes=passes, iters_per_s=round(passes / t_solve, 3), converged=p["converged"],
                use_ortho=p["use_ortho"], max_resnorm=float(resn[:nev].max()),
                phases_ms_per_pass={kk: round(v["ms"] / passes, 3) for kk, v in s.stats().items()})
@@ -48,7 +56,8 @@ def err_vs(an):
 
 if "C1" in which:   # 2-D 5-point 100x100, nev=10, unpreconditioned
     g = (100, 100)
-    solve("C1", api.stencil_op(g, np.float64), 10000, 10, np.float64, 1e-8, extra=err_vs(pr.laplacian_eigs(g, 10)))
+    A = api.stencil_op(g, np.float64)
+    solve("C1", A, 10000, 10, np.float64, 1e-8, T=precond(A), extra=err_vs(pr.laplacian_eigs(g, 10)))
 
 for name in ("C2", "C2csr"):   # 3-D 7-point 128^3 as CSR, nev=64, Jacobi T
     if name not in which:
@@ -60,7 +69,7 @@ for name in ("C2", "C2csr"):   # 3-D 7-point 128^3 as CSR, nev=64, Jacobi T
     rp, col, val = pr.laplacian_csr(g)
     A = api.csr_op(rp, col, val)
     os.environ.pop("LB2_CSR_NO_STENCIL_DETECT", None)
-    T = api.diag_op(np.full(n, 1.0 / 6.0), np.float64)
+    T = precond(A) or api.diag_op(np.full(n, 1.0 / 6.0), np.float64)
     solve(name + (" (general CSR kernel)" if name == "C2csr" else " (CSR recognised as a stencil)"), A, n, 64, np.float64,
           1e-8, T=T, extra=err_vs(pr.laplacian_eigs(g, 64)))
     del A, rp, col, val
@@ -72,7 +81,8 @@ for name, dt, tol in (("C3d", np.float64, 1e-8), ("C3s", np.float32, 1e-4)):   #
     g = (160, 160, 160)
     n = 160 ** 3
     b = pr.mass_diagonal(n)
-    c3[name] = solve(name, api.stencil_op(g, dt), n, 100, dt, tol, B=api.diag_op(b, dt))
+    A = api.stencil_op(g, dt)
+    c3[name] = solve(name, A, n, 100, dt, tol, B=api.diag_op(b, dt), T=precond(A))
 if len(c3) == 2:
     print(json.dumps({"config": "C3 float vs double", "max_rel_eig_diff": float(np.max(np.abs(c3["C3s"] - c3["C3d"]) /
                                                                                    np.abs(c3["C3d"])))}), flush=True)
