@@ -155,6 +155,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "gram_bk")) c->gram_bk = value;
   else if (!strcmp(key, "gram_load_pct")) c->gram_load_pct = value;
   else if (!strcmp(key, "gram_strip_max")) c->gram_strip_max = value;
+  else if (!strcmp(key, "gram_strip_fma")) c->gram_strip_fma = value;
   else if (!strcmp(key, "spmm_cols")) c->spmm_cols = value;
   else return -1;
   return 0;

@@ -31,6 +31,7 @@ struct lb2_ctx {
   int gram_wl = -1;      // f64 Gram through the work-list kernel (gram_wl.cu): -1 = auto, 0 = never, 1 = always
   int gram_bk = 0;       // K chunk of the work-list Gram: 0/16 or 32 (tuning)
   int gram_strip_max = 0; // work-list Gram: ragged last tile columns narrower than this go to the lock-step kernel (0 = always, -1 = never)
+  int gram_strip_fma = 0; // work-list Gram: -1 = never use the streaming FMA kernel for narrow strips (testing)
   int gram_load_pct = 0; // work-list Gram: staging-traffic cost of a tile with 256 columns in % of its DMMA time (0 = default)
   void* hostcopy = nullptr;        // lb2::HostCopyState* (pinned ring for pageable host <-> device block transfers)
   void* gram_wl_cache = nullptr;   // lb2::WlCache* (schedules per Gram shape)

@@ -558,6 +558,89 @@ static int run_wl(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int6
   return launch_wl<16, 4>(ctx, f->second, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
 }
 
+// ------------------------------------------------------------------------------------------------- narrow strips
+// G[0:ma, c0:c0+r] = A^H B[:, c0:c0+r] for a NARROW strip (r <= 8; wider ones would re-read the strip from L2 too often): a few hundred MFLOP per streamed GB, so the only
+// thing that matters is how A is read.  The tile kernels read BK x 8-byte column pieces (one DRAM page each, ~2 TB/s);
+// here a CTA owns CB columns of A and one contiguous row range and streams each column in long runs (coalesced 2 KB
+// per CTA and iteration), keeps a CB x RB block of dot products in FP64 FMA registers, and re-reads the r strip values of
+// a row from L2 (grid.x = column groups is the fast index, so the CTAs that run together share the same strip rows).
+template <int CB, int RB>
+__global__ void __launch_bounds__(256)
+    strip_gram_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ Bs, int64_t ldb, int ma, int r,
+                      int64_t n, int64_t rows_per_split, double* __restrict__ part) {
+  const int c0 = blockIdx.x * CB;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r_end = min(n, r_begin + rows_per_split);
+  double acc[CB][RB];
+#pragma unroll
+  for (int c = 0; c < CB; c++)
+#pragma unroll
+    for (int j = 0; j < RB; j++) acc[c][j] = 0.0;
+  const double* ap[CB];
+#pragma unroll
+  for (int c = 0; c < CB; c++) ap[c] = A + (int64_t)min(c0 + c, ma - 1) * lda;   // columns past ma: duplicates, never stored
+  for (int64_t row = r_begin + threadIdx.x; row < r_end; row += 256) {
+    double b[RB], a[CB];
+#pragma unroll
+    for (int c = 0; c < CB; c++) a[c] = ap[c][row];
+#pragma unroll
+    for (int j = 0; j < RB; j++) b[j] = (j < r) ? Bs[row + (int64_t)j * ldb] : 0.0;
+#pragma unroll
+    for (int c = 0; c < CB; c++)
+#pragma unroll
+      for (int j = 0; j < RB; j++) acc[c][j] = fma(a[c], b[j], acc[c][j]);
+  }
+  __shared__ double red[8][CB * RB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < CB; c++)
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+      const double v = warp_sum(acc[c][j]);
+      if (lane == 0) red[warp][c * RB + j] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < CB * RB) {
+    const int c = threadIdx.x / RB, j = threadIdx.x % RB;
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) v += red[w][threadIdx.x];
+    if (c0 + c < ma && j < r) part[(int64_t)blockIdx.y * ((int64_t)ma * r) + (c0 + c) + (int64_t)j * ma] = v;
+  }
+}
+
+__global__ void strip_reduce_kernel(const double* __restrict__ part, int nsplit, int ma, int r, double* __restrict__ G,
+                                    int ldg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ma * r) return;
+  double s = 0.0;
+  for (int k = 0; k < nsplit; k++) s += part[(int64_t)k * ((int64_t)ma * r) + idx];
+  G[(idx % ma) + (int64_t)(idx / ma) * ldg] = s;
+}
+
+// G[0:ma, 0:r] (leading dimension ldg) = A^H Bs, Bs = the r strip columns
+static int strip_gram(lb2_ctx* ctx, int64_t n, int ma, int r, const double* A, int64_t lda, const double* Bs, int64_t ldb,
+                      double* G, int ldg) {
+  const int CB = 8;
+  const int ngroups = (ma + CB - 1) / CB;
+  // ~8 resident CTAs per SM; splits of at least 4096 rows
+  int nsplit = std::max(1, (ctx->sm_count * 8 + ngroups - 1) / ngroups);
+  nsplit = (int)std::min<int64_t>(nsplit, std::max<int64_t>(1, n / 4096));
+  const int64_t rps = ((n + nsplit - 1) / nsplit + 255) / 256 * 256;
+  nsplit = (int)((n + rps - 1) / rps);
+  double* part = (double*)ctx_scratch(ctx, sizeof(double) * (size_t)nsplit * ma * r);
+  if (!part) return -1;
+  dim3 grid(ngroups, nsplit);
+  if (r <= 4) strip_gram_kernel<8, 4><<<grid, 256, 0, ctx->stream>>>(A, lda, Bs, ldb, ma, r, n, rps, part);
+  else strip_gram_kernel<8, 8><<<grid, 256, 0, ctx->stream>>>(A, lda, Bs, ldb, ma, r, n, rps, part);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  strip_reduce_kernel<<<(ma * r + 255) / 256, 256, 0, ctx->stream>>>(part, nsplit, ma, r, G, ldg);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // G[c, i] = G[i, c] for the strip columns c = c0 .. c0 + r - 1 and every row i < c: lower mirror of a strip that was
 // computed as a rectangular product (its r x r diagonal block is made exactly symmetric, like the mirrored tiles)
 __global__ void mirror_strip_kernel(double* __restrict__ G, int ldg, int c0, int r) {
@@ -573,9 +656,10 @@ __global__ void mirror_strip_kernel(double* __restrict__ G, int ldg, int c0, int
 // The work-list schedule has no two CTAs on the same rows at the same time, so every operand byte comes from HBM in
 // BK x 8-byte pieces; measured on B200 that pattern tops out near 2 TB/s, which a full 128 x 128 tile just stays under
 // (it needs 32 KB per 2 us and SM) but a narrow ragged tile does not (same panel traffic, a few DMMAs).  A Hermitian
-// product whose last tile column is narrow (m mod 128 < gram_strip_max, default: always) is therefore split: the leading
-// multiple of 128 goes through the work list, the strip G[:, c0:m] through the lock-step kernel of dense.cu (its CTAs
-// share the panel through L2), and the strip is mirrored.
+// product whose last tile column is ragged (m mod 128 != 0) is therefore split: the leading multiple of 128 goes
+// through the work list; the strip G[:, c0:m] through strip_gram_kernel when it is at most 8 columns wide (streams A
+// once in long runs, FP64 FMA) and through the lock-step kernel of dense.cu otherwise (its CTAs share the panel
+// through L2); the strip is then mirrored.
 int gram_wl_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B, int64_t ldb,
                 double* G, int ldg, int upper) {
   const int strip_max = ctx->gram_strip_max > 0 ? ctx->gram_strip_max : (ctx->gram_strip_max < 0 ? 0 : WL_T);
@@ -583,7 +667,10 @@ int gram_wl_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_
   if (upper && c0 > 0 && r > 0 && r < strip_max) {
     int rc = run_wl(ctx, n, c0, c0, A, lda, B, ldb, G, ldg, 1);
     if (rc) return rc;
-    rc = gram_tiles_f64(ctx, n, ma, r, A, lda, B + (int64_t)c0 * ldb, ldb, G + (int64_t)c0 * ldg, ldg, 0);
+    if (r <= 8 && ctx->gram_strip_fma >= 0)
+      rc = strip_gram(ctx, n, ma, r, A, lda, B + (int64_t)c0 * ldb, ldb, G + (int64_t)c0 * ldg, ldg);
+    else
+      rc = gram_tiles_f64(ctx, n, ma, r, A, lda, B + (int64_t)c0 * ldb, ldb, G + (int64_t)c0 * ldg, ldg, 0);
     if (rc) return rc;
     mirror_strip_kernel<<<(ma * r + 255) / 256, 256, 0, ctx->stream>>>(G, ldg, c0, r);
     ctx->launches++;

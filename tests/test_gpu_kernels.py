@@ -56,8 +56,8 @@ def test_gram_matches_oracle(ctx, dt, shape):
 
 
 @pytest.mark.parametrize("shape", [(9000, 900), (20000, 300), (12345, 517), (8192, 128), (50000, 129), (6000, 1030),
-                                   (4500, 256), (7001, 384)])
-@pytest.mark.parametrize("opts", [{}, {"gram_bk": 16}, {"gram_strip_max": -1}, {"gram_wl": 0}])
+                                   (4500, 256), (7001, 384), (30000, 136), (10001, 263)])
+@pytest.mark.parametrize("opts", [{}, {"gram_bk": 16}, {"gram_strip_max": -1}, {"gram_wl": 0}, {"gram_strip_fma": -1}])
 def test_gram_hermitian_worklist_kernel(ctx, shape, opts):
     """f64 Hermitian products S^H S and S^H (H S) (H = real diagonal, so the product is symmetric) through the
     work-list kernel: masked diagonal tiles, ragged last tile column (strip path and in-list path), odd n."""
