@@ -1115,9 +1115,13 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
       if (rc == 0 && rem > 0) {
         const double* Cr = C + (int64_t)nfull * 128 * ldc;
         double* Or = Out + (int64_t)nfull * 128 * ldo;
-        const int w = forced ? forced : (rem + 31) / 32 * 32;
-        if (w <= 32) rc = launch_nn_dmma<128, 32, 8, 1, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
+        // remainder tile widths in steps of 16 columns (16/48/80 run 4-warp CTAs, two per SM)
+        const int w = forced ? forced : (rem + 15) / 16 * 16;
+        if (w <= 16) rc = launch_nn_dmma<128, 16, 4, 1, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
+        else if (w <= 32) rc = launch_nn_dmma<128, 32, 8, 1, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
+        else if (w <= 48) rc = launch_nn_dmma<128, 48, 2, 2, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
         else if (w <= 64) rc = launch_nn_dmma<128, 64, 4, 2, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
+        else if (w <= 80) rc = launch_nn_dmma<128, 80, 2, 2, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
         else if (w <= 96) rc = launch_nn_dmma<128, 96, 4, 2, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
         else rc = launch_nn_dmma<128, 128, 2, 4, 16, 4>(ctx, n, kd, rem, alpha, S, lds, Cr, ldc, beta, Or, ldo);
       }

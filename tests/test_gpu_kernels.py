@@ -151,7 +151,8 @@ def test_gram_simt_and_dmma_paths_agree(ctx):
 
 # ------------------------------------------------------------------------------------------------ tall NN
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("shape", [(1, 1, 1), (130, 5, 3), (4097, 60, 40), (30001, 33, 129), (9000, 300, 70)])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (130, 5, 3), (4097, 60, 40), (30001, 33, 129), (9000, 300, 70),
+                                   (5000, 64, 300), (5001, 37, 90), (5003, 20, 16), (4999, 50, 30), (5000, 33, 110)])
 @pytest.mark.parametrize("ab", [(1.0, 0.0), (-1.0, 1.0)])
 def test_tall_nn_matches_oracle(ctx, dt, shape, ab):
     n, kd, nb = shape
