@@ -71,6 +71,20 @@ struct StencilDesc {
 };
 template <typename T>
 int spmm_stencil(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy);
+// Chebyshev-step epilogue of the stencil kernel (preconditioner T = p(A)): see spmm.cu
+template <typename T>
+struct ChebEpilogue {
+  const T* rin = nullptr;   // residual block read (x on the first step), leading dimension ldrin
+  int64_t ldrin = 0;
+  T* rout = nullptr;        // residual block written when write_r (leading dimension ldw)
+  T* dout = nullptr;        // new search direction block (leading dimension ldw)
+  int64_t ldw = 0;
+  real_t<T> c1 = 0, c2 = 0;
+  int write_r = 0;
+};
+template <typename T>
+int spmm_stencil_cheb(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* Din, int64_t ldd, T* Yacc, int64_t ldy,
+                      const ChebEpilogue<T>& ep);
 template <typename T>
 int spmm_csr(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val, int nc,
              const T* X, int64_t ldx, T* Y, int64_t ldy);

@@ -23,22 +23,43 @@
 namespace lb2 {
 
 // -------------------------------------------------------------------------------------------------------
-template <typename T, typename ApplyA>
+static StencilDesc stencil_desc(const BuiltinOp* b) {
+  StencilDesc d;
+  d.gx = (int)b->gx; d.gy = (int)b->gy; d.gz = (int)b->gz;
+  d.cdiag = b->cdiag; d.coff = b->coff; d.shift = b->shift;
+  d.potential = b->potential;
+  d.halo_lo = b->halo_lo; d.halo_hi = b->halo_hi; d.halo_ld = b->halo_ld;
+  d.bdg = (b->kind == OP_BDG) ? 1 : 0;
+  d.dre = b->dre; d.dim = b->dim;
+  return d;
+}
+
+// applyA(nc, D, AD): AD = A D.  fusedStep(nc, Din, Dout, Rin, ldrin, Rout, Y, c1, c2, write_r): one whole step inside the
+// operator kernel (stencil epilogue); returns -100 when the inner operator has no fused form.
+template <typename T, typename ApplyA, typename FusedStep>
 int cheb_apply(lb2_ctx* ctx, const BuiltinOp* b, int64_t n, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy, T* Rw,
-               T* D0, T* D1, T* ADw, int64_t ldw, ApplyA&& applyA) {
+               T* D0, T* D1, T* ADw, int64_t ldw, ApplyA&& applyA, FusedStep&& fusedStep) {
   using R = real_t<T>;
   const double theta = 0.5 * (b->cheb_hi + b->cheb_lo), delta = 0.5 * (b->cheb_hi - b->cheb_lo);
   const double sigma = theta / delta;
   double rho_old = 1.0 / sigma;
   T* Dcur = D0;
   T* Dnext = D1;
+  bool fused = true;
   if (int rc = cheb_init<T>(ctx, n, nc, X, ldx, Dcur, Y, ldy, ldw, (R)(1.0 / theta))) return rc;
   for (int j = 1; j <= b->cheb_degree; j++) {
-    if (int rc = applyA(nc, Dcur, ADw)) return rc;
     const double rho = 1.0 / (2.0 * sigma - rho_old);
-    if (int rc = cheb_update<T>(ctx, n, nc, ADw, j == 1 ? X : Rw, j == 1 ? ldx : ldw, Rw, Dcur, Dnext, ldw, Y, ldy,
-                                (R)(rho * rho_old), (R)(2.0 * rho / delta), j < b->cheb_degree))
-      return rc;
+    const R c1 = (R)(rho * rho_old), c2 = (R)(2.0 * rho / delta);
+    const T* Rin = (j == 1) ? X : Rw;
+    const int64_t ldrin = (j == 1) ? ldx : ldw;
+    const bool wr = j < b->cheb_degree;
+    int rc = fused ? fusedStep(nc, Dcur, Dnext, Rin, ldrin, Rw, Y, c1, c2, wr) : -100;
+    if (rc == -100) {
+      fused = false;
+      if ((rc = applyA(nc, Dcur, ADw))) return rc;
+      rc = cheb_update<T>(ctx, n, nc, ADw, Rin, ldrin, Rw, Dcur, Dnext, ldw, Y, ldy, c1, c2, wr);
+    }
+    if (rc) return rc;
     std::swap(Dcur, Dnext);
     rho_old = rho;
   }
@@ -53,16 +74,8 @@ int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t 
   }
   switch (b->kind) {
     case OP_STENCIL:
-    case OP_BDG: {
-      StencilDesc d;
-      d.gx = (int)b->gx; d.gy = (int)b->gy; d.gz = (int)b->gz;
-      d.cdiag = b->cdiag; d.coff = b->coff; d.shift = b->shift;
-      d.potential = b->potential;
-      d.halo_lo = b->halo_lo; d.halo_hi = b->halo_hi; d.halo_ld = b->halo_ld;
-      d.bdg = (b->kind == OP_BDG) ? 1 : 0;
-      d.dre = b->dre; d.dim = b->dim;
-      return spmm_stencil<T>(ctx, d, nc, X, ldx, Y, ldy);
-    }
+    case OP_BDG:
+      return spmm_stencil<T>(ctx, stencil_desc(b), nc, X, ldx, Y, ldy);
     case OP_CSR:
       return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy);
     case OP_DIAG:
@@ -76,8 +89,18 @@ int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t 
       T* w = nullptr;
       const size_t blk = (size_t)b->n * nc;
       LB2_CUDA_OK(cudaMalloc(&w, sizeof(T) * 4 * blk));
-      int rc = cheb_apply<T>(ctx, b, b->n, nc, X, ldx, Y, ldy, w, w + blk, w + 2 * blk, w + 3 * blk, b->n,
-                             [&](int c, const T* D, T* AD) { return apply_builtin<T>(ctx, in, c, D, b->n, AD, b->n); });
+      const bool can_fuse = (in->kind == OP_STENCIL) && !getenv("LB2_NO_CHEB_FUSE");
+      int rc = cheb_apply<T>(
+          ctx, b, b->n, nc, X, ldx, Y, ldy, w, w + blk, w + 2 * blk, w + 3 * blk, b->n,
+          [&](int c, const T* D, T* AD) { return apply_builtin<T>(ctx, in, c, D, b->n, AD, b->n); },
+          [&](int c, const T* Din, T* Dout, const T* Rin, int64_t ldrin, T* Rout, T* Yacc, real_t<T> c1, real_t<T> c2,
+              bool wr) {
+            if (!can_fuse) return -100;
+            ChebEpilogue<T> ep;
+            ep.rin = Rin; ep.ldrin = ldrin; ep.rout = Rout; ep.dout = Dout; ep.ldw = b->n; ep.c1 = c1; ep.c2 = c2;
+            ep.write_r = wr ? 1 : 0;
+            return spmm_stencil_cheb<T>(ctx, stencil_desc(in), c, Din, b->n, Yacc, ldy, ep);
+          });
       cudaStreamSynchronize(ctx->stream);
       cudaFree(w);
       return rc;
@@ -243,6 +266,7 @@ class Solver : public SolverBase {
   int rr_modified(int m, int from_col);
   int cp_from_z(int m, const T* Zm, T* VQ);           // VQ (m x k) = Z_perp Q
   int svqb(T* U, int nu, R tau, bool drop, int* nret);
+  int localize(const BuiltinOp*& b, BuiltinOp& local, const T* X);
   int ortho_drop(T* U, int nu, T* V, int nv, int* nret, bool indefinite = false);
   int rr_indef(int m, int from_col, bool initial);
   int ortho_indef_mat(int m, int nu, int nv, T* U, const T* V, const T* mat);
@@ -305,6 +329,31 @@ int Solver<T>::alloc() {
   return 0;
 }
 
+// z-slab partition of a stencil operator: every rank's X must be complete before neighbours read its boundary
+// planes; a one-element all-reduce on the solver stream is the barrier (all later overwrites of X are separated from
+// this read by the Gram / norm all-reduces of the pass, or by the barrier of the next apply).  Fills `local` with the
+// peer halo pointers for X (which must live in the arena: same offset on every rank) and redirects b to it.
+template <typename T>
+int Solver<T>::localize(const BuiltinOp*& b, BuiltinOp& local, const T* X) {
+  if (!(ctx->comm && b->n != b->n_global && b->kind == OP_STENCIL)) return 0;
+  tm.begin(PH_COMM);
+  int rcb = allreduce_sum(ctx, Scal + 12, 1, kDouble);
+  tm.end();
+  if (rcb) return rcb;
+  local = *b;
+  const size_t off = (size_t)((const char*)X - (const char*)arena);
+  if (off >= arena_bytes) {
+    fprintf(stderr, "lobpcg_b200: partitioned operator applied to a buffer outside the solver arena\n");
+    return -1;
+  }
+  const int64_t plane = b->gx * b->gy;
+  local.halo_lo = peer_lo ? (const void*)((const T*)(peer_lo + off) + (b->gz - 1) * plane) : nullptr;
+  local.halo_hi = peer_hi ? (const void*)(peer_hi + off) : nullptr;
+  local.halo_ld = n;
+  b = &local;
+  return 0;
+}
+
 // Y = Op X.  Built-in operators run as block kernels; anything else is a host callback (reference
 // linop.h:15-17) and is staged through pinned host memory column by column — functional, not fast.
 template <typename T>
@@ -319,31 +368,30 @@ int Solver<T>::apply(const LinOpRaw* op, int nc, const T* X, T* Y) {
     if (nc > k) { fprintf(stderr, "lobpcg_b200: preconditioner applied to more than sizeSub columns\n"); return -1; }
     T* w = slab[1 - cur];
     if (X == w || Y == w) { fprintf(stderr, "lobpcg_b200: preconditioner workspace aliases its operands\n"); return -1; }
-    return cheb_apply<T>(ctx, b, n, nc, X, n, Y, n, w, col(w, k), col(w, 2 * k), col(AS, k), n,
-                         [&](int c, const T* D, T* AD) { return apply(b->inner, c, D, AD); });
+    const BuiltinOp* in = builtin_of(b->inner);
+    const bool can_fuse = in && in->kind == OP_STENCIL && !getenv("LB2_NO_CHEB_FUSE");
+    return cheb_apply<T>(
+        ctx, b, n, nc, X, n, Y, n, w, col(w, k), col(w, 2 * k), col(AS, k), n,
+        [&](int c, const T* D, T* AD) { return apply(b->inner, c, D, AD); },
+        [&](int c, const T* Din, T* Dout, const T* Rin, int64_t ldrin, T* Rout, T* Yacc, R c1, R c2, bool wr) {
+          if (!can_fuse) return -100;
+          BuiltinOp local;
+          const BuiltinOp* bb = in;
+          if (int rcl = localize(bb, local, Din)) return rcl;
+          ChebEpilogue<T> ep;
+          ep.rin = Rin; ep.ldrin = ldrin; ep.rout = Rout; ep.dout = Dout; ep.ldw = n; ep.c1 = c1; ep.c2 = c2;
+          ep.write_r = wr ? 1 : 0;
+          tm.begin(PH_SPMM);
+          int rc = spmm_stencil_cheb<T>(ctx, stencil_desc(bb), c, Din, n, Yacc, n, ep);
+          tm.end();
+          phase_work[PH_SPMM] += (wr ? 6.0 : 5.0) * (double)n * c * sizeof(T);
+          phase_calls[PH_SPMM]++;
+          return rc;
+        });
   }
   if (b) {
     BuiltinOp local;
-    if (ctx->comm && b->n != b->n_global && (b->kind == OP_STENCIL)) {
-      // z-slab partition: every rank's X must be complete before neighbours read its boundary planes; a
-      // one-element all-reduce on the solver stream is the barrier (all later overwrites of X are separated
-      // from this read by the Gram / norm all-reduces of the pass).
-      tm.begin(PH_COMM);
-      int rcb = allreduce_sum(ctx, Scal + 12, 1, kDouble);
-      tm.end();
-      if (rcb) return rcb;
-      local = *b;
-      const size_t off = (size_t)((const char*)X - (const char*)arena);
-      if (off >= arena_bytes) {
-        fprintf(stderr, "lobpcg_b200: partitioned operator applied to a buffer outside the solver arena\n");
-        return -1;
-      }
-      const int64_t plane = b->gx * b->gy;
-      local.halo_lo = peer_lo ? (const void*)((const T*)(peer_lo + off) + (b->gz - 1) * plane) : nullptr;
-      local.halo_hi = peer_hi ? (const void*)(peer_hi + off) : nullptr;
-      local.halo_ld = n;
-      b = &local;
-    }
+    if (int rcl = localize(b, local, X)) return rcl;
     tm.begin(PH_SPMM);
     int rc = apply_builtin<T>(ctx, b, nc, X, n, Y, n);
     tm.end();

@@ -97,12 +97,9 @@ inline const BuiltinOp* builtin_of(const LinOpRaw* op) {
 template <typename T>
 int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy);
 
-// Y = p(A) X for an OP_CHEB operator: cheb_degree steps of the Chebyshev iteration for A y = x on [lo, hi] from y = 0
-// (y_1 = x / theta; r_j = r_{j-1} - A d_{j-1}; d_j = rho_j rho_{j-1} d_{j-1} + (2 rho_j / delta) r_j; y += d_j).
-// R, D0, D1, AD: workspace blocks (n x nc, leading dimension ldw); applyA(nc, D, AD) computes AD = A D.
-template <typename T, typename ApplyA>
-int cheb_apply(lb2_ctx* ctx, const BuiltinOp* b, int64_t n, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy, T* Rw,
-               T* D0, T* D1, T* ADw, int64_t ldw, ApplyA&& applyA);
+// OP_CHEB: Y = p(A) X, cheb_degree steps of the Chebyshev iteration for A y = x on [lo, hi] from y = 0
+// (y_1 = x / theta; r_j = r_{j-1} - A d_{j-1}; d_j = rho_j rho_{j-1} d_{j-1} + (2 rho_j / delta) r_j; y += d_j);
+// implemented in solver.cu (cheb_apply): fused into the stencil kernel's epilogue when A is a built-in stencil.
 
 // ---- phase statistics ----------------------------------------------------------------------------------
 enum Phase { PH_SPMM = 0, PH_GRAM, PH_TALLNN, PH_RESID, PH_SMALL, PH_COMM, PH_OTHER, PH_COUNT };

@@ -26,10 +26,13 @@ namespace lb2 {
 // =====================================================================================================
 template <typename T, int N> struct alignas(N * sizeof(T)) Pack { T v[N]; };
 
-template <typename T, int TXT, int TY, int EPT, int D, bool VECP, bool HAS_POT, bool BDG>
+// EPI = 1: Chebyshev-step epilogue (preconditioner T = p(A)).  X is the search direction d; instead of
+// storing A d the kernel finishes the step in registers:  r = r_in - A d;  d' = c1 d + c2 r;  y += d'  (6 block streams
+// per step instead of 9 for SpMM + separate update; d' goes to another block because neighbours still read d's halo).
+template <typename T, int TXT, int TY, int EPT, int D, bool VECP, bool HAS_POT, bool BDG, int EPI = 0>
 __global__ void __launch_bounds__(TXT* TY)
     stencil_kernel(StencilDesc d, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy, int ntx,
-                   int nty, int zchunk) {
+                   int nty, int zchunk, ChebEpilogue<T> ep) {
   using R = real_t<T>;
   using PK = Pack<T, EPT>;
   constexpr int TX = TXT * EPT;                // tile width in points; each thread owns EPT consecutive x
@@ -116,6 +119,9 @@ __global__ void __launch_bounds__(TXT* TY)
   for (int e = 0; e < EPT; e++) prev.v[e] = cur.v[e] = zero<T>();
   const int64_t idx0 = (int64_t)(z0 - 1) * plane + (int64_t)y * d.gx + x;
   T* yp = Y + (int64_t)col * ldy + hoff + idx0;                       // advanced by `plane` per step
+  const T* e_rin = EPI ? ep.rin + (int64_t)col * ep.ldrin + hoff + idx0 : nullptr;
+  T* e_rout = EPI ? ep.rout + (int64_t)col * ep.ldw + hoff + idx0 : nullptr;
+  T* e_dout = EPI ? ep.dout + (int64_t)col * ep.ldw + hoff + idx0 : nullptr;
   const R* pp = HAS_POT ? (const R*)d.potential + idx0 : nullptr;
   const T* op = BDG ? X + (int64_t)col * ldx + (half ? 0 : m) + idx0 : nullptr;
   int slot = 0;
@@ -157,17 +163,45 @@ __global__ void __launch_bounds__(TXT* TY)
         }
         out.v[e] = r;
       }
-      if (VECP && full) {
-        *reinterpret_cast<PK*>(yp) = out;
-      } else {
+      if (EPI == 0) {
+        if (VECP && full) {
+          *reinterpret_cast<PK*>(yp) = out;
+        } else {
 #pragma unroll
-        for (int e = 0; e < EPT; e++)
-          if (x + e < d.gx) yp[e] = out.v[e];
+          for (int e = 0; e < EPT; e++)
+            if (x + e < d.gx) yp[e] = out.v[e];
+        }
+      } else {   // out = A d at my points, cur = d; yp walks the accumulated solution y
+        if (VECP && full) {
+          const PK rin = *reinterpret_cast<const PK*>(e_rin);
+          PK yv = *reinterpret_cast<const PK*>(yp);
+          PK rn, dn;
+#pragma unroll
+          for (int e = 0; e < EPT; e++) {
+            rn.v[e] = sub_(rin.v[e], out.v[e]);
+            dn.v[e] = add_(rscale_(cur.v[e], ep.c1), rscale_(rn.v[e], ep.c2));
+            yv.v[e] = add_(yv.v[e], dn.v[e]);
+          }
+          if (ep.write_r) *reinterpret_cast<PK*>(e_rout) = rn;
+          *reinterpret_cast<PK*>(e_dout) = dn;
+          *reinterpret_cast<PK*>(yp) = yv;
+        } else {
+#pragma unroll
+          for (int e = 0; e < EPT; e++)
+            if (x + e < d.gx) {
+              const T rn = sub_(e_rin[e], out.v[e]);
+              const T dn = add_(rscale_(cur.v[e], ep.c1), rscale_(rn, ep.c2));
+              if (ep.write_r) e_rout[e] = rn;
+              e_dout[e] = dn;
+              yp[e] = add_(yp[e], dn);
+            }
+        }
       }
     }
     prev = cur;
     cur = next;
     yp += plane;
+    if (EPI) { e_rin += plane; e_rout += plane; e_dout += plane; }
     if (HAS_POT) pp += plane;
     if (BDG) op += plane;
   }
@@ -175,7 +209,8 @@ __global__ void __launch_bounds__(TXT* TY)
 }
 
 template <typename T, int TXT, int TY, int EPT, int D>
-static int launch_stencil(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy) {
+static int launch_stencil(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy,
+                          const ChebEpilogue<T>* ep = nullptr) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int PADL = (VEC > EPT) ? VEC : EPT;
   constexpr int TX = TXT * EPT;
@@ -191,16 +226,33 @@ static int launch_stencil(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* X
   if (plane >= (1LL << 31)) return -2;
   constexpr int AL = (VEC > EPT) ? VEC : EPT;
   auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
-  const bool vec_ok = (d.gx % AL == 0) && (ldx % AL == 0) && (ldy % AL == 0) && (plane % AL == 0) && al16(X) && al16(Y) &&
-                      (!d.halo_lo || (al16(d.halo_lo) && d.halo_ld % AL == 0)) &&
-                      (!d.halo_hi || (al16(d.halo_hi) && d.halo_ld % AL == 0)) && (!d.bdg || (plane * d.gz) % AL == 0);
+  bool vec_ok = (d.gx % AL == 0) && (ldx % AL == 0) && (ldy % AL == 0) && (plane % AL == 0) && al16(X) && al16(Y) &&
+                (!d.halo_lo || (al16(d.halo_lo) && d.halo_ld % AL == 0)) &&
+                (!d.halo_hi || (al16(d.halo_hi) && d.halo_ld % AL == 0)) && (!d.bdg || (plane * d.gz) % AL == 0);
+  if (ep) vec_ok = vec_ok && al16(ep->rin) && al16(ep->rout) && al16(ep->dout) && (ep->ldrin % AL == 0) && (ep->ldw % AL == 0);
   dim3 grid(ntx * nty * nz, nc, halves);
+  if (ep) {   // Chebyshev-step epilogue (plain stencil only)
+    if (d.bdg) return -2;
+#define LB2_STE(VP, HP)                                                                                      \
+  {                                                                                                          \
+    auto kern = stencil_kernel<T, TXT, TY, EPT, D, VP, HP, false, 1>;                                        \
+    if (smem > 48 * 1024)                                                                                    \
+      LB2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    kern<<<grid, TXT * TY, smem, ctx->stream>>>(d, X, ldx, Y, ldy, ntx, nty, zchunk, *ep);                   \
+  }
+    if (d.potential) { if (vec_ok) LB2_STE(true, true) else LB2_STE(false, true) }
+    else { if (vec_ok) LB2_STE(true, false) else LB2_STE(false, false) }
+#undef LB2_STE
+    ctx->launches++;
+    LB2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
 #define LB2_ST(VP, HP, BD)                                                                                   \
   {                                                                                                          \
     auto kern = stencil_kernel<T, TXT, TY, EPT, D, VP, HP, BD>;                                              \
     if (smem > 48 * 1024)                                                                                    \
       LB2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    kern<<<grid, TXT * TY, smem, ctx->stream>>>(d, X, ldx, Y, ldy, ntx, nty, zchunk);                        \
+    kern<<<grid, TXT * TY, smem, ctx->stream>>>(d, X, ldx, Y, ldy, ntx, nty, zchunk, ChebEpilogue<T>());     \
   }
   const bool hp = d.potential != nullptr;
   if (d.bdg) { if (vec_ok) LB2_ST(true, false, true) else LB2_ST(false, false, true) }
@@ -219,6 +271,17 @@ int spmm_stencil(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* X, int64_t
   constexpr int EPT = Sc<T>::cplx ? 1 : 2;   // consecutive x points per thread (16-byte packs for double)
   if (d.gy == 1 && d.gz == 1) return launch_stencil<T, 128, 1, EPT, 2>(ctx, d, nc, X, ldx, Y, ldy);
   return launch_stencil<T, 32, 8, EPT, 4>(ctx, d, nc, X, ldx, Y, ldy);
+}
+
+// One Chebyshev step with the stencil as A: r_out = r_in - A D, d_out = c1 D + c2 r_out, Yacc += d_out.
+template <typename T>
+int spmm_stencil_cheb(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* Din, int64_t ldd, T* Yacc, int64_t ldy,
+                      const ChebEpilogue<T>& ep) {
+  if (nc <= 0) return 0;
+  if (nc > 65535 || d.bdg) return -2;
+  constexpr int EPT = Sc<T>::cplx ? 1 : 2;
+  if (d.gy == 1 && d.gz == 1) return launch_stencil<T, 128, 1, EPT, 2>(ctx, d, nc, Din, ldd, Yacc, ldy, &ep);
+  return launch_stencil<T, 32, 8, EPT, 4>(ctx, d, nc, Din, ldd, Yacc, ldy, &ep);
 }
 
 // =====================================================================================================
@@ -320,6 +383,7 @@ int spmm_diag(lb2_ctx* ctx, int64_t n, const real_t<T>* d, int nc, const T* X, i
 
 #define LB2_INST(T)                                                                                       \
   template int spmm_stencil<T>(lb2_ctx*, const StencilDesc&, int, const T*, int64_t, T*, int64_t);         \
+  template int spmm_stencil_cheb<T>(lb2_ctx*, const StencilDesc&, int, const T*, int64_t, T*, int64_t, const ChebEpilogue<T>&); \
   template int spmm_csr<T>(lb2_ctx*, int64_t, const int64_t*, const int32_t*, const T*, int, const T*, int64_t, T*, int64_t); \
   template int spmm_diag<T>(lb2_ctx*, int64_t, const real_t<T>*, int, const T*, int64_t, T*, int64_t);
 LB2_INST(float)

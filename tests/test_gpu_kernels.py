@@ -372,15 +372,25 @@ def test_pipelined_host_copy_round_trip_is_exact(ctx):
 # ------------------------------------------------------------------------------------------------ preconditioner
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("degree", [0, 1, 2, 7])
-def test_chebyshev_operator_matches_oracle(ctx, dt, degree):
-    """T = p(A) applied as a block operator (lb2_op_apply on an lb2_op_chebyshev handle) vs the numpy restatement."""
-    g = (9, 8, 7)
-    n = 9 * 8 * 7
+@pytest.mark.parametrize("inner", ["stencil", "stencil+potential", "csr", "stencil-unfused"])
+def test_chebyshev_operator_matches_oracle(ctx, dt, degree, inner, monkeypatch):
+    """T = p(A) applied as a block operator (lb2_op_apply on an lb2_op_chebyshev handle) vs the numpy restatement:
+    the step fused into the stencil kernel's epilogue, and SpMM + update kernel for other inner operators."""
+    g = (10, 8, 7)
+    n = 10 * 8 * 7
     rng = np.random.default_rng(degree)
     X = rand(rng, (n, 5), dt)
-    A = api.stencil_op(g, dt)
-    T = api.chebyshev_op(A, degree, 0.25, 12.0)
+    pot = pr.harmonic_potential(g, 0.4) if inner == "stencil+potential" else None
+    if inner == "csr":
+        monkeypatch.setenv("LB2_CSR_NO_STENCIL_DETECT", "1")
+        rp, c, v = pr.laplacian_csr(g, dtype=api.REAL[api.PREFIX[np.dtype(dt)]])
+        A = api.csr_op(rp, c, v.astype(dt))
+    else:
+        A = api.stencil_op(g, dt, potential=pot)
+    if inner == "stencil-unfused":
+        monkeypatch.setenv("LB2_NO_CHEB_FUSE", "1")
+    T = api.chebyshev_op(A, degree, 0.25, 13.0)
     Y = T.apply(ctx, api.DeviceArray.from_numpy(ctx, X)).numpy(ctx)
-    ref = no.op_chebyshev(no.op_stencil(g, dt), degree, 0.25, 12.0)(X.astype(np.complex128 if np.dtype(dt).kind == "c"
-                                                                            else np.float64))
+    ref = no.op_chebyshev(no.op_stencil(g, dt, potential=pot), degree, 0.25, 13.0)(
+        X.astype(np.complex128 if np.dtype(dt).kind == "c" else np.float64))
     close(Y, ref, 1e-12 if rtol(dt) < 1e-6 else 1e-4)
