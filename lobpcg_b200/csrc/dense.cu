@@ -1011,6 +1011,17 @@ static int launch_nn_zmma(lb2_ctx* ctx, int64_t n, int kd, int nb, c64 alpha, co
   return 0;
 }
 
+// deterministic split reduction (+ Hermitian mirror) for float partials produced outside this file (gram_tc5.cu)
+int gram_reduce_f32(lb2_ctx* ctx, const float* part, int64_t split_stride, int nsplit, int ma, int mb, int mirror,
+                    float* G, int ldg) {
+  const int64_t tot = (int64_t)ma * mb;
+  gram_reduce_kernel<float><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(part, split_stride, nsplit, ma, mb,
+                                                                                   mirror, G, ldg);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // f64 Gram on the tile x equal-split grid (gram_dmma_kernel): every CTA of an n-range runs in the same wave, so the
 // operands come from HBM once and from L2 for every further tile.
 int gram_tiles_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B,
@@ -1063,7 +1074,13 @@ int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const
     if (!ctx->force_simt) return launch_gram_zmma(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
   }
   if constexpr (std::is_same<T, float>::value) {
-    if (!ctx->force_simt) return launch_gram_tf32(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+    if (!ctx->force_simt) {
+      if (ctx->gram_tc5 > 0 && n >= 1024) {   // tcgen05 / TMEM path (gram_tc5.cu); -100 = operands not 16-byte aligned
+        const int rc = gram_tc5_f32(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+        if (rc != -100) return rc;
+      }
+      return launch_gram_tf32(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+    }
   }
   return launch_gram_simt<T>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
 }

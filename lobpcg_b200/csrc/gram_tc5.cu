@@ -1,0 +1,281 @@
+// lobpcg_b200/csrc/gram_tc5.cu — K2/K3 for float on the 5th-generation tensor cores: G = A^H B through
+// tcgen05.mma kind::tf32 with the accumulator in TMEM (SASS: UTCMMA / tensor-memory loads).
+//
+// The algorithm needs fp32-accurate Grams (EPS_TOL = 1e-5 for s/c, reference src/core/lobpcg_s.c:10; SURVEY §7 hard
+// part 2), plain TF32 (10-bit mantissa, and the tensor core TRUNCATES fp32 inputs) is not enough.  So every operand
+// element x is split into hi = rna_tf32(x) and lo = rna_tf32(x - hi) and a product is three MMAs, lo*hi + hi*lo + hi*hi,
+// accumulated in fp32 in TMEM ("3xTF32").  The first version of this path (dense.cu: gram_tf32_kernel) does the same
+// with mma.sync and splits fragments in registers on every use; here the split happens ONCE per staged element.
+//
+// Per CTA: one 128 x 128 output tile and one contiguous row range (same tile x split grid and deterministic split
+// reduction as gram_dmma_kernel).  Per K chunk of 32 rows:
+//   1. cp.async (16-byte, zero-filling) lands the raw fp32 panels A[:, 128 cols] and B[:, 128 cols] directly in the
+//      canonical K-major no-swizzle UMMA layout: 8 x 16-byte core matrices, 128 B each, k-units 128 B apart, column
+//      groups 1 KB apart.  A warp instruction covers 8 columns x 4 k-units: 64 contiguous bytes per column in global
+//      memory (full sectors) and all 8 sixteen-byte bank groups four times in shared memory (no excess wavefronts).
+//   2. every thread converts the units it copied itself (no barrier needed for that): hi overwrites the raw tile,
+//      lo goes to a second tile; fence.proxy.async makes the generic-proxy writes visible to the tensor core.
+//   3. one thread issues 4 k-steps x 3 tcgen05.mma (M = N = 128, K = 8) and a tcgen05.commit on the stage's mbarrier;
+//      the MMAs of chunk c run while the CTA converts chunk c + 1.
+// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction) -> partial tile in global scratch.
+#include <cstdint>
+
+#include "common.cuh"
+#include "context.h"
+#include "kernels.h"
+
+namespace lb2 {
+
+namespace {
+
+constexpr int TC_T = 128;            // tile edge = UMMA M = UMMA N
+constexpr int TC_BK = 32;            // rows (K) per stage
+constexpr int TC_STAGES = 3;
+constexpr int TC_NT = 128;           // 4 warps: each owns 32 TMEM lanes in the epilogue
+constexpr uint32_t TC_LBO = 128;     // bytes between consecutive 16-byte k-units (core matrices along K)
+constexpr uint32_t TC_SBO = (TC_BK / 4) * TC_LBO;          // bytes between 8-column groups (core matrices along M/N)
+constexpr uint32_t TC_TILE = (TC_T / 8) * TC_SBO;          // 16 KB per operand tile
+constexpr uint32_t TC_STAGE = 4 * TC_TILE;                 // A_hi, A_lo, B_hi, B_lo
+constexpr uint32_t TC_SMEM = TC_STAGES * TC_STAGE + 2048;  // + barriers / tmem pointer and 1 KB alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+// bounded wait: a lost arrival traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((TC_LBO >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((TC_SBO >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128 (InstrDescriptor bit fields)
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_T >> 3) << 17) | ((uint32_t)(TC_T >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return r;
+}
+
+__global__ void __launch_bounds__(TC_NT, 1)
+    gram_tc5_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int ma, int mb,
+                    int64_t n, int64_t rows_per_split, int upper, int ntm, float* __restrict__ out,
+                    int64_t split_stride, int ldo) {
+  extern __shared__ __align__(1024) unsigned char smem_tc[];
+  const uint32_t sbase = (smem_u32(smem_tc) + 1023u) & ~1023u;        // tiles 1 KB aligned
+  unsigned char* gbase = smem_tc + (sbase - smem_u32(smem_tc));
+  const uint32_t bar0 = sbase + TC_STAGES * TC_STAGE;                  // TC_STAGES mbarriers, then the TMEM pointer
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + TC_STAGES * TC_STAGE + 64);
+
+  int ti, tj;
+  if (upper) {   // t -> (i <= j)
+    int t = blockIdx.x;
+    tj = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+    while ((tj + 1) * (tj + 2) / 2 <= t) ++tj;
+    while (tj * (tj + 1) / 2 > t) --tj;
+    ti = t - tj * (tj + 1) / 2;
+  } else {
+    ti = blockIdx.x % ntm;
+    tj = blockIdx.x / ntm;
+  }
+  const int m0 = ti * TC_T, c0 = tj * TC_T;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r_end = min(n, r_begin + rows_per_split);
+  const int nchunks = (r_end > r_begin) ? (int)((r_end - r_begin + TC_BK - 1) / TC_BK) : 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; s++) mbar_init(bar0 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "n"(TC_T)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  // this thread's copy/convert units: 8 per operand tile; unit = (column c, k-unit u) -> 16 bytes = 4 rows of one column
+  const int cc = lane & 7, uu = lane >> 3;
+  uint32_t uoff[8];            // byte offset of the unit inside an operand tile
+  int ucol[8], urow[8];        // column inside the panel, first row inside the chunk
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int blk = i * 4 + warp;          // 0..31
+    const int cg = blk & 15, uh = blk >> 4;
+    const int u = uh * 4 + uu;
+    ucol[i] = cg * 8 + cc;
+    urow[i] = u * 4;
+    uoff[i] = (uint32_t)cg * TC_SBO + (uint32_t)u * TC_LBO + (uint32_t)cc * 16u;
+  }
+
+  auto issue_loads = [&](int chunk) {
+    if (chunk < nchunks) {
+      const uint32_t st = sbase + (uint32_t)(chunk % TC_STAGES) * TC_STAGE;
+      const int64_t r0 = r_begin + (int64_t)chunk * TC_BK;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int64_t row = r0 + urow[i];
+        const int64_t left = r_end - row;
+        const int rb = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
+        {
+          const bool ok = (m0 + ucol[i] < ma) && rb > 0;
+          const float* src = ok ? A + (int64_t)(m0 + ucol[i]) * lda + row : A;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(st + uoff[i]), "l"(src), "r"(ok ? rb : 0));
+        }
+        {
+          const bool ok = (c0 + ucol[i] < mb) && rb > 0;
+          const float* src = ok ? B + (int64_t)(c0 + ucol[i]) * ldb + row : B;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(st + 2 * TC_TILE + uoff[i]), "l"(src),
+                       "r"(ok ? rb : 0));
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  issue_loads(0);
+  issue_loads(1);
+
+  for (int chunk = 0; chunk < nchunks; chunk++) {
+    const int s = chunk % TC_STAGES;
+    unsigned char* stg = gbase + (size_t)s * TC_STAGE;
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // my copies of this chunk have landed
+    // hi/lo split of my own units (A tile at 0 / TC_TILE, B tile at 2 / 3 TC_TILE)
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+      for (int op = 0; op < 2; op++) {
+        float4* ph = reinterpret_cast<float4*>(stg + (size_t)op * 2 * TC_TILE + uoff[i]);
+        float4* pl = reinterpret_cast<float4*>(stg + (size_t)op * 2 * TC_TILE + TC_TILE + uoff[i]);
+        const float4 v = *ph;
+        uint4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - __uint_as_float(h.x));
+        l.y = tf32_rna(v.y - __uint_as_float(h.y));
+        l.z = tf32_rna(v.z - __uint_as_float(h.z));
+        l.w = tf32_rna(v.w - __uint_as_float(h.w));
+        *reinterpret_cast<uint4*>(ph) = h;
+        *reinterpret_cast<uint4*>(pl) = l;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t st = sbase + (uint32_t)s * TC_STAGE;
+#pragma unroll
+      for (int ks = 0; ks < TC_BK / 8; ks++) {
+        const uint32_t ko = (uint32_t)ks * 2u * TC_LBO;       // one MMA consumes K = 8 floats = 2 k-units
+        const uint64_t ah = umma_desc(st + ko), al = umma_desc(st + TC_TILE + ko);
+        const uint64_t bh = umma_desc(st + 2 * TC_TILE + ko), bl = umma_desc(st + 3 * TC_TILE + ko);
+        umma_tf32(tmem, al, bh, (chunk > 0 || ks > 0) ? 1u : 0u);
+        umma_tf32(tmem, ah, bl, 1u);
+        umma_tf32(tmem, ah, bh, 1u);
+      }
+      umma_commit(bar0 + 8 * s);   // arrives when every MMA issued so far is complete: stage s may be refilled
+    }
+    // refill the stage of chunk - 1 with chunk + 2 once its MMAs are done
+    if (chunk + 2 < nchunks && chunk >= 1) mbar_wait(bar0 + 8 * ((chunk - 1) % TC_STAGES), (uint32_t)(((chunk - 1) / TC_STAGES) & 1));
+    issue_loads(chunk + 2);
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+
+  float* o = out + (int64_t)blockIdx.y * split_stride;
+  const int row = m0 + warp * 32 + lane;        // G row = column of the A panel = TMEM lane
+  if (nchunks > 0) {
+    mbar_wait(bar0 + 8 * ((nchunks - 1) % TC_STAGES), (uint32_t)(((nchunks - 1) / TC_STAGES) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+    for (int j0 = 0; j0 < TC_T; j0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)j0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      if (row < ma) {
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+          const int col = c0 + j0 + q;
+          if (col < mb) o[row + (int64_t)col * ldo] = __uint_as_float(v[q]);
+        }
+      }
+    }
+  } else if (row < ma) {
+    for (int q = 0; q < TC_T; q++)
+      if (c0 + q < mb) o[row + (int64_t)(c0 + q) * ldo] = 0.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TC_T) : "memory");
+}
+
+}  // namespace
+
+// float Gram through tcgen05 (3xTF32).  Returns -100 when the operands do not meet the 16-byte alignment the
+// cp.async staging needs (the caller then falls back to the mma.sync kernel).
+int gram_tc5_f32(lb2_ctx* ctx, int64_t n, int ma, int mb, const float* A, int64_t lda, const float* B, int64_t ldb,
+                 float* G, int ldg, int upper) {
+  if ((lda % 4) || (ldb % 4) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return -100;
+  const int ntm = (ma + TC_T - 1) / TC_T, ntn = (mb + TC_T - 1) / TC_T;
+  const int ntiles = upper ? ntm * (ntm + 1) / 2 : ntm * ntn;
+  int nsplit = ctx->sm_count / ntiles;
+  if (nsplit < 1) nsplit = 1;
+  const int64_t min_rows = 8 * TC_BK;
+  if ((int64_t)nsplit * min_rows > n) nsplit = (int)((n + min_rows - 1) / min_rows);
+  if (nsplit < 1) nsplit = 1;
+  int64_t rps = (n + nsplit - 1) / nsplit;
+  rps = (rps + TC_BK - 1) / TC_BK * TC_BK;
+  nsplit = (int)((n + rps - 1) / rps);
+  const int64_t split_stride = (int64_t)ma * mb;
+  float* part = (float*)ctx_scratch(ctx, sizeof(float) * split_stride * nsplit);
+  if (!part) return -1;
+  LB2_CUDA_OK(cudaFuncSetAttribute(gram_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  gram_tc5_kernel<<<dim3(ntiles, nsplit), TC_NT, TC_SMEM, ctx->stream>>>(A, lda, B, ldb, ma, mb, n, rps, upper, ntm, part,
+                                                                        split_stride, ma);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return gram_reduce_f32(ctx, part, split_stride, nsplit, ma, mb, upper, G, ldg);
+}
+
+}  // namespace lb2

@@ -23,6 +23,11 @@ int gram_wl_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_
 // dense.cu: f64 Gram on the tile x equal-split grid (first kernel; still used for rectangular products and strips)
 int gram_tiles_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B,
                    int64_t ldb, double* G, int ldg, int upper);
+int gram_reduce_f32(lb2_ctx* ctx, const float* part, int64_t split_stride, int nsplit, int ma, int mb, int mirror,
+                    float* G, int ldg);
+// gram_tc5.cu: float Gram on tcgen05 (kind::tf32, 3xTF32 split, accumulator in TMEM); -100 = alignment not met
+int gram_tc5_f32(lb2_ctx* ctx, int64_t n, int ma, int mb, const float* A, int64_t lda, const float* B, int64_t ldb,
+                 float* G, int ldg, int upper);
 int gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int BK, double* stats);
 
 // ---- elementwise.cu ---------------------------------------------------------------------------------

@@ -149,6 +149,30 @@ def test_gram_simt_and_dmma_paths_agree(ctx):
     close(G2, G1, 1e-13)
 
 
+@pytest.mark.parametrize("shape", [(4096, 128, 128), (5000, 20, 20), (20000, 300, 300), (33333, 129, 70), (8192, 260, 260),
+                                   (7777, 64, 200)])
+def test_gram_float_tcgen05_matches_fp64_reference(ctx, shape):
+    """float Gram on tcgen05 (kind::tf32, 3xTF32 split, accumulator in TMEM; csrc/gram_tc5.cu) vs an fp64 product of the
+    same float inputs: fp32-level accuracy (2e-5 of the largest entry), symmetric and rectangular, ragged tiles."""
+    n, ma, mb = shape
+    rng = np.random.default_rng(n + ma)
+    A = rand(rng, (n, ma), np.float32)
+    B = A if ma == mb else rand(rng, (n, mb), np.float32)
+    dA = api.DeviceArray.from_numpy(ctx, A, ld=(n + 3) // 4 * 4)
+    dB = dA if ma == mb else api.DeviceArray.from_numpy(ctx, B, ld=(n + 3) // 4 * 4)
+    ctx.set_option("gram_tc5", 1)
+    try:
+        G = api.gram(ctx, dA, dB, upper=(ma == mb)).numpy(ctx)
+        G2 = api.gram(ctx, dA, dB, upper=False).numpy(ctx)
+    finally:
+        ctx.set_option("gram_tc5", 0)
+    ref = A.astype(np.float64).T @ B.astype(np.float64)
+    close(G, ref, 2e-5)
+    close(G2, ref, 2e-5)
+    if ma == mb:
+        assert np.array_equal(G, G.T)
+
+
 # ------------------------------------------------------------------------------------------------ tall NN
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("shape", [(1, 1, 1), (130, 5, 3), (4097, 60, 40), (30001, 33, 129), (9000, 300, 70),
