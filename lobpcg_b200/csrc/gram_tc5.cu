@@ -3,7 +3,7 @@
 //
 // The algorithm needs fp32-accurate Grams (EPS_TOL = 1e-5 for s/c, reference src/core/lobpcg_s.c:10; SURVEY §7 hard
 // part 2), plain TF32 (10-bit mantissa, and the tensor core TRUNCATES fp32 inputs) is not enough.  So every operand
-// element x is split into hi = rna_tf32(x) and lo = rna_tf32(x - hi) and a product is three MMAs, lo*hi + hi*lo + hi*hi,
+// element x is split into hi = trunc_tf32(x) and lo = rna_tf32(x - hi) and a product is three MMAs, lo*hi + hi*lo + hi*hi,
 // accumulated in fp32 in TMEM ("3xTF32").  The first version of this path (dense.cu: gram_tf32_kernel) does the same
 // with mma.sync and splits fragments in registers on every use; here the split happens ONCE per staged element.
 //
@@ -13,8 +13,9 @@
 //      canonical K-major no-swizzle UMMA layout: 8 x 16-byte core matrices, 128 B each, k-units 128 B apart, column
 //      groups 1 KB apart.  A warp instruction covers 8 columns x 4 k-units: 64 contiguous bytes per column in global
 //      memory (full sectors) and all 8 sixteen-byte bank groups four times in shared memory (no excess wavefronts).
-//   2. every thread converts the units it copied itself (no barrier needed for that): hi overwrites the raw tile,
-//      lo goes to a second tile; fence.proxy.async makes the generic-proxy writes visible to the tensor core.
+//   2. every thread converts the units it copied itself (no barrier needed for that): the raw tile is the hi operand
+//      (the tensor core reads the upper 19 bits = exact truncation), lo = rna_tf32(x - trunc(x)) goes to a second
+//      tile; fence.proxy.async makes the generic-proxy writes visible to the tensor core.
 //   3. one thread issues 4 k-steps x 3 tcgen05.mma (M = N = 128, K = 8) and a tcgen05.commit on the stage's mbarrier;
 //      the MMAs of chunk c run while the CTA converts chunk c + 1.
 // Epilogue: tcgen05.ld (32 lanes x 32 columns per warp and instruction) -> partial tile in global scratch.
@@ -29,14 +30,19 @@ namespace lb2 {
 namespace {
 
 constexpr int TC_T = 128;            // tile edge = UMMA M = UMMA N
-constexpr int TC_BK = 32;            // rows (K) per stage
-constexpr int TC_STAGES = 3;
-constexpr int TC_NT = 128;           // 4 warps: each owns 32 TMEM lanes in the epilogue
+constexpr int TC_BK = 32;            // rows (K) per chunk
+constexpr int TC_RAW = 5;            // raw (= hi operand) stages: chunk c + 3 is requested while chunk c is converted
+constexpr int TC_LO = 2;             // lo-operand buffers (written by the CTA, read by the MMAs of one chunk)
+constexpr int TC_AHEAD = TC_RAW - 2; // prefetch distance in chunks
+constexpr int TC_FLUSH = 4;          // chunks per TMEM accumulation group (see "accuracy" below)
+constexpr int TC_NT = 256;           // 8 warps: warp w owns TMEM lanes 32 (w % 4) .. and column half w / 4 when draining
+constexpr int TC_UNITS = (TC_T * TC_BK / 4) / TC_NT;   // 16-byte units per thread, operand tile and chunk
 constexpr uint32_t TC_LBO = 128;     // bytes between consecutive 16-byte k-units (core matrices along K)
 constexpr uint32_t TC_SBO = (TC_BK / 4) * TC_LBO;          // bytes between 8-column groups (core matrices along M/N)
 constexpr uint32_t TC_TILE = (TC_T / 8) * TC_SBO;          // 16 KB per operand tile
-constexpr uint32_t TC_STAGE = 4 * TC_TILE;                 // A_hi, A_lo, B_hi, B_lo
-constexpr uint32_t TC_SMEM = TC_STAGES * TC_STAGE + 2048;  // + barriers / tmem pointer and 1 KB alignment slack
+constexpr uint32_t TC_STAGE = 2 * TC_TILE;                 // raw stage: A, B;  lo buffer: A_lo, B_lo
+constexpr uint32_t TC_BAR = (TC_RAW + TC_LO) * TC_STAGE;   // offset of the mbarriers / TMEM pointer
+constexpr uint32_t TC_SMEM = TC_BAR + 2048;                // + barriers and 1 KB alignment slack (226 KB of 227)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -92,8 +98,9 @@ __global__ void __launch_bounds__(TC_NT, 1)
   extern __shared__ __align__(1024) unsigned char smem_tc[];
   const uint32_t sbase = (smem_u32(smem_tc) + 1023u) & ~1023u;        // tiles 1 KB aligned
   unsigned char* gbase = smem_tc + (sbase - smem_u32(smem_tc));
-  const uint32_t bar0 = sbase + TC_STAGES * TC_STAGE;                  // TC_STAGES mbarriers, then the TMEM pointer
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + TC_STAGES * TC_STAGE + 64);
+  const uint32_t lo_base = sbase + TC_RAW * TC_STAGE;                  // lo buffers behind the raw stages
+  const uint32_t bar0 = sbase + TC_BAR;                                // TC_RAW mbarriers, then the TMEM pointer
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + TC_BAR + 64);
 
   int ti, tj;
   if (upper) {   // t -> (i <= j)
@@ -113,12 +120,12 @@ __global__ void __launch_bounds__(TC_NT, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; s++) mbar_init(bar0 + 8 * s, 1);
+    for (int s = 0; s < TC_RAW; s++) mbar_init(bar0 + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 0) {   // two accumulators of 128 columns (ping-pong between accumulation groups)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32((const void*)tmem_slot)),
-                 "n"(TC_T)
+                 "n"(2 * TC_T)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
@@ -127,13 +134,13 @@ __global__ void __launch_bounds__(TC_NT, 1)
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  // this thread's copy/convert units: 8 per operand tile; unit = (column c, k-unit u) -> 16 bytes = 4 rows of one column
+  // this thread's copy/convert units: TC_UNITS per operand tile; unit = (column c, k-unit u) -> 16 bytes = 4 rows of a column
   const int cc = lane & 7, uu = lane >> 3;
-  uint32_t uoff[8];            // byte offset of the unit inside an operand tile
-  int ucol[8], urow[8];        // column inside the panel, first row inside the chunk
+  uint32_t uoff[TC_UNITS];                   // byte offset of the unit inside an operand tile
+  int ucol[TC_UNITS], urow[TC_UNITS];        // column inside the panel, first row inside the chunk
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int blk = i * 4 + warp;          // 0..31
+  for (int i = 0; i < TC_UNITS; i++) {
+    const int blk = i * (TC_NT / 32) + warp;          // 0..31
     const int cg = blk & 15, uh = blk >> 4;
     const int u = uh * 4 + uu;
     ucol[i] = cg * 8 + cc;
@@ -143,10 +150,10 @@ __global__ void __launch_bounds__(TC_NT, 1)
 
   auto issue_loads = [&](int chunk) {
     if (chunk < nchunks) {
-      const uint32_t st = sbase + (uint32_t)(chunk % TC_STAGES) * TC_STAGE;
+      const uint32_t st = sbase + (uint32_t)(chunk % TC_RAW) * TC_STAGE;
       const int64_t r0 = r_begin + (int64_t)chunk * TC_BK;
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
+      for (int i = 0; i < TC_UNITS; i++) {
         const int64_t row = r0 + urow[i];
         const int64_t left = r_end - row;
         const int rb = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(TC_NT, 1)
         {
           const bool ok = (c0 + ucol[i] < mb) && rb > 0;
           const float* src = ok ? B + (int64_t)(c0 + ucol[i]) * ldb + row : B;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(st + 2 * TC_TILE + uoff[i]), "l"(src),
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(st + TC_TILE + uoff[i]), "l"(src),
                        "r"(ok ? rb : 0));
         }
       }
@@ -166,62 +173,20 @@ __global__ void __launch_bounds__(TC_NT, 1)
     asm volatile("cp.async.commit_group;\n" ::);
   };
 
-  issue_loads(0);
-  issue_loads(1);
-
-  for (int chunk = 0; chunk < nchunks; chunk++) {
-    const int s = chunk % TC_STAGES;
-    unsigned char* stg = gbase + (size_t)s * TC_STAGE;
-    asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // my copies of this chunk have landed
-    // hi/lo split of my own units (A tile at 0 / TC_TILE, B tile at 2 / 3 TC_TILE)
+  // Accuracy: the tensor core TRUNCATES when it adds into its fp32 accumulator, a relative bias of ~2^-25 per MMA that
+  // grows linearly with the row count (measured -4.8e-4 on the Gram diagonal at n = 4 M with one long accumulation,
+  // -2.8e-4 for mma.sync).  So TMEM only ever accumulates TC_FLUSH chunks (48 MMAs); finished groups are drained into
+  // fp64 registers (64 entries per thread) while the MMAs of the next group run on the other TMEM accumulator.
+  const int lq = warp & 3, ch = warp >> 2;      // TMEM lane quarter of this warp, column half
+  double accd[TC_T / 2];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-#pragma unroll
-      for (int op = 0; op < 2; op++) {
-        float4* ph = reinterpret_cast<float4*>(stg + (size_t)op * 2 * TC_TILE + uoff[i]);
-        float4* pl = reinterpret_cast<float4*>(stg + (size_t)op * 2 * TC_TILE + TC_TILE + uoff[i]);
-        const float4 v = *ph;
-        uint4 h, l;
-        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-        l.x = tf32_rna(v.x - __uint_as_float(h.x));
-        l.y = tf32_rna(v.y - __uint_as_float(h.y));
-        l.z = tf32_rna(v.z - __uint_as_float(h.z));
-        l.w = tf32_rna(v.w - __uint_as_float(h.w));
-        *reinterpret_cast<uint4*>(ph) = h;
-        *reinterpret_cast<uint4*>(pl) = l;
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> tensor core (async proxy)
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint32_t st = sbase + (uint32_t)s * TC_STAGE;
-#pragma unroll
-      for (int ks = 0; ks < TC_BK / 8; ks++) {
-        const uint32_t ko = (uint32_t)ks * 2u * TC_LBO;       // one MMA consumes K = 8 floats = 2 k-units
-        const uint64_t ah = umma_desc(st + ko), al = umma_desc(st + TC_TILE + ko);
-        const uint64_t bh = umma_desc(st + 2 * TC_TILE + ko), bl = umma_desc(st + 3 * TC_TILE + ko);
-        umma_tf32(tmem, al, bh, (chunk > 0 || ks > 0) ? 1u : 0u);
-        umma_tf32(tmem, ah, bl, 1u);
-        umma_tf32(tmem, ah, bh, 1u);
-      }
-      umma_commit(bar0 + 8 * s);   // arrives when every MMA issued so far is complete: stage s may be refilled
-    }
-    // refill the stage of chunk - 1 with chunk + 2 once its MMAs are done
-    if (chunk + 2 < nchunks && chunk >= 1) mbar_wait(bar0 + 8 * ((chunk - 1) % TC_STAGES), (uint32_t)(((chunk - 1) / TC_STAGES) & 1));
-    issue_loads(chunk + 2);
-  }
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-
-  float* o = out + (int64_t)blockIdx.y * split_stride;
-  const int row = m0 + warp * 32 + lane;        // G row = column of the A panel = TMEM lane
-  if (nchunks > 0) {
-    mbar_wait(bar0 + 8 * ((nchunks - 1) % TC_STAGES), (uint32_t)(((nchunks - 1) / TC_STAGES) & 1));
+  for (int q = 0; q < TC_T / 2; q++) accd[q] = 0.0;
+  auto drain = [&](int group) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-#pragma unroll 1
-    for (int j0 = 0; j0 < TC_T; j0 += 32) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
       uint32_t v[32];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)j0;
+      const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)((group & 1) * TC_T + ch * (TC_T / 2) + h * 32);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -233,21 +198,92 @@ __global__ void __launch_bounds__(TC_NT, 1)
           : "r"(taddr)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-      if (row < ma) {
 #pragma unroll
-        for (int q = 0; q < 32; q++) {
-          const int col = c0 + j0 + q;
-          if (col < mb) o[row + (int64_t)col * ldo] = __uint_as_float(v[q]);
-        }
+      for (int q = 0; q < 32; q++) accd[h * 32 + q] += (double)__uint_as_float(v[q]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  };
+  auto done_bar = [&](int chunk) { return bar0 + 8u * (uint32_t)(chunk % TC_RAW); };
+  auto done_par = [&](int chunk) { return (uint32_t)((chunk / TC_RAW) & 1); };
+
+#pragma unroll
+  for (int c = 0; c < TC_AHEAD; c++) issue_loads(c);
+
+  int drained = 0;   // groups [0, drained) are in accd
+  for (int chunk = 0; chunk < nchunks; chunk++) {
+    const unsigned char* raw = gbase + (size_t)(chunk % TC_RAW) * TC_STAGE;
+    unsigned char* lob = gbase + (size_t)TC_RAW * TC_STAGE + (size_t)(chunk & 1) * TC_STAGE;
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(TC_AHEAD - 1) : "memory");   // my copies of this chunk have landed
+    if (chunk >= 2) {
+      // MMAs of chunk - 2 are complete: its lo buffer (this chunk's) and its raw stage (chunk + TC_AHEAD's) are free
+      mbar_wait(done_bar(chunk - 2), done_par(chunk - 2));
+      const int gdone = (chunk - 1) / TC_FLUSH;        // groups whose last chunk is <= chunk - 2
+      if (drained < gdone) { drain(drained); drained++; }
+    }
+    issue_loads(chunk + TC_AHEAD);
+    // lo part of my own units.  The raw fp32 tile itself is the "hi" operand: the tensor core reads the upper 19 bits,
+    // i.e. hi = trunc_tf32(x) exactly; lo = rna_tf32(x - hi) is exact in fp32 before rounding, so x = hi + lo to
+    // 2^-22 |x| and the dropped lo*lo term is < 2^-20 of the product.
+    float4 rv[2 * TC_UNITS];
+#pragma unroll
+    for (int i = 0; i < TC_UNITS; i++) {
+      rv[2 * i] = *reinterpret_cast<const float4*>(raw + uoff[i]);
+      rv[2 * i + 1] = *reinterpret_cast<const float4*>(raw + TC_TILE + uoff[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < TC_UNITS; i++) {
+#pragma unroll
+      for (int op = 0; op < 2; op++) {
+        const float4 v = rv[2 * i + op];
+        uint4 l;
+        l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+        l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+        l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+        l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+        *reinterpret_cast<uint4*>(lob + (size_t)op * TC_TILE + uoff[i]) = l;
       }
     }
-  } else if (row < ma) {
-    for (int q = 0; q < TC_T; q++)
-      if (c0 + q < mb) o[row + (int64_t)(c0 + q) * ldo] = 0.f;
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t hi = sbase + (uint32_t)(chunk % TC_RAW) * TC_STAGE;
+      const uint32_t lo = lo_base + (uint32_t)(chunk & 1) * TC_STAGE;
+      const int group = chunk / TC_FLUSH;
+      const uint32_t acc = tmem + (uint32_t)((group & 1) * TC_T);
+#pragma unroll
+      for (int ks = 0; ks < TC_BK / 8; ks++) {
+        const uint32_t ko = (uint32_t)ks * 2u * TC_LBO;       // one MMA consumes K = 8 floats = 2 k-units
+        const uint64_t ah = umma_desc(hi + ko), al = umma_desc(lo + ko);
+        const uint64_t bh = umma_desc(hi + TC_TILE + ko), bl = umma_desc(lo + TC_TILE + ko);
+        umma_tf32(acc, al, bh, (chunk % TC_FLUSH != 0 || ks > 0) ? 1u : 0u);
+        umma_tf32(acc, ah, bl, 1u);
+        umma_tf32(acc, ah, bh, 1u);
+      }
+      umma_commit(done_bar(chunk));   // arrives when every MMA issued so far is complete
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+
+  if (nchunks > 0) {
+    if (nchunks >= 2) mbar_wait(done_bar(nchunks - 2), done_par(nchunks - 2));
+    mbar_wait(done_bar(nchunks - 1), done_par(nchunks - 1));
+    const int ngroups = (nchunks + TC_FLUSH - 1) / TC_FLUSH;
+    for (; drained < ngroups; drained++) drain(drained);
+  }
+  float* o = out + (int64_t)blockIdx.y * split_stride;
+  const int row = m0 + lq * 32 + lane;          // G row = column of the A panel = TMEM lane
+  if (row < ma) {
+#pragma unroll
+    for (int q = 0; q < TC_T / 2; q++) {
+      const int col = c0 + ch * (TC_T / 2) + q;
+      if (col < mb) o[row + (int64_t)col * ldo] = (float)accd[q];
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TC_T) : "memory");
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(2 * TC_T) : "memory");
 }
 
 }  // namespace
