@@ -35,7 +35,7 @@ struct lb2_ctx {
   int gram_load_pct = 0; // work-list Gram: staging-traffic cost of a tile with 256 columns in % of its DMMA time (0 = default)
   void* hostcopy = nullptr;        // lb2::HostCopyState* (pinned ring for pageable host <-> device block transfers)
   void* gram_wl_cache = nullptr;   // lb2::WlCache* (schedules per Gram shape)
-  int gram_tc5 = 0;      // float Gram through tcgen05 / TMEM (gram_tc5.cu): 0 = off, 1 = on
+  int gram_tc5 = -1;     // float Gram through tcgen05 / TMEM (gram_tc5.cu): -1 = auto (on), 0 = off, 1 = on
   int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
   int spmm_cols = 0;     // CSR SpMM columns per thread (0 = heuristic)
   // launch counter (bench.py "gpu_launches")

@@ -1075,7 +1075,7 @@ int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const
   }
   if constexpr (std::is_same<T, float>::value) {
     if (!ctx->force_simt) {
-      if (ctx->gram_tc5 > 0 && n >= 1024) {   // tcgen05 / TMEM path (gram_tc5.cu); -100 = operands not 16-byte aligned
+      if (ctx->gram_tc5 != 0 && n >= 1024) {   // tcgen05 / TMEM path (gram_tc5.cu); -100 = operands not 16-byte aligned
         const int rc = gram_tc5_f32(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
         if (rc != -100) return rc;
       }
