@@ -417,13 +417,13 @@ __global__ void __launch_bounds__(WM* WN * 32)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp % WM, wn = warp / WM;
   const int g = lane >> 2, t = lane & 3;
-  float acc[MB][NB][4];
+  float acc[MB][NB][4], accs[MB][NB][4];
 #pragma unroll
   for (int i = 0; i < MB; i++)
 #pragma unroll
     for (int j = 0; j < NB; j++)
 #pragma unroll
-      for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
+      for (int q = 0; q < 4; q++) acc[i][j][q] = accs[i][j][q] = 0.f;
   auto issue = [&](int chunk) {
     if (chunk < nchunks) {
       const int s = chunk % STAGES;
@@ -467,6 +467,18 @@ __global__ void __launch_bounds__(WM* WN * 32)
           mma_tf32_1688(acc[i][j], ah[i], bh[j]);
         }
     }
+    // the tensor core truncates when it adds into its fp32 accumulator (a bias of ~2^-25 per MMA that grows with the
+    // length of the sum, tools/f32_gram_accuracy.py): keep the hardware accumulation to one chunk and do the long sum
+    // with round-to-nearest adds
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+      for (int j = 0; j < NB; j++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          accs[i][j][q] += acc[i][j][q];
+          acc[i][j][q] = 0.f;
+        }
   }
   cp_async_wait<0>();
   float* o = out + (int64_t)blockIdx.y * split_stride;
@@ -478,7 +490,7 @@ __global__ void __launch_bounds__(WM* WN * 32)
       for (int q = 0; q < 4; q++) {
         const int row = m0 + wm * MB * 16 + i * 16 + g + ((q & 2) ? 8 : 0);
         const int col = c0 + wn * NB * 8 + j * 8 + 2 * t + (q & 1);
-        if (row < ma && col < mb) o[row + (int64_t)col * ldo] = acc[i][j][q];
+        if (row < ma && col < mb) o[row + (int64_t)col * ldo] = accs[i][j][q];
       }
 }
 
@@ -503,13 +515,13 @@ __global__ void __launch_bounds__(WM* WN * 32)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp % WM, wn = warp / WM;
   const int g = lane >> 2, t = lane & 3;
-  float acc[MB][NB][4];
+  float acc[MB][NB][4], accs[MB][NB][4];
 #pragma unroll
   for (int i = 0; i < MB; i++)
 #pragma unroll
     for (int j = 0; j < NB; j++)
 #pragma unroll
-      for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
+      for (int q = 0; q < 4; q++) acc[i][j][q] = accs[i][j][q] = 0.f;
   auto issue = [&](int chunk) {
     if (chunk < nchunks) {
       const int s = chunk % STAGES;
@@ -553,6 +565,18 @@ __global__ void __launch_bounds__(WM* WN * 32)
           mma_tf32_1688(acc[i][j], ah[i], bh[j]);
         }
     }
+    // the tensor core truncates when it adds into its fp32 accumulator (a bias of ~2^-25 per MMA that grows with the
+    // length of the sum, tools/f32_gram_accuracy.py): keep the hardware accumulation to one chunk and do the long sum
+    // with round-to-nearest adds
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+      for (int j = 0; j < NB; j++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          accs[i][j][q] += acc[i][j][q];
+          acc[i][j][q] = 0.f;
+        }
   }
   cp_async_wait<0>();
 #pragma unroll
@@ -565,7 +589,7 @@ __global__ void __launch_bounds__(WM* WN * 32)
         const int col = c0 + wn * NB * 8 + j * 8 + 2 * t + (q & 1);
         if (row < n && col < nb) {
           float* p = Out + row + (int64_t)col * ldo;
-          float v = alpha * acc[i][j][q];
+          float v = alpha * accs[i][j][q];
           if (beta != 0.f) v += beta * (*p);
           *p = v;
         }

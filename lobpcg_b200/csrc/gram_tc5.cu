@@ -42,7 +42,7 @@ constexpr int TC_BK = 32;            // rows (K) per chunk
 constexpr int TC_RAW = 5;            // raw (= hi operand) stages: chunk c + 3 is requested while chunk c is converted
 constexpr int TC_LO = 2;             // lo-operand buffers (written by the CTA, read by the MMAs of one chunk)
 constexpr int TC_AHEAD = TC_RAW - 2; // prefetch distance in chunks
-constexpr int TC_FLUSH = 4;          // chunks per TMEM accumulation group (see "accuracy" below)
+constexpr int TC_FLUSH = 2;          // chunks per TMEM accumulation group (see "accuracy" below)
 constexpr int TC_NT = 256;           // 8 warps: warp w owns TMEM lanes 32 (w % 4) .. and column half w / 4 when draining
 constexpr int TC_UNITS = (TC_T * TC_BK / 4) / TC_NT;   // 16-byte units per thread, operand tile and chunk
 constexpr uint32_t TC_LBO = 128;     // bytes between consecutive 16-byte k-units (core matrices along K)
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TC_NT, 1)
 
   // Accuracy: the tensor core TRUNCATES when it adds into its fp32 accumulator, a relative bias of ~2^-25 per MMA that
   // grows linearly with the row count (measured -4.8e-4 on the Gram diagonal at n = 4 M with one long accumulation,
-  // -2.8e-4 for mma.sync).  So TMEM only ever accumulates TC_FLUSH chunks (48 MMAs); finished groups are drained into
+  // -2.8e-4 for mma.sync).  So TMEM only ever accumulates TC_FLUSH chunks (24 MMAs); finished groups are drained into
   // fp64 registers (64 entries per thread) while the MMAs of the next group run on the other TMEM accumulator.
   const int lq = warp & 3, ch = warp >> 2;      // TMEM lane quarter of this warp, column half
   double accd[TC_T / 2];
