@@ -62,6 +62,11 @@ void *lb2_op_diag(char prefix, int64_t n, const void *diag_host);
 /* BdG-style pencil block A = [[K+shift, d],[conj d, K+shift]] with K the stencil above (config C4) */
 void *lb2_op_bdg(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, double coff, double shift,
                  double d_re, double d_im);
+/* CSR with int32 row pointers; Matrix Market coordinate file -> CSR operator (symmetric / hermitian storage expanded) */
+void *lb2_op_csr32(char prefix, int64_t n, const int32_t *rowptr_host, const int32_t *col_host, const void *val_host);
+void *lb2_op_csr_from_mtx(char prefix, const char *path);
+/* dense n x n operator (column-major host matrix of the operator's scalar type, uploaded once; block apply = library GEMM) */
+void *lb2_op_dense(char prefix, int64_t n, const void *A_host);
 /* Built-in preconditioner for alg->T (the reference only plans built-ins, README.md:15): T = p(A), `degree`
  * steps of the Chebyshev iteration for A y = x on the spectrum window [lo, hi], i.e. `degree` block applies of A per
  * block apply of T.  hi <= 0: Gershgorin bound of the built-in inner operator; lo <= 0: hi / 50.  The inner operator
@@ -84,6 +89,10 @@ int lb2_solver_finish(lb2_solver *s);
 void lb2_solver_destroy(lb2_solver *s);
 /* X0 generated on the device from the portable counter-based generator instead of uploading alg->S */
 int lb2_solver_set_device_x0(lb2_solver *s, uint64_t seed);
+/* device-pointer fast path: X0 is read from x0_dev and/or the eigenvectors are written to x_out_dev (device blocks of this
+ * rank's rows, n_local x sizeSub, column-major, ld = n_local) instead of the host buffer alg->S; NULL keeps the host path.
+ * eigVals / resNorm / converged / iter are still returned through the state struct. */
+int lb2_solver_set_device_io(lb2_solver *s, const void *x0_dev, void *x_out_dev);
 /* statistics: per-phase device milliseconds accumulated by step(); names via lb2_solver_stat_name */
 int lb2_solver_num_stats(void);
 const char *lb2_solver_stat_name(int i);

@@ -72,6 +72,12 @@ def _declare(L):
     L.lb2_op_diag.argtypes = [C.c_char, i64, vp]
     L.lb2_op_bdg.restype = vp
     L.lb2_op_bdg.argtypes = [C.c_char, i64, i64, i64, dbl, dbl, dbl, dbl, dbl]
+    L.lb2_op_csr32.restype = vp
+    L.lb2_op_csr32.argtypes = [C.c_char, i64, vp, vp, vp]
+    L.lb2_op_csr_from_mtx.restype = vp
+    L.lb2_op_csr_from_mtx.argtypes = [C.c_char, C.c_char_p]
+    L.lb2_op_dense.restype = vp
+    L.lb2_op_dense.argtypes = [C.c_char, i64, vp]
     L.lb2_op_chebyshev.restype = vp
     L.lb2_op_chebyshev.argtypes = [C.c_char, vp, ci, dbl, dbl]
     L.lb2_op_destroy.argtypes = [vp]
@@ -88,6 +94,7 @@ def _declare(L):
     L.lb2_op_stencil_slab.argtypes = [C.c_char, i64, i64, i64, i64, i64, dbl, dbl, vp]
     L.lb2_solver_destroy.argtypes = [vp]
     L.lb2_solver_set_device_x0.argtypes = [vp, u64]
+    L.lb2_solver_set_device_io.argtypes = [vp, vp, vp]
     L.lb2_solver_stat_name.restype = C.c_char_p
     L.lb2_solver_stat_name.argtypes = [ci]
     L.lb2_solver_stat.restype = dbl
@@ -362,6 +369,23 @@ def bdg_op(grid, dtype, shift, d, cdiag=None, coff=-1.0) -> LinOp:
                  2 * g[0] * g[1] * g[2])
 
 
+def mtx_op(path, dtype) -> LinOp:
+    """CSR operator read from a Matrix Market coordinate file (lb2_op_csr_from_mtx)."""
+    p = PREFIX[np.dtype(dtype)]
+    h = lib().lb2_op_csr_from_mtx(p.encode(), str(path).encode())
+    if not h:
+        raise LobpcgB200Error(f"cannot read {path}")
+    op = LinOpStruct.from_address(h)
+    return LinOp(h, p, int(op.rows))
+
+
+def dense_op(A) -> LinOp:
+    """Device-resident dense operator (lb2_op_dense): A is an n x n numpy matrix."""
+    A = np.asfortranarray(A)
+    p = PREFIX[A.dtype]
+    return LinOp(lib().lb2_op_dense(p.encode(), A.shape[0], A.ctypes.data), p, A.shape[0])
+
+
 def chebyshev_op(A: LinOp, degree: int, lo: float = 0.0, hi: float = 0.0) -> LinOp:
     """Built-in preconditioner T = p(A) (lb2_op_chebyshev): `degree` Chebyshev steps for A y = x on [lo, hi]."""
     h = lib().lb2_op_chebyshev(A.prefix.encode(), A.handle, int(degree), float(lo), float(hi))
@@ -487,6 +511,12 @@ class Solver:
             raise LobpcgB200Error("lb2_solver_create failed")
         if device_seed is not None:
             lib().lb2_solver_set_device_x0(self.h, int(device_seed))
+
+    def set_device_io(self, x0: "DeviceArray | None" = None, x_out: "DeviceArray | None" = None):
+        """Device-pointer fast path: read X0 from / write the eigenvectors to device blocks (no host copies)."""
+        self._dev_io = (x0, x_out)
+        _ck(lib().lb2_solver_set_device_io(self.h, x0.ptr if x0 is not None else None,
+                                           x_out.ptr if x_out is not None else None), "lb2_solver_set_device_io")
 
     def prepare(self):
         _ck(lib().lb2_solver_prepare(self.h), "lb2_solver_prepare")

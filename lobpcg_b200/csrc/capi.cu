@@ -235,6 +235,7 @@ static void builtin_cleanup(LinOpCtxRaw* ctx) {
     if (b->col) cudaFree(b->col);
     if (b->val) cudaFree(b->val);
     if (b->diag) cudaFree(b->diag);
+    if (b->dense) cudaFree(b->dense);
     b->magic = 0;
     free(b);
   }
@@ -418,6 +419,107 @@ void* lb2_op_diag(char prefix, int64_t n, const void* diag_host) {
   return wrap_builtin(b);
 }
 
+// CSR with 32-bit row pointers (the other common host layout)
+void* lb2_op_csr32(char prefix, int64_t n, const int32_t* rowptr_host, const int32_t* col_host, const void* val_host) {
+  if (n < 1 || !rowptr_host) return nullptr;
+  std::vector<int64_t> rp((size_t)n + 1);
+  for (int64_t i = 0; i <= n; i++) rp[(size_t)i] = rowptr_host[i];
+  return lb2_op_csr(prefix, n, rp.data(), col_host, val_host);
+}
+
+// Matrix Market reader (coordinate format; real / integer / complex; general / symmetric / hermitian / skew-symmetric):
+// builds a CSR operator of the requested scalar type with ascending column indices, duplicate entries summed.
+void* lb2_op_csr_from_mtx(char prefix, const char* path) {
+  if (!valid_prefix(prefix) || !path) return nullptr;
+  FILE* f = fopen(path, "r");
+  if (!f) { fprintf(stderr, "lobpcg_b200: cannot open %s\n", path); return nullptr; }
+  char line[1024];
+  if (!fgets(line, sizeof line, f)) { fclose(f); return nullptr; }
+  char obj[64], fmt[64], field[64], sym[64];
+  if (sscanf(line, "%%%%MatrixMarket %63s %63s %63s %63s", obj, fmt, field, sym) != 4 || strcmp(obj, "matrix") ||
+      strcmp(fmt, "coordinate")) {
+    fprintf(stderr, "lobpcg_b200: %s is not a MatrixMarket coordinate matrix\n", path);
+    fclose(f);
+    return nullptr;
+  }
+  const bool cplx = !strcmp(field, "complex"), pattern = !strcmp(field, "pattern");
+  const bool symm = !strcmp(sym, "symmetric"), herm = !strcmp(sym, "hermitian"), skew = !strcmp(sym, "skew-symmetric");
+  do { if (!fgets(line, sizeof line, f)) { fclose(f); return nullptr; } } while (line[0] == '%');
+  long long nr = 0, ncl = 0, nz = 0;
+  if (sscanf(line, "%lld %lld %lld", &nr, &ncl, &nz) != 3 || nr != ncl || nr < 1 || nr > INT32_MAX) {
+    fprintf(stderr, "lobpcg_b200: %s: need a square matrix\n", path);
+    fclose(f);
+    return nullptr;
+  }
+  struct Ent { int32_t r, c; double re, im; };
+  std::vector<Ent> e;
+  e.reserve((size_t)nz * ((symm || herm || skew) ? 2 : 1));
+  for (long long q = 0; q < nz; q++) {
+    long long i, j;
+    double re = 1.0, im = 0.0;
+    if (!fgets(line, sizeof line, f)) { fclose(f); return nullptr; }
+    const int got = pattern ? sscanf(line, "%lld %lld", &i, &j)
+                            : (cplx ? sscanf(line, "%lld %lld %lf %lf", &i, &j, &re, &im) : sscanf(line, "%lld %lld %lf", &i, &j, &re));
+    if (got < (pattern ? 2 : (cplx ? 4 : 3)) || i < 1 || j < 1 || i > nr || j > nr) { fclose(f); return nullptr; }
+    e.push_back({(int32_t)(i - 1), (int32_t)(j - 1), re, im});
+    if (i != j) {
+      if (symm) e.push_back({(int32_t)(j - 1), (int32_t)(i - 1), re, im});
+      else if (herm) e.push_back({(int32_t)(j - 1), (int32_t)(i - 1), re, -im});
+      else if (skew) e.push_back({(int32_t)(j - 1), (int32_t)(i - 1), -re, -im});
+    }
+  }
+  fclose(f);
+  std::sort(e.begin(), e.end(), [](const Ent& a, const Ent& b) { return a.r != b.r ? a.r < b.r : a.c < b.c; });
+  std::vector<int64_t> rp((size_t)nr + 1, 0);
+  std::vector<int32_t> col;
+  std::vector<double> vre, vim;
+  for (size_t q = 0; q < e.size(); q++) {
+    if (q > 0 && e[q].r == e[q - 1].r && e[q].c == e[q - 1].c) { vre.back() += e[q].re; vim.back() += e[q].im; continue; }
+    col.push_back(e[q].c); vre.push_back(e[q].re); vim.push_back(e[q].im);
+    rp[(size_t)e[q].r + 1]++;
+  }
+  for (long long i = 0; i < nr; i++) rp[(size_t)i + 1] += rp[(size_t)i];
+  const size_t nnz = col.size();
+  std::vector<char> val(scalar_size(prefix) * nnz);
+  for (size_t q = 0; q < nnz; q++) {
+    switch (prefix) {
+      case 's': ((float*)val.data())[q] = (float)vre[q]; break;
+      case 'd': ((double*)val.data())[q] = vre[q]; break;
+      case 'c': ((float*)val.data())[2 * q] = (float)vre[q]; ((float*)val.data())[2 * q + 1] = (float)vim[q]; break;
+      default: ((double*)val.data())[2 * q] = vre[q]; ((double*)val.data())[2 * q + 1] = vim[q]; break;
+    }
+  }
+  return lb2_op_csr(prefix, nr, rp.data(), col.data(), val.data());
+}
+
+// Dense operator: A is n x n, column-major, leading dimension n, of the operator's scalar type; applied
+// to whole blocks by a library GEMM.  The reference's dense examples are host callbacks (tests/test_lobpcg.c:29-42),
+// which keep working through the staged path; this constructor is the device-resident version.
+void* lb2_op_dense(char prefix, int64_t n, const void* A_host) {
+  if (!valid_prefix(prefix) || n < 1 || n > 46340 || !A_host) return nullptr;
+  if (!lb2_default_ctx()) return nullptr;
+  BuiltinOp* b = new_builtin(OP_DENSE, prefix, n);
+  b->dense = upload(A_host, scalar_size(prefix) * (size_t)n * (size_t)n);
+  if (!b->dense) { free(b); return nullptr; }
+  double hi = 0;   // Gershgorin bound from the absolute row sums
+  std::vector<double> rs((size_t)n, 0.0);
+  for (int64_t j = 0; j < n; j++)
+    for (int64_t i = 0; i < n; i++) {
+      const size_t p = (size_t)i + (size_t)j * (size_t)n;
+      double v;
+      switch (prefix) {
+        case 's': v = std::fabs((double)((const float*)A_host)[p]); break;
+        case 'd': v = std::fabs(((const double*)A_host)[p]); break;
+        case 'c': v = std::hypot((double)((const float*)A_host)[2 * p], (double)((const float*)A_host)[2 * p + 1]); break;
+        default: v = std::hypot(((const double*)A_host)[2 * p], ((const double*)A_host)[2 * p + 1]); break;
+      }
+      rs[(size_t)i] += v;
+    }
+  for (double v : rs) hi = std::max(hi, v);
+  b->spec_hi = hi;
+  return wrap_builtin(b);
+}
+
 void lb2_op_destroy(void* linop) {
   LinOpRaw* op = (LinOpRaw*)linop;
   if (!op) return;
@@ -478,6 +580,12 @@ int lb2_solver_set_device_x0(lb2_solver* s, uint64_t seed) {
   if (!s) return -1;
   s->impl->use_device_x0 = true;
   s->impl->device_seed = seed;
+  return 0;
+}
+int lb2_solver_set_device_io(lb2_solver* s, const void* x0_dev, void* x_out_dev) {
+  if (!s) return -1;
+  s->impl->dev_x0 = x0_dev;
+  s->impl->dev_xout = x_out_dev;
   return 0;
 }
 int lb2_solver_num_stats(void) { return PH_COUNT; }

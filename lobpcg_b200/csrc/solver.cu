@@ -80,6 +80,9 @@ int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t 
       return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy);
     case OP_DIAG:
       return spmm_diag<T>(ctx, b->n, (const real_t<T>*)b->diag, nc, X, ldx, Y, ldy);
+    case OP_DENSE:   // plain library GEMM (cuBLAS): Y = A X with A dense n x n
+      if (b->n > INT32_MAX || ldx > INT32_MAX || ldy > INT32_MAX) return -2;
+      return sd_gemm<T>(ctx, 'N', (int)b->n, nc, (int)b->n, (const T*)b->dense, (int)b->n, X, (int)ldx, Y, (int)ldy);
     case OP_CHEB: {   // stand-alone apply (outside a solver): temporary workspace
       const BuiltinOp* in = builtin_of(b->inner);
       if (!in) {
@@ -398,6 +401,7 @@ int Solver<T>::apply(const LinOpRaw* op, int nc, const T* X, T* Y) {
     double bytes = 2.0 * (double)n * nc * sizeof(T);
     if (b->kind == OP_CSR || b->from_csr) bytes += (double)b->nnz * (sizeof(T) + 4) + 8.0 * (double)(b->n + 1);
     if (b->kind == OP_DIAG) bytes += (double)n * sizeof(R);
+    if (b->kind == OP_DENSE) bytes += (double)n * (double)n * sizeof(T);
     phase_work[PH_SPMM] += bytes;
     phase_calls[PH_SPMM]++;
     return rc;
@@ -945,6 +949,8 @@ int Solver<T>::init() {
   T* X = Xp();
   if (use_device_x0) {
     LB2_TRY(fill_uniform<T>(ctx, n, k, X, n, device_seed, ng, row0));
+  } else if (dev_x0) {
+    LB2_CUDA_OK(cudaMemcpyAsync(X, dev_x0, sizeof(T) * (size_t)n * k, cudaMemcpyDeviceToDevice, ctx->stream));
   } else if (n == ng) {   // whole columns: one contiguous block, pipelined through pinned chunks (hostcopy.cu)
     LB2_TRY(host_copy(ctx, X, alg->S, sizeof(T) * (size_t)n * k, true));
   } else {
@@ -1062,7 +1068,9 @@ template <typename T>
 int Solver<T>::finish() {
   if (!inited) return 1;
   T* X = Xp();
-  if (n == ng) {
+  if (dev_xout) {
+    LB2_CUDA_OK(cudaMemcpyAsync(dev_xout, X, sizeof(T) * (size_t)n * k, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else if (n == ng) {
     LB2_TRY(host_copy(ctx, alg->S, X, sizeof(T) * (size_t)n * k, false));
   } else {
     LB2_CUDA_OK(cudaMemcpy2DAsync(alg->S + row0, sizeof(T) * ng, X, sizeof(T) * n, sizeof(T) * n, k,

@@ -52,7 +52,7 @@ struct State {  // == <p>_lobpcg_t (reference lobpcg.h:13-55)
 
 // ---- built-in operators (tag lives at the head of ctx->data) -------------------------------------------
 constexpr uint64_t kOpMagic = 0x4C42324F50455221ULL;  // "LB2OPER!"
-enum OpKind { OP_STENCIL = 0, OP_CSR = 1, OP_DIAG = 2, OP_BDG = 3, OP_CHEB = 4 };
+enum OpKind { OP_STENCIL = 0, OP_CSR = 1, OP_DIAG = 2, OP_BDG = 3, OP_CHEB = 4, OP_DENSE = 5 };
 
 struct BuiltinOp {
   uint64_t magic;
@@ -77,6 +77,8 @@ struct BuiltinOp {
   int from_csr;     // stencil operator recognised from CSR input (capi.cu: detect_stencil)
   // diag
   void* diag;
+  // dense n x n matrix (column-major, leading dimension n), device
+  void* dense;
   // upper bound of the spectrum (Gershgorin), computed on the host at construction; 0 = unknown
   double spec_hi;
   // chebyshev preconditioner T = p(A): `degree` applications of `inner` per block apply, spectrum window [lo, hi]
@@ -119,6 +121,10 @@ struct SolverBase {
   uint64_t phase_calls[PH_COUNT] = {0};
   uint64_t device_seed = 0;
   bool use_device_x0 = false;
+  // device-pointer fast path: X0 is read from / the eigenvectors are written to DEVICE blocks of this rank's
+  // rows (n_local x sizeSub, column-major, leading dimension n_local) instead of alg->S
+  const void* dev_x0 = nullptr;
+  void* dev_xout = nullptr;
 };
 
 SolverBase* make_solver(lb2_ctx* ctx, char prefix, void* alg, int indefinite);

@@ -162,6 +162,78 @@ def test_dense_host_callback_operator_known_eigenvalues(name):
     assert np.allclose(r["eig"][:nev], k["eig"][:nev], atol=1e-8)
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32])
+def test_builtin_dense_operator(ctx, dt):
+    """lb2_op_dense: the reference's hard-coded dense spectra (tests/test_lobpcg.c:105-114) and a random Hermitian
+    positive definite matrix against numpy.linalg.eigvalsh; block apply against A @ X."""
+    if np.dtype(dt) == np.float64:
+        for name, nev in (("lobpcg_dense_4x4", 1), ("lobpcg_dense_6x6", 2)):
+            k = KA[name]
+            n = int(round(len(k["A"]) ** 0.5))
+            A = np.array(k["A"], dtype=np.float64).reshape(n, n, order="F")
+            r = api.lobpcg(api.dense_op(A), pr.initial_block(n, nev, 3), nev, 1e-10, 500)
+            assert r["converged"] == nev and np.allclose(r["eig"][:nev], k["eig"][:nev], atol=1e-8)
+    rng = np.random.default_rng(12)
+    n = 400
+    M = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if np.dtype(dt).kind == "c" else 0)
+    A = (M @ M.conj().T / n + np.diag(np.linspace(0.1, 5.0, n))).astype(dt)
+    op = api.dense_op(A)
+    X = rng.standard_normal((n, 7)).astype(dt)
+    Y = op.apply(ctx, api.DeviceArray.from_numpy(ctx, np.asfortranarray(X))).numpy(ctx)
+    tol = 1e-12 if np.dtype(dt).itemsize >= 8 and np.dtype(dt) != np.complex64 else 1e-4
+    assert np.abs(Y - A @ X).max() / np.abs(A @ X).max() < (tol if np.dtype(dt) != np.float32 else 1e-4)
+    single = np.dtype(dt) == np.float32
+    r = api.lobpcg(op, pr.initial_block(n, 12, 5, dt), 5, 1e-4 if single else 1e-9, 3000)
+    w = np.linalg.eigvalsh(A.astype(np.complex128 if np.dtype(dt).kind == "c" else np.float64))[:5]
+    assert r["converged"] == 5
+    assert relerr(r["eig"][:5], w) < (1e-3 if single else 1e-9)
+
+
+def test_matrix_market_ingest(ctx, tmp_path):
+    """lb2_op_csr_from_mtx: symmetric coordinate file (lower triangle stored) -> CSR operator; apply and solve."""
+    import scipy.io
+    import scipy.sparse as sp
+    g = (9, 8, 7)
+    rp, c, v = pr.laplacian_csr(g, potential=pr.harmonic_potential(g, 0.5))
+    n = len(rp) - 1
+    M = sp.csr_matrix((v, c, rp), shape=(n, n))
+    path = tmp_path / "lap.mtx"
+    scipy.io.mmwrite(str(path), sp.tril(M), symmetry="symmetric")
+    op = api.mtx_op(path, np.float64)
+    X = np.asfortranarray(np.random.default_rng(2).standard_normal((n, 4)))
+    Y = op.apply(ctx, api.DeviceArray.from_numpy(ctx, X)).numpy(ctx)
+    assert np.abs(Y - M @ X).max() < 1e-12
+    r = api.lobpcg(op, pr.initial_block(n, 8, 7), 4, 1e-9, 3000)
+    w = np.linalg.eigvalsh(M.toarray())[:4]
+    assert r["converged"] == 4 and relerr(r["eig"][:4], w) < 1e-9
+    rp32 = np.ascontiguousarray(rp, dtype=np.int32)
+    h = api.lib().lb2_op_csr32(b"d", n, rp32.ctypes.data, np.ascontiguousarray(c, np.int32).ctypes.data,
+                               np.ascontiguousarray(v).ctypes.data)
+    op32 = api.LinOp(h, "d", n)
+    assert np.abs(op32.apply(ctx, api.DeviceArray.from_numpy(ctx, X)).numpy(ctx) - M @ X).max() < 1e-12
+
+
+def test_device_pointer_fast_path_matches_host_path(ctx):
+    """lb2_solver_set_device_io: X0 from a device block, eigenvectors to a device block — same result as host buffers."""
+    g = (20, 20, 20)
+    n, k, nev = 8000, 10, 5
+    X0 = pr.initial_block(n, k, 4)
+    A = api.stencil_op(g, np.float64)
+    ref = api.lobpcg(A, X0, nev, 1e-8, 3000)
+    s = api.Solver(ctx, A, n, k, nev, np.float64, 1e-8, 3000)
+    dX0 = api.DeviceArray.from_numpy(ctx, X0)
+    dOut = api.DeviceArray((n, k), np.float64)
+    s.set_device_io(dX0, dOut)
+    s.init()
+    s.step(10 ** 6)
+    r = s.finish()
+    assert r["converged"] == ref["converged"] == nev and r["iter"] == ref["iter"]
+    assert np.array_equal(r["eig"], ref["eig"])
+    assert np.array_equal(dOut.numpy(ctx), ref["X"])
+    assert not np.any(s.state_.X())          # the host block was never touched
+    s.close()
+
+
 def test_zero_initial_block_triggers_random_start():
     g, n = (30, 30), 900
     r = api.lobpcg(api.stencil_op(g, np.float64), np.zeros((n, 8), order="F"), 4, 1e-8, 3000)
