@@ -12,7 +12,9 @@
 // padded tiles (row stride == 4 mod 16 doubles).  The Gram contraction is a reduction over n: each CTA
 // owns one output tile and one contiguous n-range ("split"), partial tiles go to scratch and a second
 // kernel sums them in a fixed order (deterministic, no atomics) and mirrors the Hermitian half.
-// f32 / c32 / c64 currently use the generic register-blocked SIMT kernels at the bottom.
+// c64 uses four real DMMAs per complex MAC; f32 runs 3xTF32 on mma.sync here (Gram fallback, projection) — the default
+// f32 Gram is the tcgen05 kernel of gram_tc5.cu, the default f64 Hermitian Gram the work-list kernel of gram_wl.cu;
+// c32 uses the generic register-blocked SIMT kernels at the bottom.
 #include "common.cuh"
 #include "context.h"
 #include <cmath>

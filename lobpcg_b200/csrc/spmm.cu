@@ -292,7 +292,7 @@ int spmm_stencil_cheb(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* Din, 
 // Measured 2.9-3.1 TB/s (45-48 % of HBM peak) on the 128^3 7-point matrix: every output gathers 7 X values and only
 // the +-1 neighbours are served by L1, so the kernel is bound by L2 sector bandwidth (~5 sector reads per output),
 // not by the (col,val) stream — a shared-memory staged variant of the matrix stream measured no faster.  Getting
-// past this needs a 3-D blocked row order (next round).
+// past this needs a 3-D blocked row order.  Matrices that ARE Dirichlet stencils never get here (capi.cu: detect_stencil).
 // =====================================================================================================
 template <typename T, int NCOL, int RPT>
 __global__ void __launch_bounds__(256)
