@@ -282,7 +282,7 @@ def run_ours(args):
             A2 = dist.partitioned_stencil(ctx, part, np.float64, k)
         else:
             A2 = api.stencil_op((g, g, g), np.float64)
-        T2 = api.chebyshev_op(A2, args.cheb_degree, args.cheb_lo, 0.0)
+        T2 = api.chebyshev_op(A2, args.cheb_degree, args.cheb_lo, 0.0, mixed=not args.cheb_full_precision)
         s2 = api.Solver(ctx, A2, n, k, nev, np.float64, 1e-8, 2000, T=T2, device_seed=7)
         if part is not None:
             dist.attach(s2, part)
@@ -297,7 +297,8 @@ def run_ours(args):
         eigs2, res2 = s2.results()
         an = pr.laplacian_eigs((g, g, g), nev)
         tts = {"seconds": t_tts, "passes": int(p2["iter"]) + 1, "converged": int(p2["converged"]), "nev": nev, "tol": 1e-8,
-               "preconditioner": f"lb2_op_chebyshev(A, degree={args.cheb_degree}, lo={args.cheb_lo}, hi=Gershgorin)",
+               "preconditioner": f"lb2_op_chebyshev{'' if args.cheb_full_precision else '_mixed'}(A, degree={args.cheb_degree}, "
+                                 f"lo={args.cheb_lo}, hi=Gershgorin)",
                "max_rel_eig_err_vs_analytic": float(np.max(np.abs(eigs2[:nev] - an) / an)),
                "max_resnorm": float(res2[:nev].max()),
                "unpreconditioned_reference_point": "810 passes, 334 s on 1 GPU (profiles/full_solve_c5_1gpu_r01.json)"}
@@ -336,8 +337,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tts", action="store_true", help="skip the preconditioned full solve (time_to_solution)")
-    ap.add_argument("--cheb-degree", type=int, default=30)
-    ap.add_argument("--cheb-lo", type=float, default=0.04)
+    ap.add_argument("--cheb-degree", type=int, default=40)
+    ap.add_argument("--cheb-lo", type=float, default=0.02)
+    ap.add_argument("--cheb-full-precision", action="store_true", help="evaluate the preconditioner in double, not float")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

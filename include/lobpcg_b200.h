@@ -72,6 +72,9 @@ void *lb2_op_dense(char prefix, int64_t n, const void *A_host);
  * block apply of T.  hi <= 0: Gershgorin bound of the built-in inner operator; lo <= 0: hi / 50.  The inner operator
  * must outlive the result. */
 void *lb2_op_chebyshev(char prefix, const void *inner_linop, int degree, double lo, double hi);
+/* same polynomial, evaluated in float / complex float inside a double / complex double solve (prefix 'd' / 'z', built-in
+ * stencil inner operator; otherwise identical to lb2_op_chebyshev): half the HBM traffic per preconditioner apply */
+void *lb2_op_chebyshev_mixed(char prefix, const void *inner_linop, int degree, double lo, double hi);
 void lb2_op_destroy(void *linop);
 /* Y = Op X on device block vectors (n x nc) */
 int lb2_op_apply(lb2_ctx *ctx, const void *linop, char prefix, int nc, const void *X, int64_t ldx, void *Y,

@@ -80,6 +80,8 @@ def _declare(L):
     L.lb2_op_dense.argtypes = [C.c_char, i64, vp]
     L.lb2_op_chebyshev.restype = vp
     L.lb2_op_chebyshev.argtypes = [C.c_char, vp, ci, dbl, dbl]
+    L.lb2_op_chebyshev_mixed.restype = vp
+    L.lb2_op_chebyshev_mixed.argtypes = [C.c_char, vp, ci, dbl, dbl]
     L.lb2_op_destroy.argtypes = [vp]
     L.lb2_op_apply.argtypes = [vp, vp, C.c_char, ci, vp, i64, vp, i64]
     L.lb2_solver_create.restype = vp
@@ -386,9 +388,11 @@ def dense_op(A) -> LinOp:
     return LinOp(lib().lb2_op_dense(p.encode(), A.shape[0], A.ctypes.data), p, A.shape[0])
 
 
-def chebyshev_op(A: LinOp, degree: int, lo: float = 0.0, hi: float = 0.0) -> LinOp:
-    """Built-in preconditioner T = p(A) (lb2_op_chebyshev): `degree` Chebyshev steps for A y = x on [lo, hi]."""
-    h = lib().lb2_op_chebyshev(A.prefix.encode(), A.handle, int(degree), float(lo), float(hi))
+def chebyshev_op(A: LinOp, degree: int, lo: float = 0.0, hi: float = 0.0, mixed: bool = False) -> LinOp:
+    """Built-in preconditioner T = p(A) (lb2_op_chebyshev): `degree` Chebyshev steps for A y = x on [lo, hi];
+    mixed=True evaluates it in float / complex float inside a double solve (lb2_op_chebyshev_mixed)."""
+    fn = lib().lb2_op_chebyshev_mixed if mixed else lib().lb2_op_chebyshev
+    h = fn(A.prefix.encode(), A.handle, int(degree), float(lo), float(hi))
     return LinOp(h, A.prefix, A.n, keep=(A,))
 
 

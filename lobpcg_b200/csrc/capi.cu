@@ -236,6 +236,7 @@ static void builtin_cleanup(LinOpCtxRaw* ctx) {
     if (b->val) cudaFree(b->val);
     if (b->diag) cudaFree(b->diag);
     if (b->dense) cudaFree(b->dense);
+    if (b->potential_lo) cudaFree(b->potential_lo);
     b->magic = 0;
     free(b);
   }
@@ -417,6 +418,27 @@ void* lb2_op_diag(char prefix, int64_t n, const void* diag_host) {
   b->diag = upload(diag_host, real_size(prefix) * (size_t)n);
   if (!b->diag) { free(b); return nullptr; }
   return wrap_builtin(b);
+}
+
+// Same preconditioner, evaluated in the LOWER precision inside a double / complex-double solve (float / complex float):
+// its cost is HBM traffic and a preconditioner only has to be a fixed approximation of A^-1.  Needs a built-in stencil
+// as the inner operator and prefix 'd' or 'z'; anything else falls back to lb2_op_chebyshev.
+void* lb2_op_chebyshev_mixed(char prefix, const void* inner_linop, int degree, double lo, double hi) {
+  LinOpRaw* op = (LinOpRaw*)lb2_op_chebyshev(prefix, inner_linop, degree, lo, hi);
+  if (!op) return nullptr;
+  const BuiltinOp* bi = builtin_of((const LinOpRaw*)inner_linop);
+  if (!(prefix == 'd' || prefix == 'z') || !bi || bi->kind != OP_STENCIL) return op;
+  BuiltinOp* b = (BuiltinOp*)op->ctx->data;
+  if (bi->potential) {   // float copy of the (double) potential
+    std::vector<double> hd((size_t)bi->n);
+    std::vector<float> hf((size_t)bi->n);
+    if (cudaMemcpy(hd.data(), bi->potential, sizeof(double) * hd.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return op;
+    for (size_t i = 0; i < hd.size(); i++) hf[i] = (float)hd[i];
+    b->potential_lo = upload(hf.data(), sizeof(float) * hf.size());
+    if (!b->potential_lo) return op;
+  }
+  b->cheb_mixed = 1;
+  return op;
 }
 
 // CSR with 32-bit row pointers (the other common host layout)

@@ -294,6 +294,34 @@ int cheb_update(lb2_ctx* ctx, int64_t n, int nc, const T* AD, const T* Rin, int6
   return 0;
 }
 
+// precision conversion of a block (mixed-precision preconditioner: double <-> float, c64 <-> c32)
+template <typename TO, typename TI>
+__device__ __forceinline__ TO cvt_scalar(TI v) {
+  if constexpr (Sc<TI>::cplx) return TO{(typename Sc<TO>::real)v.re, (typename Sc<TO>::real)v.im};
+  else return (TO)v;
+}
+template <typename TO, typename TI>
+__global__ void __launch_bounds__(256)
+    convert_block_kernel(int64_t n, const TI* __restrict__ X, int64_t ldx, TO* __restrict__ Y, int64_t ldy) {
+  const TI* x = X + (int64_t)blockIdx.y * ldx;
+  TO* y = Y + (int64_t)blockIdx.y * ldy;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = cvt_scalar<TO, TI>(x[i]);
+}
+template <typename TO, typename TI>
+int convert_block(lb2_ctx* ctx, int64_t n, int nc, const TI* X, int64_t ldx, TO* Y, int64_t ldy) {
+  if (n <= 0 || nc <= 0) return 0;
+  int gx = (int)std::min<int64_t>((n + 256 * 4 - 1) / (256 * 4), 1 << 20);
+  convert_block_kernel<TO, TI><<<dim3(std::max(gx, 1), nc), 256, 0, ctx->stream>>>(n, X, ldx, Y, ldy);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template int convert_block<float, double>(lb2_ctx*, int64_t, int, const double*, int64_t, float*, int64_t);
+template int convert_block<double, float>(lb2_ctx*, int64_t, int, const float*, int64_t, double*, int64_t);
+template int convert_block<c32, c64>(lb2_ctx*, int64_t, int, const c64*, int64_t, c32*, int64_t);
+template int convert_block<c64, c32>(lb2_ctx*, int64_t, int, const c32*, int64_t, c64*, int64_t);
+
 #define LB2_INST(T)                                                                                     \
   template int residual<T>(lb2_ctx*, int64_t, int, const T*, int64_t, const T*, int64_t, const real_t<T>*, \
                            T*, int64_t, real_t<T>*);                                                    \

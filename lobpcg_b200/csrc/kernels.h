@@ -62,6 +62,10 @@ template <typename T>
 int cheb_update(lb2_ctx* ctx, int64_t n, int nc, const T* AD, const T* Rin, int64_t ldrin, T* Rout, const T* Din, T* Dout,
                 int64_t ldw, T* Y, int64_t ldy, real_t<T> c1, real_t<T> c2, bool write_r);
 
+// Y = (TO) X, block-wise (mixed-precision preconditioner)
+template <typename TO, typename TI>
+int convert_block(lb2_ctx* ctx, int64_t n, int nc, const TI* X, int64_t ldx, TO* Y, int64_t ldy);
+
 // ---- spmm.cu ----------------------------------------------------------------------------------------
 struct StencilDesc {
   int gx, gy, gz;          // local grid (gz = local planes of the z-slab)

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 #include <inttypes.h>
 
@@ -270,6 +271,8 @@ class Solver : public SolverBase {
   int cp_from_z(int m, const T* Zm, T* VQ);           // VQ (m x k) = Z_perp Q
   int svqb(T* U, int nu, R tau, bool drop, int* nret);
   int localize(const BuiltinOp*& b, BuiltinOp& local, const T* X);
+  int localize_bytes(const BuiltinOp*& b, BuiltinOp& local, const void* X, size_t elem);
+  int apply_cheb_mixed(const BuiltinOp* b, const BuiltinOp* in, int nc, const T* X, T* Y);
   int ortho_drop(T* U, int nu, T* V, int nv, int* nret, bool indefinite = false);
   int rr_indef(int m, int from_col, bool initial);
   int ortho_indef_mat(int m, int nu, int nv, T* U, const T* V, const T* mat);
@@ -338,6 +341,10 @@ int Solver<T>::alloc() {
 // peer halo pointers for X (which must live in the arena: same offset on every rank) and redirects b to it.
 template <typename T>
 int Solver<T>::localize(const BuiltinOp*& b, BuiltinOp& local, const T* X) {
+  return localize_bytes(b, local, X, sizeof(T));
+}
+template <typename T>
+int Solver<T>::localize_bytes(const BuiltinOp*& b, BuiltinOp& local, const void* X, size_t elem) {
   if (!(ctx->comm && b->n != b->n_global && b->kind == OP_STENCIL)) return 0;
   tm.begin(PH_COMM);
   int rcb = allreduce_sum(ctx, Scal + 12, 1, kDouble);
@@ -350,11 +357,54 @@ int Solver<T>::localize(const BuiltinOp*& b, BuiltinOp& local, const T* X) {
     return -1;
   }
   const int64_t plane = b->gx * b->gy;
-  local.halo_lo = peer_lo ? (const void*)((const T*)(peer_lo + off) + (b->gz - 1) * plane) : nullptr;
+  local.halo_lo = peer_lo ? (const void*)(peer_lo + off + (size_t)((b->gz - 1) * plane) * elem) : nullptr;
   local.halo_hi = peer_hi ? (const void*)(peer_hi + off) : nullptr;
   local.halo_ld = n;
   b = &local;
   return 0;
+}
+
+// T = p(A) evaluated in the lower precision (float / c32) for a double / c64 solve: the preconditioner only has to be a
+// fixed, good approximation of A^-1 on the unwanted part of the spectrum, and its cost is pure HBM traffic, which halves.
+// X is converted into the workspace, the fused stencil + Chebyshev steps run on float blocks (same arena region, so
+// row-partitioned halo reads keep working), the result is converted back.
+template <typename T>
+int Solver<T>::apply_cheb_mixed(const BuiltinOp* b, const BuiltinOp* in, int nc, const T* X, T* Y) {
+  if constexpr (sizeof(R) != 8) {
+    return -1;
+  } else {
+    using TL = typename std::conditional<Sc<T>::cplx, c32, float>::type;
+    using RL = float;
+    TL* w = reinterpret_cast<TL*>(slab[1 - cur]);      // 3k columns of T = 6k columns of TL, leading dimension n
+    TL* Xf = w;
+    TL* Rw = w + (int64_t)k * n;
+    TL* D0 = w + (int64_t)2 * k * n;
+    TL* D1 = w + (int64_t)3 * k * n;
+    TL* Yf = w + (int64_t)4 * k * n;
+    LB2_TRY((convert_block<TL, T>(ctx, n, nc, X, n, Xf, n)));
+    BuiltinOp twin = *in;                              // the inner stencil as an operator of the lower precision
+    twin.prefix = Sc<TL>::prefix;
+    twin.potential = b->potential_lo;
+    int rc = cheb_apply<TL>(
+        ctx, b, n, nc, Xf, n, Yf, n, Rw, D0, D1, (TL*)nullptr, n,
+        [&](int, const TL*, TL*) { return -1; },       // never taken: the fused step below always applies
+        [&](int c, const TL* Din, TL* Dout, const TL* Rin, int64_t ldrin, TL* Rout, TL* Yacc, RL c1, RL c2, bool wr) {
+          BuiltinOp local;
+          const BuiltinOp* bb = &twin;
+          if (int rcl = localize_bytes(bb, local, Din, sizeof(TL))) return rcl;
+          ChebEpilogue<TL> ep;
+          ep.rin = Rin; ep.ldrin = ldrin; ep.rout = Rout; ep.dout = Dout; ep.ldw = n; ep.c1 = c1; ep.c2 = c2;
+          ep.write_r = wr ? 1 : 0;
+          tm.begin(PH_SPMM);
+          int r2 = spmm_stencil_cheb<TL>(ctx, stencil_desc(bb), c, Din, n, Yacc, n, ep);
+          tm.end();
+          phase_work[PH_SPMM] += (wr ? 6.0 : 5.0) * (double)n * c * sizeof(TL);
+          phase_calls[PH_SPMM]++;
+          return r2;
+        });
+    if (rc) return rc;
+    return convert_block<T, TL>(ctx, n, nc, Yf, n, Y, n);
+  }
 }
 
 // Y = Op X.  Built-in operators run as block kernels; anything else is a host callback (reference
@@ -373,6 +423,9 @@ int Solver<T>::apply(const LinOpRaw* op, int nc, const T* X, T* Y) {
     if (X == w || Y == w) { fprintf(stderr, "lobpcg_b200: preconditioner workspace aliases its operands\n"); return -1; }
     const BuiltinOp* in = builtin_of(b->inner);
     const bool can_fuse = in && in->kind == OP_STENCIL && !getenv("LB2_NO_CHEB_FUSE");
+    if constexpr (sizeof(R) == 8) {
+      if (b->cheb_mixed && can_fuse) return apply_cheb_mixed(b, in, nc, X, Y);
+    }
     return cheb_apply<T>(
         ctx, b, n, nc, X, n, Y, n, w, col(w, k), col(w, 2 * k), col(AS, k), n,
         [&](int c, const T* D, T* AD) { return apply(b->inner, c, D, AD); },

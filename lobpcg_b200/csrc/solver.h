@@ -85,6 +85,8 @@ struct BuiltinOp {
   const LinOpRaw* inner;
   int cheb_degree;
   double cheb_lo, cheb_hi;
+  int cheb_mixed;        // 1: inside the solver the polynomial is evaluated in the lower precision (float for d, c32 for z)
+  void* potential_lo;    // float copy of the inner stencil's potential for that evaluation (device, may be null)
   // back pointer for host matvec shim
   LinOpRaw* self;
 };

@@ -1,6 +1,6 @@
 """Time-to-solution of a BASELINE config on 1..N GPUs (torchrun for N>1):
    python tools/full_solve.py G NEV [tol] [maxiter] [cheb=DEGREE,LO]   -> JSON line with iterations, seconds, eigenvalue errors
-cheb=DEGREE,LO uses the built-in polynomial preconditioner T = lb2_op_chebyshev(A, DEGREE, LO, Gershgorin bound)."""
+cheb=DEGREE,LO[,mixed] uses the built-in polynomial preconditioner T = lb2_op_chebyshev(A, DEGREE, LO, Gershgorin bound)."""
 import os, sys, time, json
 sys.path.insert(0, ".")
 import numpy as np
@@ -24,8 +24,8 @@ else:
     A = api.stencil_op((g, g, g), np.float64)
 T = None
 if cheb:
-    deg, lo = cheb.split(",")
-    T = api.chebyshev_op(A, int(deg), float(lo), 0.0)
+    deg, lo = cheb.split(",")[:2]
+    T = api.chebyshev_op(A, int(deg), float(lo), 0.0, mixed=cheb.endswith(",mixed"))
 s = api.Solver(ctx, A, n, k, nev, np.float64, tol, maxit, T=T, device_seed=7)
 if part is not None:
     dist.attach(s, part)

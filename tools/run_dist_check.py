@@ -36,4 +36,15 @@ r2 = s2.finish()
 err2 = np.max(np.abs(r2["eig"][:nev] - an) / an)
 print(f"rank {rank}: chebyshev T: iter {r2['iter']} conv {r2['converged']} max rel err vs analytic {err2:.2e}", flush=True)
 assert r2["converged"] == nev and err2 < 1e-10 and r2["iter"] * 3 < r["iter"]
+s2.close()
+# ... and evaluated in float inside the double solve (float blocks in the same arena region, float halo planes)
+T3 = api.chebyshev_op(A, 8, 0.3, 0.0, mixed=True)
+s3 = api.Solver(ctx, A, n, k, nev, np.float64, 1e-8, 5000, T=T3, device_seed=7)
+dist.attach(s3, part)
+s3.init()
+s3.step(10 ** 6)
+r3 = s3.finish()
+err3 = np.max(np.abs(r3["eig"][:nev] - an) / an)
+print(f"rank {rank}: mixed-precision chebyshev T: iter {r3['iter']} conv {r3['converged']} max rel err vs analytic {err3:.2e}", flush=True)
+assert r3["converged"] == nev and err3 < 1e-10 and r3["iter"] * 3 < r["iter"]
 dist.shutdown(ctx)
