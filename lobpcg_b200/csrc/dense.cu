@@ -1175,7 +1175,13 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
     if (!ctx->force_simt && kd > 0) return launch_nn_zmma(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
   }
   if constexpr (std::is_same<T, float>::value) {
-    if (!ctx->force_simt && kd > 0) return launch_nn_tf32(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
+    if (!ctx->force_simt && kd > 0) {
+      if (ctx->gram_tc5 != 0 && n >= 1024) {   // tcgen05 / TMEM path (nn_tc5.cu); -100 = S not 16-byte aligned
+        const int rc = nn_tc5_f32(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
+        if (rc != -100) return rc;
+      }
+      return launch_nn_tf32(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
+    }
   }
   const int nct = (nb + 63) / 64;
   const int64_t nrt = (n + 63) / 64;

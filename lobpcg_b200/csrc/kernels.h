@@ -28,6 +28,9 @@ int gram_reduce_f32(lb2_ctx* ctx, const float* part, int64_t split_stride, int n
 // gram_tc5.cu: float Gram on tcgen05 (kind::tf32, 3xTF32 split, accumulator in TMEM); -100 = alignment not met
 int gram_tc5_f32(lb2_ctx* ctx, int64_t n, int ma, int mb, const float* A, int64_t lda, const float* B, int64_t ldb,
                  float* G, int ldg, int upper);
+// nn_tc5.cu: float projection Out = alpha S C + beta Out on tcgen05 (3xTF32, TMEM accumulator); -100 = alignment not met
+int nn_tc5_f32(lb2_ctx* ctx, int64_t n, int kd, int nb, float alpha, const float* S, int64_t lds, const float* C, int ldc,
+               float beta, float* Out, int64_t ldo);
 int gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int BK, double* stats);
 
 // ---- elementwise.cu ---------------------------------------------------------------------------------

@@ -200,6 +200,25 @@ def test_tall_nn_matches_oracle(ctx, dt, shape, ab):
     close(dO.numpy(ctx), ab[0] * (S @ Cm) + ab[1] * O0, rtol(dt) * 10)
 
 
+@pytest.mark.parametrize("shape", [(4096, 32, 16), (5000, 60, 40), (20000, 300, 200), (33333, 129, 70), (8192, 900, 300),
+                                   (7777, 600, 129), (4100, 7, 5)])
+@pytest.mark.parametrize("ab", [(1.0, 0.0), (-1.0, 1.0)])
+def test_tall_nn_float_tcgen05_matches_fp64_reference(ctx, shape, ab):
+    """float projection on tcgen05 (csrc/nn_tc5.cu: MN-major A, run-time UMMA N, 3xTF32, fp64 drain) vs an fp64 product."""
+    n, kd, nb = shape
+    rng = np.random.default_rng(n + kd)
+    S, Cm, O0 = rand(rng, (n, kd), np.float32), rand(rng, (kd, nb), np.float32), rand(rng, (n, nb), np.float32)
+    ldn = (n + 3) // 4 * 4
+    dO = api.DeviceArray.from_numpy(ctx, O0, ld=ldn)
+    ctx.set_option("gram_tc5", 1)
+    try:
+        api.tall_nn(ctx, api.DeviceArray.from_numpy(ctx, S, ld=ldn), api.DeviceArray.from_numpy(ctx, Cm), dO, alpha=ab[0], beta=ab[1])
+    finally:
+        ctx.set_option("gram_tc5", -1)
+    ref = ab[0] * (S.astype(np.float64) @ Cm.astype(np.float64)) + ab[1] * O0
+    close(dO.numpy(ctx), ref, 2e-6)
+
+
 def test_tall_nn_beta_zero_ignores_nan_output(ctx):
     rng = np.random.default_rng(3)
     S, Cm = rand(rng, (3000, 40), np.float64), rand(rng, (40, 24), np.float64)
