@@ -25,7 +25,8 @@
 // MMA with no-swizzle operands), staging + split alone take 110 ms: the kernel is bound by how fast one SM can pull
 // 256 column pieces of 128 bytes per chunk (~9 ns per piece, the same ~15 GB/s per SM every column-piece Gram kernel
 // of this library sees); a warp-specialised variant (ninth warp issuing the MMAs, full/done mbarriers, no block
-// barrier) measured slower (112 ms vs 95 ms) and was dropped.  Next step: 128 x 256 tiles or a 2x2 cluster sharing
+// barrier) measured slower (112 ms vs 95 ms) and was dropped; so did a copy mapping that requests full 128-byte lines
+// (4 columns x 8 k-units per warp instruction: 164 ms, 8-way shared-memory bank conflicts on copy and split).  Next step: 128 x 256 tiles or a 2x2 cluster sharing
 // panels through TMA multicast, which halves the pieces per flop.
 #include <cstdint>
 
