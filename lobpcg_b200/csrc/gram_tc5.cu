@@ -40,13 +40,14 @@ namespace {
 
 constexpr int TC_T = 128;            // tile edge = UMMA M = UMMA N
 constexpr int TC_BK = 32;            // rows (K) per chunk
-constexpr int TC_RAW = 5;            // raw (= hi operand) stages: chunk c + 3 is requested while chunk c is converted
+constexpr int TC_RAW = 4;            // raw (= hi operand) stages: chunk c + 2 is requested while chunk c is converted
 constexpr int TC_LO = 2;             // lo-operand buffers (written by the CTA, read by the MMAs of one chunk)
 constexpr int TC_AHEAD = TC_RAW - 2; // prefetch distance in chunks
 constexpr int TC_FLUSH = 2;          // chunks per TMEM accumulation group (see "accuracy" below)
 constexpr int TC_NT = 256;           // 8 warps: warp w owns TMEM lanes 32 (w % 4) .. and column half w / 4 when draining
 constexpr int TC_UNITS = (TC_T * TC_BK / 4) / TC_NT;   // 16-byte units per thread, operand tile and chunk
-constexpr uint32_t TC_LBO = 128;     // bytes between consecutive 16-byte k-units (core matrices along K)
+constexpr uint32_t TC_LBO = 144;     // bytes between consecutive 16-byte k-units (core matrices along K): 128 + 16 so that the
+                                     // eight k-units of a column fall into eight different 16-byte bank groups
 constexpr uint32_t TC_SBO = (TC_BK / 4) * TC_LBO;          // bytes between 8-column groups (core matrices along M/N)
 constexpr uint32_t TC_TILE = (TC_T / 8) * TC_SBO;          // 16 KB per operand tile
 constexpr uint32_t TC_STAGE = 2 * TC_TILE;                 // raw stage: A, B;  lo buffer: A_lo, B_lo
@@ -144,17 +145,17 @@ __global__ void __launch_bounds__(TC_NT, 1)
   const uint32_t tmem = *tmem_slot;
 
   // this thread's copy/convert units: TC_UNITS per operand tile; unit = (column c, k-unit u) -> 16 bytes = 4 rows of a column
-  const int cc = lane & 7, uu = lane >> 3;
+  // a warp instruction covers 4 columns x all 8 k-units of the chunk: one full 128-byte line per column
+  const int uu = lane & 7, cc = lane >> 3;
   uint32_t uoff[TC_UNITS];                   // byte offset of the unit inside an operand tile
   int ucol[TC_UNITS], urow[TC_UNITS];        // column inside the panel, first row inside the chunk
 #pragma unroll
   for (int i = 0; i < TC_UNITS; i++) {
-    const int blk = i * (TC_NT / 32) + warp;          // 0..31
-    const int cg = blk & 15, uh = blk >> 4;
-    const int u = uh * 4 + uu;
-    ucol[i] = cg * 8 + cc;
-    urow[i] = u * 4;
-    uoff[i] = (uint32_t)cg * TC_SBO + (uint32_t)u * TC_LBO + (uint32_t)cc * 16u;
+    const int blk = i * (TC_NT / 32) + warp;          // 0..31: block of 4 columns
+    const int col = blk * 4 + cc;
+    ucol[i] = col;
+    urow[i] = uu * 4;
+    uoff[i] = (uint32_t)(col >> 3) * TC_SBO + (uint32_t)uu * TC_LBO + (uint32_t)(col & 7) * 16u;
   }
 
   auto issue_loads = [&](int chunk) {
