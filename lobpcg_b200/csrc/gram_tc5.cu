@@ -20,14 +20,16 @@
 //      the MMAs of chunk c run while the CTA converts chunk c + 1.
 // Epilogue: the fp64 register accumulators -> partial tile in global scratch (deterministic split reduction follows).
 //
-// Measured (B200, n = 4.096 M): 69 TFLOP/s (3xTF32 counted once) at 896 x 896, 50 at m = 600 upper, against 55 / 37 for
-// the mma.sync kernel.  Probes: the MMAs alone run the 896 x 896 case in 31 ms (211 TFLOP/s; 119 clocks per 128x128x8
-// MMA with no-swizzle operands), staging + split alone take 110 ms: the kernel is bound by how fast one SM can pull
-// 256 column pieces of 128 bytes per chunk (~9 ns per piece, the same ~15 GB/s per SM every column-piece Gram kernel
-// of this library sees); a warp-specialised variant (ninth warp issuing the MMAs, full/done mbarriers, no block
-// barrier) measured slower (112 ms vs 95 ms) and was dropped; so did a copy mapping that requests full 128-byte lines
-// (4 columns x 8 k-units per warp instruction: 164 ms, 8-way shared-memory bank conflicts on copy and split).  Next step: 128 x 256 tiles or a 2x2 cluster sharing
-// panels through TMA multicast, which halves the pieces per flop.
+// Measured (B200, n = 4.096 M): 74 TFLOP/s (3xTF32 counted once) at 896 x 896, 50 at m = 600 upper, against 55 / 37 for
+// the mma.sync kernel; the same rate at n = 65 536 (TLB- and L2-friendly), so HBM / L2 / TLB are not the limit.
+// Probe with parts of the chunk loop switched off (n = 2.1 M, 896 x 896, 44.9 ms in full): no copies 26.3 ms, no split
+// 39.1, no proxy fence 43.6, no MMAs 39.5, empty skeleton (barrier per chunk, mbarrier waits, commit, fp64 drain) 10.4 —
+// i.e. per 32-row chunk 0.47 us skeleton + 0.85 us issuing/landing the 64 warp-level cp.async + 0.27 us split + 0.25 us
+// of MMA time that is not hidden + 0.06 us fence = 2.06 us, where the 12 MMAs alone need 0.73 us (119 clocks per
+// 128x128x8 MMA with no-swizzle operands): every warp does every phase, so the phases add up instead of overlapping.
+// A first warp-specialised variant (ninth warp issuing the MMAs, full/done mbarriers, producers still copying, splitting
+// and draining in sequence) was slower (112 ms vs 95 ms).  Next step: TMA (SWIZZLE_128B tiles, one instruction per
+// panel and chunk instead of 64 warp-level copies) feeding separate split / MMA / drain warps.
 #include <cstdint>
 
 #include "common.cuh"
