@@ -273,8 +273,8 @@ def run_ours(args):
         s.close()
 
     # ---- time to solution of the same config (BASELINE metric "time-to-solution"): full solve to tol 1e-8 with the
-    # built-in polynomial preconditioner behind alg->T; the unpreconditioned solve needs 810 passes
-    # (profiles/full_solve_c5_1gpu_r01.json) and does not fit a bench run
+    # built-in polynomial preconditioner behind alg->T; the unpreconditioned solve needs 793 passes
+    # (profiles/full_solve_c5_final_r01.json) and does not fit a bench run
     tts = None
     if not args.no_tts:
         from lobpcg_b200 import problems as pr
@@ -301,7 +301,7 @@ def run_ours(args):
                                  f"lo={args.cheb_lo}, hi=Gershgorin)",
                "max_rel_eig_err_vs_analytic": float(np.max(np.abs(eigs2[:nev] - an) / an)),
                "max_resnorm": float(res2[:nev].max()),
-               "unpreconditioned_reference_point": "810 passes, 334 s on 1 GPU (profiles/full_solve_c5_1gpu_r01.json)"}
+               "unpreconditioned_reference_point": "793 passes, 296 s on 1 GPU (profiles/full_solve_c5_final_r01.json)"}
         s2.close()
 
     cpu = None
