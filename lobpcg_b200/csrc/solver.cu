@@ -828,8 +828,7 @@ int Solver<T>::ortho_indef_mat(int m, int nu, int nv, T* U, const T* V, const T*
   const size_t blk = (size_t)3 * k * k;
   T* t1 = DinvR;            // m x max(nu,nv)
   T* t2 = DinvR + blk;      // m x nu
-  T* c1 = DinvR + 2 * blk;  // nv x nu  /  nu x nu
-  T* c2 = Q;                // nu x nu transform
+  T* c1 = DinvR + 2 * blk;  // nv x nu  /  nu x nu   (svqb_mat_dev keeps its nu x nu transform in Q)
   LB2_TRY(sd_gemm<T>(ctx, 'N', m, nv, m, mat, m, V, m, t1, m));
   LB2_TRY(sd_frob<T>(ctx, m, nv, t1, m, Scal));
   LB2_TRY(d2h(hbuf, Scal, sizeof(R)));
