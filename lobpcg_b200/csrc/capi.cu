@@ -1,4 +1,5 @@
 // lobpcg_b200/csrc/capi.cu — the C ABI declared in include/lobpcg_b200.h and include/lobpcg.h.
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <algorithm>
@@ -634,13 +635,24 @@ int lb2_solver_state(lb2_solver* s, uint64_t* iter, uint64_t* converged, int* us
 static void run_solver(char prefix, void* alg, int indefinite) {
   lb2_ctx* ctx = lb2_default_ctx();
   if (!ctx) return;
+  // LB2_TIMING=1: wall-clock split of the call on stderr (set-up + X0 upload + initial RR | passes | download | tear-down)
+  const bool timing = getenv("LB2_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   lb2_solver* s = lb2_solver_create(ctx, prefix, alg, indefinite);
   if (!s) return;
+  double t1 = t0, t2 = t0, t3 = t0;
   if (lb2_solver_init(s) == 0) {
+    t1 = now();
     int rc = lb2_solver_step(s, INT_MAX);
+    t2 = now();
     if (rc >= 0) lb2_solver_finish(s);
+    t3 = now();
   }
   lb2_solver_destroy(s);
+  if (timing)
+    fprintf(stderr, "lobpcg_b200 timing: create+alloc+upload+init %.3f s, passes %.3f s, download %.3f s, destroy %.3f s\n",
+            t1 - t0, t2 - t1, t3 - t2, now() - t3);
 }
 
 #define LB2_ENTRY(P, T)                                                                               \
