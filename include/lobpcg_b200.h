@@ -65,8 +65,20 @@ void *lb2_op_bdg(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, 
 /* CSR with int32 row pointers; Matrix Market coordinate file -> CSR operator (symmetric / hermitian storage expanded) */
 void *lb2_op_csr32(char prefix, int64_t n, const int32_t *rowptr_host, const int32_t *col_host, const void *val_host);
 void *lb2_op_csr_from_mtx(char prefix, const char *path);
+/* eigenpair write-out: host block (column-major, leading dimension ld, scalars of type `prefix`) -> Matrix Market dense
+ * "array" file; eigenvalues are a rows x 1 block of the real type ('s' / 'd').  0 on success. */
+int lb2_write_mtx(const char *path, char prefix, int64_t rows, int64_t cols, const void *host, int64_t ld);
 /* dense n x n operator (column-major host matrix of the operator's scalar type, uploaded once; block apply = library GEMM) */
 void *lb2_op_dense(char prefix, int64_t n, const void *A_host);
+/* Caller-supplied block operator on DEVICE pointers: the extension of the reference's one-host-vector-at-a-time operator
+ * interface (include/lobpcg/linop.h:15-26) for applications that already have CUDA kernels.  fn computes Y = Op X for
+ * `ncols` columns (column-major, n rows, leading dimensions ldx / ldy, scalars of the operator's type), must enqueue all
+ * of its work on `cuda_stream` (a cudaStream_t) without synchronising, and returns 0 on success (any other value aborts
+ * the solve like a failed kernel launch).  spec_hi > 0 passes an upper bound of the spectrum for lb2_op_chebyshev.
+ * The result is an ordinary LinearOperator_<p>_t*; its matvec also works on host vectors. */
+typedef int (*lb2_matmat_fn)(void *user, int ncols, const void *X_dev, int64_t ldx, void *Y_dev, int64_t ldy,
+                             void *cuda_stream);
+void *lb2_op_device(char prefix, int64_t n, lb2_matmat_fn fn, void *user, double spec_hi);
 /* Built-in preconditioner for alg->T (the reference only plans built-ins, README.md:15): T = p(A), `degree`
  * steps of the Chebyshev iteration for A y = x on the spectrum window [lo, hi], i.e. `degree` block applies of A per
  * block apply of T.  hi <= 0: Gershgorin bound of the built-in inner operator; lo <= 0: hi / 50.  The inner operator

@@ -78,6 +78,9 @@ def _declare(L):
     L.lb2_op_csr_from_mtx.argtypes = [C.c_char, C.c_char_p]
     L.lb2_op_dense.restype = vp
     L.lb2_op_dense.argtypes = [C.c_char, i64, vp]
+    L.lb2_write_mtx.argtypes = [C.c_char_p, C.c_char, i64, i64, vp, i64]
+    L.lb2_op_device.restype = vp
+    L.lb2_op_device.argtypes = [C.c_char, i64, vp, vp, dbl]
     L.lb2_op_chebyshev.restype = vp
     L.lb2_op_chebyshev.argtypes = [C.c_char, vp, ci, dbl, dbl]
     L.lb2_op_chebyshev_mixed.restype = vp
@@ -386,6 +389,25 @@ def dense_op(A) -> LinOp:
     A = np.asfortranarray(A)
     p = PREFIX[A.dtype]
     return LinOp(lib().lb2_op_dense(p.encode(), A.shape[0], A.ctypes.data), p, A.shape[0])
+
+
+def write_mtx(path, a: np.ndarray):
+    """Write a host vector / block as a Matrix Market dense array file (lb2_write_mtx)."""
+    a = np.asfortranarray(a if np.ndim(a) == 2 else np.asarray(a).reshape(-1, 1))
+    _ck(lib().lb2_write_mtx(str(path).encode(), PREFIX[a.dtype].encode(), a.shape[0], a.shape[1], a.ctypes.data,
+                            max(a.shape[0], 1)), "lb2_write_mtx")
+
+
+MATMAT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+def device_op(n: int, dtype, fn, spec_hi: float = 0.0) -> LinOp:
+    """Caller-supplied block operator on device pointers (lb2_op_device): ``fn(ncols, X_ptr, ldx, Y_ptr, ldy, stream)``
+    enqueues Y = Op X on ``stream`` and returns 0."""
+    p = PREFIX[np.dtype(dtype)]
+    cb = MATMAT_FN(lambda user, nc, X, ldx, Y, ldy, stream: int(fn(nc, X, ldx, Y, ldy, stream)))
+    h = lib().lb2_op_device(p.encode(), n, C.cast(cb, C.c_void_p), None, spec_hi)
+    return LinOp(h, p, n, keep=(cb, fn))
 
 
 def chebyshev_op(A: LinOp, degree: int, lo: float = 0.0, hi: float = 0.0, mixed: bool = False) -> LinOp:

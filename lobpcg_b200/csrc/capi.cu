@@ -515,6 +515,35 @@ void* lb2_op_csr_from_mtx(char prefix, const char* path) {
   return lb2_op_csr(prefix, nr, rp.data(), col.data(), val.data());
 }
 
+// Eigenpair write-out: a host block (column-major, leading dimension ld) as a Matrix Market dense
+// "array" file, real or complex general, 17 significant digits (9 for the single-precision types).  Host-only.
+int lb2_write_mtx(const char* path, char prefix, int64_t rows, int64_t cols, const void* host, int64_t ld) {
+  if (!path || !valid_prefix(prefix) || rows < 0 || cols < 0 || ld < rows || (!host && rows * cols > 0)) return -1;
+  FILE* f = fopen(path, "w");
+  if (!f) {
+    fprintf(stderr, "lobpcg_b200: cannot open %s for writing\n", path);
+    return -1;
+  }
+  const bool cplx = (prefix == 'c' || prefix == 'z');
+  const bool dbl = (prefix == 'd' || prefix == 'z');
+  fprintf(f, "%%%%MatrixMarket matrix array %s general\n%lld %lld\n", cplx ? "complex" : "real", (long long)rows,
+          (long long)cols);
+  const int prec = dbl ? 17 : 9;
+  for (int64_t j = 0; j < cols; j++)
+    for (int64_t i = 0; i < rows; i++) {
+      const size_t q = (size_t)i + (size_t)j * (size_t)ld;
+      if (cplx) {
+        const double re = dbl ? ((const double*)host)[2 * q] : (double)((const float*)host)[2 * q];
+        const double im = dbl ? ((const double*)host)[2 * q + 1] : (double)((const float*)host)[2 * q + 1];
+        fprintf(f, "%.*g %.*g\n", prec, re, prec, im);
+      } else {
+        fprintf(f, "%.*g\n", prec, dbl ? ((const double*)host)[q] : (double)((const float*)host)[q]);
+      }
+    }
+  const bool ok = (ferror(f) == 0);
+  return (fclose(f) == 0 && ok) ? 0 : -1;
+}
+
 // Dense operator: A is n x n, column-major, leading dimension n, of the operator's scalar type; applied
 // to whole blocks by a library GEMM.  The reference's dense examples are host callbacks (tests/test_lobpcg.c:29-42),
 // which keep working through the staged path; this constructor is the device-resident version.
@@ -540,6 +569,20 @@ void* lb2_op_dense(char prefix, int64_t n, const void* A_host) {
     }
   for (double v : rs) hi = std::max(hi, v);
   b->spec_hi = hi;
+  return wrap_builtin(b);
+}
+
+// Caller-supplied block operator on device pointers (the documented extension for foreign operators).  The
+// reference's operator interface is one host vector at a time (include/lobpcg/linop.h:15-26); this constructor keeps the
+// LinearOperator_<p>_t shape but lets a CUDA application hand its own kernels to the solver: `fn` is called with device
+// block vectors (column-major, ncols columns of n rows) and must enqueue its work on `cuda_stream` without synchronising.
+void* lb2_op_device(char prefix, int64_t n, lb2_matmat_fn fn, void* user, double spec_hi) {
+  if (!valid_prefix(prefix) || n < 1 || !fn) return nullptr;
+  if (!lb2_default_ctx()) return nullptr;
+  BuiltinOp* b = new_builtin(OP_DEVICE, prefix, n);
+  b->dev_fn = (DeviceMatmat)fn;
+  b->dev_user = user;
+  b->spec_hi = spec_hi > 0 ? spec_hi : 0.0;
   return wrap_builtin(b);
 }
 

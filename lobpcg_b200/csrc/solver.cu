@@ -84,6 +84,12 @@ int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t 
     case OP_DENSE:   // plain library GEMM (cuBLAS): Y = A X with A dense n x n
       if (b->n > INT32_MAX || ldx > INT32_MAX || ldy > INT32_MAX) return -2;
       return sd_gemm<T>(ctx, 'N', (int)b->n, nc, (int)b->n, (const T*)b->dense, (int)b->n, X, (int)ldx, Y, (int)ldy);
+    case OP_DEVICE: {   // the caller's own kernels, enqueued on the solver stream (SURVEY §8b "foreign operators")
+      if (!b->dev_fn) return -1;
+      const int rc = b->dev_fn(b->dev_user, nc, X, ldx, Y, ldy, (void*)ctx->stream);
+      if (rc) fprintf(stderr, "lobpcg_b200: device operator callback returned %d\n", rc);
+      return rc;
+    }
     case OP_CHEB: {   // stand-alone apply (outside a solver): temporary workspace
       const BuiltinOp* in = builtin_of(b->inner);
       if (!in) {

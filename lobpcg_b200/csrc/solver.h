@@ -52,7 +52,9 @@ struct State {  // == <p>_lobpcg_t (reference lobpcg.h:13-55)
 
 // ---- built-in operators (tag lives at the head of ctx->data) -------------------------------------------
 constexpr uint64_t kOpMagic = 0x4C42324F50455221ULL;  // "LB2OPER!"
-enum OpKind { OP_STENCIL = 0, OP_CSR = 1, OP_DIAG = 2, OP_BDG = 3, OP_CHEB = 4, OP_DENSE = 5 };
+enum OpKind { OP_STENCIL = 0, OP_CSR = 1, OP_DIAG = 2, OP_BDG = 3, OP_CHEB = 4, OP_DENSE = 5, OP_DEVICE = 6 };
+// OP_DEVICE: caller-supplied block operator on DEVICE pointers (lb2_matmat_fn of include/lobpcg_b200.h)
+typedef int (*DeviceMatmat)(void* user, int ncols, const void* X, int64_t ldx, void* Y, int64_t ldy, void* cuda_stream);
 
 struct BuiltinOp {
   uint64_t magic;
@@ -87,6 +89,9 @@ struct BuiltinOp {
   double cheb_lo, cheb_hi;
   int cheb_mixed;        // 1: inside the solver the polynomial is evaluated in the lower precision (float for d, c32 for z)
   void* potential_lo;    // float copy of the inner stencil's potential for that evaluation (device, may be null)
+  // caller's device block operator (OP_DEVICE)
+  DeviceMatmat dev_fn;
+  void* dev_user;
   // back pointer for host matvec shim
   LinOpRaw* self;
 };

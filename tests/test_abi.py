@@ -6,6 +6,7 @@ import re
 import subprocess
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 from lobpcg_b200 import api
@@ -133,3 +134,20 @@ def test_product_never_imports_oracle():
         assert "oracle" not in re.sub(r'""".*?"""', "", txt, flags=re.S).replace("# oracle", ""), py
     for cu in (ROOT / "lobpcg_b200" / "csrc").iterdir():
         assert "oracle/" not in cu.read_text(), cu
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex64, np.complex128])
+def test_eigenpair_write_out_round_trips(dt, tmp_path):
+    """lb2_write_mtx (host-only): Matrix Market dense array files read back by scipy bit-exactly."""
+    import scipy.io
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((37, 5)) + (1j * rng.standard_normal((37, 5)) if np.dtype(dt).kind == "c" else 0)
+    a = a.astype(dt)
+    api.write_mtx(tmp_path / "x.mtx", a)
+    back = scipy.io.mmread(str(tmp_path / "x.mtx"))
+    assert back.shape == a.shape and np.array_equal(back.astype(dt), a)
+    lam = np.sort(rng.standard_normal(7)).astype(np.dtype(dt).char.lower() if np.dtype(dt).kind == "c" else dt)
+    api.write_mtx(tmp_path / "lam.mtx", lam)
+    assert np.array_equal(scipy.io.mmread(str(tmp_path / "lam.mtx")).ravel().astype(lam.dtype), lam)
+    with pytest.raises(api.LobpcgB200Error):
+        api.write_mtx(tmp_path / "no_such_dir" / "x.mtx", a)

@@ -4,6 +4,7 @@ known-answer tests, the CPU oracle and analytic spectra.
 
 Parity protocol: same X0, k >= 2 nev, compare converged counts, eigenvalues to 1e-10
 relative (1e-4 float), residual norms <= tol; never iteration counts."""
+import ctypes as C
 import json
 import subprocess
 from pathlib import Path
@@ -212,6 +213,81 @@ def test_builtin_dense_operator(ctx, dt):
     w = np.linalg.eigvalsh(A.astype(np.complex128 if np.dtype(dt).kind == "c" else np.float64))[:5]
     assert r["converged"] == 5
     assert relerr(r["eig"][:5], w) < (1e-3 if single else 1e-9)
+
+
+def test_device_callback_operator_matches_builtin():
+    """lb2_op_device: the caller's own block operator on device pointers (here it forwards to the stencil kernel through
+    the kernel-level ABI).  Same passes and eigenvalues as the built-in operator, block applies (not column by column),
+    usable as the inner operator of the polynomial preconditioner, and its matvec works on host vectors."""
+    g = (20, 18, 16)
+    n = g[0] * g[1] * g[2]
+    inner = api.stencil_op(g, np.float64)
+    L = api.lib()
+    calls = []
+
+    def fn(nc, X, ldx, Y, ldy, stream):
+        calls.append(nc)
+        return L.lb2_op_apply(L.lb2_default_ctx(), inner.handle, b"d", nc, X, ldx, Y, ldy)
+
+    A = api.device_op(n, np.float64, fn, spec_hi=12.0)
+    X0 = pr.initial_block(n, 12, 5)
+    r_dev = api.lobpcg(A, X0, 6, 1e-8, 2000)
+    ncalls = len(calls)
+    r_ref = api.lobpcg(inner, X0, 6, 1e-8, 2000)
+    assert r_dev["converged"] == r_ref["converged"] == 6
+    assert r_dev["iter"] == r_ref["iter"]
+    assert np.array_equal(r_dev["eig"], r_ref["eig"])
+    assert max(calls) >= 12 and ncalls < 4 * (r_dev["iter"] + 20)
+    assert relerr(r_dev["eig"][:6], pr.laplacian_eigs(g, 6)) < 1e-9
+    # as the inner operator of T = p(A) (unfused Chebyshev steps through the callback)
+    T = api.chebyshev_op(A, 8, 0.3, 12.0)
+    r_pre = api.lobpcg(A, X0, 6, 1e-8, 2000, T=T)
+    assert r_pre["converged"] == 6 and r_pre["iter"] < r_dev["iter"] // 2
+    assert relerr(r_pre["eig"][:6], r_ref["eig"][:6]) < 1e-10
+    # host-vector matvec of the returned LinearOperator (linop_apply in the reference's tests)
+    st = C.cast(A.handle, C.POINTER(api.LinOpStruct)).contents
+    MV = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
+    x = np.random.default_rng(4).standard_normal(n)
+    y = np.zeros(n)
+    C.cast(st.matvec, MV)(A.handle, x.ctypes.data, y.ctypes.data)
+    rp, c, v = pr.laplacian_csr(g)
+    import scipy.sparse as sp
+    assert np.abs(y - sp.csr_matrix((v, c, rp), shape=(n, n)) @ x).max() < 1e-12
+    # a failing callback aborts the solve without touching the outputs
+    bad = api.device_op(n, np.float64, lambda *a: 7)
+    r_bad = api.lobpcg(bad, X0, 6, 1e-8, 50)
+    assert r_bad["converged"] == 0
+
+
+@pytest.mark.parametrize("side_stream", [False, True])
+def test_torch_wrapper_and_torch_operator(side_stream):
+    """lobpcg_b200.torch_api: CUDA tensors in and out on torch's current stream (legacy default or a side stream);
+    a torch function as the block operator (diag(1..n), the reference's soft-locking case tests/test_lobpcg.c:455-500)."""
+    import torch
+    from lobpcg_b200 import torch_api as ta
+    g = (20, 18, 16)
+    n = g[0] * g[1] * g[2]
+    A = api.stencil_op(g, np.float64)
+    X0 = pr.initial_block(n, 12, 5)
+    ref = api.lobpcg(A, X0, 6, 1e-8, 2000)
+    stream = torch.cuda.Stream() if side_stream else torch.cuda.current_stream()
+    with torch.cuda.stream(stream):
+        X0t = torch.from_numpy(np.ascontiguousarray(X0)).cuda()          # row-major (n, k): copied once
+        eig, X, info = ta.lobpcg(A, X0t, 6, 1e-8, 2000)
+        assert X.is_cuda and X.shape == (n, 12) and X.stride() == (1, n)
+        assert info["converged"] == 6 and info["iter"] == ref["iter"]
+        assert np.array_equal(eig.cpu().numpy(), ref["eig"])
+        assert np.array_equal(X.cpu().numpy(), ref["X"])
+        # eigenvectors are usable by torch right away: residual of the first pair through torch ops
+        d = torch.arange(1, 601, dtype=torch.float64, device="cuda")
+        D = ta.torch_op(600, torch.float64, lambda Xb, Yb: torch.mul(Xb, d[:, None], out=Yb), spec_hi=600.0)
+        Z0 = torch.from_numpy(pr.initial_block(600, 6, 9)).cuda()
+        eig2, Z, info2 = ta.lobpcg(D, Z0, 3, 1e-8, 3000)
+        assert info2["converged"] == 3
+        assert np.allclose(eig2.cpu().numpy()[:3], [1.0, 2.0, 3.0], atol=1e-8)
+        r = d[:, None] * Z[:, :3] - Z[:, :3] * eig2[:3]
+        assert float(r.norm(dim=0).max()) < 1e-4
+    torch.cuda.synchronize()
 
 
 def test_matrix_market_ingest(ctx, tmp_path):
