@@ -87,6 +87,8 @@ void *lb2_op_chebyshev(char prefix, const void *inner_linop, int degree, double 
 /* same polynomial, evaluated in float / complex float inside a double / complex double solve (prefix 'd' / 'z', built-in
  * stencil inner operator; otherwise identical to lb2_op_chebyshev): half the HBM traffic per preconditioner apply */
 void *lb2_op_chebyshev_mixed(char prefix, const void *inner_linop, int degree, double lo, double hi);
+/* upper bound of the spectrum recorded at construction (Gershgorin); 0 = unknown, -1 = not a built-in operator */
+double lb2_op_spec_hi(const void *linop);
 void lb2_op_destroy(void *linop);
 /* Y = Op X on device block vectors (n x nc) */
 int lb2_op_apply(lb2_ctx *ctx, const void *linop, char prefix, int nc, const void *X, int64_t ldx, void *Y,
@@ -159,6 +161,14 @@ void *lb2_op_stencil_slab(char prefix, int64_t gx, int64_t gy, int64_t gz_local,
                           double cdiag, double coff, const void *potential_local_host);
 /* the solver keeps every tall block in one device arena; neighbours map it through CUDA IPC and the stencil
  * kernel reads their boundary planes directly over NVLink */
+/* row block [row0, row0 + n_local) of a CSR matrix (GLOBAL column indices; rowptr_local starts at 0): equal blocks on every
+ * rank, couplings at most into the two neighbouring blocks, whose rows the kernel reads in place from the neighbours'
+ * arenas (lb2_solver_set_peers).  Its spectrum bound covers the local rows only. */
+void *lb2_op_csr_slab(char prefix, int64_t n_global, int64_t row0, int64_t n_local, const int64_t *rowptr_local,
+                      const int32_t *col_global, const void *val_host);
+/* neighbour data for a stand-alone lb2_op_apply of a row-block operator: boundary planes (stencil slab) or whole blocks
+ * (CSR row block) below / above, column stride ld; NULL = no neighbour.  A solver sets these itself from the peer arenas. */
+int lb2_op_set_halo(void *linop, const void *lo, const void *hi, int64_t ld);
 int lb2_solver_arena(lb2_solver *s, void **ptr, size_t *bytes);
 int lb2_solver_set_peers(lb2_solver *s, const void *lo_arena, const void *hi_arena);
 int lb2_comm_unique_id(void *out128, const char *nccl_lib_path);   /* rank 0; broadcast by the launcher */

@@ -79,6 +79,11 @@ def _declare(L):
     L.lb2_op_dense.restype = vp
     L.lb2_op_dense.argtypes = [C.c_char, i64, vp]
     L.lb2_write_mtx.argtypes = [C.c_char_p, C.c_char, i64, i64, vp, i64]
+    L.lb2_op_set_halo.argtypes = [vp, vp, vp, i64]
+    L.lb2_op_spec_hi.restype = dbl
+    L.lb2_op_spec_hi.argtypes = [vp]
+    L.lb2_op_csr_slab.restype = vp
+    L.lb2_op_csr_slab.argtypes = [C.c_char, i64, i64, i64, vp, vp, vp]
     L.lb2_op_device.restype = vp
     L.lb2_op_device.argtypes = [C.c_char, i64, vp, vp, dbl]
     L.lb2_op_chebyshev.restype = vp
@@ -337,6 +342,29 @@ def stencil_slab_op(grid, z0, gz_local, dtype, cdiag=None, coff=-1.0, potential_
     h = lib().lb2_op_stencil_slab(p.encode(), gx, gy, gz_local, gz, z0, cdiag, coff,
                                   pot.ctypes.data if pot is not None else None)
     return LinOp(h, p, gx * gy * gz_local)
+
+
+def csr_slab_op(n_global: int, row0: int, rowptr_local, col_global, val) -> LinOp:
+    """Row block [row0, row0 + n_local) of a CSR matrix for a row-partitioned run (lb2_op_csr_slab): ``rowptr_local``
+    starts at 0, ``col_global`` holds global column indices."""
+    val = np.ascontiguousarray(val)
+    p = PREFIX[val.dtype]
+    rp = np.ascontiguousarray(rowptr_local, dtype=np.int64)
+    col = np.ascontiguousarray(col_global, dtype=np.int32)
+    n_local = len(rp) - 1
+    h = lib().lb2_op_csr_slab(p.encode(), int(n_global), int(row0), n_local, rp.ctypes.data, col.ctypes.data,
+                              val.ctypes.data)
+    return LinOp(h, p, n_local)
+
+
+def set_halo(op: LinOp, lo, hi, ld: int):
+    """Neighbour data (device pointers or None) for a stand-alone apply of a row-block operator (lb2_op_set_halo)."""
+    _ck(lib().lb2_op_set_halo(op.handle, lo, hi, int(ld)), "lb2_op_set_halo")
+
+
+def spec_hi(op: LinOp) -> float:
+    """Upper bound of the operator's spectrum recorded at construction (0 = unknown)."""
+    return float(lib().lb2_op_spec_hi(op.handle))
 
 
 def stencil_halo_apply(ctx, grid_local, X: DeviceArray, halo_lo, halo_hi, halo_ld, cdiag=6.0, coff=-1.0) -> DeviceArray:

@@ -443,6 +443,49 @@ void* lb2_op_chebyshev_mixed(char prefix, const void* inner_linop, int degree, d
 }
 
 // CSR with 32-bit row pointers (the other common host layout)
+// Row block [row0, row0 + n_local) of an n_global x n_global CSR matrix for a row-partitioned run ("same row
+// blocks, column indices remapped to local+halo").  rowptr_local starts at 0; col_global holds GLOBAL column indices.
+// Equal blocks on every rank (n_local the same everywhere: the neighbour's block is addressed at the same arena offset)
+// and couplings that reach at most into the two neighbouring blocks.  Columns are stored relative to row0; the kernel reads
+// rows of the neighbouring blocks in place from the neighbours' arenas.  spec_hi is the Gershgorin bound of the LOCAL
+// rows: pass the maximum over ranks explicitly to lb2_op_chebyshev.
+void* lb2_op_csr_slab(char prefix, int64_t n_global, int64_t row0, int64_t n_local, const int64_t* rowptr_local,
+                      const int32_t* col_global, const void* val) {
+  if (!valid_prefix(prefix) || n_local < 1 || n_global < n_local || row0 < 0 || row0 + n_local > n_global ||
+      n_global % n_local != 0 || row0 % n_local != 0 || !rowptr_local || !col_global || !val || rowptr_local[0] != 0)
+    return nullptr;
+  if (!lb2_default_ctx()) return nullptr;
+  const int64_t nnz = rowptr_local[n_local];
+  std::vector<int32_t> col((size_t)nnz);
+  const int64_t lo = std::max<int64_t>(row0 - n_local, 0), hi = std::min<int64_t>(row0 + 2 * n_local, n_global);
+  for (int64_t q = 0; q < nnz; q++) {
+    const int64_t c = col_global[q];
+    if (c < lo || c >= hi) {
+      fprintf(stderr, "lobpcg_b200: lb2_op_csr_slab: column %lld of the row block at %lld reaches beyond the neighbouring "
+                      "blocks [%lld, %lld)\n", (long long)c, (long long)row0, (long long)lo, (long long)hi);
+      return nullptr;
+    }
+    col[(size_t)q] = (int32_t)(c - row0);
+  }
+  BuiltinOp* b = new_builtin(OP_CSR, prefix, n_local);
+  b->n_global = n_global;
+  b->row0 = row0;
+  b->nnz = nnz;
+  b->rowptr = (int64_t*)upload(rowptr_local, sizeof(int64_t) * (size_t)(n_local + 1));
+  b->col = (int32_t*)upload(col.data(), sizeof(int32_t) * (size_t)nnz);
+  b->val = upload(val, scalar_size(prefix) * (size_t)nnz);
+  if (!b->rowptr || !b->col || !b->val) {
+    LinOpCtxRaw* lc = (LinOpCtxRaw*)calloc(1, sizeof(LinOpCtxRaw));
+    lc->data = b;
+    builtin_cleanup(lc);
+    return nullptr;
+  }
+  b->spec_hi = csr_gershgorin(prefix, n_local, rowptr_local, val);
+  LinOpRaw* op = wrap_builtin(b);
+  op->rows = op->cols = (uint64_t)n_global;
+  return op;
+}
+
 void* lb2_op_csr32(char prefix, int64_t n, const int32_t* rowptr_host, const int32_t* col_host, const void* val_host) {
   if (n < 1 || !rowptr_host) return nullptr;
   std::vector<int64_t> rp((size_t)n + 1);
@@ -584,6 +627,23 @@ void* lb2_op_device(char prefix, int64_t n, lb2_matmat_fn fn, void* user, double
   b->dev_user = user;
   b->spec_hi = spec_hi > 0 ? spec_hi : 0.0;
   return wrap_builtin(b);
+}
+
+// neighbour blocks for a stand-alone lb2_op_apply of a row-block operator (inside a solver they are set per apply from
+// the peer arenas): stencil slabs take the boundary PLANES below / above (column stride ld), CSR row blocks take the
+// neighbours' whole BLOCKS (column stride ld = their row count)
+int lb2_op_set_halo(void* linop, const void* lo, const void* hi, int64_t ld) {
+  const BuiltinOp* cb = builtin_of((const LinOpRaw*)linop);
+  if (!cb || !(cb->kind == OP_STENCIL || cb->kind == OP_CSR)) return -1;
+  BuiltinOp* b = const_cast<BuiltinOp*>(cb);
+  b->halo_lo = lo; b->halo_hi = hi; b->halo_ld = ld;
+  return 0;
+}
+
+// upper bound of the spectrum recorded at construction (Gershgorin; 0 = unknown, -1 = not a built-in operator)
+double lb2_op_spec_hi(const void* linop) {
+  const BuiltinOp* b = builtin_of((const LinOpRaw*)linop);
+  return b ? b->spec_hi : -1.0;
 }
 
 void lb2_op_destroy(void* linop) {

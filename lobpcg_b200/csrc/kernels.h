@@ -97,9 +97,16 @@ struct ChebEpilogue {
 template <typename T>
 int spmm_stencil_cheb(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* Din, int64_t ldd, T* Yacc, int64_t ldy,
                       const ChebEpilogue<T>& ep);
+// neighbour blocks of a row-partitioned CSR apply: the same block vector in the lower / upper neighbour's arena (device
+// pointers mapped through CUDA IPC, column stride = that rank's local row count); null where there is no neighbour
+struct CsrHalo {
+  const void* lo = nullptr;
+  const void* hi = nullptr;
+  int64_t ld_lo = 0, ld_hi = 0;
+};
 template <typename T>
 int spmm_csr(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val, int nc,
-             const T* X, int64_t ldx, T* Y, int64_t ldy);
+             const T* X, int64_t ldx, T* Y, int64_t ldy, const CsrHalo* halo = nullptr);
 template <typename T>
 int spmm_diag(lb2_ctx* ctx, int64_t n, const real_t<T>* d, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy);
 

@@ -78,6 +78,11 @@ int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t 
     case OP_BDG:
       return spmm_stencil<T>(ctx, stencil_desc(b), nc, X, ldx, Y, ldy);
     case OP_CSR:
+      if (b->n != b->n_global) {   // row block of a partitioned matrix: neighbour blocks set by Solver::localize
+        CsrHalo h;
+        h.lo = b->halo_lo; h.hi = b->halo_hi; h.ld_lo = h.ld_hi = b->halo_ld;
+        return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy, &h);
+      }
       return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy);
     case OP_DIAG:
       return spmm_diag<T>(ctx, b->n, (const real_t<T>*)b->diag, nc, X, ldx, Y, ldy);
@@ -351,7 +356,7 @@ int Solver<T>::localize(const BuiltinOp*& b, BuiltinOp& local, const T* X) {
 }
 template <typename T>
 int Solver<T>::localize_bytes(const BuiltinOp*& b, BuiltinOp& local, const void* X, size_t elem) {
-  if (!(ctx->comm && b->n != b->n_global && b->kind == OP_STENCIL)) return 0;
+  if (!(ctx->comm && b->n != b->n_global && (b->kind == OP_STENCIL || b->kind == OP_CSR))) return 0;
   tm.begin(PH_COMM);
   int rcb = allreduce_sum(ctx, Scal + 12, 1, kDouble);
   tm.end();
@@ -361,6 +366,13 @@ int Solver<T>::localize_bytes(const BuiltinOp*& b, BuiltinOp& local, const void*
   if (off >= arena_bytes) {
     fprintf(stderr, "lobpcg_b200: partitioned operator applied to a buffer outside the solver arena\n");
     return -1;
+  }
+  if (b->kind == OP_CSR) {   // the neighbour's whole block (column 0, row 0); the kernel picks rows by column index
+    local.halo_lo = peer_lo ? (const void*)(peer_lo + off) : nullptr;
+    local.halo_hi = peer_hi ? (const void*)(peer_hi + off) : nullptr;
+    local.halo_ld = n;
+    b = &local;
+    return 0;
   }
   const int64_t plane = b->gx * b->gy;
   local.halo_lo = peer_lo ? (const void*)(peer_lo + off + (size_t)((b->gz - 1) * plane) * elem) : nullptr;

@@ -294,11 +294,15 @@ int spmm_stencil_cheb(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* Din, 
 // not by the (col,val) stream — a shared-memory staged variant of the matrix stream measured no faster.  Getting
 // past this needs a 3-D blocked row order.  Matrices that ARE Dirichlet stencils never get here (capi.cu: detect_stencil).
 // =====================================================================================================
-template <typename T, int NCOL, int RPT>
+// HALO (row-partitioned matrix): column indices are relative to the first local row; an index below 0 is
+// row (index + n_lo) of the lower neighbour's block, an index >= n is row (index - n) of the upper neighbour's block, and
+// both are read in place from the neighbour's arena over NVLink (same idea as the stencil's halo planes: no exchange
+// pass, no gathered copy).
+template <typename T, int NCOL, int RPT, bool HALO>
 __global__ void __launch_bounds__(256)
     csr_kernel(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                const T* __restrict__ val, int nc, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y,
-               int64_t ldy) {
+               int64_t ldy, CsrHalo halo) {
   // a CTA owns 256 * RPT consecutive rows (thread t: rows base + t + 256 i).  RPT > 1 was measured (r01: 1/2/4/8 rows per
   // thread x 4/8/16/32 columns, 128^3 7-point matrix): no effect, the kernel stays at ~49 % of HBM with 8 or 16 columns
   // per thread — it is bound by L2 sector reads (5 gathered lines per output), not by L1 reuse inside the CTA.
@@ -313,7 +317,19 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int c = 0; c < NCOL; c++) acc[c] = zero<T>();
     const int64_t p0 = rowptr[row], p1 = rowptr[row + 1];
-    if (ncol == NCOL) {
+    if constexpr (HALO) {
+      const T* xlo = (const T*)halo.lo + (int64_t)c0 * halo.ld_lo + halo.ld_lo;   // row -1 of the local block = last row below
+      const T* xhi = (const T*)halo.hi + (int64_t)c0 * halo.ld_hi - n;
+      for (int64_t p = p0; p < p1; p++) {
+        const int64_t cj = col[p];
+        const T v = val[p];
+        const T* src = cj < 0 ? xlo + cj : (cj >= n ? xhi + cj : xb + cj);
+        const int64_t ld = cj < 0 ? halo.ld_lo : (cj >= n ? halo.ld_hi : ldx);
+#pragma unroll
+        for (int c = 0; c < NCOL; c++)
+          if (c < ncol) fma_(acc[c], v, src[(int64_t)c * ld]);
+      }
+    } else if (ncol == NCOL) {
       for (int64_t p = p0; p < p1; p++) {
         const int64_t cj = col[p];
         const T v = val[p];
@@ -338,12 +354,18 @@ __global__ void __launch_bounds__(256)
 
 template <typename T>
 int spmm_csr(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val, int nc,
-             const T* X, int64_t ldx, T* Y, int64_t ldy) {
+             const T* X, int64_t ldx, T* Y, int64_t ldy, const CsrHalo* halo) {
   if (n <= 0 || nc <= 0) return 0;
   int ncol = ctx->spmm_cols ? ctx->spmm_cols : 16;
+  const CsrHalo h = halo ? *halo : CsrHalo{};
 #define LB2_CSR2(NC, RP)                                                                                        \
-  csr_kernel<T, NC, RP><<<dim3((unsigned)((n + 256 * RP - 1) / (256 * RP)), (nc + NC - 1) / NC), 256, 0, ctx->stream>>>( \
-      n, rowptr, col, val, nc, X, ldx, Y, ldy)
+  do {                                                                                                          \
+    const dim3 grid((unsigned)((n + 256 * RP - 1) / (256 * RP)), (nc + NC - 1) / NC);                           \
+    if (halo)                                                                                                   \
+      csr_kernel<T, NC, RP, true><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, nc, X, ldx, Y, ldy, h);   \
+    else                                                                                                        \
+      csr_kernel<T, NC, RP, false><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, nc, X, ldx, Y, ldy, h);  \
+  } while (0)
 #define LB2_CSR(NC) LB2_CSR2(NC, 1)
   if (nc <= 4 || ncol <= 4) LB2_CSR(4);
   else if (nc <= 8 || ncol <= 8) LB2_CSR(8);
@@ -384,7 +406,7 @@ int spmm_diag(lb2_ctx* ctx, int64_t n, const real_t<T>* d, int nc, const T* X, i
 #define LB2_INST(T)                                                                                       \
   template int spmm_stencil<T>(lb2_ctx*, const StencilDesc&, int, const T*, int64_t, T*, int64_t);         \
   template int spmm_stencil_cheb<T>(lb2_ctx*, const StencilDesc&, int, const T*, int64_t, T*, int64_t, const ChebEpilogue<T>&); \
-  template int spmm_csr<T>(lb2_ctx*, int64_t, const int64_t*, const int32_t*, const T*, int, const T*, int64_t, T*, int64_t); \
+  template int spmm_csr<T>(lb2_ctx*, int64_t, const int64_t*, const int32_t*, const T*, int, const T*, int64_t, T*, int64_t, const CsrHalo*); \
   template int spmm_diag<T>(lb2_ctx*, int64_t, const real_t<T>*, int, const T*, int64_t, T*, int64_t);
 LB2_INST(float)
 LB2_INST(double)

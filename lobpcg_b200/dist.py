@@ -128,6 +128,34 @@ def partitioned_stencil(ctx, part: SlabPartition, dtype, k: int, potential=None)
     return api.stencil_slab_op((part.gx, part.gy, part.gz), part.z0, part.gz_local, dtype, potential_local=pot)
 
 
+def csr_row_block(rowptr, col, val, row0: int, n_local: int):
+    """Rows [row0, row0 + n_local) of a CSR matrix: (rowptr_local starting at 0, global column indices, values)."""
+    rowptr = np.asarray(rowptr)
+    p0, p1 = int(rowptr[row0]), int(rowptr[row0 + n_local])
+    return (rowptr[row0:row0 + n_local + 1] - p0).astype(np.int64), np.asarray(col)[p0:p1], np.asarray(val)[p0:p1]
+
+
+def partitioned_csr(part, rowptr, col, val):
+    """This rank's row block of a global CSR matrix as a device operator (``part``: anything with n_global, row0,
+    n_local — e.g. SlabPartition).  Couplings may reach at most into the two neighbouring row blocks."""
+    from . import api
+    rp, c, v = csr_row_block(rowptr, col, val, part.row0, part.n_local)
+    return api.csr_slab_op(part.n_global, part.row0, rp, c, v)
+
+
+def global_spec_hi(op) -> float:
+    """Maximum over ranks of the operators' local spectrum bounds (the window of a polynomial preconditioner must be
+    the same on every rank)."""
+    import torch
+    import torch.distributed as td
+    from . import api
+    t = torch.tensor([api.spec_hi(op)], dtype=torch.float64)
+    if td.get_backend() == "nccl":
+        t = t.cuda()
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return float(t.item())
+
+
 def attach(solver, part: SlabPartition):
     """Allocate the solver arena, exchange its CUDA-IPC handle with the z-neighbours and register the mapped
     peer bases.  Collective over all ranks; call before solver.init()."""

@@ -37,6 +37,34 @@ def test_partitioned_rows_reassemble_the_global_block():
     assert np.array_equal(np.vstack(pieces), X)
 
 
+def test_csr_row_blocks_with_relative_columns_reassemble_the_global_product():
+    """dist.csr_row_block + the addressing rule of the partitioned CSR kernel (csrc/spmm.cu, HALO): a column index
+    relative to the block's first row that is negative / >= n_local is a row of the lower / upper neighbour's block."""
+    import scipy.sparse as sp
+    g, world = (6, 5, 8), 4
+    rp, c, v = pr.laplacian_csr(g, potential=pr.harmonic_potential(g, 0.4))
+    n = len(rp) - 1
+    M = sp.csr_matrix((v, c, rp), shape=(n, n))
+    X = pr.initial_block(n, 3, 2)
+    out = []
+    for r in range(world):
+        part = dist.SlabPartition(*g, world, r)
+        nl = part.n_local
+        rpl, cg, vl = dist.csr_row_block(rp, c, v, part.row0, nl)
+        assert rpl[0] == 0 and rpl[-1] == len(cg) == len(vl)
+        rel = cg.astype(np.int64) - part.row0
+        assert rel.min() >= (-nl if r > 0 else 0) and rel.max() < (2 * nl if r + 1 < world else nl)
+        blocks = {-1: X[part.row0 - nl:part.row0] if r > 0 else None, 0: X[part.rows()],
+                  1: X[part.row0 + nl:part.row0 + 2 * nl] if r + 1 < world else None}
+        Y = np.zeros((nl, 3))
+        for i in range(nl):
+            for q in range(rpl[i], rpl[i + 1]):
+                side = -1 if rel[q] < 0 else (1 if rel[q] >= nl else 0)
+                Y[i] += vl[q] * blocks[side][rel[q] - side * nl]
+        out.append(Y)
+    assert np.allclose(np.vstack(out), M @ X, atol=1e-13)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as td

@@ -386,6 +386,47 @@ def test_stencil_z_slabs_with_halo_planes_reproduce_the_global_operator(ctx, dt)
     close(np.vstack(out), ref, rtol(dt))
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+def test_csr_row_blocks_with_neighbour_blocks_reproduce_the_global_operator(ctx, dt):
+    """lb2_op_csr_slab: the row-partitioned CSR operator, emulated on one GPU — every row block is its own
+    operator whose kernel reads rows of the neighbouring blocks in place (on an NVSwitch box: the neighbours' arenas).
+    Random banded matrix (couplings up to one block away), ragged rows, an empty row, all column-group widths."""
+    import scipy.sparse as sp
+    from lobpcg_b200 import dist
+    rng = np.random.default_rng(21)
+    world, nb, nc = 4, 700, 21
+    n = world * nb
+    rows, cols = [], []
+    for i in range(n):
+        if i == 1234:
+            continue                                     # empty row
+        w = int(rng.integers(1, 12))
+        cand = np.arange(max(0, (i // nb - 1) * nb), min(n, (i // nb + 2) * nb))    # own block and both neighbours
+        rows += [i] * w
+        cols += list(rng.choice(cand, size=w, replace=False))
+    vals = rand(rng, (len(rows),), dt)
+    M = sp.csr_matrix((vals, (rows, cols)), shape=(n, n)); M.sort_indices()
+    X = rand(rng, (n, nc), dt)
+    ref = M @ X
+    blocks = [api.DeviceArray.from_numpy(ctx, np.asfortranarray(X[r * nb:(r + 1) * nb])) for r in range(world)]
+    for spmm_cols in (0, 4, 8, 32):
+        ctx.set_option("spmm_cols", spmm_cols)
+        out = []
+        for r in range(world):
+            rp, c, v = dist.csr_row_block(M.indptr, M.indices, M.data, r * nb, nb)
+            op = api.csr_slab_op(n, r * nb, rp, c, v)
+            api.set_halo(op, blocks[r - 1].ptr if r > 0 else None, blocks[r + 1].ptr if r + 1 < world else None, nb)
+            out.append(op.apply(ctx, blocks[r]).numpy(ctx))
+        close(np.vstack(out), ref, 10 * rtol(dt))
+    ctx.set_option("spmm_cols", 0)
+    # a coupling beyond the neighbouring blocks is refused at construction
+    far = sp.csr_matrix(([1.0], ([0], [n - 1])), shape=(n, n)) + sp.eye(n, format="csr")
+    far = far.tocsr().astype(dt)
+    rp, c, v = dist.csr_row_block(far.indptr, far.indices, far.data, 0, nb)
+    with pytest.raises(api.LobpcgB200Error):
+        api.csr_slab_op(n, 0, rp, c, v)
+
+
 def test_csr_stencil_detection_handles_variable_diagonal_and_rejects_near_misses(ctx):
     """detect_stencil (capi.cu): a CSR matrix that IS a Dirichlet stencil with an arbitrary diagonal takes the
     stencil kernel; one changed off-diagonal value or a missing entry must fall back to the general kernel — the
