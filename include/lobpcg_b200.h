@@ -166,6 +166,9 @@ void *lb2_op_stencil_slab(char prefix, int64_t gx, int64_t gy, int64_t gz_local,
  * arenas (lb2_solver_set_peers).  Its spectrum bound covers the local rows only. */
 void *lb2_op_csr_slab(char prefix, int64_t n_global, int64_t row0, int64_t n_local, const int64_t *rowptr_local,
                       const int32_t *col_global, const void *val_host);
+/* rank-local part of the BdG operator: both fields are split by the same z-slabs, local rows = [u slab ; v slab] */
+void *lb2_op_bdg_slab(char prefix, int64_t gx, int64_t gy, int64_t gz_local, int64_t gz_global, int64_t z0, double cdiag,
+                      double coff, double shift, double d_re, double d_im);
 /* neighbour data for a stand-alone lb2_op_apply of a row-block operator: boundary planes (stencil slab) or whole blocks
  * (CSR row block) below / above, column stride ld; NULL = no neighbour.  A solver sets these itself from the peer arenas. */
 int lb2_op_set_halo(void *linop, const void *lo, const void *hi, int64_t ld);

@@ -80,6 +80,8 @@ def _declare(L):
     L.lb2_op_dense.argtypes = [C.c_char, i64, vp]
     L.lb2_write_mtx.argtypes = [C.c_char_p, C.c_char, i64, i64, vp, i64]
     L.lb2_op_set_halo.argtypes = [vp, vp, vp, i64]
+    L.lb2_op_bdg_slab.restype = vp
+    L.lb2_op_bdg_slab.argtypes = [C.c_char, i64, i64, i64, i64, i64, dbl, dbl, dbl, dbl, dbl]
     L.lb2_op_spec_hi.restype = dbl
     L.lb2_op_spec_hi.argtypes = [vp]
     L.lb2_op_csr_slab.restype = vp
@@ -342,6 +344,15 @@ def stencil_slab_op(grid, z0, gz_local, dtype, cdiag=None, coff=-1.0, potential_
     h = lib().lb2_op_stencil_slab(p.encode(), gx, gy, gz_local, gz, z0, cdiag, coff,
                                   pot.ctypes.data if pot is not None else None)
     return LinOp(h, p, gx * gy * gz_local)
+
+
+def bdg_slab_op(grid, z0, gz_local, dtype, shift, d, cdiag=6.0, coff=-1.0) -> LinOp:
+    """Rank-local part of the BdG operator (lb2_op_bdg_slab): local rows = [u z-slab ; v z-slab]."""
+    p = PREFIX[np.dtype(dtype)]
+    gx, gy, gz = (int(v) for v in grid)
+    h = lib().lb2_op_bdg_slab(p.encode(), gx, gy, int(gz_local), gz, int(z0), cdiag, coff, shift,
+                              float(np.real(d)), float(np.imag(d)))
+    return LinOp(h, p, 2 * gx * gy * int(gz_local))
 
 
 def csr_slab_op(n_global: int, row0: int, rowptr_local, col_global, val) -> LinOp:

@@ -345,6 +345,20 @@ void* lb2_op_bdg(char prefix, int64_t gx, int64_t gy, int64_t gz, double cdiag, 
   return wrap_builtin(b);
 }
 
+// rank-local part of the BdG operator for a row-partitioned run ("partition each half identically so the block
+// coupling is rank-local"): local rows = [u(z-slab) ; v(z-slab)], 2 gx gy gz_local rows
+void* lb2_op_bdg_slab(char prefix, int64_t gx, int64_t gy, int64_t gz_local, int64_t gz_global, int64_t z0, double cdiag,
+                      double coff, double shift, double d_re, double d_im) {
+  if (gz_local < 1 || gz_global < gz_local || z0 < 0 || z0 + gz_local > gz_global) return nullptr;
+  LinOpRaw* op = (LinOpRaw*)lb2_op_bdg(prefix, gx, gy, gz_local, cdiag, coff, shift, d_re, d_im);
+  if (!op) return nullptr;
+  BuiltinOp* b = (BuiltinOp*)op->ctx->data;
+  b->n_global = 2 * gx * gy * gz_global;
+  b->row0 = gx * gy * z0;   // first row of the slab inside EACH field
+  op->rows = op->cols = (uint64_t)b->n_global;
+  return op;
+}
+
 static double csr_gershgorin(char prefix, int64_t n, const int64_t* rp, const void* val) {
   double hi = 0;
   for (int64_t i = 0; i < n; i++) {
@@ -634,7 +648,7 @@ void* lb2_op_device(char prefix, int64_t n, lb2_matmat_fn fn, void* user, double
 // neighbours' whole BLOCKS (column stride ld = their row count)
 int lb2_op_set_halo(void* linop, const void* lo, const void* hi, int64_t ld) {
   const BuiltinOp* cb = builtin_of((const LinOpRaw*)linop);
-  if (!cb || !(cb->kind == OP_STENCIL || cb->kind == OP_CSR)) return -1;
+  if (!cb || !(cb->kind == OP_STENCIL || cb->kind == OP_CSR || cb->kind == OP_BDG)) return -1;
   BuiltinOp* b = const_cast<BuiltinOp*>(cb);
   b->halo_lo = lo; b->halo_hi = hi; b->halo_ld = ld;
   return 0;

@@ -227,6 +227,15 @@ class Solver : public SolverBase {
   bool indef;
   Timers tm;
   int64_t n = 0, ng = 0, row0 = 0;
+  int nseg = 1;   // row-partitioned BdG operator: local rows are two runs (the u and the v field), each a z-slab of its field
+  // local run s = rows [s n/nseg, (s+1) n/nseg) of this rank = global rows seg_global(s) + [0, n/nseg)
+  int64_t seg_len() const { return n / nseg; }
+  int64_t seg_global(int s) const { return (int64_t)s * (ng / nseg) + row0; }
+  int fill_rows(T* X, int nc, uint64_t seed) {   // uniform block with the GLOBAL counters of this rank's rows
+    for (int sg = 0; sg < nseg; sg++)
+      LB2_TRY(fill_uniform<T>(ctx, seg_len(), nc, X + sg * seg_len(), n, seed, ng, seg_global(sg)));
+    return 0;
+  }
   int k = 0, nev = 0;
   void* arena = nullptr;
   size_t arena_bytes = 0;
@@ -356,7 +365,7 @@ int Solver<T>::localize(const BuiltinOp*& b, BuiltinOp& local, const T* X) {
 }
 template <typename T>
 int Solver<T>::localize_bytes(const BuiltinOp*& b, BuiltinOp& local, const void* X, size_t elem) {
-  if (!(ctx->comm && b->n != b->n_global && (b->kind == OP_STENCIL || b->kind == OP_CSR))) return 0;
+  if (!(ctx->comm && b->n != b->n_global && (b->kind == OP_STENCIL || b->kind == OP_CSR || b->kind == OP_BDG))) return 0;
   tm.begin(PH_COMM);
   int rcb = allreduce_sum(ctx, Scal + 12, 1, kDouble);
   tm.end();
@@ -536,7 +545,7 @@ template <typename T>
 int Solver<T>::estimate_norm(const LinOpRaw* op, uint64_t seed, R* out) {
   T* x = wA;
   T* y = wB;
-  LB2_TRY(fill_uniform<T>(ctx, n, 1, x, n, seed, ng, row0));
+  LB2_TRY(fill_rows(x, 1, seed));
   LB2_TRY(sumsq_total(1, x, Scal));
   LB2_TRY(normalize_by<T>(ctx, n, x, Scal));
   for (int it = 0; it < 10; it++) {
@@ -997,6 +1006,7 @@ int Solver<T>::prepare() {
   if (ba && ba->n != ba->n_global) {  // row-partitioned operator: local rows, equal slabs on every rank
     n = ba->n;
     row0 = ba->row0;
+    nseg = (ba->kind == OP_BDG) ? 2 : 1;
     if (!ctx->comm) {
       fprintf(stderr, "lobpcg: row-partitioned operator needs a communicator (lb2_ctx_attach_comm)\n");
       return 1;
@@ -1018,14 +1028,15 @@ int Solver<T>::init() {
   cur = 0;
   T* X = Xp();
   if (use_device_x0) {
-    LB2_TRY(fill_uniform<T>(ctx, n, k, X, n, device_seed, ng, row0));
+    LB2_TRY(fill_rows(X, k, device_seed));
   } else if (dev_x0) {
     LB2_CUDA_OK(cudaMemcpyAsync(X, dev_x0, sizeof(T) * (size_t)n * k, cudaMemcpyDeviceToDevice, ctx->stream));
   } else if (n == ng) {   // whole columns: one contiguous block, pipelined through pinned chunks (hostcopy.cu)
     LB2_TRY(host_copy(ctx, X, alg->S, sizeof(T) * (size_t)n * k, true));
   } else {
-    LB2_CUDA_OK(cudaMemcpy2DAsync(X, sizeof(T) * n, alg->S + row0, sizeof(T) * ng, sizeof(T) * n, k,
-                                  cudaMemcpyHostToDevice, ctx->stream));
+    for (int sg = 0; sg < nseg; sg++)
+      LB2_CUDA_OK(cudaMemcpy2DAsync(X + sg * seg_len(), sizeof(T) * n, alg->S + seg_global(sg), sizeof(T) * ng,
+                                    sizeof(T) * seg_len(), k, cudaMemcpyHostToDevice, ctx->stream));
   }
   LB2_TRY(estimate_norm(opA, 0xA5EEDULL, &ANorm));
   if (opB) LB2_TRY(estimate_norm(opB, 0xB5EEDULL, &BNorm));
@@ -1035,7 +1046,7 @@ int Solver<T>::init() {
   LB2_TRY(sumsq_total(k, X, Scal));
   LB2_TRY(d2h(hbuf, Scal, sizeof(R)));
   LB2_TRY(sync());
-  if (std::sqrt(hbuf[0]) < (R)EpsTol<T>::v) LB2_TRY(fill_uniform<T>(ctx, n, k, X, n, 0xC0FFEEULL, ng, row0));
+  if (std::sqrt(hbuf[0]) < (R)EpsTol<T>::v) LB2_TRY(fill_rows(X, k, 0xC0FFEEULL));
 
   if (indef) {
     // ilobpcg_impl.inc:100-113: B-orthonormalise X (svqb, no dropping), indefinite RR, X <- X Cx
@@ -1143,8 +1154,9 @@ int Solver<T>::finish() {
   } else if (n == ng) {
     LB2_TRY(host_copy(ctx, alg->S, X, sizeof(T) * (size_t)n * k, false));
   } else {
-    LB2_CUDA_OK(cudaMemcpy2DAsync(alg->S + row0, sizeof(T) * ng, X, sizeof(T) * n, sizeof(T) * n, k,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
+    for (int sg = 0; sg < nseg; sg++)
+      LB2_CUDA_OK(cudaMemcpy2DAsync(alg->S + seg_global(sg), sizeof(T) * ng, X + sg * seg_len(), sizeof(T) * n,
+                                    sizeof(T) * seg_len(), k, cudaMemcpyDeviceToHost, ctx->stream));
   }
   LB2_TRY(sync());
   for (int i = 0; i < k; i++) alg->eigVals[i] = hEig[i];

@@ -128,6 +128,20 @@ def partitioned_stencil(ctx, part: SlabPartition, dtype, k: int, potential=None)
     return api.stencil_slab_op((part.gx, part.gy, part.gz), part.z0, part.gz_local, dtype, potential_local=pot)
 
 
+def partitioned_bdg(part: SlabPartition, dtype, shift, d):
+    """This rank's part of the BdG operator A = [[K+shift, d], [conj d, K+shift]] (config C4): both fields are split by
+    the same z-slabs, so the local rows are [u slab ; v slab] and the block coupling stays rank-local."""
+    from . import api
+    return api.bdg_slab_op((part.gx, part.gy, part.gz), part.z0, part.gz_local, dtype, shift, d)
+
+
+def bdg_local_rows(part: SlabPartition) -> np.ndarray:
+    """Global row indices of this rank's local rows of a BdG block vector (u slab, then v slab)."""
+    m = part.n_global
+    return np.concatenate([np.arange(part.row0, part.row0 + part.n_local),
+                           m + np.arange(part.row0, part.row0 + part.n_local)])
+
+
 def csr_row_block(rowptr, col, val, row0: int, n_local: int):
     """Rows [row0, row0 + n_local) of a CSR matrix: (rowptr_local starting at 0, global column indices, values)."""
     rowptr = np.asarray(rowptr)

@@ -65,6 +65,15 @@ def test_csr_row_blocks_with_relative_columns_reassemble_the_global_product():
     assert np.allclose(np.vstack(out), M @ X, atol=1e-13)
 
 
+def test_bdg_local_rows_cover_both_fields_once():
+    g, world = (4, 3, 8), 4
+    m = int(np.prod(g))
+    rows = np.concatenate([dist.bdg_local_rows(dist.SlabPartition(*g, world, r)) for r in range(world)])
+    assert np.array_equal(np.sort(rows), np.arange(2 * m))
+    p1 = dist.SlabPartition(*g, world, 1)
+    assert dist.bdg_local_rows(p1)[0] == p1.row0 and dist.bdg_local_rows(p1)[p1.n_local] == m + p1.row0
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as td

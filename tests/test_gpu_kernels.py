@@ -334,6 +334,32 @@ def test_bdg_operator_matches_dense_blocks(ctx):
     close(got, ref, 1e-13)
 
 
+@pytest.mark.parametrize("dt", [np.complex128, np.float64])
+def test_bdg_slabs_with_neighbour_planes_reproduce_the_global_operator(ctx, dt):
+    """lb2_op_bdg_slab: the row-partitioned BdG operator, emulated on one GPU.  Both fields are split by the
+    same z-slabs, a rank holds [u slab ; v slab], the block coupling is local and each field reads its own boundary planes
+    from the neighbours' blocks."""
+    g, world, nc = (8, 6, 12), 3, 4
+    m = int(np.prod(g))
+    plane, gzl = g[0] * g[1], g[2] // world
+    ml = plane * gzl
+    shift, d = 0.5, (0.5 * np.exp(0.7j) if np.dtype(dt).kind == "c" else 0.35)
+    rng = np.random.default_rng(8)
+    X = rand(rng, (2 * m, nc), dt)
+    ref = api.bdg_op(g, dt, shift, d).apply(ctx, api.DeviceArray.from_numpy(ctx, X)).numpy(ctx)
+    local = [np.asfortranarray(np.vstack([X[r * ml:(r + 1) * ml], X[m + r * ml:m + (r + 1) * ml]])) for r in range(world)]
+    blocks = [api.DeviceArray.from_numpy(ctx, b) for b in local]
+    item = np.dtype(dt).itemsize
+    for r in range(world):
+        op = api.bdg_slab_op(g, r * gzl, gzl, dt, shift, d)
+        lo = blocks[r - 1].ptr + (gzl - 1) * plane * item if r > 0 else None      # last plane of the u slab below
+        hi = blocks[r + 1].ptr if r + 1 < world else None                         # first plane of the u slab above
+        api.set_halo(op, lo, hi, 2 * ml)
+        Y = op.apply(ctx, blocks[r]).numpy(ctx)
+        close(Y[:ml], ref[r * ml:(r + 1) * ml], 1e-13)
+        close(Y[ml:], ref[m + r * ml:m + (r + 1) * ml], 1e-13)
+
+
 def test_stencil_linearity_at_full_size(ctx):
     """Size-independent property at the BASELINE size (160^3): A(aX + bY) = a AX + b AY and symmetry
     <X, A Y> = <A X, Y>, checked through Gram kernels so that nothing leaves the device but 2x2 matrices."""
