@@ -32,6 +32,17 @@ static double next_uniform(void) {
   return (double)(rng_state >> 11) / 9007199254740992.0 - 0.5;
 }
 
+/* device block operator supplied by the caller (lb2_op_device).  An application would launch its own kernels on `stream`;
+ * this one forwards the solver's device blocks to the kernel-level ABI (a shifted stencil, A + 0.5 I). */
+typedef struct { void *inner; int calls; int widest; } fwd_ctx;
+static int fwd_matmat(void *user, int ncols, const void *X, int64_t ldx, void *Y, int64_t ldy, void *stream) {
+  fwd_ctx *c = (fwd_ctx *)user;
+  (void)stream; /* = the default context's stream, which lb2_op_apply enqueues on */
+  c->calls++;
+  if (ncols > c->widest) c->widest = ncols;
+  return lb2_op_apply(lb2_default_ctx(), c->inner, 'd', ncols, X, ldx, Y, ldy);
+}
+
 int main(void) {
   const uint64_t n = 100, nev = 3, k = 6;
   int fails = 0;
@@ -74,6 +85,31 @@ int main(void) {
     for (uint64_t i = 0; i < n; i++) x[i] = 1.0f;
     linop_apply(As, x, y);
     if (fabsf(y[0] - 1.0f) > 1e-6f || fabsf(y[50]) > 1e-6f) fails++;
+  }
+
+  /* ---- case 4: caller-supplied DEVICE block operator, eigenpair write-out ---- */
+  {
+    LinearOperator_d_t *Ain = (LinearOperator_d_t *)lb2_op_stencil('d', (int64_t)n, 1, 1, 2.5, -1.0, NULL);
+    fwd_ctx sc = {Ain, 0, 0};
+    LinearOperator_d_t *Ash = (LinearOperator_d_t *)lb2_op_device('d', (int64_t)n, fwd_matmat, &sc, 4.5);
+    d_lobpcg_t *a4 = lobpcg_alloc(n, nev, k, d);
+    a4->A = Ash; a4->maxIter = 2000; a4->tol = 1e-8;
+    for (uint64_t i = 0; i < n * k; i++) a4->S[i] = next_uniform();
+    lobpcg(a4);
+    printf("case4: iter=%lu converged=%lu callback calls=%d widest block=%d\n", (unsigned long)a4->iter,
+           (unsigned long)a4->converged, sc.calls, sc.widest);
+    if (a4->converged != nev || sc.widest < (int)k) fails++;
+    for (int j = 0; j < (int)nev; j++) {
+      const double ex = analytic(n, j) + 0.5, rel = fabs(a4->eigVals[j] - ex) / ex;
+      printf("  lambda[%d]=%.15e rel.err=%.2e\n", j, a4->eigVals[j], rel);
+      if (rel > 1e-10) fails++;
+    }
+    if (lb2_write_mtx("caller_eigvecs.mtx", 'd', (int64_t)n, (int64_t)nev, a4->S, (int64_t)n)) fails++;
+    if (lb2_write_mtx("caller_eigvals.mtx", 'd', (int64_t)nev, 1, a4->eigVals, (int64_t)nev)) fails++;
+    remove("caller_eigvecs.mtx"); remove("caller_eigvals.mtx");
+    lobpcg_free(&a4);
+    lb2_op_destroy(Ash);
+    lb2_op_destroy(Ain);
   }
 
   /* ---- case 3: parameter validation (reference lobpcg_impl.inc:66-75): returns, outputs untouched ---- */
