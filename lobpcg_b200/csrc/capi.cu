@@ -306,6 +306,13 @@ void* lb2_op_chebyshev(char prefix, const void* inner_linop, int degree, double 
   const LinOpRaw* in = (const LinOpRaw*)inner_linop;
   if (!valid_prefix(prefix) || !in || degree < 0) return nullptr;
   const BuiltinOp* bi = builtin_of(in);
+  if (hi <= 0 && bi && bi->kind == OP_CSR && bi->n != bi->n_global) {
+    // a row block only knows the Gershgorin bound of its own rows; different windows on different ranks would apply
+    // different polynomials
+    fprintf(stderr, "lobpcg_b200: lb2_op_chebyshev over a row-partitioned CSR operator needs an explicit upper bound (hi), "
+                    "the same on every rank (maximum over ranks of lb2_op_spec_hi)\n");
+    return nullptr;
+  }
   if (hi <= 0) hi = bi ? bi->spec_hi : 0;
   if (!(hi > 0)) {
     fprintf(stderr, "lobpcg_b200: lb2_op_chebyshev needs an upper spectrum bound (hi) for this operator\n");

@@ -227,6 +227,9 @@ class Solver : public SolverBase {
   bool indef;
   Timers tm;
   int64_t n = 0, ng = 0, row0 = 0;
+  // partial sums are combined across ranks only when the rows are partitioned (an unpartitioned solve on a context that
+  // has a communicator attached is a replica and must not be summed)
+  bool reduce() const { return ctx->comm != nullptr && n != ng; }
   int nseg = 1;   // row-partitioned BdG operator: local rows are two runs (the u and the v field), each a z-slab of its field
   // local run s = rows [s n/nseg, (s+1) n/nseg) of this rank = global rows seg_global(s) + [0, n/nseg)
   int64_t seg_len() const { return n / nseg; }
@@ -510,7 +513,7 @@ int Solver<T>::gram_ar(int ma, int mb, const T* A, const T* B, T* Gout, int uppe
   phase_work[PH_GRAM] += (Sc<T>::cplx ? 4.0 : 1.0) * (double)n * ma * (upper ? (double)(ma + 1) : 2.0 * mb);
   phase_calls[PH_GRAM]++;
   if (rc) return rc;
-  if (ctx->comm) {
+  if (reduce()) {
     tm.begin(PH_COMM);
     rc = allreduce_sum(ctx, Gout, (size_t)ma * mb * kCplx, kDouble);
     tm.end();
@@ -537,7 +540,7 @@ int Solver<T>::sumsq_total(int nc, const T* X, R* out_dev) {
   tm.end();
   phase_work[PH_RESID] += (double)n * nc * sizeof(T);
   phase_calls[PH_RESID]++;
-  if (!rc && ctx->comm) rc = allreduce_sum(ctx, out_dev, 1, kDouble);
+  if (!rc && reduce()) rc = allreduce_sum(ctx, out_dev, 1, kDouble);
   return rc;
 }
 
@@ -960,7 +963,7 @@ int Solver<T>::residual_pass(bool initial) {
   const T* BX = X;
   if (opB) { LB2_TRY(apply(opB, k, X, wA)); BX = wA; }
   LB2_TRY(resid(nev, AS, BX, Eig, nullptr, Sums));
-  if (ctx->comm) LB2_TRY(allreduce_sum(ctx, Sums, nev, kDouble));
+  if (reduce()) LB2_TRY(allreduce_sum(ctx, Sums, nev, kDouble));
   LB2_TRY(d2h(hbuf, Sums, sizeof(R) * nev));
   LB2_TRY(d2h(hbuf + nev, Eig, sizeof(R) * k));
   LB2_TRY(sync());
