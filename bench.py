@@ -243,7 +243,7 @@ def run_ours(args):
     roofline = {
         "kernel": "gram_wl_kernel + gram_dmma_kernel strip (K2/K3: S^H S and S^H A S, FP64 tensor pipe DMMA.8x8x4)",
         "bound": "tensor", "achieved": gram_tf, "peak": fp64, "unit": "TFLOP/s", "frac": gram_tf / fp64,
-        "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/ncu_traffic_r01.json); "
+        "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu, profiles/ncu_traffic_r01.json); "
                                              "algorithmic operand bytes per launch = n*m*8 = %.3g" % (n_local * 3.0 * k * 8),
         "peak_source": how64, "per_gpu": True,
         "algorithmic_flops_per_launch": st["gram"]["work"] / max(st["gram"]["calls"], 1) / world,

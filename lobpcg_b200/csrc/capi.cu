@@ -156,6 +156,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "gram_bk")) c->gram_bk = value;
   else if (!strcmp(key, "gram_tc5")) c->gram_tc5 = value;
   else if (!strcmp(key, "gram_load_pct")) c->gram_load_pct = value;
+  else if (!strcmp(key, "gram_phase")) c->gram_phase = value;
   else if (!strcmp(key, "gram_strip_max")) c->gram_strip_max = value;
   else if (!strcmp(key, "gram_strip_fma")) c->gram_strip_fma = value;
   else if (!strcmp(key, "spmm_cols")) c->spmm_cols = value;

@@ -33,6 +33,7 @@ struct lb2_ctx {
   int gram_strip_max = 0; // work-list Gram: ragged last tile columns narrower than this go to the lock-step kernel (0 = always, -1 = never)
   int gram_strip_fma = 0; // work-list Gram: -1 = never use the streaming FMA kernel for narrow strips (testing)
   int gram_load_pct = 0; // work-list Gram: staging-traffic cost of a tile with 256 columns in % of its DMMA time (0 = default)
+  int gram_phase = -1;      // work-list Gram: phase-aligned cyclic walk of the pieces (gram_wl.cu); 0 = off
   void* hostcopy = nullptr;        // lb2::HostCopyState* (pinned ring for pageable host <-> device block transfers)
   void* gram_wl_cache = nullptr;   // lb2::WlCache* (schedules per Gram shape)
   int gram_tc5 = -1;     // float Gram through tcgen05 / TMEM (gram_tc5.cu): -1 = auto (on), 0 = off, 1 = on

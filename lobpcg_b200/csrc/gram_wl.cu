@@ -48,6 +48,8 @@ struct WlItem {
   int32_t b_col0, b_cols;
   int32_t layout;               // index of the first of 8 WlWarp entries
   int32_t same_panel;           // 1: A and B panels are the same columns of the same matrix -> staged once
+  int32_t c_start;              // first K chunk to process; the piece is walked cyclically from there (plan_schedule: phase)
+  int32_t pad_;
 };
 
 // Window shapes.  Per-DMMA predicates cost more than the DMMAs they skip (ptxas wraps every predicated mma.sync in
@@ -143,17 +145,21 @@ __global__ void __launch_bounds__(WL_NT, 1)
 
     const bool same = item.same_panel != 0;   // diagonal tile of S^H S: one panel feeds both operands
     TileLoaderF64<WL_T, BK, LDS, WL_NT, VEC> la, lb;
-    la.init(A, lda, item.r_begin, item.a_col0, item.a_col0 + item.a_cols, tid);
-    lb.init(B, ldb, item.r_begin, item.b_col0, item.b_col0 + item.b_cols, tid);
+    int ci = item.c_start;   // chunk index of the next copy; chunks are walked c_start .. nchunks-1, 0 .. c_start-1
+    la.init(A, lda, item.r_begin + (int64_t)ci * BK, item.a_col0, item.a_col0 + item.a_cols, tid);
+    lb.init(B, ldb, item.r_begin + (int64_t)ci * BK, item.b_col0, item.b_col0 + item.b_cols, tid);
     int issued = 0, wstage = 0;
     auto issue = [&]() {
       if (issued < nchunks) {
-        const int64_t valid = rows - (int64_t)issued * BK;
+        const int64_t valid = rows - (int64_t)ci * BK;
+        const bool wrap = (ci + 1 == nchunks);
+        const int64_t step = wrap ? -(int64_t)(nchunks - 1) * BK : (int64_t)BK;
+        ci = wrap ? 0 : ci + 1;
         la.issue(As + wstage * (WL_T * LDS), A, valid);
-        la.advance(BK);
+        la.advance(step);
         if (!same) {
           lb.issue(Bs + wstage * (WL_T * LDS), B, valid);
-          lb.advance(BK);
+          lb.advance(step);
         }
       }
       issued++;
@@ -227,7 +233,7 @@ struct WlSchedule {
   const WlWarp* layouts = nullptr;
   const int* tile_first = nullptr;
 };
-using WlKey = std::tuple<int, int, int, int64_t, int, int, int>;   // ma, mb, upper + 2 * same_ab, n, ncta, BK, load_pct
+using WlKey = std::tuple<int, int, int, int64_t, int, int, int, int>;   // ma, mb, upper + 2 * same_ab, n, ncta, BK, load_pct, phase
 constexpr int WL_LOAD_PCT = 70;   // default staging cost of a 256-column tile relative to its DMMA time, in %
 struct WlCache {
   std::map<WlKey, WlSchedule> map;
@@ -320,7 +326,8 @@ struct WlPlan {   // host-side schedule
   std::vector<double> tile_cost;
 };
 
-int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, int BK, int load_pct, WlPlan& P) {
+int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, int BK, int load_pct, WlPlan& P,
+                  int phase = 1) {
   const int ntm = (ma + WL_T - 1) / WL_T, ntn = (mb + WL_T - 1) / WL_T;
   struct Tile { int ti, tj, a_cols, b_cols, layout, same; double cost; };
   std::vector<Tile> tiles;
@@ -388,6 +395,15 @@ int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, i
       itx.b_col0 = tl.tj * WL_T; itx.b_cols = tl.b_cols;
       itx.layout = tl.layout;
       itx.same_panel = tl.same;
+      // Phase alignment: a piece starts at the chunk whose row is a multiple of its own length, so that all pieces of
+      // (nearly) equal length — the full-CTA pieces of the rectangular tiles — sit at rows congruent modulo that length
+      // at every moment; tiles that share a panel then read the same rows at the same time and the panel comes out of
+      // L2 instead of DRAM (without it every one of the m/128 tiles of a panel streams it from HBM on its own).
+      if (phase) {
+        const int64_t nch = (r1 - r0 + BK - 1) / BK, a = r0 / BK;
+        const int64_t len = std::max<int64_t>(1, std::llround(L / tl.cost / BK));   // chunks of a full-CTA piece of this tile
+        itx.c_start = (int32_t)(((len - a % len) % len) % nch);
+      }
       items.push_back(itx);
       P.item_cta.push_back(b);
       P.item_tile.push_back(tix);
@@ -410,9 +426,9 @@ int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, i
 }
 
 int build_schedule(lb2_ctx* ctx, int ma, int mb, int upper, int same_ab, int64_t n, int ncta, int BK, int load_pct,
-                   WlSchedule& S) {
+                   int phase, WlSchedule& S) {
   WlPlan P;
-  const int rc = plan_schedule(ma, mb, upper, same_ab, n, ncta, BK, load_pct, P);
+  const int rc = plan_schedule(ma, mb, upper, same_ab, n, ncta, BK, load_pct, P, phase);
   if (rc) return rc;
   const int nitems = (int)P.items.size(), ntiles = P.ntiles;
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -481,6 +497,7 @@ int gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int BK, d
     for (int i = i0; i < i1; i++) {
       if (P.items[i].r_begin != r || P.items[i].r_end <= r || P.item_tile[i] != tix) return 11;
       if (i > i0 && P.items[i].r_begin % BK) return 12;
+      if (P.items[i].c_start < 0 || (int64_t)P.items[i].c_start * BK >= P.items[i].r_end - P.items[i].r_begin) return 18;
       r = P.items[i].r_end;
       cta_cost[P.item_cta[i]] += P.tile_cost[tix] * (double)(P.items[i].r_end - P.items[i].r_begin);
     }
@@ -546,11 +563,12 @@ static int run_wl(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int6
   const int ncta = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, tiles_full * n / 4096));
   const int load_pct = ctx->gram_load_pct > 0 ? ctx->gram_load_pct : WL_LOAD_PCT;
   const int same_ab = (upper && A == B && lda == ldb) ? 1 : 0;
-  const WlKey key(ma, mb, (upper ? 1 : 0) + 2 * same_ab, n, ncta, BK, load_pct);
+  const int phase = ctx->gram_phase != 0 ? 1 : 0;
+  const WlKey key(ma, mb, (upper ? 1 : 0) + 2 * same_ab, n, ncta, BK, load_pct, phase);
   auto f = cache->map.find(key);
   if (f == cache->map.end()) {
     WlSchedule S;
-    const int rc = build_schedule(ctx, ma, mb, upper ? 1 : 0, same_ab, n, ncta, BK, load_pct, S);
+    const int rc = build_schedule(ctx, ma, mb, upper ? 1 : 0, same_ab, n, ncta, BK, load_pct, phase, S);
     if (rc) return rc;
     f = cache->map.emplace(key, S).first;
   }
