@@ -186,6 +186,10 @@ int lb2_ipc_close_handle(void *mapped_ptr);
  * tile owned once, rows partitioned exactly, contiguous items per CTA.  stats[4] (may be NULL): items, busiest CTA /
  * mean CTA cost, issued / needed DMMA blocks, tiles. */
 int lb2_gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int bk, double *stats);
+/* host-only model of the operand sharing of that schedule: fraction of the panel requests that are distinct (must come from
+ * DRAM) when all CTAs advance at their tiles' cost rate; phase = 1: phase-aligned cyclic walk of the pieces (the default) */
+int lb2_gram_wl_plan_sharing(int ma, int mb, int upper, int64_t n, int ncta, int bk, int phase, int window_chunks,
+                             int samples, double *share);
 
 const char *lb2_version(void);
 

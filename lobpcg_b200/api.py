@@ -55,6 +55,7 @@ def _declare(L):
     L.lb2_ctx_launches.argtypes = [vp]
     L.lb2_default_ctx.restype = vp
     L.lb2_gram_wl_plan_check.argtypes = [ci, ci, ci, i64, ci, ci, C.POINTER(dbl)]
+    L.lb2_gram_wl_plan_sharing.argtypes = [ci, ci, ci, i64, ci, ci, ci, ci, ci, C.POINTER(dbl)]
     L.lb2_malloc.restype = vp
     L.lb2_malloc.argtypes = [C.c_size_t]
     L.lb2_free.argtypes = [vp]

@@ -95,6 +95,10 @@ static bool detect_stencil(int64_t n, const int64_t* rp, const int32_t* col, con
 
 extern "C" {
 
+int lb2_gram_wl_plan_sharing(int ma, int mb, int upper, int64_t n, int ncta, int bk, int phase, int window, int samples,
+                             double* share) {
+  return lb2::gram_wl_plan_sharing(ma, mb, upper, n, ncta, bk, phase, window, samples, share);
+}
 int lb2_gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int bk, double* stats) {
   return lb2::gram_wl_plan_check(ma, mb, upper, n, ncta, bk, stats);
 }

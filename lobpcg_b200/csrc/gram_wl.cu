@@ -544,6 +544,54 @@ int gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int BK, d
   return 0;
 }
 
+// Host-only model of the operand sharing of a schedule (tests/test_gram_plan.py, tools/gram_phase_sim.py): every CTA
+// advances through its pieces at exactly the cost rate of their tiles; at `samples` instants the (matrix, panel, row
+// window) triples the CTAs are reading are collected, windows of `window` chunks counting as one L2-resident region.
+// *share = distinct requests / all requests: the fraction of the panel traffic that has to come from DRAM if L2 serves
+// every repeated request (1 = nothing shared).
+int gram_wl_plan_sharing(int ma, int mb, int upper, int64_t n, int ncta, int BK, int phase, int window, int samples,
+                         double* share) {
+  if (!share || window < 1 || samples < 1) return -1;
+  WlPlan P;
+  const int rc = plan_schedule(ma, mb, upper, upper, n, ncta, BK, WL_LOAD_PCT, P, phase);
+  if (rc) return rc;
+  double T = 0;
+  for (int b = 0; b < ncta; b++) {
+    double t = 0;
+    for (int i = P.cta_first[b]; i < P.cta_first[b + 1]; i++)
+      t += P.tile_cost[P.item_tile[i]] * (double)(P.items[i].r_end - P.items[i].r_begin);
+    T = std::max(T, t);
+  }
+  double total = 0, uniq = 0;
+  std::vector<std::tuple<int, int, int64_t>> reads;
+  for (int sidx = 0; sidx < samples; sidx++) {
+    const double t = (sidx + 0.5) / samples * T;
+    reads.clear();
+    for (int b = 0; b < ncta; b++) {
+      double tt = t;
+      for (int i = P.cta_first[b]; i < P.cta_first[b + 1]; i++) {
+        const WlItem& it = P.items[i];
+        const double cost = P.tile_cost[P.item_tile[i]];
+        const int64_t rows = it.r_end - it.r_begin, nch = (rows + BK - 1) / BK;
+        const double dur = cost * (double)rows;
+        if (tt < dur) {
+          const int64_t c = (it.c_start + (int64_t)(tt / (cost * BK))) % nch;
+          const int64_t w = (it.r_begin / BK + c) / window;
+          reads.emplace_back(0, it.a_col0 / WL_T, w);
+          if (!it.same_panel) reads.emplace_back(upper ? 0 : 1, it.b_col0 / WL_T, w);
+          break;
+        }
+        tt -= dur;
+      }
+    }
+    total += (double)reads.size();
+    std::sort(reads.begin(), reads.end());
+    uniq += (double)(std::unique(reads.begin(), reads.end()) - reads.begin());
+  }
+  *share = total > 0 ? uniq / total : 1.0;
+  return 0;
+}
+
 void gram_wl_cache_free(lb2_ctx* ctx) {
   WlCache* c = (WlCache*)ctx->gram_wl_cache;
   if (!c) return;

@@ -32,6 +32,8 @@ int gram_tc5_f32(lb2_ctx* ctx, int64_t n, int ma, int mb, const float* A, int64_
 int nn_tc5_f32(lb2_ctx* ctx, int64_t n, int kd, int nb, float alpha, const float* S, int64_t lds, const float* C, int ldc,
                float beta, float* Out, int64_t ldo);
 int gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int BK, double* stats);
+int gram_wl_plan_sharing(int ma, int mb, int upper, int64_t n, int ncta, int BK, int phase, int window, int samples,
+                         double* share);
 
 // ---- elementwise.cu ---------------------------------------------------------------------------------
 // W[:,j] = AX[:,j] - lambda[j] * BX[:,j]  (W may be null: norms only); sumsq[j] = ||W[:,j]||^2 (may be null)
