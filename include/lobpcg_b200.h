@@ -127,6 +127,12 @@ int lb2_solver_results(lb2_solver *s, double *eig, int neig, double *res, int nr
   /* G(ma x mb) = A^H B; upper!=0: Hermitian product (ma==mb), upper tiles computed, result mirrored */    \
   int lb2_##P##_gram(lb2_ctx *ctx, int64_t n, int ma, int mb, const void *A, int64_t lda, const void *B,   \
                      int64_t ldb, void *G, int ldg, int upper);                                            \
+  /* column-block products of the cached-Gram pass (reference design docs/plans/2026-04-08-soft-locking-merge-design.md:48-61): \
+   * G0[0:m,0:nw] = S^H W0 and, when W1 != NULL, G1[0:m,0:nw] = S^H W1 in one pass over S.  tri_c0 >= 0: rows tri_c0.. of the   \
+   * results form a Hermitian nw x nw block whose strictly-lower part may be left unwritten. */                \
+  int lb2_##P##_gram_cols(lb2_ctx *ctx, int64_t n, int m, int nw, const void *S, int64_t lds, const void *W0,  \
+                          int64_t ldw0, void *G0, int ldg0, const void *W1, int64_t ldw1, void *G1, int ldg1,  \
+                          int tri_c0);                                                                     \
   /* Out(n x nb) = alpha S(n x kd) C(kd x nb) + beta Out; alpha,beta point to one scalar each */           \
   int lb2_##P##_tall_nn(lb2_ctx *ctx, int64_t n, int kd, int nb, const void *alpha, const void *S,         \
                         int64_t lds, const void *C, int ldc, const void *beta, void *Out, int64_t ldo);    \
@@ -186,6 +192,10 @@ int lb2_ipc_close_handle(void *mapped_ptr);
  * tile owned once, rows partitioned exactly, contiguous items per CTA.  stats[4] (may be NULL): items, busiest CTA /
  * mean CTA cost, issued / needed DMMA blocks, tiles. */
 int lb2_gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int bk, double *stats);
+/* same for the column-block schedule of lb2_d_gram_cols (nprod = 1 or 2 products): additionally every output entry that is
+ * not strictly below the diagonal of the Hermitian block is covered exactly once.  stats[4]: items, busiest CTA / mean,
+ * tiles, computed tile area / full rectangular area. */
+int lb2_gram_wl_cols_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int ncta, int bk, double *stats);
 /* host-only model of the operand sharing of that schedule: fraction of the panel requests that are distinct (must come from
  * DRAM) when all CTAs advance at their tiles' cost rate; phase = 1: phase-aligned cyclic walk of the pieces (the default) */
 int lb2_gram_wl_plan_sharing(int ma, int mb, int upper, int64_t n, int ncta, int bk, int phase, int window_chunks,

@@ -55,6 +55,7 @@ def _declare(L):
     L.lb2_ctx_launches.argtypes = [vp]
     L.lb2_default_ctx.restype = vp
     L.lb2_gram_wl_plan_check.argtypes = [ci, ci, ci, i64, ci, ci, C.POINTER(dbl)]
+    L.lb2_gram_wl_cols_plan_check.argtypes = [ci, ci, ci, ci, i64, ci, ci, C.POINTER(dbl)]
     L.lb2_gram_wl_plan_sharing.argtypes = [ci, ci, ci, i64, ci, ci, ci, ci, ci, C.POINTER(dbl)]
     L.lb2_malloc.restype = vp
     L.lb2_malloc.argtypes = [C.c_size_t]
@@ -134,6 +135,7 @@ def _declare(L):
         getattr(L, f"{p}_lobpcg").argtypes = [vp]
         getattr(L, f"{p}_ilobpcg").argtypes = [vp]
         getattr(L, f"lb2_{p}_gram").argtypes = [vp, i64, ci, ci, vp, i64, vp, i64, vp, ci, ci]
+        getattr(L, f"lb2_{p}_gram_cols").argtypes = [vp, i64, ci, ci, vp, i64, vp, i64, vp, ci, vp, i64, vp, ci, ci]
         getattr(L, f"lb2_{p}_tall_nn").argtypes = [vp, i64, ci, ci, vp, vp, i64, vp, ci, vp, vp, i64]
         getattr(L, f"lb2_{p}_residual").argtypes = [vp, i64, ci, vp, i64, vp, i64, vp, vp, i64, vp]
         getattr(L, f"lb2_{p}_col_sumsq").argtypes = [vp, i64, ci, vp, i64, vp]
@@ -252,6 +254,23 @@ def gram(ctx, A: DeviceArray, B: DeviceArray, upper=False) -> DeviceArray:
     G = DeviceArray((ma, mb), A.dtype)
     _ck(getattr(lib(), f"lb2_{p}_gram")(ctx.h, n, ma, mb, A.ptr, A.ld, B.ptr, B.ld, G.ptr, G.ld, int(upper)), "gram")
     return G
+
+
+def gram_cols(ctx, S: DeviceArray, W0: DeviceArray, W1: "DeviceArray | None" = None, tri_c0: int = -1):
+    """(S^H W0, S^H W1) through lb2_<p>_gram_cols; entries strictly below the diagonal of the Hermitian block that starts
+    at row tri_c0 may be left as they were (the outputs are zero-initialised here)."""
+    p = PREFIX[S.dtype]
+    n, m = S.shape
+    nw = W0.shape[1]
+    G0 = DeviceArray((m, nw), S.dtype); G0.zero(ctx)
+    G1 = None
+    if W1 is not None:
+        G1 = DeviceArray((m, nw), S.dtype); G1.zero(ctx)
+    _ck(getattr(lib(), f"lb2_{p}_gram_cols")(ctx.h, n, m, nw, S.ptr, S.ld, W0.ptr, W0.ld, G0.ptr, G0.ld,
+                                             W1.ptr if W1 is not None else None, W1.ld if W1 is not None else 0,
+                                             G1.ptr if G1 is not None else None, G1.ld if G1 is not None else 0,
+                                             int(tri_c0)), "gram_cols")
+    return G0, G1
 
 
 def tall_nn(ctx, S: DeviceArray, Cm: DeviceArray, Out: DeviceArray, alpha=1.0, beta=0.0):

@@ -99,6 +99,9 @@ int lb2_gram_wl_plan_sharing(int ma, int mb, int upper, int64_t n, int ncta, int
                              double* share) {
   return lb2::gram_wl_plan_sharing(ma, mb, upper, n, ncta, bk, phase, window, samples, share);
 }
+int lb2_gram_wl_cols_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int ncta, int bk, double* stats) {
+  return lb2::gram_wl_cols_plan_check(m, nw, nprod, tri_c0, n, ncta, bk, stats);
+}
 int lb2_gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int bk, double* stats) {
   return lb2::gram_wl_plan_check(ma, mb, upper, n, ncta, bk, stats);
 }
@@ -811,6 +814,12 @@ static void run_solver(char prefix, void* alg, int indefinite) {
   int lb2_##P##_gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const void* A, int64_t lda, const void* B, \
                      int64_t ldb, void* G, int ldg, int upper) {                                       \
     return gram<T>(ctx, n, ma, mb, (const T*)A, lda, (const T*)B, ldb, (T*)G, ldg, upper);             \
+  }                                                                                                    \
+  int lb2_##P##_gram_cols(lb2_ctx* ctx, int64_t n, int m, int nw, const void* S, int64_t lds, const void* W0, \
+                          int64_t ldw0, void* G0, int ldg0, const void* W1, int64_t ldw1, void* G1, int ldg1, \
+                          int tri_c0) {                                                                \
+    return gram_cols<T>(ctx, n, m, nw, (const T*)S, lds, (const T*)W0, ldw0, (T*)G0, ldg0, (const T*)W1, ldw1, \
+                        (T*)G1, ldg1, tri_c0);                                                         \
   }                                                                                                    \
   int lb2_##P##_tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, const void* alpha, const void* S,     \
                         int64_t lds, const void* C, int ldc, const void* beta, void* Out, int64_t ldo) { \

@@ -36,6 +36,7 @@ struct lb2_ctx {
   int gram_phase = -1;      // work-list Gram: phase-aligned cyclic walk of the pieces (gram_wl.cu); 0 = off
   void* hostcopy = nullptr;        // lb2::HostCopyState* (pinned ring for pageable host <-> device block transfers)
   void* gram_wl_cache = nullptr;   // lb2::WlCache* (schedules per Gram shape)
+  void* gram_wl_cols_cache = nullptr;   // lb2::WlColsCache* (schedules of the column-block products, gram_wl_cols_f64)
   int gram_tc5 = -1;     // float Gram through tcgen05 / TMEM (gram_tc5.cu): -1 = auto (on), 0 = off, 1 = on
   int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
   int spmm_cols = 0;     // CSR SpMM columns per thread (0 = heuristic)

@@ -1111,6 +1111,23 @@ int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const
   return launch_gram_simt<T>(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
 }
 
+// Column-block products of the cached-Gram pass: G0[0:m,0:nw] = S^H W0 and, when W1 != null,
+// G1[0:m,0:nw] = S^H W1.  tri_c0 >= 0: rows tri_c0.. of the results are a Hermitian nw x nw block; its strictly-lower
+// part MAY be left unwritten (callers read the upper part only).  f64: one work-list launch for both products
+// (gram_wl.cu); other types: one rectangular product each.
+template <typename T>
+int gram_cols(lb2_ctx* ctx, int64_t n, int m, int nw, const T* S, int64_t lds, const T* W0, int64_t ldw0, T* G0,
+              int ldg0, const T* W1, int64_t ldw1, T* G1, int ldg1, int tri_c0) {
+  if (m <= 0 || nw <= 0) return 0;
+  if constexpr (std::is_same<T, double>::value) {
+    if (!ctx->force_simt && ctx->gram_wl != 0 && ctx->gram_tile == 0 && n >= 4096)
+      return gram_wl_cols_f64(ctx, n, m, nw, S, lds, W0, ldw0, G0, ldg0, W1, ldw1, G1, ldg1, tri_c0);
+  }
+  if (int rc = gram<T>(ctx, n, m, nw, S, lds, W0, ldw0, G0, ldg0, 0)) return rc;
+  if (W1 && G1) return gram<T>(ctx, n, m, nw, S, lds, W1, ldw1, G1, ldg1, 0);
+  return 0;
+}
+
 template <int TM, int TN, int WM, int WN, int BK, int STAGES>
 static int launch_nn_dmma(lb2_ctx* ctx, int64_t n, int kd, int nb, double alpha, const double* S,
                           int64_t lds, const double* C, int ldc, double beta, double* Out, int64_t ldo) {
@@ -1195,7 +1212,8 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
 
 #define LB2_INST(T)                                                                                   \
   template int gram<T>(lb2_ctx*, int64_t, int, int, const T*, int64_t, const T*, int64_t, T*, int, int); \
-  template int tall_nn<T>(lb2_ctx*, int64_t, int, int, T, const T*, int64_t, const T*, int, T, T*, int64_t);
+  template int tall_nn<T>(lb2_ctx*, int64_t, int, int, T, const T*, int64_t, const T*, int, T, T*, int64_t); \
+  template int gram_cols<T>(lb2_ctx*, int64_t, int, int, const T*, int64_t, const T*, int64_t, T*, int, const T*, int64_t, T*, int, int);
 LB2_INST(float)
 LB2_INST(double)
 LB2_INST(c32)

@@ -49,7 +49,7 @@ struct WlItem {
   int32_t layout;               // index of the first of 8 WlWarp entries
   int32_t same_panel;           // 1: A and B panels are the same columns of the same matrix -> staged once
   int32_t c_start;              // first K chunk to process; the piece is walked cyclically from there (plan_schedule: phase)
-  int32_t pad_;
+  int32_t b_sel;                // which column operand the B panel comes from (0: B, 1: B1; gram_wl_cols_f64)
 };
 
 // Window shapes.  Per-DMMA predicates cost more than the DMMAs they skip (ptxas wraps every predicated mma.sync in
@@ -119,9 +119,9 @@ __device__ __forceinline__ void wl_stage_dispatch(int shape, double (&acc)[8][4]
 
 template <int BK, int STAGES, bool VEC>
 __global__ void __launch_bounds__(WL_NT, 1)
-    gram_wl_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
-                   const WlItem* __restrict__ items, const int* __restrict__ cta_first,
-                   const WlWarp* __restrict__ layouts, double* __restrict__ part) {
+    gram_wl_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B0, int64_t ldb0,
+                   const double* __restrict__ B1, int64_t ldb1, const WlItem* __restrict__ items,
+                   const int* __restrict__ cta_first, const WlWarp* __restrict__ layouts, double* __restrict__ part) {
   constexpr int LDS = BK + 4;
   extern __shared__ __align__(16) double smem_wl[];
   double* As = smem_wl;
@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(WL_NT, 1)
       for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const bool same = item.same_panel != 0;   // diagonal tile of S^H S: one panel feeds both operands
+    const double* __restrict__ B = item.b_sel ? B1 : B0;
+    const int64_t ldb = item.b_sel ? ldb1 : ldb0;
     TileLoaderF64<WL_T, BK, LDS, WL_NT, VEC> la, lb;
     int ci = item.c_start;   // chunk index of the next copy; chunks are walked c_start .. nchunks-1, 0 .. c_start-1
     la.init(A, lda, item.r_begin + (int64_t)ci * BK, item.a_col0, item.a_col0 + item.a_cols, tid);
@@ -326,42 +328,42 @@ struct WlPlan {   // host-side schedule
   std::vector<double> tile_cost;
 };
 
-int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, int BK, int load_pct, WlPlan& P,
-                  int phase = 1) {
-  const int ntm = (ma + WL_T - 1) / WL_T, ntn = (mb + WL_T - 1) / WL_T;
-  struct Tile { int ti, tj, a_cols, b_cols, layout, same; double cost; };
-  std::vector<Tile> tiles;
-  std::vector<WlWarp>& layouts = P.layouts;
-  std::map<std::tuple<int, int, int>, std::pair<int, int>> lcache;   // (kind, ra, cb) -> (layout index, max blocks)
-  for (int tj = 0; tj < ntn; tj++)
-    for (int ti = 0; ti < (upper ? tj + 1 : ntm); ti++) {
-      Tile tl{};
-      tl.ti = ti; tl.tj = tj;
-      tl.a_cols = std::min(WL_T, ma - ti * WL_T);
-      tl.b_cols = std::min(WL_T, mb - tj * WL_T);
-      const int ra = (tl.a_cols + 7) / 8, cb = (tl.b_cols + 7) / 8;
-      const int kind = (upper && ti == tj) ? 1 : 0;
-      auto key = std::make_tuple(kind, ra, cb);
-      auto f = lcache.find(key);
-      if (f == lcache.end()) {
-        WlWarp w[8];
-        int cost = 0;
-        const int lrc = (kind == 1 && ra == WL_BLK && cb == WL_BLK) ? diag16_layout(w, cost) : rect_layout(ra, cb, w, cost);
-        if (lrc) return lrc;
-        const int idx = (int)layouts.size();
-        layouts.insert(layouts.end(), w, w + 8);
-        f = lcache.emplace(key, std::make_pair(idx, cost)).first;
-      }
-      tl.layout = f->second.first;
-      // cost relative to a full tile: DMMA blocks of the busiest warp, bounded below by the staging traffic
-      const double mma = f->second.second / 32.0;
-      tl.same = (same_ab && upper && ti == tj) ? 1 : 0;
-      const double load = 0.01 * load_pct * (tl.a_cols + (tl.same ? 0 : tl.b_cols)) / (2.0 * WL_T);
-      tl.cost = std::max(mma, load);
-      tiles.push_back(tl);
-      P.tile_cost.push_back(tl.cost);
-    }
+struct WlTile {      // one output tile of a schedule
+  int ti, tj;        // tile coordinates (standard products: G rows ti*128.., columns tj*128..)
+  int a_col0, a_cols, b_col0, b_cols;
+  int layout, same, b_sel;
+  double cost;
+};
+using WlLayoutCache = std::map<std::tuple<int, int, int>, std::pair<int, int>>;   // (kind, ra, cb) -> (layout index, max blocks)
+
+// warp layout + cost of a tile of a_cols x b_cols; kind 1 = diagonal tile of a Hermitian product
+int make_tile(WlTile& tl, int kind, int same, int load_pct, std::vector<WlWarp>& layouts, WlLayoutCache& lcache) {
+  const int ra = (tl.a_cols + 7) / 8, cb = (tl.b_cols + 7) / 8;
+  auto key = std::make_tuple(kind, ra, cb);
+  auto f = lcache.find(key);
+  if (f == lcache.end()) {
+    WlWarp w[8];
+    int cost = 0;
+    const int lrc = (kind == 1 && ra == WL_BLK && cb == WL_BLK) ? diag16_layout(w, cost) : rect_layout(ra, cb, w, cost);
+    if (lrc) return lrc;
+    const int idx = (int)layouts.size();
+    layouts.insert(layouts.end(), w, w + 8);
+    f = lcache.emplace(key, std::make_pair(idx, cost)).first;
+  }
+  tl.layout = f->second.first;
+  // cost relative to a full tile: DMMA blocks of the busiest warp, bounded below by the staging traffic
+  const double mma = f->second.second / 32.0;
+  tl.same = same;
+  const double load = 0.01 * load_pct * (tl.a_cols + (tl.same ? 0 : tl.b_cols)) / (2.0 * WL_T);
+  tl.cost = std::max(mma, load);
+  return 0;
+}
+
+// tiles laid end to end, weighted by their cost, cut into ncta equal pieces
+int schedule_tiles(const std::vector<WlTile>& tiles, int64_t n, int ncta, int BK, int phase, WlPlan& P) {
   const int ntiles = (int)tiles.size();
+  P.tile_cost.clear();
+  for (auto& tl : tiles) P.tile_cost.push_back(tl.cost);
   double total = 0;
   for (auto& tl : tiles) total += tl.cost * (double)n;
   const double L = total / ncta;
@@ -371,7 +373,7 @@ int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, i
   P.tile_first.assign(ntiles + 1, 0);
   double U = 0;
   for (int tix = 0; tix < ntiles; tix++) {
-    const Tile& tl = tiles[tix];
+    const WlTile& tl = tiles[tix];
     P.tile_first[tix] = (int)items.size();
     const double span = tl.cost * (double)n;
     int b_lo = (int)std::floor(U / L), b_hi = (int)std::floor((U + span) / L);
@@ -391,10 +393,11 @@ int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, i
       if (r1 <= r0) continue;
       WlItem itx{};
       itx.r_begin = r0; itx.r_end = r1;
-      itx.a_col0 = tl.ti * WL_T; itx.a_cols = tl.a_cols;
-      itx.b_col0 = tl.tj * WL_T; itx.b_cols = tl.b_cols;
+      itx.a_col0 = tl.a_col0; itx.a_cols = tl.a_cols;
+      itx.b_col0 = tl.b_col0; itx.b_cols = tl.b_cols;
       itx.layout = tl.layout;
       itx.same_panel = tl.same;
+      itx.b_sel = tl.b_sel;
       // Phase alignment: a piece starts at the chunk whose row is a multiple of its own length, so that all pieces of
       // (nearly) equal length — the full-CTA pieces of the rectangular tiles — sit at rows congruent modulo that length
       // at every moment; tiles that share a panel then read the same rows at the same time and the panel comes out of
@@ -421,7 +424,76 @@ int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, i
   P.cta_first[ncta] = nitems;
   for (int i = 1; i < nitems; i++)
     if (P.item_cta[i] < P.item_cta[i - 1]) return -3;   // cannot happen
-  P.ntm = ntm; P.ntn = ntn; P.ntiles = ntiles;
+  P.ntiles = ntiles;
+  return 0;
+}
+
+int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, int BK, int load_pct, WlPlan& P,
+                  int phase = 1) {
+  const int ntm = (ma + WL_T - 1) / WL_T, ntn = (mb + WL_T - 1) / WL_T;
+  std::vector<WlTile> tiles;
+  WlLayoutCache lcache;
+  for (int tj = 0; tj < ntn; tj++)
+    for (int ti = 0; ti < (upper ? tj + 1 : ntm); ti++) {
+      WlTile tl{};
+      tl.ti = ti; tl.tj = tj;
+      tl.a_col0 = ti * WL_T; tl.b_col0 = tj * WL_T;
+      tl.a_cols = std::min(WL_T, ma - ti * WL_T);
+      tl.b_cols = std::min(WL_T, mb - tj * WL_T);
+      const int kind = (upper && ti == tj) ? 1 : 0;
+      if (int rc = make_tile(tl, kind, (same_ab && upper && ti == tj) ? 1 : 0, load_pct, P.layouts, lcache)) return rc;
+      tiles.push_back(tl);
+    }
+  if (int rc = schedule_tiles(tiles, n, ncta, BK, phase, P)) return rc;
+  P.ntm = ntm; P.ntn = ntn;
+  return 0;
+}
+
+// Column-block products (gram_wl_cols_f64): G_q[0:m, 0:nw] = S^H W_q for q < nprod with S = [.. | W-block ..] whose
+// columns tri_c0 .. tri_c0 + nw - 1 are the W block of a Hermitian product (tri_c0 < 0: plain rectangular products).
+// Tiles that lie entirely below the diagonal of that block (first row - tri_c0 > last column) are left out: the caller
+// mirrors them from the upper part.  P.tiles_out lists the tiles in schedule order.
+struct WlTileOut { int32_t a_col0, a_cols, b_col0, b_cols, b_sel, first, last, diag; };
+int plan_schedule_cols(int m, int nw, int nprod, int tri_c0, int64_t n, int ncta, int BK, int load_pct, int phase,
+                       WlPlan& P, std::vector<WlTileOut>& out) {
+  // Row tiles: 128-column steps over [0, tri_c0) and, separately, over the Hermitian block [tri_c0, tri_c0 + nw), so
+  // that the tiles of W^H W / W^H A W are aligned with the column tiles: tiles below the diagonal are left out, full
+  // diagonal tiles use the balanced upper-triangle cover (diag16_layout), exactly as in a Hermitian product.
+  std::vector<std::pair<int, int>> rows;   // (first column of S, columns)
+  const int split = (tri_c0 >= 0 && tri_c0 + nw == m) ? tri_c0 : m;
+  for (int c = 0; c < split; c += WL_T) rows.emplace_back(c, std::min(WL_T, split - c));
+  for (int c = split; c < m; c += WL_T) rows.emplace_back(c, std::min(WL_T, m - c));
+  const int ntn = (nw + WL_T - 1) / WL_T;
+  std::vector<WlTile> tiles;
+  std::vector<int> is_diag;
+  WlLayoutCache lcache;
+  // row tile outermost: the tiles of one S panel (both products, every column tile) are neighbours on the line
+  for (size_t ri = 0; ri < rows.size(); ri++)
+    for (int q = 0; q < nprod; q++)
+      for (int tj = 0; tj < ntn; tj++) {
+        WlTile tl{};
+        tl.ti = (int)ri; tl.tj = tj; tl.b_sel = q;
+        tl.a_col0 = rows[ri].first; tl.a_cols = rows[ri].second;
+        tl.b_col0 = tj * WL_T;
+        tl.b_cols = std::min(WL_T, nw - tj * WL_T);
+        int kind = 0;
+        if (tl.a_col0 >= split) {   // inside the Hermitian block (aligned tiles)
+          const int wi = (tl.a_col0 - split) / WL_T;
+          if (wi > tj) continue;
+          kind = (wi == tj) ? 1 : 0;
+        }
+        if (int rc = make_tile(tl, kind, 0, load_pct, P.layouts, lcache)) return rc;
+        tiles.push_back(tl);
+        is_diag.push_back(kind == 1 && (tl.a_cols + 7) / 8 == WL_BLK && (tl.b_cols + 7) / 8 == WL_BLK);   // same rule as make_tile: narrower diagonal tiles compute the full square
+      }
+  if (tiles.empty()) return -5;
+  if (int rc = schedule_tiles(tiles, n, ncta, BK, phase, P)) return rc;
+  P.ntm = (int)rows.size(); P.ntn = ntn;
+  out.clear();
+  for (size_t i = 0; i < tiles.size(); i++) {
+    const WlTile& tl = tiles[i];
+    out.push_back(WlTileOut{tl.a_col0, tl.a_cols, tl.b_col0, tl.b_cols, tl.b_sel, P.tile_first[i], P.tile_first[i + 1], is_diag[i]});
+  }
   return 0;
 }
 
@@ -461,11 +533,11 @@ int launch_wl(lb2_ctx* ctx, const WlSchedule& S, int64_t n, int ma, int mb, cons
   if (vec) {
     auto k = gram_wl_kernel<BK, STAGES, true>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, S.items, S.cta_first, S.layouts, part);
+    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, B, ldb, S.items, S.cta_first, S.layouts, part);
   } else {
     auto k = gram_wl_kernel<BK, STAGES, false>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, S.items, S.cta_first, S.layouts, part);
+    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, B, ldb, S.items, S.cta_first, S.layouts, part);
   }
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
@@ -476,6 +548,89 @@ int launch_wl(lb2_ctx* ctx, const WlSchedule& S, int64_t n, int ma, int mb, cons
   LB2_CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+// G_q[a_col0 + r, b_col0 + c] = sum over the item slots of the tile, in item order (column-block products)
+__global__ void gram_wl_reduce_tiles_kernel(const double* __restrict__ part, const WlTileOut* __restrict__ tiles,
+                                            double* __restrict__ G0, int ldg0, double* __restrict__ G1, int ldg1) {
+  const WlTileOut t = tiles[blockIdx.x];
+  double* __restrict__ G = t.b_sel ? G1 : G0;
+  const int ldg = t.b_sel ? ldg1 : ldg0;
+  const int tot = t.a_cols * t.b_cols;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < tot; idx += gridDim.y * blockDim.x) {
+    const int r = idx % t.a_cols, c = idx / t.a_cols;
+    if (t.diag && r > c) continue;   // balanced upper-triangle cover: the blocks below the diagonal were not computed
+    const int64_t off = r + (int64_t)c * WL_T;
+    double s = 0.0;
+    for (int k = t.first; k < t.last; k++) s += part[(int64_t)k * (WL_T * WL_T) + off];
+    G[(t.a_col0 + r) + (int64_t)(t.b_col0 + c) * ldg] = s;
+  }
+}
+
+struct WlColsSchedule {
+  WlSchedule base;
+  const WlTileOut* tiles_dev = nullptr;
+  int ntiles = 0;
+};
+using WlColsKey = std::tuple<int, int, int, int, int64_t, int, int, int, int>;   // m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase
+
+int build_schedule_cols(lb2_ctx* ctx, int m, int nw, int nprod, int tri_c0, int64_t n, int ncta, int BK, int load_pct,
+                        int phase, WlColsSchedule& S) {
+  WlPlan P;
+  std::vector<WlTileOut> tout;
+  const int rc = plan_schedule_cols(m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase, P, tout);
+  if (rc) return rc;
+  const int nitems = (int)P.items.size(), ntiles = P.ntiles;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t o_items = 0, o_cta = al(sizeof(WlItem) * nitems), o_lay = o_cta + al(sizeof(int) * (ncta + 1)),
+               o_tile = o_lay + al(sizeof(WlWarp) * P.layouts.size()), tot = o_tile + al(sizeof(WlTileOut) * ntiles);
+  std::vector<char> host(tot, 0);
+  memcpy(host.data() + o_items, P.items.data(), sizeof(WlItem) * nitems);
+  memcpy(host.data() + o_cta, P.cta_first.data(), sizeof(int) * (ncta + 1));
+  memcpy(host.data() + o_lay, P.layouts.data(), sizeof(WlWarp) * P.layouts.size());
+  memcpy(host.data() + o_tile, tout.data(), sizeof(WlTileOut) * ntiles);
+  LB2_CUDA_OK(cudaMalloc(&S.base.dev, tot));
+  LB2_CUDA_OK(cudaMemcpyAsync(S.base.dev, host.data(), tot, cudaMemcpyHostToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  const char* d = (const char*)S.base.dev;
+  S.base.items = (const WlItem*)(d + o_items);
+  S.base.cta_first = (const int*)(d + o_cta);
+  S.base.layouts = (const WlWarp*)(d + o_lay);
+  S.tiles_dev = (const WlTileOut*)(d + o_tile);
+  S.base.nitems = nitems; S.base.ncta = ncta; S.base.ntm = P.ntm; S.base.ntn = P.ntn;
+  S.ntiles = ntiles;
+  return 0;
+}
+
+template <int BK, int STAGES>
+int launch_wl_cols(lb2_ctx* ctx, const WlColsSchedule& S, const double* A, int64_t lda, const double* B0, int64_t ldb0,
+                   double* G0, int ldg0, const double* B1, int64_t ldb1, double* G1, int ldg1) {
+  double* part = (double*)ctx_scratch(ctx, sizeof(double) * (size_t)S.base.nitems * WL_T * WL_T);
+  if (!part) return -1;
+  const bool vec = (lda % 2 == 0) && (ldb0 % 2 == 0) && (ldb1 % 2 == 0) && ((uintptr_t)A % 16 == 0) &&
+                   ((uintptr_t)B0 % 16 == 0) && ((uintptr_t)B1 % 16 == 0);
+  constexpr size_t smem = sizeof(double) * (size_t)STAGES * 2 * WL_T * (BK + 4);
+  if (vec) {
+    auto k = gram_wl_kernel<BK, STAGES, true>;
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<S.base.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B0, ldb0, B1, ldb1, S.base.items, S.base.cta_first,
+                                                  S.base.layouts, part);
+  } else {
+    auto k = gram_wl_kernel<BK, STAGES, false>;
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<S.base.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B0, ldb0, B1, ldb1, S.base.items, S.base.cta_first,
+                                                  S.base.layouts, part);
+  }
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  gram_wl_reduce_tiles_kernel<<<dim3((unsigned)S.ntiles, 8), 256, 0, ctx->stream>>>(part, S.tiles_dev, G0, ldg0, G1, ldg1);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+struct WlColsCache {
+  std::map<WlColsKey, WlColsSchedule> map;
+};
 
 }  // namespace
 
@@ -594,11 +749,19 @@ int gram_wl_plan_sharing(int ma, int mb, int upper, int64_t n, int ncta, int BK,
 
 void gram_wl_cache_free(lb2_ctx* ctx) {
   WlCache* c = (WlCache*)ctx->gram_wl_cache;
-  if (!c) return;
-  for (auto& kv : c->map)
-    if (kv.second.dev) cudaFree(kv.second.dev);
-  delete c;
-  ctx->gram_wl_cache = nullptr;
+  if (c) {
+    for (auto& kv : c->map)
+      if (kv.second.dev) cudaFree(kv.second.dev);
+    delete c;
+    ctx->gram_wl_cache = nullptr;
+  }
+  WlColsCache* cc = (WlColsCache*)ctx->gram_wl_cols_cache;
+  if (cc) {
+    for (auto& kv : cc->map)
+      if (kv.second.base.dev) cudaFree(kv.second.base.dev);
+    delete cc;
+    ctx->gram_wl_cols_cache = nullptr;
+  }
 }
 
 static int run_wl(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B,
@@ -744,6 +907,115 @@ int gram_wl_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_
     return 0;
   }
   return run_wl(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+}
+
+// Column-block Gram products of the cached-Gram pass: with S = [X | P | W] (n x m) only the W columns of
+// S^H B S and S^H A S are contracted over n,
+//     G0[0:m, 0:nw] = S^H W0   (W0 = W or B W)        G1[0:m, 0:nw] = S^H W1   (W1 = A W),
+// both in ONE launch (the S panel of a row tile feeds every tile of both products); W1 == nullptr: one product.
+// tri_c0 >= 0 says that the rows tri_c0 .. tri_c0 + nw - 1 of the results are a Hermitian nw x nw block (W^H W, W^H A W):
+// tiles entirely below its diagonal are not computed and those entries of G0 / G1 are left untouched (the caller
+// mirrors them).  2 n m nw flop per product minus the skipped tiles.
+int gram_wl_cols_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, int64_t lds, const double* W0, int64_t ldw0,
+                     double* G0, int ldg0, const double* W1, int64_t ldw1, double* G1, int ldg1, int tri_c0) {
+  if (m <= 0 || nw <= 0) return 0;
+  if (!W0 || !G0) return -2;
+  const int nprod = (W1 && G1) ? 2 : 1;
+  if (!ctx->gram_wl_cols_cache) ctx->gram_wl_cols_cache = new WlColsCache();
+  WlColsCache* cache = (WlColsCache*)ctx->gram_wl_cols_cache;
+  const int BK = (ctx->gram_bk == 16) ? 16 : 32;
+  const int64_t tiles_full = (int64_t)((m + WL_T - 1) / WL_T) * ((nw + WL_T - 1) / WL_T) * nprod;
+  const int ncta = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, tiles_full * n / 4096));
+  const int load_pct = ctx->gram_load_pct > 0 ? ctx->gram_load_pct : WL_LOAD_PCT;
+  const int phase = ctx->gram_phase != 0 ? 1 : 0;
+  const WlColsKey key(m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase);
+  auto f = cache->map.find(key);
+  if (f == cache->map.end()) {
+    WlColsSchedule Sc;
+    const int rc = build_schedule_cols(ctx, m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase, Sc);
+    if (rc) return rc;
+    f = cache->map.emplace(key, Sc).first;
+  }
+  const double* B1 = nprod == 2 ? W1 : W0;
+  const int64_t ldb1 = nprod == 2 ? ldw1 : ldw0;
+  double* Gq1 = nprod == 2 ? G1 : G0;
+  const int ldq1 = nprod == 2 ? ldg1 : ldg0;
+  if (BK == 32) return launch_wl_cols<32, 3>(ctx, f->second, S, lds, W0, ldw0, G0, ldg0, B1, ldb1, Gq1, ldq1);
+  return launch_wl_cols<16, 4>(ctx, f->second, S, lds, W0, ldw0, G0, ldg0, B1, ldb1, Gq1, ldq1);
+}
+
+// Host-only self-check of a column-block schedule (no CUDA calls; tests/test_gram_plan.py): the items of every tile
+// partition [0, n), every 8x8 block of a tile is owned by exactly one warp, every output entry that is not strictly
+// below the diagonal of the Hermitian block is covered by exactly one tile, the skipped tiles lie entirely below it.
+// stats: [0] items, [1] busiest CTA cost / mean, [2] tiles, [3] computed tile area / full rectangular area.
+int gram_wl_cols_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int ncta, int BK, double* stats) {
+  WlPlan P;
+  std::vector<WlTileOut> tout;
+  int rc = plan_schedule_cols(m, nw, nprod, tri_c0, n, ncta, BK, WL_LOAD_PCT, 1, P, tout);
+  if (rc) return rc;
+  std::vector<double> cta_cost(ncta, 0.0);
+  std::vector<int> cover((size_t)nprod * m * nw, 0);
+  double area = 0;
+  for (int tix = 0; tix < P.ntiles; tix++) {
+    const WlTileOut& t = tout[tix];
+    if (t.first != P.tile_first[tix] || t.last != P.tile_first[tix + 1] || t.last <= t.first) return 10;
+    int64_t r = 0;
+    for (int i = t.first; i < t.last; i++) {
+      const WlItem& it = P.items[i];
+      if (it.r_begin != r || it.r_end <= r || P.item_tile[i] != tix) return 11;
+      if (i > t.first && it.r_begin % BK) return 12;
+      if (it.c_start < 0 || (int64_t)it.c_start * BK >= it.r_end - it.r_begin) return 18;
+      if (it.a_col0 != t.a_col0 || it.b_col0 != t.b_col0 || it.a_cols != t.a_cols || it.b_cols != t.b_cols ||
+          it.b_sel != t.b_sel || it.same_panel != 0)
+        return 19;
+      r = it.r_end;
+      cta_cost[P.item_cta[i]] += P.tile_cost[tix] * (double)(it.r_end - it.r_begin);
+    }
+    if (r != n) return 13;
+    const int ra = (t.a_cols + 7) / 8, cb = (t.b_cols + 7) / 8;
+    int owner[16][16];
+    for (auto& row : owner) for (int& v : row) v = 0;
+    for (int w = 0; w < 8; w++) {
+      const WlWarp& c = P.layouts[P.items[t.first].layout + w];
+      if (shape_of(c.mask) != c.shape) return 17;
+      for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 4; j++)
+          if ((c.mask >> (i * 4 + j)) & 1u) {
+            const int row = c.transposed ? c.b0 + j : c.a0 + i, col = c.transposed ? c.a0 + i : c.b0 + j;
+            if (row >= 16 || col >= 16) return 14;
+            owner[row][col]++;
+          }
+    }
+    for (int row = 0; row < 16; row++)
+      for (int col = 0; col < 16; col++)
+        if (owner[row][col] != ((row < ra && col < cb && (!t.diag || row <= col)) ? 1 : 0)) return 15;
+    if (t.diag && (tri_c0 < 0 || t.a_col0 - tri_c0 != t.b_col0)) return 22;
+    if (t.a_col0 < 0 || t.b_col0 < 0 || t.a_col0 + t.a_cols > m || t.b_col0 + t.b_cols > nw || t.b_sel < 0 || t.b_sel >= nprod)
+      return 20;
+    for (int i = 0; i < t.a_cols; i++)
+      for (int j = 0; j < t.b_cols; j++)
+        if (!t.diag || i <= j) cover[((size_t)t.b_sel * m + t.a_col0 + i) * nw + t.b_col0 + j]++;
+    area += (double)t.a_cols * t.b_cols * (t.diag ? 136.0 / 256.0 : 1.0);
+  }
+  for (int q = 0; q < nprod; q++)
+    for (int i = 0; i < m; i++)
+      for (int j = 0; j < nw; j++) {
+        const int c = cover[((size_t)q * m + i) * nw + j];
+        const bool below = tri_c0 >= 0 && (i - tri_c0 > j);
+        if (c > 1 || (c == 0 && !below)) return 21;
+      }
+  for (int b = 0; b < ncta; b++)
+    for (int i = P.cta_first[b]; i < P.cta_first[b + 1]; i++)
+      if (P.item_cta[i] != b) return 16;
+  double mx = 0, sum = 0;
+  for (double c : cta_cost) { mx = std::max(mx, c); sum += c; }
+  if (stats) {
+    stats[0] = (double)P.items.size();
+    stats[1] = mx / (sum / ncta);
+    stats[2] = (double)P.ntiles;
+    stats[3] = area / ((double)nprod * m * nw);
+  }
+  return 0;
 }
 
 }  // namespace lb2

@@ -17,6 +17,11 @@ template <typename T>
 int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_t lds, const T* C, int ldc,
             T beta, T* Out, int64_t ldo);
 
+// column-block products G0 = S^H W0, G1 = S^H W1 (W1 may be null) of the cached-Gram pass; see dense.cu
+template <typename T>
+int gram_cols(lb2_ctx* ctx, int64_t n, int m, int nw, const T* S, int64_t lds, const T* W0, int64_t ldw0, T* G0,
+              int ldg0, const T* W1, int64_t ldw1, T* G1, int ldg1, int tri_c0);
+
 // gram_wl.cu: f64 Gram, work-list kernel (masked diagonal / ragged tiles, tiles laid end to end over the CTAs)
 int gram_wl_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B, int64_t ldb,
                 double* G, int ldg, int upper);
@@ -31,6 +36,11 @@ int gram_tc5_f32(lb2_ctx* ctx, int64_t n, int ma, int mb, const float* A, int64_
 // nn_tc5.cu: float projection Out = alpha S C + beta Out on tcgen05 (3xTF32, TMEM accumulator); -100 = alignment not met
 int nn_tc5_f32(lb2_ctx* ctx, int64_t n, int kd, int nb, float alpha, const float* S, int64_t lds, const float* C, int ldc,
                float beta, float* Out, int64_t ldo);
+// gram_wl.cu: column-block products of the cached-Gram pass: G0[0:m,0:nw] = S^H W0, G1[0:m,0:nw] = S^H W1 (W1 may be null) in
+// one launch; tri_c0 >= 0: rows tri_c0.. of the results are a Hermitian block whose strictly-lower tiles are skipped
+int gram_wl_cols_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, int64_t lds, const double* W0, int64_t ldw0,
+                     double* G0, int ldg0, const double* W1, int64_t ldw1, double* G1, int ldg1, int tri_c0);
+int gram_wl_cols_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int ncta, int BK, double* stats);
 int gram_wl_plan_check(int ma, int mb, int upper, int64_t n, int ncta, int BK, double* stats);
 int gram_wl_plan_sharing(int ma, int mb, int upper, int64_t n, int ncta, int BK, int phase, int window, int samples,
                          double* share);

@@ -64,3 +64,46 @@ def test_phase_aligned_walk_lets_tiles_share_panels(m, n):
     assert aligned < 0.7 * seq      # fewer panels = fewer tiles per panel = less to share (m=384: 0.62, m=896: 0.38)
     if m == 896 and n == 4_096_000:
         assert aligned < 0.42
+
+
+# ---- column-block schedule of the cached-Gram pass (lb2_<p>_gram_cols, gram_wl.cu: plan_schedule_cols) ------------------
+COLS_SHAPES = [  # (m, nw, nprod, tri_c0, n): [X P W]^H [W | AW] of the BASELINE configs, full and soft-locked / first-pass widths
+    (900, 300, 2, 600, 4_096_000), (900, 300, 2, 600, 512_000), (600, 200, 2, 400, 4_096_000), (384, 128, 2, 256, 2_097_152),
+    (600, 300, 2, 300, 4_096_000), (750, 225, 2, 525, 4_096_000), (900, 300, 1, 600, 4_096_000), (600, 300, 1, -1, 4_096_000),
+    (60, 20, 2, 40, 10_000), (240, 80, 2, 160, 32_768), (1, 1, 1, 0, 4096), (300, 300, 2, 0, 1_000_000),
+]
+
+
+def _check_cols(m, nw, nprod, tri_c0, n, ncta, bk):
+    st = (C.c_double * 4)()
+    rc = api.lib().lb2_gram_wl_cols_plan_check(m, nw, nprod, tri_c0, n, ncta, bk, st)
+    assert rc == 0, f"column-block plan check failed with code {rc} for {(m, nw, nprod, tri_c0, n, ncta, bk)}"
+    return list(st)
+
+
+@pytest.mark.parametrize("shape", COLS_SHAPES)
+@pytest.mark.parametrize("bk", [16, 32])
+def test_column_block_schedule_is_an_exact_cover(shape, bk):
+    m, nw, nprod, tri_c0, n = shape
+    tiles = ((m + 127) // 128) * ((nw + 127) // 128) * nprod
+    ncta = min(148, max(1, tiles * n // 4096))
+    items, balance, ntiles, area = _check_cols(m, nw, nprod, tri_c0, n, ncta, bk)
+    assert items <= ncta + ntiles
+    if n >= 500_000:
+        assert balance < 1.02
+    if tri_c0 < 0:
+        assert area == 1.0
+    else:
+        assert area <= 1.0
+    if (m, nw, tri_c0) == (900, 300, 600):
+        assert area < 0.9        # the tiles below the diagonal of W^H W / W^H A W are not computed
+
+
+def test_column_block_random_shapes():
+    rng = np.random.default_rng(12)
+    for _ in range(300):
+        nw = int(rng.integers(1, 500))
+        nxp = int(rng.integers(0, 1000))
+        tri = int(rng.choice([-1, nxp]))
+        n = int(rng.integers(4096, 5_000_000))
+        _check_cols(nxp + nw, nw, int(rng.integers(1, 3)), tri, n, int(rng.integers(1, 149)), int(rng.choice([16, 32])))
