@@ -119,6 +119,16 @@ double lb2_solver_stat_work(lb2_solver *s, int i);
 unsigned long long lb2_solver_stat_calls(lb2_solver *s, int i);
 void lb2_solver_reset_stats(lb2_solver *s);
 int lb2_solver_state(lb2_solver *s, uint64_t *iter, uint64_t *converged, int *use_ortho);
+/* solver options (before lb2_solver_init unless noted): "gram_cache" 0/1 — cached Gram blocks (default 1, definite solver;
+ * env LB2_GRAM_CACHE), "gram_cache_period" — passes between recomputations of the cached blocks (any time),
+ * "force_ortho" 1 — every pass in the ortho branch (any time), "debug_min_conv" n — soft-lock at least n columns (timing). */
+int lb2_solver_set_option(lb2_solver *s, const char *key, int value);
+/* "gram_cache", "gram_cache_refreshes", "gram_cache_monitor", "gram_cache_monitor_max", "arena_bytes", "arena_columns" */
+double lb2_solver_info(lb2_solver *s, const char *key);
+/* status of the last <p>_lobpcg / <p>_ilobpcg call on this thread (they return void, reference lobpcg.h:63-83):
+ * 0 = ran; 1 = parameters rejected with the reference's message, outputs untouched as in the reference;
+ * 2 = run-time failure: alg->converged = 0, alg->iter = passes done, eigVals / resNorm = NaN */
+int lb2_last_status(void);
 /* Ritz values (first neig) and residual norms (first nres) of the last pass, as doubles, without downloading X */
 int lb2_solver_results(lb2_solver *s, double *eig, int neig, double *res, int nres);
 

@@ -118,6 +118,10 @@ def _declare(L):
     L.lb2_solver_stat_calls.restype = C.c_ulonglong
     L.lb2_solver_stat_calls.argtypes = [vp, ci]
     L.lb2_solver_reset_stats.argtypes = [vp]
+    L.lb2_solver_set_option.argtypes = [vp, C.c_char_p, ci]
+    L.lb2_solver_info.restype = dbl
+    L.lb2_solver_info.argtypes = [vp, C.c_char_p]
+    L.lb2_last_status.restype = ci
     L.lb2_solver_results.argtypes = [vp, C.POINTER(dbl), ci, C.POINTER(dbl), ci]
     L.lb2_solver_state.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(ci)]
     L.lb2_comm_unique_id.argtypes = [vp, C.c_char_p]
@@ -577,7 +581,7 @@ def lobpcg(A: LinOp, X0: np.ndarray, nev: int, tol: float, max_iter: int, B: Lin
     fn = getattr(lib(), f"{st.prefix}_{'i' if indefinite else ''}lobpcg")
     fn(st.ptr)
     out = dict(eig=st.eigvals(), res=st.resnorm(), X=np.array(st.X(), order="F", copy=True),
-               iter=int(st.st.iter), converged=int(st.st.converged), sig=st.signature())
+               iter=int(st.st.iter), converged=int(st.st.converged), sig=st.signature(), status=int(lib().lb2_last_status()))
     st.free()
     return out
 
@@ -603,6 +607,12 @@ class Solver:
         _ck(lib().lb2_solver_set_device_io(self.h, x0.ptr if x0 is not None else None,
                                            x_out.ptr if x_out is not None else None), "lb2_solver_set_device_io")
 
+    def set_option(self, key: str, value: int):
+        _ck(lib().lb2_solver_set_option(self.h, key.encode(), int(value)), f"lb2_solver_set_option({key})")
+
+    def info(self, key: str) -> float:
+        return float(lib().lb2_solver_info(self.h, key.encode()))
+
     def prepare(self):
         _ck(lib().lb2_solver_prepare(self.h), "lb2_solver_prepare")
 
@@ -626,8 +636,9 @@ class Solver:
     def finish(self):
         _ck(lib().lb2_solver_finish(self.h), "lb2_solver_finish")
         s = self.state_
-        return dict(eig=s.eigvals(), res=s.resnorm(), X=s.X(), iter=int(s.st.iter), converged=int(s.st.converged),
-                    sig=s.signature())
+        # X is copied: the state's host block is freed by close() / garbage collection
+        return dict(eig=s.eigvals(), res=s.resnorm(), X=np.array(s.X(), order="F", copy=True), iter=int(s.st.iter),
+                    converged=int(s.st.converged), sig=s.signature())
 
     def progress(self):
         it, cv, uo = C.c_uint64(0), C.c_uint64(0), C.c_int(0)

@@ -764,7 +764,18 @@ int lb2_solver_state(lb2_solver* s, uint64_t* iter, uint64_t* converged, int* us
   return 0;
 }
 
+// status of the last reference-facing call on this thread (the entry points return void, reference lobpcg.h:63-83):
+// 0 = ran (converged or maxIter reached), 1 = parameters rejected with the reference's own message — outputs untouched,
+// exactly as the reference leaves them (src/core/lobpcg_impl.inc:66-75), 2 = run-time failure (device error, failed
+// factorisation, operator callback error): alg->converged = 0, alg->iter = passes done, eigVals / resNorm = NaN.
+static thread_local int g_last_status = 0;
+int lb2_last_status(void) { return g_last_status; }
+
+int lb2_solver_set_option(lb2_solver* s, const char* key, int value) { return s ? s->impl->set_option(key, value) : -1; }
+double lb2_solver_info(lb2_solver* s, const char* key) { return s ? s->impl->info(key) : -1.0; }
+
 static void run_solver(char prefix, void* alg, int indefinite) {
+  g_last_status = 2;
   lb2_ctx* ctx = lb2_default_ctx();
   if (!ctx) return;
   // LB2_TIMING=1: wall-clock split of the call on stderr (set-up + X0 upload + initial RR | passes | download | tear-down)
@@ -774,12 +785,20 @@ static void run_solver(char prefix, void* alg, int indefinite) {
   lb2_solver* s = lb2_solver_create(ctx, prefix, alg, indefinite);
   if (!s) return;
   double t1 = t0, t2 = t0, t3 = t0;
-  if (lb2_solver_init(s) == 0) {
+  int rc = lb2_solver_init(s);
+  if (rc == 0) {
     t1 = now();
-    int rc = lb2_solver_step(s, INT_MAX);
+    rc = lb2_solver_step(s, INT_MAX);
     t2 = now();
-    if (rc >= 0) lb2_solver_finish(s);
+    rc = (rc >= 0) ? lb2_solver_finish(s) : rc;
     t3 = now();
+  }
+  if (rc == 0) g_last_status = 0;
+  else if (s->impl->param_error) g_last_status = 1;
+  else {
+    g_last_status = 2;
+    s->impl->write_failure_state();
+    fprintf(stderr, "lobpcg_b200: solver failed (code %d); alg->converged = 0, eigVals = NaN (lb2_last_status() = 2)\n", rc);
   }
   lb2_solver_destroy(s);
   if (timing)

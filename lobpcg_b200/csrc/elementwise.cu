@@ -122,6 +122,80 @@ int residual(lb2_ctx* ctx, int64_t n, int nc, const T* AX, int64_t ldax, const T
   return 0;
 }
 
+// Residual norms plus the drift monitor of the cached-Gram pass (solver.cu): for column j
+//   out[j]        = ||AX_j - lambda_j BX_j||^2
+//   out[nc + j]   = Re(x_j^H AX_j)      (Rayleigh quotient numerator: must equal the Ritz value theta_j)
+//   out[2 nc + j] = Re(x_j^H BX_j)      (must equal 1)
+// X, AX (and BX) are streamed once; BX == nullptr means B = I (BX = X: two streams, same as the plain norm pass).
+template <typename T, bool HAVE_B>
+__global__ void __launch_bounds__(EW_THREADS)
+    residual_monitor_kernel(int64_t n, int64_t rows_per_chunk, const T* __restrict__ X, int64_t ldx,
+                            const T* __restrict__ AX, int64_t ldax, const T* __restrict__ BX, int64_t ldbx,
+                            const real_t<T>* __restrict__ lambda, real_t<T>* __restrict__ partial, int nchunks, int nc) {
+  using R = real_t<T>;
+  const int j = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
+  const int64_t r1 = min(n, r0 + rows_per_chunk);
+  const R lam = lambda[j];
+  const T* x = X + (int64_t)j * ldx;
+  const T* ax = AX + (int64_t)j * ldax;
+  const T* bx = HAVE_B ? BX + (int64_t)j * ldbx : x;
+  R s0 = 0, s1 = 0, s2 = 0;
+  for (int64_t i = r0 + threadIdx.x; i < r1; i += (int64_t)EW_THREADS * EW_UNROLL) {
+    T a[EW_UNROLL], b[EW_UNROLL], xv[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; u++) {
+      const int64_t ii = i + (int64_t)u * EW_THREADS;
+      a[u] = b[u] = xv[u] = zero<T>();
+      if (ii < r1) {
+        a[u] = ax[ii];
+        xv[u] = x[ii];
+        b[u] = HAVE_B ? bx[ii] : xv[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; u++) {
+      const T v = sub_(a[u], rscale_(b[u], lam));
+      s0 += abs2_(v);
+      T d1 = zero<T>(), d2 = zero<T>();
+      fmac_(d1, xv[u], a[u]);
+      fmac_(d2, xv[u], b[u]);
+      s1 += real_(d1);
+      s2 += real_(d2);
+    }
+  }
+  s0 = block_sum<R>(s0);
+  __syncthreads();
+  s1 = block_sum<R>(s1);
+  __syncthreads();
+  s2 = block_sum<R>(s2);
+  if (threadIdx.x == 0) {
+    partial[((int64_t)j) * nchunks + blockIdx.x] = s0;
+    partial[((int64_t)(nc + j)) * nchunks + blockIdx.x] = s1;
+    partial[((int64_t)(2 * nc + j)) * nchunks + blockIdx.x] = s2;
+  }
+}
+
+template <typename T>
+int residual_monitor(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, const T* AX, int64_t ldax, const T* BX,
+                     int64_t ldbx, const real_t<T>* lambda, real_t<T>* out3) {
+  using R = real_t<T>;
+  if (n <= 0 || nc <= 0) return 0;
+  const int nchunks = ew_chunks(n, nc, ctx->sm_count);
+  const int64_t rpc = (n + nchunks - 1) / nchunks;
+  R* partial = (R*)ctx_scratch(ctx, sizeof(R) * (size_t)nchunks * nc * 3);
+  if (!partial) return -1;
+  dim3 grid(nchunks, nc);
+  if (BX) residual_monitor_kernel<T, true><<<grid, EW_THREADS, 0, ctx->stream>>>(n, rpc, X, ldx, AX, ldax, BX, ldbx, lambda, partial, nchunks, nc);
+  else residual_monitor_kernel<T, false><<<grid, EW_THREADS, 0, ctx->stream>>>(n, rpc, X, ldx, AX, ldax, BX, ldbx, lambda, partial, nchunks, nc);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  finish_sums_kernel<R><<<(3 * nc + 127) / 128, 128, 0, ctx->stream>>>(partial, nchunks, 3 * nc, out3);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 template <typename T>
 int col_sumsq(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, real_t<T>* sumsq) {
   return residual<T>(ctx, n, nc, X, ldx, nullptr, 0, nullptr, nullptr, 0, sumsq);
@@ -326,6 +400,7 @@ template int convert_block<c64, c32>(lb2_ctx*, int64_t, int, const c32*, int64_t
   template int residual<T>(lb2_ctx*, int64_t, int, const T*, int64_t, const T*, int64_t, const real_t<T>*, \
                            T*, int64_t, real_t<T>*);                                                    \
   template int col_sumsq<T>(lb2_ctx*, int64_t, int, const T*, int64_t, real_t<T>*);                     \
+  template int residual_monitor<T>(lb2_ctx*, int64_t, int, const T*, int64_t, const T*, int64_t, const T*, int64_t, const real_t<T>*, real_t<T>*); \
   template int fill_uniform<T>(lb2_ctx*, int64_t, int, T*, int64_t, uint64_t, int64_t, int64_t);                \
   template int scale_cols<T>(lb2_ctx*, int64_t, int, T*, int64_t, const real_t<T>*, real_t<T>);         \
   template int normalize_by<T>(lb2_ctx*, int64_t, T*, const real_t<T>*);                                \

@@ -50,6 +50,11 @@ int gram_wl_plan_sharing(int ma, int mb, int upper, int64_t n, int ncta, int BK,
 template <typename T>
 int residual(lb2_ctx* ctx, int64_t n, int nc, const T* AX, int64_t ldax, const T* BX, int64_t ldbx,
              const real_t<T>* lambda, T* W, int64_t ldw, real_t<T>* sumsq);
+// residual norms + drift monitor: out3[j] = ||AX_j - lambda_j BX_j||^2, out3[nc+j] = Re(x_j^H AX_j), out3[2nc+j] = Re(x_j^H BX_j);
+// BX == null: B = I
+template <typename T>
+int residual_monitor(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, const T* AX, int64_t ldax, const T* BX,
+                     int64_t ldbx, const real_t<T>* lambda, real_t<T>* out3);
 // sumsq[j] = ||X[:,j]||_2^2, j < nc
 template <typename T>
 int col_sumsq(lb2_ctx* ctx, int64_t n, int nc, const T* X, int64_t ldx, real_t<T>* sumsq);

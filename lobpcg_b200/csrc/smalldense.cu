@@ -281,7 +281,7 @@ __global__ void svqb_transform_kernel(int m, const T* __restrict__ V, int ldv, c
                                       T* __restrict__ Tm, int ldt, int* __restrict__ count) {
   using R = real_t<T>;
   __shared__ R smax[256];
-  __shared__ int spos[1024 + 1];
+  extern __shared__ int spos[];   // m + 1 entries (dynamic)
   R mx = 0;
   for (int j = threadIdx.x; j < m; j += blockDim.x) mx = fmax(mx, fabs(lam[j]));
   smax[threadIdx.x] = mx;
@@ -313,11 +313,11 @@ __global__ void svqb_transform_kernel(int m, const T* __restrict__ V, int ldv, c
 template <typename T>
 int sd_svqb_transform(lb2_ctx* ctx, int m, const T* V, int ldv, const real_t<T>* lam, const real_t<T>* D,
                       real_t<T> tau, int drop, T* Tm, int ldt, int* count_dev) {
-  if (m > 1024) {
-    fprintf(stderr, "lobpcg_b200: svqb block wider than 1024 columns is not supported\n");
+  if (m > 12000) {   // 48 KB of dynamic shared memory; Solver::prepare rejects such block sizes up front
+    fprintf(stderr, "lobpcg_b200: svqb block wider than 12000 columns is not supported\n");
     return -1;
   }
-  svqb_transform_kernel<T><<<1, 256, 0, ctx->stream>>>(m, V, ldv, lam, D, tau, drop, Tm, ldt, count_dev);
+  svqb_transform_kernel<T><<<1, 256, sizeof(int) * (size_t)(m + 1), ctx->stream>>>(m, V, ldv, lam, D, tau, drop, Tm, ldt, count_dev);
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
   return 0;
@@ -445,6 +445,33 @@ int sd_cp_lower(lb2_ctx* ctx, int m, int nx, const T* Cx, T* Cp) {
   return 0;
 }
 
+// Gram matrix of S = [X P | W] from the cached [X P] block and the freshly contracted W columns (cached-Gram pass,
+// solver.cu: rr_modified): G (m x m) = [[Gc, Gw_top], [Gw_top^H, herm(Gw_bottom)]].  Only the upper triangles of Gc and of
+// the W x W block of Gw are read (the column-block kernel leaves the strictly-lower tiles of that block unwritten); the
+// result is exactly Hermitian.  Gc == nullptr: identity (ortho branch, B-orthonormal basis).
+template <typename T>
+__global__ void assemble_gram_kernel(int m, int mxp, const T* __restrict__ Gc, int ldc, const T* __restrict__ Gw, int ldw,
+                                     T* __restrict__ G, int ldg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * m) return;
+  const int i = idx % m, j = idx / m;
+  const int lo = i < j ? i : j, hi = i < j ? j : i;   // (lo, hi) is the upper-triangle twin of (i, j)
+  T v;
+  if (hi < mxp) v = Gc ? Gc[lo + (int64_t)hi * ldc] : ((lo == hi) ? make<T>(real_t<T>(1)) : zero<T>());
+  else v = Gw[lo + (int64_t)(hi - mxp) * ldw];
+  if (i > j) v = conj_(v);
+  if (i == j) v = make<T>(real_(v));
+  G[i + (int64_t)j * ldg] = v;
+}
+template <typename T>
+int sd_assemble_gram(lb2_ctx* ctx, int m, int mxp, const T* Gc, int ldc, const T* Gw, int ldw, T* G, int ldg) {
+  if (m <= 0) return 0;
+  assemble_gram_kernel<T><<<(m * m + 255) / 256, 256, 0, ctx->stream>>>(m, mxp, Gc, ldc, Gw, ldw, G, ldg);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 #define LB2_INST(T)                                                                                         \
   template int sd_potrf_upper<T>(lb2_ctx*, int, T*, int, int*);                                             \
   template int sd_syevd_upper<T>(lb2_ctx*, int, T*, int, real_t<T>*, int*);                                 \
@@ -461,7 +488,8 @@ int sd_cp_lower(lb2_ctx* ctx, int m, int nx, const T* Cx, T* Cp) {
   template int sd_trsm_upper<T>(lb2_ctx*, char, char, int, int, const T*, int, T*, int);                  \
   template int sd_gemm_ab<T>(lb2_ctx*, char, int, int, int, T, const T*, int, const T*, int, T, T*, int); \
   template int sd_indef_finalize<T>(lb2_ctx*, int, const real_t<T>*, const T*, int, T*, int, real_t<T>*, int8_t*); \
-  template int sd_cp_lower<T>(lb2_ctx*, int, int, const T*, T*);
+  template int sd_cp_lower<T>(lb2_ctx*, int, int, const T*, T*);                                           \
+  template int sd_assemble_gram<T>(lb2_ctx*, int, int, const T*, int, const T*, int, T*, int);
 LB2_INST(float)
 LB2_INST(double)
 LB2_INST(c32)

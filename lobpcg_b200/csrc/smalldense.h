@@ -21,4 +21,5 @@ template <typename T> int sd_trsm_upper(lb2_ctx* ctx, char side, char op, int ro
 template <typename T> int sd_gemm_ab(lb2_ctx* ctx, char opa, int m, int n, int k, T alpha, const T* A, int lda, const T* B, int ldb, T beta, T* C, int ldc);
 template <typename T> int sd_indef_finalize(lb2_ctx* ctx, int m, const real_t<T>* mu, const T* V, int ldv, T* VR, int ldo, real_t<T>* theta, int8_t* sig);
 template <typename T> int sd_cp_lower(lb2_ctx* ctx, int m, int nx, const T* Cx, T* Cp);
+template <typename T> int sd_assemble_gram(lb2_ctx* ctx, int m, int mxp, const T* Gc, int ldc, const T* Gw, int ldw, T* G, int ldg);
 }  // namespace lb2

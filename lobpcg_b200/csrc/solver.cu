@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <type_traits>
 #include <vector>
 #include <inttypes.h>
@@ -189,6 +190,7 @@ class Solver : public SolverBase {
   int helper_setup(int64_t rows, int kmax, const LinOpRaw* A, const LinOpRaw* B) {
     ng = n = rows; row0 = 0; k = kmax > 0 ? kmax : 1; nev = k;
     opA = A; opB = B; opT = nullptr;
+    helper_mode = true;
     LB2_CUDA_OK(cudaSetDevice(ctx->device));
     if (sd_init(ctx)) return 1;
     LB2_TRY(alloc());
@@ -219,6 +221,36 @@ class Solver : public SolverBase {
     if (it) *it = iter;
     if (cv) *cv = conv;
     if (uo) *uo = useOrtho;
+  }
+  int set_option(const char* key, int value) override {
+    if (!key) return -1;
+    if (!strcmp(key, "gram_cache")) {
+      if (prepared) return -2;   // decides the arena layout
+      gram_cache = value != 0;
+      gram_cache_forced = true;
+    } else if (!strcmp(key, "gram_cache_period")) cache_period = value > 0 ? value : 1;
+    else if (!strcmp(key, "force_ortho")) force_ortho = value;
+    else if (!strcmp(key, "debug_min_conv")) debug_min_conv = value;
+    else return -1;
+    return 0;
+  }
+  double info(const char* key) override {
+    if (!key) return -1;
+    if (!strcmp(key, "gram_cache")) return gram_cache ? 1 : 0;
+    if (!strcmp(key, "gram_cache_refreshes")) return (double)cache_refreshes;
+    if (!strcmp(key, "gram_cache_monitor")) return cache_monitor;
+    if (!strcmp(key, "gram_cache_monitor_max")) return cache_monitor_max;
+    if (!strcmp(key, "arena_bytes")) return (double)arena_bytes;
+    if (!strcmp(key, "arena_columns")) return n > 0 ? (double)arena_bytes / ((double)n * sizeof(T)) : 0.0;
+    return -1;
+  }
+  void write_failure_state() override {
+    if (!alg) return;
+    const R nan = std::numeric_limits<R>::quiet_NaN();
+    alg->converged = 0;
+    alg->iter = iter;
+    if (alg->eigVals) for (uint64_t i = 0; i < alg->sizeSub; i++) alg->eigVals[i] = nan;
+    if (alg->resNorm) for (uint64_t i = 0; i < alg->nev && i < alg->sizeSub; i++) alg->resNorm[i] = nan;
   }
 
  public:  // (the host-buffer helper API at the end of this file drives the same building blocks)
@@ -262,6 +294,26 @@ class Solver : public SolverBase {
   std::vector<R> hEig, hRes;
   const LinOpRaw *opA = nullptr, *opB = nullptr, *opT = nullptr;
   bool inited = false, done = false, prepared = false;
+  // ---- cached Gram blocks (reference design docs/plans/2026-04-08-soft-locking-merge-design.md:48-61) ----
+  // Per pass only the W columns of S^H B S and S^H A S are contracted over n (gram_cols); the [X P] blocks follow from
+  // the previous pass's small matrices: [X' P'] = S [Cx | Cp_act]  =>  [X' P']^H B [X' P'] = C^H G C, same for A.
+  // AS then only holds [AX | AW] (2k columns; the legacy path keeps [AX | AP | AW]).
+  bool gram_cache_forced = false;
+  bool gram_cache = true;        // option "gram_cache" / LB2_GRAM_CACHE=0: legacy pass (both Grams recomputed in full)
+  bool helper_mode = false;      // host-buffer helper API: one-shot calls, full-size workspaces
+  int as_cols = 0;               // columns of AS
+  T *Graw = nullptr, *GAraw = nullptr;   // assembled S^H B S / S^H A S of the current pass (before factorisation)
+  T *Gc = nullptr, *GAc = nullptr;       // cached [X P] blocks, leading dimension cache_mxp
+  T *Gw = nullptr, *GAw = nullptr;       // W columns (m x nw, ld m) from gram_cols
+  T* Ccat = nullptr;                     // [Cx | Cp_act] (m x (k + n_act), ld m)
+  bool cache_ok = false, cache_has_b = false;
+  int cache_mxp = 0, since_refresh = 0;
+  int cache_period = 64;         // option "gram_cache_period": recompute the [X P] blocks from the tall vectors every .. passes
+  double cache_monitor = 0;      // last drift monitor value (max |x^H B x - 1|, |x^H A x - theta| / ||A|| over the nev columns)
+  double cache_monitor_max = 0;
+  // testing / measurement switches (lb2_solver_set_option)
+  int force_ortho = 0;           // 1: run every pass in the ortho branch (useOrtho = 1 from the first pass)
+  int debug_min_conv = 0;        // soft-lock at least this many leading columns regardless of their residuals (timing only)
 
   T* Xp() { return slab[cur]; }
   T* col(T* base, int64_t c) { return base + c * n; }
@@ -290,7 +342,9 @@ class Solver : public SolverBase {
   int gram_self_B(int m, T* S, T* Gout);             // S^H B S (mirrored)
   int chol_transform(int m, int* bad);               // G -> D, R (in G), DinvR ; bad=1 if potrf failed or rcond small
   int rr_initial();
-  int rr_modified(int m, int from_col);
+  int rr_modified(int m);
+  int update_gram_cache(int m, int nconv);
+  double monitor_threshold() const { return kDouble ? 5e-12 : 2e-5; }
   int cp_from_z(int m, const T* Zm, T* VQ);           // VQ (m x k) = Z_perp Q
   int svqb(T* U, int nu, R tau, bool drop, int* nret);
   int localize(const BuiltinOp*& b, BuiltinOp& local, const T* X);
@@ -310,7 +364,7 @@ void Solver<T>::release() {
   if (arena) cudaFree(arena);
   arena = nullptr;
   slab[0] = slab[1] = AS = wA = wB = nullptr;
-  T** big[] = {&G, &GA, &DinvR, &Z, &Tmp, &Cx, &Cp, &Q, &Tau};
+  T** big[] = {&G, &GA, &DinvR, &Z, &Tmp, &Cx, &Cp, &Q, &Tau, &Graw, &GAraw, &Gc, &GAc, &Gw, &GAw, &Ccat};
   for (auto p : big) { if (*p) cudaFree(*p); *p = nullptr; }
   R** rs[] = {&D, &Lam, &Eig, &Sums, &Scal};
   for (auto p : rs) { if (*p) cudaFree(*p); *p = nullptr; }
@@ -330,16 +384,33 @@ int Solver<T>::alloc() {
   // every rank of a row-partitioned run (peer halo address = peer arena base + my offset)
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t slab_b = al(sizeof(T) * 3 * nk), wrk_b = al(sizeof(T) * std::max<size_t>(nk, 2 * (size_t)n));
-  arena_bytes = 3 * slab_b + 2 * wrk_b;
+  // AS = [AX | AW] with the cached Gram blocks, [AX | AP | AW] for the legacy pass, the indefinite solver and the helpers
+  if (const char* e = getenv("LB2_GRAM_CACHE")) { if (!gram_cache_forced) gram_cache = (atoi(e) != 0); }
+  if (indef) gram_cache = false;
+  as_cols = (gram_cache && !helper_mode) ? 2 * k : 3 * k;
+  const size_t as_b = al(sizeof(T) * (size_t)as_cols * n);
+  arena_bytes = 2 * slab_b + as_b + 2 * wrk_b;
   LB2_CUDA_OK(cudaMalloc(&arena, arena_bytes));
   char* base = (char*)arena;
   slab[0] = (T*)base; base += slab_b;
   slab[1] = (T*)base; base += slab_b;
-  AS = (T*)base; base += slab_b;
+  AS = (T*)base; base += as_b;
   wA = (T*)base; base += wrk_b;
   wB = (T*)base;
   T** sm[] = {&G, &GA, &DinvR, &Z, &Tmp};
   for (auto p : sm) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * m3));
+  if (gram_cache) {
+    T** sm2[] = {&Graw, &GAraw};
+    for (auto p : sm2) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * m3));
+    T** sm3[] = {&Gc, &GAc};
+    for (auto p : sm3) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * 4 * (size_t)k * k));
+    T** sm4[] = {&Gw, &GAw};
+    for (auto p : sm4) {   // zeroed once: the column-block kernel never writes the tiles below the diagonal of the W block
+      LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * k));
+      LB2_CUDA_OK(cudaMemsetAsync(*p, 0, sizeof(T) * m3 * k, ctx->stream));
+    }
+    LB2_CUDA_OK(cudaMalloc(&Ccat, sizeof(T) * m3 * 2 * k));
+  }
   LB2_CUDA_OK(cudaMalloc(&Cx, sizeof(T) * m3 * k));
   LB2_CUDA_OK(cudaMalloc(&Cp, sizeof(T) * m3 * k));
   LB2_CUDA_OK(cudaMalloc(&Q, sizeof(T) * m3 * k));
@@ -352,7 +423,7 @@ int Solver<T>::alloc() {
   LB2_CUDA_OK(cudaMalloc(&Count, sizeof(int) * 4));
   LB2_CUDA_OK(cudaMalloc(&Theta, sizeof(R) * m3));
   LB2_CUDA_OK(cudaMalloc(&dSig, m3));
-  LB2_CUDA_OK(cudaMallocHost(&hbuf, sizeof(R) * (m3 + 32)));
+  LB2_CUDA_OK(cudaMallocHost(&hbuf, sizeof(R) * (4 * (size_t)k + 64)));
   hEig.assign(k, R(0));
   hRes.assign(k, R(0));
   return 0;
@@ -635,26 +706,89 @@ int Solver<T>::cp_from_z(int m, const T* Zm, T* VQ) {
   return 0;
 }
 
-// Modified Rayleigh-Ritz on S = slab[cur][:, 0:m].  On return useOrtho in {0,1,2}; for 0/1: Cx, Cp (m x k,
-// ld m) and Eig[0:k] are set.  AS[:, from_col:m] is (re)computed here.
+// Modified Rayleigh-Ritz on S = slab[cur][:, 0:m] = [X | P_act | W_act] (np, nw = widths of P_act, W_act).  On return
+// useOrtho in {0,1,2}; for 0/1: Cx, Cp (m x k, ld m) and Eig[0:k] are set.
+//
+// Legacy pass (gram_cache off): S^H B S and S^H A S are contracted in full, AS[:, k:m] = A [P W] is recomputed here.
+// Cached pass: only the W columns are contracted — one launch for [S^H (B)W | S^H AW] — and the [X P] blocks
+// come from the cache that step_impl derives from this pass's coefficients (C^H G C); when the cache is not valid
+// (first pass, every cache_period passes, after the drift monitor tripped) the [X P] blocks are recomputed from the
+// tall vectors first.  AS = [AX | AW]; A P is only formed on such a refresh.
 template <typename T>
-int Solver<T>::rr_modified(int m, int from_col) {
+int Solver<T>::rr_modified(int m) {
   T* S = Xp();
   const int nrem = m - k;
-  if (useOrtho == 0) {
-    LB2_TRY(gram_self_B(m, S, G));
-    int bad = 0;
-    LB2_TRY(chol_transform(m, &bad));
-    if (bad) {
-      if (bad == 1) fprintf(stderr, "rayleigh_ritz_modified: Cholesky failed\n");
-      useOrtho = 2;
-      return 0;
+  const int mxp = k + np, nwc = m - mxp;
+  const bool cached = gram_cache && nwc > 0;
+  if (!cached) {
+    cache_ok = false;
+    if (useOrtho == 0) {
+      LB2_TRY(gram_self_B(m, S, G));
+      int bad = 0;
+      LB2_TRY(chol_transform(m, &bad));
+      if (bad) {
+        if (bad == 1) fprintf(stderr, "rayleigh_ritz_modified: Cholesky failed\n");
+        useOrtho = 2;
+        return 0;
+      }
+    } else {
+      useOrtho = 1;
     }
+    if (as_cols < m) { fprintf(stderr, "lobpcg_b200: internal error: AS holds %d columns, need %d\n", as_cols, m); return -1; }
+    LB2_TRY(apply(opA, m - k, col(S, k), col(AS, k)));
+    LB2_TRY(gram_ar(m, m, S, AS, GA, 1));
   } else {
-    useOrtho = 1;
+    const bool chol = (useOrtho == 0);
+    if (!chol) useOrtho = 1;
+    T* Wp = col(S, mxp);
+    T* AW = col(AS, k);
+    if (!cache_ok || cache_mxp != mxp || (chol && !cache_has_b)) {
+      // refresh: [X P]^H B [X P] and [X P]^H A [X P] from the tall vectors (A P goes where A W will be written next)
+      if (chol) LB2_TRY(gram_self_B(mxp, S, Gc));
+      if (np > 0) LB2_TRY(apply(opA, np, col(S, k), col(AS, k)));
+      LB2_TRY(gram_ar(mxp, mxp, S, AS, GAc, 1));
+      cache_ok = true;
+      cache_has_b = chol;
+      cache_mxp = mxp;
+      since_refresh = 0;
+      cache_refreshes++;
+    }
+    LB2_TRY(apply(opA, nwc, Wp, AW));
+    const T* BW = Wp;
+    if (chol && opB) { LB2_TRY(apply(opB, nwc, Wp, wA)); BW = wA; }
+    tm.begin(PH_GRAM);
+    int rc = chol ? gram_cols<T>(ctx, n, m, nwc, S, n, BW, n, Gw, m, AW, n, GAw, m, mxp)
+                  : gram_cols<T>(ctx, n, m, nwc, S, n, AW, n, GAw, m, (const T*)nullptr, 0, (T*)nullptr, 0, mxp);
+    tm.end();
+    // algorithmic flops: rectangular [X P]^H W part + Hermitian W^H W part, per product
+    phase_work[PH_GRAM] += (chol ? 2.0 : 1.0) * (Sc<T>::cplx ? 4.0 : 1.0) * (double)n * (2.0 * mxp * nwc + (double)nwc * (nwc + 1));
+    phase_calls[PH_GRAM]++;
+    if (rc) return rc;
+    if (reduce()) {
+      tm.begin(PH_COMM);
+      if (chol) rc = allreduce_sum(ctx, Gw, (size_t)m * nwc * kCplx, kDouble);
+      if (!rc) rc = allreduce_sum(ctx, GAw, (size_t)m * nwc * kCplx, kDouble);
+      tm.end();
+      if (rc) return rc;
+    }
+    tm.begin(PH_SMALL);
+    if (chol) {
+      LB2_TRY(sd_assemble_gram<T>(ctx, m, mxp, Gc, mxp, Gw, m, Graw, m));
+      LB2_CUDA_OK(cudaMemcpyAsync(G, Graw, sizeof(T) * (size_t)m * m, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    LB2_TRY(sd_assemble_gram<T>(ctx, m, mxp, GAc, mxp, GAw, m, GAraw, m));
+    LB2_CUDA_OK(cudaMemcpyAsync(GA, GAraw, sizeof(T) * (size_t)m * m, cudaMemcpyDeviceToDevice, ctx->stream));
+    tm.end();
+    if (chol) {
+      int bad = 0;
+      LB2_TRY(chol_transform(m, &bad));
+      if (bad) {
+        if (bad == 1) fprintf(stderr, "rayleigh_ritz_modified: Cholesky failed\n");
+        useOrtho = 2;
+        return 0;
+      }
+    }
   }
-  LB2_TRY(apply(opA, m - from_col, col(S, from_col), col(AS, from_col)));
-  LB2_TRY(gram_ar(m, m, S, AS, GA, 1));
   tm.begin(PH_SMALL);
   T* Zm = Z;
   if (useOrtho == 0) {
@@ -686,6 +820,35 @@ int Solver<T>::rr_modified(int m, int from_col) {
     LB2_TRY(cp_from_z(m, Zm, Cp));
   }
   tm.end();
+  return 0;
+}
+
+// After a pass: the cached [X P] blocks of the NEXT pass's basis [X' | P'_act] = S [Cx | Cp[:, nconv:]] from this pass's
+// assembled Gram matrices: G' = C^H G C (the "analytical Gram blocks" of the reference's design notes, computed instead of
+// assumed so that the rounding of the small factorisations is carried along).  Ortho branch: only the A block.
+template <typename T>
+int Solver<T>::update_gram_cache(int m, int nconv) {
+  if (!gram_cache || !cache_ok) return 0;
+  const int nact = k - nconv, mc = k + nact;
+  tm.begin(PH_SMALL);
+  LB2_CUDA_OK(cudaMemcpyAsync(Ccat, Cx, sizeof(T) * (size_t)m * k, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (nact > 0)
+    LB2_CUDA_OK(cudaMemcpyAsync(Ccat + (size_t)m * k, Cp + (size_t)nconv * m, sizeof(T) * (size_t)m * nact,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+  if (useOrtho == 0) {
+    LB2_TRY(sd_gemm<T>(ctx, 'N', m, mc, m, Graw, m, Ccat, m, Tmp, m));
+    LB2_TRY(sd_gemm<T>(ctx, 'H', mc, mc, m, Ccat, m, Tmp, m, Gc, mc));
+    cache_has_b = true;
+  } else {
+    cache_has_b = false;
+  }
+  LB2_TRY(sd_gemm<T>(ctx, 'N', m, mc, m, GAraw, m, Ccat, m, Tmp, m));
+  LB2_TRY(sd_gemm<T>(ctx, 'H', mc, mc, m, Ccat, m, Tmp, m, GAc, mc));
+  tm.end();
+  cache_mxp = mc;
+  since_refresh++;
+  // drift monitor (residual_pass) and the periodic refresh decide whether the next pass trusts these blocks
+  if (since_refresh >= cache_period || cache_monitor > monitor_threshold()) cache_ok = false;
   return 0;
 }
 
@@ -962,20 +1125,45 @@ int Solver<T>::residual_pass(bool initial) {
   LB2_TRY(apply(opA, k, X, AS));
   const T* BX = X;
   if (opB) { LB2_TRY(apply(opB, k, X, wA)); BX = wA; }
-  LB2_TRY(resid(nev, AS, BX, Eig, nullptr, Sums));
-  if (reduce()) LB2_TRY(allreduce_sum(ctx, Sums, nev, kDouble));
-  LB2_TRY(d2h(hbuf, Sums, sizeof(R) * nev));
-  LB2_TRY(d2h(hbuf + nev, Eig, sizeof(R) * k));
+  const bool monitor = gram_cache && !initial;
+  if (monitor) {
+    // same two (three with B) streams as the plain norm pass, plus the Rayleigh quotients x^H A x and x^H B x of the new
+    // Ritz vectors: the drift monitor of the cached Gram blocks
+    tm.begin(PH_RESID);
+    int rc = residual_monitor<T>(ctx, n, nev, X, n, AS, n, opB ? BX : (const T*)nullptr, n, Eig, Sums);
+    tm.end();
+    phase_work[PH_RESID] += (opB ? 3.0 : 2.0) * (double)n * nev * sizeof(T);
+    phase_calls[PH_RESID]++;
+    if (rc) return rc;
+    if (reduce()) LB2_TRY(allreduce_sum(ctx, Sums, 3 * (size_t)nev, kDouble));
+    LB2_TRY(d2h(hbuf, Sums, sizeof(R) * 3 * nev));
+    LB2_TRY(d2h(hbuf + 3 * nev, Eig, sizeof(R) * k));
+  } else {
+    LB2_TRY(resid(nev, AS, BX, Eig, nullptr, Sums));
+    if (reduce()) LB2_TRY(allreduce_sum(ctx, Sums, nev, kDouble));
+    LB2_TRY(d2h(hbuf, Sums, sizeof(R) * nev));
+    LB2_TRY(d2h(hbuf + 3 * nev, Eig, sizeof(R) * k));
+  }
   LB2_TRY(sync());
-  for (int i = 0; i < k; i++) hEig[i] = hbuf[nev + i];
+  for (int i = 0; i < k; i++) hEig[i] = hbuf[3 * nev + i];
   const R bn = BNorm > 0 ? BNorm : R(1);
   for (int i = 0; i < nev; i++) hRes[i] = std::sqrt(hbuf[i]) / (ANorm + std::fabs(hEig[i]) * bn);
+  if (monitor) {
+    double dev = 0;
+    const double an = ANorm > 0 ? (double)ANorm : 1.0;
+    for (int i = 0; i < nev; i++) {
+      dev = std::max(dev, std::fabs((double)hbuf[nev + i] - (double)hEig[i]) / an);
+      dev = std::max(dev, std::fabs((double)hbuf[2 * nev + i] - 1.0));
+    }
+    cache_monitor = dev;
+    cache_monitor_max = std::max(cache_monitor_max, dev);
+  }
   if (initial) {
     conv = 0;
   } else {
     conv = 0;
     for (int i = 0; i < nev; i++) {
-      if (hRes[i] > alg->tol) break;
+      if (hRes[i] > alg->tol && i >= debug_min_conv) break;
       conv++;
     }
   }
@@ -985,6 +1173,7 @@ int Solver<T>::residual_pass(bool initial) {
 template <typename T>
 int Solver<T>::prepare() {
   if (prepared) return 0;
+  param_error = true;    // cleared once the parameters have been accepted
   if (indef && !alg->B) {
     fprintf(stderr, "ilobpcg: B operator must not be NULL\n");
     return 1;
@@ -1005,6 +1194,10 @@ int Solver<T>::prepare() {
     fprintf(stderr, "lobpcg: 3*sizeSub (%lu) > size (%lu)\n", (unsigned long)(3 * alg->sizeSub), (unsigned long)alg->size);
     return 1;
   }
+  if (alg->sizeSub > 12000) {   // svqb keeps one int per column in shared memory (smalldense.cu: svqb_transform_kernel)
+    fprintf(stderr, "lobpcg: sizeSub (%lu) > 12000 is not supported\n", (unsigned long)alg->sizeSub);
+    return 1;
+  }
   const BuiltinOp* ba = builtin_of(opA);
   if (ba && ba->n != ba->n_global) {  // row-partitioned operator: local rows, equal slabs on every rank
     n = ba->n;
@@ -1015,6 +1208,43 @@ int Solver<T>::prepare() {
       return 1;
     }
   }
+  // every operator must act on the same rows as the block vectors: the kernels size their launches from the
+  // operator's own row count while the solver passes its leading dimension n (a mismatch would write past a block)
+  {
+    const LinOpRaw* ops[3] = {opA, opB, opT};
+    const char* names[3] = {"A", "B", "T"};
+    for (int q = 0; q < 3; q++) {
+      const LinOpRaw* op = ops[q];
+      if (!op) continue;
+      const BuiltinOp* b = builtin_of(op);
+      for (int depth = 0; b && depth < 2; depth++) {   // depth 1: inner operator of a polynomial preconditioner
+        if (b->prefix != Sc<T>::prefix) {
+          fprintf(stderr, "lobpcg: operator %s was built for type '%c', the solver runs type '%c'\n", names[q], b->prefix,
+                  Sc<T>::prefix);
+          return 1;
+        }
+        if (b->n != n || b->n_global != ng || (b->n != b->n_global && b->row0 != row0)) {
+          fprintf(stderr, "lobpcg: operator %s has %lld local / %lld global rows (first row %lld), the solver %lld / %lld "
+                          "(first row %lld)\n", names[q], (long long)b->n, (long long)b->n_global, (long long)b->row0,
+                  (long long)n, (long long)ng, (long long)row0);
+          return 1;
+        }
+        if (b->kind != OP_CHEB && b->kind != OP_DEVICE && b->device != ctx->device) {
+          fprintf(stderr, "lobpcg: operator %s lives on device %d, the solver context on device %d\n", names[q], b->device,
+                  ctx->device);
+          return 1;
+        }
+        b = (b->kind == OP_CHEB) ? builtin_of(b->inner) : nullptr;
+      }
+      // foreign operators: the reference never reads rows/cols (callers may leave them 0); reject only a stated mismatch
+      if (!builtin_of(op) && ((op->rows && op->rows != (uint64_t)ng) || (op->cols && op->cols != (uint64_t)ng))) {
+        fprintf(stderr, "lobpcg: operator %s is %lu x %lu, size is %lu\n", names[q], (unsigned long)op->rows,
+                (unsigned long)op->cols, (unsigned long)ng);
+        return 1;
+      }
+    }
+  }
+  param_error = false;
   LB2_CUDA_OK(cudaSetDevice(ctx->device));
   if (sd_init(ctx)) return 1;
   LB2_TRY(alloc());
@@ -1098,6 +1328,7 @@ int Solver<T>::step_impl(int max_steps, int* passes_out) {
     T* S = Xp();
     T* V = S;
     T* W = col(S, k + np);
+    if (force_ortho && !indef && useOrtho == 0) useOrtho = 1;
     // orthogonalise W against [X, P_act]
     if (useOrtho || indef) {
       int keep = nw;
@@ -1107,7 +1338,7 @@ int Solver<T>::step_impl(int max_steps, int* passes_out) {
     int m = k + np + nw;
     if (indef) {
       if (int rc = rr_indef(m, k, false)) return rc;
-    } else if (int rc = rr_modified(m, k)) {
+    } else if (int rc = rr_modified(m)) {
       return rc;
     }
     if (!indef && useOrtho == 2) {
@@ -1116,7 +1347,7 @@ int Solver<T>::step_impl(int max_steps, int* passes_out) {
       LB2_TRY(ortho_drop(W, nw, V, k + np, &keep));
       nw = keep;
       m = k + np + nw;
-      if (int rc = rr_modified(m, k)) return rc;
+      if (int rc = rr_modified(m)) return rc;
     }
     // X_new = S Cx into the other slab
     T* Sn = slab[1 - cur];
@@ -1134,6 +1365,7 @@ int Solver<T>::step_impl(int max_steps, int* passes_out) {
     const int nact = k - nconv;
     T* Sold = slab[1 - cur];
     LB2_TRY(nn(m, nact, make<T>(1), Sold, Cp + (size_t)nconv * m, m, zero<T>(), col(Sn, k)));
+    if (!indef) LB2_TRY(update_gram_cache(m, nconv));
     {
       const T* BX = opB ? wA : Sn;
       T* Wdst = col(Sn, k + nact);
@@ -1324,7 +1556,10 @@ static void h_rr_mod(uint64_t n, uint64_t nx, uint64_t mult, uint64_t nconv, uin
   if (AX) { if (s.up(s.AS, AX, n, (int)nx)) return; }
   else if (s.apply(A, (int)nx, s.Xp(), s.AS)) return;
   s.useOrtho = *useOrtho;
-  if (s.rr_modified(m, (int)nx)) return;
+  s.np = (mult == 3) ? (int)(nx - nconv) : 0;   // S = [X | P_act | W]: the [X P] blocks are contracted from the tall vectors
+  s.nw = m - (int)nx - s.np;
+  s.cache_ok = false;
+  if (s.nw < 0 || s.rr_modified(m)) return;
   *useOrtho = (uint8_t)s.useOrtho;
   if (s.useOrtho == 2) return;
   s.down(Cx, s.Cx, m, (int)nx);

@@ -123,6 +123,11 @@ struct SolverBase {
   virtual int finish() = 0;
   virtual void state(uint64_t* iter, uint64_t* conv, int* use_ortho) = 0;
   virtual int results(double* eig, int neig, double* res, int nres) = 0;  // host copies of the last pass
+  virtual int set_option(const char* key, int value) = 0;   // "gram_cache", "gram_cache_period", "force_ortho", "debug_min_conv", "implicit"
+  virtual double info(const char* key) = 0;                  // "gram_cache_refreshes", "gram_cache_monitor", "arena_bytes", ...
+  virtual void write_failure_state() = 0;                    // alg->converged = 0, iter, eigVals/resNorm = NaN (run-time failure)
+  bool param_error = false;   // prepare() rejected the parameters with the reference's own message (outputs stay untouched, as there)
+  uint64_t cache_refreshes = 0;
   double phase_ms[PH_COUNT] = {0};
   double phase_work[PH_COUNT] = {0};   // algorithmic flops (gram, tall_nn) or bytes (spmm, residual)
   uint64_t phase_calls[PH_COUNT] = {0};

@@ -517,3 +517,59 @@ def test_chebyshev_operator_matches_oracle(ctx, dt, degree, inner, monkeypatch):
     ref = no.op_chebyshev(no.op_stencil(g, dt, potential=pot), degree, 0.25, 13.0)(
         X.astype(np.complex128 if np.dtype(dt).kind == "c" else np.float64))
     close(Y, ref, 1e-12 if rtol(dt) < 1e-6 else 1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ column-block Gram
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [  # (n, mxp, nw): S = [XP | W], products S^H W and S^H (A W)
+    (5000, 40, 20), (9000, 600, 300), (20000, 256, 128), (8193, 300, 130), (4099, 0, 150), (30001, 525, 225),
+    (2000, 24, 12), (12345, 263, 7)])
+def test_gram_cols_matches_numpy(ctx, dt, shape):
+    """lb2_<p>_gram_cols: both column-block products of the cached-Gram pass in one call.  Entries strictly below the
+    diagonal of the Hermitian W block may be left untouched (checked: they are either exact or still zero); everything
+    else must match numpy.  f64 with n >= 4096 runs the work-list kernel (aligned W-block tiles, balanced diagonal tiles,
+    ragged edges), the other types one rectangular product each."""
+    n, mxp, nw = shape
+    rng = np.random.default_rng(n + mxp + nw)
+    S = rand(rng, (n, mxp + nw), dt)
+    W = np.asfortranarray(S[:, mxp:])
+    h = rng.uniform(0.5, 1.5, n).astype(S.real.dtype)
+    AW = np.asfortranarray(h[:, None] * W)                      # Hermitian "operator": W^H A W is Hermitian
+    dS, dW, dAW = (api.DeviceArray.from_numpy(ctx, a) for a in (S, W, AW))
+    for tri in (mxp, -1):
+        G0, G1 = api.gram_cols(ctx, dS, dW, dAW, tri_c0=tri)
+        for got, ref in ((G0.numpy(ctx), S.conj().T @ W), (G1.numpy(ctx), S.conj().T @ AW)):
+            scale = float(np.abs(ref).max())
+            err = np.abs(got - ref) / scale
+            i, j = np.meshgrid(np.arange(mxp + nw), np.arange(nw), indexing="ij")
+            below = (i - mxp > j) if tri >= 0 else np.zeros_like(i, dtype=bool)
+            assert err[~below].max() < rtol(dt)
+            ok_below = (err < rtol(dt)) | (got == 0)
+            assert ok_below[below].all()
+    G0, _ = api.gram_cols(ctx, dS, dAW, None, tri_c0=mxp)        # single product (ortho branch)
+    got, ref = G0.numpy(ctx), S.conj().T @ AW
+    i, j = np.meshgrid(np.arange(mxp + nw), np.arange(nw), indexing="ij")
+    keep = ~(i - mxp > j)
+    assert (np.abs(got - ref)[keep] / float(np.abs(ref).max())).max() < rtol(dt)
+
+
+def test_gram_cols_full_size_linearity(ctx):
+    """C5 shape (n = 4.096 M rows would need 29 GB of host memory for numpy; use a size-independent property instead):
+    device-generated S, W = S[:, mxp:], AW = 2 W  =>  G1 = 2 G0 exactly, and the upper part of the W block of G0 equals
+    the Hermitian work-list Gram of W."""
+    n, mxp, nw = 1_000_000, 600, 300
+    S = api.fill_uniform(ctx, n, mxp + nw, np.float64, 5)
+    W = api.DeviceArray((n, nw), np.float64)
+    sel = np.zeros((mxp + nw, nw), order="F"); sel[mxp:, :] = np.eye(nw)
+    api.tall_nn(ctx, S, api.DeviceArray.from_numpy(ctx, sel), W)
+    AW = api.DeviceArray((n, nw), np.float64)
+    api.tall_nn(ctx, S, api.DeviceArray.from_numpy(ctx, 2.0 * sel), AW)
+    G0, G1 = api.gram_cols(ctx, S, W, AW, tri_c0=mxp)
+    g0, g1 = G0.numpy(ctx), G1.numpy(ctx)
+    i, j = np.meshgrid(np.arange(mxp + nw), np.arange(nw), indexing="ij")
+    keep = ~(i - mxp > j)
+    assert np.max(np.abs(2.0 * g0 - g1)[keep]) / np.abs(g1).max() < 1e-13     # (the two products split their rows differently)
+    Gww = api.gram(ctx, W, W, upper=True).numpy(ctx)
+    up = np.triu_indices(nw)
+    blk = g0[mxp:, :]
+    assert np.max(np.abs(blk[up] - Gww[up])) / np.abs(Gww).max() < 1e-13

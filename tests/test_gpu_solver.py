@@ -351,6 +351,30 @@ def test_invalid_parameters_return_without_touching_outputs(capfd):
     assert "3*sizeSub" in capfd.readouterr().err
 
 
+def test_status_of_the_void_entry_points(capfd):
+    """lb2_last_status: 1 = parameters rejected, outputs untouched like the reference; 2 = run-time failure with
+    a defined state (converged 0, NaN eigenvalues) instead of stale zeros; operator shapes are checked up front."""
+    A = api.stencil_op((10,), np.float64)
+    r = api.lobpcg(A, pr.initial_block(10, 4, 1), 2, 1e-8, 10)
+    assert r["status"] == 1 and np.all(r["eig"] == 0)
+    # B with the wrong number of rows: rejected before any kernel could run past a block
+    A = api.stencil_op((10, 10, 10), np.float64)
+    X0 = pr.initial_block(1000, 8, 1)
+    r = api.lobpcg(A, X0, 4, 1e-8, 10, B=api.diag_op(np.ones(999), np.float64))
+    assert r["status"] == 1 and np.array_equal(r["X"], X0)
+    assert "operator B has 999" in capfd.readouterr().err
+    # operator of another scalar type
+    r = api.lobpcg(A, X0, 4, 1e-8, 10, T=api.diag_op(np.ones(1000), np.float32))
+    assert r["status"] == 1
+    # a device block operator that reports an error: run-time failure
+    bad = api.device_op(1000, np.float64, lambda nc, X, ldx, Y, ldy, stream: 7)
+    r = api.lobpcg(bad, X0, 4, 1e-8, 10)
+    assert r["status"] == 2 and r["converged"] == 0 and np.all(np.isnan(r["eig"])) and np.all(np.isnan(r["res"][:4]))
+    # and a good run resets it
+    r = api.lobpcg(A, X0, 4, 1e-8, 2000)
+    assert r["status"] == 0 and r["converged"] == 4
+
+
 def test_resumable_solver_matches_one_shot_and_reports_stats(ctx):
     g, n, nev, k = (40, 40), 1600, 4, 8
     A = api.stencil_op(g, np.float64)
