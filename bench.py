@@ -27,6 +27,42 @@ sys.path.insert(0, str(ROOT))
 FP64_PEAK_FILE = ROOT / "profiles" / "fp64_peak_probe_r01.jsonl"
 
 
+def fp64_peak_probe(stream, device_index, seconds=1.0):
+    """FP64 peak measured IN THIS RUN: cuBLAS DGEMM 8192^3 (through torch.matmul) back to back for ~`seconds`, CUDA events
+    on the launching stream, SM clocks sampled during the probe.  A probe of the library peak, not a product path."""
+    import torch
+    n = 8192
+    with torch.cuda.stream(stream):
+        a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        c = torch.empty(n, n, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            torch.matmul(a, b, out=c)
+        stream.synchronize()
+        sampler = ClockSampler(device_index)
+        sampler.start()
+        time.sleep(0.25)
+        t0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 0
+        e0.record(stream)
+        while True:
+            for _ in range(4):
+                torch.matmul(a, b, out=c)
+            iters += 4
+            stream.synchronize()
+            if time.time() - t0 >= seconds:
+                break
+        e1.record(stream)
+        stream.synchronize()
+        t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1)
+    del a, b, c
+    return {"tflops": 2.0 * n ** 3 * iters / (ms * 1e-3) / 1e12, "iters": iters, "ms": ms, "clocks": clocks,
+            "what": "cuBLAS DGEMM 8192^3 via torch.matmul(float64), back to back, measured inside this bench run"}
+
+
 def measured_peaks():
     hbm, how_hbm = 6650.0, "fallback"
     p = ROOT / "MEASURED_PEAKS.json"
@@ -95,55 +131,128 @@ def workload_desc(g, nev, k):
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-def cpu_reference_rate(g_full, nev, k, steps, threads=None):
-    """Times the UNMODIFIED reference (oracle/_ref) on a bounded sample: same operator family and block
-    sizes on a g_s^3 grid; iter/s is scaled to the full row count (every O(n) term of a pass is linear in n;
-    the O(k^3) small dense part is kept unscaled in the measured time, which favours the CPU)."""
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 0
+
+
+def _ref_time_passes(rb, A, X0, nev, passes):
+    """Seconds per pass of the UNMODIFIED reference: T(maxIter = passes) - T(maxIter = 0) over `passes` (the reference
+    has no timers of its own; its set-up — allocation, ||A|| estimate, initial Rayleigh-Ritz — is in both runs)."""
+    t0 = time.perf_counter(); rb.solve(A, X0, nev, 1e-8, 0); t_init = time.perf_counter() - t0
+    t0 = time.perf_counter(); r = rb.solve(A, X0, nev, 1e-8, passes); t_run = time.perf_counter() - t0
+    done = max(int(r["iter"]), 1)
+    loop = t_run - t_init
+    if loop < 0.05 * t_run:      # tiny samples: the difference of two short timings is noise
+        loop = t_run
+    return loop / done, done, t_init, t_run
+
+
+def cpu_reference_rate(g_full, nev, k, steps, threads=None, g_sample=None):
+    """Bounded sample for the `cpu_baseline` block of our own line: the unmodified reference on a g_s^3 grid with the
+    same nev / sizeSub; iter/s scaled to the full row count and LABELLED as extrapolated (every O(n) term of a pass is
+    linear in n; the O(k^3) small dense part stays unscaled in the measured time, which favours the CPU).  The
+    reference ARM (--impl reference) runs the real configuration instead."""
     from oracle import ref_bindings as rb
     from lobpcg_b200 import problems as pr
     if not rb.available():
         return None
     threads = threads or os.cpu_count() or 1
     rb.set_threads(threads)
-    g_s = 64 if k >= 200 else 96
+    g_s = g_sample or (64 if k >= 200 else 96)
     g_s = min(g_s, g_full)
     n_s = g_s ** 3
     A = rb.op_stencil((g_s, g_s, g_s), np.float64)
     X0 = pr.initial_block(n_s, k, 7)
-    t0 = time.perf_counter(); rb.solve(A, X0, nev, 1e-8, 0); t_init = time.perf_counter() - t0
-    t0 = time.perf_counter(); r = rb.solve(A, X0, nev, 1e-8, steps); t_run = time.perf_counter() - t0
-    passes = max(int(r["iter"]), 1)
-    # tiny samples: the difference of two short timings is noise; fall back to the whole call
-    per_pass = (t_run - t_init if t_run - t_init > 0.05 * t_run else t_run) / passes
+    per_pass, passes, t_init, t_run = _ref_time_passes(rb, A, X0, nev, steps)
     scale = n_s / float(g_full ** 3)
     return dict(value=scale / per_pass, unit="iter/s", cores=threads, kind="reference",
+                extrapolated=(g_s != g_full),
                 sample=(f"unmodified reference (oracle/_ref, OpenBLAS {rb.blas_config().split()[1]}, {threads} threads) "
-                        f"on {g_s}^3 rows with the same nev={nev}, sizeSub={k}: {passes} passes in {t_run - t_init:.2f} s "
-                        f"(init {t_init:.2f} s excluded), iter/s scaled by n_sample/n_full = {scale:.4f}"),
+                        f"on a {g_s}^3 SAMPLE (n={n_s}) with the same nev={nev}, sizeSub={k}: {passes} passes in "
+                        f"{t_run - t_init:.2f} s (set-up {t_init:.2f} s excluded); iter/s EXTRAPOLATED to n={g_full ** 3} "
+                        f"by n_sample/n_full = {scale:.4f}" if g_s != g_full else
+                        f"unmodified reference (oracle/_ref, OpenBLAS {rb.blas_config().split()[1]}, {threads} threads) "
+                        f"on the full {g_full}^3 grid: {passes} passes in {t_run - t_init:.2f} s (set-up {t_init:.2f} s excluded)"),
                 sample_seconds_per_pass=per_pass)
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation (unmodified sources compiled as oracle/_ref) on the SAME
+    configuration — the real grid whenever host memory and the time budget allow, with as many passes of the requested
+    K as fit the budget (>= 3).  Only when the full grid does not fit: the largest grid that does, flagged extrapolated."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import ref_bindings as rb
+    from lobpcg_b200 import problems as pr
     g, nev = args.grid, args.nev
     k = 2 * nev
-    t0 = time.perf_counter()
-    cb = cpu_reference_rate(g, nev, k, max(args.steps, 1))
-    if cb is None:
+    if not rb.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_lobpcg.so missing (make -C oracle)"}))
         return
-    wall = time.perf_counter() - t0
+    t_wall = time.perf_counter()
+    threads = os.cpu_count() or 1
+    rb.set_threads(threads)
+    # calibration on a small grid: seconds per pass and row, set-up seconds per row
+    g_c = min(48, g)
+    while 3 * k > g_c ** 3:
+        g_c += 8
+    Ac = rb.op_stencil((g_c, g_c, g_c), np.float64)
+    per_pass_c, _, t_init_c, _ = _ref_time_passes(rb, Ac, pr.initial_block(g_c ** 3, k, 7), nev, 2)
+    del Ac
+    per_row, init_per_row = per_pass_c / g_c ** 3, t_init_c / g_c ** 3
+    budget = float(args.ref_budget)
+
+    def need_bytes(gg):      # reference footprint 12 n k scalars (lobpcg.h:597-608) + X0 + its copy in the harness + slack
+        return int(14.5 * gg ** 3 * k * 8 * 1.1) + (2 << 30)
+
+    def est_seconds(gg, passes):   # two runs (with and without the loop), each with the set-up
+        return 2.0 * init_per_row * gg ** 3 + passes * per_row * gg ** 3
+
+    avail = mem_available_bytes()
+    g_run, why = g, None
+    if need_bytes(g) > avail:
+        why = f"host MemAvailable {avail / 2**30:.0f} GiB < {need_bytes(g) / 2**30:.0f} GiB needed for the full grid"
+    elif est_seconds(g, 3) > budget:
+        why = f"3 passes of the full grid estimated at {est_seconds(g, 3):.0f} s > budget {budget:.0f} s"
+    if why:
+        g_run = g
+        while g_run > g_c and (need_bytes(g_run) > avail or est_seconds(g_run, 3) > budget):
+            g_run -= 8
+        g_run = max(g_run, g_c)
+    n_run = g_run ** 3
+    passes = int(max(3, min(max(args.steps, 1), (budget - 2.0 * init_per_row * n_run) / max(per_row * n_run, 1e-9))))
+    A = rb.op_stencil((g_run, g_run, g_run), np.float64)
+    X0 = pr.initial_block(n_run, k, 7)
+    per_pass, done, t_init, t_run = _ref_time_passes(rb, A, X0, nev, passes)
+    scale = n_run / float(g ** 3)
+    value = scale / per_pass
+    extrapolated = g_run != g
+    sample = (f"unmodified reference (oracle/_ref, OpenBLAS {rb.blas_config().split()[1]}, {threads} threads) on "
+              f"{'the full' if not extrapolated else 'a REDUCED'} {g_run}^3 grid (n={n_run}), nev={nev}, sizeSub={k}: {done} passes in "
+              f"{t_run - t_init:.1f} s (set-up {t_init:.1f} s timed separately and excluded)"
+              + (f"; iter/s EXTRAPOLATED to n={g ** 3} by n_run/n_full = {scale:.4f} because {why}" if extrapolated else ""))
+    wl = workload_desc(g, nev, k)
+    if extrapolated:
+        wl += f" — reference arm timed on {g_run}^3 (n={n_run}) and extrapolated"
     line = {
-        "impl": "reference", "metric": "lobpcg_iters_per_s", "value": cb["value"], "unit": "iter/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(g, nev, k), "device": "host CPU"},
-        "cpu_baseline": {k2: cb[k2] for k2 in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {"value": cb["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": wall,
+        "impl": "reference", "metric": "lobpcg_iters_per_s", "value": value, "unit": "iter/s",
+        "n_gpus": args.gpus, "steps": done, "steps_requested": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 / value, "measured_ms_per_step": 1e3 * per_pass, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "extrapolated": extrapolated,
+        "config": {"workload": wl, "device": "host CPU", "grid_timed": g_run, "rows_timed": n_run,
+                   "passes_timed": done, "budget_s": budget,
+                   "calibration": f"{g_c}^3: {per_pass_c:.3f} s/pass, set-up {t_init_c:.2f} s"},
+        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": threads, "kind": "reference", "sample": sample,
+                         "extrapolated": extrapolated},
+        "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_wall,
     }
     print(json.dumps(line))
 
@@ -213,11 +322,49 @@ def run_ours(args):
     launches = ctx.launches - l0
     st = s.stats()
     prog = s.progress()
+    gram_cache_info = {"enabled": bool(s.info("gram_cache")), "refreshes_in_timed_region": None,
+                       "monitor_max": s.info("gram_cache_monitor_max"), "arena_columns_per_k": s.info("arena_columns") / k,
+                       "arena_gb": s.info("arena_bytes") / 1e9}
     if done != args.steps:
         raise SystemExit(f"solver stopped after {done} of {args.steps} passes (converged early?)")
 
+    # ---- further timing windows on the same solver: ~50 % of the columns soft-locked, then the
+    # sticky ortho branch (forced through a solver option); device time, max over ranks, like the main window
+    windows = {}
+    if not args.no_windows:
+        def timed_window(name, nsteps, note):
+            s.step(2)                      # settle into the new mode
+            barrier()
+            s.reset_stats()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                ea.record(stream)
+                dn = s.step(nsteps)
+                eb.record(stream)
+            barrier()
+            t = ea.elapsed_time(eb)
+            if world > 1:
+                tt = torch.tensor([t], device="cuda")
+                torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+                t = float(tt.item())
+            stw = s.stats()
+            windows[name] = {"ms_per_step": t / max(dn, 1), "steps": dn, "note": note, "solver_state": s.progress(),
+                             "ms": {kk: stw[kk]["ms"] / max(dn, 1) for kk in ("gram", "tall_nn", "spmm", "residual", "small_dense", "comm")}}
+        nw_steps = max(3, min(args.steps, 6))
+        s.set_option("debug_min_conv", nev // 2)
+        timed_window("softlocked", nw_steps, f"Cholesky branch with the leading {nev // 2} of {k} columns soft-locked "
+                     "(forced: option debug_min_conv; P and W shrink to the active columns)")
+        s.set_option("debug_min_conv", 0)
+        s.set_option("force_ortho", 1)
+        timed_window("ortho", nw_steps, "sticky ortho branch (forced: option force_ortho): ortho_drop(W | [X P]) + RR without the B-Gram")
+
     # per-kernel achieved rates over the timed region (phase timers = CUDA events on the solver stream)
     hbm, how_hbm, fp64, how64 = measured_peaks()
+    probe = None
+    if not args.no_fp64_probe:
+        probe = fp64_peak_probe(stream, local_rank)
+        fp64, how64 = probe["tflops"], probe["what"] + " (clocks: %s MHz median, reasons %s)" % (
+            probe["clocks"].get("sm_mhz"), probe["clocks"].get("reasons"))
     def rate(name, unit_div):
         d = st[name]
         return (d["work"] / (d["ms"] * 1e-3) / unit_div) if d["ms"] > 0 else 0.0
@@ -237,17 +384,24 @@ def run_ours(args):
         "comm": {"ms_per_step": st["comm"]["ms"] / done},
     }
     traffic = None
-    tf = ROOT / "profiles" / "ncu_traffic_r01.json"
+    tf = ROOT / "profiles" / "ncu_traffic_r02.json"
     if tf.exists() and g == 160 and nev == 150 and world == 1:   # the ncu capture is of this shape on one GPU
-        t = json.loads(tf.read_text())["gram_wl_kernel"]
-        traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])
+        try:
+            t = json.loads(tf.read_text())["gram_wl_kernel_cols"]
+            traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])
+        except Exception:
+            traffic = None
     roofline = {
-        "kernel": "gram_wl_kernel + gram_dmma_kernel strip (K2/K3: S^H S and S^H A S, FP64 tensor pipe DMMA.8x8x4)",
+        "kernel": "gram_wl_kernel (K2/K3, FP64 tensor pipe DMMA.8x8x4): per pass ONE launch for the W columns of both Grams, "
+                  "[X P W]^H [W | A W]; the [X P] blocks come from the cached C^H G C (SURVEY 8f-2)",
         "bound": "tensor", "achieved": gram_tf, "peak": fp64, "unit": "TFLOP/s", "frac": gram_tf / fp64,
-        "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu, profiles/ncu_traffic_r01.json); "
-                                             "algorithmic operand bytes per launch = n*m*8 = %.3g" % (n_local * 3.0 * k * 8),
+        "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/ncu_traffic_r02.json); "
+                                             "algorithmic operand bytes per launch = n*(m + 2 n_w)*8 = %.3g" % (n_local * 5.0 * k * 8),
         "peak_source": how64, "per_gpu": True,
         "algorithmic_flops_per_launch": st["gram"]["work"] / max(st["gram"]["calls"], 1) / world,
+        "algorithmic_flops_note": "needed entries only: 2 products x n x (2 m_xp n_w + n_w (n_w + 1)); a recomputation of the "
+                                  "cached blocks (every 64 passes) adds the Hermitian [X P] products",
+        "fp64_probe": probe,
         "share_of_step": st["gram"]["ms"] / (ms if ms > 0 else 1.0),
     }
 
@@ -325,6 +479,7 @@ def run_ours(args):
                        "solver_state": prog},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "time_to_solution": tts, "gpu_launches": int(launches),
             "clocks": clocks, "kernels": kernels, "hbm_peak_gbs": hbm, "hbm_peak_source": how_hbm,
+            "windows": windows, "gram_cache": gram_cache_info,
         }
         print(json.dumps(line))
     if world > 1:
@@ -339,6 +494,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=160)
     ap.add_argument("--nev", type=int, default=150)
+    ap.add_argument("--ref-budget", type=float, default=300.0,
+                    help="--impl reference: seconds for the two timed reference runs (set-up twice + the passes)")
+    ap.add_argument("--no-windows", action="store_true", help="skip the ortho-mode and soft-locked timing windows")
+    ap.add_argument("--no-fp64-probe", action="store_true", help="use the committed FP64 peak instead of probing it in this run")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tts", action="store_true", help="skip the preconditioned full solve (time_to_solution)")

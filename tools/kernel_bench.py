@@ -48,6 +48,18 @@ elif mode == "gram":
     med, mn = timeit(lambda: fn(ctx.h, n, m, mb, A.ptr, A.ld, B.ptr, B.ld, G.ptr, m, int(upper)))
     fl = CMUL * (n * m * (m + 1.0) if upper else 2.0 * n * m * mb)
     print(json.dumps(dict(kernel="gram", dtype=str(np.dtype(DT)), n=n, m=m, mb=mb, upper=upper, ms=med, ms_min=mn, pad=PAD, tflops=fl / med / 1e9, frac=fl / med / 1e9 / 35.76, gbs=8.0 * n * (m + (0 if upper else mb)) / med / 1e6)))
+elif mode == "gramcols":   # [X P W]^H [W | AW]: gramcols N MXP NW [single] [notri]
+    n, mxp, nw = int(args[0]), int(args[1]), int(args[2])
+    m = mxp + nw
+    S = api.fill_uniform(ctx, n, m, DT, 1); AW = api.fill_uniform(ctx, n, nw, DT, 2)
+    W = S.rows(0, n); W = api.DeviceArray.__new__(api.DeviceArray); W.shape, W.dtype, W.ld, W.ptr, W.nbytes, W._owner = (n, nw), S.dtype, S.ld, S.ptr + mxp * S.ld * S.dtype.itemsize, 0, S
+    G0 = api.DeviceArray((m, nw), DT); G1 = api.DeviceArray((m, nw), DT)
+    L = api.lib(); fn = getattr(L, f"lb2_{PFX}_gram_cols")
+    single = "single" in args; tri = -1 if "notri" in args else mxp
+    med, mn = timeit(lambda: fn(ctx.h, n, m, nw, S.ptr, S.ld, W.ptr, W.ld, G0.ptr, m, None if single else AW.ptr, AW.ld, None if single else G1.ptr, m, tri))
+    nprod = 1 if single else 2
+    fl = CMUL * nprod * n * (2.0 * mxp * nw + nw * (nw + 1.0))
+    print(json.dumps(dict(kernel="gram_cols", dtype=str(np.dtype(DT)), n=n, mxp=mxp, nw=nw, nprod=nprod, tri=tri, ms=med, ms_min=mn, tflops_needed=fl / med / 1e9, frac=fl / med / 1e9 / 35.76, tflops_rect=CMUL * nprod * 2.0 * n * m * nw / med / 1e9)))
 elif mode == "nn":
     n, kd, nb = int(args[0]), int(args[1]), int(args[2])
     S = api.fill_uniform(ctx, n, kd, DT, 1, ld=n + PAD); Cm = api.fill_uniform(ctx, kd, nb, DT, 2); O = api.DeviceArray((n, nb), DT, ld=n + PAD)
