@@ -472,6 +472,203 @@ int sd_assemble_gram(lb2_ctx* ctx, int m, int mxp, const T* Gc, int ldc, const T
   return 0;
 }
 
+// ---- general (non-definite) projected pencil: G_A v = theta G_B v through a non-symmetric standard problem -----------
+// The reference hands (G_A, G_B) to LAPACK GGEV (src/rayleigh/indefinite_rr_modified_impl.inc:94-118); cuSOLVER has no
+// GGEV, so the pencil is reduced with an LU solve, M = G_B^-1 G_A (G_B = S^H B S is Hermitian indefinite but non-singular
+// for a B-orthonormalised basis), and M goes to cusolverDnXgeev in complex arithmetic.  Used when S^H A S is not positive
+// definite (otherwise the Hermitian form in Solver::rr_indef applies).
+
+// B (m x nrhs) <- A^-1 B by LU with partial pivoting; A is overwritten by its factors.  ipiv: m int64 on the device.
+template <typename T>
+int sd_lu_solve(lb2_ctx* ctx, int m, T* A, int lda, T* B, int ldb, int nrhs, int64_t* ipiv, int* h_info) {
+  if (sd_init(ctx)) return -1;
+  size_t wd = 0, wh = 0;
+  LB2_SOLVER_OK(cusolverDnXgetrf_bufferSize(ctx->cusolver, g_params, m, m, CudaType<T>::v, A, lda, CudaType<T>::v, &wd, &wh));
+  if (ensure_ws(ctx, wd, wh)) return -1;
+  LB2_SOLVER_OK(cusolverDnXgetrf(ctx->cusolver, g_params, m, m, CudaType<T>::v, A, lda, ipiv, CudaType<T>::v, ctx->solver_ws,
+                                 wd, ctx->solver_hws, wh, ctx->dev_info));
+  ctx->launches++;
+  if (read_info(ctx, h_info)) return -1;
+  if (*h_info != 0) return 0;
+  LB2_SOLVER_OK(cusolverDnXgetrs(ctx->cusolver, g_params, CUBLAS_OP_N, m, nrhs, CudaType<T>::v, A, lda, ipiv, CudaType<T>::v,
+                                 B, ldb, ctx->dev_info));
+  ctx->launches++;
+  return read_info(ctx, h_info);
+}
+
+template <typename T, typename CT>
+__global__ void to_complex_kernel(int m, const T* __restrict__ A, int lda, CT* __restrict__ C, int ldc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * m) return;
+  const int i = idx % m, j = idx / m;
+  const T a = A[i + (int64_t)j * lda];
+  if constexpr (Sc<T>::cplx) C[i + (int64_t)j * ldc] = a;
+  else C[i + (int64_t)j * ldc] = CT{a, real_t<T>(0)};
+}
+
+// eigenvalues W (complex, m) and right eigenvectors VR (complex, m x m) of the m x m matrix M (type T, destroyed is Mc)
+// Mc, W, VR: complex scratch of m*m, m, m*m elements of ComplexOf<T>.
+template <typename T>
+int sd_geev(lb2_ctx* ctx, int m, const T* M, int ldm, void* Mc_, void* W_, void* VR_, int* h_info) {
+  using CT = typename ComplexOf<T>::type;
+  if (sd_init(ctx)) return -1;
+  CT* Mc = (CT*)Mc_;
+  CT* W = (CT*)W_;
+  CT* VR = (CT*)VR_;
+  to_complex_kernel<T, CT><<<(m * m + 255) / 256, 256, 0, ctx->stream>>>(m, M, ldm, Mc, m);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  size_t wd = 0, wh = 0;
+  constexpr cudaDataType ct = CudaType<CT>::v;
+  LB2_SOLVER_OK(cusolverDnXgeev_bufferSize(ctx->cusolver, g_params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_VECTOR, m, ct,
+                                           Mc, m, ct, W, ct, nullptr, m, ct, VR, m, ct, &wd, &wh));
+  if (ensure_ws(ctx, wd, wh)) return -1;
+  LB2_SOLVER_OK(cusolverDnXgeev(ctx->cusolver, g_params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_VECTOR, m, ct, Mc, m, ct,
+                                W, ct, nullptr, m, ct, VR, m, ct, ctx->solver_ws, wd, ctx->solver_hws, wh, ctx->dev_info));
+  ctx->launches++;
+  return read_info(ctx, h_info);
+}
+
+// theta[j] = Re(W[j]);  V[:, j] = VR[:, j] rotated so that its largest component is real positive (a real pencil with a
+// real eigenvalue has a real eigenvector up to that phase; the reference's real GGEV returns exactly that), cast to T.
+template <typename T, typename CT>
+__global__ void geev_extract_kernel(int m, const CT* __restrict__ W, const CT* __restrict__ VR, real_t<T>* __restrict__ theta,
+                                    T* __restrict__ V, int ldv) {
+  using R = real_t<T>;
+  const int j = blockIdx.x;
+  __shared__ R smax[128];
+  __shared__ int sidx[128];
+  R best = -1;
+  int bi = 0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const R a = abs2_(VR[i + (int64_t)j * m]);
+    if (a > best) { best = a; bi = i; }
+  }
+  smax[threadIdx.x] = best;
+  sidx[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const bool take = smax[threadIdx.x + o] > smax[threadIdx.x] ||
+                        (smax[threadIdx.x + o] == smax[threadIdx.x] && sidx[threadIdx.x + o] < sidx[threadIdx.x]);
+      if (take) { smax[threadIdx.x] = smax[threadIdx.x + o]; sidx[threadIdx.x] = sidx[threadIdx.x + o]; }
+    }
+    __syncthreads();
+  }
+  const CT piv = VR[sidx[0] + (int64_t)j * m];
+  const R pa = sqrt(abs2_(piv));
+  const CT ph = (pa > R(0)) ? CT{piv.re / pa, -piv.im / pa} : CT{R(1), R(0)};   // conj(piv) / |piv|
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const CT v = mul_(VR[i + (int64_t)j * m], ph);
+    if constexpr (Sc<T>::cplx) V[i + (int64_t)j * ldv] = v;
+    else V[i + (int64_t)j * ldv] = v.re;
+  }
+  if (threadIdx.x == 0) theta[j] = W[j].re;
+}
+template <typename T>
+int sd_geev_extract(lb2_ctx* ctx, int m, const void* W, const void* VR, real_t<T>* theta, T* V, int ldv) {
+  using CT = typename ComplexOf<T>::type;
+  geev_extract_kernel<T, CT><<<m, 128, 0, ctx->stream>>>(m, (const CT*)W, (const CT*)VR, theta, V, ldv);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// B-normalisation of eigenvector columns (indefinite_rr_modified_impl.inc:136-176): E = V^H G_B V given, column j is scaled
+// by 1 / sqrt(|E_jj|) (when |E_jj| > 1e-30); sig (may be null) receives sign(Re E_jj).
+template <typename T>
+__global__ void bnormalize_kernel(int m, T* __restrict__ V, int ldv, const T* __restrict__ E, int lde, int8_t* __restrict__ sig) {
+  using R = real_t<T>;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * m) return;
+  const int i = idx % m, j = idx / m;
+  const T d = E[j + (int64_t)j * lde];
+  const R a = sqrt(abs2_(d));
+  if (a > R(1e-30)) V[i + (int64_t)j * ldv] = rscale_(V[i + (int64_t)j * ldv], R(1) / sqrt(a));
+  if (sig && i == 0) sig[j] = (real_(d) >= R(0)) ? 1 : -1;
+}
+template <typename T>
+int sd_bnormalize(lb2_ctx* ctx, int m, T* V, int ldv, const T* E, int lde, int8_t* sig) {
+  bnormalize_kernel<T><<<(m * m + 255) / 256, 256, 0, ctx->stream>>>(m, V, ldv, E, lde, sig);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// quality numbers of the reference (indefinite_rr_modified_impl.inc:178-192): out[0] = || E with |E_jj| - 1 on the diagonal ||_F,
+// out[1] = ||V||_F, out[2] = ||G_B V||_F
+template <typename T>
+__global__ void indef_quality_kernel(int m, const T* __restrict__ E, const T* __restrict__ V, const T* __restrict__ GV,
+                                     real_t<T>* __restrict__ out) {
+  using R = real_t<T>;
+  __shared__ R r0[256], r1[256], r2[256];
+  R a = 0, b = 0, c = 0;
+  for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+    const int i = idx % m, j = idx / m;
+    const R e = (i == j) ? sqrt(abs2_(E[idx])) - R(1) : sqrt(abs2_(E[idx]));
+    a += e * e;
+    b += abs2_(V[idx]);
+    c += abs2_(GV[idx]);
+  }
+  r0[threadIdx.x] = a; r1[threadIdx.x] = b; r2[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { r0[threadIdx.x] += r0[threadIdx.x + o]; r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sqrt(r0[0]); out[1] = sqrt(r1[0]); out[2] = sqrt(r2[0]); }
+}
+template <typename T>
+int sd_indef_quality(lb2_ctx* ctx, int m, const T* E, const T* V, const T* GV, real_t<T>* out_dev) {
+  indef_quality_kernel<T><<<1, 256, 0, ctx->stream>>>(m, E, V, GV, out_dev);   // E, V, GV packed (ld = m)
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// signature sort (bubble_sort_sig_impl.inc: positive signature first with theta ascending, then negative with theta
+// descending; stable) + column reordering: Vout[:, rank(j)] = V[:, j]
+template <typename T>
+__global__ void indef_sort_kernel(int m, const real_t<T>* __restrict__ theta, const int8_t* __restrict__ sig,
+                                  const T* __restrict__ V, int ldv, T* __restrict__ Vout, int ldo,
+                                  real_t<T>* __restrict__ theta_out, int8_t* __restrict__ sig_out) {
+  const int j = blockIdx.x;
+  __shared__ int rank_s;
+  __shared__ int cnt[128];
+  const int sj = sig[j];
+  const real_t<T> tj = theta[j];
+  int c = 0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    if (i == j) continue;
+    const int si = sig[i];
+    const real_t<T> ti = theta[i];
+    bool before;   // does i come before j ?
+    if (si > 0 && sj < 0) before = true;
+    else if (si < 0 && sj > 0) before = false;
+    else if (si > 0) before = (ti < tj) || (ti == tj && i < j);
+    else before = (ti > tj) || (ti == tj && i < j);
+    c += before ? 1 : 0;
+  }
+  cnt[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) cnt[threadIdx.x] += cnt[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { rank_s = cnt[0]; theta_out[cnt[0]] = tj; sig_out[cnt[0]] = (int8_t)sj; }
+  __syncthreads();
+  const int r = rank_s;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) Vout[i + (int64_t)r * ldo] = V[i + (int64_t)j * ldv];
+}
+template <typename T>
+int sd_indef_sort(lb2_ctx* ctx, int m, const real_t<T>* theta, const int8_t* sig, const T* V, int ldv, T* Vout, int ldo,
+                  real_t<T>* theta_out, int8_t* sig_out) {
+  indef_sort_kernel<T><<<m, 128, 0, ctx->stream>>>(m, theta, sig, V, ldv, Vout, ldo, theta_out, sig_out);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 #define LB2_INST(T)                                                                                         \
   template int sd_potrf_upper<T>(lb2_ctx*, int, T*, int, int*);                                             \
   template int sd_syevd_upper<T>(lb2_ctx*, int, T*, int, real_t<T>*, int*);                                 \
@@ -489,7 +686,13 @@ int sd_assemble_gram(lb2_ctx* ctx, int m, int mxp, const T* Gc, int ldc, const T
   template int sd_gemm_ab<T>(lb2_ctx*, char, int, int, int, T, const T*, int, const T*, int, T, T*, int); \
   template int sd_indef_finalize<T>(lb2_ctx*, int, const real_t<T>*, const T*, int, T*, int, real_t<T>*, int8_t*); \
   template int sd_cp_lower<T>(lb2_ctx*, int, int, const T*, T*);                                           \
-  template int sd_assemble_gram<T>(lb2_ctx*, int, int, const T*, int, const T*, int, T*, int);
+  template int sd_assemble_gram<T>(lb2_ctx*, int, int, const T*, int, const T*, int, T*, int);          \
+  template int sd_lu_solve<T>(lb2_ctx*, int, T*, int, T*, int, int, int64_t*, int*);                       \
+  template int sd_geev<T>(lb2_ctx*, int, const T*, int, void*, void*, void*, int*);                        \
+  template int sd_geev_extract<T>(lb2_ctx*, int, const void*, const void*, real_t<T>*, T*, int);           \
+  template int sd_bnormalize<T>(lb2_ctx*, int, T*, int, const T*, int, int8_t*);                           \
+  template int sd_indef_quality<T>(lb2_ctx*, int, const T*, const T*, const T*, real_t<T>*);               \
+  template int sd_indef_sort<T>(lb2_ctx*, int, const real_t<T>*, const int8_t*, const T*, int, T*, int, real_t<T>*, int8_t*);
 LB2_INST(float)
 LB2_INST(double)
 LB2_INST(c32)

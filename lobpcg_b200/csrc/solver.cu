@@ -230,6 +230,7 @@ class Solver : public SolverBase {
       gram_cache_forced = true;
     } else if (!strcmp(key, "gram_cache_period")) cache_period = value > 0 ? value : 1;
     else if (!strcmp(key, "force_ortho")) force_ortho = value;
+    else if (!strcmp(key, "indef_geev")) indef_geev = value;
     else if (!strcmp(key, "debug_min_conv")) debug_min_conv = value;
     else return -1;
     return 0;
@@ -240,6 +241,8 @@ class Solver : public SolverBase {
     if (!strcmp(key, "gram_cache_refreshes")) return (double)cache_refreshes;
     if (!strcmp(key, "gram_cache_monitor")) return cache_monitor;
     if (!strcmp(key, "gram_cache_monitor_max")) return cache_monitor_max;
+    if (!strcmp(key, "general_rr_calls")) return (double)general_rr_calls;
+    if (!strcmp(key, "quality5_passes")) return (double)quality5_passes;
     if (!strcmp(key, "arena_bytes")) return (double)arena_bytes;
     if (!strcmp(key, "arena_columns")) return n > 0 ? (double)arena_bytes / ((double)n * sizeof(T)) : 0.0;
     return -1;
@@ -311,6 +314,14 @@ class Solver : public SolverBase {
   int cache_period = 64;         // option "gram_cache_period": recompute the [X P] blocks from the tall vectors every .. passes
   double cache_monitor = 0;      // last drift monitor value (max |x^H B x - 1|, |x^H A x - theta| / ||A|| over the nev columns)
   double cache_monitor_max = 0;
+  // general indefinite Rayleigh-Ritz (rr_indef_general)
+  int indef_geev = 0;            // option "indef_geev": 1 = always take the GEEV route (testing); default: only when S^H A S is not positive definite
+  int last_quality = 1;          // quality_flag of the last indefinite RR: 1 or 5 (indefinite_rr_modified_impl.inc:236-251)
+  uint64_t general_rr_calls = 0, quality5_passes = 0;
+  void* geev_ws = nullptr;       // complex scratch of Xgeev (lazy)
+  int64_t* geev_piv = nullptr;
+  int8_t* geev_sig = nullptr;
+  T* CxAcc = nullptr;            // accurate Cx of a quality-5 pass (lazy)
   // testing / measurement switches (lb2_solver_set_option)
   int force_ortho = 0;           // 1: run every pass in the ortho branch (useOrtho = 1 from the first pass)
   int debug_min_conv = 0;        // soft-lock at least this many leading columns regardless of their residuals (timing only)
@@ -352,9 +363,11 @@ class Solver : public SolverBase {
   int apply_cheb_mixed(const BuiltinOp* b, const BuiltinOp* in, int nc, const T* X, T* Y);
   int ortho_drop(T* U, int nu, T* V, int nv, int* nret, bool indefinite = false);
   int rr_indef(int m, int from_col, bool initial);
+  int rr_indef_general(int m, bool initial);
   int ortho_indef_mat(int m, int nu, int nv, T* U, const T* V, const T* mat);
   int svqb_mat_dev(int m, int nu, T* U, const T* mat, R tau);
-  int residual_pass(bool initial);
+  int residual_pass(bool initial, const T* Xacc = nullptr);
+  const T *res_AX = nullptr, *res_BX = nullptr;   // operands of the last residual (A X, B X — or of X_accurate in a quality-5 pass)
   int step_impl(int max_steps, int* passes_out);
   void print_state(bool header);
 };
@@ -371,6 +384,10 @@ void Solver<T>::release() {
   if (Count) cudaFree(Count); Count = nullptr;
   if (Theta) cudaFree(Theta); Theta = nullptr;
   if (dSig) cudaFree(dSig); dSig = nullptr;
+  if (geev_ws) cudaFree(geev_ws); geev_ws = nullptr;
+  if (geev_piv) cudaFree(geev_piv); geev_piv = nullptr;
+  if (geev_sig) cudaFree(geev_sig); geev_sig = nullptr;
+  if (CxAcc) cudaFree(CxAcc); CxAcc = nullptr;
   if (hbuf) cudaFreeHost(hbuf); hbuf = nullptr;
   if (hX) cudaFreeHost(hX); hX = nullptr;
   if (hY) cudaFreeHost(hY); hY = nullptr;
@@ -1064,46 +1081,104 @@ int Solver<T>::ortho_indef_mat(int m, int nu, int nv, T* U, const T* V, const T*
 
 // Indefinite Rayleigh-Ritz on S = slab[cur][:, 0:m] (reference src/rayleigh/indefinite_rr_impl.inc:51-149 and
 // indefinite_rr_modified_impl.inc:58-255).  The reference hands (G_A, G_B) to LAPACK GGEV, B-normalises the
-// eigenvectors twice and checks their B-orthogonality (quality flag); cuSOLVER has no GGEV, and for the pencils
-// this solver targets G_A = S^H A S is Hermitian positive definite, so the same eigenpairs are obtained from a
-// Hermitian problem: G_A = R^H R, K = R^-H G_B R^-1 = W diag(mu) W^H, v = R^-1 w, theta = 1/mu, v^H G_B v = mu.
-// The eigenvectors are G_B-orthogonal by construction (the reference's quality_flag == 1 path).
+// eigenvectors twice and checks their B-orthogonality (quality flag); cuSOLVER has no GGEV.
+//  * G_A = S^H A S positive definite (the BdG-type pencils the solver targets): the same eigenpairs come from a Hermitian
+//    problem, G_A = R^H R, K = R^-H G_B R^-1 = W diag(mu) W^H, v = R^-1 w, theta = 1/mu, v^H G_B v = mu — B-orthogonal
+//    by construction, i.e. always the reference's quality_flag == 1 path.
+//  * otherwise (Cholesky of G_A fails; or option "indef_geev"): rr_indef_general below — the non-symmetric route with the
+//    reference's own B-normalisation, quality check and quality-5 fallback.
 template <typename T>
 int Solver<T>::rr_indef(int m, int from_col, bool initial) {
   T* S = Xp();
+  last_quality = 1;
   LB2_TRY(apply(opA, m - from_col, col(S, from_col), col(AS, from_col)));
   LB2_TRY(gram_ar(m, m, S, AS, GA, 1));
   LB2_TRY(gram_self_B(m, S, G));
   tm.begin(PH_SMALL);
   LB2_CUDA_OK(cudaMemcpyAsync(Tmp, G, sizeof(T) * (size_t)m * m, cudaMemcpyDeviceToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaMemcpyAsync(DinvR, GA, sizeof(T) * (size_t)m * m, cudaMemcpyDeviceToDevice, ctx->stream));   // G_A survives a failed potrf
   int info = 0;
-  LB2_TRY(sd_potrf_upper<T>(ctx, m, GA, m, &info));
-  if (info != 0) {
-    tm.end();
-    fprintf(stderr, "indefinite_rayleigh_ritz: S^H A S is not positive definite (info=%d); the device path needs a "
-                    "positive definite A-Gram (GGEV fallback not available)\n", info);
-    return 1;
+  if (!indef_geev) LB2_TRY(sd_potrf_upper<T>(ctx, m, GA, m, &info));
+  if (indef_geev || info != 0) {
+    if (int rc = rr_indef_general(m, initial)) { tm.end(); return rc; }
+  } else {
+    LB2_TRY(sd_trsm_upper<T>(ctx, 'R', 'N', m, m, GA, m, Tmp, m));
+    LB2_TRY(sd_trsm_upper<T>(ctx, 'L', 'H', m, m, GA, m, Tmp, m));
+    LB2_TRY(sd_syevd_upper<T>(ctx, m, Tmp, m, Lam, &info));
+    if (info != 0) {
+      tm.end();
+      fprintf(stderr, "indefinite_rayleigh_ritz: eigensolve failed (info=%d)\n", info);
+      return 1;
+    }
+    LB2_TRY(sd_trsm_upper<T>(ctx, 'L', 'N', m, m, GA, m, Tmp, m));
+    LB2_TRY(sd_indef_finalize<T>(ctx, m, Lam, Tmp, m, Z, m, Theta, dSig));
   }
-  LB2_TRY(sd_trsm_upper<T>(ctx, 'R', 'N', m, m, GA, m, Tmp, m));
-  LB2_TRY(sd_trsm_upper<T>(ctx, 'L', 'H', m, m, GA, m, Tmp, m));
-  LB2_TRY(sd_syevd_upper<T>(ctx, m, Tmp, m, Lam, &info));
-  if (info != 0) {
-    tm.end();
-    fprintf(stderr, "indefinite_rayleigh_ritz: eigensolve failed (info=%d)\n", info);
-    return 1;
-  }
-  LB2_TRY(sd_trsm_upper<T>(ctx, 'L', 'N', m, m, GA, m, Tmp, m));
-  LB2_TRY(sd_indef_finalize<T>(ctx, m, Lam, Tmp, m, Z, m, Theta, dSig));
   LB2_CUDA_OK(cudaMemcpyAsync(Eig, Theta, sizeof(R) * k, cudaMemcpyDeviceToDevice, ctx->stream));
   LB2_CUDA_OK(cudaMemcpyAsync(Cx, Z, sizeof(T) * (size_t)m * k, cudaMemcpyDeviceToDevice, ctx->stream));
   sig_len = m;
   if (!initial) {
     LB2_TRY(sd_cp_lower<T>(ctx, m, k, Cx, Cp));
     tm.end();
+    if (last_quality == 5) {
+      // indefinite_rr_modified_impl.inc:236-247: keep the accurate Cx for the residual, B-orthogonalise a copy for the basis
+      if (!CxAcc) LB2_CUDA_OK(cudaMalloc(&CxAcc, sizeof(T) * 3 * (size_t)k * k));
+      LB2_CUDA_OK(cudaMemcpyAsync(CxAcc, Cx, sizeof(T) * (size_t)m * k, cudaMemcpyDeviceToDevice, ctx->stream));
+      LB2_TRY(svqb_mat_dev(m, k, Cx, G, eps_tol()));
+    }
     LB2_TRY(ortho_indef_mat(m, k, k, Cp, Cx, G));
   } else {
     tm.end();
   }
+  return 0;
+}
+
+// General projected pencil (G_A in DinvR, G_B in G, copy of G_B in Tmp): M = G_B^-1 G_A -> Xgeev -> theta = Re(w), eigenvectors
+// B-normalised twice, signatures, quality check, signature sort: Z (sorted eigenvectors), Theta, dSig, last_quality.
+// Mirrors src/rayleigh/indefinite_rr_modified_impl.inc:104-206 (GGEV replaced by LU + GEEV, see smalldense.cu).
+template <typename T>
+int Solver<T>::rr_indef_general(int m, bool initial) {
+  using CT = typename ComplexOf<T>::type;
+  const size_t mm = (size_t)3 * k * 3 * k;
+  if (!geev_ws) {
+    LB2_CUDA_OK(cudaMalloc(&geev_ws, sizeof(CT) * (2 * mm + 3 * (size_t)k)));
+    LB2_CUDA_OK(cudaMalloc(&geev_piv, sizeof(int64_t) * 3 * (size_t)k));
+    LB2_CUDA_OK(cudaMalloc(&geev_sig, 3 * (size_t)k));
+  }
+  CT* Mc = (CT*)geev_ws;
+  CT* Vc = Mc + mm;
+  CT* Wc = Vc + mm;
+  int info = 0;
+  LB2_TRY(sd_lu_solve<T>(ctx, m, Tmp, m, DinvR, m, m, geev_piv, &info));      // DinvR <- G_B^-1 G_A
+  if (info != 0) {
+    fprintf(stderr, "indefinite_rayleigh_ritz: S^H B S is singular (LU info=%d)\n", info);
+    return 1;
+  }
+  LB2_TRY(sd_geev<T>(ctx, m, DinvR, m, Mc, Wc, Vc, &info));
+  if (info != 0) {
+    fprintf(stderr, "indefinite_rayleigh_ritz_modified: GGEV failed\n");
+    return 1;
+  }
+  T* V = GA;   // eigenvectors (unsorted); G_A itself is no longer needed
+  LB2_TRY(sd_geev_extract<T>(ctx, m, Wc, Vc, Lam, V, m));
+  // B-normalise twice, signatures from the second pass
+  for (int pass = 0; pass < 2; pass++) {
+    LB2_TRY(sd_gemm<T>(ctx, 'N', m, m, m, G, m, V, m, Tmp, m));
+    LB2_TRY(sd_gemm<T>(ctx, 'H', m, m, m, V, m, Tmp, m, DinvR, m));
+    LB2_TRY(sd_bnormalize<T>(ctx, m, V, m, DinvR, m, pass == 1 ? geev_sig : nullptr));
+  }
+  // quality: ||V^H G_B V - I_sig||_F <= 1e-12 ||V||_F ||G_B V||_F
+  LB2_TRY(sd_gemm<T>(ctx, 'N', m, m, m, G, m, V, m, Tmp, m));
+  LB2_TRY(sd_gemm<T>(ctx, 'H', m, m, m, V, m, Tmp, m, DinvR, m));
+  LB2_TRY(sd_indef_quality<T>(ctx, m, DinvR, V, Tmp, Scal + 4));
+  LB2_TRY(d2h(hbuf, Scal + 4, 3 * sizeof(R)));
+  tm.end();            // (sync() collects the finished timer records; none may be open)
+  LB2_TRY(sync());
+  tm.begin(PH_SMALL);
+  const R eerr = hbuf[0], cerr = hbuf[1], bcerr = hbuf[2];
+  const bool quality_ok = (bcerr < (R)1e-30) || (eerr <= (R)1e-12 * cerr * bcerr);
+  last_quality = (quality_ok || initial) ? 1 : 5;   // the initial RR has no quality flag (indefinite_rr_impl.inc:51-149)
+  LB2_TRY(sd_indef_sort<T>(ctx, m, Lam, geev_sig, V, m, Z, m, Theta, dSig));
+  general_rr_calls++;
   return 0;
 }
 
@@ -1120,17 +1195,30 @@ void Solver<T>::print_state(bool header) {
 // After X (slab[cur][:,0:k]) and Eig are final for this pass: AX, residual norms of the first nev columns,
 // convergence count (contiguous prefix, lobpcg_impl.inc:224-228).  Leaves B X in wA when B != NULL.
 template <typename T>
-int Solver<T>::residual_pass(bool initial) {
+int Solver<T>::residual_pass(bool initial, const T* Xacc) {
   T* X = Xp();
   LB2_TRY(apply(opA, k, X, AS));
   const T* BX = X;
-  if (opB) { LB2_TRY(apply(opB, k, X, wA)); BX = wA; }
+  res_AX = AS;
+  if (Xacc) {
+    // quality-5 pass of the indefinite solver (ilobpcg_impl.inc:228-256): the basis continues with X = S Cx_ortho, the residual
+    // is taken from X_accurate = S Cx (accurate eigenvalue correspondence): A X_acc -> AS[:, k:2k], B X_acc -> wA
+    LB2_TRY(apply(opA, k, Xacc, col(AS, k)));
+    res_AX = col(AS, k);
+    BX = Xacc;
+    if (opB) { LB2_TRY(apply(opB, k, Xacc, wA)); BX = wA; }
+  } else if (opB) {
+    LB2_TRY(apply(opB, k, X, wA));
+    BX = wA;
+  }
+  res_BX = BX;
+  const T* AXr = res_AX;
   const bool monitor = gram_cache && !initial;
   if (monitor) {
     // same two (three with B) streams as the plain norm pass, plus the Rayleigh quotients x^H A x and x^H B x of the new
     // Ritz vectors: the drift monitor of the cached Gram blocks
     tm.begin(PH_RESID);
-    int rc = residual_monitor<T>(ctx, n, nev, X, n, AS, n, opB ? BX : (const T*)nullptr, n, Eig, Sums);
+    int rc = residual_monitor<T>(ctx, n, nev, X, n, AXr, n, opB ? BX : (const T*)nullptr, n, Eig, Sums);
     tm.end();
     phase_work[PH_RESID] += (opB ? 3.0 : 2.0) * (double)n * nev * sizeof(T);
     phase_calls[PH_RESID]++;
@@ -1139,7 +1227,7 @@ int Solver<T>::residual_pass(bool initial) {
     LB2_TRY(d2h(hbuf, Sums, sizeof(R) * 3 * nev));
     LB2_TRY(d2h(hbuf + 3 * nev, Eig, sizeof(R) * k));
   } else {
-    LB2_TRY(resid(nev, AS, BX, Eig, nullptr, Sums));
+    LB2_TRY(resid(nev, AXr, BX, Eig, nullptr, Sums));
     if (reduce()) LB2_TRY(allreduce_sum(ctx, Sums, nev, kDouble));
     LB2_TRY(d2h(hbuf, Sums, sizeof(R) * nev));
     LB2_TRY(d2h(hbuf + 3 * nev, Eig, sizeof(R) * k));
@@ -1351,9 +1439,15 @@ int Solver<T>::step_impl(int max_steps, int* passes_out) {
     }
     // X_new = S Cx into the other slab
     T* Sn = slab[1 - cur];
+    const T* Xacc = nullptr;
+    if (indef && last_quality == 5) {   // X_accurate = S Cx for the residual; the basis continues with S Cx_ortho (now in Cx)
+      LB2_TRY(nn(m, k, make<T>(1), S, CxAcc, m, zero<T>(), wB));
+      Xacc = wB;
+      quality5_passes++;
+    }
     LB2_TRY(nn(m, k, make<T>(1), S, Cx, m, zero<T>(), Sn));
     cur = 1 - cur;
-    LB2_TRY(residual_pass(false));
+    LB2_TRY(residual_pass(false, Xacc));
     if (alg->verbosity > 0) print_state(true);
     passes++;
     if (conv == (uint64_t)nev) {
@@ -1367,9 +1461,8 @@ int Solver<T>::step_impl(int max_steps, int* passes_out) {
     LB2_TRY(nn(m, nact, make<T>(1), Sold, Cp + (size_t)nconv * m, m, zero<T>(), col(Sn, k)));
     if (!indef) LB2_TRY(update_gram_cache(m, nconv));
     {
-      const T* BX = opB ? wA : Sn;
       T* Wdst = col(Sn, k + nact);
-      LB2_TRY(resid(nact, col(AS, nconv), BX + (int64_t)nconv * n, Eig + nconv, opT ? wB : Wdst, nullptr));
+      LB2_TRY(resid(nact, res_AX + (int64_t)nconv * n, res_BX + (int64_t)nconv * n, Eig + nconv, opT ? wB : Wdst, nullptr));
       if (opT) LB2_TRY(apply(opT, nact, wB, Wdst));
     }
     np = nact;
@@ -1587,11 +1680,11 @@ static void h_irr(uint64_t n, uint64_t nx, int m, bool initial, T* S, const T* A
     s.down(Cx, s.Z, m, m);   // all eigenvectors, signature-sorted
     cudaMemcpyAsync(eig, s.Theta, sizeof(real_t<T>) * m, cudaMemcpyDeviceToHost, s.ctx->stream);
   } else {
-    s.down(Cx, s.Cx, m, ncx);
+    s.down(Cx, s.last_quality == 5 ? s.CxAcc : s.Cx, m, ncx);   // quality 5: Cx stays the accurate one, Cx_ortho is the B-orthogonalised copy
     s.down(Cp, s.Cp, m, ncx);
     if (Cx_ortho) s.down(Cx_ortho, s.Cx, m, ncx);
     cudaMemcpyAsync(eig, s.Eig, sizeof(real_t<T>) * nx, cudaMemcpyDeviceToHost, s.ctx->stream);
-    if (quality) *quality = 1;
+    if (quality) *quality = s.last_quality;
   }
   cudaMemcpyAsync(sig, s.dSig, (size_t)m, cudaMemcpyDeviceToHost, s.ctx->stream);
   cudaStreamSynchronize(s.ctx->stream);

@@ -33,6 +33,13 @@ def cases():
     g = (24, 24, 24)
     c["mid_c4_z"] = dict(kind="ilobpcg", dtype=np.complex128, grid=g, shift=0.5, d=0.5 * np.exp(0.7j), nev=24, k=48,
                          tol=1e-8, seed=13, maxit=3000)
+    # indefinite A (negative shift): S^H A S is not positive definite, so the projected pencil needs the general (GGEV-type)
+    # Rayleigh-Ritz; small on purpose — the point is the code path, not the tile count
+    g = (6, 6, 6)
+    c["ilob_neg_z"] = dict(kind="ilobpcg", dtype=np.complex128, grid=g, shift=-0.9, d=0.02 * np.exp(0.7j), nev=4, k=8,
+                           tol=1e-9, seed=13, maxit=6000)
+    c["ilob_neg_d"] = dict(kind="ilobpcg", dtype=np.float64, grid=g, shift=-0.9, d=0.02, nev=4, k=8, tol=1e-9, seed=14,
+                           maxit=6000)
     return c
 
 
