@@ -292,6 +292,14 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    # host-side barrier (gloo): waiting ranks must not park an NCCL kernel on their GPUs while rank 0 uses all devices
+    host_grp = torch.distributed.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        if world > 1:
+            torch.cuda.synchronize()
+            torch.distributed.barrier(group=host_grp)
+
     s = api.Solver(ctx, A, n, k, nev, np.float64, 1e-8, 10 ** 6, device_seed=7)
     if part is not None:
         dist.attach(s, part)
@@ -407,27 +415,50 @@ def run_ours(args):
 
     # ---- e2e: the reference-facing call d_lobpcg(alg) with HOST buffers (X0 upload, result download inside) ----
     e2e = None
-    if world == 1 and not args.no_e2e:
-        X_dev = s.finish()["X"]            # any non-zero host block will do as X0; reuse the current iterate
+    if not args.no_e2e:
         passes = max(args.steps, 12)   # set-up (X0 upload, ||A||, initial RR, download) amortises over the passes
-        st2 = api._setup(A, None, n, k, nev, np.float64, 1e-8, passes, None, None, False, 0)
-        st2.X()[:, :] = X_dev
+        st2 = None
+        if world == 1:
+            X_dev = s.finish()["X"]        # any non-zero host block will do as X0; reuse the current iterate
+            st2 = api._setup(A, None, n, k, nev, np.float64, 1e-8, passes, None, None, False, 0)
+            st2.X()[:, :] = X_dev
+            del X_dev
         s.close()
         ctx.sync()
-        # warm-up of the reference-facing entry point on a small problem: one-time library initialisation of the default
-        # context (cuSOLVER / cuBLAS handles, pinned staging ring) is not part of a step
-        from lobpcg_b200 import problems as pr_w
-        api.lobpcg(api.stencil_op((24, 24, 24), np.float64), pr_w.initial_block(24 ** 3, 8, 7), 4, 1e-8, 5)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        api.lib().d_lobpcg(st2.ptr)
-        t_e2e = time.perf_counter() - t0
-        it = int(st2.st.iter)
-        e2e = {"value": it / t_e2e, "unit": "iter/s", "passes": it, "seconds": t_e2e,
-               "h2d_bytes_per_step": n * k * 8 / max(it, 1), "d2h_bytes_per_step": (n * k * 8) / max(it, 1) + (nev + k) * 8,
-               "note": "whole d_lobpcg(alg) call on host buffers: X0 upload (pageable), ||A|| estimate, initial RR, "
-                       f"{it} passes, eigenvector download; set-up amortises over the pass count"}
-        st2.free()
+        barrier()
+        if rank == 0:
+            # N GPUs: the SAME reference-facing call, d_lobpcg(alg) on host buffers, from this one process; the library
+            # spreads it over the N devices itself (csrc/multigpu.cu: worker thread per device, rows of X0 / of the
+            # eigenvectors move over N PCIe links).  The other ranks have released their arenas and wait.
+            if world > 1:
+                A_e2e = api.stencil_op((g, g, g), np.float64)
+                st2 = api._setup(A_e2e, None, n, k, nev, np.float64, 1e-8, passes, None, None, False, 0)
+                rng = np.random.default_rng(7)
+                Xh = st2.X()
+                for j0 in range(0, k, 25):
+                    Xh[:, j0:j0 + 25] = rng.random((n, min(25, k - j0))) - 0.5
+            api.lib().lb2_set_num_gpus(world)
+            # warm-up of the reference-facing entry point on a small problem: one-time library initialisation of the default
+            # contexts (cuSOLVER / cuBLAS handles, pinned staging rings, the in-process NCCL communicator) is not part of a step
+            from lobpcg_b200 import problems as pr_w
+            gw = 32 if world > 1 else 24
+            api.lobpcg(api.stencil_op((gw, gw, gw), np.float64), pr_w.initial_block(gw ** 3, 8, 7), 4, 1e-8, 5)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            api.lib().d_lobpcg(st2.ptr)
+            t_e2e = time.perf_counter() - t0
+            used = int(api.lib().lb2_last_num_gpus())
+            api.lib().lb2_set_num_gpus(0)
+            it = int(st2.st.iter)
+            e2e = {"value": it / t_e2e, "unit": "iter/s", "passes": it, "seconds": t_e2e, "gpus_used": used,
+                   "status": int(api.lib().lb2_last_status()),
+                   "h2d_bytes_per_step": n * k * 8 / max(it, 1), "d2h_bytes_per_step": (n * k * 8) / max(it, 1) + (nev + k) * 8,
+                   "note": "whole d_lobpcg(alg) call on host buffers from ONE process" +
+                           (f", spread over {used} GPUs inside the call (LB2_GPUS / lb2_set_num_gpus)" if world > 1 else "") +
+                           f": X0 upload (pageable), ||A|| estimate, initial RR, {it} passes, eigenvector download; set-up "
+                           "amortises over the pass count"}
+            st2.free()
+        host_barrier()
     else:
         s.close()
 

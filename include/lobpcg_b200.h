@@ -194,6 +194,13 @@ int lb2_comm_unique_id(void *out128, const char *nccl_lib_path);   /* rank 0; br
 int lb2_ctx_attach_comm(lb2_ctx *ctx, int rank, int size, const void *unique_id128, const char *nccl_lib_path);
 int lb2_ctx_detach_comm(lb2_ctx *ctx);
 int lb2_comm_allreduce(lb2_ctx *ctx, void *dev_buf, size_t count, int is_double);
+/* Several GPUs inside ONE call of the reference entry points (one process, one worker thread per device, peer access for
+ * the halos, an NCCL communicator kept per process): n > 1 lets <p>_lobpcg / <p>_ilobpcg partition the rows of a solve over
+ * up to n devices when every operator is a built-in stencil / BdG / CSR / diagonal / polynomial-preconditioner operator and
+ * the grid splits into equal slabs; otherwise the call runs on one GPU.  0 = take the count from the environment
+ * (LB2_GPUS = N | all; default 1).  Returns the previous setting. */
+int lb2_set_num_gpus(int n);
+int lb2_last_num_gpus(void); /* how many GPUs the last call really used */
 int lb2_ipc_get_handle(void *dev_ptr, void *out64);
 void *lb2_ipc_open_handle(const void *in64);
 int lb2_ipc_close_handle(void *mapped_ptr);

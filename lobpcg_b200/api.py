@@ -121,6 +121,8 @@ def _declare(L):
     L.lb2_solver_set_option.argtypes = [vp, C.c_char_p, ci]
     L.lb2_solver_info.restype = dbl
     L.lb2_solver_info.argtypes = [vp, C.c_char_p]
+    L.lb2_set_num_gpus.argtypes = [ci]
+    L.lb2_last_num_gpus.restype = ci
     L.lb2_last_status.restype = ci
     L.lb2_solver_results.argtypes = [vp, C.POINTER(dbl), ci, C.POINTER(dbl), ci]
     L.lb2_solver_state.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(ci)]

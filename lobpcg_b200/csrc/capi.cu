@@ -18,6 +18,12 @@
 using namespace lb2;
 
 namespace lb2 {
+int mg_requested_gpus();                                                   // multigpu.cu
+int run_solver_multi(char prefix, void* alg, int indefinite, int want);
+}
+extern "C" void lb2_note_single_gpu_call(void);
+
+namespace lb2 {
 void* ctx_scratch(lb2_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->ws_bytes) return ctx->ws;
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
@@ -776,6 +782,17 @@ double lb2_solver_info(lb2_solver* s, const char* key) { return s ? s->impl->inf
 
 static void run_solver(char prefix, void* alg, int indefinite) {
   g_last_status = 2;
+  // several GPUs in this one call (multigpu.cu): LB2_GPUS / lb2_set_num_gpus; -100 = not applicable, single-GPU path below
+  const int want = lb2::mg_requested_gpus();
+  if (want > 1) {
+    const int st = lb2::run_solver_multi(prefix, alg, indefinite, want);
+    if (st != -100) {
+      g_last_status = st;
+      if (st == 2) fprintf(stderr, "lobpcg_b200: multi-GPU solve failed; alg->converged = 0, eigVals = NaN (lb2_last_status() = 2)\n");
+      return;
+    }
+  }
+  lb2_note_single_gpu_call();
   lb2_ctx* ctx = lb2_default_ctx();
   if (!ctx) return;
   // LB2_TIMING=1: wall-clock split of the call on stderr (set-up + X0 upload + initial RR | passes | download | tear-down)

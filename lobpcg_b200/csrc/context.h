@@ -54,4 +54,8 @@ void gram_wl_cache_free(lb2_ctx* ctx);   // gram_wl.cu
 // hostcopy.cu: pipelined copy between PAGEABLE host memory and the device (host-synchronous, ordered after ctx->stream)
 int host_copy(lb2_ctx* ctx, void* dst, const void* src, size_t bytes, bool to_device);
 void hostcopy_free(lb2_ctx* ctx);
+// strided pageable host <-> device transfer (cols segments of rows_bytes; column strides in bytes)
+int host_copy_2d(lb2_ctx* ctx, void* dev, size_t ld_dev_bytes, void* host, size_t ld_host_bytes, size_t rows_bytes, int cols,
+                 bool to_device);
+void hostcopy_set_threads(lb2_ctx* ctx, int nthreads);
 }  // namespace lb2

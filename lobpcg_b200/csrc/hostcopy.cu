@@ -121,4 +121,108 @@ int host_copy(lb2_ctx* ctx, void* dst, const void* src, size_t bytes, bool to_de
   return 0;
 }
 
+
+// Strided version for row-partitioned runs: `cols` column segments of `rows_bytes` contiguous bytes each, host column stride
+// ld_host_bytes, device column stride ld_dev_bytes.  Segments are packed back to back into the pinned ring by the copy threads
+// and moved by one DMA per segment (one per chunk when the device block is contiguous, ld_dev_bytes == rows_bytes).
+int host_copy_2d(lb2_ctx* ctx, void* dev, size_t ld_dev_bytes, void* host, size_t ld_host_bytes, size_t rows_bytes, int cols,
+                 bool to_device) {
+  if (rows_bytes == 0 || cols <= 0) return 0;
+  if (ld_dev_bytes == rows_bytes && ld_host_bytes == rows_bytes) return host_copy(ctx, to_device ? dev : host, to_device ? host : dev, rows_bytes * (size_t)cols, to_device);
+  HostCopyState* s = rows_bytes * (size_t)cols >= 4 * kChunk ? state_of(ctx) : nullptr;
+  if (!s || !s->copy_stream) {
+    LB2_CUDA_OK(cudaMemcpy2DAsync(to_device ? dev : host, to_device ? ld_dev_bytes : ld_host_bytes, to_device ? host : dev,
+                                  to_device ? ld_host_bytes : ld_dev_bytes, rows_bytes, cols,
+                                  to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  // pieces: (column, byte range inside the segment), each at most kChunk bytes; a ring slot holds consecutive pieces
+  struct Piece { int col; size_t off, len; };
+  std::vector<std::vector<Piece>> groups;
+  {
+    std::vector<Piece> cur;
+    size_t fill = 0;
+    for (int j = 0; j < cols; j++)
+      for (size_t o = 0; o < rows_bytes; o += kChunk) {
+        const size_t l = std::min(kChunk, rows_bytes - o);
+        if (fill + l > kChunk && !cur.empty()) { groups.push_back(cur); cur.clear(); fill = 0; }
+        cur.push_back(Piece{j, o, l});
+        fill += l;
+      }
+    if (!cur.empty()) groups.push_back(cur);
+  }
+  auto host_side = [&](const std::vector<Piece>& g, char* pin, bool gather) {   // pageable <-> pinned, several threads
+    std::vector<size_t> start(g.size());
+    size_t acc = 0;
+    for (size_t i = 0; i < g.size(); i++) { start[i] = acc; acc += g[i].len; }
+    const int nt = std::max(1, std::min<int>(s->nthreads, (int)g.size()));
+    auto work = [&](int t) {
+      for (size_t i = t; i < g.size(); i += nt) {
+        char* h = (char*)host + (size_t)g[i].col * ld_host_bytes + g[i].off;
+        if (gather) memcpy(pin + start[i], h, g[i].len);
+        else memcpy(h, pin + start[i], g[i].len);
+      }
+    };
+    if (nt == 1) {
+      if (g.size() == 1) {
+        char* h = (char*)host + (size_t)g[0].col * ld_host_bytes + g[0].off;
+        if (gather) par_memcpy(pin, h, g[0].len, s->nthreads); else par_memcpy(h, pin, g[0].len, s->nthreads);
+      } else work(0);
+      return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+  };
+  auto dma = [&](const std::vector<Piece>& g, char* pin) -> int {
+    size_t acc = 0;
+    for (const Piece& pc : g) {
+      char* d = (char*)dev + (size_t)pc.col * ld_dev_bytes + pc.off;
+      if (to_device) LB2_CUDA_OK(cudaMemcpyAsync(d, pin + acc, pc.len, cudaMemcpyHostToDevice, s->copy_stream));
+      else LB2_CUDA_OK(cudaMemcpyAsync(pin + acc, d, pc.len, cudaMemcpyDeviceToHost, s->copy_stream));
+      acc += pc.len;
+    }
+    return 0;
+  };
+  const size_t ng = groups.size();
+  if (to_device) {
+    for (size_t c = 0; c < ng; c++) {
+      const int b = (int)(c % kRing);
+      if (c >= (size_t)kRing) LB2_CUDA_OK(cudaEventSynchronize(s->ev[b]));
+      host_side(groups[c], s->pinned[b], true);
+      if (dma(groups[c], s->pinned[b])) return -1;
+      LB2_CUDA_OK(cudaEventRecord(s->ev[b], s->copy_stream));
+    }
+    LB2_CUDA_OK(cudaStreamSynchronize(s->copy_stream));
+  } else {
+    const size_t ahead = kRing - 1;
+    for (size_t c = 0; c < std::min(ahead, ng); c++) {
+      const int b = (int)(c % kRing);
+      if (dma(groups[c], s->pinned[b])) return -1;
+      LB2_CUDA_OK(cudaEventRecord(s->ev[b], s->copy_stream));
+    }
+    for (size_t c = 0; c < ng; c++) {
+      const int b = (int)(c % kRing);
+      const size_t nx = c + ahead;
+      if (nx < ng) {
+        const int bn = (int)(nx % kRing);
+        if (dma(groups[nx], s->pinned[bn])) return -1;
+        LB2_CUDA_OK(cudaEventRecord(s->ev[bn], s->copy_stream));
+      }
+      LB2_CUDA_OK(cudaEventSynchronize(s->ev[b]));
+      host_side(groups[c], s->pinned[b], false);
+    }
+  }
+  return 0;
+}
+
+// cap on the copy threads of this context (multi-GPU runs in one process share the host cores)
+void hostcopy_set_threads(lb2_ctx* ctx, int nthreads) {
+  HostCopyState* s = state_of(ctx);
+  if (s && nthreads >= 1) s->nthreads = nthreads;
+}
+
 }  // namespace lb2

@@ -1354,10 +1354,10 @@ int Solver<T>::init() {
     LB2_CUDA_OK(cudaMemcpyAsync(X, dev_x0, sizeof(T) * (size_t)n * k, cudaMemcpyDeviceToDevice, ctx->stream));
   } else if (n == ng) {   // whole columns: one contiguous block, pipelined through pinned chunks (hostcopy.cu)
     LB2_TRY(host_copy(ctx, X, alg->S, sizeof(T) * (size_t)n * k, true));
-  } else {
+  } else {   // this rank's rows of every column: strided on the host, pipelined through the pinned ring (hostcopy.cu)
     for (int sg = 0; sg < nseg; sg++)
-      LB2_CUDA_OK(cudaMemcpy2DAsync(X + sg * seg_len(), sizeof(T) * n, alg->S + seg_global(sg), sizeof(T) * ng,
-                                    sizeof(T) * seg_len(), k, cudaMemcpyHostToDevice, ctx->stream));
+      LB2_TRY(host_copy_2d(ctx, X + sg * seg_len(), sizeof(T) * n, alg->S + seg_global(sg), sizeof(T) * ng,
+                           sizeof(T) * seg_len(), k, true));
   }
   LB2_TRY(estimate_norm(opA, 0xA5EEDULL, &ANorm));
   if (opB) LB2_TRY(estimate_norm(opB, 0xB5EEDULL, &BNorm));
@@ -1483,8 +1483,8 @@ int Solver<T>::finish() {
     LB2_TRY(host_copy(ctx, alg->S, X, sizeof(T) * (size_t)n * k, false));
   } else {
     for (int sg = 0; sg < nseg; sg++)
-      LB2_CUDA_OK(cudaMemcpy2DAsync(alg->S + seg_global(sg), sizeof(T) * ng, X + sg * seg_len(), sizeof(T) * n,
-                                    sizeof(T) * seg_len(), k, cudaMemcpyDeviceToHost, ctx->stream));
+      LB2_TRY(host_copy_2d(ctx, X + sg * seg_len(), sizeof(T) * n, alg->S + seg_global(sg), sizeof(T) * ng,
+                           sizeof(T) * seg_len(), k, false));
   }
   LB2_TRY(sync());
   for (int i = 0; i < k; i++) alg->eigVals[i] = hEig[i];
