@@ -173,6 +173,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "gram_strip_max")) c->gram_strip_max = value;
   else if (!strcmp(key, "gram_strip_fma")) c->gram_strip_fma = value;
   else if (!strcmp(key, "spmm_cols")) c->spmm_cols = value;
+  else if (!strcmp(key, "csr_window")) c->csr_window = value;
   else return -1;
   return 0;
 }
@@ -397,6 +398,27 @@ static double csr_gershgorin(char prefix, int64_t n, const int64_t* rp, const vo
   return hi;
 }
 
+// Half-width H of the near-diagonal window for the windowed CSR kernel (spmm.cu: csr_win_kernel): the largest offset
+// |col - row| <= 256 that at least 2 % of the rows use, provided the window then holds >= 40 % of the nonzeros and reaches
+// beyond the immediate neighbours (which L1 serves anyway).  0 = use the plain kernel.
+static int csr_window_halo(int64_t n, const int64_t* rp, const int32_t* col, int64_t col_shift) {
+  constexpr int HMAX = 256;
+  std::vector<int64_t> cnt(HMAX + 1, 0);
+  const int64_t nnz = rp[n];
+  for (int64_t i = 0; i < n; i++)
+    for (int64_t p = rp[i]; p < rp[i + 1]; p++) {
+      const int64_t d = std::llabs((int64_t)col[p] + col_shift - i);
+      if (d <= HMAX) cnt[(size_t)d]++;
+    }
+  int H = 0;
+  for (int d = HMAX; d >= 2; d--)
+    if (cnt[(size_t)d] >= n / 50 + 1) { H = d; break; }
+  if (H < 2) return 0;
+  int64_t in = 0;
+  for (int d = 0; d <= H; d++) in += cnt[(size_t)d];
+  return (in * 10 >= nnz * 4) ? H : 0;
+}
+
 void* lb2_op_csr(char prefix, int64_t n, const int64_t* rowptr_host, const int32_t* col_host, const void* val_host) {
   if (!valid_prefix(prefix) || n < 1 || !rowptr_host || !col_host || !val_host) return nullptr;
   if (!lb2_default_ctx()) return nullptr;
@@ -444,6 +466,7 @@ void* lb2_op_csr(char prefix, int64_t n, const int64_t* rowptr_host, const int32
     return nullptr;
   }
   b->spec_hi = csr_gershgorin(prefix, n, rowptr_host, val_host);
+  b->csr_halo = csr_window_halo(n, rowptr_host, col_host, 0);
   return wrap_builtin(b);
 }
 

@@ -40,6 +40,7 @@ struct lb2_ctx {
   int gram_tc5 = -1;     // float Gram through tcgen05 / TMEM (gram_tc5.cu): -1 = auto (on), 0 = off, 1 = on
   int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
   int spmm_cols = 0;     // CSR SpMM columns per thread (0 = heuristic)
+  int csr_window = -1;   // windowed CSR kernel for banded matrices: -1 = auto (on), 0 = off
   // launch counter (bench.py "gpu_launches")
   unsigned long long launches = 0;
   // multi-GPU (row-partitioned) state; comm == nullptr => single GPU

@@ -84,6 +84,10 @@ int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t 
         h.lo = b->halo_lo; h.hi = b->halo_hi; h.ld_lo = h.ld_hi = b->halo_ld;
         return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy, &h);
       }
+      if (b->csr_halo >= 2 && ctx->csr_window != 0) {   // banded matrix: shared-memory X window (spmm.cu: csr_win_kernel)
+        const int rc = spmm_csr_window<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy, b->csr_halo);
+        if (rc != -100) return rc;
+      }
       return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy);
     case OP_DIAG:
       return spmm_diag<T>(ctx, b->n, (const real_t<T>*)b->diag, nc, X, ldx, Y, ldy);

@@ -77,6 +77,7 @@ struct BuiltinOp {
   void* val;
   int64_t nnz;
   int from_csr;     // stencil operator recognised from CSR input (capi.cu: detect_stencil)
+  int csr_halo;     // half-width H of the near-diagonal window of the windowed CSR kernel (0: plain kernel; capi.cu: csr_window_halo)
   // diag
   void* diag;
   // dense n x n matrix (column-major, leading dimension n), device

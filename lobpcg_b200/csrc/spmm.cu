@@ -352,6 +352,87 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// =====================================================================================================
+// CSR with a shared-memory X window ("banded" matrices: most couplings of row r lie in [r - H, r + H]).
+// A CTA owns RB = 512 consecutive rows and NCOL columns of the block vector; it stages X[r0 - H, r0 + RB + H) of its
+// columns in shared memory with coalesced loads (each X element is fetched from L2 once per CTA instead of once per
+// coupling), every thread then walks the nonzeros of its rows: a column index inside the window reads shared memory,
+// anything else (far couplings, e.g. the +-gx*gy neighbours of a 3-D stencil) is gathered from global memory as before.
+// blockIdx.x = row block * ncg + column group: the CTAs of one row block are neighbours in launch order, so its
+// (col, val) stream comes from DRAM once and from L2 for the other column groups.
+// H is chosen per matrix on the host (capi.cu: csr_window_halo) from the histogram of |col - row|.
+// =====================================================================================================
+constexpr int CSRW_RB = 512;
+template <typename T, int NCOL>
+__global__ void __launch_bounds__(256)
+    csr_win_kernel(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                   const T* __restrict__ val, int nc, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y,
+                   int64_t ldy, int H, int ncg) {
+  extern __shared__ __align__(16) unsigned char csrw_smem[];
+  T* win = reinterpret_cast<T*>(csrw_smem);
+  const int WL = CSRW_RB + 2 * H;
+  const int cg = blockIdx.x % ncg;
+  const int64_t rb = blockIdx.x / ncg;
+  const int c0 = cg * NCOL;
+  const int ncol = min(NCOL, nc - c0);
+  const int64_t r0 = rb * CSRW_RB, wlo = r0 - H;
+  const T* xb = X + (int64_t)c0 * ldx;
+  for (int c = 0; c < NCOL; c++) {
+    T* w = win + (size_t)c * WL;
+    const T* xc = xb + (int64_t)c * ldx;
+    for (int i = threadIdx.x; i < WL; i += 256) {
+      const int64_t row = wlo + i;
+      w[i] = (c < ncol && row >= 0 && row < n) ? xc[row] : zero<T>();
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int rr = 0; rr < CSRW_RB / 256; rr++) {
+    const int64_t row = r0 + rr * 256 + threadIdx.x;
+    if (row >= n) break;
+    T acc[NCOL];
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) acc[c] = zero<T>();
+    const int64_t p0 = rowptr[row], p1 = rowptr[row + 1];
+    for (int64_t p = p0; p < p1; p++) {
+      const int64_t cj = col[p];
+      const T v = val[p];
+      const int64_t d = cj - wlo;
+      if ((uint64_t)d < (uint64_t)WL) {
+        const T* sp = win + d;
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) fma_(acc[c], v, sp[(size_t)c * WL]);
+      } else {
+        const T* gp = xb + cj;
+#pragma unroll
+        for (int c = 0; c < NCOL; c++)
+          if (c < ncol) fma_(acc[c], v, gp[(int64_t)c * ldx]);
+      }
+    }
+    T* yb = Y + (int64_t)c0 * ldy + row;
+#pragma unroll
+    for (int c = 0; c < NCOL; c++)
+      if (c < ncol) yb[(int64_t)c * ldy] = acc[c];
+  }
+}
+
+template <typename T>
+int spmm_csr_window(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val, int nc,
+                    const T* X, int64_t ldx, T* Y, int64_t ldy, int H) {
+  if (n <= 0 || nc <= 0) return 0;
+  constexpr int NCOL = sizeof(T) >= 16 ? 4 : (sizeof(T) == 8 ? 8 : 16);
+  const int ncg = (nc + NCOL - 1) / NCOL;
+  const int64_t nrb = (n + CSRW_RB - 1) / CSRW_RB;
+  if (nrb * ncg > 0x7fffffffLL) return -100;
+  const size_t smem = sizeof(T) * (size_t)NCOL * (CSRW_RB + 2 * H);
+  auto k = csr_win_kernel<T, NCOL>;
+  LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)(nrb * ncg), 256, smem, ctx->stream>>>(n, rowptr, col, val, nc, X, ldx, Y, ldy, H, ncg);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 template <typename T>
 int spmm_csr(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val, int nc,
              const T* X, int64_t ldx, T* Y, int64_t ldy, const CsrHalo* halo) {
@@ -407,6 +488,7 @@ int spmm_diag(lb2_ctx* ctx, int64_t n, const real_t<T>* d, int nc, const T* X, i
   template int spmm_stencil<T>(lb2_ctx*, const StencilDesc&, int, const T*, int64_t, T*, int64_t);         \
   template int spmm_stencil_cheb<T>(lb2_ctx*, const StencilDesc&, int, const T*, int64_t, T*, int64_t, const ChebEpilogue<T>&); \
   template int spmm_csr<T>(lb2_ctx*, int64_t, const int64_t*, const int32_t*, const T*, int, const T*, int64_t, T*, int64_t, const CsrHalo*); \
+  template int spmm_csr_window<T>(lb2_ctx*, int64_t, const int64_t*, const int32_t*, const T*, int, const T*, int64_t, T*, int64_t, int); \
   template int spmm_diag<T>(lb2_ctx*, int64_t, const real_t<T>*, int, const T*, int64_t, T*, int64_t);
 LB2_INST(float)
 LB2_INST(double)

@@ -573,3 +573,36 @@ def test_gram_cols_full_size_linearity(ctx):
     up = np.triu_indices(nw)
     blk = g0[mxp:, :]
     assert np.max(np.abs(blk[up] - Gww[up])) / np.abs(Gww).max() < 1e-13
+
+
+# ------------------------------------------------------------------------------------------------ windowed CSR kernel
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", [(3000, 40, 9, 5), (70001, 200, 33, 12), (5000, 256, 7, 40), (1100, 3, 4, 3)])
+def test_csr_window_kernel_matches_scipy(ctx, dt, case):
+    """csr_win_kernel (banded matrices: X window in shared memory, far couplings gathered): random band of half-width H
+    plus far entries, ragged row blocks (n not a multiple of 512), column-group tails, all four types; the plain kernel
+    (context option csr_window = 0) must give the same result."""
+    import scipy.sparse as sp
+    n, H, nc, far = case
+    rng = np.random.default_rng(n + H)
+    rows, cols = [], []
+    for d in (0, 1, -1, H, -H, H // 2):
+        i = np.arange(max(0, -d), min(n, n - d))
+        rows.append(i); cols.append(i + d)
+    rows.append(rng.integers(0, n, far * n // 10)); cols.append(rng.integers(0, n, far * n // 10))   # far / random couplings
+    r, c = np.concatenate(rows), np.concatenate(cols)
+    vals = rng.standard_normal(len(r)) + (1j * rng.standard_normal(len(r)) if np.dtype(dt).kind == "c" else 0)
+    M = sp.csr_matrix((vals.astype(dt), (r, c)), shape=(n, n))
+    M.sum_duplicates(); M.sort_indices()
+    X = rand(rng, (n, nc), dt)
+    ref = np.asarray(M @ X)
+    dX = api.DeviceArray.from_numpy(ctx, X)
+    op = api.csr_op(M.indptr, M.indices, M.data)
+    got = op.apply(ctx, dX).numpy(ctx)
+    close(got, ref, rtol(dt) * 10)
+    ctx.set_option("csr_window", 0)
+    try:
+        plain = op.apply(ctx, dX).numpy(ctx)
+    finally:
+        ctx.set_option("csr_window", -1)
+    close(plain, ref, rtol(dt) * 10)

@@ -32,6 +32,8 @@ if mode in ("stencil", "csr"):
     g, nc = int(args[0]), int(args[1]); n = g ** 3
     X = api.fill_uniform(ctx, n, nc, np.float64, 1); Y = api.DeviceArray((n, nc), np.float64)
     if mode == "csr":
+        import os
+        os.environ["LB2_CSR_NO_STENCIL_DETECT"] = "1"     # the general CSR kernels, not the recognised stencil
         rp, c, v = pr.laplacian_csr((g, g, g)); op = api.csr_op(rp, c, v); extra = len(v) * 12 + 8 * (n + 1)
     else:
         op = api.stencil_op((g, g, g), np.float64); extra = 0
