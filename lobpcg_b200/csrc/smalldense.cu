@@ -214,22 +214,34 @@ int sd_set_diag(lb2_ctx* ctx, int m, T* M, int ldm, const real_t<T>* D) {
 }
 
 // rcond_1(R) = 1 / (||R||_1 ||R^-1||_1) with R^-1 = diag(1/D) * DinvR (exact, where LAPACK trcon estimates;
-// rayleigh_ritz_modified_impl.inc:169-178).  One block; out[0] = rcond.
+// rayleigh_ritz_modified_impl.inc:169-178).  One CTA per column (coalesced column sums), then one CTA takes the maxima;
+// out[0] = rcond.  (The first version walked the columns with one thread each: 1.1 ms at m = 900, ncu launch list r02.)
 template <typename T>
-__global__ void rcond_kernel(int m, const T* __restrict__ Rm, int ldr, const T* __restrict__ DinvR, int ldd,
-                             const real_t<T>* __restrict__ D, real_t<T>* __restrict__ out) {
+__global__ void __launch_bounds__(128)
+    rcond_colsum_kernel(int m, const T* __restrict__ Rm, int ldr, const T* __restrict__ DinvR, int ldd,
+                        const real_t<T>* __restrict__ D, real_t<T>* __restrict__ sums) {
   using R = real_t<T>;
+  const int j = blockIdx.x;
+  R c1 = 0, c2 = 0;
+  for (int i = threadIdx.x; i <= j; i += blockDim.x) {
+    c1 += sqrt(abs2_(Rm[i + (int64_t)j * ldr]));
+    c2 += sqrt(abs2_(DinvR[i + (int64_t)j * ldd])) / D[i];
+  }
+  __shared__ R s1[128], s2[128];
+  s1[threadIdx.x] = c1;
+  s2[threadIdx.x] = c2;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { sums[j] = s1[0]; sums[m + j] = s2[0]; }
+}
+template <typename R>
+__global__ void rcond_finish_kernel(int m, const R* __restrict__ sums, R* __restrict__ out) {
   __shared__ R s1[256], s2[256];
   R n1 = 0, n2 = 0;
-  for (int j = threadIdx.x; j < m; j += blockDim.x) {
-    R c1 = 0, c2 = 0;
-    for (int i = 0; i <= j; i++) {
-      c1 += sqrt(abs2_(Rm[i + (int64_t)j * ldr]));
-      c2 += sqrt(abs2_(DinvR[i + (int64_t)j * ldd])) / D[i];
-    }
-    n1 = fmax(n1, c1);
-    n2 = fmax(n2, c2);
-  }
+  for (int j = threadIdx.x; j < m; j += blockDim.x) { n1 = fmax(n1, sums[j]); n2 = fmax(n2, sums[m + j]); }
   s1[threadIdx.x] = n1;
   s2[threadIdx.x] = n2;
   __syncthreads();
@@ -248,8 +260,12 @@ __global__ void rcond_kernel(int m, const T* __restrict__ Rm, int ldr, const T* 
 template <typename T>
 int sd_rcond(lb2_ctx* ctx, int m, const T* Rm, int ldr, const T* DinvR, int ldd, const real_t<T>* D,
              real_t<T>* out_dev) {
-  rcond_kernel<T><<<1, 256, 0, ctx->stream>>>(m, Rm, ldr, DinvR, ldd, D, out_dev);
-  ctx->launches++;
+  using R = real_t<T>;
+  R* sums = (R*)ctx_scratch(ctx, sizeof(R) * 2 * (size_t)m);
+  if (!sums) return -1;
+  rcond_colsum_kernel<T><<<m, 128, 0, ctx->stream>>>(m, Rm, ldr, DinvR, ldd, D, sums);
+  rcond_finish_kernel<R><<<1, 256, 0, ctx->stream>>>(m, sums, out_dev);
+  ctx->launches += 2;
   LB2_CUDA_OK(cudaGetLastError());
   return 0;
 }

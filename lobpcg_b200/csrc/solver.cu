@@ -326,6 +326,8 @@ class Solver : public SolverBase {
   int64_t* geev_piv = nullptr;
   int8_t* geev_sig = nullptr;
   T* CxAcc = nullptr;            // accurate Cx of a quality-5 pass (lazy)
+  T* SigV = nullptr;             // indefinite solver: V^H B V of this pass's ortho_indefinite = [X P] block of S^H B S
+  int sigv_cols = 0;
   // testing / measurement switches (lb2_solver_set_option)
   int force_ortho = 0;           // 1: run every pass in the ortho branch (useOrtho = 1 from the first pass)
   int debug_min_conv = 0;        // soft-lock at least this many leading columns regardless of their residuals (timing only)
@@ -381,7 +383,7 @@ void Solver<T>::release() {
   if (arena) cudaFree(arena);
   arena = nullptr;
   slab[0] = slab[1] = AS = wA = wB = nullptr;
-  T** big[] = {&G, &GA, &DinvR, &Z, &Tmp, &Cx, &Cp, &Q, &Tau, &Graw, &GAraw, &Gc, &GAc, &Gw, &GAw, &Ccat};
+  T** big[] = {&G, &GA, &DinvR, &Z, &Tmp, &Cx, &Cp, &Q, &Tau, &Graw, &GAraw, &Gc, &GAc, &Gw, &GAw, &Ccat, &SigV};
   for (auto p : big) { if (*p) cudaFree(*p); *p = nullptr; }
   R** rs[] = {&D, &Lam, &Eig, &Sums, &Scal};
   for (auto p : rs) { if (*p) cudaFree(*p); *p = nullptr; }
@@ -420,6 +422,11 @@ int Solver<T>::alloc() {
   wB = (T*)base;
   T** sm[] = {&G, &GA, &DinvR, &Z, &Tmp};
   for (auto p : sm) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * m3));
+  if (indef && !helper_mode) {
+    LB2_CUDA_OK(cudaMalloc(&SigV, sizeof(T) * 4 * (size_t)k * k));
+    LB2_CUDA_OK(cudaMalloc(&Gw, sizeof(T) * m3 * k));
+    LB2_CUDA_OK(cudaMemsetAsync(Gw, 0, sizeof(T) * m3 * k, ctx->stream));
+  }
   if (gram_cache) {
     T** sm2[] = {&Graw, &GAraw};
     for (auto p : sm2) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * m3));
@@ -919,7 +926,13 @@ int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret, bool indefinit
   const R eps = eps_tol();
   int nu = nu0;
   // indefinite metric (ortho_indefinite_impl.inc:98-105): signature matrix sig = V^H B V, kept in GA
-  if (indefinite) LB2_TRY(gram_self_B(nv, V, GA));
+  if (indefinite) {
+    LB2_TRY(gram_self_B(nv, V, GA));
+    if (SigV && !helper_mode) {   // the same matrix is the [X P] block of S^H B S in this pass's Rayleigh-Ritz (rr_indef)
+      LB2_CUDA_OK(cudaMemcpyAsync(SigV, GA, sizeof(T) * (size_t)nv * nv, cudaMemcpyDeviceToDevice, ctx->stream));
+      sigv_cols = nv;
+    }
+  }
   // ||B V||_F
   R BV_norm = 0;
   {
@@ -1097,7 +1110,29 @@ int Solver<T>::rr_indef(int m, int from_col, bool initial) {
   last_quality = 1;
   LB2_TRY(apply(opA, m - from_col, col(S, from_col), col(AS, from_col)));
   LB2_TRY(gram_ar(m, m, S, AS, GA, 1));
-  LB2_TRY(gram_self_B(m, S, G));
+  const int mxp = k + np, nwc = m - mxp;
+  if (!initial && SigV && sigv_cols == mxp && nwc > 0 && nwc <= k && !helper_mode) {
+    // S^H B S = [[V^H B V, V^H B W], [., W^H B W]]: the [X P] block is the signature matrix ortho_indefinite computed for
+    // this very V a moment ago (ortho_drop); only the W columns are contracted over n (6 n k^2 instead of 18 n k^2)
+    T* Wp = col(S, mxp);
+    LB2_TRY(apply(opB, nwc, Wp, wA));
+    tm.begin(PH_GRAM);
+    int rc = gram_cols<T>(ctx, n, m, nwc, S, n, wA, n, Gw, m, (const T*)nullptr, 0, (T*)nullptr, 0, mxp);
+    tm.end();
+    phase_work[PH_GRAM] += (Sc<T>::cplx ? 4.0 : 1.0) * (double)n * (2.0 * mxp * nwc + (double)nwc * (nwc + 1));
+    phase_calls[PH_GRAM]++;
+    if (rc) return rc;
+    if (reduce()) {
+      tm.begin(PH_COMM);
+      rc = allreduce_sum(ctx, Gw, (size_t)m * nwc * kCplx, kDouble);
+      tm.end();
+      if (rc) return rc;
+    }
+    LB2_TRY(sd_assemble_gram<T>(ctx, m, mxp, SigV, mxp, Gw, m, G, m));
+  } else {
+    LB2_TRY(gram_self_B(m, S, G));
+  }
+  sigv_cols = 0;   // valid for one Rayleigh-Ritz only (V changes with the projection)
   tm.begin(PH_SMALL);
   LB2_CUDA_OK(cudaMemcpyAsync(Tmp, G, sizeof(T) * (size_t)m * m, cudaMemcpyDeviceToDevice, ctx->stream));
   LB2_CUDA_OK(cudaMemcpyAsync(DinvR, GA, sizeof(T) * (size_t)m * m, cudaMemcpyDeviceToDevice, ctx->stream));   // G_A survives a failed potrf
