@@ -37,6 +37,7 @@ lb2_ctx *lb2_ctx_create(int device, void *cuda_stream /* cudaStream_t or NULL =>
 void lb2_ctx_destroy(lb2_ctx *ctx);
 int lb2_ctx_sync(lb2_ctx *ctx);
 int lb2_ctx_set_option(lb2_ctx *ctx, const char *key, int value);
+int lb2_ctx_trim(lb2_ctx *ctx); /* free the solver arena this context keeps for reuse by its next solve (LB2_ARENA_CACHE=0: never kept) */
 unsigned long long lb2_ctx_launches(lb2_ctx *ctx); /* kernels launched so far through this context */
 lb2_ctx *lb2_default_ctx(void);                    /* lazily created context on the current device */
 

@@ -50,6 +50,7 @@ def _declare(L):
     L.lb2_ctx_create.argtypes = [ci, vp]
     L.lb2_ctx_destroy.argtypes = [vp]
     L.lb2_ctx_sync.argtypes = [vp]
+    L.lb2_ctx_trim.argtypes = [vp]
     L.lb2_ctx_set_option.argtypes = [vp, C.c_char_p, ci]
     L.lb2_ctx_launches.restype = C.c_ulonglong
     L.lb2_ctx_launches.argtypes = [vp]
@@ -169,6 +170,10 @@ class Context:
 
     def set_option(self, key: str, value: int):
         _ck(lib().lb2_ctx_set_option(self.h, key.encode(), int(value)), f"set_option({key})")
+
+    def trim(self):
+        """Free the solver arena the context keeps for reuse by its next solve."""
+        _ck(lib().lb2_ctx_trim(self.h), "lb2_ctx_trim")
 
     @property
     def launches(self) -> int:

@@ -24,6 +24,62 @@ int run_solver_multi(char prefix, void* alg, int indefinite, int want);
 extern "C" void lb2_note_single_gpu_call(void);
 
 namespace lb2 {
+static std::mutex g_ctx_mu;
+static std::vector<lb2_ctx*> g_all_ctx;   // every live context (their cached arenas are freed when an allocation fails)
+
+static void trim_ctx(lb2_ctx* c) {
+  if (c->arena_cache) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaSetDevice(c->device);
+    cudaFree(c->arena_cache);
+    cudaSetDevice(dev);
+  }
+  c->arena_cache = nullptr;
+  c->arena_cache_bytes = 0;
+}
+
+void* arena_alloc(lb2_ctx* ctx, size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (ctx->arena_cache && ctx->arena_cache_bytes >= bytes && ctx->arena_cache_bytes <= bytes + bytes / 4) {
+      void* p = ctx->arena_cache;
+      ctx->arena_cache = nullptr;
+      ctx->arena_cache_bytes = 0;
+      return p;
+    }
+    trim_ctx(ctx);
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {   // another context may be sitting on a cached arena: free them all and retry once
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lk(g_ctx_mu);
+      for (lb2_ctx* c : g_all_ctx) trim_ctx(c);
+    }
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    fprintf(stderr, "lobpcg_b200: cannot allocate the %.2f GB solver arena (%s)\n", bytes / 1e9, cudaGetErrorString(e));
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void arena_release(lb2_ctx* ctx, void* p, size_t bytes) {
+  if (!p) return;
+  static const bool keep = [] { const char* e = getenv("LB2_ARENA_CACHE"); return !(e && atoi(e) == 0); }();
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if (keep && !ctx->arena_cache) {
+    ctx->arena_cache = p;
+    ctx->arena_cache_bytes = bytes;
+    return;
+  }
+  cudaFree(p);
+}
+
 void* ctx_scratch(lb2_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->ws_bytes) return ctx->ws;
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
@@ -135,13 +191,31 @@ lb2_ctx* lb2_ctx_create(int device, void* cuda_stream) {
     }
     c->own_stream = true;
   }
+  {
+    std::lock_guard<std::mutex> lk(lb2::g_ctx_mu);
+    lb2::g_all_ctx.push_back(c);
+  }
   return c;
+}
+
+// release the memory this context keeps for reuse (the solver arena of the last solve)
+int lb2_ctx_trim(lb2_ctx* c) {
+  if (!c) return -1;
+  std::lock_guard<std::mutex> lk(lb2::g_ctx_mu);
+  lb2::trim_ctx(c);
+  return 0;
 }
 
 void lb2_ctx_destroy(lb2_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  {
+    std::lock_guard<std::mutex> lk(lb2::g_ctx_mu);
+    lb2::trim_ctx(c);
+    auto& v = lb2::g_all_ctx;
+    v.erase(std::remove(v.begin(), v.end(), c), v.end());
+  }
   if (c->cublas) cublasDestroy(c->cublas);
   if (c->cusolver) cusolverDnDestroy(c->cusolver);
   lb2::gram_wl_cache_free(c);
@@ -199,6 +273,14 @@ lb2_ctx* lb2_default_ctx(void) {
 void* lb2_malloc(size_t bytes) {
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+  if (e != cudaSuccess) {   // cached solver arenas (arena_release) give way to any other allocation of the library
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lk(lb2::g_ctx_mu);
+      for (lb2_ctx* c : lb2::g_all_ctx) lb2::trim_ctx(c);
+    }
+    e = cudaMalloc(&p, bytes ? bytes : 1);
+  }
   if (e != cudaSuccess) {
     fprintf(stderr, "lobpcg_b200: cudaMalloc(%zu) failed: %s\n", bytes, cudaGetErrorString(e));
     return nullptr;

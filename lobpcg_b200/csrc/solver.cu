@@ -380,7 +380,10 @@ class Solver : public SolverBase {
 
 template <typename T>
 void Solver<T>::release() {
-  if (arena) cudaFree(arena);
+  if (arena) {
+    cudaStreamSynchronize(ctx->stream);   // nothing may still be running on a block the next solve reuses
+    arena_release(ctx, arena, arena_bytes);
+  }
   arena = nullptr;
   slab[0] = slab[1] = AS = wA = wB = nullptr;
   T** big[] = {&G, &GA, &DinvR, &Z, &Tmp, &Cx, &Cp, &Q, &Tau, &Graw, &GAraw, &Gc, &GAc, &Gw, &GAw, &Ccat, &SigV};
@@ -412,14 +415,20 @@ int Solver<T>::alloc() {
   if (indef) gram_cache = false;
   as_cols = (gram_cache && !helper_mode) ? 2 * k : 3 * k;
   const size_t as_b = al(sizeof(T) * (size_t)as_cols * n);
-  arena_bytes = 2 * slab_b + as_b + 2 * wrk_b;
-  LB2_CUDA_OK(cudaMalloc(&arena, arena_bytes));
+  // scratch blocks only where something uses them: wA holds B-products (B != NULL), wB the input of T, X_accurate of the
+  // indefinite solver and the out-of-place result of SVQB — which, without those, goes to the slab that is not current
+  // (dead while W is being orthogonalised).  B = T = NULL (config C5): 2 slabs + [AX | AW] = 8 n k scalars.
+  const bool need_wA = opB != nullptr || helper_mode, need_wB = opT != nullptr || indef || helper_mode;
+  arena_bytes = 2 * slab_b + as_b + (need_wA ? wrk_b : 0) + (need_wB ? wrk_b : 0);
+  arena = arena_alloc(ctx, arena_bytes);
+  if (!arena) return -1;
   char* base = (char*)arena;
   slab[0] = (T*)base; base += slab_b;
   slab[1] = (T*)base; base += slab_b;
   AS = (T*)base; base += as_b;
-  wA = (T*)base; base += wrk_b;
-  wB = (T*)base;
+  wA = wB = nullptr;
+  if (need_wA) { wA = (T*)base; base += wrk_b; }
+  if (need_wB) wB = (T*)base;
   T** sm[] = {&G, &GA, &DinvR, &Z, &Tmp};
   for (auto p : sm) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * m3));
   if (indef && !helper_mode) {
@@ -645,8 +654,8 @@ int Solver<T>::sumsq_total(int nc, const T* X, R* out_dev) {
 
 template <typename T>
 int Solver<T>::estimate_norm(const LinOpRaw* op, uint64_t seed, R* out) {
-  T* x = wA;
-  T* y = wB;
+  T* x = slab[1];             // two columns of the slab that is not in use yet (X0 lives in slab[0]; init / helpers only)
+  T* y = slab[1] + n;
   LB2_TRY(fill_rows(x, 1, seed));
   LB2_TRY(sumsq_total(1, x, Scal));
   LB2_TRY(normalize_by<T>(ctx, n, x, Scal));
@@ -905,9 +914,11 @@ int Solver<T>::svqb(T* U, int nu, R tau, bool drop, int* nret) {
   tm.end();
   LB2_TRY(sync());
   const int keep = *(int*)hbuf;
-  LB2_TRY(nn(nu, keep, make<T>(1), U, Tmp, nu, zero<T>(), wB));
+  T* out = wB ? wB : slab[1 - cur];   // (no scratch block: the other slab is dead while W is orthogonalised)
+  if (out == U || (U > out && U < out + (int64_t)keep * n)) { fprintf(stderr, "lobpcg_b200: svqb workspace aliases its operand\n"); return -1; }
+  LB2_TRY(nn(nu, keep, make<T>(1), U, Tmp, nu, zero<T>(), out));
   tm.begin(PH_OTHER);
-  LB2_TRY(copy_block<T>(ctx, n, keep, wB, n, U, n));
+  LB2_TRY(copy_block<T>(ctx, n, keep, out, n, U, n));
   tm.end();
   *nret = keep;
   return 0;
