@@ -17,6 +17,7 @@
 // c32 uses the generic register-blocked SIMT kernels at the bottom.
 #include "common.cuh"
 #include "context.h"
+#include <algorithm>
 #include <cmath>
 #include "kernels.h"
 #include "tile_loader.cuh"
@@ -782,6 +783,124 @@ __global__ void __launch_bounds__(WM* WN * 32)
   }
 }
 
+// Persistent version of the 128 x 128 tall NN tile (option nn_persist, default on): one CTA per SM walks the (row tile,
+// column tile) items b, b + gridDim.x, ... (column tile fastest, so the CTAs that run together share an S row tile through
+// L2) and the cp.async ring runs ACROSS items: while the last chunks of an item are multiplied the first chunks of the
+// next item are already in flight, and its epilogue stores overlap those loads.  The one-tile-per-CTA kernel above pays
+// the pipeline fill (two HBM round trips) and the drain once per 118 us of MMA work, with a single resident CTA per SM
+// (registers) nothing hides them.
+template <int BK, int STAGES, bool VECA, bool VECB>
+__global__ void __launch_bounds__(256, 1)
+    tall_nn_persist_kernel(const double* __restrict__ S, int64_t lds, const double* __restrict__ C, int ldc,
+                           double* __restrict__ Out, int64_t ldo, int64_t n, int kd, int nb, int nct, int64_t nitems,
+                           double alpha, double beta) {
+  constexpr int TM = 128, TN = 128, WM = 2, WN = 4, NT = 256;
+  constexpr int LDA = TM + 4;
+  constexpr int LDB = BK + 4;
+  constexpr int MB = TM / WM / 8;
+  constexpr int NB = TN / WN / 8;
+  extern __shared__ __align__(16) double smem[];
+  double* Ss = smem;                                   // [STAGES][BK][LDA]
+  double* Cs = smem + (size_t)STAGES * BK * LDA;       // [STAGES][TN][LDB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WM, wn = warp / WM;
+  const int g = lane >> 2, t = lane & 3;
+  const int nchunks = (kd + BK - 1) / BK;
+
+  // load cursor: item / chunk of the next copy
+  int64_t l_item = blockIdx.x;
+  int l_chunk = 0;
+  TileLoaderF64<BK, TM, LDA, NT, VECA> la;
+  TileLoaderF64<TN, BK, LDB, NT, VECB> lb;
+  int64_t l_rows_valid = 0;
+  auto start_item = [&](int64_t item) {
+    const int ct = (int)(item % nct);
+    const int64_t r0 = (item / nct) * TM;
+    la.init(S, lds, r0, 0, BK, tid);
+    lb.init(C, ldc, 0, ct * TN, nb, tid);
+    l_rows_valid = n - r0;
+  };
+  if (l_item < nitems) start_item(l_item);
+  int wstage = 0;
+  auto issue = [&]() {
+    if (l_item < nitems) {
+      const int kleft = kd - l_chunk * BK;
+      if (kleft >= BK) {
+        la.issue(Ss + wstage * (BK * LDA), S, l_rows_valid);
+      } else {   // tail chunk: only the first kleft k-columns exist
+        TileLoaderF64<BK, TM, LDA, NT, VECA> lt = la;
+        lt.colmask = 0;
+#pragma unroll
+        for (int s = 0; s < lt.NSLOT; s++)
+          if (tid / lt.CPC + s * lt.CSTEP < kleft) lt.colmask |= 1u << s;
+        lt.issue(Ss + wstage * (BK * LDA), S, l_rows_valid);
+      }
+      lb.issue(Cs + wstage * (TN * LDB), C, (int64_t)kleft);
+      la.advance((int64_t)BK * lds);
+      lb.advance(BK);
+      if (++l_chunk == nchunks) {
+        l_chunk = 0;
+        l_item += gridDim.x;
+        if (l_item < nitems) start_item(l_item);
+      }
+    }
+    wstage = (wstage + 1 == STAGES) ? 0 : wstage + 1;
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) issue();
+
+  int rstage = 0;
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    double acc[MB][NB][2];
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+      for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int chunk = 0; chunk < nchunks; chunk++) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      issue();
+      const double* as = Ss + rstage * (BK * LDA) + t * LDA + wm * MB * 8 + g;
+      const double* bs = Cs + rstage * (TN * LDB) + (wn * NB * 8 + g) * LDB + t;
+      rstage = (rstage + 1 == STAGES) ? 0 : rstage + 1;
+#pragma unroll
+      for (int ks = 0; ks < BK / 4; ks++) {
+        double a[MB], b[NB];
+#pragma unroll
+        for (int i = 0; i < MB; i++) a[i] = as[ks * 4 * LDA + i * 8];
+#pragma unroll
+        for (int j = 0; j < NB; j++) b[j] = bs[j * 8 * LDB + ks * 4];
+#pragma unroll
+        for (int i = 0; i < MB; i++)
+#pragma unroll
+          for (int j = 0; j < NB; j++) dmma884(acc[i][j], a[i], b[j]);
+      }
+    }
+    const int c0 = (int)(item % nct) * TN;
+    const int64_t r0 = (item / nct) * TM;
+#pragma unroll
+    for (int i = 0; i < MB; i++) {
+      const int64_t row = r0 + wm * MB * 8 + i * 8 + g;
+      if (row >= n) continue;
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+        const int col = c0 + wn * NB * 8 + j * 8 + 2 * t;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          if (col + q < nb) {
+            double* p = Out + row + (int64_t)(col + q) * ldo;
+            double v = alpha * acc[i][j][q];
+            if (beta != 0.0) v += beta * (*p);
+            *p = v;
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // Generic SIMT tall NN (all scalar types): 64 rows x 64 cols tile, BK = 16.
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -1165,7 +1284,28 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
       const int forced = ctx->nn_tile;
       const int nfull = (forced == 0 || forced == 128) ? nb / 128 : 0;
       int rc = 0;
-      if (nfull > 0) {
+      if (nfull > 0 && ctx->nn_persist != 0 && ctx->nn_bk != 16) {
+        // persistent 128 x 128 tiles: one CTA per SM, cp.async ring running across the tiles
+        const int nct = nfull;
+        const int64_t nitems = ((n + 127) / 128) * nct;
+        const bool veca = (lds % 2 == 0) && ((uintptr_t)S % 16 == 0);
+        const bool vecb = (ldc % 2 == 0) && ((uintptr_t)C % 16 == 0);
+        constexpr size_t smem = sizeof(double) * (size_t)3 * (32 * (128 + 4) + 128 * (32 + 4));
+        const unsigned grid = (unsigned)std::min<int64_t>(nitems, ctx->sm_count);
+#define LB2_NNP_LAUNCH(VA, VB)                                                                          \
+  {                                                                                                     \
+    auto kp = tall_nn_persist_kernel<32, 3, VA, VB>;                                                    \
+    LB2_CUDA_OK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    kp<<<grid, 256, smem, ctx->stream>>>(S, lds, C, ldc, Out, ldo, n, kd, nfull * 128, nct, nitems, alpha, beta); \
+  }
+        if (veca && vecb) LB2_NNP_LAUNCH(true, true)
+        else if (veca) LB2_NNP_LAUNCH(true, false)
+        else if (vecb) LB2_NNP_LAUNCH(false, true)
+        else LB2_NNP_LAUNCH(false, false)
+#undef LB2_NNP_LAUNCH
+        ctx->launches++;
+        LB2_CUDA_OK(cudaGetLastError());
+      } else if (nfull > 0) {
         if (ctx->nn_bk != 16)
           rc = launch_nn_dmma<128, 128, 2, 4, 32, 3>(ctx, n, kd, nfull * 128, alpha, S, lds, C, ldc, beta, Out, ldo);
         else
