@@ -377,14 +377,20 @@ __global__ void __launch_bounds__(256)
   const int ncol = min(NCOL, nc - c0);
   const int64_t r0 = rb * CSRW_RB, wlo = r0 - H;
   const T* xb = X + (int64_t)c0 * ldx;
+  // window fill with cp.async (zero-filling outside the matrix / beyond the last column): every copy is in flight before the
+  // first one lands — plain loads + stores serialise on the load latency (in-order issue), which made the first version of
+  // this kernel slower than the plain one
   for (int c = 0; c < NCOL; c++) {
     T* w = win + (size_t)c * WL;
     const T* xc = xb + (int64_t)c * ldx;
     for (int i = threadIdx.x; i < WL; i += 256) {
       const int64_t row = wlo + i;
-      w[i] = (c < ncol && row >= 0 && row < n) ? xc[row] : zero<T>();
+      const bool ok = c < ncol && row >= 0 && row < n;
+      cp_async_zfill<sizeof(T)>(w + i, ok ? xc + row : X, ok ? (int)sizeof(T) : 0);
     }
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
 #pragma unroll 1
   for (int rr = 0; rr < CSRW_RB / 256; rr++) {
