@@ -80,6 +80,29 @@ void arena_release(lb2_ctx* ctx, void* p, size_t bytes) {
   cudaFree(p);
 }
 
+void* pinned_take(lb2_ctx* ctx, size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (ctx->pinned_cache && ctx->pinned_cache_bytes >= bytes) {
+      void* p = ctx->pinned_cache;
+      ctx->pinned_cache = nullptr;
+      ctx->pinned_cache_bytes = 0;
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void pinned_give(lb2_ctx* ctx, void* p, size_t bytes) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!ctx->pinned_cache) { ctx->pinned_cache = p; ctx->pinned_cache_bytes = bytes; return; }
+  }
+  cudaFreeHost(p);
+}
+
 void* ctx_scratch(lb2_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->ws_bytes) return ctx->ws;
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
@@ -213,6 +236,8 @@ void lb2_ctx_destroy(lb2_ctx* c) {
   {
     std::lock_guard<std::mutex> lk(lb2::g_ctx_mu);
     lb2::trim_ctx(c);
+    if (c->pinned_cache) cudaFreeHost(c->pinned_cache);
+    c->pinned_cache = nullptr;
     auto& v = lb2::g_all_ctx;
     v.erase(std::remove(v.begin(), v.end(), c), v.end());
   }

@@ -41,11 +41,13 @@ struct lb2_ctx {
   int gram_tc5 = -1;     // float Gram through tcgen05 / TMEM (gram_tc5.cu): -1 = auto (on), 0 = off, 1 = on
   int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
   int spmm_cols = 0;     // CSR SpMM columns per thread (0 = heuristic)
-  int csr_window = -1;   // windowed CSR kernel for banded matrices: -1 = auto (on), 0 = off
+  int csr_window = -1;   // windowed CSR kernel for banded matrices: 1 = on; -1 / 0 = off (r02: 2.09 ms against 1.38 ms of the plain kernel at 128^3 x 128)
   // one released solver arena kept for the next solve on this context (arena_alloc / arena_release in capi.cu): a 100 GB
   // cudaMalloc + cudaFree pair costs 0.1-0.5 s per reference-facing call; LB2_ARENA_CACHE=0 disables, lb2_ctx_trim frees
   void* arena_cache = nullptr;
   size_t arena_cache_bytes = 0;
+  void* pinned_cache = nullptr;      // small pinned host buffer of the last solver (same idea)
+  size_t pinned_cache_bytes = 0;
   // launch counter (bench.py "gpu_launches")
   unsigned long long launches = 0;
   // multi-GPU (row-partitioned) state; comm == nullptr => single GPU
@@ -60,6 +62,8 @@ void gram_wl_cache_free(lb2_ctx* ctx);   // gram_wl.cu
 // solver arena with reuse across solves (capi.cu); arena_alloc frees every context's cached arena before giving up
 void* arena_alloc(lb2_ctx* ctx, size_t bytes);
 void arena_release(lb2_ctx* ctx, void* p, size_t bytes);
+void* pinned_take(lb2_ctx* ctx, size_t bytes);
+void pinned_give(lb2_ctx* ctx, void* p, size_t bytes);
 // hostcopy.cu: pipelined copy between PAGEABLE host memory and the device (host-synchronous, ordered after ctx->stream)
 int host_copy(lb2_ctx* ctx, void* dst, const void* src, size_t bytes, bool to_device);
 void hostcopy_free(lb2_ctx* ctx);

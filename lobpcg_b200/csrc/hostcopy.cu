@@ -16,7 +16,7 @@
 namespace lb2 {
 
 namespace {
-constexpr size_t kChunk = (size_t)32 << 20;   // bytes per pinned chunk
+constexpr size_t kChunk = (size_t)64 << 20;   // bytes per pinned chunk (copy threads are spawned per chunk: ~0.15 ms against ~1.6 ms of copying)
 constexpr int kRing = 3;
 
 struct HostCopyState {
@@ -59,7 +59,7 @@ HostCopyState* state_of(lb2_ctx* ctx) {
   }
   if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) s->copy_stream = nullptr;
   const unsigned hw = std::thread::hardware_concurrency();
-  s->nthreads = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
+  s->nthreads = (int)std::max(1u, std::min(12u, hw ? (hw * 3) / 4 : 4u));
   ctx->hostcopy = s;
   return s;
 }

@@ -84,7 +84,7 @@ int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t 
         h.lo = b->halo_lo; h.hi = b->halo_hi; h.ld_lo = h.ld_hi = b->halo_ld;
         return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy, &h);
       }
-      if (b->csr_halo >= 2 && ctx->csr_window != 0) {   // banded matrix: shared-memory X window (spmm.cu: csr_win_kernel)
+      if (b->csr_halo >= 2 && ctx->csr_window > 0) {   // banded matrix: shared-memory X window (spmm.cu: csr_win_kernel), opt-in — measured slower than the plain kernel
         const int rc = spmm_csr_window<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy, b->csr_halo);
         if (rc != -100) return rc;
       }
@@ -249,7 +249,7 @@ class Solver : public SolverBase {
     if (!strcmp(key, "general_rr_calls")) return (double)general_rr_calls;
     if (!strcmp(key, "quality5_passes")) return (double)quality5_passes;
     if (!strcmp(key, "arena_bytes")) return (double)arena_bytes;
-    if (!strcmp(key, "arena_columns")) return n > 0 ? (double)arena_bytes / ((double)n * sizeof(T)) : 0.0;
+    if (!strcmp(key, "arena_columns")) return n > 0 ? (double)tall_bytes / ((double)n * sizeof(T)) : 0.0;   // block-vector columns
     return -1;
   }
   void write_failure_state() override {
@@ -281,7 +281,7 @@ class Solver : public SolverBase {
   }
   int k = 0, nev = 0;
   void* arena = nullptr;
-  size_t arena_bytes = 0;
+  size_t arena_bytes = 0, tall_bytes = 0;   // whole allocation / the n-proportional part (block vectors)
   const char *peer_lo = nullptr, *peer_hi = nullptr;  // neighbours' arena bases (CUDA-IPC mappings), or null
   T* slab[2] = {nullptr, nullptr};
   int cur = 0;
@@ -293,6 +293,7 @@ class Solver : public SolverBase {
   R* Theta = nullptr;      // indefinite RR: all m Ritz values, signature-sorted
   int8_t* dSig = nullptr;  // indefinite RR: signatures (+1/-1), sorted
   R* hbuf = nullptr;  // pinned
+  size_t hbuf_bytes = 0;
   T *hX = nullptr, *hY = nullptr;  // host staging for host-callback operators
   int np = 0, nw = 0;
   int sig_len = 0;
@@ -394,18 +395,17 @@ void Solver<T>::release() {
   }
   arena = nullptr;
   slab[0] = slab[1] = AS = wA = wB = nullptr;
-  T** big[] = {&G, &GA, &DinvR, &Z, &Tmp, &Cx, &Cp, &Q, &Tau, &Graw, &GAraw, &Gc, &GAc, &Gw, &GAw, &Ccat, &SigV, &SigC};
-  for (auto p : big) { if (*p) cudaFree(*p); *p = nullptr; }
-  R** rs[] = {&D, &Lam, &Eig, &Sums, &Scal};
-  for (auto p : rs) { if (*p) cudaFree(*p); *p = nullptr; }
-  if (Count) cudaFree(Count); Count = nullptr;
-  if (Theta) cudaFree(Theta); Theta = nullptr;
-  if (dSig) cudaFree(dSig); dSig = nullptr;
+  // (the small matrices are carved out of the arena: nothing to free)
+  G = GA = DinvR = Z = Tmp = Cx = Cp = Q = Tau = Graw = GAraw = Gc = GAc = Gw = GAw = Ccat = SigV = SigC = nullptr;
+  D = Lam = Eig = Sums = Scal = Theta = nullptr;
+  Count = nullptr;
+  dSig = nullptr;
   if (geev_ws) cudaFree(geev_ws); geev_ws = nullptr;
   if (geev_piv) cudaFree(geev_piv); geev_piv = nullptr;
   if (geev_sig) cudaFree(geev_sig); geev_sig = nullptr;
   if (CxAcc) cudaFree(CxAcc); CxAcc = nullptr;
-  if (hbuf) cudaFreeHost(hbuf); hbuf = nullptr;
+  if (hbuf) pinned_give(ctx, hbuf, hbuf_bytes);
+  hbuf = nullptr;
   if (hX) cudaFreeHost(hX); hX = nullptr;
   if (hY) cudaFreeHost(hY); hY = nullptr;
 }
@@ -427,7 +427,42 @@ int Solver<T>::alloc() {
   // indefinite solver and the out-of-place result of SVQB — which, without those, goes to the slab that is not current
   // (dead while W is being orthogonalised).  B = T = NULL (config C5): 2 slabs + [AX | AW] = 8 n k scalars.
   const bool need_wA = opB != nullptr || helper_mode, need_wB = opT != nullptr || indef || helper_mode;
-  arena_bytes = 2 * slab_b + as_b + (need_wA ? wrk_b : 0) + (need_wB ? wrk_b : 0);
+  if (indef && !helper_mode) { if (const char* e = getenv("LB2_INDEF_CACHE")) icache = (atoi(e) != 0); }
+  // The small matrices live behind the tall blocks in the SAME allocation: one cudaMalloc per solve (none at all when the
+  // context still holds the arena of the previous solve), no cudaFree at the end — two dozen cudaMalloc / cudaFree pairs
+  // cost 0.25-1.4 s per reference-facing call on a device with ~100 GB mapped (tools/e2e_probe2.py, r02).
+  const bool icache_bufs = indef && !helper_mode;
+  struct Req { void** p; size_t bytes; bool zero; };
+  std::vector<Req> req;
+  auto want = [&](auto** p, size_t bytes, bool zero = false) { req.push_back(Req{(void**)p, al(bytes), zero}); };
+  for (T** p : {&G, &GA, &DinvR, &Z, &Tmp}) want(p, sizeof(T) * m3 * m3);
+  if (icache_bufs || gram_cache) {
+    want(&GAraw, sizeof(T) * m3 * m3);
+    want(&GAc, sizeof(T) * 4 * (size_t)k * k);
+    want(&Gw, sizeof(T) * m3 * k, true);    // zeroed: the column-block kernel never writes the tiles below the diagonal of the W block
+    want(&GAw, sizeof(T) * m3 * k, true);
+    want(&Ccat, sizeof(T) * m3 * 2 * k);
+  }
+  if (icache_bufs) {
+    want(&SigV, sizeof(T) * 4 * (size_t)k * k);
+    want(&SigC, sizeof(T) * 4 * (size_t)k * k);
+  }
+  if (gram_cache) {
+    want(&Graw, sizeof(T) * m3 * m3);
+    want(&Gc, sizeof(T) * 4 * (size_t)k * k);
+  }
+  for (T** p : {&Cx, &Cp, &Q}) want(p, sizeof(T) * m3 * k);
+  want(&Tau, sizeof(T) * m3);
+  for (R** p : {&D, &Lam, &Eig, &Theta}) want(p, sizeof(R) * m3);
+  want(&Sums, sizeof(R) * (m3 + 16));
+  want(&Scal, sizeof(R) * 16);
+  want(&Count, sizeof(int) * 4);
+  want(&dSig, m3);
+  size_t small_b = 0;
+  for (auto& r : req) small_b += r.bytes;
+  const size_t tall_b = 2 * slab_b + as_b + (need_wA ? wrk_b : 0) + (need_wB ? wrk_b : 0);
+  arena_bytes = tall_b + small_b;
+  tall_bytes = tall_b;
   arena = arena_alloc(ctx, arena_bytes);
   if (!arena) return -1;
   char* base = (char*)arena;
@@ -436,47 +471,15 @@ int Solver<T>::alloc() {
   AS = (T*)base; base += as_b;
   wA = wB = nullptr;
   if (need_wA) { wA = (T*)base; base += wrk_b; }
-  if (need_wB) wB = (T*)base;
-  T** sm[] = {&G, &GA, &DinvR, &Z, &Tmp};
-  for (auto p : sm) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * m3));
-  if (indef && !helper_mode) {
-    if (const char* e = getenv("LB2_INDEF_CACHE")) icache = (atoi(e) != 0);
-    LB2_CUDA_OK(cudaMalloc(&SigV, sizeof(T) * 4 * (size_t)k * k));
-    T** wc[] = {&Gw, &GAw};
-    for (auto p : wc) {
-      LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * k));
-      LB2_CUDA_OK(cudaMemsetAsync(*p, 0, sizeof(T) * m3 * k, ctx->stream));
-    }
-    LB2_CUDA_OK(cudaMalloc(&SigC, sizeof(T) * 4 * (size_t)k * k));
-    LB2_CUDA_OK(cudaMalloc(&GAc, sizeof(T) * 4 * (size_t)k * k));
-    LB2_CUDA_OK(cudaMalloc(&GAraw, sizeof(T) * m3 * m3));
-    LB2_CUDA_OK(cudaMalloc(&Ccat, sizeof(T) * m3 * 2 * k));
+  if (need_wB) { wB = (T*)base; base += wrk_b; }
+  for (auto& r : req) {
+    *r.p = (void*)base;
+    if (r.zero) LB2_CUDA_OK(cudaMemsetAsync(base, 0, r.bytes, ctx->stream));
+    base += r.bytes;
   }
-  if (gram_cache) {
-    T** sm2[] = {&Graw, &GAraw};
-    for (auto p : sm2) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * m3));
-    T** sm3[] = {&Gc, &GAc};
-    for (auto p : sm3) LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * 4 * (size_t)k * k));
-    T** sm4[] = {&Gw, &GAw};
-    for (auto p : sm4) {   // zeroed once: the column-block kernel never writes the tiles below the diagonal of the W block
-      LB2_CUDA_OK(cudaMalloc(p, sizeof(T) * m3 * k));
-      LB2_CUDA_OK(cudaMemsetAsync(*p, 0, sizeof(T) * m3 * k, ctx->stream));
-    }
-    LB2_CUDA_OK(cudaMalloc(&Ccat, sizeof(T) * m3 * 2 * k));
-  }
-  LB2_CUDA_OK(cudaMalloc(&Cx, sizeof(T) * m3 * k));
-  LB2_CUDA_OK(cudaMalloc(&Cp, sizeof(T) * m3 * k));
-  LB2_CUDA_OK(cudaMalloc(&Q, sizeof(T) * m3 * k));
-  LB2_CUDA_OK(cudaMalloc(&Tau, sizeof(T) * m3));
-  LB2_CUDA_OK(cudaMalloc(&D, sizeof(R) * m3));
-  LB2_CUDA_OK(cudaMalloc(&Lam, sizeof(R) * m3));
-  LB2_CUDA_OK(cudaMalloc(&Eig, sizeof(R) * m3));
-  LB2_CUDA_OK(cudaMalloc(&Sums, sizeof(R) * (m3 + 16)));
-  LB2_CUDA_OK(cudaMalloc(&Scal, sizeof(R) * 16));
-  LB2_CUDA_OK(cudaMalloc(&Count, sizeof(int) * 4));
-  LB2_CUDA_OK(cudaMalloc(&Theta, sizeof(R) * m3));
-  LB2_CUDA_OK(cudaMalloc(&dSig, m3));
-  LB2_CUDA_OK(cudaMallocHost(&hbuf, sizeof(R) * (4 * (size_t)k + 64)));
+  hbuf_bytes = sizeof(R) * (4 * (size_t)k + 64);
+  hbuf = (R*)pinned_take(ctx, hbuf_bytes);
+  if (!hbuf) return -1;
   hEig.assign(k, R(0));
   hRes.assign(k, R(0));
   return 0;

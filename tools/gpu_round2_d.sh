@@ -12,9 +12,7 @@ python tools/kernel_bench.py nn 4096000 900 300 nn_persist=0
 python tools/kernel_bench.py nn 4096000 900 512
 python tools/kernel_bench.py nn 4096000 900 512 nn_persist=0
 python tools/kernel_bench.py csr 128 128
-python tools/kernel_bench.py csr 128 128 csr_window=0
-python tools/kernel_bench.py csr 128 256
-python tools/kernel_bench.py csr 128 256 csr_window=0
+python tools/kernel_bench.py csr 128 128 csr_window=1
 python tools/kernel_bench.py stencil 128 128
 ) > gpurun_out/kb_d.jsonl 2>&1
 cat gpurun_out/kb_d.jsonl
