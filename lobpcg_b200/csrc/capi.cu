@@ -268,6 +268,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "gram_wl")) c->gram_wl = value;
   else if (!strcmp(key, "gram_bk")) c->gram_bk = value;
   else if (!strcmp(key, "gram_tc5")) c->gram_tc5 = value;
+  else if (!strcmp(key, "gram_tma")) c->gram_tma = value;
   else if (!strcmp(key, "gram_load_pct")) c->gram_load_pct = value;
   else if (!strcmp(key, "gram_phase")) c->gram_phase = value;
   else if (!strcmp(key, "gram_strip_max")) c->gram_strip_max = value;

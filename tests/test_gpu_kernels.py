@@ -606,3 +606,29 @@ def test_csr_window_kernel_matches_scipy(ctx, dt, case):
     finally:
         ctx.set_option("csr_window", -1)
     close(got, ref, rtol(dt) * 10)
+
+
+# ------------------------------------------------------------------------------------------------ TMA-fed f32 Gram
+@pytest.mark.parametrize("shape", [(4099, 20, 20), (30001, 64, 33), (20000, 150, 129), (65536, 256, 256), (100000, 300, 100),
+                                   (8193, 260, 7)])
+def test_gram_float_tma_variant_matches_numpy(ctx, shape):
+    """gram_tc5_tma_kernel (context option gram_tma = 1): operand panels brought in by cp.async.bulk.tensor (SWIZZLE_128B
+    K-major tiles, mbarrier complete_tx) instead of per-thread cp.async; same 3xTF32 arithmetic, so the same tolerance as the
+    default kernel, and the two must agree closely with each other."""
+    n, ma, mb = shape
+    rng = np.random.default_rng(n + ma)
+    A, B = rand(rng, (n, ma), np.float32), rand(rng, (n, mb), np.float32)
+    dA, dB = api.DeviceArray.from_numpy(ctx, A), api.DeviceArray.from_numpy(ctx, B)
+    ref_ab = A.astype(np.float64).T @ B.astype(np.float64)
+    ref_aa = A.astype(np.float64).T @ A.astype(np.float64)
+    base_ab = api.gram(ctx, dA, dB).numpy(ctx)
+    ctx.set_option("gram_tma", 1)
+    try:
+        got_ab = api.gram(ctx, dA, dB).numpy(ctx)
+        got_aa = api.gram(ctx, dA, dA, upper=True).numpy(ctx)
+    finally:
+        ctx.set_option("gram_tma", 0)
+    close(got_ab, ref_ab, 2e-5)
+    close(got_aa, ref_aa, 2e-5)
+    close(got_ab, base_ab.astype(np.float64), 2e-6)
+    assert np.array_equal(got_aa, got_aa.T)
