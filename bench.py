@@ -419,10 +419,12 @@ def run_ours(args):
         passes = max(args.steps, 12)   # set-up (X0 upload, ||A||, initial RR, download) amortises over the passes
         st2 = None
         if world == 1:
-            X_dev = s.finish()["X"]        # any non-zero host block will do as X0; reuse the current iterate
+            # the SAME X0 as the device-resident run above (splitmix64 seed 7, generated on the device and downloaded), so
+            # the call walks through the same passes — the Cholesky-branch regime `value` is measured in
             st2 = api._setup(A, None, n, k, nev, np.float64, 1e-8, passes, None, None, False, 0)
-            st2.X()[:, :] = X_dev
-            del X_dev
+            Xd = api.fill_uniform(ctx, n, k, np.float64, 7)
+            api._ck(api.lib().lb2_memcpy_d2h(ctx.h, st2.st.S, Xd.ptr, n * k * 8), "d2h")
+            Xd.free()
         s.close()
         ctx.sync()
         barrier()

@@ -1284,7 +1284,7 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
       const int forced = ctx->nn_tile;
       const int nfull = (forced == 0 || forced == 128) ? nb / 128 : 0;
       int rc = 0;
-      if (nfull > 0 && ctx->nn_persist != 0 && ctx->nn_bk != 16) {
+      if (nfull > 0 && ctx->nn_persist != 0 && ctx->nn_bk != 16 && ctx->nn_warps != 16) {
         // persistent 128 x 128 tiles: one CTA per SM, cp.async ring running across the tiles
         const int nct = nfull;
         const int64_t nitems = ((n + 127) / 128) * nct;
@@ -1305,6 +1305,9 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
 #undef LB2_NNP_LAUNCH
         ctx->launches++;
         LB2_CUDA_OK(cudaGetLastError());
+      } else if (nfull > 0 && ctx->nn_warps == 16) {
+        // experiment: 16 warps (4 per scheduler) with 32 x 32 warp tiles instead of 8 warps with 64 x 32
+        rc = launch_nn_dmma<128, 128, 4, 4, 32, 3>(ctx, n, kd, nfull * 128, alpha, S, lds, C, ldc, beta, Out, ldo);
       } else if (nfull > 0) {
         if (ctx->nn_bk != 16)
           rc = launch_nn_dmma<128, 128, 2, 4, 32, 3>(ctx, n, kd, nfull * 128, alpha, S, lds, C, ldc, beta, Out, ldo);

@@ -235,7 +235,6 @@ class Solver : public SolverBase {
     } else if (!strcmp(key, "gram_cache_period")) cache_period = value > 0 ? value : 1;
     else if (!strcmp(key, "force_ortho")) force_ortho = value;
     else if (!strcmp(key, "indef_geev")) indef_geev = value;
-    else if (!strcmp(key, "indef_cache")) icache = value != 0;
     else if (!strcmp(key, "debug_min_conv")) debug_min_conv = value;
     else return -1;
     return 0;
@@ -330,12 +329,6 @@ class Solver : public SolverBase {
   T* CxAcc = nullptr;            // accurate Cx of a quality-5 pass (lazy)
   T* SigV = nullptr;             // indefinite solver: V^H B V of this pass's ortho_indefinite = [X P] block of S^H B S
   int sigv_cols = 0;
-  // indefinite solver: cached [X P] blocks (same congruence as the definite solver's): V^H B V (the signature matrix of
-  // ortho_indefinite) and V^H A V of the NEXT pass follow from this pass's G_B, G_A and [Cx | Cp_act]
-  bool icache = true;            // option "indef_cache" / LB2_INDEF_CACHE=0
-  bool icache_ok = false;
-  int icache_mxp = 0, isince = 0;
-  T* SigC = nullptr;             // cached V^H B V for the next pass (GAc holds V^H A V, GAraw this pass's S^H A S)
   // testing / measurement switches (lb2_solver_set_option)
   int force_ortho = 0;           // 1: run every pass in the ortho branch (useOrtho = 1 from the first pass)
   int debug_min_conv = 0;        // soft-lock at least this many leading columns regardless of their residuals (timing only)
@@ -369,7 +362,6 @@ class Solver : public SolverBase {
   int rr_initial();
   int rr_modified(int m);
   int update_gram_cache(int m, int nconv);
-  int update_indef_cache(int m, int nconv);
   double monitor_threshold() const { return kDouble ? 5e-12 : 2e-5; }
   int cp_from_z(int m, const T* Zm, T* VQ);           // VQ (m x k) = Z_perp Q
   int svqb(T* U, int nu, R tau, bool drop, int* nret);
@@ -396,7 +388,7 @@ void Solver<T>::release() {
   arena = nullptr;
   slab[0] = slab[1] = AS = wA = wB = nullptr;
   // (the small matrices are carved out of the arena: nothing to free)
-  G = GA = DinvR = Z = Tmp = Cx = Cp = Q = Tau = Graw = GAraw = Gc = GAc = Gw = GAw = Ccat = SigV = SigC = nullptr;
+  G = GA = DinvR = Z = Tmp = Cx = Cp = Q = Tau = Graw = GAraw = Gc = GAc = Gw = GAw = Ccat = SigV = nullptr;
   D = Lam = Eig = Sums = Scal = Theta = nullptr;
   Count = nullptr;
   dSig = nullptr;
@@ -427,29 +419,25 @@ int Solver<T>::alloc() {
   // indefinite solver and the out-of-place result of SVQB — which, without those, goes to the slab that is not current
   // (dead while W is being orthogonalised).  B = T = NULL (config C5): 2 slabs + [AX | AW] = 8 n k scalars.
   const bool need_wA = opB != nullptr || helper_mode, need_wB = opT != nullptr || indef || helper_mode;
-  if (indef && !helper_mode) { if (const char* e = getenv("LB2_INDEF_CACHE")) icache = (atoi(e) != 0); }
   // The small matrices live behind the tall blocks in the SAME allocation: one cudaMalloc per solve (none at all when the
   // context still holds the arena of the previous solve), no cudaFree at the end — two dozen cudaMalloc / cudaFree pairs
   // cost 0.25-1.4 s per reference-facing call on a device with ~100 GB mapped (tools/e2e_probe2.py, r02).
-  const bool icache_bufs = indef && !helper_mode;
   struct Req { void** p; size_t bytes; bool zero; };
   std::vector<Req> req;
   auto want = [&](auto** p, size_t bytes, bool zero = false) { req.push_back(Req{(void**)p, al(bytes), zero}); };
   for (T** p : {&G, &GA, &DinvR, &Z, &Tmp}) want(p, sizeof(T) * m3 * m3);
-  if (icache_bufs || gram_cache) {
+  if (indef && !helper_mode) {   // W columns of S^H B S + the signature matrix of the pass (rr_indef)
+    want(&Gw, sizeof(T) * m3 * k, true);
+    want(&SigV, sizeof(T) * 4 * (size_t)k * k);
+  }
+  if (gram_cache) {
+    want(&Graw, sizeof(T) * m3 * m3);
     want(&GAraw, sizeof(T) * m3 * m3);
+    want(&Gc, sizeof(T) * 4 * (size_t)k * k);
     want(&GAc, sizeof(T) * 4 * (size_t)k * k);
     want(&Gw, sizeof(T) * m3 * k, true);    // zeroed: the column-block kernel never writes the tiles below the diagonal of the W block
     want(&GAw, sizeof(T) * m3 * k, true);
     want(&Ccat, sizeof(T) * m3 * 2 * k);
-  }
-  if (icache_bufs) {
-    want(&SigV, sizeof(T) * 4 * (size_t)k * k);
-    want(&SigC, sizeof(T) * 4 * (size_t)k * k);
-  }
-  if (gram_cache) {
-    want(&Graw, sizeof(T) * m3 * m3);
-    want(&Gc, sizeof(T) * 4 * (size_t)k * k);
   }
   for (T** p : {&Cx, &Cp, &Q}) want(p, sizeof(T) * m3 * k);
   want(&Tau, sizeof(T) * m3);
@@ -957,12 +945,7 @@ int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret, bool indefinit
   int nu = nu0;
   // indefinite metric (ortho_indefinite_impl.inc:98-105): signature matrix sig = V^H B V, kept in GA
   if (indefinite) {
-    if (icache && icache_ok && icache_mxp == nv && SigC && !helper_mode) {
-      LB2_CUDA_OK(cudaMemcpyAsync(GA, SigC, sizeof(T) * (size_t)nv * nv, cudaMemcpyDeviceToDevice, ctx->stream));
-    } else {
-      LB2_TRY(gram_self_B(nv, V, GA));
-      icache_ok = false;          // (the A block is recomputed by this pass's rr_indef as well)
-    }
+    LB2_TRY(gram_self_B(nv, V, GA));
     if (SigV && !helper_mode) {   // the same matrix is the [X P] block of S^H B S in this pass's Rayleigh-Ritz (rr_indef)
       LB2_CUDA_OK(cudaMemcpyAsync(SigV, GA, sizeof(T) * (size_t)nv * nv, cudaMemcpyDeviceToDevice, ctx->stream));
       sigv_cols = nv;
@@ -1143,43 +1126,34 @@ template <typename T>
 int Solver<T>::rr_indef(int m, int from_col, bool initial) {
   T* S = Xp();
   last_quality = 1;
+  LB2_TRY(apply(opA, m - from_col, col(S, from_col), col(AS, from_col)));
+  LB2_TRY(gram_ar(m, m, S, AS, GA, 1));
   const int mxp = k + np, nwc = m - mxp;
-  const bool b_cols = !initial && SigV && sigv_cols == mxp && nwc > 0 && nwc <= k && !helper_mode;
-  const bool a_cols = b_cols && icache && icache_ok && icache_mxp == mxp && GAc && GAw;
-  T* Wp = col(S, mxp);
-  if (a_cols) {
-    LB2_TRY(apply(opA, nwc, Wp, col(AS, mxp)));      // A W only; [X P]^H A [X P] comes from the cache
-  } else {
-    LB2_TRY(apply(opA, m - from_col, col(S, from_col), col(AS, from_col)));
-    LB2_TRY(gram_ar(m, m, S, AS, GA, 1));
-  }
-  if (b_cols) {
-    // S^H B S = [[V^H B V, V^H B W], [., W^H B W]]: the [X P] block is the signature matrix ortho_indefinite used for this
-    // very V a moment ago (ortho_drop); only the W columns are contracted over n (6 n k^2 instead of 18 n k^2) — together
-    // with the W columns of S^H A S when its [X P] block is cached
+  if (!initial && SigV && sigv_cols == mxp && nwc > 0 && nwc <= k && !helper_mode) {
+    // S^H B S = [[V^H B V, V^H B W], [., W^H B W]]: the [X P] block is the signature matrix ortho_indefinite computed for
+    // this very V a moment ago (ortho_drop); only the W columns are contracted over n (6 n k^2 instead of 18 n k^2).
+    // (Carrying V^H B V and V^H A V ACROSS passes as C^H G C — what the definite solver does, §4b of DESIGN.md — was tried and
+    // removed: the indefinite Rayleigh-Ritz has no column scaling, ||C|| is large, and the congruence lost the positive
+    // definiteness of S^H A S / stalled the negative-shift pencils.)
+    T* Wp = col(S, mxp);
     LB2_TRY(apply(opB, nwc, Wp, wA));
     tm.begin(PH_GRAM);
-    int rc = a_cols ? gram_cols<T>(ctx, n, m, nwc, S, n, wA, n, Gw, m, col(AS, mxp), n, GAw, m, mxp)
-                    : gram_cols<T>(ctx, n, m, nwc, S, n, wA, n, Gw, m, (const T*)nullptr, 0, (T*)nullptr, 0, mxp);
+    int rc = gram_cols<T>(ctx, n, m, nwc, S, n, wA, n, Gw, m, (const T*)nullptr, 0, (T*)nullptr, 0, mxp);
     tm.end();
-    phase_work[PH_GRAM] += (a_cols ? 2.0 : 1.0) * (Sc<T>::cplx ? 4.0 : 1.0) * (double)n * (2.0 * mxp * nwc + (double)nwc * (nwc + 1));
+    phase_work[PH_GRAM] += (Sc<T>::cplx ? 4.0 : 1.0) * (double)n * (2.0 * mxp * nwc + (double)nwc * (nwc + 1));
     phase_calls[PH_GRAM]++;
     if (rc) return rc;
     if (reduce()) {
       tm.begin(PH_COMM);
       rc = allreduce_sum(ctx, Gw, (size_t)m * nwc * kCplx, kDouble);
-      if (!rc && a_cols) rc = allreduce_sum(ctx, GAw, (size_t)m * nwc * kCplx, kDouble);
       tm.end();
       if (rc) return rc;
     }
     LB2_TRY(sd_assemble_gram<T>(ctx, m, mxp, SigV, mxp, Gw, m, G, m));
-    if (a_cols) LB2_TRY(sd_assemble_gram<T>(ctx, m, mxp, GAc, mxp, GAw, m, GA, m));
   } else {
     LB2_TRY(gram_self_B(m, S, G));
   }
   sigv_cols = 0;   // valid for one Rayleigh-Ritz only (V changes with the projection)
-  if (GAraw && !helper_mode)   // S^H A S of this pass, for the cached blocks of the next one (update_indef_cache)
-    LB2_CUDA_OK(cudaMemcpyAsync(GAraw, GA, sizeof(T) * (size_t)m * m, cudaMemcpyDeviceToDevice, ctx->stream));
   tm.begin(PH_SMALL);
   LB2_CUDA_OK(cudaMemcpyAsync(Tmp, G, sizeof(T) * (size_t)m * m, cudaMemcpyDeviceToDevice, ctx->stream));
   LB2_CUDA_OK(cudaMemcpyAsync(DinvR, GA, sizeof(T) * (size_t)m * m, cudaMemcpyDeviceToDevice, ctx->stream));   // G_A survives a failed potrf
@@ -1268,30 +1242,6 @@ int Solver<T>::rr_indef_general(int m, bool initial) {
   return 0;
 }
 
-// Indefinite solver, after a pass: [X' P'_act] = S [Cx | Cp[:, nconv:]]  =>  V'^H B V' = C^H G_B C (next pass's signature matrix
-// of ortho_indefinite and [X P] block of S^H B S) and V'^H A V' = C^H G_A C.  Recomputed from the tall vectors every
-// cache_period passes, after a quality-5 pass and when the drift monitor trips (residual_pass).
-template <typename T>
-int Solver<T>::update_indef_cache(int m, int nconv) {
-  if (!icache || !SigC || helper_mode) { icache_ok = false; return 0; }
-  const int nact = k - nconv, mc = k + nact;
-  tm.begin(PH_SMALL);
-  LB2_CUDA_OK(cudaMemcpyAsync(Ccat, Cx, sizeof(T) * (size_t)m * k, cudaMemcpyDeviceToDevice, ctx->stream));
-  if (nact > 0)
-    LB2_CUDA_OK(cudaMemcpyAsync(Ccat + (size_t)m * k, Cp + (size_t)nconv * m, sizeof(T) * (size_t)m * nact,
-                                cudaMemcpyDeviceToDevice, ctx->stream));
-  LB2_TRY(sd_gemm<T>(ctx, 'N', m, mc, m, G, m, Ccat, m, Tmp, m));
-  LB2_TRY(sd_gemm<T>(ctx, 'H', mc, mc, m, Ccat, m, Tmp, m, SigC, mc));
-  LB2_TRY(sd_gemm<T>(ctx, 'N', m, mc, m, GAraw, m, Ccat, m, Tmp, m));
-  LB2_TRY(sd_gemm<T>(ctx, 'H', mc, mc, m, Ccat, m, Tmp, m, GAc, mc));
-  tm.end();
-  icache_mxp = mc;
-  isince = icache_ok ? isince + 1 : 1;
-  icache_ok = !(isince >= cache_period || cache_monitor > monitor_threshold() || last_quality == 5);
-  if (!icache_ok) cache_refreshes++;
-  return 0;
-}
-
 template <typename T>
 void Solver<T>::print_state(bool header) {
   if (alg->verbosity <= 0) return;
@@ -1323,7 +1273,7 @@ int Solver<T>::residual_pass(bool initial, const T* Xacc) {
   }
   res_BX = BX;
   const T* AXr = res_AX;
-  const bool monitor = (gram_cache || (indef && icache && !helper_mode)) && !initial && !Xacc;
+  const bool monitor = gram_cache && !initial && !Xacc;
   if (monitor) {
     // same two (three with B) streams as the plain norm pass, plus the Rayleigh quotients x^H A x and x^H B x of the new
     // Ritz vectors: the drift monitor of the cached Gram blocks
@@ -1571,7 +1521,6 @@ int Solver<T>::step_impl(int max_steps, int* passes_out) {
     T* Sold = slab[1 - cur];
     LB2_TRY(nn(m, nact, make<T>(1), Sold, Cp + (size_t)nconv * m, m, zero<T>(), col(Sn, k)));
     if (!indef) LB2_TRY(update_gram_cache(m, nconv));
-    else LB2_TRY(update_indef_cache(m, nconv));
     {
       T* Wdst = col(Sn, k + nact);
       LB2_TRY(resid(nact, res_AX + (int64_t)nconv * n, res_BX + (int64_t)nconv * n, Eig + nconv, opT ? wB : Wdst, nullptr));
