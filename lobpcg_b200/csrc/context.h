@@ -40,7 +40,7 @@ struct lb2_ctx {
   void* gram_wl_cache = nullptr;   // lb2::WlCache* (schedules per Gram shape)
   void* gram_wl_cols_cache = nullptr;   // lb2::WlColsCache* (schedules of the column-block products, gram_wl_cols_f64)
   int gram_tc5 = -1;     // float Gram through tcgen05 / TMEM (gram_tc5.cu): -1 = auto (on), 0 = off, 1 = on
-  int gram_tma = 0;      // float Gram: TMA-fed tcgen05 kernel (gram_tc5.cu: gram_tc5_tma_kernel): 1 = on, 0 = cp.async-fed kernel
+  int gram_tma = -1;     // float Gram: TMA-fed tcgen05 kernel (gram_tc5.cu: gram_tc5_tma_kernel): -1 / 1 = on, 0 = cp.async-fed kernel
   int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
   int spmm_cols = 0;     // CSR SpMM columns per thread (0 = heuristic)
   int csr_window = -1;   // windowed CSR kernel for banded matrices: 1 = on; -1 / 0 = off (r02: 2.09 ms against 1.38 ms of the plain kernel at 128^3 x 128)

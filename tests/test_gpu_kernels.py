@@ -612,7 +612,7 @@ def test_csr_window_kernel_matches_scipy(ctx, dt, case):
 @pytest.mark.parametrize("shape", [(4099, 20, 20), (30001, 64, 33), (20000, 150, 129), (65536, 256, 256), (100000, 300, 100),
                                    (8193, 260, 7)])
 def test_gram_float_tma_variant_matches_numpy(ctx, shape):
-    """gram_tc5_tma_kernel (context option gram_tma = 1): operand panels brought in by cp.async.bulk.tensor (SWIZZLE_128B
+    """gram_tc5_tma_kernel (the default f32 Gram; context option gram_tma = 0 selects the cp.async-fed kernel): operand panels brought in by cp.async.bulk.tensor (SWIZZLE_128B
     K-major tiles, mbarrier complete_tx) instead of per-thread cp.async; same 3xTF32 arithmetic, so the same tolerance as the
     default kernel, and the two must agree closely with each other."""
     n, ma, mb = shape
@@ -621,13 +621,13 @@ def test_gram_float_tma_variant_matches_numpy(ctx, shape):
     dA, dB = api.DeviceArray.from_numpy(ctx, A), api.DeviceArray.from_numpy(ctx, B)
     ref_ab = A.astype(np.float64).T @ B.astype(np.float64)
     ref_aa = A.astype(np.float64).T @ A.astype(np.float64)
-    base_ab = api.gram(ctx, dA, dB).numpy(ctx)
-    ctx.set_option("gram_tma", 1)
+    ctx.set_option("gram_tma", 0)            # the cp.async-fed kernel of round 1
     try:
-        got_ab = api.gram(ctx, dA, dB).numpy(ctx)
-        got_aa = api.gram(ctx, dA, dA, upper=True).numpy(ctx)
+        base_ab = api.gram(ctx, dA, dB).numpy(ctx)
     finally:
-        ctx.set_option("gram_tma", 0)
+        ctx.set_option("gram_tma", -1)       # default: TMA-fed
+    got_ab = api.gram(ctx, dA, dB).numpy(ctx)
+    got_aa = api.gram(ctx, dA, dA, upper=True).numpy(ctx)
     close(got_ab, ref_ab, 2e-5)
     close(got_aa, ref_aa, 2e-5)
     close(got_ab, base_ab.astype(np.float64), 2e-6)
