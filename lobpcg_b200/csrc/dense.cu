@@ -783,6 +783,37 @@ __global__ void __launch_bounds__(WM* WN * 32)
   }
 }
 
+// k-steps [KS0, KS1) of one staged chunk of the tall NN kernels (4 columns of S per DMMA step)
+template <int MB, int NB, int LDA, int LDB, int KS0, int KS1>
+__device__ __forceinline__ void nn_ksteps(double (&acc)[MB][NB][2], const double* __restrict__ as,
+                                          const double* __restrict__ bs) {
+#pragma unroll
+  for (int ks = KS0; ks < KS1; ks++) {
+    double a[MB], b[NB];
+#pragma unroll
+    for (int i = 0; i < MB; i++) a[i] = as[ks * 4 * LDA + i * 8];
+#pragma unroll
+    for (int j = 0; j < NB; j++) b[j] = bs[j * 8 * LDB + ks * 4];
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+      for (int j = 0; j < NB; j++) dmma884(acc[i][j], a[i], b[j]);
+  }
+}
+template <int MB, int NB, int LDA, int LDB>
+__device__ __forceinline__ void nn_kstep_rt(double (&acc)[MB][NB][2], const double* __restrict__ as,
+                                            const double* __restrict__ bs, int ks) {
+  double a[MB], b[NB];
+#pragma unroll
+  for (int i = 0; i < MB; i++) a[i] = as[ks * 4 * LDA + i * 8];
+#pragma unroll
+  for (int j = 0; j < NB; j++) b[j] = bs[j * 8 * LDB + ks * 4];
+#pragma unroll
+  for (int i = 0; i < MB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) dmma884(acc[i][j], a[i], b[j]);
+}
+
 // Persistent version of the 128 x 128 tall NN tile (option nn_persist, default on): one CTA per SM walks the (row tile,
 // column tile) items b, b + gridDim.x, ... (column tile fastest, so the CTAs that run together share an S row tile through
 // L2) and the cp.async ring runs ACROSS items: while the last chunks of an item are multiplied the first chunks of the
@@ -793,7 +824,7 @@ template <int BK, int STAGES, bool VECA, bool VECB>
 __global__ void __launch_bounds__(256, 1)
     tall_nn_persist_kernel(const double* __restrict__ S, int64_t lds, const double* __restrict__ C, int ldc,
                            double* __restrict__ Out, int64_t ldo, int64_t n, int kd, int nb, int nct, int64_t nitems,
-                           double alpha, double beta) {
+                           double alpha, double beta, int split) {
   constexpr int TM = 128, TN = 128, WM = 2, WN = 4, NT = 256;
   constexpr int LDA = TM + 4;
   constexpr int LDB = BK + 4;
@@ -806,6 +837,7 @@ __global__ void __launch_bounds__(256, 1)
   const int wm = warp % WM, wn = warp / WM;
   const int g = lane >> 2, t = lane & 3;
   const int nchunks = (kd + BK - 1) / BK;
+  const int tail_ks = (kd - (nchunks - 1) * BK + 3) / 4;   // 4-column MMA steps of the last chunk
 
   // load cursor: item / chunk of the next copy
   int64_t l_item = blockIdx.x;
@@ -860,21 +892,20 @@ __global__ void __launch_bounds__(256, 1)
     for (int chunk = 0; chunk < nchunks; chunk++) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
-      issue();
+      // the copy instructions of a chunk (address arithmetic + 16 LDGSTS per thread) keep a warp away from the DMMA
+      // pipe for several hundred clocks; the two warps of a scheduler (w, w + 4) take that detour at different times
+      if (warp < split) issue();
       const double* as = Ss + rstage * (BK * LDA) + t * LDA + wm * MB * 8 + g;
       const double* bs = Cs + rstage * (TN * LDB) + (wn * NB * 8 + g) * LDB + t;
       rstage = (rstage + 1 == STAGES) ? 0 : rstage + 1;
-#pragma unroll
-      for (int ks = 0; ks < BK / 4; ks++) {
-        double a[MB], b[NB];
-#pragma unroll
-        for (int i = 0; i < MB; i++) a[i] = as[ks * 4 * LDA + i * 8];
-#pragma unroll
-        for (int j = 0; j < NB; j++) b[j] = bs[j * 8 * LDB + ks * 4];
-#pragma unroll
-        for (int i = 0; i < MB; i++)
-#pragma unroll
-          for (int j = 0; j < NB; j++) dmma884(acc[i][j], a[i], b[j]);
+      if (chunk + 1 < nchunks || tail_ks == BK / 4) {
+        nn_ksteps<MB, NB, LDA, LDB, 0, BK / 8>(acc, as, bs);
+        if (warp >= split) issue();
+        nn_ksteps<MB, NB, LDA, LDB, BK / 8, BK / 4>(acc, as, bs);
+      } else {   // last chunk of a k extent that is not a multiple of BK: only the 4-column steps that hold data
+        if (warp >= split) issue();
+#pragma unroll 1
+        for (int ks = 0; ks < tail_ks; ks++) nn_kstep_rt<MB, NB, LDA, LDB>(acc, as, bs, ks);
       }
     }
     const int c0 = (int)(item % nct) * TN;
@@ -1296,7 +1327,7 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
   {                                                                                                     \
     auto kp = tall_nn_persist_kernel<32, 3, VA, VB>;                                                    \
     LB2_CUDA_OK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    kp<<<grid, 256, smem, ctx->stream>>>(S, lds, C, ldc, Out, ldo, n, kd, nfull * 128, nct, nitems, alpha, beta); \
+    kp<<<grid, 256, smem, ctx->stream>>>(S, lds, C, ldc, Out, ldo, n, kd, nfull * 128, nct, nitems, alpha, beta, ctx->nn_stagger ? 4 : 8); \
   }
         if (veca && vecb) LB2_NNP_LAUNCH(true, true)
         else if (veca) LB2_NNP_LAUNCH(true, false)

@@ -81,11 +81,11 @@ __host__ __device__ constexpr uint32_t wl_tri_b_mask() {
 }
 constexpr int WL_SHAPE_TRI_A = 32, WL_SHAPE_TRI_B = 33, WL_SHAPE_NONE = 34;
 
-template <uint32_t MASK, int BK, int LDS>
+template <uint32_t MASK, int KS0, int KS1, int LDS>
 __device__ __forceinline__ void wl_stage(double (&acc)[8][4][2], const double* __restrict__ as,
                                          const double* __restrict__ bs) {
 #pragma unroll
-  for (int ks = 0; ks < BK / 4; ks++) {
+  for (int ks = KS0; ks < KS1; ks++) {
     double a[8], b[4];
 #pragma unroll
     for (int i = 0; i < 8; i++)
@@ -101,16 +101,16 @@ __device__ __forceinline__ void wl_stage(double (&acc)[8][4][2], const double* _
   }
 }
 
-template <int BK, int LDS>
+template <int KS0, int KS1, int LDS>
 __device__ __forceinline__ void wl_stage_dispatch(int shape, double (&acc)[8][4][2], const double* __restrict__ as,
                                                   const double* __restrict__ bs) {
 #define WL_CASE(NA, NB) \
-  case ((NA - 1) * 4 + (NB - 1)): wl_stage<wl_rect_mask(NA, NB), BK, LDS>(acc, as, bs); break;
+  case ((NA - 1) * 4 + (NB - 1)): wl_stage<wl_rect_mask(NA, NB), KS0, KS1, LDS>(acc, as, bs); break;
 #define WL_ROW(NA) WL_CASE(NA, 1) WL_CASE(NA, 2) WL_CASE(NA, 3) WL_CASE(NA, 4)
   switch (shape) {
     WL_ROW(8) WL_ROW(7) WL_ROW(6) WL_ROW(5) WL_ROW(4) WL_ROW(3) WL_ROW(2) WL_ROW(1)
-    case WL_SHAPE_TRI_A: wl_stage<wl_tri_a_mask(), BK, LDS>(acc, as, bs); break;
-    case WL_SHAPE_TRI_B: wl_stage<wl_tri_b_mask(), BK, LDS>(acc, as, bs); break;
+    case WL_SHAPE_TRI_A: wl_stage<wl_tri_a_mask(), KS0, KS1, LDS>(acc, as, bs); break;
+    case WL_SHAPE_TRI_B: wl_stage<wl_tri_b_mask(), KS0, KS1, LDS>(acc, as, bs); break;
     default: break;
   }
 #undef WL_ROW
@@ -121,7 +121,8 @@ template <int BK, int STAGES, bool VEC>
 __global__ void __launch_bounds__(WL_NT, 1)
     gram_wl_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B0, int64_t ldb0,
                    const double* __restrict__ B1, int64_t ldb1, const WlItem* __restrict__ items,
-                   const int* __restrict__ cta_first, const WlWarp* __restrict__ layouts, double* __restrict__ part) {
+                   const int* __restrict__ cta_first, const WlWarp* __restrict__ layouts, double* __restrict__ part,
+                   int split) {
   constexpr int LDS = BK + 4;
   extern __shared__ __align__(16) double smem_wl[];
   double* As = smem_wl;
@@ -178,14 +179,25 @@ __global__ void __launch_bounds__(WL_NT, 1)
     const double* abase = (cfg.transposed ? Bp : As) + aoff;
     const double* bbase = (cfg.transposed ? As : Bp) + boff;
     int rstage = 0;
+    const bool late = warp >= split;
     for (int chunk = 0; chunk < nchunks; chunk++) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      issue();
+      // The copy instructions of a chunk keep a warp away from the DMMA pipe for several hundred clocks.  Of the two
+      // warps of a scheduler (w, w + 4) the first issues the copies of chunk + 2 right after the barrier, the second
+      // ("late") issues those of chunk + 1 just before it, i.e. after its MMAs of the previous chunk, so that one of the
+      // two always feeds the pipe.  Both orders write a stage that every warp left before the previous barrier.
+      if (!late) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+      }
+      if (!late || chunk > 0) issue();
+      if (late) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+      }
       const double* as = abase + rstage * (WL_T * LDS);
       const double* bs = bbase + rstage * (WL_T * LDS);
       rstage = (rstage + 1 == STAGES) ? 0 : rstage + 1;
-      wl_stage_dispatch<BK, LDS>(shape, acc, as, bs);
+      wl_stage_dispatch<0, BK / 4, LDS>(shape, acc, as, bs);
     }
     cp_async_wait<0>();
 
@@ -533,11 +545,13 @@ int launch_wl(lb2_ctx* ctx, const WlSchedule& S, int64_t n, int ma, int mb, cons
   if (vec) {
     auto k = gram_wl_kernel<BK, STAGES, true>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, B, ldb, S.items, S.cta_first, S.layouts, part);
+    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, B, ldb, S.items, S.cta_first, S.layouts, part,
+                                            ctx->nn_stagger ? 4 : 8);
   } else {
     auto k = gram_wl_kernel<BK, STAGES, false>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, B, ldb, S.items, S.cta_first, S.layouts, part);
+    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, B, ldb, S.items, S.cta_first, S.layouts, part,
+                                            ctx->nn_stagger ? 4 : 8);
   }
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
@@ -613,12 +627,12 @@ int launch_wl_cols(lb2_ctx* ctx, const WlColsSchedule& S, const double* A, int64
     auto k = gram_wl_kernel<BK, STAGES, true>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<S.base.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B0, ldb0, B1, ldb1, S.base.items, S.base.cta_first,
-                                                  S.base.layouts, part);
+                                                  S.base.layouts, part, ctx->nn_stagger ? 4 : 8);
   } else {
     auto k = gram_wl_kernel<BK, STAGES, false>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<S.base.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B0, ldb0, B1, ldb1, S.base.items, S.base.cta_first,
-                                                  S.base.layouts, part);
+                                                  S.base.layouts, part, ctx->nn_stagger ? 4 : 8);
   }
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
