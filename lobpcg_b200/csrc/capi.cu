@@ -277,6 +277,10 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "gram_strip_fma")) c->gram_strip_fma = value;
   else if (!strcmp(key, "spmm_cols")) c->spmm_cols = value;
   else if (!strcmp(key, "csr_window")) c->csr_window = value;
+  else if (!strcmp(key, "csr_staged")) c->csr_staged = value;
+  else if (!strcmp(key, "csr_order")) c->csr_order = value;
+  else if (!strcmp(key, "csr_pipe")) c->csr_pipe = value;
+  else if (!strcmp(key, "csr_lpr")) c->csr_lpr = value;
   else return -1;
   return 0;
 }

@@ -44,6 +44,10 @@ struct lb2_ctx {
   int gram_tma = -1;     // float Gram: TMA-fed tcgen05 kernel (gram_tc5.cu: gram_tc5_tma_kernel): -1 / 1 = on, 0 = cp.async-fed kernel
   int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
   int spmm_cols = 0;     // CSR SpMM columns per thread (0 = heuristic)
+  int csr_order = 512;   // plain CSR kernel: row blocks per chunk of the chunked 1-D launch order (spmm.cu: csr_kernel), 0 = column-group-major 2-D grid
+  int csr_pipe = 1;      // plain CSR kernel: 1 = next (col, val) pair requested ahead of the current gathers, 2 = two couplings per step, 0 = plain loop
+  int csr_staged = 0;    // 1: CSR kernel with the (col, val) stream staged in shared memory (r02: 1.71 ms against 1.37 ms of the plain kernel at 128^3 x 128)
+  int csr_lpr = 0;       // lanes per row of the staged CSR kernel: 0 = from the mean row length, else 1 / 4 / 16
   int csr_window = -1;   // windowed CSR kernel for banded matrices: 1 = on; -1 / 0 = off (r02: 2.09 ms against 1.38 ms of the plain kernel at 128^3 x 128)
   // one released solver arena kept for the next solve on this context (arena_alloc / arena_release in capi.cu): a 100 GB
   // cudaMalloc + cudaFree pair costs 0.1-0.5 s per reference-facing call; LB2_ARENA_CACHE=0 disables, lb2_ctx_trim frees

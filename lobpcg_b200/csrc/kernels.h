@@ -123,7 +123,7 @@ struct CsrHalo {
 };
 template <typename T>
 int spmm_csr(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val, int nc,
-             const T* X, int64_t ldx, T* Y, int64_t ldy, const CsrHalo* halo = nullptr);
+             const T* X, int64_t ldx, T* Y, int64_t ldy, const CsrHalo* halo = nullptr, int64_t nnz = -1);
 // CSR with a shared-memory window of X around the diagonal (spmm.cu: csr_win_kernel); H = half-width in rows (<= 256)
 template <typename T>
 int spmm_csr_window(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val, int nc,

@@ -82,13 +82,13 @@ int apply_builtin(lb2_ctx* ctx, const BuiltinOp* b, int nc, const T* X, int64_t 
       if (b->n != b->n_global) {   // row block of a partitioned matrix: neighbour blocks set by Solver::localize
         CsrHalo h;
         h.lo = b->halo_lo; h.hi = b->halo_hi; h.ld_lo = h.ld_hi = b->halo_ld;
-        return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy, &h);
+        return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy, &h, b->nnz);
       }
       if (b->csr_halo >= 2 && ctx->csr_window > 0) {   // banded matrix: shared-memory X window (spmm.cu: csr_win_kernel), opt-in — measured slower than the plain kernel
         const int rc = spmm_csr_window<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy, b->csr_halo);
         if (rc != -100) return rc;
       }
-      return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy);
+      return spmm_csr<T>(ctx, b->n, b->rowptr, b->col, (const T*)b->val, nc, X, ldx, Y, ldy, nullptr, b->nnz);
     case OP_DIAG:
       return spmm_diag<T>(ctx, b->n, (const real_t<T>*)b->diag, nc, X, ldx, Y, ldy);
     case OP_DENSE:   // plain library GEMM (cuBLAS): Y = A X with A dense n x n

@@ -289,29 +289,59 @@ int spmm_stencil_cheb(lb2_ctx* ctx, const StencilDesc& d, int nc, const T* Din, 
 // threads own consecutive rows, so for banded matrices the gathers X[col, c] are coalesced across the warp
 // and the (col,val) stream of a warp is one contiguous range.  grid.x = row blocks (fast), grid.y = column
 // groups, so concurrently resident CTAs share a small column window of X in L2.
-// Measured 2.9-3.1 TB/s (45-48 % of HBM peak) on the 128^3 7-point matrix: every output gathers 7 X values and only
-// the +-1 neighbours are served by L1, so the kernel is bound by L2 sector bandwidth (~5 sector reads per output),
-// not by the (col,val) stream — a shared-memory staged variant of the matrix stream measured no faster.  Getting
-// past this needs a 3-D blocked row order.  Matrices that ARE Dirichlet stencils never get here (capi.cu: detect_stencil).
+// Round-2 sweep on the 128^3 7-point matrix x 128 columns (profiles/kernel_bench_csr_r02.jsonl; algorithmic bytes
+// nnz (s + 4) + 8 (n + 1) + 2 n nc s): plain loop, 16 columns per thread 1.29 ms = 53 % of HBM; the pipelined loop
+// (next (col, val) pair requested ahead of the current gathers) with 8 columns per thread in the chunked launch order
+// 1.17 ms = 59 % (default).  What did NOT help, each measured: staging the matrix stream in shared memory
+// (csr_staged_kernel, 1.71 ms), a row-block-major launch order (1.71 ms: short runs scattered over all columns of X,
+// poor DRAM page locality), a 2 x 4 / 4 x 2 blocked row order that puts the +-gx / +-gx*gy neighbours into the same CTA
+// (1.9 ms, same reason), two couplings per step (2.0-2.4 ms) and the pipelined loop with 16 columns (1.97 ms): more
+// gathers in flight evict the lines the +-1 / +-gx neighbours would have hit in L1.  Every output gathers 7 X values of
+// which L1 serves the +-1 neighbours only, so ~4x the bytes of X cross the L2 -> L1 path; removing the 1.2 GB of
+// matrix re-reads (chunked order) changed nothing by itself.  Getting past ~60 % needs explicit reuse of X (the stencil
+// kernel's plane ring), i.e. structure the CSR arrays do not carry.  Matrices that ARE Dirichlet stencils never get
+// here (capi.cu: detect_stencil).
 // =====================================================================================================
 // HALO (row-partitioned matrix): column indices are relative to the first local row; an index below 0 is
 // row (index + n_lo) of the lower neighbour's block, an index >= n is row (index - n) of the upper neighbour's block, and
 // both are read in place from the neighbour's arena over NVLink (same idea as the stencil's halo planes: no exchange
 // pass, no gathered copy).
-template <typename T, int NCOL, int RPT, bool HALO>
+struct CsrMap {
+  int ch = 0;        // != 0: 1-D grid, chunked order with ch row blocks per chunk
+  int ncg = 0;       // column groups
+  int64_t nrb = 0;   // row blocks
+};
+
+template <typename T, int NCOL, int RPT, bool HALO, int PIPE>
 __global__ void __launch_bounds__(256)
     csr_kernel(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                const T* __restrict__ val, int nc, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y,
-               int64_t ldy, CsrHalo halo) {
+               int64_t ldy, CsrHalo halo, CsrMap map) {
   // a CTA owns 256 * RPT consecutive rows (thread t: rows base + t + 256 i).  RPT > 1 was measured (r01: 1/2/4/8 rows per
   // thread x 4/8/16/32 columns, 128^3 7-point matrix): no effect, the kernel stays at ~49 % of HBM with 8 or 16 columns
   // per thread — it is bound by L2 sector reads (5 gathered lines per output), not by L1 reuse inside the CTA.
-  const int c0 = blockIdx.y * NCOL;
+  // map.ch != 0: 1-D grid in CHUNKED order — ch consecutive row blocks for column group 0, the same ch row blocks for
+  // column group 1, ... then the next ch row blocks.  A chunk's slice of the (col, val) stream (ch * 256 rows) then stays
+  // in L2 while the column groups take their turns (the 2-D column-group-major grid re-reads the whole matrix once per
+  // group: 1.4 GB of its 3.7 GB of DRAM reads at 128^3 x 128), while the CTAs that run together still read long
+  // contiguous runs of the same few columns of X (a row-block-major order, one row block for all column groups, measured
+  // 25 % SLOWER than the 2-D grid: short runs scattered over all columns, poor DRAM page locality).
+  int cg = blockIdx.y;
+  int64_t blk = blockIdx.x;
+  if (map.ch) {
+    const int64_t per_chunk = (int64_t)map.ch * map.ncg;
+    const int64_t chunk = blockIdx.x / per_chunk, in = blockIdx.x % per_chunk;
+    const int64_t left = map.nrb - chunk * map.ch;              // row blocks in this (possibly last, shorter) chunk
+    const int chn = (int)min((int64_t)map.ch, left);
+    cg = (int)(in / chn);
+    blk = chunk * map.ch + in % chn;
+  }
+  const int c0 = cg * NCOL;
   const int ncol = min(NCOL, nc - c0);
   const T* xb = X + (int64_t)c0 * ldx;
 #pragma unroll 1
   for (int i = 0; i < RPT; i++) {
-    const int64_t row = ((int64_t)blockIdx.x * RPT + i) * 256 + threadIdx.x;
+    const int64_t row = (blk * RPT + i) * 256 + threadIdx.x;
     if (row >= n) return;
     T acc[NCOL];
 #pragma unroll
@@ -328,6 +358,52 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int c = 0; c < NCOL; c++)
           if (c < ncol) fma_(acc[c], v, src[(int64_t)c * ld]);
+      }
+    } else if (ncol == NCOL && PIPE == 1) {
+      // software pipeline: the (col, val) pair of the NEXT coupling is requested before the gathers of the current one,
+      // so a row costs one memory latency per coupling instead of two dependent ones (col[p] -> X[col[p], :])
+      int64_t p = p0;
+      int32_t cn = 0;
+      T vn = zero<T>();
+      if (p < p1) { cn = col[p]; vn = val[p]; }
+      while (p < p1) {
+        const int64_t cj = cn;
+        const T v = vn;
+        ++p;
+        if (p < p1) { cn = col[p]; vn = val[p]; }
+        T x[NCOL];
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) x[c] = xb[cj + (int64_t)c * ldx];
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) fma_(acc[c], v, x[c]);
+      }
+    } else if (ncol == NCOL && PIPE == 2) {
+      // two couplings per step (2 x NCOL gathers in flight per thread), the next pair requested ahead of them
+      int64_t p = p0;
+      int32_t ca = 0, cb = 0;
+      T va = zero<T>(), vb = zero<T>();
+      if (p < p1) { ca = col[p]; va = val[p]; }
+      if (p + 1 < p1) { cb = col[p + 1]; vb = val[p + 1]; }
+      while (p < p1) {
+        const int64_t a = ca, b = cb;
+        const T wa = va, wb = vb;
+        const bool two = p + 1 < p1;
+        p += 2;
+        if (p < p1) { ca = col[p]; va = val[p]; }
+        if (p + 1 < p1) { cb = col[p + 1]; vb = val[p + 1]; }
+        T x[NCOL], y[NCOL];
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) x[c] = xb[a + (int64_t)c * ldx];
+        if (two) {
+#pragma unroll
+          for (int c = 0; c < NCOL; c++) y[c] = xb[b + (int64_t)c * ldx];
+        }
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) fma_(acc[c], wa, x[c]);
+        if (two) {
+#pragma unroll
+          for (int c = 0; c < NCOL; c++) fma_(acc[c], wb, y[c]);
+        }
       }
     } else if (ncol == NCOL) {
       for (int64_t p = p0; p < p1; p++) {
@@ -422,6 +498,136 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// =====================================================================================================
+// CSR with the matrix stream staged in shared memory (default general kernel).
+// A CTA owns RB = 256 / LPR consecutive rows and NCOL columns of the block vector.  The (col, val) entries of those rows
+// are ONE contiguous range of the CSR arrays: the CTA copies it to shared memory with 16-byte cp.async (fully coalesced,
+// every copy in flight at once), and only then walks its rows.  That removes the dependent global-load chain of the plain
+// kernel (col[p] -> X[col[p], :]: two DRAM/L2 latencies per nonzero with nothing else in flight, ncu: long_scoreboard
+// 21 warps per issue at 52 % of DRAM throughput) — the gathers of several nonzeros are issued back to back — and the row
+// walk reads the indices at shared-memory latency.  blockIdx.x = row block * ncg + column group: the CTAs of a row block
+// run together, so the matrix stream comes from DRAM once and from L2 for the other column groups (the plain kernel's
+// column-group-major grid re-read it nc / NCOL times: 1.4 GB of its 3.7 GB of DRAM reads at 128^3 x 128), and the rows
+// X[r +- bandwidth] that later row blocks need again stay in L2 for all columns (2 * bandwidth * nc * s bytes).
+// LPR lanes share a row (rows with many couplings): lane l takes entries l, l + LPR, ... and the partial sums are
+// combined with shuffles.  Rows longer than the staging buffer are handled by walking the range in several passes.
+// =====================================================================================================
+constexpr int CSRS_CAP = 4096;   // staged entries per pass
+
+template <typename R>
+__device__ __forceinline__ R shfl_xor_(R v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+template <typename R>
+__device__ __forceinline__ Cx<R> shfl_xor_(Cx<R> v, int o) {
+  return Cx<R>{__shfl_xor_sync(0xffffffffu, v.re, o), __shfl_xor_sync(0xffffffffu, v.im, o)};
+}
+
+template <typename T, int NCOL, int LPR, bool HALO>
+__global__ void __launch_bounds__(256)
+    csr_staged_kernel(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                      const T* __restrict__ val, int64_t nnz, int nc, const T* __restrict__ X, int64_t ldx,
+                      T* __restrict__ Y, int64_t ldy, CsrHalo halo, int ncg) {
+  constexpr int RB = 256 / LPR;
+  constexpr int VPU = 16 / (int)sizeof(T);   // values per 16-byte copy
+  extern __shared__ __align__(16) unsigned char csrs_smem[];
+  T* sval = reinterpret_cast<T*>(csrs_smem);
+  int32_t* scol = reinterpret_cast<int32_t*>(sval + CSRS_CAP);
+  const int cg = blockIdx.x % ncg;
+  const int64_t r0 = (int64_t)(blockIdx.x / ncg) * RB;
+  const int c0 = cg * NCOL;
+  const int ncol = min(NCOL, nc - c0);
+  const int sub = threadIdx.x % LPR;
+  const int64_t row = r0 + threadIdx.x / LPR;
+  int64_t p0 = 0, p1 = 0;
+  if (row < n) { p0 = rowptr[row]; p1 = rowptr[row + 1]; }
+  const int64_t pb = rowptr[r0] & ~(int64_t)3;      // 16-byte aligned start of the copies
+  const int64_t pe = rowptr[min(r0 + RB, n)];
+  const T* xb = X + (int64_t)c0 * ldx;
+  T acc[NCOL];
+#pragma unroll
+  for (int c = 0; c < NCOL; c++) acc[c] = zero<T>();
+  for (int64_t cb = pb; cb < pe; cb += CSRS_CAP) {
+    const int cnt = (int)min((int64_t)CSRS_CAP, pe - cb);
+    if (cb != pb) __syncthreads();   // every lane is done with the previous pass
+    for (int u = threadIdx.x; u * 4 < cnt; u += 256) {
+      const int64_t left = nnz - (cb + 4 * u);
+      cp_async_zfill<16>(scol + 4 * u, col + cb + 4 * u, left >= 4 ? 16 : (int)left * 4);
+    }
+    for (int u = threadIdx.x; u * VPU < cnt; u += 256) {
+      const int64_t left = nnz - (cb + VPU * u);
+      cp_async_zfill<16>(sval + VPU * u, val + cb + VPU * u, left >= VPU ? 16 : (int)left * (int)sizeof(T));
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int lo = (int)(max(p0, cb) - cb) + sub;
+    const int hi = (int)(min(p1, cb + cnt) - cb);
+    if constexpr (HALO) {
+      const T* xlo = (const T*)halo.lo + (int64_t)c0 * halo.ld_lo + halo.ld_lo;   // row -1 of the local block = last row below
+      const T* xhi = (const T*)halo.hi + (int64_t)c0 * halo.ld_hi - n;
+      for (int q = lo; q < hi; q += LPR) {
+        const int64_t cj = scol[q];
+        const T v = sval[q];
+        const T* src = cj < 0 ? xlo + cj : (cj >= n ? xhi + cj : xb + cj);
+        const int64_t ld = cj < 0 ? halo.ld_lo : (cj >= n ? halo.ld_hi : ldx);
+#pragma unroll
+        for (int c = 0; c < NCOL; c++)
+          if (c < ncol) fma_(acc[c], v, src[(int64_t)c * ld]);
+      }
+    } else if (ncol == NCOL) {
+#pragma unroll 4
+      for (int q = lo; q < hi; q += LPR) {
+        const T* src = xb + scol[q];
+        const T v = sval[q];
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) fma_(acc[c], v, src[(int64_t)c * ldx]);
+      }
+    } else {
+      for (int q = lo; q < hi; q += LPR) {
+        const T* src = xb + scol[q];
+        const T v = sval[q];
+#pragma unroll
+        for (int c = 0; c < NCOL; c++)
+          if (c < ncol) fma_(acc[c], v, src[(int64_t)c * ldx]);
+      }
+    }
+  }
+  if constexpr (LPR > 1) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int c = 0; c < NCOL; c++) acc[c] = add_(acc[c], shfl_xor_(acc[c], o));
+  }
+  if (row < n && sub == 0) {
+    T* yb = Y + (int64_t)c0 * ldy + row;
+#pragma unroll
+    for (int c = 0; c < NCOL; c++)
+      if (c < ncol) yb[(int64_t)c * ldy] = acc[c];
+  }
+}
+
+template <typename T, int NCOL, int LPR>
+static int launch_csr_staged(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val,
+                             int64_t nnz, int nc, const T* X, int64_t ldx, T* Y, int64_t ldy, const CsrHalo* halo) {
+  constexpr int RB = 256 / LPR;
+  const int ncg = (nc + NCOL - 1) / NCOL;
+  const int64_t nrb = (n + RB - 1) / RB;
+  if (nrb * ncg > 0x7fffffffLL) return -100;
+  constexpr size_t smem = (sizeof(T) + sizeof(int32_t)) * (size_t)CSRS_CAP;
+  const CsrHalo h = halo ? *halo : CsrHalo{};
+  if (halo) {
+    auto k = csr_staged_kernel<T, NCOL, LPR, true>;
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)(nrb * ncg), 256, smem, ctx->stream>>>(n, rowptr, col, val, nnz, nc, X, ldx, Y, ldy, h, ncg);
+  } else {
+    auto k = csr_staged_kernel<T, NCOL, LPR, false>;
+    LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)(nrb * ncg), 256, smem, ctx->stream>>>(n, rowptr, col, val, nnz, nc, X, ldx, Y, ldy, h, ncg);
+  }
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 template <typename T>
 int spmm_csr_window(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val, int nc,
                     const T* X, int64_t ldx, T* Y, int64_t ldy, int H) {
@@ -441,17 +647,42 @@ int spmm_csr_window(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_
 
 template <typename T>
 int spmm_csr(lb2_ctx* ctx, int64_t n, const int64_t* rowptr, const int32_t* col, const T* val, int nc,
-             const T* X, int64_t ldx, T* Y, int64_t ldy, const CsrHalo* halo) {
+             const T* X, int64_t ldx, T* Y, int64_t ldy, const CsrHalo* halo, int64_t nnz) {
   if (n <= 0 || nc <= 0) return 0;
-  int ncol = ctx->spmm_cols ? ctx->spmm_cols : 16;
+  // 64 bytes of a block-vector row per thread (8 doubles) with the pipelined loop: r02 sweep at 128^3 x 128, f64 — plain loop
+  // 16 columns 1.29 ms, pipelined 16 columns 1.97 ms (more gathers in flight thrash L1), pipelined 8 columns 1.17 ms
+  int ncol = ctx->spmm_cols ? ctx->spmm_cols : (ctx->csr_pipe == 1 ? 64 / (int)sizeof(T) : 16);
+  if (nnz >= 0 && ctx->csr_staged > 0 && (uintptr_t)col % 16 == 0 && (uintptr_t)val % 16 == 0) {
+    // staged kernel: lanes per row from the mean row length (1 for stencil-like rows, 4 / 16 for FEM-like and denser rows)
+    const double mean = (double)nnz / (double)n;
+    const int lpr = ctx->csr_lpr > 0 ? ctx->csr_lpr : (mean <= 12.0 ? 1 : (mean <= 48.0 ? 4 : 16));
+    constexpr int NC = sizeof(T) >= 16 ? 4 : 8;
+    constexpr int NCW = sizeof(T) >= 16 ? 8 : 16;
+    int rc;
+    if (lpr >= 16) rc = launch_csr_staged<T, NC, 16>(ctx, n, rowptr, col, val, nnz, nc, X, ldx, Y, ldy, halo);
+    else if (lpr >= 4) rc = launch_csr_staged<T, NC, 4>(ctx, n, rowptr, col, val, nnz, nc, X, ldx, Y, ldy, halo);
+    else if (ncol <= 8 || nc <= NC) rc = launch_csr_staged<T, NC, 1>(ctx, n, rowptr, col, val, nnz, nc, X, ldx, Y, ldy, halo);
+    else rc = launch_csr_staged<T, NCW, 1>(ctx, n, rowptr, col, val, nnz, nc, X, ldx, Y, ldy, halo);
+    if (rc != -100) return rc;
+  }
   const CsrHalo h = halo ? *halo : CsrHalo{};
+  CsrMap map{};
 #define LB2_CSR2(NC, RP)                                                                                        \
   do {                                                                                                          \
-    const dim3 grid((unsigned)((n + 256 * RP - 1) / (256 * RP)), (nc + NC - 1) / NC);                           \
+    const int64_t nrb = (n + 256 * RP - 1) / (256 * RP);                                                        \
+    const int ncg = (nc + NC - 1) / NC;                                                                         \
+    dim3 grid((unsigned)nrb, ncg);                                                                              \
+    if (ctx->csr_order > 0 && ncg > 1 && nrb * ncg <= 0x7fffffffLL) {                                           \
+      map.ch = ctx->csr_order; map.ncg = ncg; map.nrb = nrb; grid = dim3((unsigned)(nrb * ncg));                \
+    }                                                                                                           \
     if (halo)                                                                                                   \
-      csr_kernel<T, NC, RP, true><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, nc, X, ldx, Y, ldy, h);   \
+      csr_kernel<T, NC, RP, true, 0><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, nc, X, ldx, Y, ldy, h, map);   \
+    else if (ctx->csr_pipe == 1)                                                                                \
+      csr_kernel<T, NC, RP, false, 1><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, nc, X, ldx, Y, ldy, h, map);  \
+    else if (ctx->csr_pipe == 2)                                                                                \
+      csr_kernel<T, NC, RP, false, 2><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, nc, X, ldx, Y, ldy, h, map);  \
     else                                                                                                        \
-      csr_kernel<T, NC, RP, false><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, nc, X, ldx, Y, ldy, h);  \
+      csr_kernel<T, NC, RP, false, 0><<<grid, 256, 0, ctx->stream>>>(n, rowptr, col, val, nc, X, ldx, Y, ldy, h, map);  \
   } while (0)
 #define LB2_CSR(NC) LB2_CSR2(NC, 1)
   if (nc <= 4 || ncol <= 4) LB2_CSR(4);
@@ -493,7 +724,7 @@ int spmm_diag(lb2_ctx* ctx, int64_t n, const real_t<T>* d, int nc, const T* X, i
 #define LB2_INST(T)                                                                                       \
   template int spmm_stencil<T>(lb2_ctx*, const StencilDesc&, int, const T*, int64_t, T*, int64_t);         \
   template int spmm_stencil_cheb<T>(lb2_ctx*, const StencilDesc&, int, const T*, int64_t, T*, int64_t, const ChebEpilogue<T>&); \
-  template int spmm_csr<T>(lb2_ctx*, int64_t, const int64_t*, const int32_t*, const T*, int, const T*, int64_t, T*, int64_t, const CsrHalo*); \
+  template int spmm_csr<T>(lb2_ctx*, int64_t, const int64_t*, const int32_t*, const T*, int, const T*, int64_t, T*, int64_t, const CsrHalo*, int64_t); \
   template int spmm_csr_window<T>(lb2_ctx*, int64_t, const int64_t*, const int32_t*, const T*, int, const T*, int64_t, T*, int64_t, int); \
   template int spmm_diag<T>(lb2_ctx*, int64_t, const real_t<T>*, int, const T*, int64_t, T*, int64_t);
 LB2_INST(float)

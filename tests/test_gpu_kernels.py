@@ -608,6 +608,62 @@ def test_csr_window_kernel_matches_scipy(ctx, dt, case):
     close(got, ref, rtol(dt) * 10)
 
 
+# ------------------------------------------------------------------------------------------------ staged CSR kernel
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", [(3001, 7, 9, "band"), (20000, 30, 17, "rand"), (6000, 90, 5, "rand"), (6000, 3, 6, "long"),
+                                  (1500, 5, 3, "empty")])
+def test_csr_kernels_match_scipy(ctx, dt, case):
+    """General CSR kernels: csr_kernel in its chunked 1-D launch order (default) and on the 2-D grid, and csr_staged_kernel
+    (opt-in: the (col, val) range of a row block staged in shared memory, 1 / 4 / 16 lanes per row).  Banded and random
+    sparsity, mean row lengths that select every lanes-per-row variant, rows longer than the staging buffer (several
+    passes), empty rows and an empty tail, ragged row blocks, ragged last chunk, column-group tails, all four types."""
+    import scipy.sparse as sp
+    n, per_row, nc, kind = case
+    rng = np.random.default_rng(n + per_row)
+    if kind == "band":
+        rows, cols = [], []
+        for d in (0, 1, -1, 40, -40, 777, -777):
+            i = np.arange(max(0, -d), min(n, n - d))
+            rows.append(i); cols.append(i + d)
+        r, c = np.concatenate(rows), np.concatenate(cols)
+    else:
+        r = rng.integers(0, n, per_row * n); c = rng.integers(0, n, per_row * n)
+        if kind == "long":        # three rows with more entries than the staging buffer holds (4096), next to short ones
+            for row in (0, 350, n - 1):
+                r = np.concatenate([r, np.full(n, row)]); c = np.concatenate([c, np.arange(n)])
+            r = np.concatenate([r] + [np.full(5000, 351)]); c = np.concatenate([c, rng.integers(0, n, 5000)])
+        if kind == "empty":
+            keep = (r % 7 != 3) & (r < n - 300)      # empty rows inside and an empty tail of 300 rows
+            r, c = r[keep], c[keep]
+    vals = rng.standard_normal(len(r)) + (1j * rng.standard_normal(len(r)) if np.dtype(dt).kind == "c" else 0)
+    M = sp.csr_matrix((vals.astype(dt), (r, c)), shape=(n, n))
+    M.sum_duplicates(); M.sort_indices()
+    X = rand(rng, (n, nc), dt)
+    ref = np.asarray(M @ X)
+    dX = api.DeviceArray.from_numpy(ctx, X)
+    op = api.csr_op(M.indptr, M.indices, M.data)
+    tol = rtol(dt) * (400 if kind == "long" else 10)
+    close(op.apply(ctx, dX).numpy(ctx), ref, tol)          # default: plain kernel, chunked launch order
+    try:
+        for order in (0, 1, 3):                             # 2-D grid, and chunks of 1 / 3 row blocks (ragged last chunk)
+            ctx.set_option("csr_order", order)
+            close(op.apply(ctx, dX).numpy(ctx), ref, tol)
+        ctx.set_option("csr_order", 512)
+        for pipe in (0, 2):                                 # plain loop and two couplings per step (default 1: next pair ahead)
+            ctx.set_option("csr_pipe", pipe)
+            close(op.apply(ctx, dX).numpy(ctx), ref, tol)
+        ctx.set_option("csr_pipe", 1)
+        ctx.set_option("csr_staged", 1)
+        for lpr in (1, 4, 16):
+            ctx.set_option("csr_lpr", lpr)
+            close(op.apply(ctx, dX).numpy(ctx), ref, tol)
+        ctx.set_option("csr_lpr", 0)
+        ctx.set_option("spmm_cols", 8)
+        close(op.apply(ctx, dX).numpy(ctx), ref, tol)
+    finally:
+        ctx.set_option("csr_lpr", 0); ctx.set_option("spmm_cols", 0); ctx.set_option("csr_staged", 0); ctx.set_option("csr_order", 512); ctx.set_option("csr_pipe", 1)
+
+
 # ------------------------------------------------------------------------------------------------ TMA-fed f32 Gram
 @pytest.mark.parametrize("shape", [(4099, 20, 20), (30001, 64, 33), (20000, 150, 129), (65536, 256, 256), (100000, 300, 100),
                                    (8193, 260, 7)])
