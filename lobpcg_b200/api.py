@@ -238,6 +238,16 @@ class DeviceArray:
         v._owner = self
         return v
 
+    def cols(self, col0: int, ncols: int) -> "DeviceArray":
+        """Non-owning view of columns [col0, col0+ncols) (same leading dimension)."""
+        v = object.__new__(DeviceArray)
+        v.shape = (self.shape[0], int(ncols))
+        v.dtype, v.ld = self.dtype, self.ld
+        v.ptr = self.ptr + int(col0) * self.ld * self.dtype.itemsize
+        v.nbytes = 0
+        v._owner = self
+        return v
+
     def zero(self, ctx: Context):
         _ck(lib().lb2_memset(ctx.h, self.ptr, 0, self.nbytes), "memset")
 

@@ -18,7 +18,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "_lib"
 LIB = OUT / "liblobpcg_b200.so"
-SOURCES = ["dense.cu", "gram_wl.cu", "gram_tc5.cu", "nn_tc5.cu", "hostcopy.cu", "elementwise.cu", "spmm.cu", "smalldense.cu", "solver.cu", "capi.cu", "comm.cu", "multigpu.cu"]
+SOURCES = ["dense.cu", "gram_wl.cu", "gram_tc5.cu", "gram_i8.cu", "nn_tc5.cu", "hostcopy.cu", "elementwise.cu", "spmm.cu", "smalldense.cu", "solver.cu", "capi.cu", "comm.cu", "multigpu.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr",

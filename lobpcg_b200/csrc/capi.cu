@@ -246,6 +246,7 @@ void lb2_ctx_destroy(lb2_ctx* c) {
   lb2::gram_wl_cache_free(c);
   lb2::hostcopy_free(c);
   if (c->ws) cudaFree(c->ws);
+  if (c->oz_buf) cudaFree(c->oz_buf);
   if (c->solver_ws) cudaFree(c->solver_ws);
   if (c->solver_hws) free(c->solver_hws);
   if (c->dev_info) cudaFree(c->dev_info);
@@ -270,6 +271,8 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "gram_wl")) c->gram_wl = value;
   else if (!strcmp(key, "gram_bk")) c->gram_bk = value;
   else if (!strcmp(key, "gram_tc5")) c->gram_tc5 = value;
+  else if (!strcmp(key, "gram_i8")) c->gram_i8 = value;
+  else if (!strcmp(key, "oz_load_pct")) c->oz_load_pct = value;
   else if (!strcmp(key, "gram_tma")) c->gram_tma = value;
   else if (!strcmp(key, "gram_load_pct")) c->gram_load_pct = value;
   else if (!strcmp(key, "gram_phase")) c->gram_phase = value;

@@ -16,6 +16,9 @@ struct lb2_ctx {
   // scratch for deterministic split-n partial sums (Gram) and per-CTA norm partials
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  // int8 slices, exponents and partial sums of the Ozaki-split f64 Gram (gram_i8.cu); sized exactly, kept between calls
+  void* oz_buf = nullptr;
+  size_t oz_bytes = 0;
   // small-dense library handles (created lazily)
   cublasHandle_t cublas = nullptr;
   cusolverDnHandle_t cusolver = nullptr;
@@ -40,6 +43,9 @@ struct lb2_ctx {
   void* hostcopy = nullptr;        // lb2::HostCopyState* (pinned ring for pageable host <-> device block transfers)
   void* gram_wl_cache = nullptr;   // lb2::WlCache* (schedules per Gram shape)
   void* gram_wl_cols_cache = nullptr;   // lb2::WlColsCache* (schedules of the column-block products, gram_wl_cols_f64)
+  int gram_i8 = 0;       // f64 Gram through tcgen05 kind::i8 on an Ozaki split (gram_i8.cu): 1 = on, 0 = DMMA kernels (default)
+  int gram_i8_env = -1;  // LB2_GRAM_I8 as seen by the last solver set-up (-1 = unset); overrides gram_i8 for the drop-in entry points
+  int oz_load_pct = 0;   // gram_i8 schedule: cost of one 16 KB slice-tile load relative to one full-width slice product, in % (0 = 100)
   int gram_tc5 = -1;     // float Gram through tcgen05 / TMEM (gram_tc5.cu): -1 = auto (on), 0 = off, 1 = on
   int gram_tma = -1;     // float Gram: TMA-fed tcgen05 kernel (gram_tc5.cu: gram_tc5_tma_kernel): -1 / 1 = on, 0 = cp.async-fed kernel
   int force_simt = 0;    // 1 = use the generic SIMT kernels even for f64 (testing)
@@ -79,3 +85,6 @@ int host_copy_2d(lb2_ctx* ctx, void* dev, size_t ld_dev_bytes, void* host, size_
                  bool to_device);
 void hostcopy_set_threads(lb2_ctx* ctx, int nthreads);
 }  // namespace lb2
+
+// effective setting of the int8 Gram path (environment for the reference entry points, else the context option)
+inline int lb2_gram_i8_mode(const lb2_ctx* c) { return c->gram_i8_env >= 0 ? c->gram_i8_env : c->gram_i8; }

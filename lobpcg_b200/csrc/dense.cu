@@ -1240,6 +1240,10 @@ int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const
   }
   if constexpr (std::is_same<T, double>::value) {
     if (!ctx->force_simt) {
+      if (lb2_gram_i8_mode(ctx) > 0 && n >= 4096) {   // tcgen05 kind::i8 on an Ozaki split (gram_i8.cu), opt-in
+        const int rc = gram_i8_f64(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
+        if (rc != -100) return rc;
+      }
       // work-list kernel (gram_wl.cu) for Hermitian products; forced for every shape with gram_wl = 1
       if (ctx->gram_wl == 1 || (ctx->gram_wl < 0 && ctx->gram_tile == 0 && upper && n >= 4096))
         return gram_wl_f64(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
@@ -1270,6 +1274,10 @@ int gram_cols(lb2_ctx* ctx, int64_t n, int m, int nw, const T* S, int64_t lds, c
               int ldg0, const T* W1, int64_t ldw1, T* G1, int ldg1, int tri_c0) {
   if (m <= 0 || nw <= 0) return 0;
   if constexpr (std::is_same<T, double>::value) {
+    if (!ctx->force_simt && lb2_gram_i8_mode(ctx) > 0 && n >= 4096) {   // tcgen05 kind::i8 on an Ozaki split (gram_i8.cu), opt-in
+      const int rc = gram_cols_i8_f64(ctx, n, m, nw, S, lds, W0, ldw0, G0, ldg0, W1, ldw1, G1, ldg1, tri_c0);
+      if (rc != -100) return rc;
+    }
     if (!ctx->force_simt && ctx->gram_wl != 0 && ctx->gram_tile == 0 && n >= 4096)
       return gram_wl_cols_f64(ctx, n, m, nw, S, lds, W0, ldw0, G0, ldg0, W1, ldw1, G1, ldg1, tri_c0);
   }

@@ -1,0 +1,667 @@
+// lobpcg_b200/csrc/gram_i8.cu — f64 Gram products on the 5th-generation tensor cores through an Ozaki-style split
+// (option gram_i8; the DMMA work-list kernel of gram_wl.cu stays the default).
+//
+// tcgen05.mma has no f64 kind: FP64 runs on mma.sync DMMA at 37 TFLOP/s, the hard ceiling of gram_wl.cu / dense.cu.  The only
+// Blackwell-native way past it is integer arithmetic: tcgen05.mma kind::i8 (SASS UTCIMMA) multiplies signed bytes EXACTLY
+// into 32-bit integer accumulators in TMEM.  A product G = A^H B (contraction over the n rows) becomes
+//
+//   A[r, a] = 2^(eA[a] - 55) * N_A[r, a],  N = rint(x * 2^(55 - e)),  |N| < 2^54      (e from the column's largest entry)
+//   N = sum_i d_i 256^i,  i = 0..6,  d_i in [-128, 127]                               (balanced base-256 digits = 7 int8 "slices")
+//   G[a, b] = 2^(eA[a] + eB[b] - 110) * sum_L 256^L * sum_{i + j = L} sum_r dA_i[r, a] dB_j[r, b]
+//
+// with the 28 slice products of the levels L = 6..12 (the 21 products below contribute < 2^-53 of the full scale and are
+// dropped).  Every slice product is an exact integer GEMM; the per-level sums are exact in int32 for 16 384 rows
+// (7 * 2^14 * 2^14 < 2^31), are drained from TMEM into exact int64 partial sums, and the only roundings are the input
+// quantisation (2^-55 of the column maximum per element, i.e. finer than the f64 ulp of the large entries) and ONE rounding
+// per output element when the seven level sums are combined in f64.  Deterministic by construction (integer sums).
+//
+// Kernels:
+//   oz_absmax_kernel / oz_exp_kernel   column maxima -> exponents e[c]
+//   oz_split_kernel                    f64 block -> 7 int8 slices in a TILED layout: [row chunk of 128][slice][column][128 B].
+//                                      One (chunk, slice, 128-column panel) tile is 16 KB CONTIGUOUS — it is exactly one TMA box
+//                                      and one canonical K-major SWIZZLE_128B UMMA operand (a column of S = one 128-byte row).
+//   oz_gram_kernel                     persistent, warp-specialised: warp 0 = TMA producer (one cp.async.bulk.tensor.4d per slice
+//                                      tile into a ring of twelve 16 KB slots, full/empty mbarriers per slot), warp 1 = MMA issuer
+//                                      (one thread: 4 UTCIMMA of K = 32 per slice product, tcgen05.commit releases slots as their last
+//                                      use retires), warps 2-5 = drain (tcgen05.ld of the level accumulators every 128 chunks).
+//                                      TMEM holds 4 level accumulators of 128 x 128 int32 (all 512 columns), so the 7 levels are two
+//                                      work items per output tile: "lo" = levels 9..12 (10 products, slices 3..6) and "hi" = levels
+//                                      6..8 (18 products, all slices).  The slice tiles of a chunk arrive in the order B6 A0 B5 A1 ...
+//                                      so that every A slice meets the (at most three) B slices it multiplies as a sliding window.
+//   oz_reduce_kernel                   int64 partials of all items of a tile -> f64 G (+ Hermitian mirror).
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+#include <cuda.h>
+
+#include "common.cuh"
+#include "context.h"
+#include "kernels.h"
+
+namespace lb2 {
+
+namespace {
+
+constexpr int OZ_S = 7;                    // slices (base-256 digits)
+constexpr int OZ_CH = 128;                 // rows per chunk = bytes per tile row
+constexpr int OZ_T = 128;                  // tile edge
+constexpr uint32_t OZ_TILE = OZ_T * OZ_CH; // 16 KB
+constexpr int OZ_NS = 12;                  // ring slots
+constexpr int OZ_SEG = 128;                // chunks per TMEM accumulation segment (16 384 rows)
+constexpr int OZ_NT = 192;                 // warp 0 producer, warp 1 MMA, warps 2..5 drain
+constexpr uint32_t OZ_BAR = OZ_NS * OZ_TILE;
+constexpr uint32_t OZ_SMEM = OZ_BAR + 1024 + 1024;   // + barriers, + 1 KB alignment slack
+constexpr int OZ_SHIFT = 55;               // N = rint(x * 2^(55 - e))
+
+struct OzItem {
+  int32_t chunk_begin, chunk_end;   // row chunks of this piece
+  int32_t a_col0, b_col0;           // first column of the A / B panel (in the slice arrays' column numbering)
+  int32_t b_sel;                    // 0: B panel from the first B slice array, 1: from the second
+  int32_t n16;                      // UMMA N: B-panel columns rounded up to 16
+  int32_t group;                    // 0: levels 9..12 (slices 3..6), 1: levels 6..8 (all slices)
+  int32_t tile;                     // output tile index
+};
+struct OzTile {
+  int32_t a_col0, a_cols, b_col0, b_cols, b_sel;
+  int32_t g_row0, g_col0;           // where the tile goes in G
+  int32_t first, last;              // items [first, last)
+  int32_t diag;                     // 1: diagonal tile of a Hermitian product (lower part not written, mirrored instead)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+// bounded wait: a lost arrival traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int32_t c0, int32_t c1, int32_t c2,
+                                            int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (same as gram_tc5.cu): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((1024u >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = S32 (2 << 4), A = B = signed 8-bit (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t oz_idesc(int n16) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n16 >> 3) << 17) | ((uint32_t)(OZ_T >> 4) << 24);
+}
+// both operand descriptors share the constant upper word (SBO = 1024 B, version 1, SWIZZLE_128B); the lower word is the
+// shared-memory address >> 4 — one integer add per MMA in the issuing thread
+constexpr uint32_t OZ_DESC_HI = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(OZ_DESC_HI)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------- exponents
+__global__ void __launch_bounds__(256)
+    oz_absmax_kernel(const double* __restrict__ X, int64_t ld, int64_t n, int64_t rows_per_cta, unsigned long long* __restrict__ mx) {
+  const int c = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
+  const double* x = X + (int64_t)c * ld;
+  unsigned long long m = 0;
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(x[r]));   // non-negative doubles order like integers
+    m = b > m ? b : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t > m ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(mx + c, m);
+}
+// e[c]: every |x| of the column is < 2^(e - 1), so |N| = |rint(x 2^(55 - e))| <= 2^54
+__global__ void oz_exp_kernel(const unsigned long long* __restrict__ mx, int m, int* __restrict__ e) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  const unsigned long long b = mx[c];
+  int ex = 0;
+  if (b) {
+    ex = (int)((b >> 52) & 0x7FF) - 1023 + 2;
+    ex = max(-900, min(900, ex));
+  }
+  e[c] = ex;
+}
+
+// ---------------------------------------------------------------------------------------------------- split
+// out[((rc * 7 + s) * m + c) * 128 + rr]: warp = one column of one chunk, lane = 4 consecutive rows (32 bytes in, 7 x 4 bytes out)
+__global__ void __launch_bounds__(256)
+    oz_split_kernel(const double* __restrict__ X, int64_t ld, int64_t n, int m, const int* __restrict__ e, int8_t* __restrict__ out,
+                    int chunks_per_cta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * 8 + warp;
+  if (c >= m) return;
+  const double scale = __longlong_as_double((long long)(1023 + OZ_SHIFT - e[c]) << 52);
+  const double* x = X + (int64_t)c * ld;
+  const bool vec = ((ld & 1) == 0) && (((uintptr_t)X & 15) == 0);
+  for (int q = 0; q < chunks_per_cta; q++) {
+    const int64_t rc = (int64_t)blockIdx.x * chunks_per_cta + q;
+    const int64_t r = rc * OZ_CH + lane * 4;
+    if (rc * OZ_CH >= n) break;
+    double v[4];
+    if (vec && r + 3 < n) {
+      const double2 a = *reinterpret_cast<const double2*>(x + r), b = *reinterpret_cast<const double2*>(x + r + 2);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = (r + k < n) ? x[r + k] : 0.0;
+    }
+    long long N[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) N[k] = __double2ll_rn(v[k] * scale);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + ((rc * OZ_S) * (int64_t)m + c) * OZ_CH + lane * 4);
+#pragma unroll
+    for (int i = 0; i < OZ_S; i++) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int d = (int)(int8_t)(N[k] & 0xFF);   // balanced digit in [-128, 127]
+        N[k] = (N[k] - d) >> 8;
+        w |= (uint32_t)(d & 0xFF) << (8 * k);
+      }
+      o[(int64_t)i * m * (OZ_CH / 4)] = w;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- main kernel
+struct OzGroup { int amin, smin, lmin, lmax; };
+__device__ __forceinline__ OzGroup oz_group(int g) { return g ? OzGroup{0, 0, 6, 8} : OzGroup{3, 3, 9, 12}; }
+
+// MMAs of one row chunk of a level group, issued by ONE thread.  Slice tiles arrive in ring order B6 A_amin B5 A_amin+1 ...:
+// before A_a come the B slices first needed at a (j = lmin - a); A_a multiplies B_j for j in [max(smin, lmin - a), min(6, lmax - a)]
+// (level a + j -> accumulator a + j - lmin), then A_a and every B slice whose last use this was are released.  Everything is
+// unrolled at compile time: ring slots and parities live in registers, a descriptor costs one add.
+template <int AMIN, int SMIN, int LMIN, int LMAX>
+__device__ __forceinline__ void oz_mma_chunk(uint32_t sbase, uint32_t bar_full, uint32_t bar_empty, uint32_t tmem, uint32_t idesc,
+                                             uint32_t& slot, uint32_t& par, uint32_t& level_init) {
+  uint32_t sB[OZ_S], pB[OZ_S];
+  auto advance = [&]() {
+    if (++slot == OZ_NS) { slot = 0; par ^= 1u; }
+  };
+#pragma unroll
+  for (int a = AMIN; a < OZ_S; ++a) {
+    const int jlo = (LMIN - a) > SMIN ? (LMIN - a) : SMIN;
+    const int jhi = (LMAX - a) < (OZ_S - 1) ? (LMAX - a) : (OZ_S - 1);
+    const int jprev = (a == AMIN) ? OZ_S : ((LMIN - (a - 1)) > SMIN ? (LMIN - (a - 1)) : SMIN);   // B slices [jlo, jprev) arrive now
+#pragma unroll
+    for (int j = OZ_S - 1; j >= 0; --j)
+      if (j < jprev && j >= jlo) { sB[j] = slot; pB[j] = par; advance(); }
+    const uint32_t sA = slot, pA = par;
+    advance();
+#pragma unroll
+    for (int j = OZ_S - 1; j >= 0; --j)
+      if (j < jprev && j >= jlo) mbar_wait(bar_full + 8 * sB[j], pB[j]);
+    mbar_wait(bar_full + 8 * sA, pA);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t a_lo = (sbase + sA * OZ_TILE) >> 4;
+#pragma unroll
+    for (int j = 0; j < OZ_S; ++j)
+      if (j >= jlo && j <= jhi) {
+        const int L = a + j;
+        const uint32_t acc = tmem + (uint32_t)((L - LMIN) * OZ_T);
+        const uint32_t b_lo = (sbase + sB[j] * OZ_TILE) >> 4;
+        const uint32_t init = (level_init >> L) & 1u;
+#pragma unroll
+        for (int ks = 0; ks < OZ_CH / 32; ks++) umma_i8(acc, a_lo + 2u * ks, b_lo + 2u * ks, idesc, ks > 0 ? 1u : init);
+        level_init |= 1u << L;
+      }
+    umma_commit(bar_empty + 8 * sA);
+#pragma unroll
+    for (int j = 0; j < OZ_S; ++j)
+      if (j >= jlo && j <= jhi && ((a < OZ_S - 1) ? (j == LMAX - a) : true)) umma_commit(bar_empty + 8 * sB[j]);
+  }
+}
+
+__global__ void __launch_bounds__(OZ_NT, 1)
+    oz_gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                   const __grid_constant__ CUtensorMap tmB1, const OzItem* __restrict__ items, const int* __restrict__ cta_first,
+                   long long* __restrict__ part) {
+  extern __shared__ __align__(1024) unsigned char smem_oz[];
+  const uint32_t sbase = (smem_u32(smem_oz) + 1023u) & ~1023u;
+  unsigned char* gbase = smem_oz + (sbase - smem_u32(smem_oz));
+  const uint32_t bar_full = sbase + OZ_BAR, bar_empty = bar_full + 8 * OZ_NS, bar_accf = bar_empty + 8 * OZ_NS, bar_acce = bar_accf + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OZ_BAR + 8 * (2 * OZ_NS + 2) + 8);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int it0 = cta_first[blockIdx.x], it1 = cta_first[blockIdx.x + 1];
+
+  if (tid == 0) {
+    for (int s = 0; s < OZ_NS; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_accf, 1);
+    mbar_init(bar_acce, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB0) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB1) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32((const void*)tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t q = 0;
+      auto load = [&](const CUtensorMap* tm, int col0, int slice, int chunk) {
+        const uint32_t s = q % OZ_NS;
+        if (q >= OZ_NS) mbar_wait(bar_empty + 8 * s, ((q / OZ_NS) - 1) & 1);
+        mbar_expect_tx(bar_full + 8 * s, OZ_TILE);
+        tma_load_4d(sbase + s * OZ_TILE, tm, bar_full + 8 * s, 0, col0, slice, chunk);
+        q++;
+      };
+      for (int it = it0; it < it1; ++it) {
+        const OzItem im = items[it];
+        const OzGroup g = oz_group(im.group);
+        const CUtensorMap* tb = im.b_sel ? &tmB1 : &tmB0;
+        for (int chunk = im.chunk_begin; chunk < im.chunk_end; ++chunk) {
+          int jnext = OZ_S - 1;
+          for (int a = g.amin; a < OZ_S; ++a) {
+            const int jlo = max(g.smin, g.lmin - a);
+            while (jnext >= jlo) { load(tb, im.b_col0, jnext, chunk); --jnext; }
+            load(&tmA, im.a_col0, a, chunk);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t slot = 0, par = 0, segs = 0;
+      for (int it = it0; it < it1; ++it) {
+        const OzItem im = items[it];
+        const uint32_t idesc = oz_idesc(im.n16);
+        for (int seg0 = im.chunk_begin; seg0 < im.chunk_end; seg0 += OZ_SEG, ++segs) {
+          const int seg1 = min(im.chunk_end, seg0 + OZ_SEG);
+          if (segs > 0) mbar_wait(bar_acce, (segs - 1) & 1);   // the drain warps have read the previous segment's accumulators
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          uint32_t level_init = 0;
+          if (im.group) {
+            for (int chunk = seg0; chunk < seg1; ++chunk)
+              oz_mma_chunk<0, 0, 6, 8>(sbase, bar_full, bar_empty, tmem, idesc, slot, par, level_init);
+          } else {
+            for (int chunk = seg0; chunk < seg1; ++chunk)
+              oz_mma_chunk<3, 3, 9, 12>(sbase, bar_full, bar_empty, tmem, idesc, slot, par, level_init);
+          }
+          umma_commit(bar_accf);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ drain (warps 2..5)
+    const int lq = warp & 3;            // TMEM lane quarter this warp may read
+    const int row = lq * 32 + lane;     // tile row = column of the A panel
+    uint32_t segs = 0;
+    for (int it = it0; it < it1; ++it) {
+      const OzItem im = items[it];
+      const int nlev = im.group ? 3 : 4;
+      long long* p0 = part + (int64_t)it * (4 * OZ_T * OZ_T) + row;
+      for (int seg0 = im.chunk_begin; seg0 < im.chunk_end; seg0 += OZ_SEG, ++segs) {
+        mbar_wait(bar_accf, segs & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const bool first = seg0 == im.chunk_begin;
+        for (int lev = 0; lev < nlev; ++lev)
+          for (int cq = 0; cq * 32 < im.n16; ++cq) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(lev * OZ_T + cq * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            long long* p = p0 + (int64_t)(lev * OZ_T + cq * 32) * OZ_T;
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              const long long add = (long long)(int32_t)v[i];
+              p[(int64_t)i * OZ_T] = first ? add : p[(int64_t)i * OZ_T] + add;
+            }
+          }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        mbar_arrive(bar_acce);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
+}
+
+// G[g_row0 + r, g_col0 + c] = 2^(eA + eB - 110) * sum_L 256^L * (sum over the items of the tile of level L)
+__global__ void __launch_bounds__(256)
+    oz_reduce_kernel(const long long* __restrict__ part, const OzTile* __restrict__ tiles, const OzItem* __restrict__ items,
+                     const int* __restrict__ eA, const int* __restrict__ eB0, const int* __restrict__ eB1, double* __restrict__ G0,
+                     int ldg0, double* __restrict__ G1, int ldg1, int mirror) {
+  const OzTile t = tiles[blockIdx.x];
+  double* __restrict__ G = t.b_sel ? G1 : G0;
+  const int ldg = t.b_sel ? ldg1 : ldg0;
+  const int* eB = t.b_sel ? eB1 : eB0;
+  const int tot = t.a_cols * t.b_cols;
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < tot; idx += gridDim.y * blockDim.x) {
+    const int r = idx % t.a_cols, c = idx / t.a_cols;
+    if (t.diag && r > c) continue;
+    long long lev[7] = {0, 0, 0, 0, 0, 0, 0};   // levels 6..12
+    for (int k = t.first; k < t.last; k++) {
+      const int grp = items[k].group;
+      const long long* p = part + (int64_t)k * (4 * OZ_T * OZ_T) + r + (int64_t)c * OZ_T;
+      const int nl = grp ? 3 : 4, l0 = grp ? 0 : 3;
+      for (int l = 0; l < nl; l++) lev[l0 + l] += p[(int64_t)l * OZ_T * OZ_T];
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int l = 0; l < 7; l++) s += ldexp((double)lev[l], 8 * l);   // smallest level first; 2^48 of the level-6 weight is in the scale
+    const double val = ldexp(s, eA[t.a_col0 + r] + eB[t.b_col0 + c] - 2 * OZ_SHIFT + 48);
+    G[(t.g_row0 + r) + (int64_t)(t.g_col0 + c) * ldg] = val;
+    if (mirror && t.diag >= 0 && (t.g_row0 + r) != (t.g_col0 + c)) G[(t.g_col0 + c) + (int64_t)(t.g_row0 + r) * ldg] = val;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn oz_encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// 4-D map of a slice array: (byte in chunk row: 128, column: m, slice: 7, chunk: nch); box = one 128-column slice tile
+int oz_make_map(CUtensorMap* tm, const int8_t* base, int m, int64_t nch) {
+  EncodeTiledFn enc = oz_encode_tiled();
+  if (!enc) return -100;
+  const cuuint64_t dims[4] = {(cuuint64_t)OZ_CH, (cuuint64_t)m, (cuuint64_t)OZ_S, (cuuint64_t)nch};
+  const cuuint64_t strides[3] = {(cuuint64_t)OZ_CH, (cuuint64_t)OZ_CH * m, (cuuint64_t)OZ_CH * m * OZ_S};
+  const cuuint32_t box[4] = {(cuuint32_t)OZ_CH, (cuuint32_t)OZ_T, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -100;
+}
+
+// exponents + slices of an n x m f64 block
+int oz_split(lb2_ctx* ctx, int64_t n, int m, const double* X, int64_t ld, int8_t* slices, int* e, unsigned long long* mx) {
+  LB2_CUDA_OK(cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * m, ctx->stream));
+  const int64_t rows_per_cta = 65536;
+  oz_absmax_kernel<<<dim3((unsigned)((n + rows_per_cta - 1) / rows_per_cta), m), 256, 0, ctx->stream>>>(X, ld, n, rows_per_cta, mx);
+  oz_exp_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(mx, m, e);
+  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
+  const int cpc = 16;
+  oz_split_kernel<<<dim3((unsigned)((nch + cpc - 1) / cpc), (m + 7) / 8), 256, 0, ctx->stream>>>(X, ld, n, m, e, slices, cpc);
+  ctx->launches += 3;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+struct OzPlanTile { OzTile t; double w; };   // w: relative MMA cost of one chunk of the whole tile (both groups)
+
+// tiles x {lo, hi} laid end to end weighted by their MMA count, cut into ncta equal pieces (chunk granularity)
+void oz_schedule(std::vector<OzPlanTile>& tiles, int64_t nch, int ncta, double load_w, std::vector<OzItem>& items,
+                 std::vector<int>& cta_first) {
+  struct Unit { int tile, group; double cost; };
+  std::vector<Unit> units;
+  for (size_t i = 0; i < tiles.size(); i++) {
+    // a unit costs what is larger: its MMAs (10 / 18 slice products, proportional to the UMMA N) or the slice tiles it
+    // pulls through the ring (8 / 14 boxes of 16 KB whatever the panel width; load_w = relative cost of a box)
+    const double nfrac = ((tiles[i].t.b_cols + 15) / 16 * 16) / 128.0;
+    units.push_back({(int)i, 0, std::max(10.0 * nfrac, 8.0 * load_w)});
+    units.push_back({(int)i, 1, std::max(18.0 * nfrac, 14.0 * load_w)});
+  }
+  double total = 0;
+  for (auto& u : units) total += u.cost * (double)nch;
+  const double L = total / ncta;
+  cta_first.assign(ncta + 1, 0);
+  std::vector<int> item_cta;
+  double U = 0;
+  for (auto& u : units) {
+    OzTile& t = tiles[u.tile].t;
+    if (u.group == 0) t.first = (int)items.size();
+    const double span = u.cost * (double)nch;
+    int b_lo = std::min(std::max((int)std::floor(U / L), 0), ncta - 1);
+    int b_hi = std::min(std::max((int)std::floor((U + span) / L), 0), ncta - 1);
+    auto boundary = [&](int b) -> int64_t {
+      if (b <= b_lo) return 0;
+      if (b > b_hi) return nch;
+      int64_t r = (int64_t)std::llround(((double)b * L - U) / u.cost);
+      if (r < 4) r = 0;
+      if (nch - r < 4) r = nch;
+      return std::min<int64_t>(std::max<int64_t>(r, 0), nch);
+    };
+    for (int b = b_lo; b <= b_hi; b++) {
+      const int64_t c0 = boundary(b), c1 = boundary(b + 1);
+      if (c1 <= c0) continue;
+      OzItem im{};
+      im.chunk_begin = (int32_t)c0; im.chunk_end = (int32_t)c1;
+      im.a_col0 = t.a_col0; im.b_col0 = t.b_col0; im.b_sel = t.b_sel;
+      im.n16 = (t.b_cols + 15) / 16 * 16;
+      im.group = u.group;
+      im.tile = u.tile;
+      items.push_back(im);
+      item_cta.push_back(b);
+    }
+    if (u.group == 1) t.last = (int)items.size();
+    U += span;
+  }
+  size_t it = 0;
+  for (int b = 0; b < ncta; b++) {
+    while (it < items.size() && item_cta[it] < b) it++;
+    cta_first[b] = (int)it;
+  }
+  cta_first[ncta] = (int)items.size();
+}
+
+int8_t* oz_buffer(lb2_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->oz_bytes) return (int8_t*)ctx->oz_buf;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
+  if (ctx->oz_buf) cudaFree(ctx->oz_buf);
+  ctx->oz_buf = nullptr;
+  ctx->oz_bytes = 0;
+  if (cudaMalloc(&ctx->oz_buf, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    fprintf(stderr, "lobpcg_b200: cannot allocate %zu bytes for the int8 slices\n", bytes);
+    return nullptr;
+  }
+  ctx->oz_bytes = bytes;
+  return (int8_t*)ctx->oz_buf;
+}
+
+}  // namespace
+
+namespace {
+
+struct OzOperand {          // one f64 block and where its slices / exponents live
+  const double* X; int64_t ld; int m;
+  int8_t* slices; int* e;
+};
+
+// split the operands, run the tile list, reduce.  B panels come from operand 1 (b_sel = 0) or operand 2 (b_sel = 1); an
+// operand with X == nullptr aliases the slices of operand 0 (its slices / e pointers are then set by the caller).
+int oz_run(lb2_ctx* ctx, int64_t n, std::vector<OzPlanTile>& tiles, OzOperand (&op)[3], int nop, double* G0, int ldg0, double* G1,
+           int ldg1, int mirror, int8_t* buf, size_t o_rest, unsigned long long* mx) {
+  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
+  auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  std::vector<OzItem> items;
+  std::vector<int> cta_first;
+  const int ncta = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, (int64_t)tiles.size() * 2 * nch / 8));
+  oz_schedule(tiles, nch, ncta, 0.01 * (ctx->oz_load_pct > 0 ? ctx->oz_load_pct : 100), items, cta_first);
+  const size_t nitems = items.size();
+  const size_t o_part = o_rest, o_items = o_part + al(sizeof(long long) * nitems * 4 * OZ_T * OZ_T),
+               o_cta = o_items + al(sizeof(OzItem) * nitems), o_tiles = o_cta + al(sizeof(int) * (ncta + 1)),
+               total = o_tiles + al(sizeof(OzTile) * tiles.size());
+  if (total > ctx->oz_bytes) return -3;   // the caller sized the buffer with oz_rest_bytes()
+  long long* part = (long long*)(buf + o_part);
+  std::vector<OzTile> tl;
+  for (auto& p : tiles) tl.push_back(p.t);
+  LB2_CUDA_OK(cudaMemcpyAsync(buf + o_items, items.data(), sizeof(OzItem) * nitems, cudaMemcpyHostToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaMemcpyAsync(buf + o_cta, cta_first.data(), sizeof(int) * (ncta + 1), cudaMemcpyHostToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaMemcpyAsync(buf + o_tiles, tl.data(), sizeof(OzTile) * tl.size(), cudaMemcpyHostToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  const bool timing = lb2_gram_i8_mode(ctx) == 2;   // debug: per-phase device times on stderr
+  if (timing) for (auto& e : ev) cudaEventCreate(&e);
+  if (timing) cudaEventRecord(ev[0], ctx->stream);
+  for (int q = 0; q < nop; q++)
+    if (op[q].X)
+      if (int rc = oz_split(ctx, n, op[q].m, op[q].X, op[q].ld, op[q].slices, op[q].e, mx)) return rc;
+  alignas(64) CUtensorMap tm[3];
+  for (int q = 0; q < 3; q++) {
+    const OzOperand& o = op[q < nop ? q : 0];
+    // an aliased operand (X == nullptr) is addressed through operand 0's map: its column offset is already in the tiles
+    const OzOperand& src = o.X ? o : op[0];
+    if (oz_make_map(&tm[q], src.slices, src.m, nch)) return -100;
+  }
+  if (timing) cudaEventRecord(ev[1], ctx->stream);
+  LB2_CUDA_OK(cudaFuncSetAttribute(oz_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+  oz_gram_kernel<<<ncta, OZ_NT, OZ_SMEM, ctx->stream>>>(tm[0], tm[1], tm[2], (const OzItem*)(buf + o_items), (const int*)(buf + o_cta), part);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  if (timing) cudaEventRecord(ev[2], ctx->stream);
+  oz_reduce_kernel<<<dim3((unsigned)tl.size(), 8), 256, 0, ctx->stream>>>(part, (const OzTile*)(buf + o_tiles), (const OzItem*)(buf + o_items),
+                                                                          op[0].e, op[1].e, op[nop > 2 ? 2 : 1].e, G0, ldg0, G1, ldg1, mirror);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  if (timing) {
+    cudaEventRecord(ev[3], ctx->stream);
+    cudaEventSynchronize(ev[3]);
+    float t01 = 0, t12 = 0, t23 = 0;
+    cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
+    fprintf(stderr, "gram_i8 n=%lld, %zu tiles: split %.2f ms, int8 MMA kernel %.2f ms (%zu items, %d CTAs), reduce %.2f ms\n",
+            (long long)n, tiles.size(), t01, t12, nitems, ncta, t23);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+  return 0;
+}
+// bytes behind the slices: partial sums (one 4-level slot per item, items <= 2 tiles + CTAs) and the schedule
+size_t oz_rest_bytes(lb2_ctx* ctx, size_t ntiles) {
+  const size_t nitems = 2 * ntiles + (size_t)ctx->sm_count + 8;
+  return sizeof(long long) * nitems * 4 * OZ_T * OZ_T + (sizeof(OzItem) + sizeof(OzTile)) * nitems + 65536;
+}
+
+}  // namespace
+
+// G (ma x mb) = A^H B through the int8 split; upper != 0: Hermitian product (A and B span the same columns), the lower triangle
+// is mirrored.  -100 = not available.
+int gram_i8_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B, int64_t ldb, double* G,
+                int ldg, int upper) {
+  if (n >= ((int64_t)1 << 31) * OZ_CH || !oz_encode_tiled()) return -100;
+  const bool same = (A == B && lda == ldb && ma == mb);
+  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
+  auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  std::vector<OzPlanTile> tiles;
+  const int ntm = (ma + OZ_T - 1) / OZ_T, ntn = (mb + OZ_T - 1) / OZ_T;
+  for (int tj = 0; tj < ntn; tj++)
+    for (int ti = 0; ti < (upper ? tj + 1 : ntm); ti++) {
+      OzPlanTile pt{};
+      pt.t.a_col0 = ti * OZ_T; pt.t.a_cols = std::min(OZ_T, ma - ti * OZ_T);
+      pt.t.b_col0 = tj * OZ_T; pt.t.b_cols = std::min(OZ_T, mb - tj * OZ_T);
+      pt.t.b_sel = 0;
+      pt.t.g_row0 = pt.t.a_col0; pt.t.g_col0 = pt.t.b_col0;
+      pt.t.diag = (upper && ti == tj) ? 1 : 0;
+      tiles.push_back(pt);
+    }
+  const size_t bytesA = al((size_t)nch * OZ_S * ma * OZ_CH), bytesB = same ? 0 : al((size_t)nch * OZ_S * mb * OZ_CH);
+  const size_t o_eA = bytesA + bytesB, o_eB = o_eA + al(sizeof(int) * ma), o_mx = o_eB + al(sizeof(int) * mb),
+               o_rest = o_mx + al(sizeof(unsigned long long) * std::max(ma, mb));
+  int8_t* buf = oz_buffer(ctx, o_rest + oz_rest_bytes(ctx, tiles.size()));
+  if (!buf) return -1;
+  OzOperand op[3] = {{A, lda, ma, buf, (int*)(buf + o_eA)},
+                     {same ? nullptr : B, ldb, mb, same ? buf : buf + bytesA, same ? (int*)(buf + o_eA) : (int*)(buf + o_eB)},
+                     {nullptr, 0, 0, nullptr, nullptr}};
+  return oz_run(ctx, n, tiles, op, 2, G, ldg, G, ldg, upper ? 1 : 0, buf, o_rest, (unsigned long long*)(buf + o_mx));
+}
+
+// Column-block products of the cached-Gram pass through the int8 split (same contract as gram_wl_cols_f64): G0 = S^H W0 and, with
+// W1, G1 = S^H W1.  The slices of S are made once and serve as the A panels of both products and — when W0 is the column block
+// tri_c0.. of S itself (B = I) — as the B panels of the first; tiles strictly below the diagonal of the Hermitian block are skipped.
+int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, int64_t lds, const double* W0, int64_t ldw0, double* G0,
+                     int ldg0, const double* W1, int64_t ldw1, double* G1, int ldg1, int tri_c0) {
+  if (n >= ((int64_t)1 << 31) * OZ_CH || !oz_encode_tiled()) return -100;
+  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
+  auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  const int nprod = (W1 && G1) ? 2 : 1;
+  const bool herm = tri_c0 >= 0 && tri_c0 + nw == m;
+  const bool w0_in_s = herm && W0 == S + (int64_t)tri_c0 * lds && ldw0 == lds;
+  const int split = herm ? tri_c0 : m;
+  std::vector<std::pair<int, int>> rows;
+  for (int c = 0; c < split; c += OZ_T) rows.emplace_back(c, std::min(OZ_T, split - c));
+  for (int c = split; c < m; c += OZ_T) rows.emplace_back(c, std::min(OZ_T, m - c));
+  const int ntn = (nw + OZ_T - 1) / OZ_T;
+  std::vector<OzPlanTile> tiles;
+  for (auto& rw : rows)
+    for (int q = 0; q < nprod; q++)
+      for (int tj = 0; tj < ntn; tj++) {
+        if (rw.first >= split && (rw.first - split) / OZ_T > tj) continue;   // below the diagonal of the Hermitian block
+        OzPlanTile pt{};
+        pt.t.a_col0 = rw.first; pt.t.a_cols = rw.second;
+        pt.t.b_cols = std::min(OZ_T, nw - tj * OZ_T);
+        pt.t.b_sel = q;
+        pt.t.b_col0 = tj * OZ_T + ((q == 0 && w0_in_s) ? tri_c0 : 0);   // in the column numbering of the slice array it is read from
+        pt.t.g_row0 = rw.first; pt.t.g_col0 = tj * OZ_T;
+        pt.t.diag = 0;
+        tiles.push_back(pt);
+      }
+  if (tiles.empty()) return 0;
+  const size_t bS = al((size_t)nch * OZ_S * m * OZ_CH), bW0 = w0_in_s ? 0 : al((size_t)nch * OZ_S * nw * OZ_CH),
+               bW1 = nprod == 2 ? al((size_t)nch * OZ_S * nw * OZ_CH) : 0;
+  const size_t o_eS = bS + bW0 + bW1, o_e0 = o_eS + al(sizeof(int) * m), o_e1 = o_e0 + al(sizeof(int) * nw),
+               o_mx = o_e1 + al(sizeof(int) * nw), o_rest = o_mx + al(sizeof(unsigned long long) * m);
+  int8_t* buf = oz_buffer(ctx, o_rest + oz_rest_bytes(ctx, tiles.size()));
+  if (!buf) return -1;
+  int* eS = (int*)(buf + o_eS);
+  OzOperand op[3] = {{S, lds, m, buf, eS},
+                     {w0_in_s ? nullptr : W0, ldw0, nw, w0_in_s ? buf : buf + bS, w0_in_s ? eS : (int*)(buf + o_e0)},
+                     {nprod == 2 ? W1 : nullptr, ldw1, nw, buf + bS + bW0, (int*)(buf + o_e1)}};
+  // the reduce kernel indexes the exponents with the tile's b_col0, which already carries tri_c0 for an aliased W0
+  return oz_run(ctx, n, tiles, op, nprod == 2 ? 3 : 2, G0, ldg0, G1, ldg1, 0, buf, o_rest, (unsigned long long*)(buf + o_mx));
+}
+
+}  // namespace lb2

@@ -30,6 +30,11 @@ int gram_tiles_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int
                    int64_t ldb, double* G, int ldg, int upper);
 int gram_reduce_f32(lb2_ctx* ctx, const float* part, int64_t split_stride, int nsplit, int ma, int mb, int mirror,
                     float* G, int ldg);
+// gram_i8.cu: f64 Gram on tcgen05 kind::i8 through an Ozaki split into 7 int8 slices (option gram_i8); -100 = not available
+int gram_i8_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_t lda, const double* B, int64_t ldb, double* G,
+                int ldg, int upper);
+int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, int64_t lds, const double* W0, int64_t ldw0, double* G0,
+                     int ldg0, const double* W1, int64_t ldw1, double* G1, int ldg1, int tri_c0);
 // gram_tc5.cu: float Gram on tcgen05 (kind::tf32, 3xTF32 split, accumulator in TMEM); -100 = alignment not met
 int gram_tc5_f32(lb2_ctx* ctx, int64_t n, int ma, int mb, const float* A, int64_t lda, const float* B, int64_t ldb,
                  float* G, int ldg, int upper);

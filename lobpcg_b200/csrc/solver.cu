@@ -412,6 +412,7 @@ int Solver<T>::alloc() {
   const size_t slab_b = al(sizeof(T) * 3 * nk), wrk_b = al(sizeof(T) * std::max<size_t>(nk, 2 * (size_t)n));
   // AS = [AX | AW] with the cached Gram blocks, [AX | AP | AW] for the legacy pass, the indefinite solver and the helpers
   if (const char* e = getenv("LB2_GRAM_CACHE")) { if (!gram_cache_forced) gram_cache = (atoi(e) != 0); }
+  { const char* e = getenv("LB2_GRAM_I8"); ctx->gram_i8_env = e ? atoi(e) : -1; }   // f64 Gram through the int8 tensor path (gram_i8.cu)
   if (indef) gram_cache = false;
   as_cols = (gram_cache && !helper_mode) ? 2 * k : 3 * k;
   const size_t as_b = al(sizeof(T) * (size_t)as_cols * n);

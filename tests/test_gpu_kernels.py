@@ -575,6 +575,68 @@ def test_gram_cols_full_size_linearity(ctx):
     assert np.max(np.abs(blk[up] - Gww[up])) / np.abs(Gww).max() < 1e-13
 
 
+# ------------------------------------------------------------------------------------------------ int8 (Ozaki) f64 Gram
+def _wide_columns(rng, n, m):
+    """columns whose magnitudes span 14 decades and whose entries span several decades inside a column"""
+    X = rng.standard_normal((n, m)) * np.exp(rng.uniform(-3, 3, (n, 1)))
+    return np.asfortranarray(X * np.exp(rng.uniform(-16, 16, m))[None, :])
+
+
+@pytest.mark.parametrize("shape", [(4096, 128, 128, True), (20000, 150, 150, True), (40003, 150, 100, False), (8200, 33, 7, False),
+                                   (12000, 257, 257, True), (30001, 5, 300, False)])
+def test_gram_i8_matches_extended_precision(ctx, shape):
+    """gram_i8.cu (option gram_i8): f64 Gram through tcgen05.mma kind::i8 on a 7-slice int8 split with exact integer
+    accumulation.  Error measured against a long-double product, relative to |a_i| |b_j| (columns of very different
+    magnitude): must be at the level of the f64 DMMA path (a few 1e-16), ragged tiles, Hermitian mirror, n not a multiple of
+    the 128-row chunk."""
+    n, ma, mb, upper = shape
+    rng = np.random.default_rng(n + ma)
+    A = _wide_columns(rng, n, ma)
+    B = A if upper else _wide_columns(rng, n, mb)
+    ref = (A.astype(np.longdouble).T @ B.astype(np.longdouble)).astype(np.float64)
+    scale = np.sqrt(np.outer((A * A).sum(0), (B * B).sum(0)))
+    dA = api.DeviceArray.from_numpy(ctx, A)
+    dB = dA if upper else api.DeviceArray.from_numpy(ctx, B)
+    ctx.set_option("gram_i8", 1)
+    try:
+        G = api.gram(ctx, dA, dB, upper=upper).numpy(ctx)
+    finally:
+        ctx.set_option("gram_i8", 0)
+    err = np.abs(G - ref) / scale
+    assert err.max() < 2e-15, f"max error {err.max():.2e} relative to |a||b|"
+    if upper:
+        assert np.array_equal(G, G.T)
+
+
+@pytest.mark.parametrize("shape", [(9000, 600, 300), (8193, 300, 130), (4099, 0, 150), (30001, 525, 225), (12345, 263, 7)])
+def test_gram_cols_i8_matches_dmma_path(ctx, shape):
+    """Column-block products of the cached-Gram pass through the int8 path: W0 given as a column view of S (the solver's
+    B = I case: the slices of S serve both operands) and as a separate block; both products; must agree with numpy and with
+    the DMMA work-list kernel on every entry that is not strictly below the diagonal of the Hermitian block."""
+    n, mxp, nw = shape
+    rng = np.random.default_rng(n + nw)
+    S = _wide_columns(rng, n, mxp + nw)
+    h = rng.uniform(0.5, 1.5, n)
+    AW = np.asfortranarray(h[:, None] * S[:, mxp:])
+    dS, dAW = api.DeviceArray.from_numpy(ctx, S), api.DeviceArray.from_numpy(ctx, AW)
+    dWsep = api.DeviceArray.from_numpy(ctx, np.asfortranarray(S[:, mxp:]))
+    ref0, ref1 = S.T @ S[:, mxp:], S.T @ AW          # f64 BLAS references: tolerance 2e-14 of |a| |b| (their own rounding)
+    nrm = np.sqrt((S * S).sum(0))
+    sc0 = np.outer(nrm, nrm[mxp:]); sc1 = np.outer(nrm, np.sqrt((AW * AW).sum(0)))
+    i, j = np.meshgrid(np.arange(mxp + nw), np.arange(nw), indexing="ij")
+    keep = ~(i - mxp > j)
+    ctx.set_option("gram_i8", 1)
+    try:
+        for dW in (dS.cols(mxp, nw), dWsep):
+            G0, G1 = api.gram_cols(ctx, dS, dW, dAW, tri_c0=mxp)
+            assert (np.abs(G0.numpy(ctx) - ref0) / sc0)[keep].max() < 2e-14
+            assert (np.abs(G1.numpy(ctx) - ref1) / sc1)[keep].max() < 2e-14
+        G0, _ = api.gram_cols(ctx, dS, dAW, None, tri_c0=mxp)
+        assert (np.abs(G0.numpy(ctx) - ref1) / sc1)[keep].max() < 2e-14
+    finally:
+        ctx.set_option("gram_i8", 0)
+
+
 # ------------------------------------------------------------------------------------------------ windowed CSR kernel
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("case", [(3000, 40, 9, 5), (70001, 200, 33, 12), (5000, 256, 7, 40), (1100, 3, 4, 3)])
