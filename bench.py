@@ -359,6 +359,12 @@ def run_ours(args):
             windows[name] = {"ms_per_step": t / max(dn, 1), "steps": dn, "note": note, "solver_state": s.progress(),
                              "ms": {kk: stw[kk]["ms"] / max(dn, 1) for kk in ("gram", "tall_nn", "spmm", "residual", "small_dense", "comm")}}
         nw_steps = max(3, min(args.steps, 6))
+        # same state as the main window, but every f64 Gram product through tcgen05.mma kind::i8 on the Ozaki split
+        # (lobpcg_b200/csrc/gram_i8.cu; opt-in: LB2_GRAM_I8=1 / context option gram_i8)
+        ctx.set_option("gram_i8", 1)
+        timed_window("int8_gram", nw_steps, "main-window pass with the column-block Gram on the int8 tensor path (7-slice Ozaki split, "
+                     "exact integer accumulation in TMEM); includes the per-pass split of [X P W] and A W into slices")
+        ctx.set_option("gram_i8", 0)
         s.set_option("debug_min_conv", nev // 2)
         timed_window("softlocked", nw_steps, f"Cholesky branch with the leading {nev // 2} of {k} columns soft-locked "
                      "(forced: option debug_min_conv; P and W shrink to the active columns)")

@@ -45,6 +45,9 @@ struct lb2_ctx {
   void* gram_wl_cols_cache = nullptr;   // lb2::WlColsCache* (schedules of the column-block products, gram_wl_cols_f64)
   int gram_i8 = 0;       // f64 Gram through tcgen05 kind::i8 on an Ozaki split (gram_i8.cu): 1 = on, 0 = DMMA kernels (default)
   int gram_i8_env = -1;  // LB2_GRAM_I8 as seen by the last solver set-up (-1 = unset); overrides gram_i8 for the drop-in entry points
+  int oz_lockstep = 1;   // gram_i8 one-tile-per-CTA kernel: 1 = lock-step cohorts (every (tile, level group) has its own CTAs), 0 = equal-cost cut
+  int oz_cluster = 0;    // gram_i8 column-block products: 1 = 4-CTA clusters with multicast slice tiles (r02: 110 ms against 90 ms of the one-tile-per-CTA kernel at the C5 shape), 0 = one tile per CTA
+  int oz_clusters = -1;  // resident clusters of the cluster kernel (queried once; option: force a count)
   int oz_load_pct = 0;   // gram_i8 schedule: cost of one 16 KB slice-tile load relative to one full-width slice product, in % (0 = 100)
   int gram_tc5 = -1;     // float Gram through tcgen05 / TMEM (gram_tc5.cu): -1 = auto (on), 0 = off, 1 = on
   int gram_tma = -1;     // float Gram: TMA-fed tcgen05 kernel (gram_tc5.cu: gram_tc5_tma_kernel): -1 / 1 = on, 0 = cp.async-fed kernel

@@ -66,7 +66,9 @@ struct OzItem {
 struct OzTile {
   int32_t a_col0, a_cols, b_col0, b_cols, b_sel;
   int32_t g_row0, g_col0;           // where the tile goes in G
-  int32_t first, last;              // items [first, last)
+  int32_t first, last;              // items first, first + stride, ... below last
+  int32_t stride;                   // item index stride (0 = 1)
+  int32_t rank;                     // CTA rank inside the cluster that computes this tile (cluster kernel), else 0
   int32_t diag;                     // 1: diagonal tile of a Hermitian product (lower part not written, mirrored instead)
 };
 
@@ -372,11 +374,224 @@ __global__ void __launch_bounds__(OZ_NT, 1)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------- cluster kernel
+// The kernel above is bound by operand traffic, not by the tensor pipe (ncu, 640 x 256: 110 GB of DRAM reads for 26 GB of
+// slices, tensor pipe 48 % busy): an int8 slice set is as many bytes as the f64 block, but the MMAs retire 2.5 x faster than
+// DMMA.  Here four CTAs of a thread-block cluster compute a 2 x 2 SUPER-TILE (two A panels x two B panels, same row chunks, same
+// level group) and share their operands in hardware: every slice tile is needed by two CTAs, each of them fetches HALF of it
+// (a 64-column box) and the TMA unit MULTICASTS the box into both CTAs' shared memory (UTMALDG.MULTICAST), so a CTA pulls
+// half the bytes through L2 for the same MMAs.  A ring slot is refilled only when BOTH consumers have released it: the slot's
+// "empty" mbarrier counts two arrivals and tcgen05.commit.multicast delivers each consumer's arrival to both CTAs.
+constexpr int OZ_NA = 4, OZ_NB = 8;   // ring slots of the A / B slice tiles (B slots first in shared memory)
+
+struct OzCItem {
+  int32_t chunk_begin, chunk_end, group, pad;
+  int32_t a_col0[2], b_col0[2], b_sel[2], n16[2];
+};
+
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int32_t c0, int32_t c1, int32_t c2,
+                                               int32_t c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], %7;\n" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+struct OzRing { uint32_t slot, par; };
+
+template <int AMIN, int SMIN, int LMIN, int LMAX>
+__device__ __forceinline__ void oz_mma_chunk_c(uint32_t sbase, uint32_t fullA, uint32_t emptyA, uint32_t fullB, uint32_t emptyB,
+                                               uint32_t tmem, uint32_t idesc, OzRing& ra, OzRing& rb, uint32_t& level_init,
+                                               uint16_t maskA, uint16_t maskB) {
+  uint32_t sB[OZ_S], pB[OZ_S];
+#pragma unroll
+  for (int a = AMIN; a < OZ_S; ++a) {
+    const int jlo = (LMIN - a) > SMIN ? (LMIN - a) : SMIN;
+    const int jhi = (LMAX - a) < (OZ_S - 1) ? (LMAX - a) : (OZ_S - 1);
+    const int jprev = (a == AMIN) ? OZ_S : ((LMIN - (a - 1)) > SMIN ? (LMIN - (a - 1)) : SMIN);
+#pragma unroll
+    for (int j = OZ_S - 1; j >= 0; --j)
+      if (j < jprev && j >= jlo) {
+        sB[j] = rb.slot; pB[j] = rb.par;
+        if (++rb.slot == OZ_NB) { rb.slot = 0; rb.par ^= 1u; }
+      }
+    const uint32_t sA = ra.slot, pA = ra.par;
+    if (++ra.slot == OZ_NA) { ra.slot = 0; ra.par ^= 1u; }
+#pragma unroll
+    for (int j = OZ_S - 1; j >= 0; --j)
+      if (j < jprev && j >= jlo) mbar_wait(fullB + 8 * sB[j], pB[j]);
+    mbar_wait(fullA + 8 * sA, pA);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t a_lo = (sbase + (OZ_NB + sA) * OZ_TILE) >> 4;
+#pragma unroll
+    for (int j = 0; j < OZ_S; ++j)
+      if (j >= jlo && j <= jhi) {
+        const int L = a + j;
+        const uint32_t acc = tmem + (uint32_t)((L - LMIN) * OZ_T);
+        const uint32_t b_lo = (sbase + sB[j] * OZ_TILE) >> 4;
+        const uint32_t init = (level_init >> L) & 1u;
+#pragma unroll
+        for (int ks = 0; ks < OZ_CH / 32; ks++) umma_i8(acc, a_lo + 2u * ks, b_lo + 2u * ks, idesc, ks > 0 ? 1u : init);
+        level_init |= 1u << L;
+      }
+    umma_commit_mc(emptyA + 8 * sA, maskA);
+#pragma unroll
+    for (int j = 0; j < OZ_S; ++j)
+      if (j >= jlo && j <= jhi && ((a < OZ_S - 1) ? (j == LMAX - a) : true)) umma_commit_mc(emptyB + 8 * sB[j], maskB);
+  }
+}
+
+__global__ void __launch_bounds__(OZ_NT, 1)
+    oz_gram_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                           const __grid_constant__ CUtensorMap tmB1, const OzCItem* __restrict__ items,
+                           const int* __restrict__ cl_first, long long* __restrict__ part) {
+  extern __shared__ __align__(1024) unsigned char smem_oz[];
+  const uint32_t sbase = (smem_u32(smem_oz) + 1023u) & ~1023u;
+  unsigned char* gbase = smem_oz + (sbase - smem_u32(smem_oz));
+  const uint32_t fullB = sbase + OZ_BAR, emptyB = fullB + 8 * OZ_NB, fullA = emptyB + 8 * OZ_NB, emptyA = fullA + 8 * OZ_NA,
+                 bar_accf = emptyA + 8 * OZ_NA, bar_acce = bar_accf + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OZ_BAR + 8 * (2 * OZ_NS + 2) + 8);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+  const int ra = (int)(rank >> 1), rb = (int)(rank & 1);
+  const uint16_t maskA = (uint16_t)(3u << (2 * ra)), maskB = (uint16_t)((1u << rb) | (1u << (rb + 2)));
+  const int cl = blockIdx.x >> 2;
+  const int it0 = cl_first[cl], it1 = cl_first[cl + 1];
+
+  if (tid == 0) {
+    for (int s = 0; s < OZ_NB; s++) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 2); }
+    for (int s = 0; s < OZ_NA; s++) { mbar_init(fullA + 8 * s, 1); mbar_init(emptyA + 8 * s, 2); }
+    mbar_init(bar_accf, 1);
+    mbar_init(bar_acce, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB0) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB1) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32((const void*)tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();   // every CTA's barriers exist before a partner's TMA or commit can signal them
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t qa = 0, qb = 0;
+      for (int it = it0; it < it1; ++it) {
+        const OzCItem im = items[it];
+        const OzGroup g = oz_group(im.group);
+        const CUtensorMap* tb = im.b_sel[rb] ? &tmB1 : &tmB0;
+        const int acol = im.a_col0[ra] + rb * (OZ_T / 2), bcol = im.b_col0[rb] + ra * (OZ_T / 2);   // my half of each shared tile
+        for (int chunk = im.chunk_begin; chunk < im.chunk_end; ++chunk) {
+          int jnext = OZ_S - 1;
+          for (int a = g.amin; a < OZ_S; ++a) {
+            const int jlo = max(g.smin, g.lmin - a);
+            while (jnext >= jlo) {
+              const uint32_t s = qb % OZ_NB;
+              if (qb >= OZ_NB) mbar_wait(emptyB + 8 * s, ((qb / OZ_NB) - 1) & 1);
+              mbar_expect_tx(fullB + 8 * s, OZ_TILE);
+              tma_load_4d_mc(sbase + s * OZ_TILE + ra * (OZ_TILE / 2), tb, fullB + 8 * s, 0, bcol, jnext, chunk, maskB);
+              ++qb; --jnext;
+            }
+            const uint32_t s = qa % OZ_NA;
+            if (qa >= OZ_NA) mbar_wait(emptyA + 8 * s, ((qa / OZ_NA) - 1) & 1);
+            mbar_expect_tx(fullA + 8 * s, OZ_TILE);
+            tma_load_4d_mc(sbase + (OZ_NB + s) * OZ_TILE + rb * (OZ_TILE / 2), &tmA, fullA + 8 * s, 0, acol, a, chunk, maskA);
+            ++qa;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      OzRing rga{0, 0}, rgb{0, 0};
+      uint32_t segs = 0;
+      for (int it = it0; it < it1; ++it) {
+        const OzCItem im = items[it];
+        const uint32_t idesc = oz_idesc(im.n16[rb]);
+        for (int seg0 = im.chunk_begin; seg0 < im.chunk_end; seg0 += OZ_SEG, ++segs) {
+          const int seg1 = min(im.chunk_end, seg0 + OZ_SEG);
+          if (segs > 0) mbar_wait(bar_acce, (segs - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          uint32_t level_init = 0;
+          if (im.group) {
+            for (int chunk = seg0; chunk < seg1; ++chunk)
+              oz_mma_chunk_c<0, 0, 6, 8>(sbase, fullA, emptyA, fullB, emptyB, tmem, idesc, rga, rgb, level_init, maskA, maskB);
+          } else {
+            for (int chunk = seg0; chunk < seg1; ++chunk)
+              oz_mma_chunk_c<3, 3, 9, 12>(sbase, fullA, emptyA, fullB, emptyB, tmem, idesc, rga, rgb, level_init, maskA, maskB);
+          }
+          umma_commit(bar_accf);
+        }
+      }
+    }
+  } else {
+    const int lq = warp & 3;
+    const int row = lq * 32 + lane;
+    uint32_t segs = 0;
+    for (int it = it0; it < it1; ++it) {
+      const OzCItem im = items[it];
+      const int nlev = im.group ? 3 : 4;
+      const int n16 = im.n16[rb];
+      long long* p0 = part + ((int64_t)it * 4 + rank) * (4 * OZ_T * OZ_T) + row;
+      for (int seg0 = im.chunk_begin; seg0 < im.chunk_end; seg0 += OZ_SEG, ++segs) {
+        mbar_wait(bar_accf, segs & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const bool first = seg0 == im.chunk_begin;
+        for (int lev = 0; lev < nlev; ++lev)
+          for (int cq = 0; cq * 32 < n16; ++cq) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(lev * OZ_T + cq * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            long long* p = p0 + (int64_t)(lev * OZ_T + cq * 32) * OZ_T;
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              const long long add = (long long)(int32_t)v[i];
+              p[(int64_t)i * OZ_T] = first ? add : p[(int64_t)i * OZ_T] + add;
+            }
+          }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        mbar_arrive(bar_acce);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves while a partner may still multicast into it or signal its barriers
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
+}
+
 // G[g_row0 + r, g_col0 + c] = 2^(eA + eB - 110) * sum_L 256^L * (sum over the items of the tile of level L)
 __global__ void __launch_bounds__(256)
-    oz_reduce_kernel(const long long* __restrict__ part, const OzTile* __restrict__ tiles, const OzItem* __restrict__ items,
-                     const int* __restrict__ eA, const int* __restrict__ eB0, const int* __restrict__ eB1, double* __restrict__ G0,
-                     int ldg0, double* __restrict__ G1, int ldg1, int mirror) {
+    oz_reduce_kernel(const long long* __restrict__ part, const OzTile* __restrict__ tiles, const int* __restrict__ item_group,
+                     int slot_mul, const int* __restrict__ eA, const int* __restrict__ eB0, const int* __restrict__ eB1,
+                     double* __restrict__ G0, int ldg0, double* __restrict__ G1, int ldg1, int mirror) {
   const OzTile t = tiles[blockIdx.x];
   double* __restrict__ G = t.b_sel ? G1 : G0;
   const int ldg = t.b_sel ? ldg1 : ldg0;
@@ -386,9 +601,9 @@ __global__ void __launch_bounds__(256)
     const int r = idx % t.a_cols, c = idx / t.a_cols;
     if (t.diag && r > c) continue;
     long long lev[7] = {0, 0, 0, 0, 0, 0, 0};   // levels 6..12
-    for (int k = t.first; k < t.last; k++) {
-      const int grp = items[k].group;
-      const long long* p = part + (int64_t)k * (4 * OZ_T * OZ_T) + r + (int64_t)c * OZ_T;
+    for (int k = t.first; k < t.last; k += (t.stride ? t.stride : 1)) {
+      const int grp = item_group[k];
+      const long long* p = part + ((int64_t)k * slot_mul + t.rank) * (4 * OZ_T * OZ_T) + r + (int64_t)c * OZ_T;
       const int nl = grp ? 3 : 4, l0 = grp ? 0 : 3;
       for (int l = 0; l < nl; l++) lev[l0 + l] += p[(int64_t)l * OZ_T * OZ_T];
     }
@@ -397,7 +612,7 @@ __global__ void __launch_bounds__(256)
     for (int l = 0; l < 7; l++) s += ldexp((double)lev[l], 8 * l);   // smallest level first; 2^48 of the level-6 weight is in the scale
     const double val = ldexp(s, eA[t.a_col0 + r] + eB[t.b_col0 + c] - 2 * OZ_SHIFT + 48);
     G[(t.g_row0 + r) + (int64_t)(t.g_col0 + c) * ldg] = val;
-    if (mirror && t.diag >= 0 && (t.g_row0 + r) != (t.g_col0 + c)) G[(t.g_col0 + c) + (int64_t)(t.g_row0 + r) * ldg] = val;
+    if (mirror && (t.g_row0 + r) != (t.g_col0 + c)) G[(t.g_col0 + c) + (int64_t)(t.g_row0 + r) * ldg] = val;
   }
 }
 
@@ -445,7 +660,7 @@ int oz_split(lb2_ctx* ctx, int64_t n, int m, const double* X, int64_t ld, int8_t
 struct OzPlanTile { OzTile t; double w; };   // w: relative MMA cost of one chunk of the whole tile (both groups)
 
 // tiles x {lo, hi} laid end to end weighted by their MMA count, cut into ncta equal pieces (chunk granularity)
-void oz_schedule(std::vector<OzPlanTile>& tiles, int64_t nch, int ncta, double load_w, std::vector<OzItem>& items,
+void oz_schedule(std::vector<OzPlanTile>& tiles, int64_t nch, int ncta, double load_w, int lockstep, std::vector<OzItem>& items,
                  std::vector<int>& cta_first) {
   struct Unit { int tile, group; double cost; };
   std::vector<Unit> units;
@@ -455,6 +670,45 @@ void oz_schedule(std::vector<OzPlanTile>& tiles, int64_t nch, int ncta, double l
     const double nfrac = ((tiles[i].t.b_cols + 15) / 16 * 16) / 128.0;
     units.push_back({(int)i, 0, std::max(10.0 * nfrac, 8.0 * load_w)});
     units.push_back({(int)i, 1, std::max(18.0 * nfrac, 14.0 * load_w)});
+  }
+  // LOCK-STEP COHORTS (lockstep != 0): every unit gets its own CTAs — P_lo per lo unit, P_hi per hi unit, each covering an equal
+  // share of the rows from its start.  All CTAs of a cohort (same group, same row share) run the same instruction stream over
+  // the same rows at the same time, so a slice tile that several output tiles need is fetched from DRAM by whichever CTA gets
+  // there first and comes out of L2 for the others (a CTA that runs ahead pays the DRAM latency and is caught up).  The equal-cost
+  // cut below balances the work better but lets every CTA stream its own pieces from DRAM (ncu: 110 GB read for 26 GB of slices).
+  if (lockstep) {
+    const int nt = (int)tiles.size();
+    int best_lo = 0, best_hi = 0;
+    double best = 1e300;
+    for (int plo = 1; plo <= 8; plo++)
+      for (int phi = 1; phi <= 16; phi++) {
+        if ((int64_t)nt * (plo + phi) > ncta) continue;
+        const double tmax = std::max(10.0 / plo, 18.0 / phi);
+        if (tmax < best - 1e-12) { best = tmax; best_lo = plo; best_hi = phi; }
+      }
+    if (best_lo > 0 && nch >= 8 * best_hi) {
+      cta_first.assign(ncta + 1, 0);
+      int cta = 0;
+      for (int grp = 0; grp < 2; grp++) {          // cohorts are laid out group by group: neighbours in launch order share rows
+        const int P = grp ? best_hi : best_lo;
+        for (int pc = 0; pc < P; pc++)
+          for (int i = 0; i < nt; i++) {
+            OzTile& t = tiles[i].t;
+            OzItem im{};
+            im.chunk_begin = (int32_t)(nch * pc / P); im.chunk_end = (int32_t)(nch * (pc + 1) / P);
+            im.a_col0 = t.a_col0; im.b_col0 = t.b_col0; im.b_sel = t.b_sel;
+            im.n16 = (t.b_cols + 15) / 16 * 16;
+            im.group = grp;
+            im.tile = i;
+            cta_first[cta++] = (int)items.size();
+            items.push_back(im);
+          }
+      }
+      for (int b = cta; b <= ncta; b++) cta_first[b] = (int)items.size();
+      // the items of tile i are i, i + nt, i + 2 nt, ...
+      for (int i = 0; i < nt; i++) { tiles[i].t.first = i; tiles[i].t.stride = nt; tiles[i].t.last = (int)items.size(); }
+      return;
+    }
   }
   double total = 0;
   for (auto& u : units) total += u.cost * (double)nch;
@@ -532,11 +786,13 @@ int oz_run(lb2_ctx* ctx, int64_t n, std::vector<OzPlanTile>& tiles, OzOperand (&
   std::vector<OzItem> items;
   std::vector<int> cta_first;
   const int ncta = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, (int64_t)tiles.size() * 2 * nch / 8));
-  oz_schedule(tiles, nch, ncta, 0.01 * (ctx->oz_load_pct > 0 ? ctx->oz_load_pct : 100), items, cta_first);
+  oz_schedule(tiles, nch, ncta, 0.01 * (ctx->oz_load_pct > 0 ? ctx->oz_load_pct : 100), ctx->oz_lockstep, items, cta_first);
   const size_t nitems = items.size();
   const size_t o_part = o_rest, o_items = o_part + al(sizeof(long long) * nitems * 4 * OZ_T * OZ_T),
                o_cta = o_items + al(sizeof(OzItem) * nitems), o_tiles = o_cta + al(sizeof(int) * (ncta + 1)),
-               total = o_tiles + al(sizeof(OzTile) * tiles.size());
+               o_grp = o_tiles + al(sizeof(OzTile) * tiles.size()), total = o_grp + al(sizeof(int) * nitems);
+  std::vector<int> grp;
+  for (auto& im : items) grp.push_back(im.group);
   if (total > ctx->oz_bytes) return -3;   // the caller sized the buffer with oz_rest_bytes()
   long long* part = (long long*)(buf + o_part);
   std::vector<OzTile> tl;
@@ -544,6 +800,7 @@ int oz_run(lb2_ctx* ctx, int64_t n, std::vector<OzPlanTile>& tiles, OzOperand (&
   LB2_CUDA_OK(cudaMemcpyAsync(buf + o_items, items.data(), sizeof(OzItem) * nitems, cudaMemcpyHostToDevice, ctx->stream));
   LB2_CUDA_OK(cudaMemcpyAsync(buf + o_cta, cta_first.data(), sizeof(int) * (ncta + 1), cudaMemcpyHostToDevice, ctx->stream));
   LB2_CUDA_OK(cudaMemcpyAsync(buf + o_tiles, tl.data(), sizeof(OzTile) * tl.size(), cudaMemcpyHostToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaMemcpyAsync(buf + o_grp, grp.data(), sizeof(int) * nitems, cudaMemcpyHostToDevice, ctx->stream));
   LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   const bool timing = lb2_gram_i8_mode(ctx) == 2;   // debug: per-phase device times on stderr
@@ -565,7 +822,7 @@ int oz_run(lb2_ctx* ctx, int64_t n, std::vector<OzPlanTile>& tiles, OzOperand (&
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
   if (timing) cudaEventRecord(ev[2], ctx->stream);
-  oz_reduce_kernel<<<dim3((unsigned)tl.size(), 8), 256, 0, ctx->stream>>>(part, (const OzTile*)(buf + o_tiles), (const OzItem*)(buf + o_items),
+  oz_reduce_kernel<<<dim3((unsigned)tl.size(), 8), 256, 0, ctx->stream>>>(part, (const OzTile*)(buf + o_tiles), (const int*)(buf + o_grp), 1,
                                                                           op[0].e, op[1].e, op[nop > 2 ? 2 : 1].e, G0, ldg0, G1, ldg1, mirror);
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
@@ -580,10 +837,176 @@ int oz_run(lb2_ctx* ctx, int64_t n, std::vector<OzPlanTile>& tiles, OzOperand (&
   }
   return 0;
 }
+// 64-column boxes for the cluster kernel (each CTA fetches half of a shared slice tile)
+int oz_make_map64(CUtensorMap* tm, const int8_t* base, int m, int64_t nch) {
+  EncodeTiledFn enc = oz_encode_tiled();
+  if (!enc) return -100;
+  const cuuint64_t dims[4] = {(cuuint64_t)OZ_CH, (cuuint64_t)m, (cuuint64_t)OZ_S, (cuuint64_t)nch};
+  const cuuint64_t strides[3] = {(cuuint64_t)OZ_CH, (cuuint64_t)OZ_CH * m, (cuuint64_t)OZ_CH * m * OZ_S};
+  const cuuint32_t box[4] = {(cuuint32_t)OZ_CH, (cuuint32_t)(OZ_T / 2), 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -100;
+}
+
+struct OzPanel { int col0, cols, sel, valid; };     // a 128-column panel of an operand (sel: which B slice array)
+struct OzSuper {                                    // 2 x 2 super-tile: A panels pa[0..1] x B panels pb[0..1]
+  OzPanel pa[2], pb[2];
+  int g_row0[2], g_col0[2];
+  int valid[2][2];                                  // which of the four tiles are wanted
+};
+
+// number of 4-CTA clusters of the cluster kernel that can be resident at once (0: clusters not available)
+int oz_max_clusters(lb2_ctx* ctx) {
+  if (ctx->oz_clusters >= 0) return ctx->oz_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(4 * 64); cfg.blockDim = dim3(OZ_NT); cfg.dynamicSmemBytes = OZ_SMEM; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int ncl = 0;
+  if (cudaFuncSetAttribute(oz_gram_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&ncl, oz_gram_cluster_kernel, &cfg) != cudaSuccess)
+    ncl = 0;
+  cudaGetLastError();
+  ctx->oz_clusters = ncl;
+  return ncl;
+}
+
+int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOperand (&op)[3], int nop, double* G0, int ldg0, double* G1,
+                   int ldg1, int8_t* buf, size_t o_rest, unsigned long long* mx, int ncl_max) {
+  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
+  auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  const double load_w = 0.01 * (ctx->oz_load_pct > 0 ? ctx->oz_load_pct : 100);
+  // units: (super-tile, group); a cluster advances at the pace of its slowest CTA; each CTA pulls HALF boxes
+  struct Unit { int st, group; double cost; };
+  std::vector<Unit> units;
+  for (size_t i = 0; i < supers.size(); i++) {
+    const int nmax = std::max(supers[i].pb[0].cols, supers[i].pb[1].cols);
+    const double nfrac = ((nmax + 15) / 16 * 16) / 128.0;
+    units.push_back({(int)i, 0, std::max(10.0 * nfrac, 4.0 * load_w)});
+    units.push_back({(int)i, 1, std::max(18.0 * nfrac, 7.0 * load_w)});
+  }
+  const int ncl = (int)std::min<int64_t>(ncl_max, std::max<int64_t>(1, (int64_t)units.size() * nch / 8));
+  double total = 0;
+  for (auto& u : units) total += u.cost * (double)nch;
+  const double L = total / ncl;
+  std::vector<OzCItem> items;
+  std::vector<int> item_cl, grp, cl_first(ncl + 1, 0);
+  std::vector<std::pair<int, int>> unit_items(units.size());
+  double U = 0;
+  for (size_t ui = 0; ui < units.size(); ui++) {
+    const Unit& u = units[ui];
+    const OzSuper& st = supers[u.st];
+    unit_items[ui].first = (int)items.size();
+    const double span = u.cost * (double)nch;
+    const int b_lo = std::min(std::max((int)std::floor(U / L), 0), ncl - 1), b_hi = std::min(std::max((int)std::floor((U + span) / L), 0), ncl - 1);
+    auto boundary = [&](int b) -> int64_t {
+      if (b <= b_lo) return 0;
+      if (b > b_hi) return nch;
+      int64_t r = (int64_t)std::llround(((double)b * L - U) / u.cost);
+      if (r < 4) r = 0;
+      if (nch - r < 4) r = nch;
+      return std::min<int64_t>(std::max<int64_t>(r, 0), nch);
+    };
+    for (int b = b_lo; b <= b_hi; b++) {
+      const int64_t c0 = boundary(b), c1 = boundary(b + 1);
+      if (c1 <= c0) continue;
+      OzCItem im{};
+      im.chunk_begin = (int32_t)c0; im.chunk_end = (int32_t)c1; im.group = u.group;
+      for (int h = 0; h < 2; h++) {
+        im.a_col0[h] = st.pa[h].col0;
+        im.b_col0[h] = st.pb[h].col0; im.b_sel[h] = st.pb[h].sel; im.n16[h] = (st.pb[h].cols + 15) / 16 * 16;
+      }
+      items.push_back(im);
+      item_cl.push_back(b);
+      grp.push_back(u.group);
+    }
+    unit_items[ui].second = (int)items.size();
+    U += span;
+  }
+  size_t it = 0;
+  for (int b = 0; b < ncl; b++) {
+    while (it < items.size() && item_cl[it] < b) it++;
+    cl_first[b] = (int)it;
+  }
+  cl_first[ncl] = (int)items.size();
+  // output tiles: the wanted members of every super-tile (items of both groups are adjacent: units 2 i and 2 i + 1)
+  std::vector<OzTile> tl;
+  for (size_t i = 0; i < supers.size(); i++)
+    for (int ia = 0; ia < 2; ia++)
+      for (int ib = 0; ib < 2; ib++) {
+        if (!supers[i].valid[ia][ib]) continue;
+        OzTile t{};
+        t.a_col0 = supers[i].pa[ia].col0; t.a_cols = supers[i].pa[ia].cols;
+        t.b_col0 = supers[i].pb[ib].col0; t.b_cols = supers[i].pb[ib].cols; t.b_sel = supers[i].pb[ib].sel;
+        t.g_row0 = supers[i].g_row0[ia]; t.g_col0 = supers[i].g_col0[ib];
+        t.first = unit_items[2 * i].first; t.last = unit_items[2 * i + 1].second;
+        t.rank = ia * 2 + ib;
+        t.diag = 0;
+        tl.push_back(t);
+      }
+  const size_t nitems = items.size();
+  const size_t o_part = o_rest, o_items = o_part + al(sizeof(long long) * nitems * 4 * 4 * OZ_T * OZ_T),
+               o_cl = o_items + al(sizeof(OzCItem) * nitems), o_tiles = o_cl + al(sizeof(int) * (ncl + 1)),
+               o_grp = o_tiles + al(sizeof(OzTile) * tl.size()), totalb = o_grp + al(sizeof(int) * nitems);
+  if (totalb > ctx->oz_bytes) return -3;
+  long long* part = (long long*)(buf + o_part);
+  LB2_CUDA_OK(cudaMemcpyAsync(buf + o_items, items.data(), sizeof(OzCItem) * nitems, cudaMemcpyHostToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaMemcpyAsync(buf + o_cl, cl_first.data(), sizeof(int) * (ncl + 1), cudaMemcpyHostToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaMemcpyAsync(buf + o_tiles, tl.data(), sizeof(OzTile) * tl.size(), cudaMemcpyHostToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaMemcpyAsync(buf + o_grp, grp.data(), sizeof(int) * nitems, cudaMemcpyHostToDevice, ctx->stream));
+  LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  const bool timing = lb2_gram_i8_mode(ctx) == 2;
+  if (timing) for (auto& e : ev) cudaEventCreate(&e);
+  if (timing) cudaEventRecord(ev[0], ctx->stream);
+  for (int q = 0; q < nop; q++)
+    if (op[q].X)
+      if (int rc = oz_split(ctx, n, op[q].m, op[q].X, op[q].ld, op[q].slices, op[q].e, mx)) return rc;
+  alignas(64) CUtensorMap tm[3];
+  for (int q = 0; q < 3; q++) {
+    const OzOperand& o = op[q < nop ? q : 0];
+    const OzOperand& src = o.X ? o : op[0];
+    if (oz_make_map64(&tm[q], src.slices, src.m, nch)) return -100;
+  }
+  if (timing) cudaEventRecord(ev[1], ctx->stream);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(4 * ncl); cfg.blockDim = dim3(OZ_NT); cfg.dynamicSmemBytes = OZ_SMEM; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    LB2_CUDA_OK(cudaFuncSetAttribute(oz_gram_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    LB2_CUDA_OK(cudaLaunchKernelEx(&cfg, oz_gram_cluster_kernel, tm[0], tm[1], tm[2], (const OzCItem*)(buf + o_items),
+                                   (const int*)(buf + o_cl), part));
+  }
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  if (timing) cudaEventRecord(ev[2], ctx->stream);
+  oz_reduce_kernel<<<dim3((unsigned)tl.size(), 8), 256, 0, ctx->stream>>>(part, (const OzTile*)(buf + o_tiles), (const int*)(buf + o_grp), 4,
+                                                                          op[0].e, op[1].e, op[nop > 2 ? 2 : 1].e, G0, ldg0, G1, ldg1, 0);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  if (timing) {
+    cudaEventRecord(ev[3], ctx->stream);
+    cudaEventSynchronize(ev[3]);
+    float t01 = 0, t12 = 0, t23 = 0;
+    cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
+    fprintf(stderr, "gram_i8 n=%lld, %zu super-tiles (%zu tiles): split %.2f ms, int8 cluster kernel %.2f ms (%zu items, %d clusters), reduce %.2f ms\n",
+            (long long)n, supers.size(), tl.size(), t01, t12, nitems, ncl, t23);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+  return 0;
+}
+
 // bytes behind the slices: partial sums (one 4-level slot per item, items <= 2 tiles + CTAs) and the schedule
 size_t oz_rest_bytes(lb2_ctx* ctx, size_t ntiles) {
   const size_t nitems = 2 * ntiles + (size_t)ctx->sm_count + 8;
-  return sizeof(long long) * nitems * 4 * OZ_T * OZ_T + (sizeof(OzItem) + sizeof(OzTile)) * nitems + 65536;
+  return sizeof(long long) * nitems * 4 * OZ_T * OZ_T + (sizeof(OzCItem) + sizeof(OzTile) + 64) * nitems + 65536;
 }
 
 }  // namespace
@@ -650,17 +1073,51 @@ int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, in
         tiles.push_back(pt);
       }
   if (tiles.empty()) return 0;
+  // 2 x 2 super-tiles for the cluster kernel: A panels paired in order, B panels paired as (W0 tile j, W1 tile j) (both products)
+  // or as neighbouring column tiles (one product); a missing partner repeats the panel and is not written out
+  std::vector<OzSuper> supers;
+  const int ncl_max = (ctx->oz_cluster != 0) ? oz_max_clusters(ctx) : 0;
+  if (ncl_max > 0) {
+    std::vector<OzPanel> pa, pb;
+    std::vector<int> pb_gcol, pb_tj;
+    for (auto& rw : rows) pa.push_back({rw.first, rw.second, 0, 1});
+    if (pa.size() % 2) { OzPanel d = pa.back(); d.valid = 0; pa.push_back(d); }
+    auto bpanel = [&](int q, int tj) { return OzPanel{tj * OZ_T + ((q == 0 && w0_in_s) ? tri_c0 : 0), std::min(OZ_T, nw - tj * OZ_T), q, 1}; };
+    if (nprod == 2) {
+      for (int tj = 0; tj < ntn; tj++)
+        for (int q = 0; q < 2; q++) { pb.push_back(bpanel(q, tj)); pb_gcol.push_back(tj * OZ_T); pb_tj.push_back(tj); }
+    } else {
+      for (int tj = 0; tj < ntn; tj++) { pb.push_back(bpanel(0, tj)); pb_gcol.push_back(tj * OZ_T); pb_tj.push_back(tj); }
+      if (pb.size() % 2) { OzPanel d = pb.back(); d.valid = 0; pb.push_back(d); pb_gcol.push_back(pb_gcol.back()); pb_tj.push_back(pb_tj.back()); }
+    }
+    for (size_t ia = 0; ia < pa.size(); ia += 2)
+      for (size_t ib = 0; ib < pb.size(); ib += 2) {
+        OzSuper st{};
+        bool any = false;
+        for (int x = 0; x < 2; x++) { st.pa[x] = pa[ia + x]; st.g_row0[x] = pa[ia + x].col0; }
+        for (int y = 0; y < 2; y++) { st.pb[y] = pb[ib + y]; st.g_col0[y] = pb_gcol[ib + y]; }
+        for (int x = 0; x < 2; x++)
+          for (int y = 0; y < 2; y++) {
+            const bool below = st.pa[x].col0 >= split && (st.pa[x].col0 - split) / OZ_T > pb_tj[ib + y];
+            st.valid[x][y] = (st.pa[x].valid && st.pb[y].valid && !below) ? 1 : 0;
+            any = any || st.valid[x][y];
+          }
+        if (any) supers.push_back(st);
+      }
+  }
   const size_t bS = al((size_t)nch * OZ_S * m * OZ_CH), bW0 = w0_in_s ? 0 : al((size_t)nch * OZ_S * nw * OZ_CH),
                bW1 = nprod == 2 ? al((size_t)nch * OZ_S * nw * OZ_CH) : 0;
   const size_t o_eS = bS + bW0 + bW1, o_e0 = o_eS + al(sizeof(int) * m), o_e1 = o_e0 + al(sizeof(int) * nw),
                o_mx = o_e1 + al(sizeof(int) * nw), o_rest = o_mx + al(sizeof(unsigned long long) * m);
-  int8_t* buf = oz_buffer(ctx, o_rest + oz_rest_bytes(ctx, tiles.size()));
+  int8_t* buf = oz_buffer(ctx, o_rest + std::max(oz_rest_bytes(ctx, tiles.size()), 4 * oz_rest_bytes(ctx, supers.size())));
   if (!buf) return -1;
   int* eS = (int*)(buf + o_eS);
   OzOperand op[3] = {{S, lds, m, buf, eS},
                      {w0_in_s ? nullptr : W0, ldw0, nw, w0_in_s ? buf : buf + bS, w0_in_s ? eS : (int*)(buf + o_e0)},
                      {nprod == 2 ? W1 : nullptr, ldw1, nw, buf + bS + bW0, (int*)(buf + o_e1)}};
   // the reduce kernel indexes the exponents with the tile's b_col0, which already carries tri_c0 for an aliased W0
+  if (!supers.empty())
+    return oz_run_cluster(ctx, n, supers, op, nprod == 2 ? 3 : 2, G0, ldg0, G1, ldg1, buf, o_rest, (unsigned long long*)(buf + o_mx), ncl_max);
   return oz_run(ctx, n, tiles, op, nprod == 2 ? 3 : 2, G0, ldg0, G1, ldg1, 0, buf, o_rest, (unsigned long long*)(buf + o_mx));
 }
 

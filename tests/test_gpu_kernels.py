@@ -627,14 +627,17 @@ def test_gram_cols_i8_matches_dmma_path(ctx, shape):
     keep = ~(i - mxp > j)
     ctx.set_option("gram_i8", 1)
     try:
-        for dW in (dS.cols(mxp, nw), dWsep):
-            G0, G1 = api.gram_cols(ctx, dS, dW, dAW, tri_c0=mxp)
-            assert (np.abs(G0.numpy(ctx) - ref0) / sc0)[keep].max() < 2e-14
-            assert (np.abs(G1.numpy(ctx) - ref1) / sc1)[keep].max() < 2e-14
-        G0, _ = api.gram_cols(ctx, dS, dAW, None, tri_c0=mxp)
-        assert (np.abs(G0.numpy(ctx) - ref1) / sc1)[keep].max() < 2e-14
+        # one tile per CTA in lock-step cohorts (default), with the equal-cost cut, and the 4-CTA cluster kernel (multicast tiles)
+        for lockstep, cluster in ((1, 0), (0, 0), (1, 1)):
+            ctx.set_option("oz_lockstep", lockstep); ctx.set_option("oz_cluster", cluster)
+            for dW in (dS.cols(mxp, nw), dWsep):
+                G0, G1 = api.gram_cols(ctx, dS, dW, dAW, tri_c0=mxp)
+                assert (np.abs(G0.numpy(ctx) - ref0) / sc0)[keep].max() < 2e-14
+                assert (np.abs(G1.numpy(ctx) - ref1) / sc1)[keep].max() < 2e-14
+            G0, _ = api.gram_cols(ctx, dS, dAW, None, tri_c0=mxp)
+            assert (np.abs(G0.numpy(ctx) - ref1) / sc1)[keep].max() < 2e-14
     finally:
-        ctx.set_option("gram_i8", 0)
+        ctx.set_option("gram_i8", 0); ctx.set_option("oz_lockstep", 1); ctx.set_option("oz_cluster", 0)
 
 
 # ------------------------------------------------------------------------------------------------ windowed CSR kernel
