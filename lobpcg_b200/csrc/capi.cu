@@ -275,6 +275,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "oz_load_pct")) c->oz_load_pct = value;
   else if (!strcmp(key, "oz_cluster")) c->oz_cluster = value;
   else if (!strcmp(key, "oz_lockstep")) c->oz_lockstep = value;
+  else if (!strcmp(key, "nn_i8")) c->nn_i8 = value;
   else if (!strcmp(key, "oz_clusters")) c->oz_clusters = value;
   else if (!strcmp(key, "gram_tma")) c->gram_tma = value;
   else if (!strcmp(key, "gram_load_pct")) c->gram_load_pct = value;

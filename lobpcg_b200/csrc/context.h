@@ -19,6 +19,11 @@ struct lb2_ctx {
   // int8 slices, exponents and partial sums of the Ozaki-split f64 Gram (gram_i8.cu); sized exactly, kept between calls
   void* oz_buf = nullptr;
   size_t oz_bytes = 0;
+  // the block whose slices sit at the start of oz_buf (left by the last column-block Gram; reused by the projections of the pass)
+  const void* oz_tag_ptr = nullptr;
+  int64_t oz_tag_n = 0, oz_tag_ld = 0;
+  int oz_tag_m = 0;
+  size_t oz_tag_e_off = 0;
   // small-dense library handles (created lazily)
   cublasHandle_t cublas = nullptr;
   cusolverDnHandle_t cusolver = nullptr;
@@ -45,6 +50,7 @@ struct lb2_ctx {
   void* gram_wl_cols_cache = nullptr;   // lb2::WlColsCache* (schedules of the column-block products, gram_wl_cols_f64)
   int gram_i8 = 0;       // f64 Gram through tcgen05 kind::i8 on an Ozaki split (gram_i8.cu): 1 = on, 0 = DMMA kernels (default)
   int gram_i8_env = -1;  // LB2_GRAM_I8 as seen by the last solver set-up (-1 = unset); overrides gram_i8 for the drop-in entry points
+  int nn_i8 = 1;         // with gram_i8 on: projections Out = S C (alpha 1, beta 0) on the int8 tensor path too (0 = DMMA kernel)
   int oz_lockstep = 1;   // gram_i8 one-tile-per-CTA kernel: 1 = lock-step cohorts (every (tile, level group) has its own CTAs), 0 = equal-cost cut
   int oz_cluster = 0;    // gram_i8 column-block products: 1 = 4-CTA clusters with multicast slice tiles (r02: 110 ms against 90 ms of the one-tile-per-CTA kernel at the C5 shape), 0 = one tile per CTA
   int oz_clusters = -1;  // resident clusters of the cluster kernel (queried once; option: force a count)

@@ -34,6 +34,7 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#include <climits>
 #include <cuda.h>
 
 #include "common.cuh"
@@ -587,6 +588,208 @@ __global__ void __launch_bounds__(OZ_NT, 1)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------- projection (tall NN)
+// Out (n x nb) = S C on the same slices: the contraction now runs over the COLUMNS of S, so a slice tile of S — the very box
+// the Gram kernels load, (128 rows of a chunk) x (128 columns) — is read as an MN-major operand (M = rows contiguous, K =
+// columns; instruction-descriptor bit 15).  The column exponents of S are folded into the small matrix: C'[c, j] = 2^eS[c] C[c, j]
+// is split into 7 slices with one exponent f[j] per output column (oz_cprep_kernel), laid out K-major like the Gram operands.
+// A CTA owns row chunks and a 64-column output tile: 7 level accumulators x 64 columns fit TMEM (448 of 512 columns), so all
+// 28 slice products of a K chunk run in one pass (tile order B0 .. B6 A6 A5 ... A0, A_a x B_j for j >= 6 - a).  The CTAs that
+// share a row chunk (one per output tile) form a lock-step cohort: the slices of S come from DRAM once and from L2 for the rest.
+constexpr int ON_NA = 7, ON_NB = 10;                    // ring slots: A tiles 16 KB, B tiles 8 KB (B slots first)
+constexpr uint32_t ON_BT = OZ_TILE / 2;                 // B tile: 64 output columns x 128 B of k
+constexpr uint32_t ON_BAR = ON_NB * ON_BT + ON_NA * OZ_TILE;
+constexpr uint32_t ON_SMEM = ON_BAR + 1024 + 1024;
+constexpr int ON_TN = 64;
+
+// slices of C' = diag(2^eS) C: one CTA per output column j.  out[((kc * 7 + s) * nb + j) * 128 + (c % 128)], zero beyond kd.
+__global__ void __launch_bounds__(128)
+    oz_cprep_kernel(const double* __restrict__ C, int ldc, int kd, int nb, const int* __restrict__ eS, int8_t* __restrict__ out,
+                    int* __restrict__ f, int nkc) {
+  const int j = blockIdx.x;
+  __shared__ int smax[4];
+  // largest binary exponent of |C[c, j]| 2^eS[c]: frexp exponent + eS (a zero entry contributes nothing)
+  int mx = INT_MIN;
+  for (int c = threadIdx.x; c < kd; c += 128) {
+    const double v = C[c + (int64_t)j * ldc];
+    if (v != 0.0) {
+      int ex;
+      frexp(v, &ex);                       // |v| = m 2^ex, m in [0.5, 1)
+      mx = max(mx, ex + eS[c]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = max(max(smax[0], smax[1]), max(smax[2], smax[3]));
+  const int fj = (mx == INT_MIN) ? 0 : max(-900, min(900, mx + 1));      // every |C'| < 2^(fj - 1)
+  if (threadIdx.x == 0) f[j] = fj;
+  for (int c = threadIdx.x; c < nkc * OZ_CH; c += 128) {
+    long long N = 0;
+    if (c < kd) N = __double2ll_rn(ldexp(C[c + (int64_t)j * ldc], eS[c] + OZ_SHIFT - fj));
+    int8_t* o = out + (((int64_t)(c / OZ_CH) * OZ_S) * nb + j) * OZ_CH + (c % OZ_CH);
+#pragma unroll
+    for (int i = 0; i < OZ_S; i++) {
+      const int d = (int)(int8_t)(N & 0xFF);
+      N = (N - d) >> 8;
+      o[(int64_t)i * nb * OZ_CH] = (int8_t)d;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t on_idesc(int n16) {   // as oz_idesc, A operand MN-major
+  return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(n16 >> 3) << 17) | ((uint32_t)(OZ_T >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(OZ_NT, 1)
+    oz_nn_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmC, const int* __restrict__ f,
+                 double* __restrict__ Out, int64_t ldo, int64_t n, int nb, int nkc, int64_t nch, int njt, int ncoh) {
+  extern __shared__ __align__(1024) unsigned char smem_oz[];
+  const uint32_t sbase = (smem_u32(smem_oz) + 1023u) & ~1023u;
+  unsigned char* gbase = smem_oz + (sbase - smem_u32(smem_oz));
+  const uint32_t abase0 = sbase + ON_NB * ON_BT;
+  const uint32_t fullB = sbase + ON_BAR, emptyB = fullB + 8 * ON_NB, fullA = emptyB + 8 * ON_NB, emptyA = fullA + 8 * ON_NA,
+                 bar_accf = emptyA + 8 * ON_NA, bar_acce = bar_accf + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + ON_BAR + 8 * (2 * ON_NA + 2 * ON_NB + 2) + 8);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // CTA = (cohort, output tile): cohort c takes row chunks c, c + ncoh, ...; launch order puts the members of a cohort side by side
+  const int jt = blockIdx.x % njt, coh = blockIdx.x / njt;
+  const int j0 = jt * ON_TN;
+  const int ncols = min(ON_TN, nb - j0);
+  const int n16 = (ncols + 15) / 16 * 16;
+
+  if (tid == 0) {
+    for (int s = 0; s < ON_NB; s++) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
+    for (int s = 0; s < ON_NA; s++) { mbar_init(fullA + 8 * s, 1); mbar_init(emptyA + 8 * s, 1); }
+    mbar_init(bar_accf, 1);
+    mbar_init(bar_acce, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmS) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmC) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32((const void*)tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t qa = 0, qb = 0;
+      for (int64_t rc = coh; rc < nch; rc += ncoh)
+        for (int kc = 0; kc < nkc; ++kc) {
+          // all seven B slices first (the first step, A slice 6, multiplies every one of them), then A slices 6 .. 0
+          for (int j = 0; j < OZ_S; ++j) {
+            const uint32_t s = qb % ON_NB;
+            if (qb >= ON_NB) mbar_wait(emptyB + 8 * s, ((qb / ON_NB) - 1) & 1);
+            mbar_expect_tx(fullB + 8 * s, ON_BT);
+            tma_load_4d(sbase + s * ON_BT, &tmC, fullB + 8 * s, 0, j0, j, kc);
+            ++qb;
+          }
+          for (int a = OZ_S - 1; a >= 0; --a) {
+            const uint32_t s = qa % ON_NA;
+            if (qa >= ON_NA) mbar_wait(emptyA + 8 * s, ((qa / ON_NA) - 1) & 1);
+            mbar_expect_tx(fullA + 8 * s, OZ_TILE);
+            tma_load_4d(abase0 + s * OZ_TILE, &tmS, fullA + 8 * s, 0, kc * OZ_T, a, (int32_t)rc);
+            ++qa;
+          }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = on_idesc(n16);
+      OzRing rga{0, 0}, rgb{0, 0};
+      uint32_t segs = 0;
+      for (int64_t rc = coh; rc < nch; rc += ncoh, ++segs) {
+        if (segs > 0) mbar_wait(bar_acce, (segs - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        for (int kc = 0; kc < nkc; ++kc) {
+          // A slices in DESCENDING order: step a multiplies B slices 6 - a .. 6 (level a + j - 6) and is the last use of B slice
+          // 6 - a, so the B slots drain one by one during the chunk and the next chunk's B slices stream in behind them
+          uint32_t sB[OZ_S];
+#pragma unroll
+          for (int j = 0; j < OZ_S; ++j) {
+            sB[j] = rgb.slot;
+            mbar_wait(fullB + 8 * rgb.slot, rgb.par);
+            if (++rgb.slot == ON_NB) { rgb.slot = 0; rgb.par ^= 1u; }
+          }
+#pragma unroll
+          for (int a = OZ_S - 1; a >= 0; --a) {
+            const uint32_t sA = rga.slot;
+            mbar_wait(fullA + 8 * sA, rga.par);
+            if (++rga.slot == ON_NA) { rga.slot = 0; rga.par ^= 1u; }
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t a_lo = (abase0 + sA * OZ_TILE) >> 4;
+            const uint32_t init = (kc == 0 && a == OZ_S - 1) ? 0u : 1u;   // the first step touches every level once
+#pragma unroll
+            for (int j = 0; j < OZ_S; ++j)
+              if (j >= OZ_S - 1 - a) {
+                const uint32_t acc = tmem + (uint32_t)((a + j - (OZ_S - 1)) * ON_TN);
+                const uint32_t b_lo = (sbase + sB[j] * ON_BT) >> 4;
+#pragma unroll
+                for (int ks = 0; ks < OZ_CH / 32; ks++) umma_i8(acc, a_lo + 256u * ks, b_lo + 2u * ks, idesc, ks > 0 ? 1u : init);
+              }
+            umma_commit(emptyA + 8 * sA);
+            umma_commit(emptyB + 8 * sB[OZ_S - 1 - a]);
+          }
+        }
+        umma_commit(bar_accf);
+      }
+    }
+  } else {
+    const int lq = warp & 3;
+    const int rr = lq * 32 + lane;
+    uint32_t segs = 0;
+    for (int64_t rc = coh; rc < nch; rc += ncoh, ++segs) {
+      mbar_wait(bar_accf, segs & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const int64_t row = rc * OZ_CH + rr;
+      for (int cq = 0; cq * 32 < n16; ++cq) {
+        double sum[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) sum[i] = 0.0;
+#pragma unroll
+        for (int lev = 0; lev < OZ_S; ++lev) {       // smallest level first
+          uint32_t v[32];
+          const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(lev * ON_TN + cq * 32);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          const double w = __longlong_as_double((long long)(1023 + 8 * lev) << 52);   // 2^(8 lev)
+#pragma unroll
+          for (int i = 0; i < 32; i++) sum[i] = fma((double)(int32_t)v[i], w, sum[i]);
+        }
+        if (row < n) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const int col = j0 + cq * 32 + i;
+            // 2^(f - 62) as an exact double (f is clamped far inside the exponent range by the split)
+            if (col < nb) Out[row + (int64_t)col * ldo] = sum[i] * __longlong_as_double((long long)(1023 + f[col] - 2 * OZ_SHIFT + 48) << 52);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      mbar_arrive(bar_acce);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
+}
+
 // G[g_row0 + r, g_col0 + c] = 2^(eA + eB - 110) * sum_L 256^L * (sum over the items of the tile of level L)
 __global__ void __launch_bounds__(256)
     oz_reduce_kernel(const long long* __restrict__ part, const OzTile* __restrict__ tiles, const int* __restrict__ item_group,
@@ -759,6 +962,7 @@ int8_t* oz_buffer(lb2_ctx* ctx, size_t bytes) {
   if (ctx->oz_buf) cudaFree(ctx->oz_buf);
   ctx->oz_buf = nullptr;
   ctx->oz_bytes = 0;
+  ctx->oz_tag_ptr = nullptr;
   if (cudaMalloc(&ctx->oz_buf, bytes) != cudaSuccess) {
     cudaGetLastError();
     fprintf(stderr, "lobpcg_b200: cannot allocate %zu bytes for the int8 slices\n", bytes);
@@ -1003,10 +1207,25 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
   return 0;
 }
 
+// 64-output-column boxes of the C' slices for the projection kernel
+int oz_make_map_c(CUtensorMap* tm, const int8_t* base, int nb, int nkc) {
+  EncodeTiledFn enc = oz_encode_tiled();
+  if (!enc) return -100;
+  const cuuint64_t dims[4] = {(cuuint64_t)OZ_CH, (cuuint64_t)nb, (cuuint64_t)OZ_S, (cuuint64_t)nkc};
+  const cuuint64_t strides[3] = {(cuuint64_t)OZ_CH, (cuuint64_t)OZ_CH * nb, (cuuint64_t)OZ_CH * nb * OZ_S};
+  const cuuint32_t box[4] = {(cuuint32_t)OZ_CH, (cuuint32_t)ON_TN, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -100;
+}
+
+constexpr size_t OZ_TAIL = (size_t)32 << 20;   // room behind every slice buffer for the projection's C' slices and exponents
+
 // bytes behind the slices: partial sums (one 4-level slot per item, items <= 2 tiles + CTAs) and the schedule
 size_t oz_rest_bytes(lb2_ctx* ctx, size_t ntiles) {
   const size_t nitems = 2 * ntiles + (size_t)ctx->sm_count + 8;
-  return sizeof(long long) * nitems * 4 * OZ_T * OZ_T + (sizeof(OzCItem) + sizeof(OzTile) + 64) * nitems + 65536;
+  return sizeof(long long) * nitems * 4 * OZ_T * OZ_T + (sizeof(OzCItem) + sizeof(OzTile) + 64) * nitems + 65536 + OZ_TAIL;
 }
 
 }  // namespace
@@ -1036,6 +1255,7 @@ int gram_i8_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_
                o_rest = o_mx + al(sizeof(unsigned long long) * std::max(ma, mb));
   int8_t* buf = oz_buffer(ctx, o_rest + oz_rest_bytes(ctx, tiles.size()));
   if (!buf) return -1;
+  ctx->oz_tag_ptr = nullptr;
   OzOperand op[3] = {{A, lda, ma, buf, (int*)(buf + o_eA)},
                      {same ? nullptr : B, ldb, mb, same ? buf : buf + bytesA, same ? (int*)(buf + o_eA) : (int*)(buf + o_eB)},
                      {nullptr, 0, 0, nullptr, nullptr}};
@@ -1112,6 +1332,8 @@ int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, in
   int8_t* buf = oz_buffer(ctx, o_rest + std::max(oz_rest_bytes(ctx, tiles.size()), 4 * oz_rest_bytes(ctx, supers.size())));
   if (!buf) return -1;
   int* eS = (int*)(buf + o_eS);
+  // the slices of S stay valid for the projections of this pass (tall_nn_i8_f64): same block, not written in between
+  ctx->oz_tag_ptr = S; ctx->oz_tag_n = n; ctx->oz_tag_m = m; ctx->oz_tag_ld = lds; ctx->oz_tag_e_off = o_eS;
   OzOperand op[3] = {{S, lds, m, buf, eS},
                      {w0_in_s ? nullptr : W0, ldw0, nw, w0_in_s ? buf : buf + bS, w0_in_s ? eS : (int*)(buf + o_e0)},
                      {nprod == 2 ? W1 : nullptr, ldw1, nw, buf + bS + bW0, (int*)(buf + o_e1)}};
@@ -1119,6 +1341,47 @@ int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, in
   if (!supers.empty())
     return oz_run_cluster(ctx, n, supers, op, nprod == 2 ? 3 : 2, G0, ldg0, G1, ldg1, buf, o_rest, (unsigned long long*)(buf + o_mx), ncl_max);
   return oz_run(ctx, n, tiles, op, nprod == 2 ? 3 : 2, G0, ldg0, G1, ldg1, 0, buf, o_rest, (unsigned long long*)(buf + o_mx));
+}
+
+// Out (n x nb) = S C (alpha = 1, beta = 0) on the int8 tensor path.  Uses the slices of S left by the last gram_cols_i8_f64 on the
+// same block (the solver's pass: Gram, then X = S Cx and P = S Cp); splits S itself otherwise.  -100 = not available.
+int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int64_t lds, const double* C, int ldc, double* Out,
+                   int64_t ldo) {
+  if (n >= ((int64_t)1 << 31) * OZ_CH || !oz_encode_tiled()) return -100;
+  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
+  auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  const int nkc = (kd + OZ_CH - 1) / OZ_CH;
+  const size_t c_bytes = al((size_t)nkc * OZ_S * nb * OZ_CH), need_tail = c_bytes + al(sizeof(int) * nb);
+  if (need_tail > OZ_TAIL) return -100;
+  const bool cached = ctx->oz_buf && ctx->oz_tag_ptr == S && ctx->oz_tag_n == n && ctx->oz_tag_m == kd && ctx->oz_tag_ld == lds;
+  int8_t* buf;
+  int* eS;
+  if (cached) {
+    buf = (int8_t*)ctx->oz_buf;
+    eS = (int*)(buf + ctx->oz_tag_e_off);
+  } else {
+    const size_t bS = al((size_t)nch * OZ_S * kd * OZ_CH), o_eS = bS, o_mx = o_eS + al(sizeof(int) * kd),
+                 tot = o_mx + al(sizeof(unsigned long long) * kd) + OZ_TAIL;
+    buf = oz_buffer(ctx, tot);
+    if (!buf) return -1;
+    eS = (int*)(buf + o_eS);
+    if (int rc = oz_split(ctx, n, kd, S, lds, buf, eS, (unsigned long long*)(buf + o_mx))) return rc;
+    ctx->oz_tag_ptr = S; ctx->oz_tag_n = n; ctx->oz_tag_m = kd; ctx->oz_tag_ld = lds; ctx->oz_tag_e_off = o_eS;
+  }
+  int8_t* cs = buf + (ctx->oz_bytes - OZ_TAIL);
+  int* f = (int*)(cs + c_bytes);
+  oz_cprep_kernel<<<nb, 128, 0, ctx->stream>>>(C, ldc, kd, nb, eS, cs, f, nkc);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  alignas(64) CUtensorMap tmS, tmC;
+  if (oz_make_map(&tmS, buf, kd, nch) || oz_make_map_c(&tmC, cs, nb, nkc)) return -100;
+  const int njt = (nb + ON_TN - 1) / ON_TN;
+  const int ncoh = (int)std::max<int64_t>(1, std::min<int64_t>(nch, ctx->sm_count / njt));
+  LB2_CUDA_OK(cudaFuncSetAttribute(oz_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ON_SMEM));
+  oz_nn_kernel<<<ncoh * njt, OZ_NT, ON_SMEM, ctx->stream>>>(tmS, tmC, f, Out, ldo, n, nb, nkc, nch, njt, ncoh);
+  ctx->launches++;
+  LB2_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace lb2

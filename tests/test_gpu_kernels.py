@@ -640,6 +640,36 @@ def test_gram_cols_i8_matches_dmma_path(ctx, shape):
         ctx.set_option("gram_i8", 0); ctx.set_option("oz_lockstep", 1); ctx.set_option("oz_cluster", 0)
 
 
+@pytest.mark.parametrize("shape", [(4096, 128, 64), (20000, 150, 70), (9000, 900, 300), (8200, 33, 7), (12289, 384, 129), (30001, 600, 44)])
+def test_tall_nn_i8_matches_extended_precision(ctx, shape):
+    """Projection Out = S C on the int8 tensor path (gram_i8.cu: oz_nn_kernel; S read as an MN-major operand from the slices,
+    the column exponents of S folded into the slices of C): error against a long-double product, normwise per output column, at
+    f64 level; with slices left by a preceding column-block Gram of the same S (the solver's order) and without."""
+    n, kd, nb = shape
+    rng = np.random.default_rng(n + kd)
+    S = _wide_columns(rng, n, kd)
+    Cm = np.asfortranarray(rng.standard_normal((kd, nb)) * np.exp(rng.uniform(-6, 6, (kd, 1))) / np.sqrt((S * S).sum(0))[:, None])
+    ref = (S.astype(np.longdouble) @ Cm.astype(np.longdouble)).astype(np.float64)
+    # fixed point per COLUMN: the slices carry an entry of S to 2^-55 of its column's largest entry and an entry of
+    # C' = diag(colmax S) C to 2^-55 of the largest entry of its column, so the error bound of Out[r, j] is absolute per output
+    # column, sum_c colmax_c |C[c, j]| * O(sqrt(kd) 2^-53) — normwise like a backward-stable GEMM, not elementwise
+    cmax = np.abs(S).max(0)
+    scale = (cmax[:, None] * np.abs(Cm)).sum(0)[None, :]
+    dS, dC = api.DeviceArray.from_numpy(ctx, S), api.DeviceArray.from_numpy(ctx, Cm)
+    ctx.set_option("gram_i8", 1)
+    try:
+        for warm in (False, True):
+            if warm and kd > nb:                      # leave the slices of S behind, as the Gram of a pass does
+                api.gram_cols(ctx, dS, dS.cols(kd - nb, nb), None, tri_c0=kd - nb)
+            Out = api.DeviceArray((n, nb), np.float64)
+            api.tall_nn(ctx, dS, dC, Out)
+            err = np.abs(Out.numpy(ctx) - ref) / scale
+            assert err.max() < 1e-14, f"max error {err.max():.2e} relative to the normwise scale (warm={warm})"
+            assert np.median(err) < 2e-15
+    finally:
+        ctx.set_option("gram_i8", 0)
+
+
 # ------------------------------------------------------------------------------------------------ windowed CSR kernel
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("case", [(3000, 40, 9, 5), (70001, 200, 33, 12), (5000, 256, 7, 40), (1100, 3, 4, 3)])
