@@ -149,10 +149,11 @@ __global__ void __launch_bounds__(256)
   if ((threadIdx.x & 31) == 0 && m) atomicMax(mx + c, m);
 }
 // e[c]: every |x| of the column is < 2^(e - 1), so |N| = |rint(x 2^(55 - e))| <= 2^54
-__global__ void oz_exp_kernel(const unsigned long long* __restrict__ mx, int m, int* __restrict__ e) {
+__global__ void oz_exp_kernel(const unsigned long long* __restrict__ mx, int m, int* __restrict__ e, int* __restrict__ nonfinite) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= m) return;
   const unsigned long long b = mx[c];
+  if (((b >> 52) & 0x7FF) == 0x7FF) atomicOr(nonfinite, 1);   // Inf / NaN in the block: the outputs become NaN (flag read by the reduce / drain)
   int ex = 0;
   if (b) {
     ex = (int)((b >> 52) & 0x7FF) - 1023 + 2;
@@ -644,7 +645,8 @@ __device__ __forceinline__ uint32_t on_idesc(int n16) {   // as oz_idesc, A oper
 
 __global__ void __launch_bounds__(OZ_NT, 1)
     oz_nn_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmC, const int* __restrict__ f,
-                 double* __restrict__ Out, int64_t ldo, int64_t n, int nb, int nkc, int64_t nch, int njt, int ncoh) {
+                 double* __restrict__ Out, int64_t ldo, int64_t n, int nb, int nkc, int64_t nch, int njt, int ncoh,
+                 const int* __restrict__ nonfinite) {
   extern __shared__ __align__(1024) unsigned char smem_oz[];
   const uint32_t sbase = (smem_u32(smem_oz) + 1023u) & ~1023u;
   unsigned char* gbase = smem_oz + (sbase - smem_u32(smem_oz));
@@ -744,6 +746,7 @@ __global__ void __launch_bounds__(OZ_NT, 1)
   } else {
     const int lq = warp & 3;
     const int rr = lq * 32 + lane;
+    const double poison = *nonfinite ? __longlong_as_double(0x7FF8000000000000LL) : 0.0;   // Inf / NaN in S: NaN out
     uint32_t segs = 0;
     for (int64_t rc = coh; rc < nch; rc += ncoh, ++segs) {
       mbar_wait(bar_accf, segs & 1);
@@ -777,7 +780,7 @@ __global__ void __launch_bounds__(OZ_NT, 1)
           for (int i = 0; i < 32; i++) {
             const int col = j0 + cq * 32 + i;
             // 2^(f - 62) as an exact double (f is clamped far inside the exponent range by the split)
-            if (col < nb) Out[row + (int64_t)col * ldo] = sum[i] * __longlong_as_double((long long)(1023 + f[col] - 2 * OZ_SHIFT + 48) << 52);
+            if (col < nb) Out[row + (int64_t)col * ldo] = sum[i] * __longlong_as_double((long long)(1023 + f[col] - 2 * OZ_SHIFT + 48) << 52) + poison;
           }
         }
       }
@@ -794,8 +797,9 @@ __global__ void __launch_bounds__(OZ_NT, 1)
 __global__ void __launch_bounds__(256)
     oz_reduce_kernel(const long long* __restrict__ part, const OzTile* __restrict__ tiles, const int* __restrict__ item_group,
                      int slot_mul, const int* __restrict__ eA, const int* __restrict__ eB0, const int* __restrict__ eB1,
-                     double* __restrict__ G0, int ldg0, double* __restrict__ G1, int ldg1, int mirror) {
+                     double* __restrict__ G0, int ldg0, double* __restrict__ G1, int ldg1, int mirror, const int* __restrict__ nonfinite) {
   const OzTile t = tiles[blockIdx.x];
+  const bool bad = *nonfinite != 0;
   double* __restrict__ G = t.b_sel ? G1 : G0;
   const int ldg = t.b_sel ? ldg1 : ldg0;
   const int* eB = t.b_sel ? eB1 : eB0;
@@ -813,7 +817,7 @@ __global__ void __launch_bounds__(256)
     double s = 0.0;
 #pragma unroll
     for (int l = 0; l < 7; l++) s += ldexp((double)lev[l], 8 * l);   // smallest level first; 2^48 of the level-6 weight is in the scale
-    const double val = ldexp(s, eA[t.a_col0 + r] + eB[t.b_col0 + c] - 2 * OZ_SHIFT + 48);
+    const double val = bad ? __longlong_as_double(0x7FF8000000000000LL) : ldexp(s, eA[t.a_col0 + r] + eB[t.b_col0 + c] - 2 * OZ_SHIFT + 48);
     G[(t.g_row0 + r) + (int64_t)(t.g_col0 + c) * ldg] = val;
     if (mirror && (t.g_row0 + r) != (t.g_col0 + c)) G[(t.g_col0 + c) + (int64_t)(t.g_row0 + r) * ldg] = val;
   }
@@ -846,12 +850,15 @@ int oz_make_map(CUtensorMap* tm, const int8_t* base, int m, int64_t nch) {
   return r == CUDA_SUCCESS ? 0 : -100;
 }
 
+// non-finite flag: the last int of the slice buffer (stable while the buffer lives; cleared by every call that splits anew)
+int* oz_flag(lb2_ctx* ctx) { return (int*)((char*)ctx->oz_buf + ctx->oz_bytes - 64); }
+
 // exponents + slices of an n x m f64 block
 int oz_split(lb2_ctx* ctx, int64_t n, int m, const double* X, int64_t ld, int8_t* slices, int* e, unsigned long long* mx) {
   LB2_CUDA_OK(cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * m, ctx->stream));
   const int64_t rows_per_cta = 65536;
   oz_absmax_kernel<<<dim3((unsigned)((n + rows_per_cta - 1) / rows_per_cta), m), 256, 0, ctx->stream>>>(X, ld, n, rows_per_cta, mx);
-  oz_exp_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(mx, m, e);
+  oz_exp_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(mx, m, e, oz_flag(ctx));
   const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
   const int cpc = 16;
   oz_split_kernel<<<dim3((unsigned)((nch + cpc - 1) / cpc), (m + 7) / 8), 256, 0, ctx->stream>>>(X, ld, n, m, e, slices, cpc);
@@ -1010,6 +1017,7 @@ int oz_run(lb2_ctx* ctx, int64_t n, std::vector<OzPlanTile>& tiles, OzOperand (&
   const bool timing = lb2_gram_i8_mode(ctx) == 2;   // debug: per-phase device times on stderr
   if (timing) for (auto& e : ev) cudaEventCreate(&e);
   if (timing) cudaEventRecord(ev[0], ctx->stream);
+  LB2_CUDA_OK(cudaMemsetAsync(oz_flag(ctx), 0, sizeof(int), ctx->stream));
   for (int q = 0; q < nop; q++)
     if (op[q].X)
       if (int rc = oz_split(ctx, n, op[q].m, op[q].X, op[q].ld, op[q].slices, op[q].e, mx)) return rc;
@@ -1027,7 +1035,7 @@ int oz_run(lb2_ctx* ctx, int64_t n, std::vector<OzPlanTile>& tiles, OzOperand (&
   LB2_CUDA_OK(cudaGetLastError());
   if (timing) cudaEventRecord(ev[2], ctx->stream);
   oz_reduce_kernel<<<dim3((unsigned)tl.size(), 8), 256, 0, ctx->stream>>>(part, (const OzTile*)(buf + o_tiles), (const int*)(buf + o_grp), 1,
-                                                                          op[0].e, op[1].e, op[nop > 2 ? 2 : 1].e, G0, ldg0, G1, ldg1, mirror);
+                                                                          op[0].e, op[1].e, op[nop > 2 ? 2 : 1].e, G0, ldg0, G1, ldg1, mirror, oz_flag(ctx));
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
   if (timing) {
@@ -1167,6 +1175,7 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
   const bool timing = lb2_gram_i8_mode(ctx) == 2;
   if (timing) for (auto& e : ev) cudaEventCreate(&e);
   if (timing) cudaEventRecord(ev[0], ctx->stream);
+  LB2_CUDA_OK(cudaMemsetAsync(oz_flag(ctx), 0, sizeof(int), ctx->stream));
   for (int q = 0; q < nop; q++)
     if (op[q].X)
       if (int rc = oz_split(ctx, n, op[q].m, op[q].X, op[q].ld, op[q].slices, op[q].e, mx)) return rc;
@@ -1192,7 +1201,7 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
   LB2_CUDA_OK(cudaGetLastError());
   if (timing) cudaEventRecord(ev[2], ctx->stream);
   oz_reduce_kernel<<<dim3((unsigned)tl.size(), 8), 256, 0, ctx->stream>>>(part, (const OzTile*)(buf + o_tiles), (const int*)(buf + o_grp), 4,
-                                                                          op[0].e, op[1].e, op[nop > 2 ? 2 : 1].e, G0, ldg0, G1, ldg1, 0);
+                                                                          op[0].e, op[1].e, op[nop > 2 ? 2 : 1].e, G0, ldg0, G1, ldg1, 0, oz_flag(ctx));
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
   if (timing) {
@@ -1352,7 +1361,7 @@ int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int
   auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
   const int nkc = (kd + OZ_CH - 1) / OZ_CH;
   const size_t c_bytes = al((size_t)nkc * OZ_S * nb * OZ_CH), need_tail = c_bytes + al(sizeof(int) * nb);
-  if (need_tail > OZ_TAIL) return -100;
+  if (need_tail + 1024 > OZ_TAIL) return -100;
   const bool cached = ctx->oz_buf && ctx->oz_tag_ptr == S && ctx->oz_tag_n == n && ctx->oz_tag_m == kd && ctx->oz_tag_ld == lds;
   int8_t* buf;
   int* eS;
@@ -1365,6 +1374,7 @@ int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int
     buf = oz_buffer(ctx, tot);
     if (!buf) return -1;
     eS = (int*)(buf + o_eS);
+    LB2_CUDA_OK(cudaMemsetAsync(oz_flag(ctx), 0, sizeof(int), ctx->stream));
     if (int rc = oz_split(ctx, n, kd, S, lds, buf, eS, (unsigned long long*)(buf + o_mx))) return rc;
     ctx->oz_tag_ptr = S; ctx->oz_tag_n = n; ctx->oz_tag_m = kd; ctx->oz_tag_ld = lds; ctx->oz_tag_e_off = o_eS;
   }
@@ -1378,7 +1388,7 @@ int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int
   const int njt = (nb + ON_TN - 1) / ON_TN;
   const int ncoh = (int)std::max<int64_t>(1, std::min<int64_t>(nch, ctx->sm_count / njt));
   LB2_CUDA_OK(cudaFuncSetAttribute(oz_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ON_SMEM));
-  oz_nn_kernel<<<ncoh * njt, OZ_NT, ON_SMEM, ctx->stream>>>(tmS, tmC, f, Out, ldo, n, nb, nkc, nch, njt, ncoh);
+  oz_nn_kernel<<<ncoh * njt, OZ_NT, ON_SMEM, ctx->stream>>>(tmS, tmC, f, Out, ldo, n, nb, nkc, nch, njt, ncoh, oz_flag(ctx));
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
   return 0;

@@ -670,6 +670,29 @@ def test_tall_nn_i8_matches_extended_precision(ctx, shape):
         ctx.set_option("gram_i8", 0)
 
 
+def test_int8_path_propagates_non_finite_input(ctx):
+    """A NaN or Inf anywhere in an operand cannot be represented by the integer slices: the int8 path flags it while it looks
+    for the column maxima and returns NaN outputs (a reference BLAS would propagate it to the affected entries; here the whole
+    result is poisoned, which the solver turns into its usual "factorisation failed" exit) instead of silently dropping it."""
+    rng = np.random.default_rng(3)
+    n, m = 9000, 40
+    S = rng.standard_normal((n, m))
+    S[1234, 7] = np.nan
+    dS = api.DeviceArray.from_numpy(ctx, np.asfortranarray(S))
+    Cm = api.DeviceArray.from_numpy(ctx, np.asfortranarray(rng.standard_normal((m, 9))))
+    ctx.set_option("gram_i8", 1)
+    try:
+        assert np.isnan(api.gram(ctx, dS, dS, upper=True).numpy(ctx)).all()
+        Out = api.DeviceArray((n, 9), np.float64)
+        api.tall_nn(ctx, dS, Cm, Out)
+        assert np.isnan(Out.numpy(ctx)).all()
+        S[1234, 7] = 1.0                                   # and a clean block afterwards is clean again
+        dS2 = api.DeviceArray.from_numpy(ctx, np.asfortranarray(S))
+        assert np.isfinite(api.gram(ctx, dS2, dS2, upper=True).numpy(ctx)).all()
+    finally:
+        ctx.set_option("gram_i8", 0)
+
+
 # ------------------------------------------------------------------------------------------------ windowed CSR kernel
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("case", [(3000, 40, 9, 5), (70001, 200, 33, 12), (5000, 256, 7, 40), (1100, 3, 4, 3)])

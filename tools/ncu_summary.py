@@ -10,6 +10,7 @@ import sys
 from pathlib import Path
 
 KEEP = [
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "derived__lts__lts2xbar_bytes.sum.per_second",
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_tensor_cycles_active.min.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.max.pct_of_peak_sustained_elapsed",
@@ -33,6 +34,9 @@ TITLES = {
     "nntc5": ("nn_tc5_kernel (K6 f32 projection on tcgen05, 600 -> 400)", "python tools/kernel_bench.py nn 4096000 600 400 dtype=f32"),
     "gramtc5": ("gram_tc5_kernel (K3 f32 on tcgen05, 600 x 200 rectangular)", "python tools/kernel_bench.py gram 4096000 600 mb=200 dtype=f32"),
     "resid": ("residual_kernel (K7/K8)", "python tools/kernel_bench.py resid 4096000 300"),
+    "ozgram": ("oz_gram_kernel (opt-in int8 tensor path: column-block Gram on tcgen05 kind::i8, lock-step cohorts)", "python tools/kernel_bench.py gramcols 4096000 600 300 gram_i8=1"),
+    "oznn": ("oz_nn_kernel (opt-in int8 tensor path: projection 900 -> 300, S slices as MN-major operand)", "python tools/kernel_bench.py nn 4096000 900 300 gram_i8=1"),
+    "ozsplit": ("oz_split_kernel (f64 block -> 7 int8 slices, tiled layout)", "python tools/kernel_bench.py gramcols 4096000 600 300 gram_i8=1"),
 }
 
 
@@ -40,7 +44,7 @@ def main(d):
     d = Path(d)
     traffic = {}
     print("# ncu --set full summaries, round 2 (one launch per kernel, B200, `--clock-control none`)\n")
-    print("Captured by `tools/gpu_round2_f.sh` after the same command had run without ncu in the same call; raw pages exported on "
+    print("Captured by `tools/gpu_round2_f.sh` / `tools/gpu_round2_p.sh` after the same command had run without ncu in the same call; raw pages exported on "
           "the box (`ncu -i … --page raw --csv`), summarised by `tools/ncu_summary.py`.  Durations are profiler-side (cold "
           "caches, serialised) — the bench numbers are CUDA-event timings.\n")
     for name, (title, cmd) in TITLES.items():
@@ -66,8 +70,12 @@ def main(d):
         traffic[name] = {"kernel": m["Kernel Name"][0][:120], "dram_bytes_read": gb("dram__bytes_read.sum"),
                          "dram_bytes_write": gb("dram__bytes_write.sum"), "gpu_time_ms": float(m["gpu__time_duration.sum"][0]) *
                          {"ms": 1, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(m["gpu__time_duration.sum"][1], 1)}
-    out = {"gram_wl_kernel_cols": traffic.get("gramcols"), **traffic}
-    Path("profiles/ncu_traffic_r02.json").write_text(json.dumps(out, indent=1))
+    tf = Path("profiles/ncu_traffic_r02.json")
+    old = json.loads(tf.read_text()) if tf.exists() else {}
+    old.update(traffic)                      # kernels that were not captured again keep their earlier record
+    if "gramcols" in traffic:
+        old["gram_wl_kernel_cols"] = traffic["gramcols"]
+    tf.write_text(json.dumps(old, indent=1))
 
 
 if __name__ == "__main__":

@@ -12,9 +12,9 @@ from pathlib import Path
 
 LIB = Path(__file__).resolve().parents[1] / "lobpcg_b200" / "_lib" / "liblobpcg_b200.so"
 FAMILIES = ["gram_wl_kernel", "tall_nn_persist_kernel", "tall_nn_dmma_kernel", "gram_dmma_kernel", "strip_gram_kernel",
-            "gram_zmma_kernel", "tall_nn_zmma_kernel", "gram_tc5_tma_kernel", "gram_tc5_kernel", "nn_tc5_kernel", "gram_tf32_kernel",
-            "stencil_kernel", "csr_win_kernel", "csr_kernel", "residual_kernel", "residual_monitor_kernel"]
-KEYS = ["DMMA", "HMMA", "UTCHMMA", "UTCMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UTMAPF", "LDGSTS", "LDG", "STG", "LDS", "STS",
+            "gram_zmma_kernel", "tall_nn_zmma_kernel", "oz_gram_kernel", "oz_gram_cluster_kernel", "oz_nn_kernel", "oz_split_kernel", "gram_tc5_tma_kernel", "gram_tc5_kernel", "nn_tc5_kernel", "gram_tf32_kernel",
+            "stencil_kernel", "csr_staged_kernel", "csr_win_kernel", "csr_kernel", "residual_kernel", "residual_monitor_kernel"]
+KEYS = ["DMMA", "HMMA", "UTCHMMA", "UTCIMMA", "UTCMMA", "UTCBAR", "UCGABAR_ARV", "LDTM", "UTMALDG", "UTMASTG", "UTMAPF", "LDGSTS", "LDG", "STG", "LDS", "STS",
         "BAR", "DFMA", "DADD", "FFMA", "SYNCS", "WARPSYNC"]
 
 
@@ -57,7 +57,7 @@ def main():
             op = m.group(1)
             base = op.split(".")[0]
             cnt[base] += 1
-            if first is None and base in (("UTMALDG",) if "tma" in fam else ("DMMA", "HMMA", "UTCHMMA", "UTCMMA")):
+            if first is None and base in (("UTMALDG",) if ("tma" in fam or "cluster" in fam) else ("DMMA", "HMMA", "UTCHMMA", "UTCIMMA", "UTCMMA")):
                 first = i
         print(f"## {fam}\n")
         print(f"`{names[f][:160]}`: {len(lines)} instructions, {len(cand)} instance(s) in the library\n")
