@@ -266,6 +266,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "nn_bk")) c->nn_bk = value;
   else if (!strcmp(key, "nn_persist")) c->nn_persist = value;
   else if (!strcmp(key, "nn_stagger")) c->nn_stagger = value;
+  else if (!strcmp(key, "gram_merge")) c->gram_merge = value;
   else if (!strcmp(key, "nn_warps")) c->nn_warps = value;
   else if (!strcmp(key, "force_simt")) c->force_simt = value;
   else if (!strcmp(key, "gram_wl")) c->gram_wl = value;

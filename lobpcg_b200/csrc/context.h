@@ -37,6 +37,7 @@ struct lb2_ctx {
   int nn_tile = 0;       // 0 = heuristic
   int nn_bk = 0;         // K chunk of the 128x128 tall_nn tile: 0/16 or 32 (tuning)
   int nn_warps = 0;      // f64 tall_nn experiment: 16 = 16-warp CTAs with 32x32 warp tiles (one tile per CTA)
+  int gram_merge = 1;    // column-block Gram: the two products' ragged remainder column tiles computed as one merged tile (0 = separately)
   int nn_stagger = 1;    // f64 tall_nn / work-list Gram: the two warps of a scheduler issue their chunk copies half a chunk apart (0 = together)
   int nn_persist = -1;   // f64 tall_nn: persistent 128x128 tiles with the copy ring running across tiles (-1 = on, 0 = off)
   int gram_wl = -1;      // f64 Gram through the work-list kernel (gram_wl.cu): -1 = auto, 0 = never, 1 = always

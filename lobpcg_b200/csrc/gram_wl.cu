@@ -120,9 +120,9 @@ __device__ __forceinline__ void wl_stage_dispatch(int shape, double (&acc)[8][4]
 template <int BK, int STAGES, bool VEC>
 __global__ void __launch_bounds__(WL_NT, 1)
     gram_wl_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B0, int64_t ldb0,
-                   const double* __restrict__ B1, int64_t ldb1, const WlItem* __restrict__ items,
-                   const int* __restrict__ cta_first, const WlWarp* __restrict__ layouts, double* __restrict__ part,
-                   int split) {
+                   const double* __restrict__ B1, int64_t ldb1, const double* __restrict__ B2, int64_t ldb2,
+                   const WlItem* __restrict__ items, const int* __restrict__ cta_first, const WlWarp* __restrict__ layouts,
+                   double* __restrict__ part, int split) {
   constexpr int LDS = BK + 4;
   extern __shared__ __align__(16) double smem_wl[];
   double* As = smem_wl;
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(WL_NT, 1)
       for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const bool same = item.same_panel != 0;   // diagonal tile of S^H S: one panel feeds both operands
-    const double* __restrict__ B = item.b_sel ? B1 : B0;
-    const int64_t ldb = item.b_sel ? ldb1 : ldb0;
+    const double* __restrict__ B = item.b_sel == 2 ? B2 : (item.b_sel ? B1 : B0);
+    const int64_t ldb = item.b_sel == 2 ? ldb2 : (item.b_sel ? ldb1 : ldb0);
     TileLoaderF64<WL_T, BK, LDS, WL_NT, VEC> la, lb;
     int ci = item.c_start;   // chunk index of the next copy; chunks are walked c_start .. nchunks-1, 0 .. c_start-1
     la.init(A, lda, item.r_begin + (int64_t)ci * BK, item.a_col0, item.a_col0 + item.a_cols, tid);
@@ -465,9 +465,9 @@ int plan_schedule(int ma, int mb, int upper, int same_ab, int64_t n, int ncta, i
 // columns tri_c0 .. tri_c0 + nw - 1 are the W block of a Hermitian product (tri_c0 < 0: plain rectangular products).
 // Tiles that lie entirely below the diagonal of that block (first row - tri_c0 > last column) are left out: the caller
 // mirrors them from the upper part.  P.tiles_out lists the tiles in schedule order.
-struct WlTileOut { int32_t a_col0, a_cols, b_col0, b_cols, b_sel, first, last, diag; };
+struct WlTileOut { int32_t a_col0, a_cols, b_col0, b_cols, b_sel, first, last, diag, msplit; };   // b_sel 2: merged remainder tile, columns < msplit -> G0, the rest -> G1
 int plan_schedule_cols(int m, int nw, int nprod, int tri_c0, int64_t n, int ncta, int BK, int load_pct, int phase,
-                       WlPlan& P, std::vector<WlTileOut>& out) {
+                       WlPlan& P, std::vector<WlTileOut>& out, int merge = 1) {
   // Row tiles: 128-column steps over [0, tri_c0) and, separately, over the Hermitian block [tri_c0, tri_c0 + nw), so
   // that the tiles of W^H W / W^H A W are aligned with the column tiles: tiles below the diagonal are left out, full
   // diagonal tiles use the balanced upper-triangle cover (diag16_layout), exactly as in a Hermitian product.
@@ -479,20 +479,26 @@ int plan_schedule_cols(int m, int nw, int nprod, int tri_c0, int64_t n, int ncta
   std::vector<WlTile> tiles;
   std::vector<int> is_diag;
   WlLayoutCache lcache;
+  // MERGED REMAINDER TILE: the last, ragged column tile of k = 300 is 44 columns wide — a 128 x 44 tile stages 172 columns for 96
+  // MMA blocks and is bound by its copies, twice per S panel (both products).  With both products present and a remainder of
+  // at most 64 columns the two remainder panels are gathered into one scratch block [W0 rem | W1 rem] (gram_wl_cols_f64) and
+  // computed as ONE tile of 2 * rem columns (b_sel = 2); the reduction scatters its halves to the two outputs.
+  const int nfull = nw / WL_T, rem = nw - nfull * WL_T;
+  const bool merged = merge && nprod == 2 && rem > 0 && 2 * rem <= WL_T;
   // row tile outermost: the tiles of one S panel (both products, every column tile) are neighbours on the line
   for (size_t ri = 0; ri < rows.size(); ri++)
-    for (int q = 0; q < nprod; q++)
-      for (int tj = 0; tj < ntn; tj++) {
+    for (int q = 0; q < (merged ? nprod + 1 : nprod); q++)
+      for (int tj = (q == nprod ? nfull : 0); tj < (q == nprod ? nfull + 1 : (merged ? nfull : ntn)); tj++) {
         WlTile tl{};
         tl.ti = (int)ri; tl.tj = tj; tl.b_sel = q;
         tl.a_col0 = rows[ri].first; tl.a_cols = rows[ri].second;
-        tl.b_col0 = tj * WL_T;
-        tl.b_cols = std::min(WL_T, nw - tj * WL_T);
+        tl.b_col0 = (q == nprod) ? 0 : tj * WL_T;                       // merged panel: column 0 of the gathered block
+        tl.b_cols = (q == nprod) ? 2 * rem : std::min(WL_T, nw - tj * WL_T);
         int kind = 0;
         if (tl.a_col0 >= split) {   // inside the Hermitian block (aligned tiles)
           const int wi = (tl.a_col0 - split) / WL_T;
           if (wi > tj) continue;
-          kind = (wi == tj) ? 1 : 0;
+          kind = (wi == tj && q != nprod) ? 1 : 0;
         }
         if (int rc = make_tile(tl, kind, 0, load_pct, P.layouts, lcache)) return rc;
         tiles.push_back(tl);
@@ -504,7 +510,9 @@ int plan_schedule_cols(int m, int nw, int nprod, int tri_c0, int64_t n, int ncta
   out.clear();
   for (size_t i = 0; i < tiles.size(); i++) {
     const WlTile& tl = tiles[i];
-    out.push_back(WlTileOut{tl.a_col0, tl.a_cols, tl.b_col0, tl.b_cols, tl.b_sel, P.tile_first[i], P.tile_first[i + 1], is_diag[i]});
+    const bool mt = tl.b_sel == nprod;   // merged remainder tile
+    out.push_back(WlTileOut{tl.a_col0, tl.a_cols, mt ? nfull * WL_T : tl.b_col0, tl.b_cols, mt ? 2 : tl.b_sel, P.tile_first[i],
+                            P.tile_first[i + 1], is_diag[i], mt ? rem : 0});
   }
   return 0;
 }
@@ -545,12 +553,12 @@ int launch_wl(lb2_ctx* ctx, const WlSchedule& S, int64_t n, int ma, int mb, cons
   if (vec) {
     auto k = gram_wl_kernel<BK, STAGES, true>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, B, ldb, S.items, S.cta_first, S.layouts, part,
+    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, B, ldb, B, ldb, S.items, S.cta_first, S.layouts, part,
                                             ctx->nn_stagger ? 4 : 8);
   } else {
     auto k = gram_wl_kernel<BK, STAGES, false>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, B, ldb, S.items, S.cta_first, S.layouts, part,
+    k<<<S.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B, ldb, B, ldb, B, ldb, S.items, S.cta_first, S.layouts, part,
                                             ctx->nn_stagger ? 4 : 8);
   }
   ctx->launches++;
@@ -567,8 +575,8 @@ int launch_wl(lb2_ctx* ctx, const WlSchedule& S, int64_t n, int ma, int mb, cons
 __global__ void gram_wl_reduce_tiles_kernel(const double* __restrict__ part, const WlTileOut* __restrict__ tiles,
                                             double* __restrict__ G0, int ldg0, double* __restrict__ G1, int ldg1) {
   const WlTileOut t = tiles[blockIdx.x];
-  double* __restrict__ G = t.b_sel ? G1 : G0;
-  const int ldg = t.b_sel ? ldg1 : ldg0;
+  double* __restrict__ G = t.b_sel == 1 ? G1 : G0;
+  const int ldg = t.b_sel == 1 ? ldg1 : ldg0;
   const int tot = t.a_cols * t.b_cols;
   for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < tot; idx += gridDim.y * blockDim.x) {
     const int r = idx % t.a_cols, c = idx / t.a_cols;
@@ -576,7 +584,12 @@ __global__ void gram_wl_reduce_tiles_kernel(const double* __restrict__ part, con
     const int64_t off = r + (int64_t)c * WL_T;
     double s = 0.0;
     for (int k = t.first; k < t.last; k++) s += part[(int64_t)k * (WL_T * WL_T) + off];
-    G[(t.a_col0 + r) + (int64_t)(t.b_col0 + c) * ldg] = s;
+    if (t.b_sel == 2) {   // merged remainder tile: [W0 rem | W1 rem]
+      if (c < t.msplit) G0[(t.a_col0 + r) + (int64_t)(t.b_col0 + c) * ldg0] = s;
+      else G1[(t.a_col0 + r) + (int64_t)(t.b_col0 + c - t.msplit) * ldg1] = s;
+    } else {
+      G[(t.a_col0 + r) + (int64_t)(t.b_col0 + c) * ldg] = s;
+    }
   }
 }
 
@@ -584,15 +597,18 @@ struct WlColsSchedule {
   WlSchedule base;
   const WlTileOut* tiles_dev = nullptr;
   int ntiles = 0;
+  int merged_rem = 0;   // > 0: the schedule has merged remainder tiles of 2 * merged_rem columns (b_sel = 2)
 };
-using WlColsKey = std::tuple<int, int, int, int, int64_t, int, int, int, int>;   // m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase
+using WlColsKey = std::tuple<int, int, int, int, int64_t, int, int, int, int, int>;   // m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase, merge
 
 int build_schedule_cols(lb2_ctx* ctx, int m, int nw, int nprod, int tri_c0, int64_t n, int ncta, int BK, int load_pct,
-                        int phase, WlColsSchedule& S) {
+                        int phase, int merge, WlColsSchedule& S) {
   WlPlan P;
   std::vector<WlTileOut> tout;
-  const int rc = plan_schedule_cols(m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase, P, tout);
+  const int rc = plan_schedule_cols(m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase, P, tout, merge);
   if (rc) return rc;
+  for (auto& t : tout)
+    if (t.b_sel == 2) S.merged_rem = t.msplit;
   const int nitems = (int)P.items.size(), ntiles = P.ntiles;
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t o_items = 0, o_cta = al(sizeof(WlItem) * nitems), o_lay = o_cta + al(sizeof(int) * (ncta + 1)),
@@ -616,22 +632,33 @@ int build_schedule_cols(lb2_ctx* ctx, int m, int nw, int nprod, int tri_c0, int6
 }
 
 template <int BK, int STAGES>
-int launch_wl_cols(lb2_ctx* ctx, const WlColsSchedule& S, const double* A, int64_t lda, const double* B0, int64_t ldb0,
-                   double* G0, int ldg0, const double* B1, int64_t ldb1, double* G1, int ldg1) {
-  double* part = (double*)ctx_scratch(ctx, sizeof(double) * (size_t)S.base.nitems * WL_T * WL_T);
+int launch_wl_cols(lb2_ctx* ctx, const WlColsSchedule& S, int64_t n, int nw, const double* A, int64_t lda, const double* B0,
+                   int64_t ldb0, double* G0, int ldg0, const double* B1, int64_t ldb1, double* G1, int ldg1) {
+  const size_t part_bytes = (sizeof(double) * (size_t)S.base.nitems * WL_T * WL_T + 255) & ~(size_t)255;
+  const int rem = S.merged_rem;
+  const int64_t ldm = (n + 1) & ~(int64_t)1;                                  // even leading dimension: 16-byte copies
+  double* part = (double*)ctx_scratch(ctx, part_bytes + (rem ? sizeof(double) * (size_t)ldm * 2 * rem : 0));
   if (!part) return -1;
+  double* Bm = (double*)((char*)part + part_bytes);
+  if (rem) {   // gather the two ragged remainder panels side by side: [W0[:, nw - rem :] | W1[:, nw - rem :]]
+    const int c0 = nw - rem;
+    LB2_CUDA_OK(cudaMemcpy2DAsync(Bm, sizeof(double) * ldm, B0 + (int64_t)c0 * ldb0, sizeof(double) * ldb0, sizeof(double) * n, rem,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    LB2_CUDA_OK(cudaMemcpy2DAsync(Bm + (int64_t)rem * ldm, sizeof(double) * ldm, B1 + (int64_t)c0 * ldb1, sizeof(double) * ldb1,
+                                  sizeof(double) * n, rem, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
   const bool vec = (lda % 2 == 0) && (ldb0 % 2 == 0) && (ldb1 % 2 == 0) && ((uintptr_t)A % 16 == 0) &&
                    ((uintptr_t)B0 % 16 == 0) && ((uintptr_t)B1 % 16 == 0);
   constexpr size_t smem = sizeof(double) * (size_t)STAGES * 2 * WL_T * (BK + 4);
   if (vec) {
     auto k = gram_wl_kernel<BK, STAGES, true>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<S.base.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B0, ldb0, B1, ldb1, S.base.items, S.base.cta_first,
+    k<<<S.base.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B0, ldb0, B1, ldb1, Bm, ldm, S.base.items, S.base.cta_first,
                                                   S.base.layouts, part, ctx->nn_stagger ? 4 : 8);
   } else {
     auto k = gram_wl_kernel<BK, STAGES, false>;
     LB2_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<S.base.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B0, ldb0, B1, ldb1, S.base.items, S.base.cta_first,
+    k<<<S.base.ncta, WL_NT, smem, ctx->stream>>>(A, lda, B0, ldb0, B1, ldb1, Bm, ldm, S.base.items, S.base.cta_first,
                                                   S.base.layouts, part, ctx->nn_stagger ? 4 : 8);
   }
   ctx->launches++;
@@ -942,11 +969,12 @@ int gram_wl_cols_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, in
   const int ncta = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, tiles_full * n / 4096));
   const int load_pct = ctx->gram_load_pct > 0 ? ctx->gram_load_pct : WL_LOAD_PCT;
   const int phase = ctx->gram_phase != 0 ? 1 : 0;
-  const WlColsKey key(m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase);
+  const int merge = ctx->gram_merge != 0 ? 1 : 0;
+  const WlColsKey key(m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase, merge);
   auto f = cache->map.find(key);
   if (f == cache->map.end()) {
     WlColsSchedule Sc;
-    const int rc = build_schedule_cols(ctx, m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase, Sc);
+    const int rc = build_schedule_cols(ctx, m, nw, nprod, tri_c0, n, ncta, BK, load_pct, phase, merge, Sc);
     if (rc) return rc;
     f = cache->map.emplace(key, Sc).first;
   }
@@ -954,8 +982,8 @@ int gram_wl_cols_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, in
   const int64_t ldb1 = nprod == 2 ? ldw1 : ldw0;
   double* Gq1 = nprod == 2 ? G1 : G0;
   const int ldq1 = nprod == 2 ? ldg1 : ldg0;
-  if (BK == 32) return launch_wl_cols<32, 3>(ctx, f->second, S, lds, W0, ldw0, G0, ldg0, B1, ldb1, Gq1, ldq1);
-  return launch_wl_cols<16, 4>(ctx, f->second, S, lds, W0, ldw0, G0, ldg0, B1, ldb1, Gq1, ldq1);
+  if (BK == 32) return launch_wl_cols<32, 3>(ctx, f->second, n, nw, S, lds, W0, ldw0, G0, ldg0, B1, ldb1, Gq1, ldq1);
+  return launch_wl_cols<16, 4>(ctx, f->second, n, nw, S, lds, W0, ldw0, G0, ldg0, B1, ldb1, Gq1, ldq1);
 }
 
 // Host-only self-check of a column-block schedule (no CUDA calls; tests/test_gram_plan.py): the items of every tile
@@ -979,7 +1007,7 @@ int gram_wl_cols_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int
       if (it.r_begin != r || it.r_end <= r || P.item_tile[i] != tix) return 11;
       if (i > t.first && it.r_begin % BK) return 12;
       if (it.c_start < 0 || (int64_t)it.c_start * BK >= it.r_end - it.r_begin) return 18;
-      if (it.a_col0 != t.a_col0 || it.b_col0 != t.b_col0 || it.a_cols != t.a_cols || it.b_cols != t.b_cols ||
+      if (it.a_col0 != t.a_col0 || it.b_col0 != (t.b_sel == 2 ? 0 : t.b_col0) || it.a_cols != t.a_cols || it.b_cols != t.b_cols ||
           it.b_sel != t.b_sel || it.same_panel != 0)
         return 19;
       r = it.r_end;
@@ -1004,6 +1032,16 @@ int gram_wl_cols_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int
       for (int col = 0; col < 16; col++)
         if (owner[row][col] != ((row < ra && col < cb && (!t.diag || row <= col)) ? 1 : 0)) return 15;
     if (t.diag && (tri_c0 < 0 || t.a_col0 - tri_c0 != t.b_col0)) return 22;
+    if (t.b_sel == 2) {   // merged remainder tile: columns [0, msplit) -> product 0, [msplit, 2 msplit) -> product 1
+      if (nprod != 2 || t.diag || t.msplit <= 0 || t.b_cols != 2 * t.msplit || t.b_col0 + t.msplit != nw || t.a_col0 < 0 ||
+          t.a_col0 + t.a_cols > m)
+        return 23;
+      for (int i = 0; i < t.a_cols; i++)
+        for (int j = 0; j < t.b_cols; j++)
+          cover[((size_t)(j / t.msplit) * m + t.a_col0 + i) * nw + t.b_col0 + j % t.msplit]++;
+      area += (double)t.a_cols * t.b_cols;
+      continue;
+    }
     if (t.a_col0 < 0 || t.b_col0 < 0 || t.a_col0 + t.a_cols > m || t.b_col0 + t.b_cols > nw || t.b_sel < 0 || t.b_sel >= nprod)
       return 20;
     for (int i = 0; i < t.a_cols; i++)
