@@ -307,6 +307,7 @@ def run_ours(args):
     s.step(args.warmup)
     barrier()
     s.reset_stats()
+    ctx.oz_stats()
     l0 = ctx.launches
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -329,6 +330,8 @@ def run_ours(args):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     launches = ctx.launches - l0
     st = s.stats()
+    oz = ctx.oz_stats()                       # int8 tensor path: device time of split / MMA kernel / reduce inside the Gram phase
+    int8_on = oz["calls"] > 0
     prog = s.progress()
     gram_cache_info = {"enabled": bool(s.info("gram_cache")), "refreshes_in_timed_region": None,
                        "monitor_max": s.info("gram_cache_monitor_max"), "arena_columns_per_k": s.info("arena_columns") / k,
@@ -359,12 +362,13 @@ def run_ours(args):
             windows[name] = {"ms_per_step": t / max(dn, 1), "steps": dn, "note": note, "solver_state": s.progress(),
                              "ms": {kk: stw[kk]["ms"] / max(dn, 1) for kk in ("gram", "tall_nn", "spmm", "residual", "small_dense", "comm")}}
         nw_steps = max(3, min(args.steps, 6))
-        # same state as the main window, but every f64 Gram product through tcgen05.mma kind::i8 on the Ozaki split
-        # (lobpcg_b200/csrc/gram_i8.cu; opt-in: LB2_GRAM_I8=1 / context option gram_i8)
-        ctx.set_option("gram_i8", 1)
-        timed_window("int8_gram", nw_steps, "main-window pass with the column-block Gram on the int8 tensor path (7-slice Ozaki split, "
-                     "exact integer accumulation in TMEM); includes the per-pass split of [X P W] and A W into slices")
-        ctx.set_option("gram_i8", 0)
+        # same state as the main window with the int8 tensor path switched off: the f64 DMMA kernels (gram_wl_kernel,
+        # tall_nn_persist_kernel) that were the default before round 2's int8 path (lobpcg_b200/csrc/gram_i8.cu)
+        if int8_on:
+            ctx.set_option("gram_i8", 0)
+            timed_window("dmma", nw_steps, "main-window pass on the FP64 tensor pipe (mma.sync DMMA work-list Gram + persistent projection; "
+                         "context option gram_i8 = 0 / LB2_GRAM_I8=0)")
+            ctx.set_option("gram_i8", -1)
         s.set_option("debug_min_conv", nev // 2)
         timed_window("softlocked", nw_steps, f"Cholesky branch with the leading {nev // 2} of {k} columns soft-locked "
                      "(forced: option debug_min_conv; P and W shrink to the active columns)")
@@ -405,19 +409,56 @@ def run_ours(args):
             traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"])
         except Exception:
             traffic = None
-    roofline = {
-        "kernel": "gram_wl_kernel (K2/K3, FP64 tensor pipe DMMA.8x8x4): per pass ONE launch for the W columns of both Grams, "
-                  "[X P W]^H [W | A W]; the [X P] blocks come from the cached C^H G C (SURVEY 8f-2)",
-        "bound": "tensor", "achieved": gram_tf, "peak": fp64, "unit": "TFLOP/s", "frac": gram_tf / fp64,
-        "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/ncu_traffic_r02.json); "
-                                             "algorithmic operand bytes per launch = n*(m + 2 n_w)*8 = %.3g" % (n_local * 5.0 * k * 8),
-        "peak_source": how64, "per_gpu": True,
-        "algorithmic_flops_per_launch": st["gram"]["work"] / max(st["gram"]["calls"], 1) / world,
-        "algorithmic_flops_note": "needed entries only: 2 products x n x (2 m_xp n_w + n_w (n_w + 1)); a recomputation of the "
-                                  "cached blocks (every 64 passes) adds the Hermitian [X P] products",
-        "fp64_probe": probe,
-        "share_of_step": st["gram"]["ms"] / (ms if ms > 0 else 1.0),
-    }
+    gram_flops_launch = st["gram"]["work"] / max(st["gram"]["calls"], 1) / world
+    if int8_on:
+        # dominant kernel of the default path: the int8 Gram kernel.  Its arithmetic is 28 exact int8 slice products per f64
+        # product (levels 6..12 of the 7 x 7 digit products), so a launch executes 28 x the algorithmic f64 flop count in int8
+        # tensor operations.  Peak: MEASURED_PEAKS.json has no int8 entry; tcgen05.mma kind::i8 issues at twice the bf16 rate
+        # on sm_100 (K = 32 against K = 16 per instruction at the same instruction time), so 2 x the measured bf16 rate.
+        try:
+            mp = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+            i8_peak, i8_src = 2.0 * float(mp["bf16_tflops_sustained"]), "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (measured; no int8 entry in the file)"
+        except Exception:
+            i8_peak, i8_src = 2.0 * 1400.0, "2 x 1.4 PFLOP/s bf16 sustained, of fallback (B200_PROFILING.md)"
+        mma_ms = oz["mma_ms"] / max(oz["calls"], 1)
+        i8_tops = 28.0 * gram_flops_launch / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else 0.0
+        try:
+            t = json.loads(tf.read_text())["ozgram"] if (tf.exists() and g == 160 and nev == 150 and world == 1) else None
+            traffic = float(t["dram_bytes_read"] + t["dram_bytes_write"]) if t else None
+        except Exception:
+            traffic = None
+        roofline = {
+            "kernel": "oz_gram_cluster_kernel (K2/K3 on tcgen05.mma kind::i8, SASS UTCIMMA: f64 column-block Gram [X P W]^H [W | A W] as 28 "
+                      "exact int8 slice products of a 7-slice Ozaki split, TMA multicast operands, int32 accumulators in TMEM, int64 "
+                      "partial sums; lobpcg_b200/csrc/gram_i8.cu, DESIGN.md 3b)",
+            "bound": "tensor", "achieved": i8_tops, "peak": i8_peak, "unit": "TFLOP/s", "frac": i8_tops / i8_peak,
+            "unit_note": "int8 tensor operations (exact integer multiply-adds x 2) per second of the MMA kernel alone",
+            "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/ncu_traffic_r02.json); "
+                                                 "algorithmic operand bytes per launch = 7 n (m + n_w) = %.3g (slices of [X P W] and A W)" % (n_local * 7.0 * 4 * k),
+            "peak_source": i8_src, "per_gpu": True,
+            "algorithmic_flops_per_launch": 28.0 * gram_flops_launch,
+            "algorithmic_flops_note": "28 int8 slice products x the needed f64 flops of the launch, 2 products x n x (2 m_xp n_w + n_w (n_w + 1)) = %.4g" % gram_flops_launch,
+            "ms_per_launch": {"split": oz["split_ms"] / max(oz["calls"], 1), "mma_kernel": mma_ms, "reduce": oz["reduce_ms"] / max(oz["calls"], 1)},
+            "f64_equivalent": {"tflops_gram_phase": gram_tf, "tflops_mma_kernel": gram_flops_launch / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else 0.0,
+                               "fp64_dgemm_peak": fp64, "fp64_peak_source": how64,
+                               "note": "the same products on the FP64 tensor pipe (window 'dmma'): gram_wl_kernel at 0.85 of this DGEMM peak"},
+            "fp64_probe": probe,
+            "share_of_step": oz["mma_ms"] / (ms if ms > 0 else 1.0),
+        }
+    else:
+        roofline = {
+            "kernel": "gram_wl_kernel (K2/K3, FP64 tensor pipe DMMA.8x8x4): per pass ONE launch for the W columns of both Grams, "
+                      "[X P W]^H [W | A W]; the [X P] blocks come from the cached C^H G C (SURVEY 8f-2)",
+            "bound": "tensor", "achieved": gram_tf, "peak": fp64, "unit": "TFLOP/s", "frac": gram_tf / fp64,
+            "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/ncu_traffic_r02.json); "
+                                                 "algorithmic operand bytes per launch = n*(m + 2 n_w)*8 = %.3g" % (n_local * 5.0 * k * 8),
+            "peak_source": how64, "per_gpu": True,
+            "algorithmic_flops_per_launch": gram_flops_launch,
+            "algorithmic_flops_note": "needed entries only: 2 products x n x (2 m_xp n_w + n_w (n_w + 1)); a recomputation of the "
+                                      "cached blocks (every 64 passes) adds the Hermitian [X P] products",
+            "fp64_probe": probe,
+            "share_of_step": st["gram"]["ms"] / (ms if ms > 0 else 1.0),
+        }
 
     # ---- e2e: the reference-facing call d_lobpcg(alg) with HOST buffers (X0 upload, result download inside) ----
     e2e = None
@@ -538,6 +579,10 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "time_to_solution": tts, "gpu_launches": int(launches),
             "clocks": clocks, "kernels": kernels, "hbm_peak_gbs": hbm, "hbm_peak_source": how_hbm,
             "windows": windows, "gram_cache": gram_cache_info,
+            "dtype_note": ("f64 results; the tall products (Gram, projection) are evaluated EXACTLY on the int8 tensor cores from a 7-slice "
+                           "split of the f64 operands (int32 / int64 accumulation, one f64 rounding per output), everything else in f64"
+                           if int8_on else "f64 throughout (FP64 tensor pipe)"),
+            "int8_tensor_path": {"active": bool(int8_on), "gram_ms_per_step": {kk: oz[kk] / max(done, 1) for kk in ("split_ms", "mma_ms", "reduce_ms")}},
         }
         print(json.dumps(line))
     if world > 1:

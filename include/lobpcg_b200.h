@@ -39,6 +39,8 @@ int lb2_ctx_sync(lb2_ctx *ctx);
 int lb2_ctx_set_option(lb2_ctx *ctx, const char *key, int value);
 int lb2_ctx_trim(lb2_ctx *ctx); /* free the solver arena this context keeps for reuse by its next solve (LB2_ARENA_CACHE=0: never kept) */
 unsigned long long lb2_ctx_launches(lb2_ctx *ctx); /* kernels launched so far through this context */
+/* device times (ms) of the int8 tensor-path Gram since the last query: out4 = {split, MMA kernel, reduce, calls} */
+int lb2_ctx_oz_stats(lb2_ctx *ctx, double *out4);
 lb2_ctx *lb2_default_ctx(void);                    /* lazily created context on the current device */
 
 /* device memory for FFI callers that have no CUDA runtime of their own */

@@ -54,6 +54,7 @@ def _declare(L):
     L.lb2_ctx_set_option.argtypes = [vp, C.c_char_p, ci]
     L.lb2_ctx_launches.restype = C.c_ulonglong
     L.lb2_ctx_launches.argtypes = [vp]
+    L.lb2_ctx_oz_stats.argtypes = [vp, C.POINTER(dbl)]
     L.lb2_default_ctx.restype = vp
     L.lb2_gram_wl_plan_check.argtypes = [ci, ci, ci, i64, ci, ci, C.POINTER(dbl)]
     L.lb2_gram_wl_cols_plan_check.argtypes = [ci, ci, ci, ci, i64, ci, ci, C.POINTER(dbl)]
@@ -170,6 +171,12 @@ class Context:
 
     def set_option(self, key: str, value: int):
         _ck(lib().lb2_ctx_set_option(self.h, key.encode(), int(value)), f"set_option({key})")
+
+    def oz_stats(self):
+        """{split_ms, mma_ms, reduce_ms, calls} of the int8 tensor-path Gram since the last query."""
+        out = (C.c_double * 4)()
+        _ck(lib().lb2_ctx_oz_stats(self.h, out), "lb2_ctx_oz_stats")
+        return dict(split_ms=out[0], mma_ms=out[1], reduce_ms=out[2], calls=int(out[3]))
 
     def trim(self):
         """Free the solver arena the context keeps for reuse by its next solve."""

@@ -28,15 +28,42 @@ static std::mutex g_ctx_mu;
 static std::vector<lb2_ctx*> g_all_ctx;   // every live context (their cached arenas are freed when an allocation fails)
 
 static void trim_ctx(lb2_ctx* c) {
+  int dev = 0;
+  cudaGetDevice(&dev);
   if (c->arena_cache) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaSetDevice(c->device);
     cudaFree(c->arena_cache);
-    cudaSetDevice(dev);
   }
   c->arena_cache = nullptr;
   c->arena_cache_bytes = 0;
+  if (c->oz_buf && c->active_solvers == 0) {   // int8 slice buffer of a context with no solve in flight (gram_i8.cu)
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->oz_buf);
+    c->oz_buf = nullptr;
+    c->oz_bytes = 0;
+    c->oz_tag_ptr = nullptr;
+  }
+  cudaSetDevice(dev);
+}
+
+void* oz_malloc(lb2_ctx* ctx, size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) == cudaSuccess) return p;
+  cudaGetLastError();
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (lb2_ctx* c : g_all_ctx)
+      if (c != ctx) trim_ctx(c);
+    if (ctx->arena_cache) {   // this context's own cached arena (no solve in flight on it uses the cache)
+      cudaFree(ctx->arena_cache);
+      ctx->arena_cache = nullptr;
+      ctx->arena_cache_bytes = 0;
+    }
+  }
+  if (cudaMalloc(&p, bytes) == cudaSuccess) return p;
+  cudaGetLastError();
+  return nullptr;
 }
 
 void* arena_alloc(lb2_ctx* ctx, size_t bytes) {
@@ -247,6 +274,7 @@ void lb2_ctx_destroy(lb2_ctx* c) {
   lb2::hostcopy_free(c);
   if (c->ws) cudaFree(c->ws);
   if (c->oz_buf) cudaFree(c->oz_buf);
+  for (auto& e : c->oz_ev) if (e) cudaEventDestroy(e);
   if (c->solver_ws) cudaFree(c->solver_ws);
   if (c->solver_hws) free(c->solver_hws);
   if (c->dev_info) cudaFree(c->dev_info);
@@ -276,6 +304,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "oz_load_pct")) c->oz_load_pct = value;
   else if (!strcmp(key, "oz_cluster")) c->oz_cluster = value;
   else if (!strcmp(key, "oz_lockstep")) c->oz_lockstep = value;
+  else if (!strcmp(key, "oz_prefetch")) c->oz_prefetch = value;
   else if (!strcmp(key, "nn_i8")) c->nn_i8 = value;
   else if (!strcmp(key, "oz_clusters")) c->oz_clusters = value;
   else if (!strcmp(key, "gram_tma")) c->gram_tma = value;
@@ -294,6 +323,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
 }
 
 unsigned long long lb2_ctx_launches(lb2_ctx* c) { return c ? c->launches : 0ULL; }
+int lb2_ctx_oz_stats(lb2_ctx* c, double* out4) { return (c && out4) ? lb2::oz_stats_query(c, out4) : -1; }
 
 static std::mutex g_mu;
 static std::map<int, lb2_ctx*> g_default;

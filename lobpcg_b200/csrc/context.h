@@ -24,6 +24,13 @@ struct lb2_ctx {
   int64_t oz_tag_n = 0, oz_tag_ld = 0;
   int oz_tag_m = 0;
   size_t oz_tag_e_off = 0;
+  // device times of the int8 Gram phases (split / MMA kernel / reduce), accumulated over calls (lb2_ctx_oz_stats)
+  cudaEvent_t oz_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool oz_ev_pending = false;
+  double oz_ms[3] = {0.0, 0.0, 0.0};
+  long long oz_calls = 0;
+  bool oz_reuse = false;     // set by the solver between the Gram of a pass and its projections: only then are the cached slices trusted
+  int active_solvers = 0;    // solvers holding an arena on this context (their slice buffer must not be taken away under memory pressure)
   // small-dense library handles (created lazily)
   cublasHandle_t cublas = nullptr;
   cusolverDnHandle_t cusolver = nullptr;
@@ -49,11 +56,12 @@ struct lb2_ctx {
   void* hostcopy = nullptr;        // lb2::HostCopyState* (pinned ring for pageable host <-> device block transfers)
   void* gram_wl_cache = nullptr;   // lb2::WlCache* (schedules per Gram shape)
   void* gram_wl_cols_cache = nullptr;   // lb2::WlColsCache* (schedules of the column-block products, gram_wl_cols_f64)
-  int gram_i8 = 0;       // f64 Gram through tcgen05 kind::i8 on an Ozaki split (gram_i8.cu): 1 = on, 0 = DMMA kernels (default)
+  int gram_i8 = -1;      // f64 Gram / projection on tcgen05 kind::i8 through an Ozaki split (gram_i8.cu): -1 = auto (on for n >= 2^18 rows), 1 = on (n >= 4096), 0 = DMMA kernels, 2 = on + phase times on stderr
   int gram_i8_env = -1;  // LB2_GRAM_I8 as seen by the last solver set-up (-1 = unset); overrides gram_i8 for the drop-in entry points
   int nn_i8 = 1;         // with gram_i8 on: projections Out = S C (alpha 1, beta 0) on the int8 tensor path too (0 = DMMA kernel)
+  int oz_prefetch = 0;   // int8 kernels: L2 prefetch distance of the slice tiles in chunks (0 = off: measured slower at every distance, r02)
   int oz_lockstep = 1;   // gram_i8 one-tile-per-CTA kernel: 1 = lock-step cohorts (every (tile, level group) has its own CTAs), 0 = equal-cost cut
-  int oz_cluster = 0;    // gram_i8 column-block products: 1 = 4-CTA clusters with multicast slice tiles (r02: 110 ms against 90 ms of the one-tile-per-CTA kernel at the C5 shape), 0 = one tile per CTA
+  int oz_cluster = 1;    // gram_i8 column-block products: 1 = 4-CTA clusters with multicast slice tiles (r02, C5 shape: 71 ms against 78 ms of the one-tile-per-CTA kernel), 0 = one tile per CTA
   int oz_clusters = -1;  // resident clusters of the cluster kernel (queried once; option: force a count)
   int oz_load_pct = 0;   // gram_i8 schedule: cost of one 16 KB slice-tile load relative to one full-width slice product, in % (0 = 100)
   int gram_tc5 = -1;     // float Gram through tcgen05 / TMEM (gram_tc5.cu): -1 = auto (on), 0 = off, 1 = on
@@ -98,3 +106,13 @@ void hostcopy_set_threads(lb2_ctx* ctx, int nthreads);
 
 // effective setting of the int8 Gram path (environment for the reference entry points, else the context option)
 inline int lb2_gram_i8_mode(const lb2_ctx* c) { return c->gram_i8_env >= 0 ? c->gram_i8_env : c->gram_i8; }
+// does a product over n rows take the int8 path?  auto: only where the tall kernels dominate (the path has more launches and a
+// host-side schedule per call)
+inline bool lb2_gram_i8_on(const lb2_ctx* c, int64_t n) {
+  const int mode = lb2_gram_i8_mode(c);
+  return mode > 0 ? n >= 4096 : (mode < 0 && n >= ((int64_t)1 << 18));
+}
+namespace lb2 {
+// device memory for the int8 slices; under pressure frees the cached arenas and the idle slice buffers of other contexts (capi.cu)
+void* oz_malloc(lb2_ctx* ctx, size_t bytes);
+}

@@ -1240,7 +1240,7 @@ int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const
   }
   if constexpr (std::is_same<T, double>::value) {
     if (!ctx->force_simt) {
-      if (lb2_gram_i8_mode(ctx) > 0 && n >= 4096) {   // tcgen05 kind::i8 on an Ozaki split (gram_i8.cu), opt-in
+      if (lb2_gram_i8_on(ctx, n)) {   // tcgen05 kind::i8 on an Ozaki split (gram_i8.cu)
         const int rc = gram_i8_f64(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
         if (rc != -100) return rc;
       }
@@ -1274,7 +1274,7 @@ int gram_cols(lb2_ctx* ctx, int64_t n, int m, int nw, const T* S, int64_t lds, c
               int ldg0, const T* W1, int64_t ldw1, T* G1, int ldg1, int tri_c0) {
   if (m <= 0 || nw <= 0) return 0;
   if constexpr (std::is_same<T, double>::value) {
-    if (!ctx->force_simt && lb2_gram_i8_mode(ctx) > 0 && n >= 4096) {   // tcgen05 kind::i8 on an Ozaki split (gram_i8.cu), opt-in
+    if (!ctx->force_simt && lb2_gram_i8_on(ctx, n)) {   // tcgen05 kind::i8 on an Ozaki split (gram_i8.cu)
       const int rc = gram_cols_i8_f64(ctx, n, m, nw, S, lds, W0, ldw0, G0, ldg0, W1, ldw1, G1, ldg1, tri_c0);
       if (rc != -100) return rc;
     }
@@ -1318,8 +1318,8 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
             T beta, T* Out, int64_t ldo) {
   if (n <= 0 || nb <= 0) return 0;
   if constexpr (std::is_same<T, double>::value) {
-    if (!ctx->force_simt && kd > 0 && lb2_gram_i8_mode(ctx) > 0 && ctx->nn_i8 != 0 && n >= 4096 && alpha == 1.0 && beta == 0.0) {
-      const int rc = tall_nn_i8_f64(ctx, n, kd, nb, S, lds, C, ldc, Out, ldo);   // int8 tensor path (gram_i8.cu), opt-in
+    if (!ctx->force_simt && kd > 0 && lb2_gram_i8_on(ctx, n) && ctx->nn_i8 != 0 && alpha == 1.0 && beta == 0.0) {
+      const int rc = tall_nn_i8_f64(ctx, n, kd, nb, S, lds, C, ldc, Out, ldo);   // int8 tensor path (gram_i8.cu)
       if (rc != -100) return rc;
     }
     if (!ctx->force_simt && kd > 0) {

@@ -92,8 +92,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
   __trap();
 }
+// The producer and MMA warps run WARP-UNIFORM code (all 32 lanes, identical values) and every single-thread instruction is
+// predicated on elect.sync inside its asm block.  Issuing from inside an `if (lane == 0)` region instead makes the operands
+// thread-private in the compiler's eyes: ptxas then wraps every UTCIMMA / UTMALDG / UTCBAR (which take uniform registers) in a
+// "waterfall" loop — ELECT, six R2UR.BROADCAST, branch — about 130 clocks per MMA against 64 clocks of MMA execution
+// (r02 SASS; the issue thread, not memory, was what held the tensor pipe at 48 %).
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(bar),
+      "r"(bytes)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
@@ -101,8 +111,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int32_t c0, int32_t c1, int32_t c2,
                                             int32_t c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}\n" ::"r"(
+          dst),
       "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// L2 prefetch of a box (UTMAPF.L2): no shared memory, no barrier — the later load of the same box finds it in L2
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];\n\t}\n" ::"l"(tm),
+      "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 // K-major SWIZZLE_128B shared-memory matrix descriptor (same as gram_tc5.cu): 8-row groups 1024 B apart
@@ -118,16 +140,21 @@ __device__ __forceinline__ uint32_t oz_idesc(int n16) {
 constexpr uint32_t OZ_DESC_HI = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "mov.b64 da, {%1, %5};\n\t"
       "mov.b64 db, {%2, %5};\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(OZ_DESC_HI)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
+      : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------- exponents
@@ -255,13 +282,13 @@ __device__ __forceinline__ void oz_mma_chunk(uint32_t sbase, uint32_t bar_full, 
 __global__ void __launch_bounds__(OZ_NT, 1)
     oz_gram_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                    const __grid_constant__ CUtensorMap tmB1, const OzItem* __restrict__ items, const int* __restrict__ cta_first,
-                   long long* __restrict__ part) {
+                   long long* __restrict__ part, int pf) {
   extern __shared__ __align__(1024) unsigned char smem_oz[];
   const uint32_t sbase = (smem_u32(smem_oz) + 1023u) & ~1023u;
   unsigned char* gbase = smem_oz + (sbase - smem_u32(smem_oz));
   const uint32_t bar_full = sbase + OZ_BAR, bar_empty = bar_full + 8 * OZ_NS, bar_accf = bar_empty + 8 * OZ_NS, bar_acce = bar_accf + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OZ_BAR + 8 * (2 * OZ_NS + 2) + 8);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   const int it0 = cta_first[blockIdx.x], it1 = cta_first[blockIdx.x + 1];
 
   if (tid == 0) {
@@ -281,11 +308,11 @@ __global__ void __launch_bounds__(OZ_NT, 1)
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {   // all 32 lanes: warp-uniform control flow, single-thread instructions elected inside their asm blocks
       uint32_t q = 0;
       auto load = [&](const CUtensorMap* tm, int col0, int slice, int chunk) {
         const uint32_t s = q % OZ_NS;
@@ -299,6 +326,14 @@ __global__ void __launch_bounds__(OZ_NT, 1)
         const OzGroup g = oz_group(im.group);
         const CUtensorMap* tb = im.b_sel ? &tmB1 : &tmB0;
         for (int chunk = im.chunk_begin; chunk < im.chunk_end; ++chunk) {
+          // the ring (192 KB) divided by the slot round trip bounds the fill rate, and most of the round trip is DRAM latency:
+          // the boxes of chunk + pf are requested into L2 now, so that their loads a few microseconds later are L2 hits
+          const int pc = chunk + pf;
+          if (pf > 0 && pc < im.chunk_end)
+            for (int sl = g.smin; sl < OZ_S; ++sl) {
+              tma_prefetch_4d(tb, 0, im.b_col0, sl, pc);
+              tma_prefetch_4d(&tmA, 0, im.a_col0, sl, pc);
+            }
           int jnext = OZ_S - 1;
           for (int a = g.amin; a < OZ_S; ++a) {
             const int jlo = max(g.smin, g.lmin - a);
@@ -310,7 +345,7 @@ __global__ void __launch_bounds__(OZ_NT, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {   // all 32 lanes: warp-uniform control flow, single-thread instructions elected inside their asm blocks
       uint32_t slot = 0, par = 0, segs = 0;
       for (int it = it0; it < it1; ++it) {
         const OzItem im = items[it];
@@ -394,15 +429,20 @@ struct OzCItem {
 __device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int32_t c0, int32_t c1, int32_t c2,
                                                int32_t c3, uint16_t mask) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], "
-      "[%2], %7;\n" ::"r"(dst),
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], %7;\n\t}\n" ::"r"(dst),
       "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
-               "h"(mask)
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(bar),
+      "h"(mask)
+      : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
@@ -463,7 +503,7 @@ __global__ void __launch_bounds__(OZ_NT, 1)
   const uint32_t fullB = sbase + OZ_BAR, emptyB = fullB + 8 * OZ_NB, fullA = emptyB + 8 * OZ_NB, emptyA = fullA + 8 * OZ_NA,
                  bar_accf = emptyA + 8 * OZ_NA, bar_acce = bar_accf + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OZ_BAR + 8 * (2 * OZ_NS + 2) + 8);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
   const int ra = (int)(rank >> 1), rb = (int)(rank & 1);
@@ -490,10 +530,10 @@ __global__ void __launch_bounds__(OZ_NT, 1)
   __syncthreads();
   cluster_sync_all();   // every CTA's barriers exist before a partner's TMA or commit can signal them
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // all 32 lanes: warp-uniform control flow, single-thread instructions elected inside their asm blocks
       uint32_t qa = 0, qb = 0;
       for (int it = it0; it < it1; ++it) {
         const OzCItem im = items[it];
@@ -521,7 +561,7 @@ __global__ void __launch_bounds__(OZ_NT, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // all 32 lanes: warp-uniform control flow, single-thread instructions elected inside their asm blocks
       OzRing rga{0, 0}, rgb{0, 0};
       uint32_t segs = 0;
       for (int it = it0; it < it1; ++it) {
@@ -646,7 +686,7 @@ __device__ __forceinline__ uint32_t on_idesc(int n16) {   // as oz_idesc, A oper
 __global__ void __launch_bounds__(OZ_NT, 1)
     oz_nn_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmC, const int* __restrict__ f,
                  double* __restrict__ Out, int64_t ldo, int64_t n, int nb, int nkc, int64_t nch, int njt, int ncoh,
-                 const int* __restrict__ nonfinite) {
+                 const int* __restrict__ nonfinite, int pf) {
   extern __shared__ __align__(1024) unsigned char smem_oz[];
   const uint32_t sbase = (smem_u32(smem_oz) + 1023u) & ~1023u;
   unsigned char* gbase = smem_oz + (sbase - smem_u32(smem_oz));
@@ -654,7 +694,7 @@ __global__ void __launch_bounds__(OZ_NT, 1)
   const uint32_t fullB = sbase + ON_BAR, emptyB = fullB + 8 * ON_NB, fullA = emptyB + 8 * ON_NB, emptyA = fullA + 8 * ON_NA,
                  bar_accf = emptyA + 8 * ON_NA, bar_acce = bar_accf + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + ON_BAR + 8 * (2 * ON_NA + 2 * ON_NB + 2) + 8);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   // CTA = (cohort, output tile): cohort c takes row chunks c, c + ncoh, ...; launch order puts the members of a cohort side by side
   const int jt = blockIdx.x % njt, coh = blockIdx.x / njt;
   const int j0 = jt * ON_TN;
@@ -678,13 +718,20 @@ __global__ void __launch_bounds__(OZ_NT, 1)
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // all 32 lanes: warp-uniform control flow, single-thread instructions elected inside their asm blocks
       uint32_t qa = 0, qb = 0;
       for (int64_t rc = coh; rc < nch; rc += ncoh)
         for (int kc = 0; kc < nkc; ++kc) {
+          if (pf > 0) {   // S slices of a later K chunk into L2 (see oz_gram_kernel)
+            int pk = kc + pf;
+            int64_t prc = rc;
+            while (pk >= nkc) { pk -= nkc; prc += ncoh; }
+            if (prc < nch)
+              for (int sl = 0; sl < OZ_S; ++sl) tma_prefetch_4d(&tmS, 0, pk * OZ_T, sl, (int32_t)prc);
+          }
           // all seven B slices first (the first step, A slice 6, multiplies every one of them), then A slices 6 .. 0
           for (int j = 0; j < OZ_S; ++j) {
             const uint32_t s = qb % ON_NB;
@@ -703,7 +750,7 @@ __global__ void __launch_bounds__(OZ_NT, 1)
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // all 32 lanes: warp-uniform control flow, single-thread instructions elected inside their asm blocks
       const uint32_t idesc = on_idesc(n16);
       OzRing rga{0, 0}, rgb{0, 0};
       uint32_t segs = 0;
@@ -850,6 +897,26 @@ int oz_make_map(CUtensorMap* tm, const int8_t* base, int m, int64_t nch) {
   return r == CUDA_SUCCESS ? 0 : -100;
 }
 
+// phase times of the int8 Gram: four events per call, resolved at the start of the next call (after the stream synchronisation that
+// call needs anyway) or by lb2_ctx_oz_stats
+void oz_stats_resolve(lb2_ctx* ctx) {
+  if (!ctx->oz_ev_pending) return;
+  if (cudaEventSynchronize(ctx->oz_ev[3]) == cudaSuccess) {
+    for (int i = 0; i < 3; i++) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ctx->oz_ev[i], ctx->oz_ev[i + 1]) == cudaSuccess) ctx->oz_ms[i] += t;
+    }
+    ctx->oz_calls++;
+  }
+  cudaGetLastError();
+  ctx->oz_ev_pending = false;
+}
+void oz_stats_mark(lb2_ctx* ctx, int i) {
+  if (!ctx->oz_ev[i] && cudaEventCreate(&ctx->oz_ev[i]) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaEventRecord(ctx->oz_ev[i], ctx->stream);
+  if (i == 3) ctx->oz_ev_pending = true;
+}
+
 // non-finite flag: the last int of the slice buffer (stable while the buffer lives; cleared by every call that splits anew)
 int* oz_flag(lb2_ctx* ctx) { return (int*)((char*)ctx->oz_buf + ctx->oz_bytes - 64); }
 
@@ -970,11 +1037,8 @@ int8_t* oz_buffer(lb2_ctx* ctx, size_t bytes) {
   ctx->oz_buf = nullptr;
   ctx->oz_bytes = 0;
   ctx->oz_tag_ptr = nullptr;
-  if (cudaMalloc(&ctx->oz_buf, bytes) != cudaSuccess) {
-    cudaGetLastError();
-    fprintf(stderr, "lobpcg_b200: cannot allocate %zu bytes for the int8 slices\n", bytes);
-    return nullptr;
-  }
+  ctx->oz_buf = oz_malloc(ctx, bytes);
+  if (!ctx->oz_buf) return nullptr;   // not enough device memory for the slices: the callers fall back to the DMMA kernels (-100)
   ctx->oz_bytes = bytes;
   return (int8_t*)ctx->oz_buf;
 }
@@ -1013,10 +1077,9 @@ int oz_run(lb2_ctx* ctx, int64_t n, std::vector<OzPlanTile>& tiles, OzOperand (&
   LB2_CUDA_OK(cudaMemcpyAsync(buf + o_tiles, tl.data(), sizeof(OzTile) * tl.size(), cudaMemcpyHostToDevice, ctx->stream));
   LB2_CUDA_OK(cudaMemcpyAsync(buf + o_grp, grp.data(), sizeof(int) * nitems, cudaMemcpyHostToDevice, ctx->stream));
   LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   const bool timing = lb2_gram_i8_mode(ctx) == 2;   // debug: per-phase device times on stderr
-  if (timing) for (auto& e : ev) cudaEventCreate(&e);
-  if (timing) cudaEventRecord(ev[0], ctx->stream);
+  oz_stats_resolve(ctx);
+  oz_stats_mark(ctx, 0);
   LB2_CUDA_OK(cudaMemsetAsync(oz_flag(ctx), 0, sizeof(int), ctx->stream));
   for (int q = 0; q < nop; q++)
     if (op[q].X)
@@ -1028,24 +1091,25 @@ int oz_run(lb2_ctx* ctx, int64_t n, std::vector<OzPlanTile>& tiles, OzOperand (&
     const OzOperand& src = o.X ? o : op[0];
     if (oz_make_map(&tm[q], src.slices, src.m, nch)) return -100;
   }
-  if (timing) cudaEventRecord(ev[1], ctx->stream);
+  oz_stats_mark(ctx, 1);
   LB2_CUDA_OK(cudaFuncSetAttribute(oz_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
-  oz_gram_kernel<<<ncta, OZ_NT, OZ_SMEM, ctx->stream>>>(tm[0], tm[1], tm[2], (const OzItem*)(buf + o_items), (const int*)(buf + o_cta), part);
+  oz_gram_kernel<<<ncta, OZ_NT, OZ_SMEM, ctx->stream>>>(tm[0], tm[1], tm[2], (const OzItem*)(buf + o_items), (const int*)(buf + o_cta), part,
+                                                        ctx->oz_prefetch > 0 ? ctx->oz_prefetch : 0);
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
-  if (timing) cudaEventRecord(ev[2], ctx->stream);
+  oz_stats_mark(ctx, 2);
   oz_reduce_kernel<<<dim3((unsigned)tl.size(), 8), 256, 0, ctx->stream>>>(part, (const OzTile*)(buf + o_tiles), (const int*)(buf + o_grp), 1,
                                                                           op[0].e, op[1].e, op[nop > 2 ? 2 : 1].e, G0, ldg0, G1, ldg1, mirror, oz_flag(ctx));
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
+  oz_stats_mark(ctx, 3);
   if (timing) {
-    cudaEventRecord(ev[3], ctx->stream);
-    cudaEventSynchronize(ev[3]);
+    cudaEventSynchronize(ctx->oz_ev[3]);
     float t01 = 0, t12 = 0, t23 = 0;
-    cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
+    cudaEventElapsedTime(&t01, ctx->oz_ev[0], ctx->oz_ev[1]); cudaEventElapsedTime(&t12, ctx->oz_ev[1], ctx->oz_ev[2]);
+    cudaEventElapsedTime(&t23, ctx->oz_ev[2], ctx->oz_ev[3]);
     fprintf(stderr, "gram_i8 n=%lld, %zu tiles: split %.2f ms, int8 MMA kernel %.2f ms (%zu items, %d CTAs), reduce %.2f ms\n",
             (long long)n, tiles.size(), t01, t12, nitems, ncta, t23);
-    for (auto& e : ev) cudaEventDestroy(e);
   }
   return 0;
 }
@@ -1091,7 +1155,8 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
                    int ldg1, int8_t* buf, size_t o_rest, unsigned long long* mx, int ncl_max) {
   const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
   auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
-  const double load_w = 0.01 * (ctx->oz_load_pct > 0 ? ctx->oz_load_pct : 100);
+  // r02 sweep at the C5 shape (one half-box = 8 KB per CTA and slice tile): 130 % 76.6 ms, 160 % 72.1, 200 % 63.1, 250 % 61.2, 300 % 63.7
+  const double load_w = 0.01 * (ctx->oz_load_pct > 0 ? ctx->oz_load_pct : 250);
   // units: (super-tile, group); a cluster advances at the pace of its slowest CTA; each CTA pulls HALF boxes
   struct Unit { int st, group; double cost; };
   std::vector<Unit> units;
@@ -1171,10 +1236,9 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
   LB2_CUDA_OK(cudaMemcpyAsync(buf + o_tiles, tl.data(), sizeof(OzTile) * tl.size(), cudaMemcpyHostToDevice, ctx->stream));
   LB2_CUDA_OK(cudaMemcpyAsync(buf + o_grp, grp.data(), sizeof(int) * nitems, cudaMemcpyHostToDevice, ctx->stream));
   LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   const bool timing = lb2_gram_i8_mode(ctx) == 2;
-  if (timing) for (auto& e : ev) cudaEventCreate(&e);
-  if (timing) cudaEventRecord(ev[0], ctx->stream);
+  oz_stats_resolve(ctx);
+  oz_stats_mark(ctx, 0);
   LB2_CUDA_OK(cudaMemsetAsync(oz_flag(ctx), 0, sizeof(int), ctx->stream));
   for (int q = 0; q < nop; q++)
     if (op[q].X)
@@ -1185,7 +1249,7 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
     const OzOperand& src = o.X ? o : op[0];
     if (oz_make_map64(&tm[q], src.slices, src.m, nch)) return -100;
   }
-  if (timing) cudaEventRecord(ev[1], ctx->stream);
+  oz_stats_mark(ctx, 1);
   {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(4 * ncl); cfg.blockDim = dim3(OZ_NT); cfg.dynamicSmemBytes = OZ_SMEM; cfg.stream = ctx->stream;
@@ -1199,19 +1263,19 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
   }
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
-  if (timing) cudaEventRecord(ev[2], ctx->stream);
+  oz_stats_mark(ctx, 2);
   oz_reduce_kernel<<<dim3((unsigned)tl.size(), 8), 256, 0, ctx->stream>>>(part, (const OzTile*)(buf + o_tiles), (const int*)(buf + o_grp), 4,
                                                                           op[0].e, op[1].e, op[nop > 2 ? 2 : 1].e, G0, ldg0, G1, ldg1, 0, oz_flag(ctx));
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
+  oz_stats_mark(ctx, 3);
   if (timing) {
-    cudaEventRecord(ev[3], ctx->stream);
-    cudaEventSynchronize(ev[3]);
+    cudaEventSynchronize(ctx->oz_ev[3]);
     float t01 = 0, t12 = 0, t23 = 0;
-    cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
+    cudaEventElapsedTime(&t01, ctx->oz_ev[0], ctx->oz_ev[1]); cudaEventElapsedTime(&t12, ctx->oz_ev[1], ctx->oz_ev[2]);
+    cudaEventElapsedTime(&t23, ctx->oz_ev[2], ctx->oz_ev[3]);
     fprintf(stderr, "gram_i8 n=%lld, %zu super-tiles (%zu tiles): split %.2f ms, int8 cluster kernel %.2f ms (%zu items, %d clusters), reduce %.2f ms\n",
             (long long)n, supers.size(), tl.size(), t01, t12, nitems, ncl, t23);
-    for (auto& e : ev) cudaEventDestroy(e);
   }
   return 0;
 }
@@ -1263,7 +1327,7 @@ int gram_i8_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_
   const size_t o_eA = bytesA + bytesB, o_eB = o_eA + al(sizeof(int) * ma), o_mx = o_eB + al(sizeof(int) * mb),
                o_rest = o_mx + al(sizeof(unsigned long long) * std::max(ma, mb));
   int8_t* buf = oz_buffer(ctx, o_rest + oz_rest_bytes(ctx, tiles.size()));
-  if (!buf) return -1;
+  if (!buf) return -100;
   ctx->oz_tag_ptr = nullptr;
   OzOperand op[3] = {{A, lda, ma, buf, (int*)(buf + o_eA)},
                      {same ? nullptr : B, ldb, mb, same ? buf : buf + bytesA, same ? (int*)(buf + o_eA) : (int*)(buf + o_eB)},
@@ -1339,7 +1403,7 @@ int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, in
   const size_t o_eS = bS + bW0 + bW1, o_e0 = o_eS + al(sizeof(int) * m), o_e1 = o_e0 + al(sizeof(int) * nw),
                o_mx = o_e1 + al(sizeof(int) * nw), o_rest = o_mx + al(sizeof(unsigned long long) * m);
   int8_t* buf = oz_buffer(ctx, o_rest + std::max(oz_rest_bytes(ctx, tiles.size()), 4 * oz_rest_bytes(ctx, supers.size())));
-  if (!buf) return -1;
+  if (!buf) return -100;
   int* eS = (int*)(buf + o_eS);
   // the slices of S stay valid for the projections of this pass (tall_nn_i8_f64): same block, not written in between
   ctx->oz_tag_ptr = S; ctx->oz_tag_n = n; ctx->oz_tag_m = m; ctx->oz_tag_ld = lds; ctx->oz_tag_e_off = o_eS;
@@ -1362,7 +1426,7 @@ int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int
   const int nkc = (kd + OZ_CH - 1) / OZ_CH;
   const size_t c_bytes = al((size_t)nkc * OZ_S * nb * OZ_CH), need_tail = c_bytes + al(sizeof(int) * nb);
   if (need_tail + 1024 > OZ_TAIL) return -100;
-  const bool cached = ctx->oz_buf && ctx->oz_tag_ptr == S && ctx->oz_tag_n == n && ctx->oz_tag_m == kd && ctx->oz_tag_ld == lds;
+  const bool cached = ctx->oz_reuse && ctx->oz_buf && ctx->oz_tag_ptr == S && ctx->oz_tag_n == n && ctx->oz_tag_m == kd && ctx->oz_tag_ld == lds;
   int8_t* buf;
   int* eS;
   if (cached) {
@@ -1372,7 +1436,7 @@ int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int
     const size_t bS = al((size_t)nch * OZ_S * kd * OZ_CH), o_eS = bS, o_mx = o_eS + al(sizeof(int) * kd),
                  tot = o_mx + al(sizeof(unsigned long long) * kd) + OZ_TAIL;
     buf = oz_buffer(ctx, tot);
-    if (!buf) return -1;
+    if (!buf) return -100;
     eS = (int*)(buf + o_eS);
     LB2_CUDA_OK(cudaMemsetAsync(oz_flag(ctx), 0, sizeof(int), ctx->stream));
     if (int rc = oz_split(ctx, n, kd, S, lds, buf, eS, (unsigned long long*)(buf + o_mx))) return rc;
@@ -1388,9 +1452,20 @@ int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int
   const int njt = (nb + ON_TN - 1) / ON_TN;
   const int ncoh = (int)std::max<int64_t>(1, std::min<int64_t>(nch, ctx->sm_count / njt));
   LB2_CUDA_OK(cudaFuncSetAttribute(oz_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ON_SMEM));
-  oz_nn_kernel<<<ncoh * njt, OZ_NT, ON_SMEM, ctx->stream>>>(tmS, tmC, f, Out, ldo, n, nb, nkc, nch, njt, ncoh, oz_flag(ctx));
+  oz_nn_kernel<<<ncoh * njt, OZ_NT, ON_SMEM, ctx->stream>>>(tmS, tmC, f, Out, ldo, n, nb, nkc, nch, njt, ncoh, oz_flag(ctx),
+                                                            ctx->oz_prefetch > 0 ? ctx->oz_prefetch : 0);
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// accumulated device times (ms) of the int8 Gram phases since the last query: out = {split, MMA kernel, reduce, calls}
+int oz_stats_query(lb2_ctx* ctx, double* out) {
+  cudaStreamSynchronize(ctx->stream);
+  oz_stats_resolve(ctx);
+  for (int i = 0; i < 3; i++) { out[i] = ctx->oz_ms[i]; ctx->oz_ms[i] = 0.0; }
+  out[3] = (double)ctx->oz_calls;
+  ctx->oz_calls = 0;
   return 0;
 }
 

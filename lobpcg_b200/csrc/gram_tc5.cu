@@ -86,16 +86,24 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128 (InstrDescriptor bit fields)
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_T >> 3) << 17) | ((uint32_t)(TC_T >> 4) << 24);
 
+// Single-thread instructions are issued from WARP-UNIFORM code and predicated on elect.sync: inside an `if (tid == 0)` region the
+// operands look thread-private to ptxas, which then wraps every UTCHMMA / UTMALDG / UTCBAR in an ELECT + R2UR.BROADCAST waterfall
+// loop (~130 clocks per MMA; found on the int8 kernels, gram_i8.cu).
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
+      : "memory");
 }
 
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
@@ -131,6 +139,7 @@ __global__ void __launch_bounds__(TC_NT, 1)
   const int64_t r_end = min(n, r_begin + rows_per_split);
   const int nchunks = (r_end > r_begin) ? (int)((r_end - r_begin + TC_BK - 1) / TC_BK) : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index the compiler knows to be uniform
 
   if (tid == 0) {
     for (int s = 0; s < TC_RAW; s++) mbar_init(bar0 + 8 * s, 1);
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(TC_NT, 1)
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // this thread's copy/convert units: TC_UNITS per operand tile; unit = (column c, k-unit u) -> 16 bytes = 4 rows of a column
   // a warp instruction covers 4 columns x all 8 k-units of the chunk: one full 128-byte line per column
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(TC_NT, 1)
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> tensor core (async proxy)
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {   // all 32 lanes of warp 0; the single-thread instructions are elected inside their asm blocks
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint32_t hi = sbase + (uint32_t)(chunk % TC_RAW) * TC_STAGE;
       const uint32_t lo = lo_base + (uint32_t)(chunk & 1) * TC_STAGE;
@@ -318,11 +327,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((1024u >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(bar),
+      "r"(bytes)
+      : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int32_t c0, int32_t c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}\n" ::"r"(dst),
       "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
@@ -354,6 +370,7 @@ __global__ void __launch_bounds__(TC_NT, 1)
   const int64_t r_end = min(n, r_begin + rows_per_split);
   const int nchunks = (r_end > r_begin) ? (int)((r_end - r_begin + TC_BK - 1) / TC_BK) : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index the compiler knows to be uniform
 
   if (tid == 0) {
     for (int s = 0; s < TC_RAW; s++) { mbar_init(bar_done + 8 * s, 1); mbar_init(bar_full + 8 * s, 1); }
@@ -370,9 +387,9 @@ __global__ void __launch_bounds__(TC_NT, 1)
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  auto issue_tma = [&](int chunk) {   // one thread
+  auto issue_tma = [&](int chunk) {   // warp 0, warp-uniform
     if (chunk < nchunks) {
       const uint32_t s = (uint32_t)(chunk % TC_RAW);
       const uint32_t st = sbase + s * T2_STAGE;
@@ -412,7 +429,7 @@ __global__ void __launch_bounds__(TC_NT, 1)
   auto done_bar = [&](int chunk) { return bar_done + 8u * (uint32_t)(chunk % TC_RAW); };
   auto ring_par = [&](int chunk) { return (uint32_t)((chunk / TC_RAW) & 1); };
 
-  if (tid == 0)
+  if (warp_u == 0)
     for (int c = 0; c < TC_AHEAD; c++) issue_tma(c);
 
   int drained = 0;
@@ -426,7 +443,7 @@ __global__ void __launch_bounds__(TC_NT, 1)
       const int gdone = (chunk - 1) / TC_FLUSH;
       if (drained < gdone) { drain(drained); drained++; }
     }
-    if (tid == 0) issue_tma(chunk + TC_AHEAD);
+    if (warp_u == 0) issue_tma(chunk + TC_AHEAD);
     mbar_wait(bar_full + 8 * stage, ring_par(chunk));     // both boxes of this chunk have landed (async proxy -> visible)
     // lo = rna_tf32(x - trunc_tf32(x)), unit by unit (layout-agnostic: the lo tile mirrors the raw tile byte for byte)
 #pragma unroll
@@ -442,7 +459,7 @@ __global__ void __launch_bounds__(TC_NT, 1)
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {   // all 32 lanes of warp 0; the single-thread instructions are elected inside their asm blocks
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint32_t hi = sbase + stage * T2_STAGE;
       const uint32_t lo = lo_base + (uint32_t)(chunk & 1) * T2_STAGE;

@@ -69,10 +69,12 @@ __device__ __forceinline__ uint64_t desc_n(uint32_t saddr, uint32_t lbo, uint32_
          ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void umma_n(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  // issued from warp-uniform code, predicated on elect.sync (see gram_tc5.cu: avoids ptxas' R2UR waterfall per MMA)
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(NT_NT, 1)
   const int tn = min(NT_T, (nb - c0 + 15) / 16 * 16);       // UMMA N of this CTA
   const int nchunks = (kd + NT_BK - 1) / NT_BK;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index the compiler knows to be uniform
   // D = F32, A = B = TF32, both K-major, N = tn, M = 128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tn >> 3) << 17) | ((uint32_t)(NT_T >> 4) << 24);
 
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(NT_NT, 1)
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // copy units.  A: 4-byte elements, a warp instruction = 32 consecutive rows of one k-column; B: (column c, k-unit u),
   // 8 columns x 4 units per warp instruction
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(NT_NT, 1)
       *reinterpret_cast<uint32_t*>(lob + aoff[i]) = rna_n(rv[i] - __uint_as_float(__float_as_uint(rv[i]) & 0xFFFFE000u));
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {   // all 32 lanes of warp 0
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint32_t st = sbase + (uint32_t)(chunk % NT_RAW) * NT_STAGE;
       const uint32_t alo = sbase + NT_LO0 + (uint32_t)(chunk & 1) * NT_TILE;
@@ -240,7 +243,11 @@ __global__ void __launch_bounds__(NT_NT, 1)
         umma_n(acc, ah, bl, idesc, 1u);
         umma_n(acc, ah, bh, idesc, 1u);
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(done_bar(chunk)) : "memory");
+      asm volatile(
+          "{\n\t.reg .pred q;\n\t"
+          "elect.sync _|q, 0xffffffff;\n\t"
+          "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(done_bar(chunk))
+          : "memory");
     }
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");

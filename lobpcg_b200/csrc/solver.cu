@@ -384,6 +384,8 @@ void Solver<T>::release() {
   if (arena) {
     cudaStreamSynchronize(ctx->stream);   // nothing may still be running on a block the next solve reuses
     arena_release(ctx, arena, arena_bytes);
+    if (ctx->active_solvers > 0) ctx->active_solvers--;
+    ctx->oz_reuse = false;
   }
   arena = nullptr;
   slab[0] = slab[1] = AS = wA = wB = nullptr;
@@ -454,6 +456,7 @@ int Solver<T>::alloc() {
   tall_bytes = tall_b;
   arena = arena_alloc(ctx, arena_bytes);
   if (!arena) return -1;
+  ctx->active_solvers++;
   char* base = (char*)arena;
   slab[0] = (T*)base; base += slab_b;
   slab[1] = (T*)base; base += slab_b;
@@ -805,6 +808,7 @@ int Solver<T>::rr_modified(int m) {
     int rc = chol ? gram_cols<T>(ctx, n, m, nwc, S, n, BW, n, Gw, m, AW, n, GAw, m, mxp)
                   : gram_cols<T>(ctx, n, m, nwc, S, n, AW, n, GAw, m, (const T*)nullptr, 0, (T*)nullptr, 0, mxp);
     tm.end();
+    ctx->oz_reuse = true;   // int8 path: S is not written again before this pass's projections X' = S Cx, P' = S Cp read its slices
     // algorithmic flops: rectangular [X P]^H W part + Hermitian W^H W part, per product
     phase_work[PH_GRAM] += (chol ? 2.0 : 1.0) * (Sc<T>::cplx ? 4.0 : 1.0) * (double)n * (2.0 * mxp * nwc + (double)nwc * (nwc + 1));
     phase_calls[PH_GRAM]++;
@@ -1475,6 +1479,7 @@ template <typename T>
 int Solver<T>::step_impl(int max_steps, int* passes_out) {
   int& passes = *passes_out;
   while (!done && passes < max_steps && iter < alg->maxIter) {
+    ctx->oz_reuse = false;   // int8 path: the slices of the previous pass's basis are stale
     T* S = Xp();
     T* V = S;
     T* W = col(S, k + np);
