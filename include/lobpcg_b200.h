@@ -41,6 +41,10 @@ int lb2_ctx_trim(lb2_ctx *ctx); /* free the solver arena this context keeps for 
 unsigned long long lb2_ctx_launches(lb2_ctx *ctx); /* kernels launched so far through this context */
 /* device times (ms) of the int8 tensor-path Gram since the last query: out4 = {split, MMA kernel, reduce, calls} */
 int lb2_ctx_oz_stats(lb2_ctx *ctx, double *out4);
+/* host-only self-check of the int8 schedules of the column-block products (no device needed): mode 0 = one tile per CTA with an
+ * equal-cost cut, 1 = lock-step cohorts, 2 = 4-CTA clusters (nworkers = clusters).  0 = exact cover of the outputs, the items of every
+ * (tile, level group) partition the rows.  stats[4] (may be NULL): items, busiest worker / mean, tiles written, workers used. */
+int lb2_oz_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int nworkers, int mode, double *stats);
 lb2_ctx *lb2_default_ctx(void);                    /* lazily created context on the current device */
 
 /* device memory for FFI callers that have no CUDA runtime of their own */

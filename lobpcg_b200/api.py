@@ -55,6 +55,7 @@ def _declare(L):
     L.lb2_ctx_launches.restype = C.c_ulonglong
     L.lb2_ctx_launches.argtypes = [vp]
     L.lb2_ctx_oz_stats.argtypes = [vp, C.POINTER(dbl)]
+    L.lb2_oz_plan_check.argtypes = [ci, ci, ci, ci, i64, ci, ci, C.POINTER(dbl)]
     L.lb2_default_ctx.restype = vp
     L.lb2_gram_wl_plan_check.argtypes = [ci, ci, ci, i64, ci, ci, C.POINTER(dbl)]
     L.lb2_gram_wl_cols_plan_check.argtypes = [ci, ci, ci, ci, i64, ci, ci, C.POINTER(dbl)]

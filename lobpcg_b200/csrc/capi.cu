@@ -294,6 +294,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "nn_bk")) c->nn_bk = value;
   else if (!strcmp(key, "nn_persist")) c->nn_persist = value;
   else if (!strcmp(key, "nn_stagger")) c->nn_stagger = value;
+  else if (!strcmp(key, "hostcopy_threads")) lb2::hostcopy_set_threads(c, value);
   else if (!strcmp(key, "gram_merge")) c->gram_merge = value;
   else if (!strcmp(key, "nn_warps")) c->nn_warps = value;
   else if (!strcmp(key, "force_simt")) c->force_simt = value;
@@ -323,6 +324,9 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
 }
 
 unsigned long long lb2_ctx_launches(lb2_ctx* c) { return c ? c->launches : 0ULL; }
+int lb2_oz_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int nworkers, int mode, double* stats) {
+  return lb2::oz_plan_check(m, nw, nprod, tri_c0, n, nworkers, mode, stats);
+}
 int lb2_ctx_oz_stats(lb2_ctx* c, double* out4) { return (c && out4) ? lb2::oz_stats_query(c, out4) : -1; }
 
 static std::mutex g_mu;

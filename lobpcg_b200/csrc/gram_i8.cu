@@ -1151,13 +1151,65 @@ int oz_max_clusters(lb2_ctx* ctx) {
   return ncl;
 }
 
-int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOperand (&op)[3], int nop, double* G0, int ldg0, double* G1,
-                   int ldg1, int8_t* buf, size_t o_rest, unsigned long long* mx, int ncl_max) {
-  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
-  auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
-  // r02 sweep at the C5 shape (one half-box = 8 KB per CTA and slice tile): 130 % 76.6 ms, 160 % 72.1, 200 % 63.1, 250 % 61.2, 300 % 63.7
-  const double load_w = 0.01 * (ctx->oz_load_pct > 0 ? ctx->oz_load_pct : 250);
-  // units: (super-tile, group); a cluster advances at the pace of its slowest CTA; each CTA pulls HALF boxes
+// Output tiles (one-tile-per-CTA kernel) and 2 x 2 super-tiles (cluster kernel) of the column-block products G_q = S^H W_q:
+// 128-column row panels over [0, tri_c0) and, separately, over the Hermitian block [tri_c0, m); tiles strictly below the diagonal
+// of that block are left out.  Super-tiles: A panels paired in order, B panels paired as (W0 tile j, W1 tile j) (both products) or
+// as neighbouring column tiles (one product); a missing partner repeats the panel and is not written out.  Host-only.
+void oz_cols_tiles(int m, int nw, int nprod, int tri_c0, bool w0_in_s, bool want_supers, std::vector<OzPlanTile>& tiles,
+                   std::vector<OzSuper>& supers) {
+  const bool herm = tri_c0 >= 0 && tri_c0 + nw == m;
+  const int split = herm ? tri_c0 : m;
+  std::vector<std::pair<int, int>> rows;
+  for (int c = 0; c < split; c += OZ_T) rows.emplace_back(c, std::min(OZ_T, split - c));
+  for (int c = split; c < m; c += OZ_T) rows.emplace_back(c, std::min(OZ_T, m - c));
+  const int ntn = (nw + OZ_T - 1) / OZ_T;
+  for (auto& rw : rows)
+    for (int q = 0; q < nprod; q++)
+      for (int tj = 0; tj < ntn; tj++) {
+        if (rw.first >= split && (rw.first - split) / OZ_T > tj) continue;   // below the diagonal of the Hermitian block
+        OzPlanTile pt{};
+        pt.t.a_col0 = rw.first; pt.t.a_cols = rw.second;
+        pt.t.b_cols = std::min(OZ_T, nw - tj * OZ_T);
+        pt.t.b_sel = q;
+        pt.t.b_col0 = tj * OZ_T + ((q == 0 && w0_in_s) ? tri_c0 : 0);   // in the column numbering of the slice array it is read from
+        pt.t.g_row0 = rw.first; pt.t.g_col0 = tj * OZ_T;
+        pt.t.diag = 0;
+        tiles.push_back(pt);
+      }
+  if (!want_supers || tiles.empty()) return;
+  std::vector<OzPanel> pa, pb;
+  std::vector<int> pb_gcol, pb_tj;
+  for (auto& rw : rows) pa.push_back({rw.first, rw.second, 0, 1});
+  if (pa.size() % 2) { OzPanel d = pa.back(); d.valid = 0; pa.push_back(d); }
+  auto bpanel = [&](int q, int tj) { return OzPanel{tj * OZ_T + ((q == 0 && w0_in_s) ? tri_c0 : 0), std::min(OZ_T, nw - tj * OZ_T), q, 1}; };
+  if (nprod == 2) {
+    for (int tj = 0; tj < ntn; tj++)
+      for (int q = 0; q < 2; q++) { pb.push_back(bpanel(q, tj)); pb_gcol.push_back(tj * OZ_T); pb_tj.push_back(tj); }
+  } else {
+    for (int tj = 0; tj < ntn; tj++) { pb.push_back(bpanel(0, tj)); pb_gcol.push_back(tj * OZ_T); pb_tj.push_back(tj); }
+    if (pb.size() % 2) { OzPanel d = pb.back(); d.valid = 0; pb.push_back(d); pb_gcol.push_back(pb_gcol.back()); pb_tj.push_back(pb_tj.back()); }
+  }
+  for (size_t ia = 0; ia < pa.size(); ia += 2)
+    for (size_t ib = 0; ib < pb.size(); ib += 2) {
+      OzSuper st{};
+      bool any = false;
+      for (int x = 0; x < 2; x++) { st.pa[x] = pa[ia + x]; st.g_row0[x] = pa[ia + x].col0; }
+      for (int y = 0; y < 2; y++) { st.pb[y] = pb[ib + y]; st.g_col0[y] = pb_gcol[ib + y]; }
+      for (int x = 0; x < 2; x++)
+        for (int y = 0; y < 2; y++) {
+          const bool below = st.pa[x].col0 >= split && (st.pa[x].col0 - split) / OZ_T > pb_tj[ib + y];
+          st.valid[x][y] = (st.pa[x].valid && st.pb[y].valid && !below) ? 1 : 0;
+          any = any || st.valid[x][y];
+        }
+      if (any) supers.push_back(st);
+    }
+}
+
+// Cluster schedule, host-only: (super-tile, level group) units laid end to end by cost and cut into equal pieces for ncl clusters
+// (a cluster advances at the pace of its slowest CTA; each CTA pulls HALF boxes); out: items, first item of every cluster, and
+// the output tiles (the wanted members of every super-tile; items of both groups of a super-tile are adjacent).
+void oz_schedule_cluster(const std::vector<OzSuper>& supers, int64_t nch, int ncl_max, double load_w, std::vector<OzCItem>& items,
+                         std::vector<int>& grp, std::vector<int>& cl_first, std::vector<OzTile>& tl, int* ncl_out) {
   struct Unit { int st, group; double cost; };
   std::vector<Unit> units;
   for (size_t i = 0; i < supers.size(); i++) {
@@ -1167,11 +1219,12 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
     units.push_back({(int)i, 1, std::max(18.0 * nfrac, 7.0 * load_w)});
   }
   const int ncl = (int)std::min<int64_t>(ncl_max, std::max<int64_t>(1, (int64_t)units.size() * nch / 8));
+  *ncl_out = ncl;
   double total = 0;
   for (auto& u : units) total += u.cost * (double)nch;
   const double L = total / ncl;
-  std::vector<OzCItem> items;
-  std::vector<int> item_cl, grp, cl_first(ncl + 1, 0);
+  std::vector<int> item_cl;
+  cl_first.assign(ncl + 1, 0);
   std::vector<std::pair<int, int>> unit_items(units.size());
   double U = 0;
   for (size_t ui = 0; ui < units.size(); ui++) {
@@ -1210,8 +1263,6 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
     cl_first[b] = (int)it;
   }
   cl_first[ncl] = (int)items.size();
-  // output tiles: the wanted members of every super-tile (items of both groups are adjacent: units 2 i and 2 i + 1)
-  std::vector<OzTile> tl;
   for (size_t i = 0; i < supers.size(); i++)
     for (int ia = 0; ia < 2; ia++)
       for (int ib = 0; ib < 2; ib++) {
@@ -1225,6 +1276,19 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
         t.diag = 0;
         tl.push_back(t);
       }
+}
+
+int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOperand (&op)[3], int nop, double* G0, int ldg0, double* G1,
+                   int ldg1, int8_t* buf, size_t o_rest, unsigned long long* mx, int ncl_max) {
+  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
+  auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  // r02 sweep at the C5 shape (one half-box = 8 KB per CTA and slice tile): 130 % 76.6 ms, 160 % 72.1, 200 % 63.1, 250 % 61.2, 300 % 63.7
+  const double load_w = 0.01 * (ctx->oz_load_pct > 0 ? ctx->oz_load_pct : 250);
+  std::vector<OzCItem> items;
+  std::vector<int> grp, cl_first;
+  std::vector<OzTile> tl;
+  int ncl = 1;
+  oz_schedule_cluster(supers, nch, ncl_max, load_w, items, grp, cl_first, tl, &ncl);
   const size_t nitems = items.size();
   const size_t o_part = o_rest, o_items = o_part + al(sizeof(long long) * nitems * 4 * 4 * OZ_T * OZ_T),
                o_cl = o_items + al(sizeof(OzCItem) * nitems), o_tiles = o_cl + al(sizeof(int) * (ncl + 1)),
@@ -1346,58 +1410,11 @@ int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, in
   const int nprod = (W1 && G1) ? 2 : 1;
   const bool herm = tri_c0 >= 0 && tri_c0 + nw == m;
   const bool w0_in_s = herm && W0 == S + (int64_t)tri_c0 * lds && ldw0 == lds;
-  const int split = herm ? tri_c0 : m;
-  std::vector<std::pair<int, int>> rows;
-  for (int c = 0; c < split; c += OZ_T) rows.emplace_back(c, std::min(OZ_T, split - c));
-  for (int c = split; c < m; c += OZ_T) rows.emplace_back(c, std::min(OZ_T, m - c));
-  const int ntn = (nw + OZ_T - 1) / OZ_T;
   std::vector<OzPlanTile> tiles;
-  for (auto& rw : rows)
-    for (int q = 0; q < nprod; q++)
-      for (int tj = 0; tj < ntn; tj++) {
-        if (rw.first >= split && (rw.first - split) / OZ_T > tj) continue;   // below the diagonal of the Hermitian block
-        OzPlanTile pt{};
-        pt.t.a_col0 = rw.first; pt.t.a_cols = rw.second;
-        pt.t.b_cols = std::min(OZ_T, nw - tj * OZ_T);
-        pt.t.b_sel = q;
-        pt.t.b_col0 = tj * OZ_T + ((q == 0 && w0_in_s) ? tri_c0 : 0);   // in the column numbering of the slice array it is read from
-        pt.t.g_row0 = rw.first; pt.t.g_col0 = tj * OZ_T;
-        pt.t.diag = 0;
-        tiles.push_back(pt);
-      }
-  if (tiles.empty()) return 0;
-  // 2 x 2 super-tiles for the cluster kernel: A panels paired in order, B panels paired as (W0 tile j, W1 tile j) (both products)
-  // or as neighbouring column tiles (one product); a missing partner repeats the panel and is not written out
   std::vector<OzSuper> supers;
   const int ncl_max = (ctx->oz_cluster != 0) ? oz_max_clusters(ctx) : 0;
-  if (ncl_max > 0) {
-    std::vector<OzPanel> pa, pb;
-    std::vector<int> pb_gcol, pb_tj;
-    for (auto& rw : rows) pa.push_back({rw.first, rw.second, 0, 1});
-    if (pa.size() % 2) { OzPanel d = pa.back(); d.valid = 0; pa.push_back(d); }
-    auto bpanel = [&](int q, int tj) { return OzPanel{tj * OZ_T + ((q == 0 && w0_in_s) ? tri_c0 : 0), std::min(OZ_T, nw - tj * OZ_T), q, 1}; };
-    if (nprod == 2) {
-      for (int tj = 0; tj < ntn; tj++)
-        for (int q = 0; q < 2; q++) { pb.push_back(bpanel(q, tj)); pb_gcol.push_back(tj * OZ_T); pb_tj.push_back(tj); }
-    } else {
-      for (int tj = 0; tj < ntn; tj++) { pb.push_back(bpanel(0, tj)); pb_gcol.push_back(tj * OZ_T); pb_tj.push_back(tj); }
-      if (pb.size() % 2) { OzPanel d = pb.back(); d.valid = 0; pb.push_back(d); pb_gcol.push_back(pb_gcol.back()); pb_tj.push_back(pb_tj.back()); }
-    }
-    for (size_t ia = 0; ia < pa.size(); ia += 2)
-      for (size_t ib = 0; ib < pb.size(); ib += 2) {
-        OzSuper st{};
-        bool any = false;
-        for (int x = 0; x < 2; x++) { st.pa[x] = pa[ia + x]; st.g_row0[x] = pa[ia + x].col0; }
-        for (int y = 0; y < 2; y++) { st.pb[y] = pb[ib + y]; st.g_col0[y] = pb_gcol[ib + y]; }
-        for (int x = 0; x < 2; x++)
-          for (int y = 0; y < 2; y++) {
-            const bool below = st.pa[x].col0 >= split && (st.pa[x].col0 - split) / OZ_T > pb_tj[ib + y];
-            st.valid[x][y] = (st.pa[x].valid && st.pb[y].valid && !below) ? 1 : 0;
-            any = any || st.valid[x][y];
-          }
-        if (any) supers.push_back(st);
-      }
-  }
+  oz_cols_tiles(m, nw, nprod, tri_c0, w0_in_s, ncl_max > 0, tiles, supers);
+  if (tiles.empty()) return 0;
   const size_t bS = al((size_t)nch * OZ_S * m * OZ_CH), bW0 = w0_in_s ? 0 : al((size_t)nch * OZ_S * nw * OZ_CH),
                bW1 = nprod == 2 ? al((size_t)nch * OZ_S * nw * OZ_CH) : 0;
   const size_t o_eS = bS + bW0 + bW1, o_e0 = o_eS + al(sizeof(int) * m), o_e1 = o_e0 + al(sizeof(int) * nw),
@@ -1456,6 +1473,106 @@ int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int
                                                             ctx->oz_prefetch > 0 ? ctx->oz_prefetch : 0);
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Host-only self-check of the int8 schedules of the column-block products (no device needed; tests/test_oz_plan.py).
+// mode 0: one tile per CTA, equal-cost cut; 1: lock-step cohorts; 2: 4-CTA clusters (ncta = resident clusters).  Verifies that every
+// output entry that is not in a tile strictly below the diagonal of the Hermitian block is produced by exactly one tile, that the
+// items of every (tile or super-tile, level group) partition the row chunks, that a worker's items are contiguous, and (lock-step)
+// that no CTA has more than one item.  stats[4]: items, busiest worker / mean (cost model), tiles written, workers used.
+int oz_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int nworkers, int mode, double* stats) {
+  if (m <= 0 || nw <= 0 || nprod < 1 || nprod > 2 || n <= 0 || nworkers < 1) return 1;
+  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
+  std::vector<OzPlanTile> tiles;
+  std::vector<OzSuper> supers;
+  oz_cols_tiles(m, nw, nprod, tri_c0, false, mode == 2, tiles, supers);
+  if (tiles.empty()) return 2;
+  std::vector<OzTile> tl;
+  std::vector<int> grp, first;
+  std::vector<std::pair<int64_t, int64_t>> ranges;   // chunk range of every item
+  std::vector<double> wcost;
+  int nused = 0;
+  if (mode == 2) {
+    if (supers.empty()) return 3;
+    std::vector<OzCItem> items;
+    int ncl = 1;
+    oz_schedule_cluster(supers, nch, nworkers, 2.5, items, grp, first, tl, &ncl);
+    nused = ncl;
+    wcost.assign(ncl, 0.0);
+    for (auto& im : items) ranges.emplace_back(im.chunk_begin, im.chunk_end);
+    for (int b = 0; b < ncl; b++)
+      for (int i = first[b]; i < first[b + 1]; i++) {   // the scheduler's own cost model (oz_schedule_cluster)
+        const double nfrac = std::max(items[i].n16[0], items[i].n16[1]) / 128.0;
+        const double c = grp[i] ? std::max(18.0 * nfrac, 7.0 * 2.5) : std::max(10.0 * nfrac, 4.0 * 2.5);
+        wcost[b] += c * (double)(ranges[i].second - ranges[i].first);
+      }
+    if (first[ncl] != (int)items.size()) return 4;
+    // a super-tile's items: both groups adjacent, each group a partition of [0, nch)
+    for (auto& t : tl) {
+      for (int g = 0; g < 2; g++) {
+        int64_t r = 0;
+        for (int i = t.first; i < t.last; i++)
+          if (grp[i] == g) { if (ranges[i].first != r) return 5; r = ranges[i].second; }
+        if (r != nch) return 6;
+      }
+      if (t.rank < 0 || t.rank > 3) return 7;
+    }
+  } else {
+    std::vector<OzItem> items;
+    const int ncta = (int)std::min<int64_t>(nworkers, std::max<int64_t>(1, (int64_t)tiles.size() * 2 * nch / 8));
+    oz_schedule(tiles, nch, ncta, 1.0, mode == 1, items, first);
+    nused = ncta;
+    wcost.assign(ncta, 0.0);
+    for (auto& im : items) { ranges.emplace_back(im.chunk_begin, im.chunk_end); grp.push_back(im.group); }
+    if (first[ncta] != (int)items.size()) return 4;
+    for (int b = 0; b < ncta; b++) {
+      if (mode == 1 && first[b + 1] - first[b] > 1 && (int64_t)tiles.size() * 3 <= ncta) return 8;
+      for (int i = first[b]; i < first[b + 1]; i++) {   // the scheduler's own cost model (oz_schedule, load_w = 1)
+        const double nfrac = items[i].n16 / 128.0;
+        const double c = grp[i] ? std::max(18.0 * nfrac, 14.0) : std::max(10.0 * nfrac, 8.0);
+        wcost[b] += c * (double)(ranges[i].second - ranges[i].first);
+      }
+    }
+    for (size_t ti = 0; ti < tiles.size(); ti++) {
+      const OzTile& t = tiles[ti].t;
+      const int st = t.stride ? t.stride : 1;
+      for (int g = 0; g < 2; g++) {
+        std::vector<std::pair<int64_t, int64_t>> rs;
+        for (int i = t.first; i < t.last; i += st)
+          if (items[i].tile == (int)ti && grp[i] == g) rs.push_back(ranges[i]);
+          else if (items[i].tile != (int)ti) return 9;
+        std::sort(rs.begin(), rs.end());
+        int64_t r = 0;
+        for (auto& x : rs) { if (x.first != r) return 5; r = x.second; }
+        if (r != nch) return 6;
+      }
+      tl.push_back(t);
+    }
+  }
+  // coverage of the outputs
+  const bool herm = tri_c0 >= 0 && tri_c0 + nw == m;
+  std::vector<int> cover((size_t)nprod * m * nw, 0);
+  for (auto& t : tl) {
+    if (t.a_col0 < 0 || t.a_col0 + t.a_cols > m || t.g_col0 < 0 || t.g_col0 + t.b_cols > nw || t.b_sel < 0 || t.b_sel >= nprod) return 10;
+    for (int i = 0; i < t.a_cols; i++)
+      for (int j = 0; j < t.b_cols; j++) cover[((size_t)t.b_sel * m + t.g_row0 + i) * nw + t.g_col0 + j]++;
+  }
+  for (int q = 0; q < nprod; q++)
+    for (int i = 0; i < m; i++)
+      for (int j = 0; j < nw; j++) {
+        const int c = cover[((size_t)q * m + i) * nw + j];
+        const bool below_tile = herm && i >= tri_c0 && (i - tri_c0) / OZ_T > j / OZ_T;
+        if (c > 1 || (c == 0 && !below_tile)) return 11;
+      }
+  double mx = 0, sum = 0;
+  for (double c : wcost) { mx = std::max(mx, c); sum += c; }
+  if (stats) {
+    stats[0] = (double)ranges.size();
+    stats[1] = sum > 0 ? mx / (sum / nused) : 1.0;
+    stats[2] = (double)tl.size();
+    stats[3] = (double)nused;
+  }
   return 0;
 }
 
