@@ -274,6 +274,7 @@ void lb2_ctx_destroy(lb2_ctx* c) {
   lb2::hostcopy_free(c);
   if (c->ws) cudaFree(c->ws);
   if (c->oz_buf) cudaFree(c->oz_buf);
+  if (c->oz_hint) cudaFree(c->oz_hint);
   for (auto& e : c->oz_ev) if (e) cudaEventDestroy(e);
   if (c->solver_ws) cudaFree(c->solver_ws);
   if (c->solver_hws) free(c->solver_hws);
@@ -306,6 +307,7 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "oz_cluster")) c->oz_cluster = value;
   else if (!strcmp(key, "oz_lockstep")) c->oz_lockstep = value;
   else if (!strcmp(key, "oz_prefetch")) c->oz_prefetch = value;
+  else if (!strcmp(key, "oz_hints")) c->oz_hints = value;
   else if (!strcmp(key, "nn_i8")) c->nn_i8 = value;
   else if (!strcmp(key, "oz_clusters")) c->oz_clusters = value;
   else if (!strcmp(key, "gram_tma")) c->gram_tma = value;

@@ -29,6 +29,13 @@ struct lb2_ctx {
   bool oz_ev_pending = false;
   double oz_ms[3] = {0.0, 0.0, 0.0};
   long long oz_calls = 0;
+  // exponent hints of the three operand roles of the solver's column-block Gram (device: 3 x 4096 exponents + 3 redo flags)
+  void* oz_hint = nullptr;
+  bool oz_hint_valid[3] = {false, false, false};
+  int64_t oz_hint_n[3] = {0, 0, 0};
+  int oz_hint_m[3] = {0, 0, 0};
+  long long oz_hint_redos = 0;
+  int oz_hints = 1;          // option: 0 = every split takes its column maxima in a separate pass
   bool oz_reuse = false;     // set by the solver between the Gram of a pass and its projections: only then are the cached slices trusted
   int active_solvers = 0;    // solvers holding an arena on this context (their slice buffer must not be taken away under memory pressure)
   // small-dense library handles (created lazily)

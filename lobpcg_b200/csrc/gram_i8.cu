@@ -191,12 +191,14 @@ __global__ void oz_exp_kernel(const unsigned long long* __restrict__ mx, int m, 
 
 // ---------------------------------------------------------------------------------------------------- split
 // out[((rc * 7 + s) * m + c) * 128 + rr]: warp = one column of one chunk, lane = 4 consecutive rows (32 bytes in, 7 x 4 bytes out)
+template <bool TRACK>
 __global__ void __launch_bounds__(256)
     oz_split_kernel(const double* __restrict__ X, int64_t ld, int64_t n, int m, const int* __restrict__ e, int8_t* __restrict__ out,
-                    int chunks_per_cta) {
+                    int chunks_per_cta, unsigned long long* __restrict__ mx) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.y * 8 + warp;
   if (c >= m) return;
+  unsigned long long vmax = 0;   // TRACK: largest |x| of this warp's part of the column (the exponents came from a hint)
   const double scale = __longlong_as_double((long long)(1023 + OZ_SHIFT - e[c]) << 52);
   const double* x = X + (int64_t)c * ld;
   const bool vec = ((ld & 1) == 0) && (((uintptr_t)X & 15) == 0);
@@ -215,6 +217,13 @@ __global__ void __launch_bounds__(256)
     long long N[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) N[k] = __double2ll_rn(v[k] * scale);
+    if constexpr (TRACK) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v[k]));
+        vmax = b > vmax ? b : vmax;
+      }
+    }
     uint32_t* o = reinterpret_cast<uint32_t*>(out + ((rc * OZ_S) * (int64_t)m + c) * OZ_CH + lane * 4);
 #pragma unroll
     for (int i = 0; i < OZ_S; i++) {
@@ -228,6 +237,35 @@ __global__ void __launch_bounds__(256)
       o[(int64_t)i * m * (OZ_CH / 4)] = w;
     }
   }
+  if constexpr (TRACK) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(0xffffffffu, vmax, o);
+      vmax = t > vmax ? t : vmax;
+    }
+    if (lane == 0 && vmax) atomicMax(mx + c, vmax);
+  }
+}
+
+// After a split with HINTED exponents: were they right?  e_used[c] must cover the column's actual maximum (else digits
+// overflowed) and must not exceed what the maximum needs by more than 4 bits (else precision was given away); either sets
+// *redo.  The hint for the next split of this operand role is the exponent the fresh maximum needs plus one guard bit.
+__global__ void oz_hint_check_kernel(const unsigned long long* __restrict__ mx, int m, const int* __restrict__ e_used,
+                                     int* __restrict__ hint, int* __restrict__ redo, int* __restrict__ nonfinite) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  const unsigned long long b = mx[c];
+  if (((b >> 52) & 0x7FF) == 0x7FF) atomicOr(nonfinite, 1);
+  int need = 0;
+  if (b) need = max(-900, min(900, (int)((b >> 52) & 0x7FF) - 1023 + 2));
+  if (b && (need > e_used[c] || e_used[c] - need > 4)) atomicOr(redo, 1);
+  if (!b && e_used[c] != 1) { /* an all-zero column is exact with any exponent */ }
+  hint[c] = need + 1;
+}
+// fresh exponents -> hint (+ 1 guard bit) after a full (absmax) split
+__global__ void oz_hint_store_kernel(const int* __restrict__ e, int m, int* __restrict__ hint) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < m) hint[c] = e[c] + 1;
 }
 
 // ---------------------------------------------------------------------------------------------------- main kernel
@@ -921,15 +959,38 @@ void oz_stats_mark(lb2_ctx* ctx, int i) {
 int* oz_flag(lb2_ctx* ctx) { return (int*)((char*)ctx->oz_buf + ctx->oz_bytes - 64); }
 
 // exponents + slices of an n x m f64 block
-int oz_split(lb2_ctx* ctx, int64_t n, int m, const double* X, int64_t ld, int8_t* slices, int* e, unsigned long long* mx) {
+constexpr int OZ_HINT_MAX = 4096;   // columns per operand role that can carry exponent hints
+
+// exponents + slices of an n x m f64 block.  role >= 0 (operand of the solver's column-block Gram: 0 = [X P W], 1 = B W, 2 = A W)
+// with use_hint: the exponents are the ones the PREVIOUS split of this role suggested (that split's column maxima + 1 guard bit),
+// the column maxima are collected by the split kernel itself and oz_hint_check_kernel decides whether the split stands
+// (ctx->oz_redo[role], read by the caller) — the separate pass over the block for its maxima (a third of the split's time) is gone.
+int oz_split(lb2_ctx* ctx, int64_t n, int m, const double* X, int64_t ld, int8_t* slices, int* e, unsigned long long* mx,
+             int role = -1, bool use_hint = false) {
   LB2_CUDA_OK(cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * m, ctx->stream));
+  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
+  const int cpc = 16;
+  const dim3 sgrid((unsigned)((nch + cpc - 1) / cpc), (m + 7) / 8);
+  int* hint = (role >= 0 && ctx->oz_hint && m <= OZ_HINT_MAX) ? (int*)ctx->oz_hint + (size_t)role * OZ_HINT_MAX : nullptr;
+  if (use_hint && hint) {
+    int* redo = (int*)ctx->oz_hint + 3 * OZ_HINT_MAX + role;
+    LB2_CUDA_OK(cudaMemcpyAsync(e, hint, sizeof(int) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+    LB2_CUDA_OK(cudaMemsetAsync(redo, 0, sizeof(int), ctx->stream));
+    oz_split_kernel<true><<<sgrid, 256, 0, ctx->stream>>>(X, ld, n, m, e, slices, cpc, mx);
+    oz_hint_check_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(mx, m, e, hint, redo, oz_flag(ctx));
+    ctx->launches += 2;
+    LB2_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   const int64_t rows_per_cta = 65536;
   oz_absmax_kernel<<<dim3((unsigned)((n + rows_per_cta - 1) / rows_per_cta), m), 256, 0, ctx->stream>>>(X, ld, n, rows_per_cta, mx);
   oz_exp_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(mx, m, e, oz_flag(ctx));
-  const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
-  const int cpc = 16;
-  oz_split_kernel<<<dim3((unsigned)((nch + cpc - 1) / cpc), (m + 7) / 8), 256, 0, ctx->stream>>>(X, ld, n, m, e, slices, cpc);
+  oz_split_kernel<false><<<sgrid, 256, 0, ctx->stream>>>(X, ld, n, m, e, slices, cpc, mx);
   ctx->launches += 3;
+  if (hint) {
+    oz_hint_store_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(e, m, hint);
+    ctx->launches++;
+  }
   LB2_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1050,7 +1111,36 @@ namespace {
 struct OzOperand {          // one f64 block and where its slices / exponents live
   const double* X; int64_t ld; int m;
   int8_t* slices; int* e;
+  int role = -1;            // >= 0: operand role of the solver's column-block Gram (exponent hints carried from pass to pass)
 };
+
+// splits of the operands of a run; hinted splits are verified (one small device-to-host read) and redone in full when the hint was off
+int oz_split_operands(lb2_ctx* ctx, int64_t n, OzOperand (&op)[3], int nop, unsigned long long* mx) {
+  if (!ctx->oz_hint && ctx->oz_hints != 0) {
+    if (cudaMalloc(&ctx->oz_hint, sizeof(int) * (3 * OZ_HINT_MAX + 4)) != cudaSuccess) { cudaGetLastError(); ctx->oz_hint = nullptr; }
+  }
+  bool hinted[3] = {false, false, false};
+  for (int q = 0; q < nop; q++) {
+    if (!op[q].X) continue;
+    const int r = op[q].role;
+    const bool ok = ctx->oz_hints != 0 && ctx->oz_hint && r >= 0 && r < 3 && op[q].m <= OZ_HINT_MAX && ctx->oz_hint_valid[r] &&
+                    ctx->oz_hint_n[r] == n && ctx->oz_hint_m[r] == op[q].m;
+    if (int rc = oz_split(ctx, n, op[q].m, op[q].X, op[q].ld, op[q].slices, op[q].e, mx, r, ok)) return rc;
+    hinted[q] = ok;
+    if (r >= 0 && r < 3) { ctx->oz_hint_valid[r] = ctx->oz_hint != nullptr; ctx->oz_hint_n[r] = n; ctx->oz_hint_m[r] = op[q].m; }
+  }
+  if (hinted[0] || hinted[1] || hinted[2]) {
+    int redo[3] = {0, 0, 0};
+    LB2_CUDA_OK(cudaMemcpyAsync(redo, (int*)ctx->oz_hint + 3 * OZ_HINT_MAX, sizeof(redo), cudaMemcpyDeviceToHost, ctx->stream));
+    LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < nop; q++)
+      if (hinted[q] && redo[op[q].role]) {   // a column grew past its guard bit or shrank by more than 4 bits: split again from fresh maxima
+        ctx->oz_hint_redos++;
+        if (int rc = oz_split(ctx, n, op[q].m, op[q].X, op[q].ld, op[q].slices, op[q].e, mx, op[q].role, false)) return rc;
+      }
+  }
+  return 0;
+}
 
 // split the operands, run the tile list, reduce.  B panels come from operand 1 (b_sel = 0) or operand 2 (b_sel = 1); an
 // operand with X == nullptr aliases the slices of operand 0 (its slices / e pointers are then set by the caller).
@@ -1081,9 +1171,7 @@ int oz_run(lb2_ctx* ctx, int64_t n, std::vector<OzPlanTile>& tiles, OzOperand (&
   oz_stats_resolve(ctx);
   oz_stats_mark(ctx, 0);
   LB2_CUDA_OK(cudaMemsetAsync(oz_flag(ctx), 0, sizeof(int), ctx->stream));
-  for (int q = 0; q < nop; q++)
-    if (op[q].X)
-      if (int rc = oz_split(ctx, n, op[q].m, op[q].X, op[q].ld, op[q].slices, op[q].e, mx)) return rc;
+  if (int rc = oz_split_operands(ctx, n, op, nop, mx)) return rc;
   alignas(64) CUtensorMap tm[3];
   for (int q = 0; q < 3; q++) {
     const OzOperand& o = op[q < nop ? q : 0];
@@ -1304,9 +1392,7 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
   oz_stats_resolve(ctx);
   oz_stats_mark(ctx, 0);
   LB2_CUDA_OK(cudaMemsetAsync(oz_flag(ctx), 0, sizeof(int), ctx->stream));
-  for (int q = 0; q < nop; q++)
-    if (op[q].X)
-      if (int rc = oz_split(ctx, n, op[q].m, op[q].X, op[q].ld, op[q].slices, op[q].e, mx)) return rc;
+  if (int rc = oz_split_operands(ctx, n, op, nop, mx)) return rc;
   alignas(64) CUtensorMap tm[3];
   for (int q = 0; q < 3; q++) {
     const OzOperand& o = op[q < nop ? q : 0];
@@ -1424,9 +1510,9 @@ int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, in
   int* eS = (int*)(buf + o_eS);
   // the slices of S stay valid for the projections of this pass (tall_nn_i8_f64): same block, not written in between
   ctx->oz_tag_ptr = S; ctx->oz_tag_n = n; ctx->oz_tag_m = m; ctx->oz_tag_ld = lds; ctx->oz_tag_e_off = o_eS;
-  OzOperand op[3] = {{S, lds, m, buf, eS},
-                     {w0_in_s ? nullptr : W0, ldw0, nw, w0_in_s ? buf : buf + bS, w0_in_s ? eS : (int*)(buf + o_e0)},
-                     {nprod == 2 ? W1 : nullptr, ldw1, nw, buf + bS + bW0, (int*)(buf + o_e1)}};
+  OzOperand op[3] = {{S, lds, m, buf, eS, 0},
+                     {w0_in_s ? nullptr : W0, ldw0, nw, w0_in_s ? buf : buf + bS, w0_in_s ? eS : (int*)(buf + o_e0), 1},
+                     {nprod == 2 ? W1 : nullptr, ldw1, nw, buf + bS + bW0, (int*)(buf + o_e1), 2}};
   // the reduce kernel indexes the exponents with the tile's b_col0, which already carries tri_c0 for an aliased W0
   if (!supers.empty())
     return oz_run_cluster(ctx, n, supers, op, nprod == 2 ? 3 : 2, G0, ldg0, G1, ldg1, buf, o_rest, (unsigned long long*)(buf + o_mx), ncl_max);

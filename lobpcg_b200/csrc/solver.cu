@@ -457,6 +457,8 @@ int Solver<T>::alloc() {
   arena = arena_alloc(ctx, arena_bytes);
   if (!arena) return -1;
   ctx->active_solvers++;
+  // int8 path: exponent hints never cross solves (a solve must not depend on what ran before it on this context)
+  ctx->oz_hint_valid[0] = ctx->oz_hint_valid[1] = ctx->oz_hint_valid[2] = false;
   char* base = (char*)arena;
   slab[0] = (T*)base; base += slab_b;
   slab[1] = (T*)base; base += slab_b;

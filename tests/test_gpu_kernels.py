@@ -670,6 +670,42 @@ def test_tall_nn_i8_matches_extended_precision(ctx, shape):
         ctx.set_option("gram_i8", 0)
 
 
+def test_gram_cols_i8_exponent_hints(ctx):
+    """The solver's column-block Gram carries the column exponents from call to call (the split then collects the maxima itself
+    instead of a separate pass).  A column that grew past the guard bit or shrank by more than 4 bits must trigger a fresh
+    split: results stay at the accuracy of the unhinted path whatever the previous call saw."""
+    rng = np.random.default_rng(77)
+    n, mxp, nw = 20000, 140, 70
+    S = _wide_columns(rng, n, mxp + nw)
+    i, j = np.meshgrid(np.arange(mxp + nw), np.arange(nw), indexing="ij")
+    keep = ~(i - mxp > j)
+
+    def run(Sm):
+        AW = np.asfortranarray(1.5 * Sm[:, mxp:])
+        dS, dAW = api.DeviceArray.from_numpy(ctx, np.asfortranarray(Sm)), api.DeviceArray.from_numpy(ctx, AW)
+        G0, G1 = api.gram_cols(ctx, dS, dS.cols(mxp, nw), dAW, tri_c0=mxp)
+        nrm = np.sqrt((Sm * Sm).sum(0))
+        for got, ref, sc in ((G0.numpy(ctx), Sm.T @ Sm[:, mxp:], np.outer(nrm, nrm[mxp:])), (G1.numpy(ctx), Sm.T @ AW, 1.5 * np.outer(nrm, nrm[mxp:]))):
+            assert (np.abs(got - ref) / sc)[keep].max() < 2e-14
+        return G0.numpy(ctx)
+
+    ctx.set_option("gram_i8", 1)
+    try:
+        a = run(S)                      # fresh maxima
+        b = run(S)                      # hinted (same data: one guard bit coarser digits, same result to rounding)
+        assert np.abs(a - b)[keep].max() <= 1e-15 * np.abs(a).max()
+        S2 = S.copy(); S2[:, 5] *= 2.0 ** 9; S2[:, mxp + 3] *= 2.0 ** -30; S2[:, 17] *= 1.7
+        run(S2)                         # column 5 overflows its hint, column mxp + 3 lost 30 bits: both must be split afresh
+        run(S2)
+        ctx.set_option("oz_hints", 0)
+        c = run(S2)
+        ctx.set_option("oz_hints", 1)
+        d = run(S2)
+        assert np.abs(c - d)[keep].max() <= 1e-15 * np.abs(c).max()
+    finally:
+        ctx.set_option("gram_i8", 0); ctx.set_option("oz_hints", 1)
+
+
 def test_int8_path_propagates_non_finite_input(ctx):
     """A NaN or Inf anywhere in an operand cannot be represented by the integer slices: the int8 path flags it while it looks
     for the column maxima and returns NaN outputs (a reference BLAS would propagate it to the affected entries; here the whole
