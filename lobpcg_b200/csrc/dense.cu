@@ -1318,8 +1318,10 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
             T beta, T* Out, int64_t ldo) {
   if (n <= 0 || nb <= 0) return 0;
   if constexpr (std::is_same<T, double>::value) {
-    if (!ctx->force_simt && kd > 0 && lb2_gram_i8_on(ctx, n) && ctx->nn_i8 != 0 && alpha == 1.0 && beta == 0.0) {
-      const int rc = tall_nn_i8_f64(ctx, n, kd, nb, S, lds, C, ldc, Out, ldo);   // int8 tensor path (gram_i8.cu)
+    // int8 tensor path (gram_i8.cu): plain products always; updates (alpha, beta general) when the slices of S are already there
+    if (!ctx->force_simt && kd > 0 && lb2_gram_i8_on(ctx, n) && ctx->nn_i8 != 0 &&
+        ((alpha == 1.0 && beta == 0.0) || oz_slices_cached(ctx, S, n, kd, lds))) {
+      const int rc = tall_nn_i8_f64(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
       if (rc != -100) return rc;
     }
     if (!ctx->force_simt && kd > 0) {

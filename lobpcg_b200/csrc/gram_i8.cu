@@ -724,7 +724,7 @@ __device__ __forceinline__ uint32_t on_idesc(int n16) {   // as oz_idesc, A oper
 __global__ void __launch_bounds__(OZ_NT, 1)
     oz_nn_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmC, const int* __restrict__ f,
                  double* __restrict__ Out, int64_t ldo, int64_t n, int nb, int nkc, int64_t nch, int njt, int ncoh,
-                 const int* __restrict__ nonfinite, int pf) {
+                 const int* __restrict__ nonfinite, int pf, double alpha, double beta) {
   extern __shared__ __align__(1024) unsigned char smem_oz[];
   const uint32_t sbase = (smem_u32(smem_oz) + 1023u) & ~1023u;
   unsigned char* gbase = smem_oz + (sbase - smem_u32(smem_oz));
@@ -865,7 +865,11 @@ __global__ void __launch_bounds__(OZ_NT, 1)
           for (int i = 0; i < 32; i++) {
             const int col = j0 + cq * 32 + i;
             // 2^(f - 62) as an exact double (f is clamped far inside the exponent range by the split)
-            if (col < nb) Out[row + (int64_t)col * ldo] = sum[i] * __longlong_as_double((long long)(1023 + f[col] - 2 * OZ_SHIFT + 48) << 52) + poison;
+            if (col < nb) {
+              double* o = Out + row + (int64_t)col * ldo;
+              const double v = alpha * (sum[i] * __longlong_as_double((long long)(1023 + f[col] - 2 * OZ_SHIFT + 48) << 52)) + poison;
+              *o = (beta != 0.0) ? v + beta * *o : v;
+            }
           }
         }
       }
@@ -1478,7 +1482,8 @@ int gram_i8_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_
                o_rest = o_mx + al(sizeof(unsigned long long) * std::max(ma, mb));
   int8_t* buf = oz_buffer(ctx, o_rest + oz_rest_bytes(ctx, tiles.size()));
   if (!buf) return -100;
-  ctx->oz_tag_ptr = nullptr;
+  // the slices of A stay behind for a projection from the same block (armed by the solver: ortho_drop's U -= V (V^H B U), SVQB's U T)
+  ctx->oz_tag_ptr = A; ctx->oz_tag_n = n; ctx->oz_tag_m = ma; ctx->oz_tag_ld = lda; ctx->oz_tag_e_off = o_eA;
   OzOperand op[3] = {{A, lda, ma, buf, (int*)(buf + o_eA)},
                      {same ? nullptr : B, ldb, mb, same ? buf : buf + bytesA, same ? (int*)(buf + o_eA) : (int*)(buf + o_eB)},
                      {nullptr, 0, 0, nullptr, nullptr}};
@@ -1519,10 +1524,10 @@ int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, in
   return oz_run(ctx, n, tiles, op, nprod == 2 ? 3 : 2, G0, ldg0, G1, ldg1, 0, buf, o_rest, (unsigned long long*)(buf + o_mx));
 }
 
-// Out (n x nb) = S C (alpha = 1, beta = 0) on the int8 tensor path.  Uses the slices of S left by the last gram_cols_i8_f64 on the
+// Out (n x nb) = alpha S C + beta Out on the int8 tensor path.  Uses the slices of S left by the last gram_cols_i8_f64 on the
 // same block (the solver's pass: Gram, then X = S Cx and P = S Cp); splits S itself otherwise.  -100 = not available.
-int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int64_t lds, const double* C, int ldc, double* Out,
-                   int64_t ldo) {
+int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, double alpha, const double* S, int64_t lds, const double* C, int ldc,
+                   double beta, double* Out, int64_t ldo) {
   if (n >= ((int64_t)1 << 31) * OZ_CH || !oz_encode_tiled()) return -100;
   const int64_t nch = (n + OZ_CH - 1) / OZ_CH;
   auto al = [](size_t v) { return (v + 1023) / 1024 * 1024; };
@@ -1556,7 +1561,7 @@ int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int
   const int ncoh = (int)std::max<int64_t>(1, std::min<int64_t>(nch, ctx->sm_count / njt));
   LB2_CUDA_OK(cudaFuncSetAttribute(oz_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ON_SMEM));
   oz_nn_kernel<<<ncoh * njt, OZ_NT, ON_SMEM, ctx->stream>>>(tmS, tmC, f, Out, ldo, n, nb, nkc, nch, njt, ncoh, oz_flag(ctx),
-                                                            ctx->oz_prefetch > 0 ? ctx->oz_prefetch : 0);
+                                                            ctx->oz_prefetch > 0 ? ctx->oz_prefetch : 0, alpha, beta);
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1660,6 +1665,11 @@ int oz_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int nworkers,
     stats[3] = (double)nused;
   }
   return 0;
+}
+
+// are the slices of this block the ones the last Gram left behind (and has the solver vouched that the block is unchanged)?
+bool oz_slices_cached(const lb2_ctx* ctx, const void* S, int64_t n, int kd, int64_t lds) {
+  return ctx->oz_reuse && ctx->oz_buf && ctx->oz_tag_ptr == S && ctx->oz_tag_n == n && ctx->oz_tag_m == kd && ctx->oz_tag_ld == lds;
 }
 
 // accumulated device times (ms) of the int8 Gram phases since the last query: out = {split, MMA kernel, reduce, calls}

@@ -35,9 +35,10 @@ int gram_i8_f64(lb2_ctx* ctx, int64_t n, int ma, int mb, const double* A, int64_
                 int ldg, int upper);
 int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, int64_t lds, const double* W0, int64_t ldw0, double* G0,
                      int ldg0, const double* W1, int64_t ldw1, double* G1, int ldg1, int tri_c0);
-// Out = S C (alpha = 1, beta = 0) on the same slices, S read as an MN-major int8 operand; -100 = not available
-int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, const double* S, int64_t lds, const double* C, int ldc, double* Out,
-                   int64_t ldo);
+// Out = alpha S C + beta Out on the same slices, S read as an MN-major int8 operand; -100 = not available
+int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, double alpha, const double* S, int64_t lds, const double* C, int ldc,
+                   double beta, double* Out, int64_t ldo);
+bool oz_slices_cached(const lb2_ctx* ctx, const void* S, int64_t n, int kd, int64_t lds);
 int oz_plan_check(int m, int nw, int nprod, int tri_c0, int64_t n, int nworkers, int mode, double* stats);   // host-only schedule check
 int oz_stats_query(lb2_ctx* ctx, double* out);   // {split ms, MMA kernel ms, reduce ms, calls} of the int8 Gram since the last query
 // gram_tc5.cu: float Gram on tcgen05 (kind::tf32, 3xTF32 split, accumulator in TMEM); -100 = alignment not met

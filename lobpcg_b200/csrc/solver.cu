@@ -914,6 +914,7 @@ int Solver<T>::svqb(T* U, int nu, R tau, bool drop, int* nret) {
   } else {
     LB2_TRY(gram_ar(nu, nu, U, U, G, 1));
   }
+  const bool reuse_u = true;   // int8 path: U is unchanged until U T below has been formed — the slices of this Gram serve it
   tm.begin(PH_SMALL);
   LB2_TRY(sd_dscale<T>(ctx, nu, G, nu, D));
   int info = 0;
@@ -930,7 +931,9 @@ int Solver<T>::svqb(T* U, int nu, R tau, bool drop, int* nret) {
   const int keep = *(int*)hbuf;
   T* out = wB ? wB : slab[1 - cur];   // (no scratch block: the other slab is dead while W is orthogonalised)
   if (out == U || (U > out && U < out + (int64_t)keep * n)) { fprintf(stderr, "lobpcg_b200: svqb workspace aliases its operand\n"); return -1; }
+  ctx->oz_reuse = reuse_u;
   LB2_TRY(nn(nu, keep, make<T>(1), U, Tmp, nu, zero<T>(), out));
+  ctx->oz_reuse = false;
   tm.begin(PH_OTHER);
   LB2_TRY(copy_block<T>(ctx, n, keep, out, n, U, n));
   tm.end();
@@ -985,12 +988,14 @@ int Solver<T>::ortho_drop(T* U, int nu0, T* V, int nv, int* nret, bool indefinit
     const T* BU = U;
     if (opB) { LB2_TRY(apply(opB, nu, U, wA)); BU = wA; }
     LB2_TRY(gram_ar(nv, nu, V, BU, Tmp, 0));
+    ctx->oz_reuse = true;    // int8 path: V is unchanged between this product and the update below — its slices serve both
     if (indefinite) {  // U -= V (sig (V^H B U))   (ortho_indefinite_impl.inc:121-133)
       LB2_TRY(sd_gemm<T>(ctx, 'N', nv, nu, nv, GA, nv, Tmp, nv, Z, nv));
       LB2_TRY(nn(nv, nu, make<T>(-1), V, Z, nv, make<T>(1), U));
     } else {
       LB2_TRY(nn(nv, nu, make<T>(-1), V, Tmp, nv, make<T>(1), U));
     }
+    ctx->oz_reuse = false;
     for (int inner = 0; inner < 3; inner++) {
       int keep = nu;
       LB2_TRY(svqb(U, nu, eps, true, &keep));

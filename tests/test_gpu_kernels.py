@@ -670,6 +670,31 @@ def test_tall_nn_i8_matches_extended_precision(ctx, shape):
         ctx.set_option("gram_i8", 0)
 
 
+def test_tall_nn_i8_update_on_cached_slices(ctx):
+    """U <- U - V (V^H U) the way ortho_drop does it on the int8 path: the rectangular Gram V^H U leaves the slices of V behind,
+    the solver vouches that V is unchanged (oz_reuse) and the update Out = alpha V C + beta Out reads them (no second split)."""
+    rng = np.random.default_rng(9)
+    n, nv, nu = 30000, 200, 70
+    V = np.linalg.qr(rng.standard_normal((n, nv)))[0]
+    U = rng.standard_normal((n, nu))
+    dV, dU = api.DeviceArray.from_numpy(ctx, np.asfortranarray(V)), api.DeviceArray.from_numpy(ctx, np.asfortranarray(U))
+    ctx.set_option("gram_i8", 1)
+    try:
+        Cm = api.gram(ctx, dV, dU)                                   # V^H U, slices of V stay behind
+        ctx.set_option("oz_reuse", 1)
+        l0 = ctx.launches
+        api.tall_nn(ctx, dV, Cm, dU, alpha=-1.0, beta=1.0)
+        launches = ctx.launches - l0
+        ctx.set_option("oz_reuse", 0)
+        got = dU.numpy(ctx)
+        ref = U - V @ (V.T @ U)
+        assert np.abs(got - ref).max() < 1e-13 * np.abs(U).max()
+        assert np.abs(V.T @ got).max() < 1e-12
+        assert launches == 2                                          # slices of the small matrix + the projection kernel: no split of V
+    finally:
+        ctx.set_option("gram_i8", 0); ctx.set_option("oz_reuse", 0)
+
+
 def test_gram_cols_i8_exponent_hints(ctx):
     """The solver's column-block Gram carries the column exponents from call to call (the split then collects the maxima itself
     instead of a separate pass).  A column that grew past the guard bit or shrank by more than 4 bits must trigger a fresh
