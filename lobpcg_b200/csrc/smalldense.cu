@@ -128,9 +128,11 @@ int sd_qr_q(lb2_ctx* ctx, int rows, int cols, T* A, int lda, T* tau) {
   LB2_SOLVER_OK(orgqr_bs(ctx->cusolver, rows, cols, cols, A, lda, tau, &lw));
   const size_t need = wd > sizeof(T) * (size_t)lw ? wd : sizeof(T) * (size_t)lw;
   if (ensure_ws(ctx, need, wh)) return -1;
+  // both steps report through their own info word (the reference checks geqrf / orgqr, rayleigh_ritz_modified_impl.inc:233-246);
+  // they are read together with the next host synchronisation of the caller (sd_qr_info)
   LB2_SOLVER_OK(cusolverDnXgeqrf(ctx->cusolver, g_params, rows, cols, CudaType<T>::v, A, lda, CudaType<T>::v, tau,
-                                 CudaType<T>::v, ctx->solver_ws, wd, ctx->solver_hws, wh, ctx->dev_info));
-  LB2_SOLVER_OK(orgqr_run(ctx->cusolver, rows, cols, cols, A, lda, tau, (T*)ctx->solver_ws, lw, ctx->dev_info));
+                                 CudaType<T>::v, ctx->solver_ws, wd, ctx->solver_hws, wh, ctx->dev_info + 2));
+  LB2_SOLVER_OK(orgqr_run(ctx->cusolver, rows, cols, cols, A, lda, tau, (T*)ctx->solver_ws, lw, ctx->dev_info + 3));
   ctx->launches += 2;
   return 0;
 }

@@ -338,7 +338,20 @@ class Solver : public SolverBase {
 
   void release();
   int alloc();
-  int sync() { LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); tm.collect(phase_ms); return 0; }
+  int qr_info_pending = 0;   // cp_from_z: the info words of geqrf / orgqr travel with the next host synchronisation
+  int sync() {
+    LB2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    tm.collect(phase_ms);
+    if (qr_info_pending) {
+      qr_info_pending = 0;
+      const int* qi = reinterpret_cast<const int*>(hbuf + 4 * (size_t)k + 60);
+      if (qi[0] != 0 || qi[1] != 0) {
+        fprintf(stderr, "rayleigh_ritz_modified: QR of the P basis failed (geqrf info=%d, orgqr info=%d)\n", qi[0], qi[1]);
+        return -1;
+      }
+    }
+    return 0;
+  }
   int d2h(void* dst, const void* src, size_t bytes) {
     LB2_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
@@ -752,6 +765,10 @@ int Solver<T>::cp_from_z(int m, const T* Zm, T* VQ) {
   const int nrem = m - k;
   LB2_TRY(sd_transpose<T>(ctx, nrem, k, Zm + (size_t)k * m, m, Q, nrem));
   LB2_TRY(sd_qr_q<T>(ctx, nrem, k, Q, nrem, Tau));
+  if (ctx->dev_info && hbuf) {   // read with the next host synchronisation (Solver::sync)
+    LB2_CUDA_OK(cudaMemcpyAsync(hbuf + 4 * (size_t)k + 60, ctx->dev_info + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    qr_info_pending = 1;
+  }
   LB2_TRY(sd_gemm<T>(ctx, 'N', m, k, nrem, Zm + (size_t)k * m, m, Q, nrem, VQ, m));
   return 0;
 }
