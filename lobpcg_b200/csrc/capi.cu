@@ -308,6 +308,8 @@ int lb2_ctx_set_option(lb2_ctx* c, const char* key, int value) {
   else if (!strcmp(key, "oz_lockstep")) c->oz_lockstep = value;
   else if (!strcmp(key, "oz_prefetch")) c->oz_prefetch = value;
   else if (!strcmp(key, "oz_hints")) c->oz_hints = value;
+  else if (!strcmp(key, "oz_ring")) c->oz_ring = value;
+  else if (!strcmp(key, "oz_nn_ring")) c->oz_nn_ring = value;
   else if (!strcmp(key, "oz_reuse")) c->oz_reuse = value != 0;   // what the solver sets between a Gram and the projections from the same block (tests)
   else if (!strcmp(key, "nn_i8")) c->nn_i8 = value;
   else if (!strcmp(key, "oz_clusters")) c->oz_clusters = value;

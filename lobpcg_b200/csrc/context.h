@@ -66,6 +66,8 @@ struct lb2_ctx {
   int gram_i8 = -1;      // f64 Gram / projection on tcgen05 kind::i8 through an Ozaki split (gram_i8.cu): -1 = auto (on for n >= 2^18 rows), 1 = on (n >= 4096), 0 = DMMA kernels, 2 = on + phase times on stderr
   int gram_i8_env = -1;  // LB2_GRAM_I8 as seen by the last solver set-up (-1 = unset); overrides gram_i8 for the drop-in entry points
   int nn_i8 = 1;         // with gram_i8 on: projections Out = S C (alpha 1, beta 0) on the int8 tensor path too (0 = DMMA kernel)
+  int oz_ring = 0;       // cluster Gram kernel: A-ring slots (3 / 4 / 5 / 6 of 12; 0 = 4)
+  int oz_nn_ring = 0;    // int8 projection kernel: A-ring slots (5 / 6 / 7 / 8; 0 = 7)
   int oz_prefetch = 0;   // int8 kernels: L2 prefetch distance of the slice tiles in chunks (0 = off: measured slower at every distance, r02)
   int oz_lockstep = 1;   // gram_i8 one-tile-per-CTA kernel: 1 = lock-step cohorts (every (tile, level group) has its own CTAs), 0 = equal-cost cut
   int oz_cluster = 1;    // gram_i8 column-block products: 1 = 4-CTA clusters with multicast slice tiles (r02, C5 shape: 71 ms against 78 ms of the one-tile-per-CTA kernel), 0 = one tile per CTA

@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(OZ_NT, 1)
 // (a 64-column box) and the TMA unit MULTICASTS the box into both CTAs' shared memory (UTMALDG.MULTICAST), so a CTA pulls
 // half the bytes through L2 for the same MMAs.  A ring slot is refilled only when BOTH consumers have released it: the slot's
 // "empty" mbarrier counts two arrivals and tcgen05.commit.multicast delivers each consumer's arrival to both CTAs.
-constexpr int OZ_NA = 4, OZ_NB = 8;   // ring slots of the A / B slice tiles (B slots first in shared memory)
+// ring slots of the A / B slice tiles (B slots first in shared memory): template parameters NA + NB = 12 (option oz_ring)
 
 struct OzCItem {
   int32_t chunk_begin, chunk_end, group, pad;
@@ -489,7 +489,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 struct OzRing { uint32_t slot, par; };
 
-template <int AMIN, int SMIN, int LMIN, int LMAX>
+template <int AMIN, int SMIN, int LMIN, int LMAX, int OZ_NA, int OZ_NB>
 __device__ __forceinline__ void oz_mma_chunk_c(uint32_t sbase, uint32_t fullA, uint32_t emptyA, uint32_t fullB, uint32_t emptyB,
                                                uint32_t tmem, uint32_t idesc, OzRing& ra, OzRing& rb, uint32_t& level_init,
                                                uint16_t maskA, uint16_t maskB) {
@@ -531,6 +531,7 @@ __device__ __forceinline__ void oz_mma_chunk_c(uint32_t sbase, uint32_t fullA, u
   }
 }
 
+template <int OZ_NA, int OZ_NB>
 __global__ void __launch_bounds__(OZ_NT, 1)
     oz_gram_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                            const __grid_constant__ CUtensorMap tmB1, const OzCItem* __restrict__ items,
@@ -612,10 +613,10 @@ __global__ void __launch_bounds__(OZ_NT, 1)
           uint32_t level_init = 0;
           if (im.group) {
             for (int chunk = seg0; chunk < seg1; ++chunk)
-              oz_mma_chunk_c<0, 0, 6, 8>(sbase, fullA, emptyA, fullB, emptyB, tmem, idesc, rga, rgb, level_init, maskA, maskB);
+              oz_mma_chunk_c<0, 0, 6, 8, OZ_NA, OZ_NB>(sbase, fullA, emptyA, fullB, emptyB, tmem, idesc, rga, rgb, level_init, maskA, maskB);
           } else {
             for (int chunk = seg0; chunk < seg1; ++chunk)
-              oz_mma_chunk_c<3, 3, 9, 12>(sbase, fullA, emptyA, fullB, emptyB, tmem, idesc, rga, rgb, level_init, maskA, maskB);
+              oz_mma_chunk_c<3, 3, 9, 12, OZ_NA, OZ_NB>(sbase, fullA, emptyA, fullB, emptyB, tmem, idesc, rga, rgb, level_init, maskA, maskB);
           }
           umma_commit(bar_accf);
         }
@@ -675,9 +676,9 @@ __global__ void __launch_bounds__(OZ_NT, 1)
 // A CTA owns row chunks and a 64-column output tile: 7 level accumulators x 64 columns fit TMEM (448 of 512 columns), so all
 // 28 slice products of a K chunk run in one pass (tile order B0 .. B6 A6 A5 ... A0, A_a x B_j for j >= 6 - a).  The CTAs that
 // share a row chunk (one per output tile) form a lock-step cohort: the slices of S come from DRAM once and from L2 for the rest.
-constexpr int ON_NA = 7, ON_NB = 10;                    // ring slots: A tiles 16 KB, B tiles 8 KB (B slots first)
+// ring slots: A tiles 16 KB, B tiles 8 KB (B slots first): template parameters ON_NA, ON_NB with 16 NA + 8 NB = 192 KB, NB >= 8
 constexpr uint32_t ON_BT = OZ_TILE / 2;                 // B tile: 64 output columns x 128 B of k
-constexpr uint32_t ON_BAR = ON_NB * ON_BT + ON_NA * OZ_TILE;
+constexpr uint32_t ON_BAR = 12 * OZ_TILE;                 // barriers behind the 192 KB of ring slots
 constexpr uint32_t ON_SMEM = ON_BAR + 1024 + 1024;
 constexpr int ON_TN = 64;
 
@@ -721,6 +722,7 @@ __device__ __forceinline__ uint32_t on_idesc(int n16) {   // as oz_idesc, A oper
   return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(n16 >> 3) << 17) | ((uint32_t)(OZ_T >> 4) << 24);
 }
 
+template <int ON_NA, int ON_NB>
 __global__ void __launch_bounds__(OZ_NT, 1)
     oz_nn_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmC, const int* __restrict__ f,
                  double* __restrict__ Out, int64_t ldo, int64_t n, int nb, int nkc, int64_t nch, int njt, int ncoh,
@@ -1235,8 +1237,8 @@ int oz_max_clusters(lb2_ctx* ctx) {
   at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int ncl = 0;
-  if (cudaFuncSetAttribute(oz_gram_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM) != cudaSuccess ||
-      cudaOccupancyMaxActiveClusters(&ncl, oz_gram_cluster_kernel, &cfg) != cudaSuccess)
+  if (cudaFuncSetAttribute(oz_gram_cluster_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&ncl, oz_gram_cluster_kernel<4, 8>, &cfg) != cudaSuccess)
     ncl = 0;
   cudaGetLastError();
   ctx->oz_clusters = ncl;
@@ -1411,9 +1413,19 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    LB2_CUDA_OK(cudaFuncSetAttribute(oz_gram_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
-    LB2_CUDA_OK(cudaLaunchKernelEx(&cfg, oz_gram_cluster_kernel, tm[0], tm[1], tm[2], (const OzCItem*)(buf + o_items),
-                                   (const int*)(buf + o_cl), part));
+#define LB2_OZC(NA, NB)                                                                                                        \
+  {                                                                                                                            \
+    LB2_CUDA_OK(cudaFuncSetAttribute(oz_gram_cluster_kernel<NA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM)); \
+    LB2_CUDA_OK(cudaLaunchKernelEx(&cfg, oz_gram_cluster_kernel<NA, NB>, tm[0], tm[1], tm[2], (const OzCItem*)(buf + o_items),     \
+                                   (const int*)(buf + o_cl), part));                                                              \
+  }
+    switch (ctx->oz_ring) {   // A-ring slots (tuning option); default 4 A + 8 B
+      case 3: LB2_OZC(3, 9) break;
+      case 5: LB2_OZC(5, 7) break;
+      case 6: LB2_OZC(6, 6) break;
+      default: LB2_OZC(4, 8) break;
+    }
+#undef LB2_OZC
   }
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
@@ -1559,9 +1571,20 @@ int tall_nn_i8_f64(lb2_ctx* ctx, int64_t n, int kd, int nb, double alpha, const 
   if (oz_make_map(&tmS, buf, kd, nch) || oz_make_map_c(&tmC, cs, nb, nkc)) return -100;
   const int njt = (nb + ON_TN - 1) / ON_TN;
   const int ncoh = (int)std::max<int64_t>(1, std::min<int64_t>(nch, ctx->sm_count / njt));
-  LB2_CUDA_OK(cudaFuncSetAttribute(oz_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ON_SMEM));
-  oz_nn_kernel<<<ncoh * njt, OZ_NT, ON_SMEM, ctx->stream>>>(tmS, tmC, f, Out, ldo, n, nb, nkc, nch, njt, ncoh, oz_flag(ctx),
-                                                            ctx->oz_prefetch > 0 ? ctx->oz_prefetch : 0, alpha, beta);
+#define LB2_OZN(NA, NB)                                                                                                   \
+  {                                                                                                                       \
+    LB2_CUDA_OK(cudaFuncSetAttribute(oz_nn_kernel<NA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ON_SMEM));   \
+    oz_nn_kernel<NA, NB><<<ncoh * njt, OZ_NT, ON_SMEM, ctx->stream>>>(tmS, tmC, f, Out, ldo, n, nb, nkc, nch, njt, ncoh,   \
+                                                                      oz_flag(ctx), ctx->oz_prefetch > 0 ? ctx->oz_prefetch : 0, \
+                                                                      alpha, beta);                                        \
+  }
+  switch (ctx->oz_nn_ring) {   // A-ring slots of the projection kernel (tuning option); default 7 A + 10 B
+    case 5: LB2_OZN(5, 14) break;
+    case 6: LB2_OZN(6, 12) break;
+    case 8: LB2_OZN(8, 8) break;
+    default: LB2_OZN(7, 10) break;
+  }
+#undef LB2_OZN
   ctx->launches++;
   LB2_CUDA_OK(cudaGetLastError());
   return 0;
