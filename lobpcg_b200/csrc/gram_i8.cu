@@ -1416,8 +1416,12 @@ int oz_run_cluster(lb2_ctx* ctx, int64_t n, std::vector<OzSuper>& supers, OzOper
 #define LB2_OZC(NA, NB)                                                                                                        \
   {                                                                                                                            \
     LB2_CUDA_OK(cudaFuncSetAttribute(oz_gram_cluster_kernel<NA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM)); \
-    LB2_CUDA_OK(cudaLaunchKernelEx(&cfg, oz_gram_cluster_kernel<NA, NB>, tm[0], tm[1], tm[2], (const OzCItem*)(buf + o_items),     \
-                                   (const int*)(buf + o_cl), part));                                                              \
+    if (cudaLaunchKernelEx(&cfg, oz_gram_cluster_kernel<NA, NB>, tm[0], tm[1], tm[2], (const OzCItem*)(buf + o_items),            \
+                           (const int*)(buf + o_cl), part) != cudaSuccess) {                                                      \
+      cudaGetLastError();                                                                                                       \
+      ctx->oz_clusters = 0;   /* cluster launches do not work here (e.g. a restricted device): one tile per CTA from now on */    \
+      return -101;                                                                                                              \
+    }                                                                                                                           \
   }
     switch (ctx->oz_ring) {   // A-ring slots (tuning option); default 4 A + 8 B
       case 3: LB2_OZC(3, 9) break;
@@ -1531,8 +1535,10 @@ int gram_cols_i8_f64(lb2_ctx* ctx, int64_t n, int m, int nw, const double* S, in
                      {w0_in_s ? nullptr : W0, ldw0, nw, w0_in_s ? buf : buf + bS, w0_in_s ? eS : (int*)(buf + o_e0), 1},
                      {nprod == 2 ? W1 : nullptr, ldw1, nw, buf + bS + bW0, (int*)(buf + o_e1), 2}};
   // the reduce kernel indexes the exponents with the tile's b_col0, which already carries tri_c0 for an aliased W0
-  if (!supers.empty())
-    return oz_run_cluster(ctx, n, supers, op, nprod == 2 ? 3 : 2, G0, ldg0, G1, ldg1, buf, o_rest, (unsigned long long*)(buf + o_mx), ncl_max);
+  if (!supers.empty()) {
+    const int rc = oz_run_cluster(ctx, n, supers, op, nprod == 2 ? 3 : 2, G0, ldg0, G1, ldg1, buf, o_rest, (unsigned long long*)(buf + o_mx), ncl_max);
+    if (rc != -101) return rc;   // -101: the cluster launch was refused — same product with the one-tile-per-CTA kernel
+  }
   return oz_run(ctx, n, tiles, op, nprod == 2 ? 3 : 2, G0, ldg0, G1, ldg1, 0, buf, o_rest, (unsigned long long*)(buf + o_mx));
 }
 
