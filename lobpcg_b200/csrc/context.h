@@ -63,7 +63,7 @@ struct lb2_ctx {
   void* hostcopy = nullptr;        // lb2::HostCopyState* (pinned ring for pageable host <-> device block transfers)
   void* gram_wl_cache = nullptr;   // lb2::WlCache* (schedules per Gram shape)
   void* gram_wl_cols_cache = nullptr;   // lb2::WlColsCache* (schedules of the column-block products, gram_wl_cols_f64)
-  int gram_i8 = -1;      // f64 Gram / projection on tcgen05 kind::i8 through an Ozaki split (gram_i8.cu): -1 = auto (on for n >= 2^18 rows), 1 = on (n >= 4096), 0 = DMMA kernels, 2 = on + phase times on stderr
+  int gram_i8 = -1;      // f64 Gram / projection on tcgen05 kind::i8 through an Ozaki split (gram_i8.cu): -1 = auto (on for n >= 2^18 rows and products of at least 200 x 200), 1 = on (n >= 4096), 0 = DMMA kernels, 2 = on + phase times on stderr
   int gram_i8_env = -1;  // LB2_GRAM_I8 as seen by the last solver set-up (-1 = unset); overrides gram_i8 for the drop-in entry points
   int nn_i8 = 1;         // with gram_i8 on: projections Out = S C (alpha 1, beta 0) on the int8 tensor path too (0 = DMMA kernel)
   int oz_ring = 0;       // cluster Gram kernel: A-ring slots (3 / 4 / 5 / 6 of 12; 0 = 4)
@@ -117,9 +117,11 @@ void hostcopy_set_threads(lb2_ctx* ctx, int nthreads);
 inline int lb2_gram_i8_mode(const lb2_ctx* c) { return c->gram_i8_env >= 0 ? c->gram_i8_env : c->gram_i8; }
 // does a product over n rows take the int8 path?  auto: only where the tall kernels dominate (the path has more launches and a
 // host-side schedule per call)
-inline bool lb2_gram_i8_on(const lb2_ctx* c, int64_t n) {
+// (ma x mb = shape of the small side of the product: the path pays where the product is bound by the tensor pipe; narrow blocks are
+// bound by HBM, and there the split's extra pass over the operands costs more than the faster MMAs return)
+inline bool lb2_gram_i8_on(const lb2_ctx* c, int64_t n, int64_t ma = 1 << 20, int64_t mb = 1) {
   const int mode = lb2_gram_i8_mode(c);
-  return mode > 0 ? n >= 4096 : (mode < 0 && n >= ((int64_t)1 << 18));
+  return mode > 0 ? n >= 4096 : (mode < 0 && n >= ((int64_t)1 << 18) && ma * mb >= 40000);
 }
 namespace lb2 {
 // device memory for the int8 slices; under pressure frees the cached arenas and the idle slice buffers of other contexts (capi.cu)

@@ -1240,10 +1240,11 @@ int gram(lb2_ctx* ctx, int64_t n, int ma, int mb, const T* A, int64_t lda, const
   }
   if constexpr (std::is_same<T, double>::value) {
     if (!ctx->force_simt) {
-      if (lb2_gram_i8_on(ctx, n)) {   // tcgen05 kind::i8 on an Ozaki split (gram_i8.cu)
+      if (lb2_gram_i8_on(ctx, n, ma, mb)) {   // tcgen05 kind::i8 on an Ozaki split (gram_i8.cu)
         const int rc = gram_i8_f64(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
         if (rc != -100) return rc;
       }
+      ctx->oz_tag_ptr = nullptr;   // this product leaves no slices behind: a projection that follows must not find older ones
       // work-list kernel (gram_wl.cu) for Hermitian products; forced for every shape with gram_wl = 1
       if (ctx->gram_wl == 1 || (ctx->gram_wl < 0 && ctx->gram_tile == 0 && upper && n >= 4096))
         return gram_wl_f64(ctx, n, ma, mb, A, lda, B, ldb, G, ldg, upper);
@@ -1274,10 +1275,11 @@ int gram_cols(lb2_ctx* ctx, int64_t n, int m, int nw, const T* S, int64_t lds, c
               int ldg0, const T* W1, int64_t ldw1, T* G1, int ldg1, int tri_c0) {
   if (m <= 0 || nw <= 0) return 0;
   if constexpr (std::is_same<T, double>::value) {
-    if (!ctx->force_simt && lb2_gram_i8_on(ctx, n)) {   // tcgen05 kind::i8 on an Ozaki split (gram_i8.cu)
+    if (!ctx->force_simt && lb2_gram_i8_on(ctx, n, m, nw)) {   // tcgen05 kind::i8 on an Ozaki split (gram_i8.cu)
       const int rc = gram_cols_i8_f64(ctx, n, m, nw, S, lds, W0, ldw0, G0, ldg0, W1, ldw1, G1, ldg1, tri_c0);
       if (rc != -100) return rc;
     }
+    ctx->oz_tag_ptr = nullptr;   // (see gram: no stale slices for the projections of this pass)
     if (!ctx->force_simt && ctx->gram_wl != 0 && ctx->gram_tile == 0 && n >= 4096)
       return gram_wl_cols_f64(ctx, n, m, nw, S, lds, W0, ldw0, G0, ldg0, W1, ldw1, G1, ldg1, tri_c0);
   }
@@ -1319,8 +1321,8 @@ int tall_nn(lb2_ctx* ctx, int64_t n, int kd, int nb, T alpha, const T* S, int64_
   if (n <= 0 || nb <= 0) return 0;
   if constexpr (std::is_same<T, double>::value) {
     // int8 tensor path (gram_i8.cu): plain products always; updates (alpha, beta general) when the slices of S are already there
-    if (!ctx->force_simt && kd > 0 && lb2_gram_i8_on(ctx, n) && ctx->nn_i8 != 0 &&
-        ((alpha == 1.0 && beta == 0.0) || oz_slices_cached(ctx, S, n, kd, lds))) {
+    if (!ctx->force_simt && kd > 0 && ctx->nn_i8 != 0 &&
+        ((alpha == 1.0 && beta == 0.0 && lb2_gram_i8_on(ctx, n, kd, nb)) || (lb2_gram_i8_on(ctx, n) && oz_slices_cached(ctx, S, n, kd, lds)))) {
       const int rc = tall_nn_i8_f64(ctx, n, kd, nb, alpha, S, lds, C, ldc, beta, Out, ldo);
       if (rc != -100) return rc;
     }
