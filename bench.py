@@ -130,6 +130,14 @@ def workload_desc(g, nev, k):
             f"double, tol=1e-8, B=T=NULL, X0 splitmix64 seed 7")
 
 
+def bench_config(g, nev, k, world):
+    """`config` of the JSON line: the SAME dict for both arms (the reference arm runs "on your arm's config"); what is
+    specific to one run (solver state, grid really timed by the reference arm) goes into separate keys of the line."""
+    n_local = g ** 3 // max(world, 1)
+    return {"workload": workload_desc(g, nev, k), "parallelism": f"rows in {world} z-slab(s)",
+            "l2": "inputs larger than L2 (each n x 3k slab is %.1f GB per GPU)" % (n_local * 3 * k * 8 / 1e9)}
+
+
 # ------------------------------------------------------------------------------------------------ CPU legs
 def mem_available_bytes():
     try:
@@ -238,17 +246,17 @@ def run_reference_arm(args):
               f"{'the full' if not extrapolated else 'a REDUCED'} {g_run}^3 grid (n={n_run}), nev={nev}, sizeSub={k}: {done} passes in "
               f"{t_run - t_init:.1f} s (set-up {t_init:.1f} s timed separately and excluded)"
               + (f"; iter/s EXTRAPOLATED to n={g ** 3} by n_run/n_full = {scale:.4f} because {why}" if extrapolated else ""))
-    wl = workload_desc(g, nev, k)
-    if extrapolated:
-        wl += f" — reference arm timed on {g_run}^3 (n={n_run}) and extrapolated"
+    cfg = bench_config(g, nev, k, max(args.gpus, 1))
+    if extrapolated:     # not the same configuration: say so where the two arms are compared
+        cfg["workload"] += f" — reference arm timed on {g_run}^3 (n={n_run}) and extrapolated"
     line = {
         "impl": "reference", "metric": "lobpcg_iters_per_s", "value": value, "unit": "iter/s",
         "n_gpus": args.gpus, "steps": done, "steps_requested": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 / value, "measured_ms_per_step": 1e3 * per_pass, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "extrapolated": extrapolated,
-        "config": {"workload": wl, "device": "host CPU", "grid_timed": g_run, "rows_timed": n_run,
-                   "passes_timed": done, "budget_s": budget,
-                   "calibration": f"{g_c}^3: {per_pass_c:.3f} s/pass, set-up {t_init_c:.2f} s"},
+        "config": cfg,
+        "reference_run": {"device": "host CPU", "grid_timed": g_run, "rows_timed": n_run, "passes_timed": done, "budget_s": budget,
+                          "calibration": f"{g_c}^3: {per_pass_c:.3f} s/pass, set-up {t_init_c:.2f} s"},
         "cpu_baseline": {"value": value, "unit": "iter/s", "cores": threads, "kind": "reference", "sample": sample,
                          "extrapolated": extrapolated},
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -573,9 +581,7 @@ def run_ours(args):
             "metric": "lobpcg_iters_per_s", "value": done / (ms * 1e-3), "unit": "iter/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / done, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_desc(g, nev, k), "parallelism": f"rows in {world} z-slab(s)",
-                       "l2": "inputs larger than L2 (each n x 3k slab is %.1f GB per GPU)" % (n_local * 3 * k * 8 / 1e9),
-                       "solver_state": prog},
+            "config": bench_config(g, nev, k, world), "solver_state": prog,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "time_to_solution": tts, "gpu_launches": int(launches),
             "clocks": clocks, "kernels": kernels, "hbm_peak_gbs": hbm, "hbm_peak_source": how_hbm,
             "windows": windows, "gram_cache": gram_cache_info,
